@@ -1,0 +1,221 @@
+/* bos_b200.h -- C ABI of the B200-native Gauss-Newton solver for 2D bearing-only SLAM.
+ *
+ * This is the drop-in boundary under the reference's C++ class surface
+ * (torchipeppo/prb-project-bearing-only-slam).  The reference has no FFI of its own: the
+ * entry points below are what a binding for `proj02::Solver` / `triangulate_landmarks`
+ * would call, and each cites the reference interface it replaces.  Plain pointers and
+ * sizes only; every call returns an int status (0 = ok); no exception crosses the
+ * boundary; a context owns its device memory and stream and is used from one host
+ * thread at a time.  There is NO CPU fallback: without a CUDA device every compute call
+ * fails with BOS_ERR_CUDA.
+ *
+ * Index conventions (bit-exact with the reference):
+ *   pose stix      = insertion order of State::add_pose            (framework/state.cpp:20-30)
+ *   landmark stix  = insertion order of State::add_landmark        (framework/state.cpp:32-41);
+ *                    after triangulate_landmarks that is ASCENDING landmark id
+ *                    (slam/triangulation.cpp:65-74)
+ *   delta layout   = [3*NP pose | 2*NL landmark]                   (framework/state.cpp:69-80)
+ *   pose on the wire = (x, y, c, s) with c = R(0,0), s = R(1,0) of the reference's
+ *                    Isometry2f (never re-orthonormalised, as in the reference)
+ * All floating point crosses the boundary as double whatever the compute precision.
+ */
+#ifndef BOS_B200_H
+#define BOS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BOS_API __attribute__((visibility("default")))
+#else
+#define BOS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bos_ctx bos_ctx;
+typedef struct bos_batch bos_batch;
+
+enum {
+    BOS_OK = 0,
+    BOS_ERR_INVALID = 1,   /* bad argument (null pointer, index out of range, self-loop ...) */
+    BOS_ERR_CUDA = 2,      /* CUDA runtime failure, or no device */
+    BOS_ERR_STATE = 3,     /* call order (e.g. step before upload_problem) */
+    BOS_ERR_NCCL = 4,      /* NCCL missing or failed */
+    BOS_ERR_NOMEM = 5
+};
+
+enum { BOS_PRECISION_F64 = 0, BOS_PRECISION_F32 = 1 };
+enum { BOS_SOLVER_AUTO = 0, BOS_SOLVER_DENSE_CHOLESKY = 1, BOS_SOLVER_PCG = 2 };
+
+typedef struct bos_options {
+    int device;               /* CUDA ordinal */
+    int precision;            /* BOS_PRECISION_* ; F64 is the 1e-9 parity path, F32 is the reference's own precision */
+    int solver;               /* BOS_SOLVER_* ; AUTO = dense Cholesky when 3*NP <= dense_max_dim, else PCG */
+    int dense_max_dim;        /* default 36000 */
+    double kernel_threshold;  /* slam/solver.cpp:16  default 1.0  */
+    double damping;           /* slam/solver.cpp:17  default 0.01 */
+    int pcg_max_iters;        /* default 5000 */
+    double pcg_rtol;          /* stop when sqrt(r^T M^-1 r) <= rtol * its initial value; default 1e-10 */
+    int reserved[8];
+} bos_options;
+
+/* Per-iteration outputs.  The reference prints none of these; chi2 is defined as the sum of the
+ * per-edge error_omeganorm it already computes BEFORE the robust scaling (slam/solver.cpp:38,55). */
+typedef struct bos_stats {
+    double chi2_bearing;
+    double chi2_odometry;
+    int64_t over_bearing;     /* edges whose error_omeganorm exceeded kernel_threshold */
+    int64_t over_odometry;
+    double delta_inf;         /* max |dx| */
+    int solver_status;        /* 0 ok, 1 = non-positive pivot (the reference's "not SPD" console message, solver.cpp:82-84) */
+    int solver_used;          /* BOS_SOLVER_DENSE_CHOLESKY or BOS_SOLVER_PCG */
+    int pcg_iterations;
+    int gpu_launches;         /* kernels launched by the last step() */
+    float ms_linearize;       /* CUDA-event times of the last step(), on the context's stream */
+    float ms_solve;
+    float ms_update;
+    float ms_allreduce;
+} bos_stats;
+
+BOS_API void bos_default_options(bos_options* o);
+BOS_API int bos_version(void);
+
+/* Solver::Solver (slam/solver.cpp:5-18): create a context; problem and state are uploaded separately. */
+BOS_API int bos_create(const bos_options* opts, bos_ctx** out);
+BOS_API int bos_destroy(bos_ctx* ctx);
+BOS_API const char* bos_last_error(const bos_ctx* ctx);
+
+/* Solver::set_kernel_threshold / set_damping_factor (slam/solver.cpp:20-25). */
+BOS_API int bos_set_kernel_threshold(bos_ctx* ctx, double kt);
+BOS_API int bos_set_damping_factor(bos_ctx* ctx, double df);
+
+/* The edge vectors + construct_the_permutation (slam/solver.cpp:5-18, 99-125).  Edges arrive with
+ * ids already resolved to stix (the reference resolves them per edge per iteration through
+ * std::map::at, framework/state.cpp:43-63).  Host buffers are borrowed for the call and copied.
+ * b_omega may be NULL (= 1, framework/observation.hpp:17).  o_z is [Eo][3]; o_omega is [Eo][9]
+ * row-major, assumed symmetric as utils/g2o_utils.cpp:91-106 builds it.
+ * Builds the CSR-of-blocks sparsity pattern and the per-edge block slots. */
+BOS_API int bos_upload_problem(bos_ctx* ctx, int NP, int NL, int fixed_pose_stix,
+                       int64_t Eb, const int32_t* b_pose, const int32_t* b_lm, const double* b_z, const double* b_omega,
+                       int64_t Eo, const int32_t* o_src, const int32_t* o_dst, const double* o_z, const double* o_omega);
+
+/* Solver::state (slam/solver.hpp:26). poses [NP][4] = x,y,c,s ; lms [NL][2].  Either may be NULL. */
+BOS_API int bos_set_state(bos_ctx* ctx, const double* poses_xycs, const double* lms_xy);
+BOS_API int bos_get_state(bos_ctx* ctx, double* poses_xycs, double* lms_xy);
+
+/* The three phases of Solver::step (slam/solver.cpp:27-97), callable one by one for parity tests:
+ *   linearize : lines 28-69  (errors, Jacobians, robust kernel, H/b accumulation, damping)
+ *   solve     : lines 72-94  (gauge fix, factorise, solve, re-expand dx)
+ *   update    : line  96     (State::apply_boxplus, framework/state.cpp:69-80) */
+BOS_API int bos_linearize(bos_ctx* ctx);
+BOS_API int bos_solve(bos_ctx* ctx);
+BOS_API int bos_update(bos_ctx* ctx);
+
+/* Solver::step(): exactly one GN iteration including the state update, state resident on the device. */
+BOS_API int bos_step(bos_ctx* ctx, bos_stats* stats);
+/* Same, through HOST buffers: uploads the state, steps, downloads the new state (the reference's
+ * callers read solver.state after every step, executables/bearing_only_slam.cpp:31-36). */
+BOS_API int bos_step_host(bos_ctx* ctx, double* poses_xycs_inout, double* lms_xy_inout, bos_stats* stats);
+BOS_API int bos_get_stats(bos_ctx* ctx, bos_stats* stats);
+
+/* triangulate_landmarks (slam/triangulation.cpp:5-74) on the uploaded bearing edges and the current
+ * poses; writes all NL landmarks of the device state.  single_obs_count (may be NULL) receives the
+ * number of landmarks with exactly one observation (the reference's console warning, :38-42). */
+BOS_API int bos_triangulate(bos_ctx* ctx, int* single_obs_count);
+
+/* ---- parity / inspection (tests and the harness; not on the hot path) ------------------------ */
+typedef struct bos_pattern_info {
+    int64_t n_hpl;        /* unique (pose, landmark) blocks, 3x2 */
+    int64_t n_hpp_off;    /* unique pose-pose off-diagonal blocks, 3x3, stored as H[lo][hi] */
+    int64_t csc_n;        /* N - 3 */
+    int64_t csc_nnz;      /* scalar nnz of H_nofixed, both triangles (what SimplicialLDLT is handed) */
+    int64_t N;
+    int64_t vals_len;     /* scalars in the reducible value buffer */
+} bos_pattern_info;
+BOS_API int bos_pattern_info_get(bos_ctx* ctx, bos_pattern_info* out);
+/* Block coordinates, sorted: hpl_pose/hpl_lm [n_hpl]; off_lo/off_hi [n_hpp_off]; per-edge slots. */
+BOS_API int bos_download_pattern(bos_ctx* ctx, int32_t* hpl_pose, int32_t* hpl_lm, int32_t* off_lo, int32_t* off_hi,
+                         int64_t* b_slot, int64_t* o_slot);
+/* Block values after linearize: Hpp [NP][9], Hll [NL][4], Hpl [n_hpl][6], Hoff [n_hpp_off][9], b [N]. Any may be NULL. */
+BOS_API int bos_download_blocks(bos_ctx* ctx, double* Hpp, double* Hll, double* Hpl, double* Hoff, double* b);
+/* H_nofixed as scalar CSC (sorted rows, both triangles) and b_nofixed: slam/solver.cpp:72-75. */
+BOS_API int bos_download_csc(bos_ctx* ctx, int32_t* colptr, int32_t* rowidx, double* val, double* b_nofixed);
+BOS_API int bos_download_delta(bos_ctx* ctx, double* delta);
+BOS_API int bos_upload_delta(bos_ctx* ctx, const double* delta);
+/* Per-edge error (before the robust scaling) and Jacobian in the caller's edge order:
+ * err_b [Eb], jac_b [Eb][5] = [J_pose | J_lm]; err_o [Eo][3], jac_o [Eo][18] = 3x6 row-major [J_src | J_dst]. */
+BOS_API int bos_edge_terms(bos_ctx* ctx, double* err_b, double* jac_b, double* err_o, double* jac_o);
+
+/* Host-only view of the pattern builder (integer work, no device needed): what bos_upload_problem builds,
+ * exposed so the sparsity pattern, edge-to-block indexing and sharding can be checked bit-exactly anywhere. */
+typedef struct bos_host_pattern bos_host_pattern;
+BOS_API int bos_host_pattern_create(int NP, int NL, int fixed_pose_stix, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm,
+                            int64_t Eo, const int32_t* o_src, const int32_t* o_dst, bos_host_pattern** out);
+BOS_API int bos_host_pattern_destroy(bos_host_pattern* p);
+BOS_API int bos_host_pattern_info(const bos_host_pattern* p, bos_pattern_info* out);
+BOS_API int bos_host_pattern_get(const bos_host_pattern* p, int32_t* hpl_pose, int32_t* hpl_lm, int32_t* off_lo, int32_t* off_hi,
+                         int64_t* b_slot, int64_t* o_slot, int32_t* csc_colptr, int32_t* csc_rowidx);
+/* The contiguous edge ranges rank `rank` of `nranks` linearizes: out4 = b_begin, b_end, o_begin, o_end. */
+BOS_API int bos_host_edge_shard(int64_t Eb, int64_t Eo, int rank, int nranks, int64_t* out4);
+
+/* ---- multi-GPU: edge-sharded linearization, partials combined by an NCCL allreduce ------------ */
+#define BOS_NCCL_UID_BYTES 128
+BOS_API int bos_nccl_unique_id(char* uid128);
+BOS_API int bos_comm_init(bos_ctx* ctx, int rank, int nranks, const char* uid128);
+/* reduce_mode 0: allreduce the whole value buffer (H, b); 1: allreduce only the blocks that can overlap
+ * between ranks (b, diagonal blocks, pose-pose blocks) and allgather the rank-owned pose-landmark blocks. */
+BOS_API int bos_set_reduce_mode(bos_ctx* ctx, int reduce_mode);
+/* Without NCCL: shard bookkeeping only (used by the host-side tests): this rank linearizes its
+ * contiguous range of the pose-sorted edges. */
+BOS_API int bos_set_edge_shard(bos_ctx* ctx, int rank, int nranks);
+BOS_API int bos_get_edge_shard(bos_ctx* ctx, int64_t* b_begin, int64_t* b_end, int64_t* o_begin, int64_t* o_end);
+
+/* ---- batched small problems: one GN iteration per problem per launch ------------------------- */
+/* nprob problems sharing one topology (stix arrays, omegas, fixed pose); measurements and states are
+ * per problem: b_z [nprob][Eb], o_z [nprob][Eo][3]. */
+BOS_API int bos_batch_create(const bos_options* opts, int nprob, int NP, int NL, int fixed_pose_stix,
+                     int Eb, const int32_t* b_pose, const int32_t* b_lm, const double* b_z, const double* b_omega,
+                     int Eo, const int32_t* o_src, const int32_t* o_dst, const double* o_z, const double* o_omega,
+                     bos_batch** out);
+BOS_API int bos_batch_destroy(bos_batch* b);
+BOS_API int bos_batch_set_states(bos_batch* b, const double* poses_xycs, const double* lms_xy); /* [nprob][NP][4], [nprob][NL][2] */
+BOS_API int bos_batch_get_states(bos_batch* b, double* poses_xycs, double* lms_xy);
+/* chi2 [nprob][2] (bearing, odometry), delta_inf [nprob], status [nprob]; any may be NULL. */
+BOS_API int bos_batch_step(bos_batch* b, double* chi2, double* delta_inf, int32_t* status);
+/* Steps resident on the device without reading results back; elapsed_ms (may be NULL) is the
+ * CUDA-event time of the n_steps launches. */
+BOS_API int bos_batch_step_device(bos_batch* b, int n_steps, float* elapsed_ms);
+BOS_API const char* bos_batch_last_error(const bos_batch* b);
+
+/* ---- synthetic bearing-only worlds (bench / tests input generator; host code) ----------------- */
+typedef struct bos_synth_spec {
+    int n_poses;
+    int n_landmarks;
+    int64_t target_bearing_edges;   /* sensor range is tuned to approach this count */
+    uint64_t seed;
+    double bearing_sigma;           /* default 3e-3 rad */
+    double odom_sigma_xy;           /* default 1/sqrt(500) */
+    double odom_sigma_theta;        /* default 1/sqrt(5000) */
+    double init_drift;              /* amplitude (m) of the smooth drift applied to the ground truth for the initial guess */
+    double init_noise;              /* white noise (m, rad/10) on the initial guess */
+    int reserved[8];
+} bos_synth_spec;
+typedef struct bos_synth bos_synth;
+BOS_API void bos_synth_default_spec(bos_synth_spec* s);
+BOS_API int bos_synth_create(const bos_synth_spec* spec, bos_synth** out);
+BOS_API int bos_synth_destroy(bos_synth* w);
+/* counts[0..3] = NP, NL, Eb, Eo */
+BOS_API int bos_synth_counts(const bos_synth* w, int64_t* counts4);
+/* ids and values of the generated world; every pointer may be NULL.  Values are rounded to float and
+ * widened, as the g2o loader does (utils/g2o_utils.cpp: std::stof). */
+BOS_API int bos_synth_get(const bos_synth* w, int32_t* pose_ids, double* poses_xyt_init, double* poses_xyt_true,
+                  int32_t* lm_ids, double* lms_xy_true,
+                  int32_t* b_pose_id, int32_t* b_lm_id, double* b_z,
+                  int32_t* o_src_id, int32_t* o_dst_id, double* o_z, double* o_omega);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOS_B200_H */

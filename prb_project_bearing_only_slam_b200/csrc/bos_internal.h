@@ -1,0 +1,156 @@
+// bos_internal.h -- shared declarations of the CUDA product library (not part of the C ABI).
+#pragma once
+
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+namespace bos {
+
+// Typed view of everything a kernel needs.  One instance per context, built after upload.
+template <typename S>
+struct Dev {
+    int NP = 0, NL = 0, fixed = 0, Eb = 0, Eo = 0, N = 0;
+    int n_hpl = 0, n_off = 0;
+    // bearing edges, sorted by (pose, landmark); SoA
+    const int* b_pose = nullptr;
+    const int* b_lm = nullptr;
+    const S* b_z = nullptr;
+    const S* b_om = nullptr;
+    const int* b_slot = nullptr;  // null => slot == sorted edge index (no duplicate (pose, lm) pairs)
+    const int* b_perm = nullptr;  // sorted index -> caller's edge index
+    // odometry edges, caller order; o_z = [3][Eo], o_om = [6][Eo] (00 01 02 11 12 22)
+    const int* o_src = nullptr;
+    const int* o_dst = nullptr;
+    const S* o_z = nullptr;
+    const S* o_om = nullptr;
+    const int* o_slot = nullptr;
+    // CSR-of-blocks pattern
+    const int* slot_pose = nullptr;  // [n_hpl]
+    const int* slot_lm = nullptr;    // [n_hpl]
+    const int* pose_ptr = nullptr;   // [NP+1] into the (pose, lm)-sorted Hpl slots
+    const int* lm_ptr = nullptr;     // [NL+1] into lm_order
+    const int* lm_order = nullptr;   // [n_hpl] slot indices sorted by (lm, pose)
+    const int* lm_order_pose = nullptr;  // [n_hpl] pose of lm_order[k]
+    const int* lm_order_lm = nullptr;    // [n_hpl] landmark of lm_order[k]
+    const int* pp_ptr = nullptr;     // [NP+1] pose-pose adjacency
+    const int* pp_nbr = nullptr;     // [2*n_off] neighbour pose
+    const int* pp_slot = nullptr;    // [2*n_off] slot; bit 31 set when this pose is the 'hi' side (use the transpose)
+    const int* off_lo = nullptr;     // [n_off] block row pose of Hoff[k]
+    const int* off_hi = nullptr;     // [n_off] block column pose
+    const int* tri_ptr = nullptr;    // [NL+1] bearing edges grouped by landmark (caller order inside a landmark)
+    const int* tri_edge = nullptr;   // [Eb] sorted-edge index
+    // state
+    S* pose = nullptr;  // [NP][4] x,y,c,s
+    S* lm = nullptr;    // [NL][2]
+    // value buffer  [ b (N) | Hpp (6 NP) | Hll (3 NL) | Hoff (9 n_off) | Hpl (6 n_hpl) ]
+    S* vals = nullptr;
+    S* b = nullptr;
+    S* Hpp = nullptr;   // xx xy xt yy yt tt
+    S* Hll = nullptr;   // xx xy yy
+    S* Hoff = nullptr;  // 3x3 row-major, block H[lo][hi]
+    S* Hpl = nullptr;   // 3x2 row-major
+    double* stats = nullptr;  // [8] chi2_b, chi2_o, over_b, over_o, delta_inf(bits), status, -, -
+    S* delta = nullptr;       // [N]
+};
+
+struct ShardRange {
+    int b_begin = 0, b_end = 0, o_begin = 0, o_end = 0;
+};
+
+// ---- launchers (one translation unit each) -------------------------------------------------------
+template <typename S>
+int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping_here,
+                     bool zero_hpl, int sm_count, cudaStream_t st);
+template <typename S>
+int launch_edge_terms(const Dev<S>& d, S* err_b, S* jac_b, S* err_o, S* jac_o, cudaStream_t st);
+template <typename S>
+int launch_update(const Dev<S>& d, cudaStream_t st);
+template <typename S>
+int launch_triangulate(const Dev<S>& d, int* single_obs_count_dev, cudaStream_t st);
+
+// dense path
+template <typename S>
+struct DenseWork {
+    S* Smat = nullptr;      // [n][n] lower triangle used, column-major (ld = n)
+    S* g = nullptr;         // [n] reduced rhs / solution
+    S* hllinv = nullptr;    // [NL][3]
+    S* ul = nullptr;        // [NL][2]
+    S* tl = nullptr;        // [NL][2]
+    S* tl_blk = nullptr;    // [64] scratch of the backward substitution
+    int n = 0;              // 3*NP
+    size_t bytes = 0;
+};
+template <typename S>
+int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStream_t st, int* launches);
+
+// PCG path
+template <typename S>
+struct PcgWork {
+    S* hllinv = nullptr;   // [NL][3]
+    S* ul = nullptr;       // [NL][2]
+    S* tl = nullptr;       // [NL][2]
+    S* Hlp = nullptr;      // [n_hpl][6] copy of Hpl in (lm, pose) order
+    S* minv = nullptr;     // [NP][6] inverse of the diagonal blocks of S
+    S* g = nullptr;        // [3NP]
+    S* x = nullptr;
+    S* r = nullptr;
+    S* z = nullptr;
+    S* p0 = nullptr;
+    S* p1 = nullptr;
+    S* y = nullptr;
+    double* scal = nullptr;  // [16] rz, pAp, rz_new, rz0, done flag, iterations ...
+};
+template <typename S>
+int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st,
+                     int* iterations_out, int* launches);
+
+// batched
+template <typename S>
+struct BatchDev {
+    int nprob = 0, NP = 0, NL = 0, fixed = 0, Eb = 0, Eo = 0;
+    const int* b_pose = nullptr;
+    const int* b_lm = nullptr;
+    const S* b_om = nullptr;   // [Eb]
+    const S* b_z = nullptr;    // [nprob][Eb]
+    const int* o_src = nullptr;
+    const int* o_dst = nullptr;
+    const S* o_om = nullptr;   // [Eo][6]
+    const S* o_z = nullptr;    // [nprob][Eo][3]
+    S* pose = nullptr;         // [nprob][NP][4]
+    S* lm = nullptr;           // [nprob][NL][2]
+    double* chi2 = nullptr;    // [nprob][2]
+    double* delta_inf = nullptr;
+    int* status = nullptr;
+};
+template <typename S>
+int launch_batch_step(const BatchDev<S>& d, double kernel_threshold, double damping, cudaStream_t st);
+size_t batch_smem_bytes(int NP, int NL, size_t scalar_bytes);
+
+// ---- host-side pattern builder (pattern.cpp) --------------------------------------------------------
+struct HostPattern {
+    int NP = 0, NL = 0, fixed = 0, Eb = 0, Eo = 0, N = 0;
+    // (pose, lm)-sorted bearing edges
+    std::vector<int> b_pose, b_lm, b_perm, b_slot;
+    bool slots_identity = true;
+    std::vector<int> slot_pose, slot_lm;    // unique (pose, lm) blocks, sorted
+    std::vector<int> pose_ptr, lm_ptr, lm_order, lm_order_pose, lm_order_lm;
+    std::vector<int> o_src, o_dst, o_slot;
+    std::vector<int> off_lo, off_hi;        // unique pose-pose blocks, sorted
+    std::vector<int> pp_ptr, pp_nbr, pp_slot;
+    std::vector<int> tri_ptr, tri_edge;
+    std::vector<char> touched;              // [NP + NL]
+    // scalar CSC pattern of H_nofixed (slam/solver.cpp:72-75)
+    std::vector<int> csc_colptr, csc_rowidx;
+    // where each CSC entry comes from: source kind (0 Hpp,1 Hll,2 Hoff,3 Hpl), flat index into the EXPANDED block arrays
+    std::vector<int> csc_src_kind;
+    std::vector<int64_t> csc_src_index;
+    std::string error;
+};
+int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm,
+                  int64_t Eo, const int32_t* o_src, const int32_t* o_dst);
+
+}  // namespace bos

@@ -1,0 +1,972 @@
+// ctx.cu -- the C ABI of include/bos_b200.h: context, problem upload, phase sequencing, NCCL plumbing.
+// No CPU fallback lives here: every compute entry point launches CUDA kernels or fails.
+#include "../../include/bos_b200.h"
+#include "bos_internal.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace bos;
+
+namespace {
+
+struct DevAlloc {
+    std::vector<void*> ptrs;
+    ~DevAlloc() { release(); }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+    template <typename T>
+    T* get(size_t count) {
+        void* p = nullptr;
+        if (count == 0) count = 1;
+        if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+    template <typename T>
+    T* upload(const std::vector<T>& v) {
+        T* p = get<T>(v.size());
+        if (p && !v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return p;
+    }
+};
+
+// ---- NCCL through dlopen: the single-GPU path never depends on it -------------------------------------
+typedef struct { char internal[BOS_NCCL_UID_BYTES]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            api.GetUniqueId = (int (*)(nccl_uid_t*))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid_t, int))dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (int (*)(nccl_comm_t))dlsym(api.handle, "ncclCommDestroy");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+            api.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+            api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather;
+        }
+    }
+    return api;
+}
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+
+}  // namespace
+
+struct bos_ctx {
+    bos_options opt;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    bool have_problem = false, linearized = false, solved = false;
+    HostPattern P;
+    DevAlloc mem;
+    Dev<double> dd;
+    Dev<float> df;
+    DenseWork<double> dwd; DenseWork<float> dwf;
+    PcgWork<double> pwd; PcgWork<float> pwf;
+    bool dense_ready = false, pcg_ready = false;
+    void* edge_scratch = nullptr;
+    int* d_single_obs = nullptr;
+    size_t vals_len = 0, vals_prefix = 0, hpl_padded = 0;
+    bos_stats stats;
+    int solver_used = 0;
+    // multi-GPU
+    int rank = 0, nranks = 1, reduce_mode = 0;
+    nccl_comm_t comm = nullptr;
+    ShardRange shard;
+    int shard_chunk_b = 0;
+    int launches = 0;
+    bool pcg_bad = false;
+
+    bool f64() const { return opt.precision == BOS_PRECISION_F64; }
+};
+
+namespace {
+
+int fail(bos_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CUDA_OK(c, call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) return fail(c, BOS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+template <typename S> Dev<S>& dev(bos_ctx* c);
+template <> Dev<double>& dev<double>(bos_ctx* c) { return c->dd; }
+template <> Dev<float>& dev<float>(bos_ctx* c) { return c->df; }
+template <typename S> DenseWork<S>& dwork(bos_ctx* c);
+template <> DenseWork<double>& dwork<double>(bos_ctx* c) { return c->dwd; }
+template <> DenseWork<float>& dwork<float>(bos_ctx* c) { return c->dwf; }
+template <typename S> PcgWork<S>& pwork(bos_ctx* c);
+template <> PcgWork<double>& pwork<double>(bos_ctx* c) { return c->pwd; }
+template <> PcgWork<float>& pwork<float>(bos_ctx* c) { return c->pwf; }
+
+template <typename S>
+std::vector<S> narrow(const double* src, size_t n) {
+    std::vector<S> v(n);
+    for (size_t i = 0; i < n; i++) v[i] = (S)src[i];
+    return v;
+}
+
+void shard_ranges(int64_t Eb, int64_t Eo, int r, int R, int64_t out[4], int64_t* chunk_b) {
+    const int64_t cb = (Eb + R - 1) / R, co = (Eo + R - 1) / R;
+    if (chunk_b) *chunk_b = cb;
+    out[0] = std::min(Eb, r * cb); out[1] = std::min(Eb, (r + 1) * cb);
+    out[2] = std::min(Eo, r * co); out[3] = std::min(Eo, (r + 1) * co);
+}
+void compute_shard(bos_ctx* c) {
+    int64_t o[4], cb;
+    shard_ranges(c->P.Eb, c->P.Eo, c->rank, c->nranks, o, &cb);
+    c->shard_chunk_b = (int)cb;
+    c->shard.b_begin = (int)o[0]; c->shard.b_end = (int)o[1];
+    c->shard.o_begin = (int)o[2]; c->shard.o_end = (int)o[3];
+}
+
+template <typename S>
+int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const double* o_z, const double* o_omega) {
+    HostPattern& P = c->P;
+    Dev<S>& d = dev<S>(c);
+    d = Dev<S>();
+    DevAlloc& m = c->mem;
+    d.NP = P.NP; d.NL = P.NL; d.fixed = P.fixed; d.Eb = P.Eb; d.Eo = P.Eo; d.N = P.N;
+    d.n_hpl = (int)P.slot_pose.size(); d.n_off = (int)P.off_lo.size();
+    // bearing SoA in sorted order
+    std::vector<S> bz(P.Eb), bom(P.Eb);
+    for (int k = 0; k < P.Eb; k++) {
+        bz[k] = (S)b_z[P.b_perm[k]];
+        bom[k] = b_omega ? (S)b_omega[P.b_perm[k]] : S(1);
+    }
+    std::vector<S> oz((size_t)3 * P.Eo), oom((size_t)6 * P.Eo);
+    static const int up[6] = {0, 1, 2, 4, 5, 8};
+    for (int e = 0; e < P.Eo; e++) {
+        for (int k = 0; k < 3; k++) oz[(size_t)k * P.Eo + e] = (S)o_z[3 * (size_t)e + k];
+        for (int k = 0; k < 6; k++) oom[(size_t)k * P.Eo + e] = (S)o_omega[9 * (size_t)e + up[k]];
+    }
+#define UP(field, vec)                                   \
+    d.field = m.upload(vec);                             \
+    if (!d.field) return fail(c, BOS_ERR_NOMEM, "device allocation failed: " #field);
+    UP(b_pose, P.b_pose) UP(b_lm, P.b_lm) UP(b_z, bz) UP(b_om, bom) UP(b_perm, P.b_perm)
+    if (!P.slots_identity) { UP(b_slot, P.b_slot) }
+    UP(o_src, P.o_src) UP(o_dst, P.o_dst) UP(o_z, oz) UP(o_om, oom) UP(o_slot, P.o_slot)
+    UP(slot_pose, P.slot_pose) UP(slot_lm, P.slot_lm) UP(pose_ptr, P.pose_ptr) UP(lm_ptr, P.lm_ptr)
+    UP(lm_order, P.lm_order) UP(lm_order_pose, P.lm_order_pose) UP(lm_order_lm, P.lm_order_lm)
+    UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)
+    UP(tri_ptr, P.tri_ptr) UP(tri_edge, P.tri_edge)
+#undef UP
+    d.pose = m.get<S>(4 * (size_t)P.NP);
+    d.lm = m.get<S>(2 * (size_t)std::max(P.NL, 1));
+    c->vals_prefix = (size_t)P.N + 6 * (size_t)P.NP + 3 * (size_t)P.NL + 9 * (size_t)d.n_off;
+    c->vals_len = c->vals_prefix + 6 * (size_t)d.n_hpl;
+    // room for an in-place allgather of equally sized Hpl shards (up to 8 ranks, padded)
+    c->hpl_padded = 6 * ((size_t)d.n_hpl + 64);
+    d.vals = m.get<S>(c->vals_prefix + c->hpl_padded);
+    d.stats = m.get<double>(8);
+    d.delta = m.get<S>((size_t)P.N);
+    c->d_single_obs = m.get<int>(1);
+    if (!d.pose || !d.lm || !d.vals || !d.stats || !d.delta || !c->d_single_obs) return fail(c, BOS_ERR_NOMEM, "device allocation failed");
+    d.b = d.vals;
+    d.Hpp = d.b + P.N;
+    d.Hll = d.Hpp + 6 * (size_t)P.NP;
+    d.Hoff = d.Hll + 3 * (size_t)P.NL;
+    d.Hpl = d.Hoff + 9 * (size_t)d.n_off;
+    CUDA_OK(c, cudaMemset(d.vals, 0, (c->vals_prefix + c->hpl_padded) * sizeof(S)));
+    CUDA_OK(c, cudaMemset(d.delta, 0, (size_t)P.N * sizeof(S)));
+    CUDA_OK(c, cudaMemset(d.stats, 0, 8 * sizeof(double)));
+    CUDA_OK(c, cudaMemset(d.pose, 0, 4 * (size_t)P.NP * sizeof(S)));
+    CUDA_OK(c, cudaMemset(d.lm, 0, 2 * (size_t)std::max(P.NL, 1) * sizeof(S)));
+    return BOS_OK;
+}
+
+template <typename S>
+int ensure_dense(bos_ctx* c) {
+    if (c->dense_ready) return BOS_OK;
+    Dev<S>& d = dev<S>(c);
+    DenseWork<S>& w = dwork<S>(c);
+    w.n = 3 * d.NP;
+    w.Smat = c->mem.get<S>((size_t)w.n * w.n);
+    w.g = c->mem.get<S>((size_t)w.n);
+    w.hllinv = c->mem.get<S>(3 * (size_t)std::max(d.NL, 1));
+    w.ul = c->mem.get<S>(2 * (size_t)std::max(d.NL, 1));
+    w.tl = c->mem.get<S>(2 * (size_t)std::max(d.NL, 1));
+    w.tl_blk = c->mem.get<S>(64);
+    if (!w.Smat || !w.g || !w.hllinv || !w.ul || !w.tl || !w.tl_blk) return fail(c, BOS_ERR_NOMEM, "dense workspace allocation failed");
+    c->dense_ready = true;
+    return BOS_OK;
+}
+template <typename S>
+int ensure_pcg(bos_ctx* c) {
+    if (c->pcg_ready) return BOS_OK;
+    Dev<S>& d = dev<S>(c);
+    PcgWork<S>& w = pwork<S>(c);
+    const size_t n = 3 * (size_t)d.NP, nl = (size_t)std::max(d.NL, 1);
+    w.hllinv = c->mem.get<S>(3 * nl); w.ul = c->mem.get<S>(2 * nl); w.tl = c->mem.get<S>(2 * nl);
+    w.Hlp = c->mem.get<S>(6 * (size_t)std::max(d.n_hpl, 1));
+    w.minv = c->mem.get<S>(6 * (size_t)d.NP);
+    w.x = c->mem.get<S>(n); w.r = c->mem.get<S>(n); w.z = c->mem.get<S>(n);
+    w.p0 = c->mem.get<S>(n); w.y = c->mem.get<S>(n);
+    w.scal = c->mem.get<double>(16);
+    if (!w.hllinv || !w.ul || !w.tl || !w.Hlp || !w.minv || !w.x || !w.r || !w.z || !w.p0 || !w.y || !w.scal)
+        return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+    c->pcg_ready = true;
+    return BOS_OK;
+}
+
+int pick_solver(bos_ctx* c) {
+    if (c->opt.solver == BOS_SOLVER_DENSE_CHOLESKY || c->opt.solver == BOS_SOLVER_PCG) return c->opt.solver;
+    return (3 * c->P.NP <= c->opt.dense_max_dim) ? BOS_SOLVER_DENSE_CHOLESKY : BOS_SOLVER_PCG;
+}
+
+template <typename S>
+int allreduce_impl(bos_ctx* c) {
+    if (c->nranks <= 1 || !c->comm) return BOS_OK;
+    NcclApi& n = nccl();
+    Dev<S>& d = dev<S>(c);
+    const int dt = sizeof(S) == 8 ? kNcclFloat64 : kNcclFloat32;
+    int rc;
+    if (c->reduce_mode == 1 && c->P.slots_identity) {
+        rc = n.AllReduce(d.vals, d.vals, c->vals_prefix, dt, kNcclSum, c->comm, c->stream);
+        if (rc == 0) {
+            const size_t cnt = 6 * (size_t)c->shard_chunk_b;
+            rc = n.AllGather(d.Hpl + cnt * c->rank, d.Hpl, cnt, dt, c->comm, c->stream);
+        }
+    } else {
+        rc = n.AllReduce(d.vals, d.vals, c->vals_len, dt, kNcclSum, c->comm, c->stream);
+    }
+    if (rc == 0) rc = n.AllReduce(d.stats, d.stats, 4, kNcclFloat64, kNcclSum, c->comm, c->stream);
+    if (rc != 0) return fail(c, BOS_ERR_NCCL, std::string("nccl: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
+    return BOS_OK;
+}
+
+template <typename S>
+int linearize_impl(bos_ctx* c) {
+    Dev<S>& d = dev<S>(c);
+    const bool multi = c->nranks > 1;
+    const bool zero_hpl = !c->P.slots_identity || (multi && !(c->reduce_mode == 1 && c->P.slots_identity));
+    const double damp_here = (c->rank == 0) ? c->opt.damping : 0.0;
+    c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, damp_here, zero_hpl, c->sm_count, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    c->linearized = true; c->solved = false;
+    return BOS_OK;
+}
+
+template <typename S>
+int solve_impl(bos_ctx* c) {
+    Dev<S>& d = dev<S>(c);
+    const int which = pick_solver(c);
+    c->solver_used = which;
+    int nl = 0, rc = 0;
+    if (which == BOS_SOLVER_DENSE_CHOLESKY) {
+        int e = ensure_dense<S>(c);
+        if (e) return e;
+        rc = launch_dense_solve<S>(d, dwork<S>(c), c->opt.damping, c->stream, &nl);
+        c->stats.pcg_iterations = 0;
+        c->pcg_bad = false;
+    } else {
+        int e = ensure_pcg<S>(c);
+        if (e) return e;
+        int iters = 0;
+        double rtol = c->opt.pcg_rtol;
+        if (sizeof(S) == 4 && rtol < 1e-6) rtol = 1e-6;
+        rc = launch_pcg_solve<S>(d, pwork<S>(c), c->opt.pcg_max_iters, rtol, c->stream, &iters, &nl);
+        if (rc < 0) return fail(c, BOS_ERR_CUDA, std::string("pcg: ") + cudaGetErrorString(cudaGetLastError()));
+        c->stats.pcg_iterations = iters;
+        c->pcg_bad = (rc == 1);
+    }
+    c->launches += nl;
+    CUDA_OK(c, cudaGetLastError());
+    c->solved = true;
+    return BOS_OK;
+}
+
+template <typename S>
+int update_impl(bos_ctx* c) {
+    c->launches += launch_update<S>(dev<S>(c), c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    c->linearized = false; c->solved = false;
+    return BOS_OK;
+}
+
+template <typename S>
+int fetch_stats(bos_ctx* c) {
+    double h[8];
+    CUDA_OK(c, cudaMemcpyAsync(h, dev<S>(c).stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->stats.chi2_bearing = h[0]; c->stats.chi2_odometry = h[1];
+    c->stats.over_bearing = (int64_t)llround(h[2]); c->stats.over_odometry = (int64_t)llround(h[3]);
+    c->stats.delta_inf = h[4];
+    c->stats.solver_status = (h[5] != 0.0 || c->pcg_bad) ? 1 : 0;
+    c->stats.solver_used = c->solver_used;
+    return BOS_OK;
+}
+
+template <typename S>
+int step_impl(bos_ctx* c) {
+    c->launches = 0;
+    int rc;
+    cudaEventRecord(c->ev[0], c->stream);
+    if ((rc = linearize_impl<S>(c))) return rc;
+    cudaEventRecord(c->ev[1], c->stream);
+    if ((rc = allreduce_impl<S>(c))) return rc;
+    cudaEventRecord(c->ev[2], c->stream);
+    if ((rc = solve_impl<S>(c))) return rc;
+    cudaEventRecord(c->ev[3], c->stream);
+    if ((rc = update_impl<S>(c))) return rc;
+    cudaEventRecord(c->ev[4], c->stream);
+    if ((rc = fetch_stats<S>(c))) return rc;
+    cudaEventElapsedTime(&c->stats.ms_linearize, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->stats.ms_allreduce, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->stats.ms_solve, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->stats.ms_update, c->ev[3], c->ev[4]);
+    c->stats.gpu_launches = c->launches;
+    return BOS_OK;
+}
+
+template <typename S>
+int set_state_impl(bos_ctx* c, const double* poses, const double* lms) {
+    Dev<S>& d = dev<S>(c);
+    if (poses) {
+        if (sizeof(S) == 8) CUDA_OK(c, cudaMemcpyAsync(d.pose, poses, 4 * (size_t)d.NP * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        else {
+            std::vector<S> v = narrow<S>(poses, 4 * (size_t)d.NP);
+            CUDA_OK(c, cudaMemcpyAsync(d.pose, v.data(), v.size() * sizeof(S), cudaMemcpyHostToDevice, c->stream));
+            CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    if (lms && d.NL > 0) {
+        if (sizeof(S) == 8) CUDA_OK(c, cudaMemcpyAsync(d.lm, lms, 2 * (size_t)d.NL * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        else {
+            std::vector<S> v = narrow<S>(lms, 2 * (size_t)d.NL);
+            CUDA_OK(c, cudaMemcpyAsync(d.lm, v.data(), v.size() * sizeof(S), cudaMemcpyHostToDevice, c->stream));
+            CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    c->linearized = false; c->solved = false;
+    return BOS_OK;
+}
+
+template <typename S>
+int get_array(bos_ctx* c, const S* dptr, double* out, size_t n) {
+    if (!out || n == 0) return BOS_OK;
+    if (sizeof(S) == 8) {
+        CUDA_OK(c, cudaMemcpyAsync(out, dptr, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    } else {
+        std::vector<S> v(n);
+        CUDA_OK(c, cudaMemcpyAsync(v.data(), dptr, n * sizeof(S), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < n; i++) out[i] = (double)v[i];
+    }
+    return BOS_OK;
+}
+
+// expanded (full) block arrays from the compact device layout
+template <typename S>
+int download_blocks_impl(bos_ctx* c, double* Hpp, double* Hll, double* Hpl, double* Hoff, double* b) {
+    Dev<S>& d = dev<S>(c);
+    std::vector<double> vals(c->vals_len);
+    int rc = get_array<S>(c, d.vals, vals.data(), c->vals_len);
+    if (rc) return rc;
+    const double* vb = vals.data();
+    const double* vpp = vb + d.N;
+    const double* vll = vpp + 6 * (size_t)d.NP;
+    const double* voff = vll + 3 * (size_t)d.NL;
+    const double* vpl = voff + 9 * (size_t)d.n_off;
+    if (b) std::copy(vb, vb + d.N, b);
+    if (Hpp)
+        for (int p = 0; p < d.NP; p++) {
+            const double* h = vpp + 6 * (size_t)p;
+            const double m[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
+            std::copy(m, m + 9, Hpp + 9 * (size_t)p);
+        }
+    if (Hll)
+        for (int l = 0; l < d.NL; l++) {
+            const double* h = vll + 3 * (size_t)l;
+            const double m[4] = {h[0], h[1], h[1], h[2]};
+            std::copy(m, m + 4, Hll + 4 * (size_t)l);
+        }
+    if (Hoff) std::copy(voff, voff + 9 * (size_t)d.n_off, Hoff);
+    if (Hpl) std::copy(vpl, vpl + 6 * (size_t)d.n_hpl, Hpl);
+    return BOS_OK;
+}
+
+template <typename S>
+int edge_terms_impl(bos_ctx* c, double* err_b, double* jac_b, double* err_o, double* jac_o) {
+    Dev<S>& d = dev<S>(c);
+    DevAlloc tmp;
+    S* eb = tmp.get<S>((size_t)d.Eb); S* jb = tmp.get<S>(5 * (size_t)d.Eb);
+    S* eo = tmp.get<S>(3 * (size_t)d.Eo); S* jo = tmp.get<S>(18 * (size_t)d.Eo);
+    if (!eb || !jb || !eo || !jo) return fail(c, BOS_ERR_NOMEM, "edge term scratch allocation failed");
+    launch_edge_terms<S>(d, eb, jb, eo, jo, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    int rc;
+    if ((rc = get_array<S>(c, eb, err_b, (size_t)d.Eb))) return rc;
+    if ((rc = get_array<S>(c, jb, jac_b, 5 * (size_t)d.Eb))) return rc;
+    if ((rc = get_array<S>(c, eo, err_o, 3 * (size_t)d.Eo))) return rc;
+    if ((rc = get_array<S>(c, jo, jac_o, 18 * (size_t)d.Eo))) return rc;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BOS_OK;
+}
+
+template <typename S>
+int triangulate_impl(bos_ctx* c, int* single) {
+    Dev<S>& d = dev<S>(c);
+    CUDA_OK(c, cudaMemsetAsync(c->d_single_obs, 0, sizeof(int), c->stream));
+    launch_triangulate<S>(d, c->d_single_obs, c->stream);
+    CUDA_OK(c, cudaGetLastError());
+    int h = 0;
+    CUDA_OK(c, cudaMemcpyAsync(&h, c->d_single_obs, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (single) *single = h;
+    return BOS_OK;
+}
+
+#define DISPATCH(c, fn, ...) ((c)->f64() ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+#define NEED(c, cond, msg) \
+    if (!(cond)) return fail(c, BOS_ERR_STATE, msg)
+
+}  // namespace
+
+extern "C" {
+
+void bos_default_options(bos_options* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->device = 0;
+    o->precision = BOS_PRECISION_F64;
+    o->solver = BOS_SOLVER_AUTO;
+    o->dense_max_dim = 36000;
+    o->kernel_threshold = 1.0;
+    o->damping = 0.01f;  // the reference's float literal, widened (slam/solver.cpp:17)
+    o->pcg_max_iters = 5000;
+    o->pcg_rtol = 1e-10;
+}
+
+int bos_version(void) { return 100; }
+
+int bos_create(const bos_options* opts, bos_ctx** out) {
+    if (!out) return BOS_ERR_INVALID;
+    *out = nullptr;
+    std::unique_ptr<bos_ctx> c(new bos_ctx());
+    if (opts) c->opt = *opts; else bos_default_options(&c->opt);
+    std::memset(&c->stats, 0, sizeof(c->stats));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return BOS_ERR_CUDA;
+    if (c->opt.device < 0 || c->opt.device >= ndev) return BOS_ERR_INVALID;
+    if (cudaSetDevice(c->opt.device) != cudaSuccess) return BOS_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->opt.device) != cudaSuccess) return BOS_ERR_CUDA;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return BOS_ERR_CUDA;
+    for (auto& e : c->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return BOS_ERR_CUDA;
+    *out = c.release();
+    return BOS_OK;
+}
+
+int bos_destroy(bos_ctx* c) {
+    if (!c) return BOS_OK;
+    cudaSetDevice(c->opt.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    c->mem.release();
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return BOS_OK;
+}
+
+const char* bos_last_error(const bos_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int bos_set_kernel_threshold(bos_ctx* c, double kt) {
+    if (!c) return BOS_ERR_INVALID;
+    c->opt.kernel_threshold = kt;
+    return BOS_OK;
+}
+int bos_set_damping_factor(bos_ctx* c, double df) {
+    if (!c) return BOS_ERR_INVALID;
+    c->opt.damping = df;
+    return BOS_OK;
+}
+
+int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm,
+                       const double* b_z, const double* b_omega, int64_t Eo, const int32_t* o_src, const int32_t* o_dst,
+                       const double* o_z, const double* o_omega) {
+    if (!c) return BOS_ERR_INVALID;
+    if ((Eb > 0 && (!b_pose || !b_lm || !b_z)) || (Eo > 0 && (!o_src || !o_dst || !o_z || !o_omega)))
+        return fail(c, BOS_ERR_INVALID, "null edge array");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    c->have_problem = false; c->dense_ready = false; c->pcg_ready = false;
+    c->mem.release();
+    if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst) != 0)
+        return fail(c, BOS_ERR_INVALID, c->P.error);
+    int rc = c->f64() ? upload_impl<double>(c, b_z, b_omega, o_z, o_omega) : upload_impl<float>(c, b_z, b_omega, o_z, o_omega);
+    if (rc) return rc;
+    compute_shard(c);
+    c->have_problem = true; c->linearized = false; c->solved = false;
+    return BOS_OK;
+}
+
+int bos_set_state(bos_ctx* c, const double* poses, const double* lms) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "set_state before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, set_state_impl, c, poses, lms);
+    if (rc) return rc;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BOS_OK;
+}
+
+int bos_get_state(bos_ctx* c, double* poses, double* lms) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "get_state before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc;
+    if (c->f64()) {
+        if ((rc = get_array<double>(c, c->dd.pose, poses, 4 * (size_t)c->dd.NP))) return rc;
+        return get_array<double>(c, c->dd.lm, lms, 2 * (size_t)c->dd.NL);
+    }
+    if ((rc = get_array<float>(c, c->df.pose, poses, 4 * (size_t)c->df.NP))) return rc;
+    return get_array<float>(c, c->df.lm, lms, 2 * (size_t)c->df.NL);
+}
+
+int bos_linearize(bos_ctx* c) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "linearize before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, linearize_impl, c);
+    if (rc) return rc;
+    if ((rc = DISPATCH(c, allreduce_impl, c))) return rc;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BOS_OK;
+}
+
+int bos_solve(bos_ctx* c) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem && c->linearized, "solve before linearize");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, solve_impl, c);
+    if (rc) return rc;
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BOS_OK;
+}
+
+int bos_update(bos_ctx* c) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "update before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, update_impl, c);
+    if (rc) return rc;
+    return DISPATCH(c, fetch_stats, c);
+}
+
+int bos_step(bos_ctx* c, bos_stats* stats) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "step before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, step_impl, c);
+    if (rc) return rc;
+    if (stats) *stats = c->stats;
+    return BOS_OK;
+}
+
+int bos_step_host(bos_ctx* c, double* poses, double* lms, bos_stats* stats) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "step before upload_problem");
+    if (!poses) return fail(c, BOS_ERR_INVALID, "null state");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, set_state_impl, c, poses, lms);
+    if (rc) return rc;
+    if ((rc = DISPATCH(c, step_impl, c))) return rc;
+    if ((rc = bos_get_state(c, poses, lms))) return rc;
+    if (stats) *stats = c->stats;
+    return BOS_OK;
+}
+
+int bos_get_stats(bos_ctx* c, bos_stats* stats) {
+    if (!c || !stats) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "get_stats before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, fetch_stats, c);
+    if (rc) return rc;
+    *stats = c->stats;
+    return BOS_OK;
+}
+
+int bos_triangulate(bos_ctx* c, int* single_obs_count) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "triangulate before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    return DISPATCH(c, triangulate_impl, c, single_obs_count);
+}
+
+int bos_pattern_info_get(bos_ctx* c, bos_pattern_info* out) {
+    if (!c || !out) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "pattern before upload_problem");
+    out->n_hpl = (int64_t)c->P.slot_pose.size();
+    out->n_hpp_off = (int64_t)c->P.off_lo.size();
+    out->csc_n = c->P.N - 3;
+    out->csc_nnz = (int64_t)c->P.csc_rowidx.size();
+    out->N = c->P.N;
+    out->vals_len = (int64_t)c->vals_len;
+    return BOS_OK;
+}
+
+int bos_download_pattern(bos_ctx* c, int32_t* hpl_pose, int32_t* hpl_lm, int32_t* off_lo, int32_t* off_hi, int64_t* b_slot, int64_t* o_slot) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "pattern before upload_problem");
+    const HostPattern& P = c->P;
+    if (hpl_pose) std::copy(P.slot_pose.begin(), P.slot_pose.end(), hpl_pose);
+    if (hpl_lm) std::copy(P.slot_lm.begin(), P.slot_lm.end(), hpl_lm);
+    if (off_lo) std::copy(P.off_lo.begin(), P.off_lo.end(), off_lo);
+    if (off_hi) std::copy(P.off_hi.begin(), P.off_hi.end(), off_hi);
+    if (b_slot)
+        for (int k = 0; k < P.Eb; k++) b_slot[P.b_perm[k]] = P.b_slot[k];  // caller's edge order
+    if (o_slot)
+        for (int e = 0; e < P.Eo; e++) o_slot[e] = P.o_slot[e];
+    return BOS_OK;
+}
+
+int bos_download_blocks(bos_ctx* c, double* Hpp, double* Hll, double* Hpl, double* Hoff, double* b) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem && c->linearized, "download_blocks before linearize");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    return DISPATCH(c, download_blocks_impl, c, Hpp, Hll, Hpl, Hoff, b);
+}
+
+int bos_download_csc(bos_ctx* c, int32_t* colptr, int32_t* rowidx, double* val, double* b_nofixed) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "download_csc before upload_problem");
+    const HostPattern& P = c->P;
+    if (colptr) std::copy(P.csc_colptr.begin(), P.csc_colptr.end(), colptr);
+    if (rowidx) std::copy(P.csc_rowidx.begin(), P.csc_rowidx.end(), rowidx);
+    if (!val && !b_nofixed) return BOS_OK;
+    NEED(c, c->linearized, "download_csc values before linearize");
+    std::vector<double> Hpp(9 * (size_t)P.NP), Hll(4 * (size_t)std::max(P.NL, 1)), Hpl(6 * P.slot_pose.size() + 1), Hoff(9 * P.off_lo.size() + 1), b(P.N);
+    int rc = bos_download_blocks(c, Hpp.data(), Hll.data(), Hpl.data(), Hoff.data(), b.data());
+    if (rc) return rc;
+    if (val) {
+        const double* src[4] = {Hpp.data(), Hll.data(), Hoff.data(), Hpl.data()};
+        for (size_t k = 0; k < P.csc_rowidx.size(); k++) val[k] = src[P.csc_src_kind[k]][P.csc_src_index[k]];
+    }
+    if (b_nofixed) {
+        const int f3 = 3 * P.fixed;
+        for (int i = 0, k = 0; i < P.N; i++)
+            if (i < f3 || i >= f3 + 3) b_nofixed[k++] = b[i];
+    }
+    return BOS_OK;
+}
+
+int bos_download_delta(bos_ctx* c, double* delta) {
+    if (!c || !delta) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "download_delta before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    if (c->f64()) return get_array<double>(c, c->dd.delta, delta, (size_t)c->P.N);
+    return get_array<float>(c, c->df.delta, delta, (size_t)c->P.N);
+}
+
+int bos_upload_delta(bos_ctx* c, const double* delta) {
+    if (!c || !delta) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "upload_delta before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    if (c->f64()) {
+        CUDA_OK(c, cudaMemcpy(c->dd.delta, delta, (size_t)c->P.N * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> v = narrow<float>(delta, (size_t)c->P.N);
+        CUDA_OK(c, cudaMemcpy(c->df.delta, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return BOS_OK;
+}
+
+int bos_edge_terms(bos_ctx* c, double* err_b, double* jac_b, double* err_o, double* jac_o) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "edge_terms before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    return DISPATCH(c, edge_terms_impl, c, err_b, jac_b, err_o, jac_o);
+}
+
+int bos_nccl_unique_id(char* uid128) {
+    if (!uid128) return BOS_ERR_INVALID;
+    NcclApi& n = nccl();
+    if (!n.ok) return BOS_ERR_NCCL;
+    nccl_uid_t id;
+    if (n.GetUniqueId(&id) != 0) return BOS_ERR_NCCL;
+    std::memcpy(uid128, id.internal, BOS_NCCL_UID_BYTES);
+    return BOS_OK;
+}
+
+int bos_comm_init(bos_ctx* c, int rank, int nranks, const char* uid128) {
+    if (!c || !uid128 || nranks < 1 || rank < 0 || rank >= nranks) return BOS_ERR_INVALID;
+    if (nranks > 64) return fail(c, BOS_ERR_INVALID, "at most 64 ranks");
+    NcclApi& n = nccl();
+    if (!n.ok) return fail(c, BOS_ERR_NCCL, "libnccl.so.2 not loadable");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    nccl_uid_t id;
+    std::memcpy(id.internal, uid128, BOS_NCCL_UID_BYTES);
+    int rc = n.CommInitRank(&c->comm, nranks, id, rank);
+    if (rc != 0) return fail(c, BOS_ERR_NCCL, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
+    c->rank = rank; c->nranks = nranks;
+    if (c->have_problem) compute_shard(c);
+    return BOS_OK;
+}
+
+int bos_set_reduce_mode(bos_ctx* c, int mode) {
+    if (!c || (mode != 0 && mode != 1)) return BOS_ERR_INVALID;
+    c->reduce_mode = mode;
+    return BOS_OK;
+}
+
+int bos_set_edge_shard(bos_ctx* c, int rank, int nranks) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks || nranks > 64) return BOS_ERR_INVALID;
+    c->rank = rank; c->nranks = nranks;
+    if (c->have_problem) compute_shard(c);
+    return BOS_OK;
+}
+
+int bos_get_edge_shard(bos_ctx* c, int64_t* b_begin, int64_t* b_end, int64_t* o_begin, int64_t* o_end) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "shard before upload_problem");
+    if (b_begin) *b_begin = c->shard.b_begin;
+    if (b_end) *b_end = c->shard.b_end;
+    if (o_begin) *o_begin = c->shard.o_begin;
+    if (o_end) *o_end = c->shard.o_end;
+    return BOS_OK;
+}
+
+}  // extern "C"
+
+struct bos_host_pattern {
+    HostPattern P;
+};
+
+extern "C" {
+
+int bos_host_pattern_create(int NP, int NL, int fixed, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm, int64_t Eo,
+                            const int32_t* o_src, const int32_t* o_dst, bos_host_pattern** out) {
+    if (!out) return BOS_ERR_INVALID;
+    *out = nullptr;
+    if ((Eb > 0 && (!b_pose || !b_lm)) || (Eo > 0 && (!o_src || !o_dst))) return BOS_ERR_INVALID;
+    std::unique_ptr<bos_host_pattern> h(new bos_host_pattern());
+    if (build_pattern(h->P, NP, NL, fixed, Eb, b_pose, b_lm, Eo, o_src, o_dst) != 0) return BOS_ERR_INVALID;
+    *out = h.release();
+    return BOS_OK;
+}
+int bos_host_pattern_destroy(bos_host_pattern* p) {
+    delete p;
+    return BOS_OK;
+}
+int bos_host_pattern_info(const bos_host_pattern* p, bos_pattern_info* out) {
+    if (!p || !out) return BOS_ERR_INVALID;
+    const HostPattern& P = p->P;
+    out->n_hpl = (int64_t)P.slot_pose.size();
+    out->n_hpp_off = (int64_t)P.off_lo.size();
+    out->csc_n = P.N - 3;
+    out->csc_nnz = (int64_t)P.csc_rowidx.size();
+    out->N = P.N;
+    out->vals_len = (int64_t)P.N + 6LL * P.NP + 3LL * P.NL + 9LL * (int64_t)P.off_lo.size() + 6LL * (int64_t)P.slot_pose.size();
+    return BOS_OK;
+}
+int bos_host_pattern_get(const bos_host_pattern* p, int32_t* hpl_pose, int32_t* hpl_lm, int32_t* off_lo, int32_t* off_hi,
+                         int64_t* b_slot, int64_t* o_slot, int32_t* csc_colptr, int32_t* csc_rowidx) {
+    if (!p) return BOS_ERR_INVALID;
+    const HostPattern& P = p->P;
+    if (hpl_pose) std::copy(P.slot_pose.begin(), P.slot_pose.end(), hpl_pose);
+    if (hpl_lm) std::copy(P.slot_lm.begin(), P.slot_lm.end(), hpl_lm);
+    if (off_lo) std::copy(P.off_lo.begin(), P.off_lo.end(), off_lo);
+    if (off_hi) std::copy(P.off_hi.begin(), P.off_hi.end(), off_hi);
+    if (b_slot)
+        for (int k = 0; k < P.Eb; k++) b_slot[P.b_perm[k]] = P.b_slot[k];
+    if (o_slot)
+        for (int e = 0; e < P.Eo; e++) o_slot[e] = P.o_slot[e];
+    if (csc_colptr) std::copy(P.csc_colptr.begin(), P.csc_colptr.end(), csc_colptr);
+    if (csc_rowidx) std::copy(P.csc_rowidx.begin(), P.csc_rowidx.end(), csc_rowidx);
+    return BOS_OK;
+}
+int bos_host_edge_shard(int64_t Eb, int64_t Eo, int rank, int nranks, int64_t* out4) {
+    if (!out4 || nranks < 1 || rank < 0 || rank >= nranks || Eb < 0 || Eo < 0) return BOS_ERR_INVALID;
+    shard_ranges(Eb, Eo, rank, nranks, out4, nullptr);
+    return BOS_OK;
+}
+
+}  // extern "C"
+
+// ---- batched problems ---------------------------------------------------------------------------------------
+struct bos_batch {
+    bos_options opt;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevAlloc mem;
+    BatchDev<double> dd;
+    BatchDev<float> df;
+    std::string err;
+    bool f64() const { return opt.precision == BOS_PRECISION_F64; }
+};
+
+namespace {
+template <typename S> BatchDev<S>& bdev(bos_batch* b);
+template <> BatchDev<double>& bdev<double>(bos_batch* b) { return b->dd; }
+template <> BatchDev<float>& bdev<float>(bos_batch* b) { return b->df; }
+
+template <typename S>
+int batch_create_impl(bos_batch* B, int nprob, int NP, int NL, int fixed, int Eb, const int32_t* b_pose, const int32_t* b_lm,
+                      const double* b_z, const double* b_omega, int Eo, const int32_t* o_src, const int32_t* o_dst,
+                      const double* o_z, const double* o_omega) {
+    BatchDev<S>& d = bdev<S>(B);
+    d.nprob = nprob; d.NP = NP; d.NL = NL; d.fixed = fixed; d.Eb = Eb; d.Eo = Eo;
+    DevAlloc& m = B->mem;
+    std::vector<int> bp(b_pose, b_pose + Eb), bl(b_lm, b_lm + Eb), os(o_src, o_src + Eo), od(o_dst, o_dst + Eo);
+    std::vector<S> bom(Eb), bz = narrow<S>(b_z, (size_t)nprob * Eb), oz = narrow<S>(o_z, (size_t)nprob * Eo * 3), oom((size_t)6 * Eo);
+    for (int e = 0; e < Eb; e++) bom[e] = b_omega ? (S)b_omega[e] : S(1);
+    static const int up[6] = {0, 1, 2, 4, 5, 8};
+    for (int e = 0; e < Eo; e++)
+        for (int k = 0; k < 6; k++) oom[6 * (size_t)e + k] = (S)o_omega[9 * (size_t)e + up[k]];
+    d.b_pose = m.upload(bp); d.b_lm = m.upload(bl); d.b_om = m.upload(bom); d.b_z = m.upload(bz);
+    d.o_src = m.upload(os); d.o_dst = m.upload(od); d.o_om = m.upload(oom); d.o_z = m.upload(oz);
+    d.pose = m.get<S>((size_t)nprob * NP * 4); d.lm = m.get<S>((size_t)nprob * std::max(NL, 1) * 2);
+    d.chi2 = m.get<double>(2 * (size_t)nprob); d.delta_inf = m.get<double>((size_t)nprob); d.status = m.get<int>((size_t)nprob);
+    if (!d.b_pose || !d.b_lm || !d.b_om || !d.b_z || !d.o_src || !d.o_dst || !d.o_om || !d.o_z || !d.pose || !d.lm || !d.chi2 ||
+        !d.delta_inf || !d.status) {
+        B->err = "device allocation failed";
+        return BOS_ERR_NOMEM;
+    }
+    return BOS_OK;
+}
+template <typename S>
+int batch_xfer(bos_batch* B, double* poses, double* lms, bool to_device) {
+    BatchDev<S>& d = bdev<S>(B);
+    const size_t np = (size_t)d.nprob * d.NP * 4, nl = (size_t)d.nprob * d.NL * 2;
+    auto one = [&](S* dptr, double* h, size_t n) -> int {
+        if (!h || n == 0) return 0;
+        std::vector<S> v(n);
+        if (to_device) {
+            for (size_t i = 0; i < n; i++) v[i] = (S)h[i];
+            if (cudaMemcpy(dptr, v.data(), n * sizeof(S), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        } else {
+            if (cudaMemcpy(v.data(), dptr, n * sizeof(S), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+            for (size_t i = 0; i < n; i++) h[i] = (double)v[i];
+        }
+        return 0;
+    };
+    if (cudaStreamSynchronize(B->stream) != cudaSuccess) return BOS_ERR_CUDA;
+    if (one(d.pose, poses, np) || one(d.lm, lms, nl)) { B->err = "state copy failed"; return BOS_ERR_CUDA; }
+    return BOS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int bos_batch_create(const bos_options* opts, int nprob, int NP, int NL, int fixed, int Eb, const int32_t* b_pose, const int32_t* b_lm,
+                     const double* b_z, const double* b_omega, int Eo, const int32_t* o_src, const int32_t* o_dst,
+                     const double* o_z, const double* o_omega, bos_batch** out) {
+    if (!out) return BOS_ERR_INVALID;
+    *out = nullptr;
+    if (nprob <= 0 || NP <= 0 || NL < 0 || Eb < 0 || Eo < 0 || fixed < 0 || fixed >= NP) return BOS_ERR_INVALID;
+    if ((Eb > 0 && (!b_pose || !b_lm || !b_z)) || (Eo > 0 && (!o_src || !o_dst || !o_z || !o_omega))) return BOS_ERR_INVALID;
+    for (int e = 0; e < Eb; e++)
+        if (b_pose[e] < 0 || b_pose[e] >= NP || b_lm[e] < 0 || b_lm[e] >= NL) return BOS_ERR_INVALID;
+    for (int e = 0; e < Eo; e++)
+        if (o_src[e] < 0 || o_src[e] >= NP || o_dst[e] < 0 || o_dst[e] >= NP || o_src[e] == o_dst[e]) return BOS_ERR_INVALID;
+    std::unique_ptr<bos_batch> B(new bos_batch());
+    if (opts) B->opt = *opts; else bos_default_options(&B->opt);
+    const size_t smem = batch_smem_bytes(NP, NL, B->f64() ? 8 : 4);
+    if (smem > 200 * 1024) return BOS_ERR_INVALID;  // "mini-sized" problems only: the whole system lives in shared memory
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return BOS_ERR_CUDA;
+    if (cudaSetDevice(B->opt.device) != cudaSuccess) return BOS_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking) != cudaSuccess) return BOS_ERR_CUDA;
+    if (cudaEventCreate(&B->ev0) != cudaSuccess || cudaEventCreate(&B->ev1) != cudaSuccess) return BOS_ERR_CUDA;
+    int rc = B->f64() ? batch_create_impl<double>(B.get(), nprob, NP, NL, fixed, Eb, b_pose, b_lm, b_z, b_omega, Eo, o_src, o_dst, o_z, o_omega)
+                      : batch_create_impl<float>(B.get(), nprob, NP, NL, fixed, Eb, b_pose, b_lm, b_z, b_omega, Eo, o_src, o_dst, o_z, o_omega);
+    if (rc) return rc;
+    *out = B.release();
+    return BOS_OK;
+}
+
+int bos_batch_destroy(bos_batch* B) {
+    if (!B) return BOS_OK;
+    cudaSetDevice(B->opt.device);
+    if (B->stream) cudaStreamSynchronize(B->stream);
+    B->mem.release();
+    if (B->ev0) cudaEventDestroy(B->ev0);
+    if (B->ev1) cudaEventDestroy(B->ev1);
+    if (B->stream) cudaStreamDestroy(B->stream);
+    delete B;
+    return BOS_OK;
+}
+
+const char* bos_batch_last_error(const bos_batch* B) { return B ? B->err.c_str() : "null batch"; }
+
+int bos_batch_set_states(bos_batch* B, const double* poses, const double* lms) {
+    if (!B) return BOS_ERR_INVALID;
+    cudaSetDevice(B->opt.device);
+    return B->f64() ? batch_xfer<double>(B, const_cast<double*>(poses), const_cast<double*>(lms), true)
+                    : batch_xfer<float>(B, const_cast<double*>(poses), const_cast<double*>(lms), true);
+}
+int bos_batch_get_states(bos_batch* B, double* poses, double* lms) {
+    if (!B) return BOS_ERR_INVALID;
+    cudaSetDevice(B->opt.device);
+    return B->f64() ? batch_xfer<double>(B, poses, lms, false) : batch_xfer<float>(B, poses, lms, false);
+}
+
+int bos_batch_step_device(bos_batch* B, int n_steps, float* elapsed_ms) {
+    if (!B || n_steps < 0) return BOS_ERR_INVALID;
+    cudaSetDevice(B->opt.device);
+    cudaEventRecord(B->ev0, B->stream);
+    for (int i = 0; i < n_steps; i++) {
+        int rc = B->f64() ? launch_batch_step<double>(B->dd, B->opt.kernel_threshold, B->opt.damping, B->stream)
+                          : launch_batch_step<float>(B->df, B->opt.kernel_threshold, B->opt.damping, B->stream);
+        if (rc < 0) { B->err = "batch launch configuration failed"; return BOS_ERR_CUDA; }
+    }
+    cudaEventRecord(B->ev1, B->stream);
+    cudaError_t e = cudaStreamSynchronize(B->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { B->err = cudaGetErrorString(e); return BOS_ERR_CUDA; }
+    if (elapsed_ms) cudaEventElapsedTime(elapsed_ms, B->ev0, B->ev1);
+    return BOS_OK;
+}
+
+int bos_batch_step(bos_batch* B, double* chi2, double* delta_inf, int32_t* status) {
+    if (!B) return BOS_ERR_INVALID;
+    int rc = bos_batch_step_device(B, 1, nullptr);
+    if (rc) return rc;
+    const int nprob = B->f64() ? B->dd.nprob : B->df.nprob;
+    const double* dchi = B->f64() ? B->dd.chi2 : B->df.chi2;
+    const double* ddel = B->f64() ? B->dd.delta_inf : B->df.delta_inf;
+    const int* dst = B->f64() ? B->dd.status : B->df.status;
+    if (chi2 && cudaMemcpy(chi2, dchi, 2 * (size_t)nprob * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return BOS_ERR_CUDA;
+    if (delta_inf && cudaMemcpy(delta_inf, ddel, (size_t)nprob * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return BOS_ERR_CUDA;
+    if (status && cudaMemcpy(status, dst, (size_t)nprob * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return BOS_ERR_CUDA;
+    return BOS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// pattern.cpp -- host-side, one-time, integer-only: the CSR-of-blocks sparsity pattern of H and the
+// per-edge block slots.  Replaces what the reference rediscovers for every edge of every iteration
+// (std::map id lookups, framework/state.cpp:43-63; sparse merges, slam/solver.cpp:44,60) and
+// construct_the_permutation (slam/solver.cpp:99-125): the fixed pose's rows/cols are simply absent
+// from the exported scalar pattern.  Everything here must be bit-exact against the oracle.
+#include "bos_internal.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace bos {
+
+int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const int32_t* b_pose, const int32_t* b_lm,
+                  int64_t Eo64, const int32_t* o_src, const int32_t* o_dst) {
+    P = HostPattern();
+    if (NP <= 0 || NL < 0 || Eb64 < 0 || Eo64 < 0 || Eb64 > 0x3fffffff || Eo64 > 0x3fffffff) { P.error = "bad sizes"; return 1; }
+    if (fixed < 0 || fixed >= NP) { P.error = "fixed pose stix out of range"; return 1; }
+    const int Eb = (int)Eb64, Eo = (int)Eo64;
+    P.NP = NP; P.NL = NL; P.fixed = fixed; P.Eb = Eb; P.Eo = Eo; P.N = 3 * NP + 2 * NL;
+    for (int e = 0; e < Eb; e++)
+        if (b_pose[e] < 0 || b_pose[e] >= NP || b_lm[e] < 0 || b_lm[e] >= NL) { P.error = "bearing edge index out of range"; return 1; }
+    for (int e = 0; e < Eo; e++) {
+        if (o_src[e] < 0 || o_src[e] >= NP || o_dst[e] < 0 || o_dst[e] >= NP) { P.error = "odometry edge index out of range"; return 1; }
+        if (o_src[e] == o_dst[e]) { P.error = "odometry self-loop"; return 1; }
+    }
+    P.touched.assign((size_t)NP + NL, 0);
+
+    // ---- bearing edges sorted by (pose, lm), ties in caller order ------------------------------------------
+    std::vector<uint64_t> key(Eb);
+    P.b_perm.resize(Eb);
+    std::iota(P.b_perm.begin(), P.b_perm.end(), 0);
+    for (int e = 0; e < Eb; e++) key[e] = ((uint64_t)(uint32_t)b_pose[e] << 32) | (uint32_t)b_lm[e];
+    bool sorted = true;
+    for (int e = 1; e < Eb && sorted; e++) sorted = key[e - 1] <= key[e];
+    if (!sorted)
+        std::stable_sort(P.b_perm.begin(), P.b_perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    P.b_pose.resize(Eb); P.b_lm.resize(Eb); P.b_slot.resize(Eb);
+    P.slot_pose.clear(); P.slot_lm.clear();
+    P.slots_identity = true;
+    for (int k = 0; k < Eb; k++) {
+        const int e = P.b_perm[k];
+        P.b_pose[k] = b_pose[e]; P.b_lm[k] = b_lm[e];
+        P.touched[b_pose[e]] = 1; P.touched[(size_t)NP + b_lm[e]] = 1;
+        if (k == 0 || key[e] != key[P.b_perm[k - 1]]) { P.slot_pose.push_back(b_pose[e]); P.slot_lm.push_back(b_lm[e]); }
+        P.b_slot[k] = (int)P.slot_pose.size() - 1;
+        if (P.b_slot[k] != k) P.slots_identity = false;
+    }
+    const int n_hpl = (int)P.slot_pose.size();
+    P.pose_ptr.assign(NP + 1, 0);
+    for (int s = 0; s < n_hpl; s++) P.pose_ptr[P.slot_pose[s] + 1]++;
+    for (int i = 0; i < NP; i++) P.pose_ptr[i + 1] += P.pose_ptr[i];
+    // slots grouped by landmark, ascending pose inside a landmark (counting sort keeps slot order)
+    P.lm_ptr.assign(NL + 1, 0);
+    for (int s = 0; s < n_hpl; s++) P.lm_ptr[P.slot_lm[s] + 1]++;
+    for (int j = 0; j < NL; j++) P.lm_ptr[j + 1] += P.lm_ptr[j];
+    P.lm_order.resize(n_hpl); P.lm_order_pose.resize(n_hpl); P.lm_order_lm.resize(n_hpl);
+    {
+        std::vector<int> cur(P.lm_ptr.begin(), P.lm_ptr.end() - 1);
+        for (int s = 0; s < n_hpl; s++) {
+            int k = cur[P.slot_lm[s]]++;
+            P.lm_order[k] = s; P.lm_order_pose[k] = P.slot_pose[s]; P.lm_order_lm[k] = P.slot_lm[s];
+        }
+    }
+    // bearing edges grouped by landmark in caller order (triangulation rows, slam/triangulation.cpp:5-19)
+    P.tri_ptr.assign(NL + 1, 0);
+    for (int e = 0; e < Eb; e++) P.tri_ptr[b_lm[e] + 1]++;
+    for (int j = 0; j < NL; j++) P.tri_ptr[j + 1] += P.tri_ptr[j];
+    P.tri_edge.resize(Eb);
+    {
+        std::vector<int> inv(Eb);
+        for (int k = 0; k < Eb; k++) inv[P.b_perm[k]] = k;
+        std::vector<int> cur(P.tri_ptr.begin(), P.tri_ptr.end() - 1);
+        for (int e = 0; e < Eb; e++) P.tri_edge[cur[b_lm[e]]++] = inv[e];
+    }
+
+    // ---- odometry edges: unique unordered pose pairs ---------------------------------------------------------
+    P.o_src.assign(o_src, o_src + Eo); P.o_dst.assign(o_dst, o_dst + Eo);
+    std::vector<uint64_t> okey(Eo);
+    for (int e = 0; e < Eo; e++) {
+        int lo = std::min(o_src[e], o_dst[e]), hi = std::max(o_src[e], o_dst[e]);
+        okey[e] = ((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi;
+        P.touched[o_src[e]] = 1; P.touched[o_dst[e]] = 1;
+    }
+    std::vector<uint64_t> uniq(okey);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    const int n_off = (int)uniq.size();
+    P.off_lo.resize(n_off); P.off_hi.resize(n_off);
+    for (int k = 0; k < n_off; k++) { P.off_lo[k] = (int)(uniq[k] >> 32); P.off_hi[k] = (int)(uniq[k] & 0xffffffffu); }
+    P.o_slot.resize(Eo);
+    for (int e = 0; e < Eo; e++) P.o_slot[e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), okey[e]) - uniq.begin());
+    // pose-pose adjacency, neighbours ascending
+    P.pp_ptr.assign(NP + 1, 0);
+    for (int k = 0; k < n_off; k++) { P.pp_ptr[P.off_lo[k] + 1]++; P.pp_ptr[P.off_hi[k] + 1]++; }
+    for (int i = 0; i < NP; i++) P.pp_ptr[i + 1] += P.pp_ptr[i];
+    P.pp_nbr.resize(2 * (size_t)n_off); P.pp_slot.resize(2 * (size_t)n_off);
+    {
+        std::vector<int> cur(P.pp_ptr.begin(), P.pp_ptr.end() - 1);
+        // first the neighbours below a pose (it is the 'hi' side), in ascending lo; uniq is sorted by (lo, hi)
+        for (int k = 0; k < n_off; k++) { int i = P.off_hi[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_lo[k]; P.pp_slot[c] = k | (int)0x80000000; }
+        for (int k = 0; k < n_off; k++) { int i = P.off_lo[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_hi[k]; P.pp_slot[c] = k; }
+    }
+
+    // ---- scalar CSC pattern of H_nofixed with the source of every entry ------------------------------------
+    auto nofixed = [&](int i) { const int f3 = 3 * fixed; return i < f3 ? i : (i < f3 + 3 ? -1 : i - 3); };
+    const int n = P.N - 3;
+    P.csc_colptr.assign(n + 1, 0);
+    P.csc_rowidx.clear(); P.csc_src_kind.clear(); P.csc_src_index.clear();
+    auto emit = [&](int grow, int kind, int64_t idx) {
+        int r = nofixed(grow);
+        if (r < 0) return;
+        P.csc_rowidx.push_back(r); P.csc_src_kind.push_back(kind); P.csc_src_index.push_back(idx);
+    };
+    for (int p = 0; p < NP; p++) {
+        if (p == fixed) continue;
+        for (int c = 0; c < 3; c++) {
+            // neighbours below p, p itself, neighbours above p, then landmarks
+            int a0 = P.pp_ptr[p], a1 = P.pp_ptr[p + 1];
+            int q = a0;
+            for (; q < a1 && P.pp_nbr[q] < p; q++) {
+                int slot = P.pp_slot[q] & 0x7fffffff;  // block H[nbr][p]: row a in nbr, col c in p
+                for (int a = 0; a < 3; a++) emit(3 * P.pp_nbr[q] + a, 2, (int64_t)slot * 9 + a * 3 + c);
+            }
+            for (int a = 0; a < 3; a++)
+                if (P.touched[p] || a == c) emit(3 * p + a, 0, (int64_t)p * 9 + a * 3 + c);
+            for (; q < a1; q++) {
+                int slot = P.pp_slot[q] & 0x7fffffff;  // block H[p][nbr]: entry (row a in nbr, col c in p) is its transpose [c][a]
+                for (int a = 0; a < 3; a++) emit(3 * P.pp_nbr[q] + a, 2, (int64_t)slot * 9 + c * 3 + a);
+            }
+            for (int s = P.pose_ptr[p]; s < P.pose_ptr[p + 1]; s++)
+                for (int a = 0; a < 2; a++) emit(3 * NP + 2 * P.slot_lm[s] + a, 3, (int64_t)s * 6 + c * 2 + a);
+            P.csc_colptr[nofixed(3 * p + c) + 1] = (int)P.csc_rowidx.size();
+        }
+    }
+    for (int l = 0; l < NL; l++) {
+        for (int c = 0; c < 2; c++) {
+            for (int k = P.lm_ptr[l]; k < P.lm_ptr[l + 1]; k++) {
+                int s = P.lm_order[k];
+                for (int a = 0; a < 3; a++) emit(3 * P.slot_pose[s] + a, 3, (int64_t)s * 6 + a * 2 + c);
+            }
+            for (int a = 0; a < 2; a++)
+                if (P.touched[(size_t)NP + l] || a == c) emit(3 * NP + 2 * l + a, 1, (int64_t)l * 4 + a * 2 + c);
+            P.csc_colptr[nofixed(3 * NP + 2 * l + c) + 1] = (int)P.csc_rowidx.size();
+        }
+    }
+    return 0;
+}
+
+}  // namespace bos

@@ -1,0 +1,370 @@
+// solve_dense.cu -- K4/K5a/K6 for small problems: the 2x2 landmark blocks are Schur-complemented out
+// EXPLICITLY into a dense pose system, which is Cholesky-factorised and solved; landmarks follow by
+// back-substitution.  Replaces SimplicialLDLT on H_nofixed (slam/solver.hpp:72, solver.cpp:77-94):
+// exact block elimination + exact factorisation give the same dx up to rounding.
+//
+// The factorisation is a right-looking blocked Cholesky (panel 64): diagonal-block POTRF in one CTA,
+// row-parallel TRSM on the panel, and the trailing update C -= P P^T as 64x64 tiles -- the one real dense
+// contraction on the path, run on the FP64 tensor pipe (mma.sync m8n8k4 f64 = DMMA; tcgen05 has no FP64
+// kind).  S is column-major, lower triangle only.
+#include "bos_internal.h"
+#include "bos_math.cuh"
+#include "bos_schur.cuh"
+
+namespace bos {
+
+constexpr int NB = 64;        // panel width / tile edge
+constexpr int LDT = NB + 4;   // smem leading dimension: == 4 (mod 16) doubles -> conflict-free DMMA fragment loads
+
+// ---- assembly of the dense reduced system -----------------------------------------------------------
+template <typename S>
+__global__ void __launch_bounds__(256) k_dense_fill_diag(Dev<S> d, S* __restrict__ Sm, S* __restrict__ g, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.NP) return;
+    const S* h = d.Hpp + 6LL * p;
+    const S m[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
+    for (int a = 0; a < 3; a++) {
+        for (int c = 0; c < 3; c++) Sm[(size_t)(3 * p + a) + (size_t)(3 * p + c) * n] = m[a * 3 + c];
+        g[3 * p + a] = -d.b[3LL * p + a];
+    }
+}
+template <typename S>
+__global__ void __launch_bounds__(256) k_dense_fill_off(Dev<S> d, S* __restrict__ Sm, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d.n_off) return;
+    const int lo = d.off_lo[k], hi = d.off_hi[k];
+    const S* B = d.Hoff + 9LL * k;  // H[lo][hi]; the lower triangle holds its transpose at (hi, lo)
+    for (int a = 0; a < 3; a++)
+        for (int c = 0; c < 3; c++) Sm[(size_t)(3 * hi + c) + (size_t)(3 * lo + a) * n] = B[a * 3 + c];
+}
+
+// one warp per landmark: S[pi,pj] -= Hpl_i Hll^-1 Hpl_j^T for every pair of its observing poses (pi >= pj),
+// g[pi] += Hpl_i Hll^-1 b_l
+template <typename S>
+__global__ void __launch_bounds__(256) k_dense_schur(Dev<S> d, const S* __restrict__ hllinv, const S* __restrict__ ul,
+                                                     S* __restrict__ Sm, S* __restrict__ g, int n) {
+    const int lane = threadIdx.x & 31;
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (l >= d.NL) return;
+    const int k0 = d.lm_ptr[l], m = d.lm_ptr[l + 1] - k0;
+    const S i00 = hllinv[3LL * l], i01 = hllinv[3LL * l + 1], i11 = hllinv[3LL * l + 2];
+    const S u0 = ul[2LL * l], u1 = ul[2LL * l + 1];
+    for (int i = lane; i < m; i += 32) {
+        const S* B = d.Hpl + 6LL * d.lm_order[k0 + i];
+        const int p = d.lm_order_pose[k0 + i];
+        red_add(g + 3 * p + 0, B[0] * u0 + B[1] * u1);
+        red_add(g + 3 * p + 1, B[2] * u0 + B[3] * u1);
+        red_add(g + 3 * p + 2, B[4] * u0 + B[5] * u1);
+    }
+    const long long npairs = (long long)m * (m + 1) / 2;
+    for (long long idx = lane; idx < npairs; idx += 32) {
+        int i = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+        while ((long long)i * (i + 1) / 2 > idx) i--;
+        while ((long long)(i + 1) * (i + 2) / 2 <= idx) i++;
+        const int j = (int)(idx - (long long)i * (i + 1) / 2);
+        const S* Bi = d.Hpl + 6LL * d.lm_order[k0 + i];
+        const S* Bj = d.Hpl + 6LL * d.lm_order[k0 + j];
+        const int pi = d.lm_order_pose[k0 + i], pj = d.lm_order_pose[k0 + j];  // ascending pose inside a landmark: pi >= pj
+        S bj[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) bj[k] = Bj[k];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const S ya0 = Bi[2 * a] * i00 + Bi[2 * a + 1] * i01;
+            const S ya1 = Bi[2 * a] * i01 + Bi[2 * a + 1] * i11;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (i == j && c > a) continue;  // diagonal block: lower part only
+                red_add(Sm + (size_t)(3 * pi + a) + (size_t)(3 * pj + c) * n, -(ya0 * bj[2 * c] + ya1 * bj[2 * c + 1]));
+            }
+        }
+    }
+}
+
+// ---- blocked Cholesky ---------------------------------------------------------------------------------
+// diagonal block: unblocked Cholesky in shared memory, one CTA
+template <typename S>
+__global__ void __launch_bounds__(256) k_potrf_diag(S* __restrict__ Sm, int n, int k0, int kb, double* __restrict__ stats) {
+    __shared__ S A[NB][NB + 1];  // A[col][row]
+    for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
+        int c = t / kb, r = t % kb;
+        A[c][r] = Sm[(size_t)(k0 + r) + (size_t)(k0 + c) * n];
+    }
+    __syncthreads();
+    for (int j = 0; j < kb; j++) {
+        if (threadIdx.x == 0) {
+            S dj = A[j][j];
+            if (!(dj > S(0))) { stats[5] = 1.0; dj = (dj < S(0)) ? -dj : S(1e-30); }
+            A[j][j] = sqrt(dj);
+        }
+        __syncthreads();
+        const S inv = S(1) / A[j][j];
+        for (int i = j + 1 + threadIdx.x; i < kb; i += blockDim.x) A[j][i] *= inv;
+        __syncthreads();
+        // trailing update of columns j+1..kb-1
+        const int i = threadIdx.x & (NB - 1);
+        for (int k = j + 1 + (threadIdx.x >> 6); k < kb; k += (blockDim.x >> 6))
+            if (i >= k && i < kb) A[k][i] -= A[j][i] * A[j][k];
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
+        int c = t / kb, r = t % kb;
+        if (r >= c) Sm[(size_t)(k0 + r) + (size_t)(k0 + c) * n] = A[c][r];
+    }
+}
+
+// panel: A[i, k0:k0+kb] <- A[i, k0:k0+kb] * L_kk^-T, one thread per row below the diagonal block
+template <typename S>
+__global__ void __launch_bounds__(128) k_trsm_panel(S* __restrict__ Sm, int n, int k0, int kb) {
+    __shared__ S L[NB][NB + 1];  // L[row j][col m]
+    for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
+        int j = t / NB, m = t % NB;
+        S v = (j == m) ? S(1) : S(0);
+        if (j < kb && m <= j) v = Sm[(size_t)(k0 + j) + (size_t)(k0 + m) * n];
+        L[j][m] = v;
+    }
+    __syncthreads();
+    const int i = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S x[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) x[j] = (j < kb) ? Sm[(size_t)i + (size_t)(k0 + j) * n] : S(0);
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        S s = x[j];
+#pragma unroll
+        for (int m = 0; m < j; m++) s -= x[m] * L[j][m];
+        x[j] = s / L[j][j];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+        if (j < kb) Sm[(size_t)i + (size_t)(k0 + j) * n] = x[j];
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// trailing update: C[ti,tj] -= P[ti] P[tj]^T over the lower tiles of the trailing matrix, 64x64 per CTA.
+// P = panel columns k0..k0+kb.  128 threads = 4 warps in a 2x2 arrangement of 32x32 warp tiles.
+template <typename S>
+__global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, int k0, int kb, int r0, int T) {
+    extern __shared__ unsigned char smem_raw[];
+    S* sA = reinterpret_cast<S*>(smem_raw);   // [NB k][LDT rows]
+    S* sB = sA + NB * LDT;
+    // decode the lower-triangular tile index
+    const long long idx = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((long long)ti * (ti + 1) / 2 > idx) ti--;
+    while ((long long)(ti + 1) * (ti + 2) / 2 <= idx) ti++;
+    const int tj = (int)(idx - (long long)ti * (ti + 1) / 2);
+    (void)T;
+    const int ra = r0 + ti * NB, rb = r0 + tj * NB;
+    for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
+        const int k = t / NB, r = t % NB;
+        S va = S(0), vb = S(0);
+        if (k < kb) {
+            if (ra + r < n) va = Sm[(size_t)(ra + r) + (size_t)(k0 + k) * n];
+            if (rb + r < n) vb = Sm[(size_t)(rb + r) + (size_t)(k0 + k) * n];
+        }
+        sA[k * LDT + r] = va;
+        sB[k * LDT + r] = vb;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    if constexpr (sizeof(S) == 8) {
+        double acc[4][4][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll 4
+        for (int kk = 0; kk < NB; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                af[t] = sA[(kk + fk) * LDT + wm + t * 8 + fr];
+                bf[t] = sB[(kk + fk) * LDT + wn + t * 8 + fr];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int row = ra + wm + a * 8 + fr;
+                const int col = rb + wn + b * 8 + 2 * fk;
+                if (row < n) {
+                    if (col < n) Sm[(size_t)row + (size_t)col * n] -= acc[a][b][0];
+                    if (col + 1 < n) Sm[(size_t)row + (size_t)(col + 1) * n] -= acc[a][b][1];
+                }
+            }
+    } else {
+        // FP32 path: scalar FMAs, 8x4 register tile per thread
+        const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+        float acc[8][4];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+        for (int k = 0; k < NB; k++) {
+            float av[8], bv[4];
+#pragma unroll
+            for (int a = 0; a < 8; a++) av[a] = sA[k * LDT + tx * 8 + a];
+#pragma unroll
+            for (int b = 0; b < 4; b++) bv[b] = sB[k * LDT + ty * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int row = ra + tx * 8 + a, col = rb + ty * 4 + b;
+                if (row < n && col < n) Sm[(size_t)row + (size_t)col * n] -= acc[a][b];
+            }
+        (void)lane; (void)wm; (void)wn;
+    }
+}
+
+// ---- triangular solves with the factor ------------------------------------------------------------------
+// forward, diagonal block: y_k = L_kk^-1 g_k   (one CTA of NB threads)
+template <typename S>
+__global__ void __launch_bounds__(NB) k_fwd_diag(const S* __restrict__ Sm, S* __restrict__ g, int n, int k0, int kb) {
+    __shared__ S y[NB];
+    const int j = threadIdx.x;
+    S v = (j < kb) ? g[k0 + j] : S(0);
+    for (int m = 0; m < kb; m++) {
+        if (j == m) y[m] = v / Sm[(size_t)(k0 + m) + (size_t)(k0 + m) * n];
+        __syncthreads();
+        if (j > m && j < kb) v -= Sm[(size_t)(k0 + j) + (size_t)(k0 + m) * n] * y[m];
+    }
+    if (j < kb) g[k0 + j] = y[j];
+}
+// forward, below the block: g_i -= sum_m L[i, k0+m] y_m
+template <typename S>
+__global__ void __launch_bounds__(256) k_fwd_update(const S* __restrict__ Sm, S* __restrict__ g, int n, int k0, int kb) {
+    __shared__ S y[NB];
+    if (threadIdx.x < NB) y[threadIdx.x] = (threadIdx.x < kb) ? g[k0 + threadIdx.x] : S(0);
+    __syncthreads();
+    const int i = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S s = S(0);
+    for (int m = 0; m < kb; m++) s += Sm[(size_t)i + (size_t)(k0 + m) * n] * y[m];
+    g[i] -= s;
+}
+// backward, gather: t_m = sum_{i >= k0+kb} L[i, k0+m] x_i   (t zeroed by the caller)
+template <typename S>
+__global__ void __launch_bounds__(256) k_bwd_gather(const S* __restrict__ Sm, const S* __restrict__ x, S* __restrict__ t,
+                                                    int n, int k0, int kb) {
+    __shared__ S part[8][NB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
+    const S xi = (i < n) ? x[i] : S(0);
+    for (int m = 0; m < kb; m++) {
+        S v = (i < n) ? Sm[(size_t)i + (size_t)(k0 + m) * n] * xi : S(0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BOS_FULL_MASK, v, o);
+        if (lane == 0) part[warp][m] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kb) {
+        S s = S(0);
+        for (int w = 0; w < 8; w++) s += part[w][threadIdx.x];
+        red_add(t + threadIdx.x, s);
+    }
+}
+// backward, diagonal block: x_k = L_kk^-T (y_k - t)
+template <typename S>
+__global__ void __launch_bounds__(NB) k_bwd_diag(const S* __restrict__ Sm, S* __restrict__ g, const S* __restrict__ t, int n, int k0, int kb) {
+    __shared__ S x[NB];
+    const int j = threadIdx.x;
+    S v = (j < kb) ? g[k0 + j] - t[j] : S(0);
+    for (int m = kb - 1; m >= 0; m--) {
+        if (j == m) x[m] = v / Sm[(size_t)(k0 + m) + (size_t)(k0 + m) * n];
+        __syncthreads();
+        if (j < m) v -= Sm[(size_t)(k0 + m) + (size_t)(k0 + j) * n] * x[m];  // L^T[j][m] = L[m][j]
+    }
+    if (j < kb) g[k0 + j] = x[j];
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) k_copy_delta_p(const S* __restrict__ g, S* __restrict__ delta, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) delta[i] = g[i];
+}
+
+template <typename S>
+int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStream_t st, int* launches) {
+    (void)damping;
+    int nl = 0;
+    const int n = w.n;
+    const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256;
+    cudaMemsetAsync(w.Smat, 0, sizeof(S) * (size_t)n * n, st);
+    k_dense_fill_diag<S><<<gp, 256, 0, st>>>(d, w.Smat, w.g, n); nl++;
+    if (d.n_off > 0) { k_dense_fill_off<S><<<(d.n_off + 255) / 256, 256, 0, st>>>(d, w.Smat, n); nl++; }
+    if (d.NL > 0) {
+        k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++;
+        k_dense_schur<S><<<(d.NL * 32 + 255) / 256, 256, 0, st>>>(d, w.hllinv, w.ul, w.Smat, w.g, n); nl++;
+    }
+    const size_t smem = 2 * (size_t)NB * LDT * sizeof(S);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_syrk_tiles<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(double)));
+        cudaFuncSetAttribute(k_syrk_tiles<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(float)));
+        attr_set = true;
+    }
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int kb = (n - k0 < NB) ? n - k0 : NB;
+        k_potrf_diag<S><<<1, 256, 0, st>>>(w.Smat, n, k0, kb, d.stats); nl++;
+        const int r0 = k0 + kb;
+        if (r0 < n) {
+            k_trsm_panel<S><<<(n - r0 + 127) / 128, 128, 0, st>>>(w.Smat, n, k0, kb); nl++;
+            const int T = (n - r0 + NB - 1) / NB;
+            const long long tiles = (long long)T * (T + 1) / 2;
+            k_syrk_tiles<S><<<(unsigned)tiles, 128, smem, st>>>(w.Smat, n, k0, kb, r0, T); nl++;
+        }
+    }
+    // forward substitution L y = g
+    for (int k0 = 0; k0 < n; k0 += NB) {
+        const int kb = (n - k0 < NB) ? n - k0 : NB;
+        k_fwd_diag<S><<<1, NB, 0, st>>>(w.Smat, w.g, n, k0, kb); nl++;
+        const int r0 = k0 + kb;
+        if (r0 < n) { k_fwd_update<S><<<(n - r0 + 255) / 256, 256, 0, st>>>(w.Smat, w.g, n, k0, kb); nl++; }
+    }
+    // backward substitution L^T x = y
+    const int last = ((n - 1) / NB) * NB;
+    for (int k0 = last; k0 >= 0; k0 -= NB) {
+        const int kb = (n - k0 < NB) ? n - k0 : NB;
+        const int r0 = k0 + kb;
+        cudaMemsetAsync(w.tl_blk, 0, sizeof(S) * NB, st);
+        if (r0 < n) { k_bwd_gather<S><<<(n - r0 + 255) / 256, 256, 0, st>>>(w.Smat, w.g, w.tl_blk, n, k0, kb); nl++; }
+        k_bwd_diag<S><<<1, NB, 0, st>>>(w.Smat, w.g, w.tl_blk, n, k0, kb); nl++;
+    }
+    k_copy_delta_p<S><<<(n + 255) / 256, 256, 0, st>>>(w.g, d.delta, n); nl++;
+    if (d.NL > 0) {
+        cudaMemsetAsync(w.tl, 0, sizeof(S) * 2 * (size_t)d.NL, st);
+        if (d.n_hpl > 0) {
+            k_lm_gather<S><<<(d.n_hpl + 255) / 256, 256, 0, st>>>(d.n_hpl, d.Hpl, d.lm_order, d.lm_order_pose, d.lm_order_lm,
+                                                                    d.delta, w.tl, nullptr);
+            nl++;
+        }
+        k_lm_backsub<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.tl); nl++;
+    }
+    if (launches) *launches = nl;
+    return 0;
+}
+
+template int launch_dense_solve<double>(const Dev<double>&, DenseWork<double>&, double, cudaStream_t, int*);
+template int launch_dense_solve<float>(const Dev<float>&, DenseWork<float>&, double, cudaStream_t, int*);
+
+}  // namespace bos

@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (stated by the north star):
+  * sparsity pattern / edge-to-block indexing / landmark association: bit-exact
+  * FP64: H, b, chi2 within 1e-9 (block / column-norm relative); dx and states within 1e-8 relative
+    after one iteration and 1e-6 after 20 (rounding of two different factorisation orders amplified by
+    the conditioning of H, ~1e6 on the bundled data)
+  * FP32 path: H, b within 2e-4, states within 5e-3 after 10 iterations (documented, not a parity claim)
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import (angle_diff, csc_rel_err, golden_problem, load_golden, oracle_for, rel_block_err, synth_problem)
+from prb_project_bearing_only_slam_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+
+
+def make_ctx(pr, P, L, **opts):
+    ctx = capi.Context(**opts)
+    pr.upload(ctx)
+    ctx.set_state(P, L)
+    return ctx
+
+
+def golden_setup(name, dtype="f64"):
+    g = load_golden(name)
+    pr = golden_problem(g)
+    o = oracle_for(g["pose_ids"], g["poses_xyt"], pr, dtype)
+    return g, pr, o
+
+
+def align_wrap_branch(pr, o, eb_gpu, jb_orc):
+    """A bearing residual within rounding of +-pi may wrap either way (two-observation landmarks triangulated behind a
+    pose give exactly pi).  Returns the correction to the oracle's b that moves such edges onto the GPU's branch."""
+    eb_orc = o.edge_terms()[0]
+    amb = np.where((np.abs(np.abs(eb_orc) - np.pi) < 1e-9) & (np.sign(eb_orc) != np.sign(eb_gpu)))[0]
+    db = np.zeros(3 * pr.NP + 2 * pr.NL)
+    for e in amb:
+        om = 1.0 if pr.b_omega is None else pr.b_omega[e]
+        scale = lambda v: v * math.sqrt(1.0 / (v * om * v)) if v * om * v > 1.0 else v
+        de = scale(eb_gpu[e]) - scale(eb_orc[e])
+        p, l = pr.b_pose[e], pr.b_lm[e]
+        J = jb_orc[e].copy()
+        if p != pr.fixed_stix:
+            db[3 * p:3 * p + 3] += J[:3] * om * de
+        db[3 * pr.NP + 2 * l:3 * pr.NP + 2 * l + 2] += J[3:] * om * de
+    return db, amb
+
+
+def nofixed(pr, v):
+    keep = np.ones(len(v), bool)
+    keep[3 * pr.fixed_stix:3 * pr.fixed_stix + 3] = False
+    return v[keep]
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mini", "full"])
+def test_edge_terms_match_oracle(built_lib, name):
+    g, pr, o = golden_setup(name)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L)
+    o.linearize()
+    eb, jb, eo, jo = ctx.edge_terms()
+    oeb, ojb, oeo, ojo = o.edge_terms()
+    assert np.abs(angle_diff(eb, oeb)).max() <= 1e-12          # errors, modulo the +-pi branch
+    assert rel_block_err(jb, ojb) <= TOL64 and rel_block_err(jo, ojo) <= TOL64
+    assert np.abs(eo[:, :2] - oeo[:, :2]).max() <= 1e-12 and np.abs(angle_diff(eo[:, 2], oeo[:, 2])).max() <= 1e-12
+    # the golden fixture (generated in the build container) says the same
+    assert np.abs(angle_diff(eb, g["err_b_f64"])).max() <= 1e-12 and rel_block_err(jb, g["jac_b_f64"]) <= TOL64
+
+
+@pytest.mark.parametrize("name", ["mini", "full"])
+def test_pattern_and_H_b_chi2_match_oracle(built_lib, name):
+    g, pr, o = golden_setup(name)
+    P, L = o.state()
+    assert np.abs(L - g["lms_tri_f64"]).max() == 0.0
+    ctx = make_ctx(pr, P, L)
+    o.linearize()
+    ctx.linearize()
+    colptr, rowidx, val, b = ctx.csc()
+    ocol, orow, oval, ob = o.csc()
+    assert np.array_equal(colptr, ocol) and np.array_equal(rowidx, orow)                 # bit-exact pattern
+    assert np.array_equal(colptr, g["csc_colptr"]) and np.array_equal(rowidx, g["csc_rowidx"])
+    eb = ctx.edge_terms()[0]
+    db, amb = align_wrap_branch(pr, o, eb, o.edge_terms()[1])
+    ob = ob + nofixed(pr, db)
+    assert csc_rel_err(colptr, val, oval) <= TOL64
+    assert np.abs(b - ob).max() <= TOL64 * np.abs(ob).max()
+    st, os_ = ctx.stats(), o.stats()
+    assert st.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=TOL64)
+    assert st.chi2_odometry == pytest.approx(os_["chi2_odometry"], rel=1e-7, abs=1e-15)
+    assert (st.over_bearing, st.over_odometry) == (os_["over_bearing"], os_["over_odometry"])
+    if len(amb) == 0:
+        assert csc_rel_err(colptr, val, g["csc_val_f64"]) <= TOL64
+
+
+@pytest.mark.parametrize("name,solver", [("mini", capi.SOLVER_DENSE_CHOLESKY), ("full", capi.SOLVER_DENSE_CHOLESKY),
+                                         ("mini", capi.SOLVER_PCG), ("full", capi.SOLVER_PCG)])
+def test_solve_and_update_match_oracle(built_lib, name, solver):
+    g, pr, o = golden_setup(name)
+    # start two iterations in, where no residual sits on the +-pi branch cut
+    o.step(0); o.step(0)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L, solver=solver, pcg_rtol=1e-13, pcg_max_iters=20000)
+    o.linearize(); o.solve(0)
+    ctx.linearize(); ctx.solve()
+    d, od = ctx.delta(), o.delta()
+    assert np.all(d[3 * pr.fixed_stix:3 * pr.fixed_stix + 3] == 0.0)                      # gauge: the fixed pose does not move
+    assert np.abs(d - od).max() <= 1e-8 * np.abs(od).max()
+    # the solve really solves the GPU's own system: ||H dx + b|| small, checked with scipy on the downloaded CSC
+    import scipy.sparse as sp
+    colptr, rowidx, val, b = ctx.csc()
+    n = len(colptr) - 1
+    H = sp.csc_matrix((val, rowidx, colptr), shape=(n, n))
+    r = H @ nofixed(pr, d) + b
+    assert np.abs(r).max() <= 1e-9 * np.abs(b).max()
+    o.apply_boxplus(); ctx.update()
+    P2, L2 = ctx.get_state(); oP, oL = o.state()
+    assert np.abs(P2 - oP).max() <= 1e-9 * max(1.0, np.abs(oP).max()) and np.abs(L2 - oL).max() <= 1e-8 * max(1.0, np.abs(oL).max())
+    assert ctx.stats().delta_inf == pytest.approx(np.abs(od).max(), rel=1e-8)
+
+
+@pytest.mark.parametrize("name,iters", [("mini", 50), ("full", 20)])
+def test_gn_trajectory_matches_oracle(built_lib, name, iters):
+    g, pr, o = golden_setup(name)
+    o.step(0); o.step(0)                      # leave the +-pi branch cut of the triangulated start (see align_wrap_branch)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L)
+    for it in range(iters):
+        o.step(0)
+        s = ctx.step()
+        os_ = o.stats()
+        assert s.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=1e-7), it
+        assert s.chi2_odometry == pytest.approx(os_["chi2_odometry"], rel=1e-6, abs=1e-12), it
+        assert s.over_bearing == os_["over_bearing"] and s.solver_status == 0
+    P2, L2 = ctx.get_state(); oP, oL = o.state()
+    assert np.abs(P2 - oP).max() <= 1e-6 and np.abs(L2 - oL).max() <= 1e-6
+    # and the oracle's own fixture (from the triangulated start) agrees with where the reference converges
+    t = g["trajectory_f64"]
+    assert s.chi2_bearing == pytest.approx(t[-1, 0], rel=2e-3)
+
+
+def test_full_dataset_from_the_triangulated_start(built_lib):
+    """The reference's own call sequence (executables/bearing_only_slam.cpp:52-71, 95-98) end to end on the GPU:
+    triangulate on the device, then 30 iterations; converges to the chi2 the oracle converges to."""
+    g = load_golden("full")
+    pr = golden_problem(g)
+    ctx = capi.Context()
+    pr.upload(ctx)
+    ctx.set_state(g["poses_xycs"], None)
+    assert ctx.triangulate() == 3                                   # landmarks 69, 112, 114 (slam/triangulation.cpp:41)
+    _, L = ctx.get_state()
+    assert np.abs(L - g["lms_tri_f64"]).max() <= 1e-9 * np.abs(g["lms_tri_f64"]).max()
+    for it in range(30):
+        s = ctx.step()
+        if it == 0:
+            assert s.chi2_bearing == pytest.approx(g["trajectory_f64"][0, 0], rel=1e-9) and s.over_bearing == 10
+    t = g["trajectory_f64"]
+    assert s.chi2_bearing == pytest.approx(t[29, 0], rel=1e-3) and s.chi2_odometry == pytest.approx(t[29, 1], rel=1e-3)
+
+
+@pytest.mark.parametrize("name", ["mini", "full"])
+def test_triangulation_matches_oracle(built_lib, name):
+    g = load_golden(name)
+    pr = golden_problem(g)
+    ctx = capi.Context()
+    pr.upload(ctx)
+    ctx.set_state(g["poses_xycs"], None)
+    n1 = ctx.triangulate()
+    _, L = ctx.get_state()
+    assert n1 == len(g["single_obs_f64"])
+    assert np.abs(L - g["lms_tri_f64"]).max() <= 1e-9 * np.abs(g["lms_tri_f64"]).max()
+    # rank-1 landmarks: the non-pivot coordinate is exactly zero, as in Eigen's basic solution
+    for lid in g["single_obs_f64"]:
+        j = int(np.where(pr.lm_ids == lid)[0][0])
+        assert (L[j] == 0).sum() == 1 and (g["lms_tri_f64"][j] == 0).sum() == 1
+
+
+def test_step_host_equals_step_device(built_lib):
+    g, pr, o = golden_setup("full")
+    P, L = o.state()
+    a = make_ctx(pr, P, L)
+    b = make_ctx(pr, P, L)
+    Ph, Lh = P.copy(), L.copy()
+    for _ in range(3):
+        sa = a.step()
+        sb = b.step_host(Ph, Lh)
+        assert sa.chi2_bearing == pytest.approx(sb.chi2_bearing, rel=1e-12)
+    Pa, La = a.get_state()
+    assert np.abs(Pa - Ph).max() <= 1e-12 and np.abs(La - Lh).max() <= 1e-12
+    assert sa.gpu_launches > 0
+
+
+def test_setters_and_robust_kernel(built_lib):
+    g, pr, o = golden_setup("full")
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L)
+    for kt, df in ((0.05, 0.5), (1e9, 1e-3)):
+        o.set_params(kt, df); ctx.set_kernel_threshold(kt); ctx.set_damping_factor(df)
+        o.linearize(); ctx.linearize()
+        colptr, _, val, b = ctx.csc(); _, _, oval, ob = o.csc()
+        db, _ = align_wrap_branch(pr, o, ctx.edge_terms()[0], o.edge_terms()[1])
+        assert csc_rel_err(colptr, val, oval) <= TOL64
+        assert np.abs(b - (ob + nofixed(pr, db))).max() <= TOL64 * np.abs(ob).max()
+        assert ctx.stats().over_bearing == o.stats()["over_bearing"]
+
+
+def test_duplicate_blocks_isolated_nodes_and_other_fixed_pose(built_lib):
+    """Edge cases of the pattern: duplicate (pose, lm) pairs, repeated / reversed odometry pairs, a loop closure,
+    an edge-free pose, a fixed pose in the middle."""
+    rng = np.random.default_rng(11)
+    w, pr0 = synth_problem(60, 14, 500, seed=3)
+    from prb_project_bearing_only_slam_b200.problem import Problem
+    bp = np.concatenate([w["b_pose_id"], w["b_pose_id"][:7]]); bl = np.concatenate([w["b_lm_id"], w["b_lm_id"][:7]])
+    bz = np.concatenate([w["b_z"], w["b_z"][:7] + 0.01])
+    perm = rng.permutation(len(bz))                                             # unsorted edge order
+    src = np.concatenate([w["o_src_id"], [w["pose_ids"][40], w["pose_ids"][3], w["pose_ids"][9]]])
+    dst = np.concatenate([w["o_dst_id"], [w["pose_ids"][2], w["pose_ids"][2], w["pose_ids"][8]]])
+    oz = np.vstack([w["o_z"], rng.normal(size=(3, 3)) * 0.1]); oom = np.vstack([w["o_omega"], w["o_omega"][:3]])
+    oom[-1] = np.array([[400, 30, 5], [30, 600, -20], [5, -20, 4000.0]]).ravel()  # full symmetric Omega
+    pose_ids = np.concatenate([w["pose_ids"], [9999]]); xyt = np.vstack([w["poses_init"], [[3.0, 4.0, 0.5]]])  # edge-free pose
+    pr = Problem(pose_ids, bp[perm], bl[perm], bz[perm], src, dst, oz, oom, fixed_pose_id=int(w["pose_ids"][17]))
+    o = oracle_for(pose_ids, xyt, pr)
+    P, L = o.state()
+    for solver in (capi.SOLVER_DENSE_CHOLESKY, capi.SOLVER_PCG):
+        ctx = make_ctx(pr, P, L, solver=solver, pcg_rtol=1e-13)
+        o.set_state(P, L)
+        o.linearize(); ctx.linearize()
+        colptr, rowidx, val, b = ctx.csc(); ocol, orow, oval, ob = o.csc()
+        assert np.array_equal(colptr, ocol) and np.array_equal(rowidx, orow)
+        assert csc_rel_err(colptr, val, oval) <= TOL64 and np.abs(b - ob).max() <= TOL64 * np.abs(ob).max()
+        eb, jb, eo, jo = ctx.edge_terms(); oeb, ojb, oeo, ojo = o.edge_terms()
+        assert np.abs(angle_diff(eb, oeb)).max() <= 1e-12 and rel_block_err(jb, ojb) <= TOL64   # caller's edge order is kept
+        o.solve(0); ctx.solve()
+        d, od = ctx.delta(), o.delta()
+        assert np.abs(d - od).max() <= 1e-8 * np.abs(od).max()
+        assert np.all(d[3 * 17:3 * 17 + 3] == 0) and np.abs(d[3 * 60:3 * 60 + 3]).max() <= 1e-12 * np.abs(od).max() + 1e-300
+
+
+@pytest.mark.parametrize("solver", [capi.SOLVER_DENSE_CHOLESKY, capi.SOLVER_PCG])
+def test_synthetic_world_converges_like_oracle(built_lib, solver):
+    w, pr = synth_problem(600, 130, 6000, seed=21)
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L, solver=solver, pcg_rtol=1e-12)
+    Lg = ctx.get_state()[1]
+    chi = []
+    for it in range(8):
+        o.step(0)
+        s = ctx.step()
+        chi.append(s.chi2_bearing + s.chi2_odometry)
+        os_ = o.stats()
+        assert s.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=1e-6)
+        assert s.solver_used == solver
+    P2, L2 = ctx.get_state(); oP, oL = o.state()
+    assert np.abs(P2 - oP).max() <= 1e-6 and np.abs(L2 - oL).max() <= 1e-6
+    assert chi[-1] < chi[0]
+    # it converged towards the ground truth (up to the gauge): poses within a few cm of the true trajectory
+    err = np.hypot(P2[:, 0] - w["poses_true"][:, 0], P2[:, 1] - w["poses_true"][:, 1])
+    assert np.median(err) < 0.5
+
+
+def test_dense_cholesky_multi_panel_matches_pcg_and_oracle(built_lib):
+    """A reduced system wider than one 64-column panel per tile row exercises POTRF/TRSM/SYRK (DMMA) tiling."""
+    w, pr = synth_problem(150, 40, 1500, seed=8)       # n = 450 = 7 panels + a ragged one of 2
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr)
+    P, L = o.state()
+    o.linearize(); o.solve(0)
+    od = o.delta()
+    for solver in (capi.SOLVER_DENSE_CHOLESKY, capi.SOLVER_PCG):
+        ctx = make_ctx(pr, P, L, solver=solver, pcg_rtol=1e-13)
+        ctx.linearize(); ctx.solve()
+        assert np.abs(ctx.delta() - od).max() <= 1e-8 * np.abs(od).max(), solver
+
+
+def test_fp32_path_documented_tolerance(built_lib):
+    g = load_golden("full")
+    pr = golden_problem(g)
+    o = oracle_for(g["pose_ids"], g["poses_xyt"], pr, "f32")
+    o.step(0); o.step(0)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L, precision=capi.PRECISION_F32)
+    o.linearize(); ctx.linearize()
+    colptr, _, val, b = ctx.csc(); _, _, oval, ob = o.csc()
+    assert csc_rel_err(colptr, val, oval) <= 2e-4 and np.abs(b - ob).max() <= 2e-4 * np.abs(ob).max()
+    for _ in range(10):
+        o.step(0); s = ctx.step()
+    P2, L2 = ctx.get_state(); oP, oL = o.state()
+    assert np.abs(P2 - oP).max() <= 5e-3 and np.abs(L2 - oL).max() <= 5e-3
+    assert s.chi2_bearing == pytest.approx(o.stats()["chi2_bearing"], rel=5e-3)
+
+
+def test_batched_mini_problems_match_oracle(built_lib):
+    g = load_golden("mini")
+    pr = golden_problem(g)
+    nprob = 64
+    rng = np.random.default_rng(5)
+    o = oracle_for(g["pose_ids"], g["poses_xyt"], pr)
+    P0, L0 = o.state()
+    th = np.arctan2(P0[:, 3], P0[:, 2])
+    poses = np.zeros((nprob, pr.NP, 4)); lms = np.zeros((nprob, pr.NL, 2))
+    bz = np.zeros((nprob, pr.Eb)); oz = np.zeros((nprob, pr.Eo, 3))
+    for k in range(nprob):
+        t = th + rng.normal(size=pr.NP) * 0.01
+        poses[k, :, 0] = P0[:, 0] + rng.normal(size=pr.NP) * 0.05; poses[k, :, 1] = P0[:, 1] + rng.normal(size=pr.NP) * 0.05
+        poses[k, :, 2] = np.cos(t); poses[k, :, 3] = np.sin(t)
+        lms[k] = L0 + rng.normal(size=L0.shape) * 0.05
+        bz[k] = pr.b_z + rng.normal(size=pr.Eb) * 0.003; oz[k] = pr.o_z + rng.normal(size=pr.o_z.shape) * 0.01
+    B = capi.Batch(nprob, pr.NP, pr.NL, pr.fixed_stix, pr.b_pose, pr.b_lm, bz, None, pr.o_src, pr.o_dst, oz, pr.o_omega)
+    B.set_states(poses, lms)
+    chi, dinf, st = B.step()
+    Pg, Lg = B.get_states()
+    assert np.all(st == 0)
+    from oracle.oracle import Oracle
+    for k in (0, 1, 17, 63):
+        ok = Oracle("f64")
+        ok.set_problem(g["pose_ids"], g["poses_xyt"], g["b_pose_id"], g["b_lm_id"], bz[k], g["o_src_id"], g["o_dst_id"], oz[k],
+                       pr.o_omega, fixed_id=pr.fixed_pose_id, lm_ids=pr.lm_ids, lms_xy=lms[k])
+        ok.solver_init(pr.fixed_pose_id)
+        ok.set_state(poses[k], lms[k])
+        ok.step(0)
+        s = ok.stats(); oP, oL = ok.state()
+        assert chi[k, 0] == pytest.approx(s["chi2_bearing"], rel=1e-9) and chi[k, 1] == pytest.approx(s["chi2_odometry"], rel=1e-9)
+        assert np.abs(Pg[k] - oP).max() <= 1e-9 and np.abs(Lg[k] - oL).max() <= 1e-9
+        assert dinf[k] == pytest.approx(s["delta_inf"], rel=1e-7)
+
+
+def test_large_world_size_independent_properties(built_lib):
+    """At a size the oracle's dense solve cannot reach: linearization parity against the oracle's O(E) assembly,
+    the PCG solve checked by the residual of the GPU's own system, chi2 decreasing, dense == PCG."""
+    import scipy.sparse as sp
+    w, pr = synth_problem(20000, 4000, 200000, seed=77)
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-11, pcg_max_iters=20000)
+    assert np.abs(ctx.get_state()[1] - L).max() == 0
+    o.linearize(); ctx.linearize()
+    colptr, rowidx, val, b = ctx.csc(); ocol, orow, oval, ob = o.csc()
+    assert np.array_equal(colptr, ocol) and np.array_equal(rowidx, orow)
+    assert csc_rel_err(colptr, val, oval) <= TOL64 and np.abs(b - ob).max() <= TOL64 * np.abs(ob).max()
+    ctx.solve()
+    d = ctx.delta()
+    n = len(colptr) - 1
+    H = sp.csc_matrix((val, rowidx, colptr), shape=(n, n))
+    r = H @ nofixed(pr, d) + b
+    assert np.abs(r).max() <= 1e-8 * np.abs(b).max()
+    chi = []
+    for _ in range(4):
+        s = ctx.step(); chi.append(s.chi2_bearing + s.chi2_odometry)
+    assert chi[-1] < 0.5 * chi[0] and s.pcg_iterations > 0
