@@ -28,6 +28,12 @@ struct Dev {
     const S* o_z = nullptr;
     const S* o_om = nullptr;
     const int* o_slot = nullptr;
+    const int* oe_ptr = nullptr;     // [NP+1] odometry edges incident to a pose
+    const int* oe_edge = nullptr;    // [2*Eo] (edge << 1) | role, role 0: the pose is the edge's source, 1: its destination
+    const unsigned char* o_shared = nullptr;  // [Eo] 1 when the edge's pose pair is shared with another edge (needs RED + zero init)
+    int has_shared_off = 0;
+    int Eb_pad = 0;                  // bearing SoA arrays are padded to a multiple of 4 (omega = 0 in the padding)
+    int hpl_ld = 0;                  // plane stride of Hpl (multiple of 4)
     // CSR-of-blocks pattern
     const int* slot_pose = nullptr;  // [n_hpl]
     const int* slot_lm = nullptr;    // [n_hpl]
@@ -46,13 +52,13 @@ struct Dev {
     // state
     S* pose = nullptr;  // [NP][4] x,y,c,s
     S* lm = nullptr;    // [NL][2]
-    // value buffer  [ b (N) | Hpp (6 NP) | Hll (3 NL) | Hoff (9 n_off) | Hpl (6 n_hpl) ]
+    // value buffer  [ b (N) | Hpp (6 NP) | Hll (3 NL) | Hoff (9 n_off) | pad | Hpl (6 planes x hpl_ld) ]
     S* vals = nullptr;
     S* b = nullptr;
     S* Hpp = nullptr;   // xx xy xt yy yt tt
     S* Hll = nullptr;   // xx xy yy
     S* Hoff = nullptr;  // 3x3 row-major, block H[lo][hi]
-    S* Hpl = nullptr;   // 3x2 row-major
+    S* Hpl = nullptr;   // SoA: entry k (3x2 row-major index) of block s at Hpl[k * hpl_ld + s]
     double* stats = nullptr;  // [8] chi2_b, chi2_o, over_b, over_o, delta_inf(bits), status, -, -
     S* delta = nullptr;       // [N]
 };
@@ -64,7 +70,7 @@ struct ShardRange {
 // ---- launchers (one translation unit each) -------------------------------------------------------
 template <typename S>
 int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping_here,
-                     bool zero_hpl, int sm_count, cudaStream_t st);
+                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st);
 template <typename S>
 int launch_edge_terms(const Dev<S>& d, S* err_b, S* jac_b, S* err_o, S* jac_o, cudaStream_t st);
 template <typename S>
@@ -138,7 +144,9 @@ struct HostPattern {
     bool slots_identity = true;
     std::vector<int> slot_pose, slot_lm;    // unique (pose, lm) blocks, sorted
     std::vector<int> pose_ptr, lm_ptr, lm_order, lm_order_pose, lm_order_lm;
-    std::vector<int> o_src, o_dst, o_slot;
+    std::vector<int> o_src, o_dst, o_slot, oe_ptr, oe_edge;
+    std::vector<unsigned char> o_shared;
+    bool has_shared_off = false;
     std::vector<int> off_lo, off_hi;        // unique pose-pose blocks, sorted
     std::vector<int> pp_ptr, pp_nbr, pp_slot;
     std::vector<int> tri_ptr, tri_edge;

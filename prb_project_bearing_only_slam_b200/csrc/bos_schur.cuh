@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_lm_prep(Dev<S> d, S* __restrict__ hllin
 // equal landmark inside the warp, one RED per run head.  blocks: either a (lm, pose)-ordered copy (order
 // == nullptr) or the (pose, lm)-ordered Hpl gathered through `order`.
 template <typename S>
-__global__ void __launch_bounds__(256) k_lm_gather(int n_hpl, const S* __restrict__ blocks, const int* __restrict__ order,
+__global__ void __launch_bounds__(256) k_lm_gather(int n_hpl, const S* __restrict__ blocks, int ld, const int* __restrict__ order,
                                                    const int* __restrict__ k_pose, const int* __restrict__ k_lm,
                                                    const S* __restrict__ x, S* __restrict__ tl, const double* done) {
     if (done && *done != 0.0) return;
@@ -61,10 +61,10 @@ __global__ void __launch_bounds__(256) k_lm_gather(int n_hpl, const S* __restric
     if (valid) {
         l = __ldg(k_lm + k);
         const int p = __ldg(k_pose + k);
-        const S* B = blocks + 6LL * (order ? __ldg(order + k) : k);
+        const S* B = blocks + (order ? __ldg(order + k) : k);   // SoA planes, stride ld
         const S x0 = x[3LL * p], x1 = x[3LL * p + 1], x2 = x[3LL * p + 2];
-        v[0] = B[0] * x0 + B[2] * x1 + B[4] * x2;
-        v[1] = B[1] * x0 + B[3] * x1 + B[5] * x2;
+        v[0] = B[0] * x0 + B[2LL * ld] * x1 + B[4LL * ld] * x2;
+        v[1] = B[(long long)ld] * x0 + B[3LL * ld] * x1 + B[5LL * ld] * x2;
     }
     bool head;
     warp_run_reduce<S, 2>(v, l, lane, head);

@@ -139,7 +139,7 @@ std::vector<S> narrow(const double* src, size_t n) {
 }
 
 void shard_ranges(int64_t Eb, int64_t Eo, int r, int R, int64_t out[4], int64_t* chunk_b) {
-    const int64_t cb = (Eb + R - 1) / R, co = (Eo + R - 1) / R;
+    const int64_t cb = (((Eb + R - 1) / R) + 3) / 4 * 4, co = (Eo + R - 1) / R;  // bearing shards start on a multiple of 4 edges
     if (chunk_b) *chunk_b = cb;
     out[0] = std::min(Eb, r * cb); out[1] = std::min(Eb, (r + 1) * cb);
     out[2] = std::min(Eo, r * co); out[3] = std::min(Eo, (r + 1) * co);
@@ -160,12 +160,17 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     DevAlloc& m = c->mem;
     d.NP = P.NP; d.NL = P.NL; d.fixed = P.fixed; d.Eb = P.Eb; d.Eo = P.Eo; d.N = P.N;
     d.n_hpl = (int)P.slot_pose.size(); d.n_off = (int)P.off_lo.size();
-    // bearing SoA in sorted order
-    std::vector<S> bz(P.Eb), bom(P.Eb);
+    // bearing SoA in sorted order, padded to a multiple of 4 edges (the kernel reads 4 per thread); padding has omega = 0
+    d.Eb_pad = (P.Eb + 3) / 4 * 4 + 4;
+    d.hpl_ld = (d.n_hpl + 3) / 4 * 4 + 4 * 64;   // room for the padded in-place allgather of rank shards
+    std::vector<S> bz(d.Eb_pad, S(0)), bom(d.Eb_pad, S(0));
+    std::vector<int> bpose(d.Eb_pad, P.Eb ? P.b_pose[P.Eb - 1] : 0), blm(d.Eb_pad, 0), bslot(d.Eb_pad, 0);
     for (int k = 0; k < P.Eb; k++) {
         bz[k] = (S)b_z[P.b_perm[k]];
         bom[k] = b_omega ? (S)b_omega[P.b_perm[k]] : S(1);
+        bpose[k] = P.b_pose[k]; blm[k] = P.b_lm[k]; bslot[k] = P.b_slot[k];
     }
+    d.has_shared_off = P.has_shared_off ? 1 : 0;
     std::vector<S> oz((size_t)3 * P.Eo), oom((size_t)6 * P.Eo);
     static const int up[6] = {0, 1, 2, 4, 5, 8};
     for (int e = 0; e < P.Eo; e++) {
@@ -175,9 +180,10 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
 #define UP(field, vec)                                   \
     d.field = m.upload(vec);                             \
     if (!d.field) return fail(c, BOS_ERR_NOMEM, "device allocation failed: " #field);
-    UP(b_pose, P.b_pose) UP(b_lm, P.b_lm) UP(b_z, bz) UP(b_om, bom) UP(b_perm, P.b_perm)
-    if (!P.slots_identity) { UP(b_slot, P.b_slot) }
+    UP(b_pose, bpose) UP(b_lm, blm) UP(b_z, bz) UP(b_om, bom) UP(b_perm, P.b_perm)
+    if (!P.slots_identity) { UP(b_slot, bslot) }
     UP(o_src, P.o_src) UP(o_dst, P.o_dst) UP(o_z, oz) UP(o_om, oom) UP(o_slot, P.o_slot)
+    UP(oe_ptr, P.oe_ptr) UP(oe_edge, P.oe_edge) UP(o_shared, P.o_shared)
     UP(slot_pose, P.slot_pose) UP(slot_lm, P.slot_lm) UP(pose_ptr, P.pose_ptr) UP(lm_ptr, P.lm_ptr)
     UP(lm_order, P.lm_order) UP(lm_order_pose, P.lm_order_pose) UP(lm_order_lm, P.lm_order_lm)
     UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)
@@ -185,10 +191,9 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
 #undef UP
     d.pose = m.get<S>(4 * (size_t)P.NP);
     d.lm = m.get<S>(2 * (size_t)std::max(P.NL, 1));
-    c->vals_prefix = (size_t)P.N + 6 * (size_t)P.NP + 3 * (size_t)P.NL + 9 * (size_t)d.n_off;
-    c->vals_len = c->vals_prefix + 6 * (size_t)d.n_hpl;
-    // room for an in-place allgather of equally sized Hpl shards (up to 8 ranks, padded)
-    c->hpl_padded = 6 * ((size_t)d.n_hpl + 64);
+    c->vals_prefix = ((size_t)P.N + 6 * (size_t)P.NP + 3 * (size_t)P.NL + 9 * (size_t)d.n_off + 7) / 8 * 8;  // Hpl planes 32-byte aligned
+    c->hpl_padded = 6 * (size_t)d.hpl_ld;
+    c->vals_len = c->vals_prefix + c->hpl_padded;
     d.vals = m.get<S>(c->vals_prefix + c->hpl_padded);
     d.stats = m.get<double>(8);
     d.delta = m.get<S>((size_t)P.N);
@@ -198,7 +203,7 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     d.Hpp = d.b + P.N;
     d.Hll = d.Hpp + 6 * (size_t)P.NP;
     d.Hoff = d.Hll + 3 * (size_t)P.NL;
-    d.Hpl = d.Hoff + 9 * (size_t)d.n_off;
+    d.Hpl = d.vals + c->vals_prefix;
     CUDA_OK(c, cudaMemset(d.vals, 0, (c->vals_prefix + c->hpl_padded) * sizeof(S)));
     CUDA_OK(c, cudaMemset(d.delta, 0, (size_t)P.N * sizeof(S)));
     CUDA_OK(c, cudaMemset(d.stats, 0, 8 * sizeof(double)));
@@ -230,7 +235,7 @@ int ensure_pcg(bos_ctx* c) {
     PcgWork<S>& w = pwork<S>(c);
     const size_t n = 3 * (size_t)d.NP, nl = (size_t)std::max(d.NL, 1);
     w.hllinv = c->mem.get<S>(3 * nl); w.ul = c->mem.get<S>(2 * nl); w.tl = c->mem.get<S>(2 * nl);
-    w.Hlp = c->mem.get<S>(6 * (size_t)std::max(d.n_hpl, 1));
+    w.Hlp = c->mem.get<S>(6 * (size_t)std::max(d.hpl_ld, 4));
     w.minv = c->mem.get<S>(6 * (size_t)d.NP);
     w.x = c->mem.get<S>(n); w.r = c->mem.get<S>(n); w.z = c->mem.get<S>(n);
     w.p0 = c->mem.get<S>(n); w.y = c->mem.get<S>(n);
@@ -255,9 +260,10 @@ int allreduce_impl(bos_ctx* c) {
     int rc;
     if (c->reduce_mode == 1 && c->P.slots_identity) {
         rc = n.AllReduce(d.vals, d.vals, c->vals_prefix, dt, kNcclSum, c->comm, c->stream);
-        if (rc == 0) {
-            const size_t cnt = 6 * (size_t)c->shard_chunk_b;
-            rc = n.AllGather(d.Hpl + cnt * c->rank, d.Hpl, cnt, dt, c->comm, c->stream);
+        const size_t cnt = (size_t)c->shard_chunk_b;   // rank shards of every plane are equally sized (padded)
+        for (int k = 0; k < 6 && rc == 0; k++) {
+            S* plane = d.Hpl + (size_t)k * d.hpl_ld;
+            rc = n.AllGather(plane + cnt * c->rank, plane, cnt, dt, c->comm, c->stream);
         }
     } else {
         rc = n.AllReduce(d.vals, d.vals, c->vals_len, dt, kNcclSum, c->comm, c->stream);
@@ -272,8 +278,9 @@ int linearize_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const bool multi = c->nranks > 1;
     const bool zero_hpl = !c->P.slots_identity || (multi && !(c->reduce_mode == 1 && c->P.slots_identity));
+    const bool zero_hoff = multi || c->P.has_shared_off;
     const double damp_here = (c->rank == 0) ? c->opt.damping : 0.0;
-    c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, damp_here, zero_hpl, c->sm_count, c->stream);
+    c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream);
     CUDA_OK(c, cudaGetLastError());
     c->linearized = true; c->solved = false;
     return BOS_OK;
@@ -400,7 +407,7 @@ int download_blocks_impl(bos_ctx* c, double* Hpp, double* Hll, double* Hpl, doub
     const double* vpp = vb + d.N;
     const double* vll = vpp + 6 * (size_t)d.NP;
     const double* voff = vll + 3 * (size_t)d.NL;
-    const double* vpl = voff + 9 * (size_t)d.n_off;
+    const double* vpl = vals.data() + c->vals_prefix;
     if (b) std::copy(vb, vb + d.N, b);
     if (Hpp)
         for (int p = 0; p < d.NP; p++) {
@@ -415,7 +422,9 @@ int download_blocks_impl(bos_ctx* c, double* Hpp, double* Hll, double* Hpl, doub
             std::copy(m, m + 4, Hll + 4 * (size_t)l);
         }
     if (Hoff) std::copy(voff, voff + 9 * (size_t)d.n_off, Hoff);
-    if (Hpl) std::copy(vpl, vpl + 6 * (size_t)d.n_hpl, Hpl);
+    if (Hpl)
+        for (int s = 0; s < d.n_hpl; s++)
+            for (int k = 0; k < 6; k++) Hpl[6 * (size_t)s + k] = vpl[(size_t)k * d.hpl_ld + s];
     return BOS_OK;
 }
 

@@ -2,19 +2,21 @@
 //
 // Replaces the two per-edge loops and the damping of Solver::step (slam/solver.cpp:28-69) and
 // error_and_jacobian x2 (slam/solver_jacobians.cpp:9-168).  The reference merges an N x N sparse
-// temporary into H for every edge; here every edge adds straight into precomputed block slots:
+// temporary into H for every edge; here every edge adds straight into precomputed block slots.
 //
-//   K3  k_init_values      b = 0, diagonal blocks = damping * I (H += damping * I, solver.cpp:64-69),
-//                          pose-pose blocks = 0            (one coalesced pass over the value prefix)
-//   K1  k_linearize_bearing  edge-parallel over the (pose, landmark)-sorted SoA edge buffer:
-//        - pose-landmark 3x2 block: owned by the edge -> staged per warp in shared memory and written
-//          with coalesced stores (no atomics, no zero-init);
-//        - pose 3x3 diagonal block + b_pose: warp-segmented reduction over the run of edges of one
-//          pose, one RED per value per run head;
-//        - landmark 2x2 diagonal block + b_lm: RED per edge (landmark runs are scattered);
-//        - chi2 / over-threshold counts: warp + block reduction, one RED per CTA.
-//   K2  k_linearize_odometry  J_dst = -J_src entry for entry, so one 3x3 M = J_s^T Omega J_s and one
-//        3-vector serve the source block, the destination block and the off-diagonal block.
+//   K2+K3  k_pose_odometry_init   one thread per pose: damping * I (H += damping * I, solver.cpp:64-69) plus the
+//          contributions of the odometry edges incident to that pose, gathered through a CSR list and written
+//          with PLAIN stores (no atomics, no separate zero-init pass).  J_dst = -J_src entry for entry, so one
+//          M = J_s^T Omega J_s and one 3-vector serve the source block, the destination block and the
+//          off-diagonal block.  The same kernel resets the landmark blocks and b_lm.
+//   K1     k_linearize_bearing    edge-parallel over the (pose, landmark)-sorted SoA edge buffer, FOUR consecutive
+//          edges per thread (256-bit vector loads of the index / measurement / omega arrays):
+//          - pose-landmark 3x2 blocks: owned by the edge -> stored SoA (6 planes), each thread writes its four
+//            consecutive entries of a plane with one 256-bit store (no atomics, no zero-init);
+//          - pose 3x3 diagonal block + b_pose: accumulated in registers over the thread's run of equal poses,
+//            then a warp-segmented reduction over the lanes' runs, one RED per value per run head;
+//          - landmark 2x2 diagonal block + b_lm: RED per edge (a landmark's edges are scattered over the buffer);
+//          - chi2 / over-threshold counts: warp + block reduction, one RED per CTA.
 //
 // The fixed pose (gauge, solver.cpp:72-73) is handled by zeroing its Jacobian blocks at the source:
 // its rows/cols then hold only the damping and a zero rhs, which is the same linear system as
@@ -24,118 +26,246 @@
 
 namespace bos {
 
+// ---- 4-wide vector access: 256-bit for double (LDG/STG.E.ENL2.256 on sm_100a), 128-bit for float -----------
+__device__ __forceinline__ void load4(const double* p, double v[4]) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void load4(const float* p, float v[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const int* p, int v[4]) {
+    int4 t = __ldg(reinterpret_cast<const int4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void store4(double* p, const double v[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ---- K2 + K3 ---------------------------------------------------------------------------------------------------
 template <typename S>
-__global__ void __launch_bounds__(256) k_init_values(S* __restrict__ vals, int N, int NP, int NL, long long prefix_len,
-                                                     S damping, double* __restrict__ stats) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    if (i < 8) stats[i] = 0.0;
-    const long long hpp0 = N, hll0 = (long long)N + 6LL * NP, off0 = hll0 + 3LL * NL;
-    for (; i < prefix_len; i += stride) {
-        S v = S(0);
-        if (i >= hpp0 && i < hll0) {
-            int k = (int)((i - hpp0) % 6);
-            if (k == 0 || k == 3 || k == 5) v = damping;
-        } else if (i >= hll0 && i < off0) {
-            int k = (int)((i - hll0) % 3);
-            if (k == 0 || k == 2) v = damping;
+__global__ void __launch_bounds__(128) k_pose_odometry_init(Dev<S> d, int o_begin, int o_end, S kernel_threshold, S damping) {
+    __shared__ double red[2][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double chi_acc = 0.0;
+    int over_acc = 0;
+    if (i < d.NL) {
+        S* hl = d.Hll + 3LL * i;
+        hl[0] = damping; hl[1] = S(0); hl[2] = damping;
+        d.b[3LL * d.NP + 2LL * i] = S(0);
+        d.b[3LL * d.NP + 2LL * i + 1] = S(0);
+    }
+    if (i < d.NP) {
+        S h[6] = {damping, S(0), S(0), damping, S(0), damping};
+        S b[3] = {S(0), S(0), S(0)};
+        const size_t Eo = (size_t)d.Eo;
+        for (int q = d.oe_ptr[i]; q < d.oe_ptr[i + 1]; q++) {
+            const int code = __ldg(d.oe_edge + q);
+            const int e = code >> 1, role = code & 1;
+            if (e < o_begin || e >= o_end) continue;
+            const int s = __ldg(d.o_src + e), t = __ldg(d.o_dst + e);
+            const PoseV<S> Xs = load_pose<S>(d.pose, s), Xd = load_pose<S>(d.pose, t);
+            S om[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) om[k] = __ldg(d.o_om + k * Eo + e);
+            S err[3], u0, u1;
+            odometry_terms<S>(Xs, Xd, __ldg(d.o_z + e), __ldg(d.o_z + Eo + e), __ldg(d.o_z + 2 * Eo + e), err, u0, u1);
+            const S chi = odometry_chi<S>(om, err);
+            S scale = S(1);
+            const bool over = chi > kernel_threshold;
+            if (over) scale = sqrt(kernel_threshold / chi);   // scales the ERROR only (slam/solver.cpp:54-58)
+            S M[6], v[3];
+            odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, om, err, M, v, scale);
+            const bool fs = (s == d.fixed), ft = (t == d.fixed);
+            if (role == 0) {
+                chi_acc += (double)chi;
+                over_acc += over ? 1 : 0;
+                if (!fs) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) h[k] += M[k];
+                    b[0] += v[0]; b[1] += v[1]; b[2] += v[2];
+                }
+                // H[lo][hi] += J_lo^T Omega J_hi = -M (M symmetric, so the orientation does not matter)
+                S* ho = d.Hoff + 9LL * __ldg(d.o_slot + e);
+                const S z = (fs || ft) ? S(0) : S(1);
+                const S m9[9] = {-M[0] * z, -M[1] * z, -M[2] * z, -M[1] * z, -M[3] * z, -M[4] * z, -M[2] * z, -M[4] * z, -M[5] * z};
+                if (d.o_shared[e]) {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) red_add(ho + k, m9[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) ho[k] = m9[k];
+                }
+            } else if (!ft) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) h[k] += M[k];
+                b[0] -= v[0]; b[1] -= v[1]; b[2] -= v[2];
+            }
         }
-        vals[i] = v;
+        S* hp = d.Hpp + 6LL * i;
+#pragma unroll
+        for (int k = 0; k < 6; k++) hp[k] = h[k];
+        S* bp = d.b + 3LL * i;
+        bp[0] = b[0]; bp[1] = b[1]; bp[2] = b[2];
+    }
+    double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
+    if (lane == 0) { red[0][warp] = c; red[1][warp] = o; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cs = 0, os = 0;
+        for (int w = 0; w < 4; w++) { cs += red[0][w]; os += red[1][w]; }
+        if (cs != 0.0) atomicAdd(d.stats + 1, cs);
+        if (os != 0.0) atomicAdd(d.stats + 3, os);
     }
 }
 
+// ---- K1 ----------------------------------------------------------------------------------------------------------
 constexpr int kLinThreads = 256;
+constexpr int kEPT = 4;  // edges per thread
 
 template <typename S, bool kIdentSlots>
-__global__ void __launch_bounds__(kLinThreads) k_linearize_bearing(Dev<S> d, int e_begin, int e_end, S kernel_threshold) {
-    __shared__ S stage[kLinThreads / 32][6 * 32];
+__global__ void __launch_bounds__(kLinThreads, 2) k_linearize_bearing(Dev<S> d, int e_begin, int e_end, S kernel_threshold) {
     __shared__ double red[2][kLinThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double chi_acc = 0.0;
     int over_acc = 0;
-    const int n = e_end - e_begin;
-    const int ntiles = (n + kLinThreads - 1) / kLinThreads;
+    const int n = e_end - e_begin;  // e_begin is a multiple of 4
+    const int ntiles = (n + kLinThreads * kEPT - 1) / (kLinThreads * kEPT);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int e = e_begin + tile * kLinThreads + threadIdx.x;
-        const bool valid = e < e_end;
-        int p = -1 - lane, l = 0;
-        S J[5] = {S(0), S(0), S(0), S(0), S(0)};
-        S err = S(0), om = S(0);
-        if (valid) {
-            p = __ldg(d.b_pose + e);
-            l = __ldg(d.b_lm + e);
-            S z = __ldg(d.b_z + e);
-            om = __ldg(d.b_om + e);
-            PoseV<S> X = load_pose<S>(d.pose, p);
-            S lx, ly;
-            load_lm<S>(d.lm, l, lx, ly);
-            bearing_terms<S>(X, lx, ly, z, err, J);
-            // threshold robust kernel: scales the ERROR only (slam/solver.cpp:37-41)
-            S chi = err * om * err;
-            chi_acc += (double)chi;
-            if (chi > kernel_threshold) { err *= sqrt(kernel_threshold / chi); over_acc++; }
-            if (p == d.fixed) { J[0] = J[1] = J[2] = S(0); }
+        const int e0 = e_begin + (tile * kLinThreads + threadIdx.x) * kEPT;
+        const bool any = e0 < e_end;
+        int p4[4] = {-1, -1, -1, -1}, l4[4] = {0, 0, 0, 0};
+        S z4[4], om4[4];
+        if (any) {  // the SoA arrays are padded to a multiple of 4 edges
+            load4(d.b_pose + e0, p4);
+            load4(d.b_lm + e0, l4);
+            load4(d.b_z + e0, z4);
+            load4(d.b_om + e0, om4);
         }
-        const S w0 = J[0] * om, w1 = J[1] * om, w2 = J[2] * om;  // (J^T omega), pose part
-        const S w3 = J[3] * om, w4 = J[4] * om;                  // landmark part
-        // ---- pose-landmark 3x2 block -----------------------------------------------------------
-        if (kIdentSlots) {
-            S* sp = &stage[warp][lane * 6];
-            sp[0] = w0 * J[3]; sp[1] = w0 * J[4];
-            sp[2] = w1 * J[3]; sp[3] = w1 * J[4];
-            sp[4] = w2 * J[3]; sp[5] = w2 * J[4];
-            __syncwarp();
-            const long long base = 6LL * (e_begin + tile * kLinThreads + warp * 32);
-            const long long lim = 6LL * e_end;
+        S hpl[6][4];
+        S acc[9], head[9];
 #pragma unroll
-            for (int j = 0; j < 6; j++) {
-                long long gi = base + j * 32 + lane;
-                if (gi < lim) d.Hpl[gi] = stage[warp][j * 32 + lane];
+        for (int k = 0; k < 9; k++) { acc[k] = S(0); head[k] = S(0); }
+        int cur = any ? p4[0] : (-1 - lane);
+        int head_key = cur;
+        bool has_head = false;
+        PoseV<S> X = {S(0), S(0), S(1), S(0)};
+        int xpose = -1;
+#pragma unroll
+        for (int j = 0; j < kEPT; j++) {
+            const bool valid = any && (e0 + j < e_end);
+            S J[5] = {S(0), S(0), S(0), S(0), S(0)};
+            S err = S(0), om = S(0);
+            const int p = p4[j], l = l4[j];
+            if (valid) {
+                if (p != xpose) { X = load_pose<S>(d.pose, p); xpose = p; }
+                S lx, ly;
+                load_lm<S>(d.lm, l, lx, ly);
+                om = om4[j];
+                bearing_terms<S>(X, lx, ly, z4[j], err, J);
+                // threshold robust kernel: scales the ERROR only (slam/solver.cpp:37-41)
+                const S chi = err * om * err;
+                chi_acc += (double)chi;
+                if (chi > kernel_threshold) { err *= sqrt(kernel_threshold / chi); over_acc++; }
+                if (p == d.fixed) { J[0] = J[1] = J[2] = S(0); }
             }
-            __syncwarp();
-        } else if (valid) {
-            S* hp = d.Hpl + 6LL * __ldg(d.b_slot + e);
-            red_add(hp + 0, w0 * J[3]); red_add(hp + 1, w0 * J[4]);
-            red_add(hp + 2, w1 * J[3]); red_add(hp + 3, w1 * J[4]);
-            red_add(hp + 4, w2 * J[3]); red_add(hp + 5, w2 * J[4]);
+            const S w0 = J[0] * om, w1 = J[1] * om, w2 = J[2] * om;  // (J^T omega), pose part
+            const S w3 = J[3] * om, w4 = J[4] * om;                  // landmark part
+            hpl[0][j] = w0 * J[3]; hpl[1][j] = w0 * J[4];
+            hpl[2][j] = w1 * J[3]; hpl[3][j] = w1 * J[4];
+            hpl[4][j] = w2 * J[3]; hpl[5][j] = w2 * J[4];
+            if (valid) {
+                S* hl = d.Hll + 3LL * l;
+                red_add(hl + 0, w3 * J[3]);
+                red_add(hl + 1, w3 * J[4]);
+                red_add(hl + 2, w4 * J[4]);
+                S* bl = d.b + 3LL * d.NP + 2LL * l;
+                red_add(bl + 0, w3 * err);
+                red_add(bl + 1, w4 * err);
+                if (!kIdentSlots) {
+                    const long long s = __ldg(d.b_slot + e0 + j);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) red_add(d.Hpl + (long long)k * d.hpl_ld + s, hpl[k][j]);
+                }
+                // pose side: runs of equal pose inside the thread
+                if (p != cur) {
+                    if (!has_head) {
+                        has_head = true; head_key = cur;
+#pragma unroll
+                        for (int k = 0; k < 9; k++) head[k] = acc[k];
+                    } else if (cur != d.fixed) {  // a run that starts and ends inside this thread
+                        S* hp = d.Hpp + 6LL * cur;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) red_add(hp + k, acc[k]);
+                        S* bp = d.b + 3LL * cur;
+                        red_add(bp + 0, acc[6]); red_add(bp + 1, acc[7]); red_add(bp + 2, acc[8]);
+                    }
+                    cur = p;
+#pragma unroll
+                    for (int k = 0; k < 9; k++) acc[k] = S(0);
+                }
+                acc[0] += w0 * J[0]; acc[1] += w0 * J[1]; acc[2] += w0 * J[2];
+                acc[3] += w1 * J[1]; acc[4] += w1 * J[2]; acc[5] += w2 * J[2];
+                acc[6] += w0 * err; acc[7] += w1 * err; acc[8] += w2 * err;
+            }
         }
-        // ---- landmark 2x2 block and b_lm ----------------------------------------------------------
-        if (valid) {
-            S* hl = d.Hll + 3LL * l;
-            red_add(hl + 0, w3 * J[3]);
-            red_add(hl + 1, w3 * J[4]);
-            red_add(hl + 2, w4 * J[4]);
-            S* bl = d.b + 3LL * d.NP + 2LL * l;
-            red_add(bl + 0, w3 * err);
-            red_add(bl + 1, w4 * err);
+        // ---- pose-landmark blocks: plane k, four consecutive slots ------------------------------------------------
+        if (kIdentSlots && any) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) store4(d.Hpl + (long long)k * d.hpl_ld + e0, hpl[k]);
         }
-        // ---- pose 3x3 block and b_pose: segmented reduction over runs of equal pose ---------------
-        S v[9] = {w0 * J[0], w0 * J[1], w0 * J[2], w1 * J[1], w1 * J[2], w2 * J[2], w0 * err, w1 * err, w2 * err};
-        const int prev = __shfl_up_sync(BOS_FULL_MASK, p, 1);
-        const bool head = (lane == 0) || (prev != p);
-        const unsigned heads = __ballot_sync(BOS_FULL_MASK, head);
+        // ---- pose side across lanes ------------------------------------------------------------------------------------
+        // (1) a lane's head piece (its first pose, when the pose changes inside the lane) continues the previous
+        //     lane's last run: hand it down one lane when the keys agree, else emit it here.
+        const int prev_tail_key = __shfl_up_sync(BOS_FULL_MASK, cur, 1);
+        const int next_has_head = __shfl_down_sync(BOS_FULL_MASK, has_head ? 1 : 0, 1);
+        const int next_head_key = __shfl_down_sync(BOS_FULL_MASK, head_key, 1);
+        const bool take = (lane < 31) && next_has_head && (next_head_key == cur);
+        const bool any_head = __any_sync(BOS_FULL_MASK, has_head);
+        if (any_head) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const S t = __shfl_down_sync(BOS_FULL_MASK, head[k], 1);
+                if (take) acc[k] += t;
+            }
+            const bool given = (lane > 0) && (prev_tail_key == head_key);
+            if (has_head && !given && head_key != d.fixed && head_key >= 0) {
+                S* hp = d.Hpp + 6LL * head_key;
+#pragma unroll
+                for (int k = 0; k < 6; k++) red_add(hp + k, head[k]);
+                S* bp = d.b + 3LL * head_key;
+                red_add(bp + 0, head[6]); red_add(bp + 1, head[7]); red_add(bp + 2, head[8]);
+            }
+        }
+        // (2) segmented reduction of the lanes' last runs over lanes with equal key
+        const bool is_head = (lane == 0) || (prev_tail_key != cur);
+        const unsigned heads = __ballot_sync(BOS_FULL_MASK, is_head);
         const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
-        const int run_left = after ? __ffs(after) : (32 - lane);  // lanes from me to the end of my run, inclusive
+        const int run_left = after ? __ffs(after) : (32 - lane);
         const int max_run = __reduce_max_sync(BOS_FULL_MASK, run_left);
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             if (off < max_run) {
 #pragma unroll
                 for (int k = 0; k < 9; k++) {
-                    S t = __shfl_down_sync(BOS_FULL_MASK, v[k], off);
-                    if (off < run_left) v[k] += t;
+                    const S t = __shfl_down_sync(BOS_FULL_MASK, acc[k], off);
+                    if (off < run_left) acc[k] += t;
                 }
             }
         }
-        if (head && valid && p != d.fixed) {
-            S* hp = d.Hpp + 6LL * p;
+        if (is_head && any && cur != d.fixed && cur >= 0) {
+            S* hp = d.Hpp + 6LL * cur;
 #pragma unroll
-            for (int k = 0; k < 6; k++) red_add(hp + k, v[k]);
-            S* bp = d.b + 3LL * p;
-            red_add(bp + 0, v[6]); red_add(bp + 1, v[7]); red_add(bp + 2, v[8]);
+            for (int k = 0; k < 6; k++) red_add(hp + k, acc[k]);
+            S* bp = d.b + 3LL * cur;
+            red_add(bp + 0, acc[6]); red_add(bp + 1, acc[7]); red_add(bp + 2, acc[8]);
         }
     }
-    // ---- chi2 / over-threshold ------------------------------------------------------------------------
+    // ---- chi2 / over-threshold ------------------------------------------------------------------------------------------
     double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
     if (lane == 0) { red[0][warp] = c; red[1][warp] = o; }
     __syncthreads();
@@ -148,76 +278,21 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize_bearing(Dev<S> d, int
 }
 
 template <typename S>
-__global__ void __launch_bounds__(128) k_linearize_odometry(Dev<S> d, int e_begin, int e_end, S kernel_threshold) {
-    __shared__ double red[2][4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double chi_acc = 0.0;
-    int over_acc = 0;
-    for (int e = e_begin + blockIdx.x * blockDim.x + threadIdx.x; e < e_end; e += gridDim.x * blockDim.x) {
-        const int s = __ldg(d.o_src + e), t = __ldg(d.o_dst + e);
-        const PoseV<S> Xs = load_pose<S>(d.pose, s), Xd = load_pose<S>(d.pose, t);
-        const size_t Eo = (size_t)d.Eo;
-        S om[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) om[k] = __ldg(d.o_om + k * Eo + e);
-        S err[3], u0, u1;
-        odometry_terms<S>(Xs, Xd, __ldg(d.o_z + e), __ldg(d.o_z + Eo + e), __ldg(d.o_z + 2 * Eo + e), err, u0, u1);
-        S chi = odometry_chi<S>(om, err);
-        chi_acc += (double)chi;
-        S scale = S(1);
-        if (chi > kernel_threshold) { scale = sqrt(kernel_threshold / chi); over_acc++; }
-        S M[6], v[3];
-        odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, om, err, M, v, scale);
-        const bool fs = (s == d.fixed), ft = (t == d.fixed);
-        if (!fs) {
-            S* h = d.Hpp + 6LL * s;
-#pragma unroll
-            for (int k = 0; k < 6; k++) red_add(h + k, M[k]);
-            S* b = d.b + 3LL * s;
-            red_add(b + 0, v[0]); red_add(b + 1, v[1]); red_add(b + 2, v[2]);
-        }
-        if (!ft) {
-            S* h = d.Hpp + 6LL * t;
-#pragma unroll
-            for (int k = 0; k < 6; k++) red_add(h + k, M[k]);
-            S* b = d.b + 3LL * t;
-            red_add(b + 0, -v[0]); red_add(b + 1, -v[1]); red_add(b + 2, -v[2]);
-        }
-        if (!fs && !ft) {
-            // H[lo][hi] += J_lo^T Omega J_hi = -M (M symmetric, so the orientation does not matter)
-            S* h = d.Hoff + 9LL * __ldg(d.o_slot + e);
-            red_add(h + 0, -M[0]); red_add(h + 1, -M[1]); red_add(h + 2, -M[2]);
-            red_add(h + 3, -M[1]); red_add(h + 4, -M[3]); red_add(h + 5, -M[4]);
-            red_add(h + 6, -M[2]); red_add(h + 7, -M[4]); red_add(h + 8, -M[5]);
-        }
-    }
-    double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
-    if (lane == 0) { red[0][warp] = c; red[1][warp] = o; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double cs = 0, os = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { cs += red[0][w]; os += red[1][w]; }
-        if (cs != 0.0) atomicAdd(d.stats + 1, cs);
-        if (os != 0.0) atomicAdd(d.stats + 3, os);
-    }
-}
-
-template <typename S>
 int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping_here,
-                     bool zero_hpl, int sm_count, cudaStream_t st) {
+                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st) {
     int launches = 0;
-    long long prefix = (long long)d.N + 6LL * d.NP + 3LL * d.NL + 9LL * d.n_off;
-    if (zero_hpl) prefix += 6LL * d.n_hpl;
+    cudaMemsetAsync(d.stats, 0, 8 * sizeof(double), st);
+    if (zero_hoff && d.n_off > 0) cudaMemsetAsync(d.Hoff, 0, sizeof(S) * 9 * (size_t)d.n_off, st);
+    if (zero_hpl && d.n_hpl > 0) cudaMemsetAsync(d.Hpl, 0, sizeof(S) * 6 * (size_t)d.hpl_ld, st);
     {
-        long long blocks = (prefix + 255) / 256;
-        if (blocks > 148LL * 16) blocks = 148LL * 16;
-        if (blocks < 1) blocks = 1;
-        k_init_values<S><<<(unsigned)blocks, 256, 0, st>>>(d.vals, d.N, d.NP, d.NL, prefix, (S)damping_here, d.stats);
+        const int n = d.NP > d.NL ? d.NP : d.NL;
+        k_pose_odometry_init<S><<<(n + 127) / 128, 128, 0, st>>>(d, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here);
         launches++;
     }
     const int nb = r.b_end - r.b_begin;
     if (nb > 0) {
-        int tiles = (nb + kLinThreads - 1) / kLinThreads;
+        const int per_tile = kLinThreads * kEPT;
+        int tiles = (nb + per_tile - 1) / per_tile;
         int per_sm = 0;
         if (d.b_slot == nullptr) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize_bearing<S, true>, kLinThreads, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize_bearing<S, false>, kLinThreads, 0);
@@ -228,13 +303,6 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
             k_linearize_bearing<S, true><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold);
         else
             k_linearize_bearing<S, false><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold);
-        launches++;
-    }
-    const int no = r.o_end - r.o_begin;
-    if (no > 0) {
-        int grid = (no + 127) / 128;
-        if (grid > sm_count * 8) grid = sm_count * 8;
-        k_linearize_odometry<S><<<grid, 128, 0, st>>>(d, r.o_begin, r.o_end, (S)kernel_threshold);
         launches++;
     }
     return launches;
@@ -321,8 +389,8 @@ int launch_update(const Dev<S>& d, cudaStream_t st) {
     return 1;
 }
 
-template int launch_linearize<double>(const Dev<double>&, const ShardRange&, double, double, bool, int, cudaStream_t);
-template int launch_linearize<float>(const Dev<float>&, const ShardRange&, double, double, bool, int, cudaStream_t);
+template int launch_linearize<double>(const Dev<double>&, const ShardRange&, double, double, bool, bool, int, cudaStream_t);
+template int launch_linearize<float>(const Dev<float>&, const ShardRange&, double, double, bool, bool, int, cudaStream_t);
 template int launch_edge_terms<double>(const Dev<double>&, double*, double*, double*, double*, cudaStream_t);
 template int launch_edge_terms<float>(const Dev<float>&, float*, float*, float*, float*, cudaStream_t);
 template int launch_update<double>(const Dev<double>&, cudaStream_t);

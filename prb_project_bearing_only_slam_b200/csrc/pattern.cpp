@@ -89,6 +89,19 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
     for (int k = 0; k < n_off; k++) { P.off_lo[k] = (int)(uniq[k] >> 32); P.off_hi[k] = (int)(uniq[k] & 0xffffffffu); }
     P.o_slot.resize(Eo);
     for (int e = 0; e < Eo; e++) P.o_slot[e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), okey[e]) - uniq.begin());
+    {
+        std::vector<int> cnt(n_off, 0);
+        for (int e = 0; e < Eo; e++) cnt[P.o_slot[e]]++;
+        P.o_shared.resize(Eo);
+        for (int e = 0; e < Eo; e++) { P.o_shared[e] = cnt[P.o_slot[e]] > 1; P.has_shared_off |= cnt[P.o_slot[e]] > 1; }
+        // odometry edges incident to each pose (edge order inside a pose)
+        P.oe_ptr.assign(NP + 1, 0);
+        for (int e = 0; e < Eo; e++) { P.oe_ptr[o_src[e] + 1]++; P.oe_ptr[o_dst[e] + 1]++; }
+        for (int i = 0; i < NP; i++) P.oe_ptr[i + 1] += P.oe_ptr[i];
+        P.oe_edge.resize(2 * (size_t)Eo);
+        std::vector<int> cur(P.oe_ptr.begin(), P.oe_ptr.end() - 1);
+        for (int e = 0; e < Eo; e++) { P.oe_edge[cur[o_src[e]]++] = (e << 1); P.oe_edge[cur[o_dst[e]]++] = (e << 1) | 1; }
+    }
     // pose-pose adjacency, neighbours ascending
     P.pp_ptr.assign(NP + 1, 0);
     for (int k = 0; k < n_off; k++) { P.pp_ptr[P.off_lo[k] + 1]++; P.pp_ptr[P.off_hi[k] + 1]++; }

@@ -50,11 +50,12 @@ __global__ void __launch_bounds__(256) k_dense_schur(Dev<S> d, const S* __restri
     const S i00 = hllinv[3LL * l], i01 = hllinv[3LL * l + 1], i11 = hllinv[3LL * l + 2];
     const S u0 = ul[2LL * l], u1 = ul[2LL * l + 1];
     for (int i = lane; i < m; i += 32) {
-        const S* B = d.Hpl + 6LL * d.lm_order[k0 + i];
+        const S* B = d.Hpl + d.lm_order[k0 + i];
+        const long long ld = d.hpl_ld;
         const int p = d.lm_order_pose[k0 + i];
-        red_add(g + 3 * p + 0, B[0] * u0 + B[1] * u1);
-        red_add(g + 3 * p + 1, B[2] * u0 + B[3] * u1);
-        red_add(g + 3 * p + 2, B[4] * u0 + B[5] * u1);
+        red_add(g + 3 * p + 0, B[0] * u0 + B[ld] * u1);
+        red_add(g + 3 * p + 1, B[2 * ld] * u0 + B[3 * ld] * u1);
+        red_add(g + 3 * p + 2, B[4 * ld] * u0 + B[5 * ld] * u1);
     }
     const long long npairs = (long long)m * (m + 1) / 2;
     for (long long idx = lane; idx < npairs; idx += 32) {
@@ -62,16 +63,17 @@ __global__ void __launch_bounds__(256) k_dense_schur(Dev<S> d, const S* __restri
         while ((long long)i * (i + 1) / 2 > idx) i--;
         while ((long long)(i + 1) * (i + 2) / 2 <= idx) i++;
         const int j = (int)(idx - (long long)i * (i + 1) / 2);
-        const S* Bi = d.Hpl + 6LL * d.lm_order[k0 + i];
-        const S* Bj = d.Hpl + 6LL * d.lm_order[k0 + j];
+        const S* Bi = d.Hpl + d.lm_order[k0 + i];
+        const S* Bj = d.Hpl + d.lm_order[k0 + j];
+        const long long ld = d.hpl_ld;
         const int pi = d.lm_order_pose[k0 + i], pj = d.lm_order_pose[k0 + j];  // ascending pose inside a landmark: pi >= pj
-        S bj[6];
+        S bi[6], bj[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) bj[k] = Bj[k];
+        for (int k = 0; k < 6; k++) { bi[k] = Bi[k * ld]; bj[k] = Bj[k * ld]; }
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            const S ya0 = Bi[2 * a] * i00 + Bi[2 * a + 1] * i01;
-            const S ya1 = Bi[2 * a] * i01 + Bi[2 * a + 1] * i11;
+            const S ya0 = bi[2 * a] * i00 + bi[2 * a + 1] * i01;
+            const S ya1 = bi[2 * a] * i01 + bi[2 * a + 1] * i11;
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 if (i == j && c > a) continue;  // diagonal block: lower part only
@@ -354,7 +356,7 @@ int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStr
     if (d.NL > 0) {
         cudaMemsetAsync(w.tl, 0, sizeof(S) * 2 * (size_t)d.NL, st);
         if (d.n_hpl > 0) {
-            k_lm_gather<S><<<(d.n_hpl + 255) / 256, 256, 0, st>>>(d.n_hpl, d.Hpl, d.lm_order, d.lm_order_pose, d.lm_order_lm,
+            k_lm_gather<S><<<(d.n_hpl + 255) / 256, 256, 0, st>>>(d.n_hpl, d.Hpl, d.hpl_ld, d.lm_order, d.lm_order_pose, d.lm_order_lm,
                                                                     d.delta, w.tl, nullptr);
             nl++;
         }

@@ -29,11 +29,12 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
 
 // (lm, pose)-ordered copy of the pose-landmark blocks, refreshed once per GN iteration
 template <typename S>
-__global__ void __launch_bounds__(256) k_copy_hlp(int n_hpl, const S* __restrict__ Hpl, const int* __restrict__ order, S* __restrict__ Hlp) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 6LL * n_hpl) return;
-    const int k = (int)(i / 6), c = (int)(i % 6);
-    Hlp[i] = Hpl[6LL * __ldg(order + k) + c];
+__global__ void __launch_bounds__(256) k_copy_hlp(int n_hpl, int ld, const S* __restrict__ Hpl, const int* __restrict__ order, S* __restrict__ Hlp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_hpl) return;
+    const int s = __ldg(order + k);
+#pragma unroll
+    for (int c = 0; c < 6; c++) Hlp[(long long)c * ld + k] = Hpl[(long long)c * ld + s];
 }
 
 // one thread per pose: reduced rhs, diagonal block of S, its inverse, and the PCG start vectors
@@ -48,13 +49,13 @@ __global__ void __launch_bounds__(256) k_pcg_pose_prep(Dev<S> d, PcgWork<S> w) {
 #pragma unroll
         for (int k = 0; k < 6; k++) sd[k] = d.Hpp[6LL * p + k];
         for (int s = d.pose_ptr[p]; s < d.pose_ptr[p + 1]; s++) {
-            const S* B = d.Hpl + 6LL * s;
+            const S* B = d.Hpl + s;
             const int l = d.slot_lm[s];
             const S i00 = w.hllinv[3LL * l], i01 = w.hllinv[3LL * l + 1], i11 = w.hllinv[3LL * l + 2];
             const S u0 = w.ul[2LL * l], u1 = w.ul[2LL * l + 1];
             S b[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) b[k] = B[k];
+            for (int k = 0; k < 6; k++) b[k] = B[(long long)k * d.hpl_ld];
             S y[6];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
@@ -140,10 +141,11 @@ __global__ void __launch_bounds__(256) k_pcg_pose_scatter(Dev<S> d, PcgWork<S> w
         const S t0 = w.tl[2LL * l], t1 = w.tl[2LL * l + 1];
         const S i00 = w.hllinv[3LL * l], i01 = w.hllinv[3LL * l + 1], i11 = w.hllinv[3LL * l + 2];
         const S u0 = i00 * t0 + i01 * t1, u1 = i01 * t0 + i11 * t1;
-        const S* B = d.Hpl + 6LL * s;
-        v[0] = -(B[0] * u0 + B[1] * u1);
-        v[1] = -(B[2] * u0 + B[3] * u1);
-        v[2] = -(B[4] * u0 + B[5] * u1);
+        const S* B = d.Hpl + s;
+        const long long ld = d.hpl_ld;
+        v[0] = -(B[0] * u0 + B[ld] * u1);
+        v[1] = -(B[2 * ld] * u0 + B[3 * ld] * u1);
+        v[2] = -(B[4 * ld] * u0 + B[5 * ld] * u1);
     }
     bool head;
     warp_run_reduce<S, 3>(v, p, lane, head);
@@ -228,7 +230,7 @@ int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), st);
     if (d.NL > 0) { k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++; }
     if (d.n_hpl > 0) {
-        k_copy_hlp<S><<<(unsigned)((6LL * d.n_hpl + 255) / 256), 256, 0, st>>>(d.n_hpl, d.Hpl, d.lm_order, w.Hlp);
+        k_copy_hlp<S><<<gh, 256, 0, st>>>(d.n_hpl, d.hpl_ld, d.Hpl, d.lm_order, w.Hlp);
         nl++;
     }
     k_pcg_pose_prep<S><<<gp, 256, 0, st>>>(d, w); nl++;
@@ -243,7 +245,7 @@ int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
             const int parity = it & 1;
             k_pcg_y_init<S><<<gp, 256, 0, st>>>(d, w, parity);
             if (d.n_hpl > 0) {
-                k_lm_gather<S><<<gh, 256, 0, st>>>(d.n_hpl, w.Hlp, nullptr, d.lm_order_pose, d.lm_order_lm, w.p0, w.tl, w.scal + SC_DONE);
+                k_lm_gather<S><<<gh, 256, 0, st>>>(d.n_hpl, w.Hlp, d.hpl_ld, nullptr, d.lm_order_pose, d.lm_order_lm, w.p0, w.tl, w.scal + SC_DONE);
                 k_pcg_pose_scatter<S><<<gh, 256, 0, st>>>(d, w);
                 nl += 2;
             }
@@ -267,7 +269,7 @@ int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     if (d.NL > 0) {
         cudaMemsetAsync(w.tl, 0, sizeof(S) * 2 * (size_t)d.NL, st);
         if (d.n_hpl > 0) {
-            k_lm_gather<S><<<gh, 256, 0, st>>>(d.n_hpl, w.Hlp, nullptr, d.lm_order_pose, d.lm_order_lm, w.x, w.tl, nullptr);
+            k_lm_gather<S><<<gh, 256, 0, st>>>(d.n_hpl, w.Hlp, d.hpl_ld, nullptr, d.lm_order_pose, d.lm_order_lm, w.x, w.tl, nullptr);
             nl++;
         }
         k_lm_backsub<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.tl); nl++;
