@@ -37,7 +37,21 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, ptxas_info=False):
+def build(force=False, verbose=False, ptxas_info=False, extra_flags=None, out=None, objdir=None):
+    """extra_flags / out / objdir build an experimental variant (e.g. -DBOS_EPT=4) beside the default library."""
+    global OBJ, LIB
+    saved = (OBJ, LIB)
+    if objdir:
+        OBJ = objdir
+    if out:
+        LIB = out
+    try:
+        return _build(force, verbose, ptxas_info, list(extra_flags or []))
+    finally:
+        OBJ, LIB = saved
+
+
+def _build(force, verbose, ptxas_info, extra_flags):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
@@ -47,7 +61,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         o = os.path.join(OBJ, src + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-x", "cu", "-c", s, "-o", o]
+            cmd = [nvcc()] + NVCC_FLAGS + extra_flags + (["-Xptxas", "-v"] if ptxas_info else []) + ["-x", "cu", "-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbos_b200.so")
+LIB_PATH = os.environ.get("BOS_LIB_PATH") or os.path.join(_HERE, "libbos_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_NOMEM = range(6)
 PRECISION_F64, PRECISION_F32 = 0, 1

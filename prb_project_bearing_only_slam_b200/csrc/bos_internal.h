@@ -10,6 +10,10 @@
 
 namespace bos {
 
+// bearing edges are linearized in tiles of this many (pose, landmark)-sorted edges; the landmark-side sums of a tile
+// are aggregated in shared memory through a host-precomputed tile-local grouping before they touch global memory
+constexpr int kLinTile = 512;
+
 // Typed view of everything a kernel needs.  One instance per context, built after upload.
 template <typename S>
 struct Dev {
@@ -30,6 +34,7 @@ struct Dev {
     const int* o_slot = nullptr;
     const int* oe_ptr = nullptr;     // [NP+1] odometry edges incident to a pose
     const int* oe_edge = nullptr;    // [2*Eo] (edge << 1) | role, role 0: the pose is the edge's source, 1: its destination
+    const int* oe_other = nullptr;   // [2*Eo] the pose at the other end of that edge
     const unsigned char* o_shared = nullptr;  // [Eo] 1 when the edge's pose pair is shared with another edge (needs RED + zero init)
     int has_shared_off = 0;
     int Eb_pad = 0;                  // bearing SoA arrays are padded to a multiple of 4 (omega = 0 in the padding)
@@ -47,6 +52,10 @@ struct Dev {
     const int* pp_slot = nullptr;    // [2*n_off] slot; bit 31 set when this pose is the 'hi' side (use the transpose)
     const int* off_lo = nullptr;     // [n_off] block row pose of Hoff[k]
     const int* off_hi = nullptr;     // [n_off] block column pose
+    const int* tile_ptr = nullptr;   // [ntiles+1] groups (distinct landmarks) of each tile
+    const int* tg_lm = nullptr;      // [n_groups] landmark of the group
+    const int* tg_eptr = nullptr;    // [n_groups+1] into tg_edge
+    const unsigned short* tg_edge = nullptr;  // [Eb] tile-local edge index
     const int* tri_ptr = nullptr;    // [NL+1] bearing edges grouped by landmark (caller order inside a landmark)
     const int* tri_edge = nullptr;   // [Eb] sorted-edge index
     // state
@@ -144,12 +153,14 @@ struct HostPattern {
     bool slots_identity = true;
     std::vector<int> slot_pose, slot_lm;    // unique (pose, lm) blocks, sorted
     std::vector<int> pose_ptr, lm_ptr, lm_order, lm_order_pose, lm_order_lm;
-    std::vector<int> o_src, o_dst, o_slot, oe_ptr, oe_edge;
+    std::vector<int> o_src, o_dst, o_slot, oe_ptr, oe_edge, oe_other;
     std::vector<unsigned char> o_shared;
     bool has_shared_off = false;
     std::vector<int> off_lo, off_hi;        // unique pose-pose blocks, sorted
     std::vector<int> pp_ptr, pp_nbr, pp_slot;
     std::vector<int> tri_ptr, tri_edge;
+    std::vector<int> tile_ptr, tg_lm, tg_eptr;
+    std::vector<unsigned short> tg_edge;
     std::vector<char> touched;              // [NP + NL]
     // scalar CSC pattern of H_nofixed (slam/solver.cpp:72-75)
     std::vector<int> csc_colptr, csc_rowidx;

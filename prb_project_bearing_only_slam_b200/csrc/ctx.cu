@@ -139,7 +139,7 @@ std::vector<S> narrow(const double* src, size_t n) {
 }
 
 void shard_ranges(int64_t Eb, int64_t Eo, int r, int R, int64_t out[4], int64_t* chunk_b) {
-    const int64_t cb = (((Eb + R - 1) / R) + 3) / 4 * 4, co = (Eo + R - 1) / R;  // bearing shards start on a multiple of 4 edges
+    const int64_t cb = (((Eb + R - 1) / R) + kLinTile - 1) / kLinTile * kLinTile, co = (Eo + R - 1) / R;  // bearing shards are whole tiles
     if (chunk_b) *chunk_b = cb;
     out[0] = std::min(Eb, r * cb); out[1] = std::min(Eb, (r + 1) * cb);
     out[2] = std::min(Eo, r * co); out[3] = std::min(Eo, (r + 1) * co);
@@ -162,7 +162,7 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     d.n_hpl = (int)P.slot_pose.size(); d.n_off = (int)P.off_lo.size();
     // bearing SoA in sorted order, padded to a multiple of 4 edges (the kernel reads 4 per thread); padding has omega = 0
     d.Eb_pad = (P.Eb + 3) / 4 * 4 + 4;
-    d.hpl_ld = (d.n_hpl + 3) / 4 * 4 + 4 * 64;   // room for the padded in-place allgather of rank shards
+    d.hpl_ld = (d.n_hpl + 3) / 4 * 4 + 8 * kLinTile;   // room for up to 8 tile-padded rank shards   // room for the padded in-place allgather of rank shards
     std::vector<S> bz(d.Eb_pad, S(0)), bom(d.Eb_pad, S(0));
     std::vector<int> bpose(d.Eb_pad, P.Eb ? P.b_pose[P.Eb - 1] : 0), blm(d.Eb_pad, 0), bslot(d.Eb_pad, 0);
     for (int k = 0; k < P.Eb; k++) {
@@ -183,11 +183,12 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(b_pose, bpose) UP(b_lm, blm) UP(b_z, bz) UP(b_om, bom) UP(b_perm, P.b_perm)
     if (!P.slots_identity) { UP(b_slot, bslot) }
     UP(o_src, P.o_src) UP(o_dst, P.o_dst) UP(o_z, oz) UP(o_om, oom) UP(o_slot, P.o_slot)
-    UP(oe_ptr, P.oe_ptr) UP(oe_edge, P.oe_edge) UP(o_shared, P.o_shared)
+    UP(oe_ptr, P.oe_ptr) UP(oe_edge, P.oe_edge) UP(oe_other, P.oe_other) UP(o_shared, P.o_shared)
     UP(slot_pose, P.slot_pose) UP(slot_lm, P.slot_lm) UP(pose_ptr, P.pose_ptr) UP(lm_ptr, P.lm_ptr)
     UP(lm_order, P.lm_order) UP(lm_order_pose, P.lm_order_pose) UP(lm_order_lm, P.lm_order_lm)
     UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)
     UP(tri_ptr, P.tri_ptr) UP(tri_edge, P.tri_edge)
+    UP(tile_ptr, P.tile_ptr) UP(tg_lm, P.tg_lm) UP(tg_eptr, P.tg_eptr) UP(tg_edge, P.tg_edge)
 #undef UP
     d.pose = m.get<S>(4 * (size_t)P.NP);
     d.lm = m.get<S>(2 * (size_t)std::max(P.NL, 1));
@@ -258,7 +259,7 @@ int allreduce_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const int dt = sizeof(S) == 8 ? kNcclFloat64 : kNcclFloat32;
     int rc;
-    if (c->reduce_mode == 1 && c->P.slots_identity) {
+    if (c->reduce_mode == 1 && c->P.slots_identity && c->nranks <= 8) {
         rc = n.AllReduce(d.vals, d.vals, c->vals_prefix, dt, kNcclSum, c->comm, c->stream);
         const size_t cnt = (size_t)c->shard_chunk_b;   // rank shards of every plane are equally sized (padded)
         for (int k = 0; k < 6 && rc == 0; k++) {
@@ -277,7 +278,7 @@ template <typename S>
 int linearize_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const bool multi = c->nranks > 1;
-    const bool zero_hpl = !c->P.slots_identity || (multi && !(c->reduce_mode == 1 && c->P.slots_identity));
+    const bool zero_hpl = !c->P.slots_identity || (multi && !(c->reduce_mode == 1 && c->P.slots_identity && c->nranks <= 8));
     const bool zero_hoff = multi || c->P.has_shared_off;
     const double damp_here = (c->rank == 0) ? c->opt.damping : 0.0;
     c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream);

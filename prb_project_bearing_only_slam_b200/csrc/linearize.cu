@@ -24,6 +24,8 @@
 #include "bos_internal.h"
 #include "bos_math.cuh"
 
+#include <cstdlib>
+
 namespace bos {
 
 // ---- 4-wide vector access: 256-bit for double (LDG/STG.E.ENL2.256 on sm_100a), 128-bit for float -----------
@@ -45,9 +47,22 @@ __device__ __forceinline__ void store4(float* p, const float v[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// 2-wide flavours (128-bit for double)
+__device__ __forceinline__ void load2(const double* p, double v[2]) { double2 t = __ldg(reinterpret_cast<const double2*>(p)); v[0] = t.x; v[1] = t.y; }
+__device__ __forceinline__ void load2(const float* p, float v[2]) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
+__device__ __forceinline__ void load2(const int* p, int v[2]) { int2 t = __ldg(reinterpret_cast<const int2*>(p)); v[0] = t.x; v[1] = t.y; }
+__device__ __forceinline__ void store2(double* p, const double v[2]) { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+__device__ __forceinline__ void store2(float* p, const float v[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+template <int N, typename T> __device__ __forceinline__ void loadN(const T* p, T* v) {
+    if constexpr (N == 4) load4(p, v); else if constexpr (N == 2) load2(p, v); else v[0] = __ldg(p);
+}
+template <int N, typename T> __device__ __forceinline__ void storeN(T* p, const T* v) {
+    if constexpr (N == 4) store4(p, v); else if constexpr (N == 2) store2(p, v); else p[0] = v[0];
+}
+
 // ---- K2 + K3 ---------------------------------------------------------------------------------------------------
 template <typename S>
-__global__ void __launch_bounds__(128) k_pose_odometry_init(Dev<S> d, int o_begin, int o_end, S kernel_threshold, S damping) {
+__global__ void __launch_bounds__(128, 8) k_pose_odometry_init(Dev<S> d, int o_begin, int o_end, S kernel_threshold, S damping) {
     __shared__ double red[2][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,12 +78,16 @@ __global__ void __launch_bounds__(128) k_pose_odometry_init(Dev<S> d, int o_begi
         S h[6] = {damping, S(0), S(0), damping, S(0), damping};
         S b[3] = {S(0), S(0), S(0)};
         const size_t Eo = (size_t)d.Eo;
-        for (int q = d.oe_ptr[i]; q < d.oe_ptr[i + 1]; q++) {
+        const PoseV<S> Xi = load_pose<S>(d.pose, i);
+        const int q0 = __ldg(d.oe_ptr + i), q1 = __ldg(d.oe_ptr + i + 1);
+        for (int q = q0; q < q1; q++) {
             const int code = __ldg(d.oe_edge + q);
+            const int other = __ldg(d.oe_other + q);
             const int e = code >> 1, role = code & 1;
             if (e < o_begin || e >= o_end) continue;
-            const int s = __ldg(d.o_src + e), t = __ldg(d.o_dst + e);
-            const PoseV<S> Xs = load_pose<S>(d.pose, s), Xd = load_pose<S>(d.pose, t);
+            const PoseV<S> Xo = load_pose<S>(d.pose, other);
+            const int s = role ? other : i, t = role ? i : other;
+            const PoseV<S> Xs = role ? Xo : Xi, Xd = role ? Xi : Xo;
             S om[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) om[k] = __ldg(d.o_om + k * Eo + e);
@@ -125,28 +144,50 @@ __global__ void __launch_bounds__(128) k_pose_odometry_init(Dev<S> d, int o_begi
 
 // ---- K1 ----------------------------------------------------------------------------------------------------------
 constexpr int kLinThreads = 256;
-constexpr int kEPT = 4;  // edges per thread
+#ifndef BOS_EPT
+#define BOS_EPT 2
+#endif
+#ifndef BOS_LIN_MINBLOCKS
+#define BOS_LIN_MINBLOCKS 3
+#endif
+constexpr int kEPT = BOS_EPT;  // consecutive edges per thread
+static_assert(kLinThreads * kEPT == kLinTile, "one CTA iteration covers exactly one tile");
 
 template <typename S, bool kIdentSlots>
-__global__ void __launch_bounds__(kLinThreads, 2) k_linearize_bearing(Dev<S> d, int e_begin, int e_end, S kernel_threshold) {
+__global__ void __launch_bounds__(kLinThreads, BOS_LIN_MINBLOCKS) k_linearize_bearing(Dev<S> d, int e_begin, int e_end, S kernel_threshold, int dbg) {
     __shared__ double red[2][kLinThreads / 32];
+    __shared__ S sl[5][kLinTile];   // landmark-side terms of the tile: Hll xx, xy, yy and b_l x, y per edge
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double chi_acc = 0.0;
     int over_acc = 0;
-    const int n = e_end - e_begin;  // e_begin is a multiple of 4
+    const int n = e_end - e_begin;  // e_begin is a multiple of the tile size
     const int ntiles = (n + kLinThreads * kEPT - 1) / (kLinThreads * kEPT);
+    // software pipeline: the next tile's index / measurement vectors are in flight while this tile computes
+    int np4[kEPT], nl4[kEPT];
+    S nz4[kEPT], nom4[kEPT];
+    {
+        const int e0 = e_begin + (blockIdx.x * kLinThreads + threadIdx.x) * kEPT;
+        if (blockIdx.x < ntiles && e0 < e_end) {  // the SoA arrays are padded to a multiple of 4 edges
+            loadN<kEPT>(d.b_pose + e0, np4); loadN<kEPT>(d.b_lm + e0, nl4);
+            loadN<kEPT>(d.b_z + e0, nz4); loadN<kEPT>(d.b_om + e0, nom4);
+        }
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int e0 = e_begin + (tile * kLinThreads + threadIdx.x) * kEPT;
         const bool any = e0 < e_end;
-        int p4[4] = {-1, -1, -1, -1}, l4[4] = {0, 0, 0, 0};
-        S z4[4], om4[4];
-        if (any) {  // the SoA arrays are padded to a multiple of 4 edges
-            load4(d.b_pose + e0, p4);
-            load4(d.b_lm + e0, l4);
-            load4(d.b_z + e0, z4);
-            load4(d.b_om + e0, om4);
+        int p4[kEPT], l4[kEPT];
+        S z4[kEPT], om4[kEPT];
+#pragma unroll
+        for (int j = 0; j < kEPT; j++) { p4[j] = any ? np4[j] : -1; l4[j] = any ? nl4[j] : 0; z4[j] = nz4[j]; om4[j] = nom4[j]; }
+        {
+            const int tn = tile + gridDim.x;
+            const int en = e_begin + (tn * kLinThreads + threadIdx.x) * kEPT;
+            if (tn < ntiles && en < e_end) {
+                loadN<kEPT>(d.b_pose + en, np4); loadN<kEPT>(d.b_lm + en, nl4);
+                loadN<kEPT>(d.b_z + en, nz4); loadN<kEPT>(d.b_om + en, nom4);
+            }
         }
-        S hpl[6][4];
+        S hpl[6][kEPT];
         S acc[9], head[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) { acc[k] = S(0); head[k] = S(0); }
@@ -178,14 +219,12 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize_bearing(Dev<S> d, 
             hpl[0][j] = w0 * J[3]; hpl[1][j] = w0 * J[4];
             hpl[2][j] = w1 * J[3]; hpl[3][j] = w1 * J[4];
             hpl[4][j] = w2 * J[3]; hpl[5][j] = w2 * J[4];
+            {
+                const int le = threadIdx.x * kEPT + j;
+                sl[0][le] = w3 * J[3]; sl[1][le] = w3 * J[4]; sl[2][le] = w4 * J[4];
+                sl[3][le] = w3 * err; sl[4][le] = w4 * err;
+            }
             if (valid) {
-                S* hl = d.Hll + 3LL * l;
-                red_add(hl + 0, w3 * J[3]);
-                red_add(hl + 1, w3 * J[4]);
-                red_add(hl + 2, w4 * J[4]);
-                S* bl = d.b + 3LL * d.NP + 2LL * l;
-                red_add(bl + 0, w3 * err);
-                red_add(bl + 1, w4 * err);
                 if (!kIdentSlots) {
                     const long long s = __ldg(d.b_slot + e0 + j);
 #pragma unroll
@@ -214,9 +253,9 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize_bearing(Dev<S> d, 
             }
         }
         // ---- pose-landmark blocks: plane k, four consecutive slots ------------------------------------------------
-        if (kIdentSlots && any) {
+        if (kIdentSlots && any && !(dbg & 4)) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) store4(d.Hpl + (long long)k * d.hpl_ld + e0, hpl[k]);
+            for (int k = 0; k < 6; k++) storeN<kEPT>(d.Hpl + (long long)k * d.hpl_ld + e0, hpl[k]);
         }
         // ---- pose side across lanes ------------------------------------------------------------------------------------
         // (1) a lane's head piece (its first pose, when the pose changes inside the lane) continues the previous
@@ -257,13 +296,33 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize_bearing(Dev<S> d, 
                 }
             }
         }
-        if (is_head && any && cur != d.fixed && cur >= 0) {
+        if (is_head && any && cur != d.fixed && cur >= 0 && !(dbg & 2)) {
             S* hp = d.Hpp + 6LL * cur;
 #pragma unroll
             for (int k = 0; k < 6; k++) red_add(hp + k, acc[k]);
             S* bp = d.b + 3LL * cur;
             red_add(bp + 0, acc[6]); red_add(bp + 1, acc[7]); red_add(bp + 2, acc[8]);
         }
+        // ---- landmark side: one group per distinct landmark of the tile, summed from shared memory ------------------
+        __syncthreads();
+        if (!(dbg & 1)) {
+            const int gt = (e_begin / kLinTile) + tile;
+            const int g0 = __ldg(d.tile_ptr + gt), g1 = __ldg(d.tile_ptr + gt + 1);
+            for (int g = g0 + threadIdx.x; g < g1; g += kLinThreads) {
+                const int l = __ldg(d.tg_lm + g);
+                const int a = __ldg(d.tg_eptr + g), b = __ldg(d.tg_eptr + g + 1);
+                S v0 = S(0), v1 = S(0), v2 = S(0), v3 = S(0), v4 = S(0);
+                for (int q = a; q < b; q++) {
+                    const int le = __ldg(d.tg_edge + q);
+                    v0 += sl[0][le]; v1 += sl[1][le]; v2 += sl[2][le]; v3 += sl[3][le]; v4 += sl[4][le];
+                }
+                S* hl = d.Hll + 3LL * l;
+                red_add(hl + 0, v0); red_add(hl + 1, v1); red_add(hl + 2, v2);
+                S* bl = d.b + 3LL * d.NP + 2LL * l;
+                red_add(bl + 0, v3); red_add(bl + 1, v4);
+            }
+        }
+        __syncthreads();
     }
     // ---- chi2 / over-threshold ------------------------------------------------------------------------------------------
     double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
@@ -299,10 +358,12 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
         if (per_sm < 1) per_sm = 1;
         int grid = sm_count * per_sm;
         if (grid > tiles) grid = tiles;
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("BOS_LIN_DEBUG"); dbg = e ? atoi(e) : 0; }
         if (d.b_slot == nullptr)
-            k_linearize_bearing<S, true><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold);
+            k_linearize_bearing<S, true><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
         else
-            k_linearize_bearing<S, false><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold);
+            k_linearize_bearing<S, false><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
         launches++;
     }
     return launches;

@@ -73,6 +73,29 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         for (int e = 0; e < Eb; e++) P.tri_edge[cur[b_lm[e]]++] = inv[e];
     }
 
+    // tile-local grouping of the sorted bearing edges by landmark (static: depends only on the edge lists)
+    {
+        const int ntiles = (Eb + kLinTile - 1) / kLinTile;
+        P.tile_ptr.assign(ntiles + 1, 0);
+        P.tg_lm.clear(); P.tg_eptr.assign(1, 0); P.tg_edge.resize(Eb);
+        std::vector<std::pair<int, int>> tmp;
+        for (int t = 0; t < ntiles; t++) {
+            const int a = t * kLinTile, b = std::min(Eb, a + kLinTile);
+            tmp.clear();
+            for (int k = a; k < b; k++) tmp.emplace_back(P.b_lm[k], k - a);
+            std::sort(tmp.begin(), tmp.end());
+            for (size_t i = 0; i < tmp.size(); i++) {
+                if (i == 0 || tmp[i].first != tmp[i - 1].first) {
+                    if (i) P.tg_eptr.push_back(a + (int)i);
+                    P.tg_lm.push_back(tmp[i].first);
+                }
+                P.tg_edge[a + i] = (unsigned short)tmp[i].second;
+            }
+            if (!tmp.empty()) P.tg_eptr.push_back(b);
+            P.tile_ptr[t + 1] = (int)P.tg_lm.size();
+        }
+    }
+
     // ---- odometry edges: unique unordered pose pairs ---------------------------------------------------------
     P.o_src.assign(o_src, o_src + Eo); P.o_dst.assign(o_dst, o_dst + Eo);
     std::vector<uint64_t> okey(Eo);
@@ -98,9 +121,12 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         P.oe_ptr.assign(NP + 1, 0);
         for (int e = 0; e < Eo; e++) { P.oe_ptr[o_src[e] + 1]++; P.oe_ptr[o_dst[e] + 1]++; }
         for (int i = 0; i < NP; i++) P.oe_ptr[i + 1] += P.oe_ptr[i];
-        P.oe_edge.resize(2 * (size_t)Eo);
+        P.oe_edge.resize(2 * (size_t)Eo); P.oe_other.resize(2 * (size_t)Eo);
         std::vector<int> cur(P.oe_ptr.begin(), P.oe_ptr.end() - 1);
-        for (int e = 0; e < Eo; e++) { P.oe_edge[cur[o_src[e]]++] = (e << 1); P.oe_edge[cur[o_dst[e]]++] = (e << 1) | 1; }
+        for (int e = 0; e < Eo; e++) {
+            int a = cur[o_src[e]]++; P.oe_edge[a] = (e << 1); P.oe_other[a] = o_dst[e];
+            int b = cur[o_dst[e]]++; P.oe_edge[b] = (e << 1) | 1; P.oe_other[b] = o_src[e];
+        }
     }
     // pose-pose adjacency, neighbours ascending
     P.pp_ptr.assign(NP + 1, 0);

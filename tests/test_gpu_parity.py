@@ -192,7 +192,7 @@ def test_step_host_equals_step_device(built_lib):
         sb = b.step_host(Ph, Lh)
         assert sa.chi2_bearing == pytest.approx(sb.chi2_bearing, rel=1e-12)
     Pa, La = a.get_state()
-    assert np.abs(Pa - Ph).max() <= 1e-12 and np.abs(La - Lh).max() <= 1e-12
+    assert np.abs(Pa - Ph).max() <= 1e-10 and np.abs(La - Lh).max() <= 1e-10   # atomics order differs between runs
     assert sa.gpu_launches > 0
 
 
