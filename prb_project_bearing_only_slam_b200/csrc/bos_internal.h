@@ -52,6 +52,7 @@ struct Dev {
     const int* pp_slot = nullptr;    // [2*n_off] slot; bit 31 set when this pose is the 'hi' side (use the transpose)
     const int* off_lo = nullptr;     // [n_off] block row pose of Hoff[k]
     const int* off_hi = nullptr;     // [n_off] block column pose
+    const int* epose_ptr = nullptr;  // [NP+1] CSR of the (pose, lm)-sorted bearing EDGES by pose
     const int* tile_ptr = nullptr;   // [ntiles+1] groups (distinct landmarks) of each tile
     const int* tg_lm = nullptr;      // [n_groups] landmark of the group
     const int* tg_eptr = nullptr;    // [n_groups+1] into tg_edge
@@ -159,7 +160,7 @@ struct HostPattern {
     std::vector<int> off_lo, off_hi;        // unique pose-pose blocks, sorted
     std::vector<int> pp_ptr, pp_nbr, pp_slot;
     std::vector<int> tri_ptr, tri_edge;
-    std::vector<int> tile_ptr, tg_lm, tg_eptr;
+    std::vector<int> tile_ptr, tg_lm, tg_eptr, epose_ptr;
     std::vector<unsigned short> tg_edge;
     std::vector<char> touched;              // [NP + NL]
     // scalar CSC pattern of H_nofixed (slam/solver.cpp:72-75)

@@ -188,7 +188,7 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(lm_order, P.lm_order) UP(lm_order_pose, P.lm_order_pose) UP(lm_order_lm, P.lm_order_lm)
     UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)
     UP(tri_ptr, P.tri_ptr) UP(tri_edge, P.tri_edge)
-    UP(tile_ptr, P.tile_ptr) UP(tg_lm, P.tg_lm) UP(tg_eptr, P.tg_eptr) UP(tg_edge, P.tg_edge)
+    UP(epose_ptr, P.epose_ptr) UP(tile_ptr, P.tile_ptr) UP(tg_lm, P.tg_lm) UP(tg_eptr, P.tg_eptr) UP(tg_edge, P.tg_edge)
 #undef UP
     d.pose = m.get<S>(4 * (size_t)P.NP);
     d.lm = m.get<S>(2 * (size_t)std::max(P.NL, 1));

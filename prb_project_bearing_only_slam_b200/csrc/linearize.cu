@@ -144,191 +144,136 @@ __global__ void __launch_bounds__(128, 8) k_pose_odometry_init(Dev<S> d, int o_b
 
 // ---- K1 ----------------------------------------------------------------------------------------------------------
 constexpr int kLinThreads = 256;
-#ifndef BOS_EPT
-#define BOS_EPT 2
-#endif
+constexpr int kEPT = kLinTile / kLinThreads;  // consecutive edges per thread (2)
+static_assert(kLinThreads * kEPT == kLinTile && kEPT == 2, "one CTA covers exactly one tile, two edges per thread");
 #ifndef BOS_LIN_MINBLOCKS
 #define BOS_LIN_MINBLOCKS 3
 #endif
-constexpr int kEPT = BOS_EPT;  // consecutive edges per thread
-static_assert(kLinThreads * kEPT == kLinTile, "one CTA iteration covers exactly one tile");
+constexpr int kNT = 14;  // per-edge terms staged in shared memory: 5 landmark-side + 9 pose-side
 
+// One CTA per tile of kLinTile sorted edges.
+//   phase 1: every thread linearizes two consecutive edges, stores their pose-landmark blocks (128-bit stores into
+//            the SoA planes) and stages the 14 landmark-/pose-side products in shared memory;
+//   phase 2: one thread per distinct landmark of the tile (host-precomputed grouping) and one thread per pose run of the
+//            tile sum their edges from shared memory and issue ONE set of REDs each.
+// The grouping metadata of phase 2 is fetched before phase 1 so its latency hides behind the arithmetic.
 template <typename S, bool kIdentSlots>
 __global__ void __launch_bounds__(kLinThreads, BOS_LIN_MINBLOCKS) k_linearize_bearing(Dev<S> d, int e_begin, int e_end, S kernel_threshold, int dbg) {
     __shared__ double red[2][kLinThreads / 32];
-    __shared__ S sl[5][kLinTile];   // landmark-side terms of the tile: Hll xx, xy, yy and b_l x, y per edge
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S (*st)[kLinTile] = reinterpret_cast<S (*)[kLinTile]>(smem_raw);   // [kNT][kLinTile]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int ta = e_begin + tile * kLinTile;                 // e_begin is a multiple of the tile size
+    const int tb = (ta + kLinTile < e_end) ? ta + kLinTile : e_end;
+    const int e0 = ta + tid * kEPT;
+    const bool any = e0 < tb;
+    // ---- loads: this thread's two edges, then the phase-2 metadata --------------------------------------------------
+    int p2[kEPT] = {-1, -1}, l2[kEPT] = {0, 0};
+    S z2[kEPT] = {S(0), S(0)}, om2[kEPT] = {S(0), S(0)};
+    if (any) {  // the SoA arrays are padded to a multiple of 4 edges
+        loadN<kEPT>(d.b_pose + e0, p2); loadN<kEPT>(d.b_lm + e0, l2);
+        loadN<kEPT>(d.b_z + e0, z2); loadN<kEPT>(d.b_om + e0, om2);
+    }
+    const int gt = ta / kLinTile;
+    const int g0 = __ldg(d.tile_ptr + gt), g1 = __ldg(d.tile_ptr + gt + 1);
+    const int pfirst = __ldg(d.b_pose + ta), plast = __ldg(d.b_pose + tb - 1);
+    int gl = 0, ga = 0, gb = 0, ra = 0, rb = 0;
+    if (g0 + tid < g1) { gl = __ldg(d.tg_lm + g0 + tid); ga = __ldg(d.tg_eptr + g0 + tid); gb = __ldg(d.tg_eptr + g0 + tid + 1); }
+    const int rt = kLinThreads - 1 - tid;   // pose runs are taken from the top of the CTA, landmark groups from the bottom
+    if (pfirst + rt <= plast) { ra = __ldg(d.epose_ptr + pfirst + rt); rb = __ldg(d.epose_ptr + pfirst + rt + 1); }
+    // ---- phase 1 -------------------------------------------------------------------------------------------------------
     double chi_acc = 0.0;
     int over_acc = 0;
-    const int n = e_end - e_begin;  // e_begin is a multiple of the tile size
-    const int ntiles = (n + kLinThreads * kEPT - 1) / (kLinThreads * kEPT);
-    // software pipeline: the next tile's index / measurement vectors are in flight while this tile computes
-    int np4[kEPT], nl4[kEPT];
-    S nz4[kEPT], nom4[kEPT];
-    {
-        const int e0 = e_begin + (blockIdx.x * kLinThreads + threadIdx.x) * kEPT;
-        if (blockIdx.x < ntiles && e0 < e_end) {  // the SoA arrays are padded to a multiple of 4 edges
-            loadN<kEPT>(d.b_pose + e0, np4); loadN<kEPT>(d.b_lm + e0, nl4);
-            loadN<kEPT>(d.b_z + e0, nz4); loadN<kEPT>(d.b_om + e0, nom4);
+    S hpl[6][kEPT];
+    S tv[kNT][kEPT];
+    PoseV<S> X = {S(0), S(0), S(1), S(0)};
+    int xpose = -1;
+#pragma unroll
+    for (int j = 0; j < kEPT; j++) {
+        const bool valid = any && (e0 + j < tb);
+        S J[5] = {S(0), S(0), S(0), S(0), S(0)};
+        S err = S(0), om = S(0);
+        const int p = p2[j], l = l2[j];
+        if (valid) {
+            if (p != xpose) { X = load_pose<S>(d.pose, p); xpose = p; }
+            S lx, ly;
+            load_lm<S>(d.lm, l, lx, ly);
+            om = om2[j];
+            bearing_terms<S>(X, lx, ly, z2[j], err, J);
+            // threshold robust kernel: scales the ERROR only (slam/solver.cpp:37-41)
+            const S chi = err * om * err;
+            chi_acc += (double)chi;
+            if (chi > kernel_threshold) { err *= sqrt(kernel_threshold / chi); over_acc++; }
+            if (p == d.fixed) { J[0] = J[1] = J[2] = S(0); }
+        }
+        const S w0 = J[0] * om, w1 = J[1] * om, w2 = J[2] * om;  // (J^T omega), pose part
+        const S w3 = J[3] * om, w4 = J[4] * om;                  // landmark part
+        hpl[0][j] = w0 * J[3]; hpl[1][j] = w0 * J[4];
+        hpl[2][j] = w1 * J[3]; hpl[3][j] = w1 * J[4];
+        hpl[4][j] = w2 * J[3]; hpl[5][j] = w2 * J[4];
+        tv[0][j] = w3 * J[3]; tv[1][j] = w3 * J[4]; tv[2][j] = w4 * J[4];
+        tv[3][j] = w3 * err; tv[4][j] = w4 * err;
+        tv[5][j] = w0 * J[0]; tv[6][j] = w0 * J[1]; tv[7][j] = w0 * J[2];
+        tv[8][j] = w1 * J[1]; tv[9][j] = w1 * J[2]; tv[10][j] = w2 * J[2];
+        tv[11][j] = w0 * err; tv[12][j] = w1 * err; tv[13][j] = w2 * err;
+        if (!kIdentSlots && valid) {
+            const long long s = __ldg(d.b_slot + e0 + j);
+#pragma unroll
+            for (int k = 0; k < 6; k++) red_add(d.Hpl + (long long)k * d.hpl_ld + s, hpl[k][j]);
         }
     }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int e0 = e_begin + (tile * kLinThreads + threadIdx.x) * kEPT;
-        const bool any = e0 < e_end;
-        int p4[kEPT], l4[kEPT];
-        S z4[kEPT], om4[kEPT];
 #pragma unroll
-        for (int j = 0; j < kEPT; j++) { p4[j] = any ? np4[j] : -1; l4[j] = any ? nl4[j] : 0; z4[j] = nz4[j]; om4[j] = nom4[j]; }
-        {
-            const int tn = tile + gridDim.x;
-            const int en = e_begin + (tn * kLinThreads + threadIdx.x) * kEPT;
-            if (tn < ntiles && en < e_end) {
-                loadN<kEPT>(d.b_pose + en, np4); loadN<kEPT>(d.b_lm + en, nl4);
-                loadN<kEPT>(d.b_z + en, nz4); loadN<kEPT>(d.b_om + en, nom4);
+    for (int k = 0; k < kNT; k++) {   // two adjacent edges -> one 128-bit (64-bit for float) shared store, conflict-free
+        typedef typename Vec2T<S>::type V2;
+        V2 v; v.x = tv[k][0]; v.y = tv[k][1];
+        *reinterpret_cast<V2*>(&st[k][tid * kEPT]) = v;
+    }
+    if (kIdentSlots && any && !(dbg & 4)) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) storeN<kEPT>(d.Hpl + (long long)k * d.hpl_ld + e0, hpl[k]);
+    }
+    __syncthreads();
+    // ---- phase 2: landmark groups -------------------------------------------------------------------------------------------
+    if (!(dbg & 1)) {
+        for (int g = g0 + tid; g < g1; g += kLinThreads) {
+            if (g != g0 + tid) { gl = __ldg(d.tg_lm + g); ga = __ldg(d.tg_eptr + g); gb = __ldg(d.tg_eptr + g + 1); }
+            S v0 = S(0), v1 = S(0), v2 = S(0), v3 = S(0), v4 = S(0);
+            for (int q = ga; q < gb; q++) {
+                const int le = __ldg(d.tg_edge + q);
+                v0 += st[0][le]; v1 += st[1][le]; v2 += st[2][le]; v3 += st[3][le]; v4 += st[4][le];
             }
+            S* hl = d.Hll + 3LL * gl;
+            red_add(hl + 0, v0); red_add(hl + 1, v1); red_add(hl + 2, v2);
+            S* bl = d.b + 3LL * d.NP + 2LL * gl;
+            red_add(bl + 0, v3); red_add(bl + 1, v4);
         }
-        S hpl[6][kEPT];
-        S acc[9], head[9];
+    }
+    // ---- phase 2: pose runs (taken from the top of the CTA so they overlap the landmark groups of the low threads) --------
+    if (!(dbg & 2)) {
+        for (int p = pfirst + rt; p <= plast; p += kLinThreads) {
+            if (p != pfirst + rt) { ra = __ldg(d.epose_ptr + p); rb = __ldg(d.epose_ptr + p + 1); }
+            const int a = (ra > ta ? ra : ta) - ta, b = (rb < tb ? rb : tb) - ta;
+            if (p == d.fixed || a >= b) continue;
+            S v[9];
 #pragma unroll
-        for (int k = 0; k < 9; k++) { acc[k] = S(0); head[k] = S(0); }
-        int cur = any ? p4[0] : (-1 - lane);
-        int head_key = cur;
-        bool has_head = false;
-        PoseV<S> X = {S(0), S(0), S(1), S(0)};
-        int xpose = -1;
+            for (int k = 0; k < 9; k++) v[k] = S(0);
+            for (int q = a; q < b; q++) {
 #pragma unroll
-        for (int j = 0; j < kEPT; j++) {
-            const bool valid = any && (e0 + j < e_end);
-            S J[5] = {S(0), S(0), S(0), S(0), S(0)};
-            S err = S(0), om = S(0);
-            const int p = p4[j], l = l4[j];
-            if (valid) {
-                if (p != xpose) { X = load_pose<S>(d.pose, p); xpose = p; }
-                S lx, ly;
-                load_lm<S>(d.lm, l, lx, ly);
-                om = om4[j];
-                bearing_terms<S>(X, lx, ly, z4[j], err, J);
-                // threshold robust kernel: scales the ERROR only (slam/solver.cpp:37-41)
-                const S chi = err * om * err;
-                chi_acc += (double)chi;
-                if (chi > kernel_threshold) { err *= sqrt(kernel_threshold / chi); over_acc++; }
-                if (p == d.fixed) { J[0] = J[1] = J[2] = S(0); }
+                for (int k = 0; k < 9; k++) v[k] += st[5 + k][q];
             }
-            const S w0 = J[0] * om, w1 = J[1] * om, w2 = J[2] * om;  // (J^T omega), pose part
-            const S w3 = J[3] * om, w4 = J[4] * om;                  // landmark part
-            hpl[0][j] = w0 * J[3]; hpl[1][j] = w0 * J[4];
-            hpl[2][j] = w1 * J[3]; hpl[3][j] = w1 * J[4];
-            hpl[4][j] = w2 * J[3]; hpl[5][j] = w2 * J[4];
-            {
-                const int le = threadIdx.x * kEPT + j;
-                sl[0][le] = w3 * J[3]; sl[1][le] = w3 * J[4]; sl[2][le] = w4 * J[4];
-                sl[3][le] = w3 * err; sl[4][le] = w4 * err;
-            }
-            if (valid) {
-                if (!kIdentSlots) {
-                    const long long s = __ldg(d.b_slot + e0 + j);
+            S* hp = d.Hpp + 6LL * p;
 #pragma unroll
-                    for (int k = 0; k < 6; k++) red_add(d.Hpl + (long long)k * d.hpl_ld + s, hpl[k][j]);
-                }
-                // pose side: runs of equal pose inside the thread
-                if (p != cur) {
-                    if (!has_head) {
-                        has_head = true; head_key = cur;
-#pragma unroll
-                        for (int k = 0; k < 9; k++) head[k] = acc[k];
-                    } else if (cur != d.fixed) {  // a run that starts and ends inside this thread
-                        S* hp = d.Hpp + 6LL * cur;
-#pragma unroll
-                        for (int k = 0; k < 6; k++) red_add(hp + k, acc[k]);
-                        S* bp = d.b + 3LL * cur;
-                        red_add(bp + 0, acc[6]); red_add(bp + 1, acc[7]); red_add(bp + 2, acc[8]);
-                    }
-                    cur = p;
-#pragma unroll
-                    for (int k = 0; k < 9; k++) acc[k] = S(0);
-                }
-                acc[0] += w0 * J[0]; acc[1] += w0 * J[1]; acc[2] += w0 * J[2];
-                acc[3] += w1 * J[1]; acc[4] += w1 * J[2]; acc[5] += w2 * J[2];
-                acc[6] += w0 * err; acc[7] += w1 * err; acc[8] += w2 * err;
-            }
+            for (int k = 0; k < 6; k++) red_add(hp + k, v[k]);
+            S* bp = d.b + 3LL * p;
+            red_add(bp + 0, v[6]); red_add(bp + 1, v[7]); red_add(bp + 2, v[8]);
         }
-        // ---- pose-landmark blocks: plane k, four consecutive slots ------------------------------------------------
-        if (kIdentSlots && any && !(dbg & 4)) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) storeN<kEPT>(d.Hpl + (long long)k * d.hpl_ld + e0, hpl[k]);
-        }
-        // ---- pose side across lanes ------------------------------------------------------------------------------------
-        // (1) a lane's head piece (its first pose, when the pose changes inside the lane) continues the previous
-        //     lane's last run: hand it down one lane when the keys agree, else emit it here.
-        const int prev_tail_key = __shfl_up_sync(BOS_FULL_MASK, cur, 1);
-        const int next_has_head = __shfl_down_sync(BOS_FULL_MASK, has_head ? 1 : 0, 1);
-        const int next_head_key = __shfl_down_sync(BOS_FULL_MASK, head_key, 1);
-        const bool take = (lane < 31) && next_has_head && (next_head_key == cur);
-        const bool any_head = __any_sync(BOS_FULL_MASK, has_head);
-        if (any_head) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-                const S t = __shfl_down_sync(BOS_FULL_MASK, head[k], 1);
-                if (take) acc[k] += t;
-            }
-            const bool given = (lane > 0) && (prev_tail_key == head_key);
-            if (has_head && !given && head_key != d.fixed && head_key >= 0) {
-                S* hp = d.Hpp + 6LL * head_key;
-#pragma unroll
-                for (int k = 0; k < 6; k++) red_add(hp + k, head[k]);
-                S* bp = d.b + 3LL * head_key;
-                red_add(bp + 0, head[6]); red_add(bp + 1, head[7]); red_add(bp + 2, head[8]);
-            }
-        }
-        // (2) segmented reduction of the lanes' last runs over lanes with equal key
-        const bool is_head = (lane == 0) || (prev_tail_key != cur);
-        const unsigned heads = __ballot_sync(BOS_FULL_MASK, is_head);
-        const unsigned after = (lane == 31) ? 0u : (heads >> (lane + 1));
-        const int run_left = after ? __ffs(after) : (32 - lane);
-        const int max_run = __reduce_max_sync(BOS_FULL_MASK, run_left);
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            if (off < max_run) {
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    const S t = __shfl_down_sync(BOS_FULL_MASK, acc[k], off);
-                    if (off < run_left) acc[k] += t;
-                }
-            }
-        }
-        if (is_head && any && cur != d.fixed && cur >= 0 && !(dbg & 2)) {
-            S* hp = d.Hpp + 6LL * cur;
-#pragma unroll
-            for (int k = 0; k < 6; k++) red_add(hp + k, acc[k]);
-            S* bp = d.b + 3LL * cur;
-            red_add(bp + 0, acc[6]); red_add(bp + 1, acc[7]); red_add(bp + 2, acc[8]);
-        }
-        // ---- landmark side: one group per distinct landmark of the tile, summed from shared memory ------------------
-        __syncthreads();
-        if (!(dbg & 1)) {
-            const int gt = (e_begin / kLinTile) + tile;
-            const int g0 = __ldg(d.tile_ptr + gt), g1 = __ldg(d.tile_ptr + gt + 1);
-            for (int g = g0 + threadIdx.x; g < g1; g += kLinThreads) {
-                const int l = __ldg(d.tg_lm + g);
-                const int a = __ldg(d.tg_eptr + g), b = __ldg(d.tg_eptr + g + 1);
-                S v0 = S(0), v1 = S(0), v2 = S(0), v3 = S(0), v4 = S(0);
-                for (int q = a; q < b; q++) {
-                    const int le = __ldg(d.tg_edge + q);
-                    v0 += sl[0][le]; v1 += sl[1][le]; v2 += sl[2][le]; v3 += sl[3][le]; v4 += sl[4][le];
-                }
-                S* hl = d.Hll + 3LL * l;
-                red_add(hl + 0, v0); red_add(hl + 1, v1); red_add(hl + 2, v2);
-                S* bl = d.b + 3LL * d.NP + 2LL * l;
-                red_add(bl + 0, v3); red_add(bl + 1, v4);
-            }
-        }
-        __syncthreads();
     }
     // ---- chi2 / over-threshold ------------------------------------------------------------------------------------------
     double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
     if (lane == 0) { red[0][warp] = c; red[1][warp] = o; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double cs = 0, os = 0;
         for (int w = 0; w < kLinThreads / 32; w++) { cs += red[0][w]; os += red[1][w]; }
         if (cs != 0.0) atomicAdd(d.stats + 0, cs);
@@ -350,22 +295,24 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
     }
     const int nb = r.b_end - r.b_begin;
     if (nb > 0) {
-        const int per_tile = kLinThreads * kEPT;
-        int tiles = (nb + per_tile - 1) / per_tile;
-        int per_sm = 0;
-        if (d.b_slot == nullptr) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize_bearing<S, true>, kLinThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linearize_bearing<S, false>, kLinThreads, 0);
-        if (per_sm < 1) per_sm = 1;
-        int grid = sm_count * per_sm;
-        if (grid > tiles) grid = tiles;
+        const int tiles = (nb + kLinTile - 1) / kLinTile;
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("BOS_LIN_DEBUG"); dbg = e ? atoi(e) : 0; }
+        const size_t smem = sizeof(S) * kNT * kLinTile;
+        static bool attr_done[2] = {false, false};
+        bool& done = attr_done[sizeof(S) == 8 ? 0 : 1];
+        if (!done) {
+            cudaFuncSetAttribute(k_linearize_bearing<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_linearize_bearing<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            done = true;
+        }
         if (d.b_slot == nullptr)
-            k_linearize_bearing<S, true><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
+            k_linearize_bearing<S, true><<<tiles, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
         else
-            k_linearize_bearing<S, false><<<grid, kLinThreads, 0, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
+            k_linearize_bearing<S, false><<<tiles, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
         launches++;
     }
+    (void)sm_count;
     return launches;
 }
 

@@ -73,6 +73,9 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         for (int e = 0; e < Eb; e++) P.tri_edge[cur[b_lm[e]]++] = inv[e];
     }
 
+    P.epose_ptr.assign(NP + 1, 0);
+    for (int k = 0; k < Eb; k++) P.epose_ptr[P.b_pose[k] + 1]++;
+    for (int i = 0; i < NP; i++) P.epose_ptr[i + 1] += P.epose_ptr[i];
     // tile-local grouping of the sorted bearing edges by landmark (static: depends only on the edge lists)
     {
         const int ntiles = (Eb + kLinTile - 1) / kLinTile;
