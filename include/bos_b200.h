@@ -58,7 +58,9 @@ typedef struct bos_options {
     double damping;           /* slam/solver.cpp:17  default 0.01 */
     int pcg_max_iters;        /* default 5000 */
     double pcg_rtol;          /* stop when sqrt(r^T M^-1 r) <= rtol * its initial value; default 1e-10 */
-    int reserved[8];
+    int pcg_variant;          /* 0 = one persistent cooperative kernel for the whole PCG solve (default; falls back to 1 when a
+                                 landmark has more than 1024 observations), 1 = classic loop of small kernels */
+    int reserved[7];
 } bos_options;
 
 /* Per-iteration outputs.  The reference prints none of these; chi2 is defined as the sum of the

@@ -13,6 +13,9 @@ namespace bos {
 // bearing edges are linearized in tiles of this many (pose, landmark)-sorted edges; the landmark-side sums of a tile
 // are aggregated in shared memory through a host-precomputed tile-local grouping before they touch global memory
 constexpr int kLinTile = 512;
+// the fused PCG kernel reads the per-edge factors from two sliced-ELL layouts (see pattern.cpp)
+constexpr int kPcgThreads = 1024;                  // one persistent CTA per SM
+constexpr int kEllLanesL = 4;                      // lanes per landmark row in the landmark-major layout
 
 // Typed view of everything a kernel needs.  One instance per context, built after upload.
 template <typename S>
@@ -57,6 +60,16 @@ struct Dev {
     const int* tg_lm = nullptr;      // [n_groups] landmark of the group
     const int* tg_eptr = nullptr;    // [n_groups+1] into tg_edge
     const unsigned short* tg_edge = nullptr;  // [Eb] tile-local edge index
+    // sliced-ELL layouts of the bearing edges for the fused PCG kernel
+    int n_clm = 0, nLg = 0, nPg = 0;
+    long long nLs = 0, nPs = 0;      // slots of the two layouts
+    const int* pl_lm_id = nullptr;   // [n_clm] landmark stix of compact row r (rows sorted by descending observation count)
+    const int* ell_Loff = nullptr;   // [nLg+1] column offset of each landmark group
+    const int* ell_Lmap = nullptr;   // [nLs] sorted bearing-edge index of the slot, -1 for padding
+    const int* ell_Lpose = nullptr;  // [nLs] pose of the slot (0 for padding; the factor is 0 there)
+    const int* ell_Poff = nullptr;   // [nPg+1]
+    const int* ell_Pmap = nullptr;   // [nPs]
+    const int* ell_Prow = nullptr;   // [nPs] compact landmark row of the slot
     const int* tri_ptr = nullptr;    // [NL+1] bearing edges grouped by landmark (caller order inside a landmark)
     const int* tri_edge = nullptr;   // [Eb] sorted-edge index
     // state
@@ -118,7 +131,22 @@ struct PcgWork {
     S* p0 = nullptr;
     S* p1 = nullptr;
     S* y = nullptr;
-    double* scal = nullptr;  // [16] rz, pAp, rz_new, rz0, done flag, iterations ...
+    // fused kernel: the operator is applied from per-EDGE factors.  A bearing edge's 3x2 block is rank one,
+    // Hpl_k = Jp_k^T omega Jl_k, and Jp_k = (-j0, -j1, j0 ly - j1 lx) is determined by Jl_k = (j0, j1) and the landmark position,
+    // so two scalars per edge (sqrt(omega) Jl) replace the six of the block.
+    S* jP = nullptr;               // [2][Eb_pad] factors in sorted-edge order (scratch of the fill)
+    S* Lj = nullptr;               // [2][nLs] factors in the landmark-major ELL layout
+    S* Pj = nullptr;               // [2][nPs] factors in the pose-major ELL layout
+    S* hllinv_c = nullptr;         // [n_clm][3] Hll^-1 in compact row order
+    S* ul4 = nullptr;              // [n_clm][4] u_l = Hll^-1 t_l (rewritten every CG iteration) and the landmark position lx, ly
+    S* z4 = nullptr;               // [2][NP][4] double-buffered z (padded to one 32-byte sector per pose)
+    S* v4 = nullptr;               // [4][NP][4] p, s, x, r padded the same way
+    S* yoff = nullptr;             // [NP][4] off-diagonal pose-pose part of S z
+    int Eb_pad = 0;
+    double* scal = nullptr;  // [32] classic: rz, pAp, rz_new, rz0, done flag, iterations ...; fused: see solve_pcg.cu
+    unsigned* bar = nullptr; // [4] grid barrier counter of the fused kernel
+    int variant = 0;         // bos_options.pcg_variant: 0 = fused persistent kernel, 1 = classic multi-kernel loop
+    int sm_count = 148;
 };
 template <typename S>
 int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st,
@@ -160,6 +188,7 @@ struct HostPattern {
     std::vector<int> off_lo, off_hi;        // unique pose-pose blocks, sorted
     std::vector<int> pp_ptr, pp_nbr, pp_slot;
     std::vector<int> tri_ptr, tri_edge;
+    std::vector<int> pl_lm_id, b_row, ell_Loff, ell_Lmap, ell_Lpose, ell_Poff, ell_Pmap, ell_Prow;
     std::vector<int> tile_ptr, tg_lm, tg_eptr, epose_ptr;
     std::vector<unsigned short> tg_edge;
     std::vector<char> touched;              // [NP + NL]

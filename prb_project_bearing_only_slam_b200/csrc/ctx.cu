@@ -189,6 +189,10 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)
     UP(tri_ptr, P.tri_ptr) UP(tri_edge, P.tri_edge)
     UP(epose_ptr, P.epose_ptr) UP(tile_ptr, P.tile_ptr) UP(tg_lm, P.tg_lm) UP(tg_eptr, P.tg_eptr) UP(tg_edge, P.tg_edge)
+    UP(pl_lm_id, P.pl_lm_id) UP(ell_Loff, P.ell_Loff) UP(ell_Lmap, P.ell_Lmap) UP(ell_Lpose, P.ell_Lpose)
+    UP(ell_Poff, P.ell_Poff) UP(ell_Pmap, P.ell_Pmap) UP(ell_Prow, P.ell_Prow)
+    d.n_clm = (int)P.pl_lm_id.size(); d.nLg = (int)P.ell_Loff.size() - 1; d.nPg = (int)P.ell_Poff.size() - 1;
+    d.nLs = (long long)P.ell_Lmap.size(); d.nPs = (long long)P.ell_Pmap.size();
 #undef UP
     d.pose = m.get<S>(4 * (size_t)P.NP);
     d.lm = m.get<S>(2 * (size_t)std::max(P.NL, 1));
@@ -240,9 +244,18 @@ int ensure_pcg(bos_ctx* c) {
     w.minv = c->mem.get<S>(6 * (size_t)d.NP);
     w.x = c->mem.get<S>(n); w.r = c->mem.get<S>(n); w.z = c->mem.get<S>(n);
     w.p0 = c->mem.get<S>(n); w.y = c->mem.get<S>(n);
-    w.scal = c->mem.get<double>(16);
-    if (!w.hllinv || !w.ul || !w.tl || !w.Hlp || !w.minv || !w.x || !w.r || !w.z || !w.p0 || !w.y || !w.scal)
-        return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+    w.scal = c->mem.get<double>(32);
+    w.bar = c->mem.get<unsigned>(4);
+    w.Eb_pad = d.Eb_pad;
+    w.jP = c->mem.get<S>(2 * (size_t)std::max(d.Eb_pad, 4));
+    w.Lj = c->mem.get<S>(2 * (size_t)std::max(d.nLs, 32LL));
+    w.Pj = c->mem.get<S>(2 * (size_t)std::max(d.nPs, 32LL));
+    w.hllinv_c = c->mem.get<S>(3 * (size_t)std::max(d.n_clm, 1));
+    w.ul4 = c->mem.get<S>(4 * (size_t)std::max(d.n_clm, 1));
+    w.z4 = c->mem.get<S>(8 * (size_t)d.NP);
+    w.v4 = c->mem.get<S>(16 * (size_t)d.NP);
+    w.yoff = c->mem.get<S>(4 * (size_t)d.NP);
+    if (!w.jP || !w.Lj || !w.Pj || !w.hllinv_c || !w.ul4 || !w.z4 || !w.v4 || !w.yoff) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
     c->pcg_ready = true;
     return BOS_OK;
 }

@@ -76,6 +76,59 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
     P.epose_ptr.assign(NP + 1, 0);
     for (int k = 0; k < Eb; k++) P.epose_ptr[P.b_pose[k] + 1]++;
     for (int i = 0; i < NP; i++) P.epose_ptr[i + 1] += P.epose_ptr[i];
+    // sliced-ELL layouts of the bearing EDGES for the fused PCG kernel (both coalesced for one-row-per-lane loops):
+    //   L: rows = observed landmarks, renumbered compactly by descending observation count (uniform row length inside a
+    //      group), kEllLanesL lanes per row (a row's edges go round-robin over its lanes), 32 / kEllLanesL rows per group;
+    //   P: rows = poses in stix order, one lane per row, 32 rows per group.
+    // A group is stored column-major: slot = (group offset + t) * 32 + lane; width = the group's longest row.
+    {
+        std::vector<int> eptr(NL + 1, 0), eord(Eb);
+        for (int k = 0; k < Eb; k++) eptr[P.b_lm[k] + 1]++;
+        for (int j = 0; j < NL; j++) eptr[j + 1] += eptr[j];
+        {
+            std::vector<int> cur(eptr.begin(), eptr.end() - 1);
+            for (int k = 0; k < Eb; k++) eord[cur[P.b_lm[k]]++] = k;   // ascending sorted-edge index = ascending pose
+        }
+        P.pl_lm_id.clear();
+        for (int l = 0; l < NL; l++)
+            if (eptr[l + 1] > eptr[l]) P.pl_lm_id.push_back(l);
+        std::stable_sort(P.pl_lm_id.begin(), P.pl_lm_id.end(),
+                         [&](int a, int b) { return eptr[a + 1] - eptr[a] > eptr[b + 1] - eptr[b]; });
+        const int n_clm = (int)P.pl_lm_id.size();
+        P.b_row.assign(Eb, 0);
+        constexpr int RPG = 32 / kEllLanesL;
+        const int nLg = (n_clm + RPG - 1) / RPG;
+        P.ell_Loff.assign(nLg + 1, 0);
+        for (int g = 0; g < nLg; g++) {
+            const int l0 = P.pl_lm_id[g * RPG];
+            P.ell_Loff[g + 1] = P.ell_Loff[g] + (eptr[l0 + 1] - eptr[l0] + kEllLanesL - 1) / kEllLanesL;
+        }
+        P.ell_Lmap.assign((size_t)P.ell_Loff[nLg] * 32, -1);
+        P.ell_Lpose.assign((size_t)P.ell_Loff[nLg] * 32, 0);
+        for (int r = 0; r < n_clm; r++) {
+            const int l = P.pl_lm_id[r], g = r / RPG, lane0 = (r % RPG) * kEllLanesL;
+            for (int q = eptr[l]; q < eptr[l + 1]; q++) {
+                const int k = eord[q], idx = q - eptr[l];
+                const size_t slot = ((size_t)P.ell_Loff[g] + idx / kEllLanesL) * 32 + lane0 + idx % kEllLanesL;
+                P.ell_Lmap[slot] = k; P.ell_Lpose[slot] = P.b_pose[k];
+                P.b_row[k] = r;
+            }
+        }
+        const int nPg = (NP + 31) / 32;
+        P.ell_Poff.assign(nPg + 1, 0);
+        for (int g = 0; g < nPg; g++) {
+            int wmax = 0;
+            for (int i = g * 32; i < std::min(NP, g * 32 + 32); i++) wmax = std::max(wmax, P.epose_ptr[i + 1] - P.epose_ptr[i]);
+            P.ell_Poff[g + 1] = P.ell_Poff[g] + wmax;
+        }
+        P.ell_Pmap.assign((size_t)P.ell_Poff[nPg] * 32, -1);
+        P.ell_Prow.assign((size_t)P.ell_Poff[nPg] * 32, 0);
+        for (int i = 0; i < NP; i++)
+            for (int k = P.epose_ptr[i]; k < P.epose_ptr[i + 1]; k++) {
+                const size_t slot = ((size_t)P.ell_Poff[i / 32] + (k - P.epose_ptr[i])) * 32 + i % 32;
+                P.ell_Pmap[slot] = k; P.ell_Prow[slot] = P.b_row[k];
+            }
+    }
     // tile-local grouping of the sorted bearing edges by landmark (static: depends only on the edge lists)
     {
         const int ntiles = (Eb + kLinTile - 1) / kLinTile;

@@ -13,6 +13,8 @@
 #include "bos_math.cuh"
 #include "bos_schur.cuh"
 
+#include <cstdio>
+
 namespace bos {
 
 enum { SC_RZ0 = 0, SC_RZ1 = 1, SC_PAP = 2, SC_RZINIT = 3, SC_DONE = 4, SC_ITER = 5, SC_TOL2 = 6, SC_BAD = 7 };
@@ -221,9 +223,425 @@ __global__ void k_pcg_promote(double* scal) {
     if (scal[8] != 0.0) scal[SC_DONE] = 1.0;
 }
 
+
+// =================================================================================================================
+// Fused variant: the whole PCG solve is ONE persistent cooperative kernel (one 1024-thread CTA per SM, 2 grid barriers
+// per CG iteration, no host round trips, no value atomics).
+//
+// Operator.  A bearing edge's 3x2 block is rank one, Hpl_k = Jp_k^T omega Jl_k, and its pose Jacobian is determined by
+// the landmark Jacobian and the landmark position: Jp_k = (-j0, -j1, j0 ly - j1 lx) for Jl_k = (j0, j1)
+// (slam/solver_jacobians.cpp:51-89: the pose translation columns are minus the landmark columns, the theta column is
+// Jl . (ly, -lx)).  So S z = Hpp z - sum_k Jp_k^T (jh_k . u_l(k)),  u_l = Hll^-1 sum_k jh_k (Jp_k . z_pose(k)),
+// jh = sqrt(omega) Jl, needs TWO scalars per edge instead of the six of the block: 20 B per edge with its index word.
+// The factors are kept in two sliced-ELL layouts (landmark rows for t_l, pose rows for w), ~90 MB at 2 M edges: the
+// whole CG working set is L2-resident, every row is one lane's loop of coalesced, independent loads.
+//
+// Recurrences: Chronopoulos-Gear CG (one reduction point per iteration): z = M^-1 r, w = S z, gamma = r.z, delta = z.w,
+//   beta = gamma/gamma_old, alpha = gamma / (delta - beta gamma / alpha_old), p = z + beta p, s = w + beta s,
+//   x += alpha p, r -= alpha s.   delta is assembled WITHOUT w:
+//   delta = sum_i z_i.(Hpp_ii z_i) + sum_i z_i.(sum_nbr Hpp_ij z_j) - sum_l t_l.u_l
+//   phase L: (a) pose-parallel off-diagonal pose-pose products yoff_i = sum_nbr Hpp_ij z_j; (b) landmark rows:
+//            t_l over the row's lanes, u_l = Hll^-1 t_l stored per landmark.
+//   phase P: one lane per pose: w_i = Hpp_ii z_i + yoff_i - sum_k Jp_k^T (jh_k.u_l(k)) is complete locally, so the
+//            vector updates, z' = M^-1 r and the next gamma / delta parts follow in the same thread.
+enum { FS_GAMMA0 = 16, FS_DELTA0 = 19 };
+
+// -DBOS_PCG_TIMING: thread 0 of a few CTAs prints clock64 deltas per phase (diagnostic builds only)
+#ifdef BOS_PCG_TIMING
+#define PCG_T(k) do { if (threadIdx.x == 0) { long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; } } while (0)
+#else
+#define PCG_T(k) do { } while (0)
+#endif
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of the (cooperatively launched, hence co-resident) grid; counter only grows, zeroed before the launch
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& epoch) {
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * nblocks;
+        while (ld_acquire_u32(counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double block_sum_pcg(double v, double* red) {   // result valid in thread 0
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < kPcgThreads / 32; k++) s += red[k];
+    return s;
+}
+
+// 4-padded vectors: one 32-byte (FP64) / 16-byte (FP32) record per pose or landmark, read and written through L2 (.cg)
+__device__ __forceinline__ void ld4cg(const double* p, double& a, double& b, double& c, double& d) {
+    const double2 u = __ldcg(reinterpret_cast<const double2*>(p)), v = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    a = u.x; b = u.y; c = v.x; d = v.y;
+}
+__device__ __forceinline__ void ld4cg(const float* p, float& a, float& b, float& c, float& d) {
+    const float4 u = __ldcg(reinterpret_cast<const float4*>(p));
+    a = u.x; b = u.y; c = u.z; d = u.w;
+}
+__device__ __forceinline__ void st4cg(double* p, double a, double b, double c) {
+    __stcg(reinterpret_cast<double2*>(p), make_double2(a, b));
+    __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(c, 0.0));
+}
+__device__ __forceinline__ void st4cg(float* p, float a, float b, float c) { __stcg(reinterpret_cast<float4*>(p), make_float4(a, b, c, 0.f)); }
+__device__ __forceinline__ void st2cg(double* p, double a, double b) { __stcg(reinterpret_cast<double2*>(p), make_double2(a, b)); }
+__device__ __forceinline__ void st2cg(float* p, float a, float b) { __stcg(reinterpret_cast<float2*>(p), make_float2(a, b)); }
+
+// ---- once per GN iteration: per-edge factors in sorted-edge order, then gathered into the two ELL layouts ------------
+template <typename S>
+__global__ void __launch_bounds__(256) k_pcg_edge_factors(Dev<S> d, S* __restrict__ jP, int ld) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d.Eb) return;
+    const int p = __ldg(d.b_pose + k);
+    S j0 = S(0), j1 = S(0);
+    if (p != d.fixed) {   // the fixed pose's Jacobian block is zero (gauge): its edges drop out of Hpl
+        const PoseV<S> X = load_pose<S>(d.pose, p);
+        S lx, ly;
+        load_lm<S>(d.lm, __ldg(d.b_lm + k), lx, ly);
+        S err, J[5];
+        bearing_terms<S>(X, lx, ly, S(0), err, J);
+        const S so = sqrt(__ldg(d.b_om + k));
+        j0 = so * J[3]; j1 = so * J[4];
+    }
+    jP[k] = j0; jP[(size_t)ld + k] = j1;
+}
+template <typename S>
+__global__ void __launch_bounds__(256) k_ell_fill(Dev<S> d, PcgWork<S> w) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < d.n_clm) {   // Hll^-1, u = 0 and the landmark position in compact row order
+        const int L = __ldg(d.pl_lm_id + k);
+        w.hllinv_c[3LL * k] = w.hllinv[3LL * L]; w.hllinv_c[3LL * k + 1] = w.hllinv[3LL * L + 1]; w.hllinv_c[3LL * k + 2] = w.hllinv[3LL * L + 2];
+        w.ul4[4LL * k] = S(0); w.ul4[4LL * k + 1] = S(0); w.ul4[4LL * k + 2] = d.lm[2LL * L]; w.ul4[4LL * k + 3] = d.lm[2LL * L + 1];
+    }
+    if (k < d.nLs) {
+        const int e = __ldg(d.ell_Lmap + k);
+        w.Lj[k] = (e >= 0) ? w.jP[e] : S(0);
+        w.Lj[d.nLs + k] = (e >= 0) ? w.jP[(size_t)w.Eb_pad + e] : S(0);
+    }
+    if (k < d.nPs) {
+        const int e = __ldg(d.ell_Pmap + k);
+        w.Pj[k] = (e >= 0) ? w.jP[e] : S(0);
+        w.Pj[d.nPs + k] = (e >= 0) ? w.jP[(size_t)w.Eb_pad + e] : S(0);
+    }
+}
+
+// one thread per pose: reduced rhs g, diagonal block of S and its inverse, and the start vectors of the fused loop
+template <typename S>
+__global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) {
+    __shared__ double red[8];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double gz = 0.0, zw = 0.0;
+    if (p < d.NP) {
+        S g[3] = {-d.b[3LL * p], -d.b[3LL * p + 1], -d.b[3LL * p + 2]};
+        S hp[6], sd[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { hp[k] = d.Hpp[6LL * p + k]; sd[k] = hp[k]; }
+        for (int s = d.pose_ptr[p]; s < d.pose_ptr[p + 1]; s++) {
+            const S* B = d.Hpl + s;
+            const int l = d.slot_lm[s];
+            const S i00 = w.hllinv[3LL * l], i01 = w.hllinv[3LL * l + 1], i11 = w.hllinv[3LL * l + 2];
+            const S u0 = w.ul[2LL * l], u1 = w.ul[2LL * l + 1];
+            S b[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) b[k] = B[(long long)k * d.hpl_ld];
+            S y[6];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                g[a] += b[2 * a] * u0 + b[2 * a + 1] * u1;
+                y[2 * a] = b[2 * a] * i00 + b[2 * a + 1] * i01;
+                y[2 * a + 1] = b[2 * a] * i01 + b[2 * a + 1] * i11;
+            }
+            sd[0] -= y[0] * b[0] + y[1] * b[1];
+            sd[1] -= y[0] * b[2] + y[1] * b[3];
+            sd[2] -= y[0] * b[4] + y[1] * b[5];
+            sd[3] -= y[2] * b[2] + y[3] * b[3];
+            sd[4] -= y[2] * b[4] + y[3] * b[5];
+            sd[5] -= y[4] * b[4] + y[5] * b[5];
+        }
+        S mi[6];
+        sym3_inverse<S>(sd, mi);
+#pragma unroll
+        for (int k = 0; k < 6; k++) w.minv[6LL * p + k] = mi[k];
+        const S z[3] = {mi[0] * g[0] + mi[1] * g[1] + mi[2] * g[2], mi[1] * g[0] + mi[3] * g[1] + mi[4] * g[2],
+                        mi[2] * g[0] + mi[4] * g[1] + mi[5] * g[2]};
+        const S hz[3] = {hp[0] * z[0] + hp[1] * z[1] + hp[2] * z[2], hp[1] * z[0] + hp[3] * z[1] + hp[4] * z[2],
+                         hp[2] * z[0] + hp[4] * z[1] + hp[5] * z[2]};
+        const size_t np4 = 4 * (size_t)d.NP;
+        S* v = w.v4 + 4LL * p;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            v[a] = S(0); v[np4 + a] = S(0); v[2 * np4 + a] = S(0);          // p, s, x
+            v[3 * np4 + a] = (a < 3) ? g[a] : S(0);                           // r
+            w.z4[4LL * p + a] = (a < 3) ? z[a] : S(0);
+            w.z4[np4 + 4LL * p + a] = S(0);
+            w.yoff[4LL * p + a] = S(0);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            gz += (double)g[a] * (double)z[a];
+            zw += (double)z[a] * (double)hz[a];
+        }
+    }
+    double s1 = block_sum_256(gz, red);
+    __syncthreads();
+    double s2 = block_sum_256(zw, red);
+    if (threadIdx.x == 0) {
+        if (s1 != 0.0) atomicAdd(w.scal + FS_GAMMA0, s1);
+        if (s2 != 0.0) atomicAdd(w.scal + FS_DELTA0, s2);
+    }
+}
+
+// Landmark rows of the L layout, kEllLanesL lanes per row.  MODE 0: t_l from vec4 (= z), u_l = Hll^-1 t_l stored,
+// dacc -= t.u.   MODE 1: landmark back-substitution dx_l = Hll^-1 (-b_l - t_l) with vec4 = x.
+template <typename S, int MODE>
+__device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork<S>& w, const S* vec4, int wg, int nwarps, double& dacc) {
+    constexpr int RPG = 32 / kEllLanesL;
+    const int lane = threadIdx.x & 31;
+    const S* Lj0 = w.Lj;
+    const S* Lj1 = w.Lj + d.nLs;
+    for (int g = wg; g < d.nLg; g += nwarps) {
+        const int off = __ldg(d.ell_Loff + g), W = __ldg(d.ell_Loff + g + 1) - off;
+        const int row = g * RPG + lane / kEllLanesL;
+        const bool valid = row < d.n_clm;
+        S lx = S(0), ly = S(0);
+        if (valid) { lx = __ldg(w.ul4 + 4LL * row + 2); ly = __ldg(w.ul4 + 4LL * row + 3); }   // static half of the record
+        S t0 = S(0), t1 = S(0);
+        const long long s0 = (long long)off * 32 + lane;
+#pragma unroll 4
+        for (int t = 0; t < W; t++) {
+            const long long slot = s0 + (long long)t * 32;
+            const S j0 = __ldg(Lj0 + slot), j1 = __ldg(Lj1 + slot);
+            const int ps = __ldg(d.ell_Lpose + slot);
+            S z0, z1, z2, zp;
+            ld4cg(vec4 + 4LL * ps, z0, z1, z2, zp);
+            const S sc = (j0 * ly - j1 * lx) * z2 - j0 * z0 - j1 * z1;   // Jp_k . z
+            t0 += j0 * sc; t1 += j1 * sc;
+        }
+#pragma unroll
+        for (int o = 1; o < kEllLanesL; o <<= 1) {
+            t0 += __shfl_xor_sync(BOS_FULL_MASK, t0, o);
+            t1 += __shfl_xor_sync(BOS_FULL_MASK, t1, o);
+        }
+        if (valid && (lane % kEllLanesL) == 0) {
+            const S i00 = __ldg(w.hllinv_c + 3LL * row), i01 = __ldg(w.hllinv_c + 3LL * row + 1), i11 = __ldg(w.hllinv_c + 3LL * row + 2);
+            if (MODE == 0) {
+                const S u0 = i00 * t0 + i01 * t1, u1 = i01 * t0 + i11 * t1;
+                st2cg(w.ul4 + 4LL * row, u0, u1);
+                dacc -= (double)t0 * (double)u0 + (double)t1 * (double)u1;
+            } else {
+                const int L = __ldg(d.pl_lm_id + row);
+                const S r0 = -d.b[3LL * d.NP + 2LL * L] - t0, r1 = -d.b[3LL * d.NP + 2LL * L + 1] - t1;
+                d.delta[3LL * d.NP + 2LL * L] = i00 * r0 + i01 * r1;
+                d.delta[3LL * d.NP + 2LL * L + 1] = i01 * r0 + i11 * r1;
+            }
+        }
+    }
+}
+
+template <typename S>
+__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2) {
+    __shared__ double red[kPcgThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nwarps = gridDim.x * (kPcgThreads / 32);
+    const int wg = (tid >> 5) * gridDim.x + blockIdx.x;      // consecutive groups go to different SMs
+    unsigned epoch = 0;
+    double* sc = w.scal;
+    const size_t np4 = 4 * (size_t)d.NP;
+    const S* Pj0 = w.Pj;
+    const S* Pj1 = w.Pj + d.nPs;
+#ifdef BOS_PCG_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
+    const double gamma_init = __ldcg(sc + FS_GAMMA0);
+    double gamma_prev = 1.0, alpha_prev = 1.0;
+    int it = 0;
+    bool bad = false;
+    if (gamma_init > 0.0) {
+        for (; it < max_iters;) {
+            const int cur = it % 3, nxt = (it + 1) % 3, nn = (it + 2) % 3;
+            const S* zc = w.z4 + (size_t)(it & 1) * np4;
+            S* zn = w.z4 + (size_t)((it + 1) & 1) * np4;
+            // ---- phase L: off-diagonal pose-pose products, t_l / u_l per landmark, delta parts ---------------------------------
+            double dacc = 0.0;
+            for (int g = wg; g < d.nPg; g += nwarps) {
+                const int i = g * 32 + lane;
+                if (i >= d.NP) continue;
+                const int q0 = __ldg(d.pp_ptr + i), q1 = __ldg(d.pp_ptr + i + 1);
+                if (q0 == q1) continue;
+                S y0 = S(0), y1 = S(0), y2 = S(0);
+                for (int q = q0; q < q1; q++) {
+                    const int nb = __ldg(d.pp_nbr + q);
+                    const int sl = __ldg(d.pp_slot + q);
+                    const S* Bo = d.Hoff + 9LL * (sl & 0x7fffffff);
+                    S n0, n1, n2, np_;
+                    ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+                    if (sl >= 0) {
+                        y0 += Bo[0] * n0 + Bo[1] * n1 + Bo[2] * n2;
+                        y1 += Bo[3] * n0 + Bo[4] * n1 + Bo[5] * n2;
+                        y2 += Bo[6] * n0 + Bo[7] * n1 + Bo[8] * n2;
+                    } else {
+                        y0 += Bo[0] * n0 + Bo[3] * n1 + Bo[6] * n2;
+                        y1 += Bo[1] * n0 + Bo[4] * n1 + Bo[7] * n2;
+                        y2 += Bo[2] * n0 + Bo[5] * n1 + Bo[8] * n2;
+                    }
+                }
+                st4cg(w.yoff + 4LL * i, y0, y1, y2);
+                S z0, z1, z2, zp;
+                ld4cg(zc + 4LL * i, z0, z1, z2, zp);
+                dacc += (double)z0 * (double)y0 + (double)z1 * (double)y1 + (double)z2 * (double)y2;
+            }
+            PCG_T(0);
+            pcg_landmark_rows<S, 0>(d, w, zc, wg, nwarps, dacc);
+            PCG_T(1);
+            {
+                const double sdel = block_sum_pcg(dacc, red);
+                if (tid == 0 && sdel != 0.0) atomicAdd(sc + FS_DELTA0 + cur, sdel);
+            }
+            PCG_T(2);
+            grid_barrier(w.bar, gridDim.x, epoch);
+            PCG_T(3);
+            const double gamma = __ldcg(sc + FS_GAMMA0 + cur), delta = __ldcg(sc + FS_DELTA0 + cur);
+            const double beta = (it == 0) ? 0.0 : gamma / gamma_prev;
+            const double denom = (it == 0) ? delta : delta - beta * gamma / alpha_prev;
+            if (!(denom > 0.0)) { bad = true; break; }
+            const double alpha = gamma / denom;
+            if (blockIdx.x == 0 && tid == 0) { __stcg(sc + FS_GAMMA0 + nn, 0.0); __stcg(sc + FS_DELTA0 + nn, 0.0); }
+            // ---- phase P: one lane per pose: w_i, vector updates, preconditioner, next gamma / delta parts -------------------
+            const S al = (S)alpha, be = (S)beta;
+            double gacc = 0.0, dacc2 = 0.0;
+            for (int g = wg; g < d.nPg; g += nwarps) {
+                const int i = g * 32 + lane;
+                const bool valid = i < d.NP;
+                const int ic = valid ? i : d.NP - 1;
+                const int off = __ldg(d.ell_Poff + g), W = __ldg(d.ell_Poff + g + 1) - off;
+                S z0, z1, z2, zp, y0, y1, y2, yp;
+                ld4cg(zc + 4LL * ic, z0, z1, z2, zp);
+                ld4cg(w.yoff + 4LL * ic, y0, y1, y2, yp);
+                const S* hp = d.Hpp + 6LL * ic;
+                const S h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3), h4 = __ldg(hp + 4), h5 = __ldg(hp + 5);
+                S w0 = h0 * z0 + h1 * z1 + h2 * z2 + y0;
+                S w1 = h1 * z0 + h3 * z1 + h4 * z2 + y1;
+                S w2 = h2 * z0 + h4 * z1 + h5 * z2 + y2;
+                const long long s0 = (long long)off * 32 + lane;
+#pragma unroll 4
+                for (int t = 0; t < W; t++) {
+                    const long long slot = s0 + (long long)t * 32;
+                    const S j0 = __ldg(Pj0 + slot), j1 = __ldg(Pj1 + slot);
+                    const int c = __ldg(d.ell_Prow + slot);
+                    S u0, u1, lx, ly;
+                    ld4cg(w.ul4 + 4LL * c, u0, u1, lx, ly);
+                    const S m = j0 * u0 + j1 * u1;
+                    w0 += j0 * m; w1 += j1 * m; w2 -= (j0 * ly - j1 * lx) * m;
+                }
+                if (!valid) continue;
+                S* v = w.v4 + 4LL * i;
+                S p0, p1, p2, s0_, s1, s2, x0, x1, x2, r0, r1, r2, pad;
+                ld4cg(v, p0, p1, p2, pad); ld4cg(v + np4, s0_, s1, s2, pad); ld4cg(v + 2 * np4, x0, x1, x2, pad); ld4cg(v + 3 * np4, r0, r1, r2, pad);
+                p0 = z0 + be * p0; p1 = z1 + be * p1; p2 = z2 + be * p2;
+                s0_ = w0 + be * s0_; s1 = w1 + be * s1; s2 = w2 + be * s2;
+                x0 += al * p0; x1 += al * p1; x2 += al * p2;
+                r0 -= al * s0_; r1 -= al * s1; r2 -= al * s2;
+                st4cg(v, p0, p1, p2); st4cg(v + np4, s0_, s1, s2); st4cg(v + 2 * np4, x0, x1, x2); st4cg(v + 3 * np4, r0, r1, r2);
+                const S* mi = w.minv + 6LL * i;
+                const S m0 = __ldg(mi), m1 = __ldg(mi + 1), m2 = __ldg(mi + 2), m3 = __ldg(mi + 3), m4 = __ldg(mi + 4), m5 = __ldg(mi + 5);
+                const S zn0 = m0 * r0 + m1 * r1 + m2 * r2, zn1 = m1 * r0 + m3 * r1 + m4 * r2, zn2 = m2 * r0 + m4 * r1 + m5 * r2;
+                st4cg(zn + 4LL * i, zn0, zn1, zn2);
+                gacc += (double)r0 * (double)zn0 + (double)r1 * (double)zn1 + (double)r2 * (double)zn2;
+                dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
+                         (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
+            }
+            PCG_T(4);
+            {
+                const double sg = block_sum_pcg(gacc, red);
+                const double sd2 = block_sum_pcg(dacc2, red);
+                if (tid == 0) {
+                    if (sg != 0.0) atomicAdd(sc + FS_GAMMA0 + nxt, sg);
+                    if (sd2 != 0.0) atomicAdd(sc + FS_DELTA0 + nxt, sd2);
+                }
+            }
+            PCG_T(5);
+            grid_barrier(w.bar, gridDim.x, epoch);
+            PCG_T(6);
+            gamma_prev = gamma; alpha_prev = alpha;
+            it++;
+            const double gnew = __ldcg(sc + FS_GAMMA0 + nxt);
+            if (!(gnew > tol2 * gamma_init)) break;
+        }
+    }
+    // ---- epilogue: dx_p = x, dx_l by back-substitution -------------------------------------------------------------------
+    const S* x4 = w.v4 + 2 * np4;
+    const int gtid = blockIdx.x * kPcgThreads + tid, gsz = gridDim.x * kPcgThreads;
+    for (int i = gtid; i < d.NP; i += gsz) {
+        S x0, x1, x2, xp;
+        ld4cg(x4 + 4LL * i, x0, x1, x2, xp);
+        d.delta[3LL * i] = x0; d.delta[3LL * i + 1] = x1; d.delta[3LL * i + 2] = x2;
+    }
+    for (int l = gtid; l < d.NL; l += gsz)
+        if (__ldg(d.tri_ptr + l) == __ldg(d.tri_ptr + l + 1)) {   // unobserved landmark: dx_l = -Hll^-1 b_l
+            d.delta[3LL * d.NP + 2LL * l] = -w.ul[2LL * l];
+            d.delta[3LL * d.NP + 2LL * l + 1] = -w.ul[2LL * l + 1];
+        }
+    double unused = 0.0;
+    pcg_landmark_rows<S, 1>(d, w, x4, wg, nwarps, unused);
+    if (gtid == 0) { sc[SC_ITER] = (double)it; sc[SC_BAD] = bad ? 1.0 : 0.0; }
+#ifdef BOS_PCG_TIMING
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2))
+        printf("cta %d iters %d cycles/iter: offdiag %lld Lrows %lld bsum %lld bar1 %lld phaseP %lld bsum2 %lld bar2 %lld\n", (int)blockIdx.x, it,
+               tacc[0] / (it ? it : 1), tacc[1] / (it ? it : 1), tacc[2] / (it ? it : 1), tacc[3] / (it ? it : 1), tacc[4] / (it ? it : 1),
+               tacc[5] / (it ? it : 1), tacc[6] / (it ? it : 1));
+#endif
+}
+
+template <typename S>
+int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st, int* iterations_out, int* launches) {
+    int nl = 0;
+    const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256;
+    cudaMemsetAsync(w.scal, 0, 32 * sizeof(double), st);
+    cudaMemsetAsync(w.bar, 0, 4 * sizeof(unsigned), st);
+    if (d.NL > 0) { k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++; }
+    if (d.Eb > 0) {
+        k_pcg_edge_factors<S><<<(d.Eb + 255) / 256, 256, 0, st>>>(d, w.jP, w.Eb_pad); nl++;
+        long long n = d.nLs > d.nPs ? d.nLs : d.nPs;
+        if (n < d.n_clm) n = d.n_clm;
+        k_ell_fill<S><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, w); nl++;
+    }
+    k_pcg_fused_prep<S><<<gp, 256, 0, st>>>(d, w); nl++;
+    int grid = (d.nPg > d.nLg ? d.nPg : d.nLg);                 // groups of 32 rows: one warp each
+    grid = (grid + kPcgThreads / 32 - 1) / (kPcgThreads / 32);
+    if (grid > w.sm_count) grid = w.sm_count;
+    if (grid < 1) grid = 1;
+    Dev<S> dd = d;
+    PcgWork<S> ww = w;
+    double tol2 = rtol * rtol;
+    void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2};
+    if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(grid), dim3(kPcgThreads), args, 0, st) != cudaSuccess) return -1;
+    nl++;
+    double host_scal[32];
+    if (cudaMemcpyAsync(host_scal, w.scal, 32 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (iterations_out) *iterations_out = (int)host_scal[SC_ITER];
+    if (launches) *launches = nl;
+    return host_scal[SC_BAD] != 0.0 ? 1 : 0;
+}
+
 template <typename S>
 int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st,
                      int* iterations_out, int* launches) {
+    if (w.variant == 0) return launch_pcg_fused<S>(d, w, max_iters, rtol, st, iterations_out, launches);
     int nl = 0;
     const int n = 3 * d.NP;
     const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256, gh = (d.n_hpl + 255) / 256, gn = (n + 255) / 256;

@@ -353,3 +353,34 @@ def test_large_world_size_independent_properties(built_lib):
     for _ in range(4):
         s = ctx.step(); chi.append(s.chi2_bearing + s.chi2_odometry)
     assert chi[-1] < 0.5 * chi[0] and s.pcg_iterations > 0
+
+
+def test_pcg_fused_kernel_equals_classic_loop(built_lib):
+    """The persistent cooperative PCG kernel (Chronopoulos-Gear recurrences, RED scatter) and the classic multi-kernel loop
+    solve the same system: same dx to solver tolerance, on a world with duplicate blocks, unobserved and single-observation
+    landmarks (exercises the padded tile layout)."""
+    from prb_project_bearing_only_slam_b200.problem import Problem
+    w, pr0 = synth_problem(3000, 700, 30000, seed=5)
+    lm_ids = np.concatenate([pr0.lm_ids, [10 ** 6, 10 ** 6 + 1]]).astype(np.int32)      # two landmarks nobody observes
+    bp = np.concatenate([w["b_pose_id"], w["b_pose_id"][:50]]); bl = np.concatenate([w["b_lm_id"], w["b_lm_id"][:50]])
+    bz = np.concatenate([w["b_z"], w["b_z"][:50] + 0.002])
+    pr = Problem(w["pose_ids"], bp, bl, bz, w["o_src_id"], w["o_dst_id"], w["o_z"], w["o_omega"], fixed_pose_id=int(w["pose_ids"][5]),
+                 lm_ids=lm_ids)
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr0)
+    P, L0 = o.state()
+    L = np.vstack([L0, [[1.0, 2.0], [3.0, 4.0]]])
+    ds, its = [], []
+    for variant in (0, 1):
+        ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-12, pcg_max_iters=20000, pcg_variant=variant)
+        ctx.linearize(); ctx.solve()
+        ds.append(ctx.delta()); its.append(ctx.stats().pcg_iterations)
+        if variant == 0:
+            import scipy.sparse as sp
+            colptr, rowidx, val, b = ctx.csc()
+            n = len(colptr) - 1
+            H = sp.csc_matrix((val, rowidx, colptr), shape=(n, n))
+            r = H @ nofixed(pr, ds[0]) + b
+            assert np.abs(r).max() <= 1e-9 * np.abs(b).max()
+    assert np.abs(ds[0] - ds[1]).max() <= 1e-8 * np.abs(ds[1]).max()
+    assert np.all(ds[0][-4:] == 0.0)                                                     # unobserved landmarks: b_l = 0 -> dx_l = 0
+    assert its[0] > 0 and abs(its[0] - its[1]) <= 0.2 * its[1] + 5
