@@ -127,6 +127,20 @@ BOS_API int bos_get_stats(bos_ctx* ctx, bos_stats* stats);
  * number of landmarks with exactly one observation (the reference's console warning, :38-42). */
 BOS_API int bos_triangulate(bos_ctx* ctx, int* single_obs_count);
 
+/* ---- context-free forms (what the reference's free function / per-edge methods would bind) -------------------- */
+/* triangulate_landmarks(State&, const BearingObservationVector&) (slam/triangulation.hpp:8, triangulation.cpp:5-74):
+ * poses_xycs [NP][4]; bearing edges with pose stix and landmark index 0..NL-1 in ASCENDING landmark id (the stix
+ * order in which the reference adds them, triangulation.cpp:65-74); writes lms_xy [NL][2].  opts may be NULL. */
+BOS_API int bos_triangulate_landmarks(const bos_options* opts, int NP, const double* poses_xycs, int64_t Eb, const int32_t* b_pose,
+                              const int32_t* b_lm, const double* b_z, int NL, double* lms_xy, int* single_obs_count);
+/* Solver::error_and_jacobian (slam/solver.hpp:35-37) for n independent edges, evaluated on the device:
+ * bearing: poses_xycs [n][4], lms_xy [n][2], z [n] -> err [n], jac [n][5] = [J_pose | J_lm];
+ * odometry: src/dst [n][4], z [n][3] -> err [n][3], jac [n][18] = 3x6 row-major [J_src | J_dst]. */
+BOS_API int bos_eval_bearing_edges(const bos_options* opts, int64_t n, const double* poses_xycs, const double* lms_xy, const double* z,
+                           double* err, double* jac5);
+BOS_API int bos_eval_odometry_edges(const bos_options* opts, int64_t n, const double* src_xycs, const double* dst_xycs, const double* z3,
+                            double* err3, double* jac18);
+
 /* ---- parity / inspection (tests and the harness; not on the hot path) ------------------------ */
 typedef struct bos_pattern_info {
     int64_t n_hpl;        /* unique (pose, landmark) blocks, 3x2 */

@@ -55,6 +55,7 @@ SYMBOLS = [
     "bos_set_edge_shard", "bos_get_edge_shard", "bos_batch_create", "bos_batch_destroy", "bos_batch_set_states",
     "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error", "bos_synth_default_spec",
     "bos_synth_create", "bos_synth_destroy", "bos_synth_counts", "bos_synth_get",
+    "bos_triangulate_landmarks", "bos_eval_bearing_edges", "bos_eval_odometry_edges",
 ]
 
 _lib = None
@@ -116,6 +117,9 @@ def lib():
         L.bos_synth_destroy.argtypes = [vp]
         L.bos_synth_counts.argtypes = [vp, vp]
         L.bos_synth_get.argtypes = [vp] + [vp] * 12
+        L.bos_triangulate_landmarks.argtypes = [C.POINTER(Options), i32, vp, i64, vp, vp, vp, i32, vp, C.POINTER(C.c_int)]
+        L.bos_eval_bearing_edges.argtypes = [C.POINTER(Options), i64, vp, vp, vp, vp, vp]
+        L.bos_eval_odometry_edges.argtypes = [C.POINTER(Options), i64, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

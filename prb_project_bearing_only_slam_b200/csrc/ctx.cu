@@ -738,6 +738,54 @@ int bos_edge_terms(bos_ctx* c, double* err_b, double* jac_b, double* err_o, doub
     return DISPATCH(c, edge_terms_impl, c, err_b, jac_b, err_o, jac_o);
 }
 
+int bos_triangulate_landmarks(const bos_options* opts, int NP, const double* poses, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm,
+                              const double* b_z, int NL, double* lms, int* single_obs_count) {
+    if (!poses || !lms || NP <= 0 || NL < 0 || Eb < 0) return BOS_ERR_INVALID;
+    bos_ctx* c = nullptr;
+    int rc = bos_create(opts, &c);
+    if (rc) return rc;
+    rc = bos_upload_problem(c, NP, NL, 0, Eb, b_pose, b_lm, b_z, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+    if (!rc) rc = bos_set_state(c, poses, nullptr);
+    if (!rc) rc = bos_triangulate(c, single_obs_count);
+    if (!rc) rc = bos_get_state(c, nullptr, lms);
+    bos_destroy(c);
+    return rc;
+}
+
+int bos_eval_bearing_edges(const bos_options* opts, int64_t n, const double* poses, const double* lms, const double* z, double* err, double* jac5) {
+    if (n <= 0 || n > 0x3fffffff || !poses || !lms || !z || !err || !jac5) return BOS_ERR_INVALID;
+    std::vector<int32_t> idx((size_t)n);
+    for (int64_t i = 0; i < n; i++) idx[(size_t)i] = (int32_t)i;
+    bos_ctx* c = nullptr;
+    int rc = bos_create(opts, &c);
+    if (rc) return rc;
+    rc = bos_upload_problem(c, (int)n, (int)n, 0, n, idx.data(), idx.data(), z, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+    if (!rc) rc = bos_set_state(c, poses, lms);
+    if (!rc) rc = bos_edge_terms(c, err, jac5, nullptr, nullptr);
+    bos_destroy(c);
+    return rc;
+}
+
+int bos_eval_odometry_edges(const bos_options* opts, int64_t n, const double* src, const double* dst, const double* z3, double* err3, double* jac18) {
+    if (n <= 0 || n > 0x1fffffff || !src || !dst || !z3 || !err3 || !jac18) return BOS_ERR_INVALID;
+    std::vector<int32_t> s((size_t)n), t((size_t)n);
+    std::vector<double> poses(8 * (size_t)n), om(9 * (size_t)n, 0.0);
+    for (int64_t i = 0; i < n; i++) {
+        s[(size_t)i] = (int32_t)i; t[(size_t)i] = (int32_t)(n + i);
+        std::copy(src + 4 * i, src + 4 * i + 4, poses.begin() + 4 * i);
+        std::copy(dst + 4 * i, dst + 4 * i + 4, poses.begin() + 4 * (n + i));
+        om[9 * (size_t)i] = om[9 * (size_t)i + 4] = om[9 * (size_t)i + 8] = 1.0;
+    }
+    bos_ctx* c = nullptr;
+    int rc = bos_create(opts, &c);
+    if (rc) return rc;
+    rc = bos_upload_problem(c, (int)(2 * n), 0, 0, 0, nullptr, nullptr, nullptr, nullptr, n, s.data(), t.data(), z3, om.data());
+    if (!rc) rc = bos_set_state(c, poses.data(), nullptr);
+    if (!rc) rc = bos_edge_terms(c, nullptr, nullptr, err3, jac18);
+    bos_destroy(c);
+    return rc;
+}
+
 int bos_nccl_unique_id(char* uid128) {
     if (!uid128) return BOS_ERR_INVALID;
     NcclApi& n = nccl();

@@ -63,3 +63,25 @@ def csc_rel_err(colptr, val_a, val_b):
 def angle_diff(a, b):
     d = np.asarray(a) - np.asarray(b)
     return (d + np.pi) % (2 * np.pi) - np.pi
+
+
+def write_g2o_from_golden(g, path, ground_truth=False):
+    """Writes a g2o file holding the golden fixture's problem (values are float32-exact, %.9g round-trips through std::stof):
+    the initial-guess flavour (poses, FIX, edges) or the ground-truth flavour (landmarks + poses of the GT file, same edges)."""
+    with open(path, "w") as f:
+        if ground_truth:
+            for i, (x, y) in zip(g["gt_lm_ids"], g["gt_lms_xy"]):
+                f.write("VERTEX_XY %d %.9g %.9g\n" % (i, x, y))
+            ids, xyt = g["gt_pose_ids"], g["gt_poses_xyt"]
+        else:
+            ids, xyt = g["pose_ids"], g["poses_xyt"]
+        for i, (x, y, t) in zip(ids, xyt):
+            f.write("VERTEX_SE2 %d %.9g %.9g %.9g\n" % (i, x, y, t))
+        f.write("FIX %d\n" % int(g["fixed_pose_id"]))
+        for s, d, z, om in zip(g["o_src_id"], g["o_dst_id"], g["o_z"], g["o_omega"].reshape(-1, 3, 3)):
+            f.write("EDGE_SE2 %d %d %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n" % (s, d, z[0], z[1], z[2], om[0, 0], om[0, 1], om[0, 2],
+                                                                                       om[1, 1], om[1, 2], om[2, 2]))
+        for p, l, z in zip(g["b_pose_id"], g["b_lm_id"], g["b_z"]):
+            f.write("EDGE_BEARING_SE2_XY %d %d %.9g 57295.8\n" % (p, l, z))
+        f.write("\nSOMETHING_ELSE 1 2 3\n")     # the loader prints "Unrecognized SOMETHING_ELSE" and carries on
+    return path

@@ -1,0 +1,104 @@
+"""The C++ host mirror of the reference's API (prb_project_bearing_only_slam_b200/host): State / observations / parse_g2o /
+triangulate_landmarks / Solver with the reference's names and call sequence, driven by tests/cpp/test_host_api.cpp (a
+machine-checkable restatement of the reference's manual tests) and by the headless harness."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, write_g2o_from_golden
+
+
+@pytest.fixture(scope="session")
+def host_test_exe(built_lib, tmp_path_factory):
+    from prb_project_bearing_only_slam_b200 import build_host
+    build_host.build()
+    out = str(tmp_path_factory.mktemp("hostcpp") / "test_host_api")
+    here = os.path.dirname(os.path.abspath(__file__))
+    return build_host.build_test(os.path.join(here, "cpp", "test_host_api.cpp"), out)
+
+
+def kv(text):
+    return dict(re.findall(r"(\w+)=(\S+)", text))
+
+
+@pytest.mark.parametrize("name", ["mini", "full"])
+def test_host_api_cpu_side(host_test_exe, tmp_path, name):
+    g = load_golden(name)
+    ig = write_g2o_from_golden(g, str(tmp_path / (name + "_ig.g2o")))
+    r = subprocess.run([host_test_exe, "cpu", ig], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = kv(r.stdout)
+    assert out["failures"] == "0"
+    assert "Unrecognized SOMETHING_ELSE" in r.stdout and "Warning: no poses found" in r.stdout
+    assert (int(out["poses"]), int(out["landmarks"]), int(out["bearings"]), int(out["odometries"])) == (
+        len(g["pose_ids"]), 0, len(g["b_z"]), len(g["o_src_id"]))
+    assert int(out["fixed"]) == int(g["fixed_pose_id"])
+    assert float(out["bound"]) == pytest.approx(float(g["bound"]), rel=1e-6)
+    p0 = re.search(r"pose0=(\S+) (\S+) (\S+) (\S+)", r.stdout).groups()
+    assert int(p0[0]) == int(g["pose_ids"][0])
+    assert np.allclose([float(x) for x in p0[1:3]], g["poses_xyt"][0][:2], rtol=1e-6, atol=1e-7)
+    e0 = re.search(r"edge0=(\S+) (\S+) (\S+)", r.stdout).groups()
+    assert (int(e0[0]), int(e0[1])) == (int(g["b_pose_id"][0]), int(g["b_lm_id"][0])) and float(e0[2]) == pytest.approx(float(g["b_z"][0]), rel=1e-7)
+
+
+def test_headless_harness_usage_and_missing_file(host_test_exe):
+    from prb_project_bearing_only_slam_b200 import build_host
+    r = subprocess.run([build_host.EXE], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "usage: bearing_only_slam <dataset_fname>" in r.stdout
+    r = subprocess.run([build_host.EXE, "/nonexistent.g2o"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "Warning: no poses found" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,iters", [("mini", 20), ("full", 30)])
+def test_host_api_on_the_device(host_test_exe, tmp_path, name, iters):
+    g = load_golden(name)
+    ig = write_g2o_from_golden(g, str(tmp_path / (name + "_ig.g2o")))
+    gt = write_g2o_from_golden(g, str(tmp_path / (name + "_gt.g2o")), ground_truth=True)
+    r = subprocess.run([host_test_exe, "gpu", ig, gt, str(iters)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr
+    out = kv(r.stdout)
+    assert out["failures"] == "0"
+    # landmarks are added in ascending id order with the oracle's triangulated positions (float state)
+    tri = np.array([[float(a), float(b), float(c)] for a, b, c in re.findall(r"^tri (\S+) (\S+) (\S+)$", r.stdout, re.M)])
+    assert np.array_equal(tri[:, 0].astype(int), g["lm_ids"]) and np.all(np.diff(tri[:, 0]) > 0)
+    assert np.abs(tri[:, 1:] - g["lms_tri_f64"]).max() <= 2e-6 * max(1.0, np.abs(g["lms_tri_f64"]).max())
+    n_single = len(g["single_obs_f64"])
+    assert r.stdout.count("only has one observation") == n_single
+    # per-iteration chi2 follows the oracle's trajectory from the same (float-rounded) start
+    chi = np.array([[float(a), float(b)] for a, b in re.findall(r"chi2_bearing=(\S+) chi2_odometry=(\S+)", r.stdout)])
+    t = g["trajectory_f64"]
+    assert len(chi) == iters
+    assert chi[0, 0] == pytest.approx(t[0, 0], rel=1e-4) and chi[-1, 0] == pytest.approx(t[iters - 1, 0], rel=2e-3)
+    assert chi[-1, 1] == pytest.approx(t[iters - 1, 1], rel=2e-3, abs=1e-9)
+    assert all(s == "0" for s in re.findall(r"status=(\d)", r.stdout))
+    # the reference's own pinned numbers (tests/solver_stuff.cpp:82-88, 156-162): FP32 central differences, 2 significant digits
+    assert float(out["predict_odometry_worst"]) < 2e-3
+    if name == "full":
+        m = re.search(r"bearing_jacobian highest_sum=(\S+) highest_max=(\S+) average_sum=(\S+) average_max=(\S+)", r.stdout).groups()
+        assert float(m[0]) < 0.03 and float(m[2]) < 2e-3
+        m = re.search(r"odom_jacobian highest_sum=(\S+) highest_max=(\S+) average_sum=(\S+) average_max=(\S+)", r.stdout).groups()
+        assert float(m[0]) < 0.01 and float(m[2]) == pytest.approx(0.0017143, rel=0.5)
+    # a caller-side edit of solver.state is uploaded before the next step
+    assert float(out["nudge_recovery"]) < 0.5
+
+
+@pytest.mark.gpu
+def test_headless_harness_on_the_full_dataset(host_test_exe, tmp_path):
+    from prb_project_bearing_only_slam_b200 import build_host
+    g = load_golden("full")
+    ig = write_g2o_from_golden(g, str(tmp_path / "full_ig.g2o"))
+    outp = str(tmp_path / "final.g2o")
+    r = subprocess.run([build_host.EXE, ig, "--iters", "30", "--out", outp], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr
+    final = float(re.search(r"final_chi2 (\S+)", r.stdout).group(1))
+    t = g["trajectory_f64"]
+    assert final == pytest.approx(t[29, 0] + t[29, 1], rel=2e-3)
+    lines = open(outp).read().splitlines()
+    assert sum(l.startswith("VERTEX_SE2") for l in lines) == 301 and sum(l.startswith("VERTEX_XY") for l in lines) == 141
+    # the written poses are where the oracle converges
+    P = np.array([[float(x) for x in l.split()[2:5]] for l in lines if l.startswith("VERTEX_SE2")])
+    assert np.abs(P[:, :2] - g["poses_final_f64"][:, :2]).max() < 5e-3
