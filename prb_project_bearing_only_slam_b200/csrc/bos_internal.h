@@ -69,7 +69,7 @@ struct Dev {
     const int* ell_Lpose = nullptr;  // [nLs] pose of the slot (0 for padding; the factor is 0 there)
     const int* ell_Poff = nullptr;   // [nPg+1]
     const int* ell_Pmap = nullptr;   // [nPs]
-    const int* ell_Prow = nullptr;   // [nPs] compact landmark row of the slot
+    const int* ell_Prow = nullptr;   // [nPs] compact landmark row of the slot, -1 for padding
     const int* tri_ptr = nullptr;    // [NL+1] bearing edges grouped by landmark (caller order inside a landmark)
     const int* tri_edge = nullptr;   // [Eb] sorted-edge index
     // state
@@ -136,12 +136,14 @@ struct PcgWork {
     // so two scalars per edge (sqrt(omega) Jl) replace the six of the block.
     S* jP = nullptr;               // [2][Eb_pad] factors in sorted-edge order (scratch of the fill)
     S* Lj = nullptr;               // [2][nLs] factors in the landmark-major ELL layout
-    S* Pj = nullptr;               // [2][nPs] factors in the pose-major ELL layout
+    S* Pw = nullptr;               // [nPs] sqrt(omega) per pose-major slot; only when the bearing omegas are not all equal
+    int omega_uniform = 1;         // all bearing omegas equal: the pose-major pass recomputes its factors from the state
+    double sqrt_omega = 1.0;       // ... with this scale
     S* hllinv_c = nullptr;         // [n_clm][3] Hll^-1 in compact row order
     S* ul4 = nullptr;              // [n_clm][4] u_l = Hll^-1 t_l (rewritten every CG iteration) and the landmark position lx, ly
     S* z4 = nullptr;               // [2][NP][4] double-buffered z (padded to one 32-byte sector per pose)
-    S* v4 = nullptr;               // [4][NP][4] p, s, x, r padded the same way
-    S* yoff = nullptr;             // [NP][4] off-diagonal pose-pose part of S z
+    S* vS = nullptr;               // [15][NP] p, s, x, r, yoff by component: home of the pose vectors that do not fit in the
+                                   // persistent kernel's shared memory, and hand-over buffer (r in, x out) for those that do
     int Eb_pad = 0;
     double* scal = nullptr;  // [32] classic: rz, pAp, rz_new, rz0, done flag, iterations ...; fused: see solve_pcg.cu
     unsigned* bar = nullptr; // [4] grid barrier counter of the fused kernel

@@ -70,6 +70,22 @@ __device__ __forceinline__ void load_lm(const S* __restrict__ lm, int j, S& lx, 
     lx = v.x; ly = v.y;
 }
 
+// Landmark half of the bearing Jacobian, J_lm = a R^T with a = [-gy, gx] / |g|^2 (slam/solver_jacobians.cpp:32-49, 85-89).
+// The pose half follows from it: J_pose = (-J_lm[0], -J_lm[1], J_lm . (ly, -lx)).  Shared by the assembly path's
+// bearing_terms and by the PCG operator, which re-derives its per-edge factors from the state.
+template <typename S>
+__device__ __forceinline__ void bearing_jl(const PoseV<S>& X, S lx, S ly, S& j0, S& j1) {
+    const S c = X.c, s = X.s;
+    const S itx = (-c) * X.x + (-s) * X.y;
+    const S ity = s * X.x + (-c) * X.y;
+    const S gx = (c * lx + s * ly) + itx;
+    const S gy = ((-s) * lx + c * ly) + ity;
+    const S f = S(1) / (gx * gx + gy * gy);
+    const S a0 = f * (-gy), a1 = f * gx;
+    j0 = a0 * c + a1 * (-s);
+    j1 = a0 * s + a1 * c;
+}
+
 // Bearing error and 1x5 Jacobian [J_pose(3) | J_lm(2)]  (slam/solver_jacobians.cpp:9-95, 301-305).
 // g = X^-1 * l with Eigen's isometry inverse: R^T l + (-(R^T) t); J = a * [-R^T | R^T (ly,-lx)^T | R^T],
 // a = [-gy, gx] / |g|^2.  The world-frame landmark appears in the theta column because boxplus is a

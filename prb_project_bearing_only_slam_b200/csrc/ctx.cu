@@ -105,6 +105,7 @@ struct bos_ctx {
     int shard_chunk_b = 0;
     int launches = 0;
     bool pcg_bad = false;
+    std::vector<double> b_omega_sorted;   // bearing omegas in sorted-edge order (host copy for the PCG setup)
 
     bool f64() const { return opt.precision == BOS_PRECISION_F64; }
 };
@@ -165,9 +166,11 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     d.hpl_ld = (d.n_hpl + 3) / 4 * 4 + 8 * kLinTile;   // room for up to 8 tile-padded rank shards   // room for the padded in-place allgather of rank shards
     std::vector<S> bz(d.Eb_pad, S(0)), bom(d.Eb_pad, S(0));
     std::vector<int> bpose(d.Eb_pad, P.Eb ? P.b_pose[P.Eb - 1] : 0), blm(d.Eb_pad, 0), bslot(d.Eb_pad, 0);
+    c->b_omega_sorted.assign(P.Eb, 1.0);
     for (int k = 0; k < P.Eb; k++) {
         bz[k] = (S)b_z[P.b_perm[k]];
         bom[k] = b_omega ? (S)b_omega[P.b_perm[k]] : S(1);
+        if (b_omega) c->b_omega_sorted[k] = (double)bom[k];
         bpose[k] = P.b_pose[k]; blm[k] = P.b_lm[k]; bslot[k] = P.b_slot[k];
     }
     d.has_shared_off = P.has_shared_off ? 1 : 0;
@@ -209,11 +212,13 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     d.Hll = d.Hpp + 6 * (size_t)P.NP;
     d.Hoff = d.Hll + 3 * (size_t)P.NL;
     d.Hpl = d.vals + c->vals_prefix;
-    CUDA_OK(c, cudaMemset(d.vals, 0, (c->vals_prefix + c->hpl_padded) * sizeof(S)));
-    CUDA_OK(c, cudaMemset(d.delta, 0, (size_t)P.N * sizeof(S)));
-    CUDA_OK(c, cudaMemset(d.stats, 0, 8 * sizeof(double)));
-    CUDA_OK(c, cudaMemset(d.pose, 0, 4 * (size_t)P.NP * sizeof(S)));
-    CUDA_OK(c, cudaMemset(d.lm, 0, 2 * (size_t)std::max(P.NL, 1) * sizeof(S)));
+    // on the context's own (non-blocking) stream: a legacy-stream memset is not ordered with later copies on that stream
+    CUDA_OK(c, cudaMemsetAsync(d.vals, 0, (c->vals_prefix + c->hpl_padded) * sizeof(S), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(d.delta, 0, (size_t)P.N * sizeof(S), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(d.stats, 0, 8 * sizeof(double), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(d.pose, 0, 4 * (size_t)P.NP * sizeof(S), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(d.lm, 0, 2 * (size_t)std::max(P.NL, 1) * sizeof(S), c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return BOS_OK;
 }
 
@@ -249,13 +254,26 @@ int ensure_pcg(bos_ctx* c) {
     w.Eb_pad = d.Eb_pad;
     w.jP = c->mem.get<S>(2 * (size_t)std::max(d.Eb_pad, 4));
     w.Lj = c->mem.get<S>(2 * (size_t)std::max(d.nLs, 32LL));
-    w.Pj = c->mem.get<S>(2 * (size_t)std::max(d.nPs, 32LL));
+    {   // bearing omegas: one value for all edges is the common case (the reference never sets another, observation.hpp:17)
+        const HostPattern& P = c->P;
+        w.omega_uniform = 1; w.sqrt_omega = 1.0;
+        const std::vector<double>& om = c->b_omega_sorted;
+        if (!om.empty()) {
+            for (double v : om) if (v != om[0]) { w.omega_uniform = 0; break; }
+            w.sqrt_omega = std::sqrt(om[0]);
+        }
+        if (!w.omega_uniform) {
+            std::vector<S> pw(P.ell_Pmap.size(), S(0));
+            for (size_t k = 0; k < pw.size(); k++) if (P.ell_Pmap[k] >= 0) pw[k] = (S)std::sqrt(om[P.ell_Pmap[k]]);
+            w.Pw = c->mem.upload(pw);
+            if (!w.Pw) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+        }
+    }
     w.hllinv_c = c->mem.get<S>(3 * (size_t)std::max(d.n_clm, 1));
     w.ul4 = c->mem.get<S>(4 * (size_t)std::max(d.n_clm, 1));
     w.z4 = c->mem.get<S>(8 * (size_t)d.NP);
-    w.v4 = c->mem.get<S>(16 * (size_t)d.NP);
-    w.yoff = c->mem.get<S>(4 * (size_t)d.NP);
-    if (!w.jP || !w.Lj || !w.Pj || !w.hllinv_c || !w.ul4 || !w.z4 || !w.v4 || !w.yoff) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+    w.vS = c->mem.get<S>(15 * (size_t)d.NP);
+    if (!w.jP || !w.Lj || !w.hllinv_c || !w.ul4 || !w.z4 || !w.vS) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
     c->pcg_ready = true;
     return BOS_OK;
 }

@@ -122,7 +122,7 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
             P.ell_Poff[g + 1] = P.ell_Poff[g] + wmax;
         }
         P.ell_Pmap.assign((size_t)P.ell_Poff[nPg] * 32, -1);
-        P.ell_Prow.assign((size_t)P.ell_Poff[nPg] * 32, 0);
+        P.ell_Prow.assign((size_t)P.ell_Poff[nPg] * 32, -1);
         for (int i = 0; i < NP; i++)
             for (int k = P.epose_ptr[i]; k < P.epose_ptr[i + 1]; k++) {
                 const size_t slot = ((size_t)P.ell_Poff[i / 32] + (k - P.epose_ptr[i])) * 32 + i % 32;

@@ -232,19 +232,25 @@ __global__ void k_pcg_promote(double* scal) {
 // the landmark Jacobian and the landmark position: Jp_k = (-j0, -j1, j0 ly - j1 lx) for Jl_k = (j0, j1)
 // (slam/solver_jacobians.cpp:51-89: the pose translation columns are minus the landmark columns, the theta column is
 // Jl . (ly, -lx)).  So S z = Hpp z - sum_k Jp_k^T (jh_k . u_l(k)),  u_l = Hll^-1 sum_k jh_k (Jp_k . z_pose(k)),
-// jh = sqrt(omega) Jl, needs TWO scalars per edge instead of the six of the block: 20 B per edge with its index word.
-// The factors are kept in two sliced-ELL layouts (landmark rows for t_l, pose rows for w), ~90 MB at 2 M edges: the
-// whole CG working set is L2-resident, every row is one lane's loop of coalesced, independent loads.
+// jh = sqrt(omega) Jl, needs TWO scalars per edge instead of the six of the block.
+//   landmark-major pass: the factors are stored (20 B per edge with the pose word) in a sliced-ELL layout, 4 lanes per row;
+//   pose-major pass:     one lane per pose; the lane holds its pose, each slot gathers one 32-byte landmark record
+//                        (u_l and the landmark position) and RE-DERIVES jh from the state: 4 B per edge.
+// The pose vectors p, s, x, r and the off-diagonal product live in SHARED MEMORY for the whole solve (a pose is owned by
+// one lane of one CTA for all iterations); only z crosses CTAs.  Per CG iteration ~110 MB are touched at 2 M edges,
+// all of it L2-resident.
 //
 // Recurrences: Chronopoulos-Gear CG (one reduction point per iteration): z = M^-1 r, w = S z, gamma = r.z, delta = z.w,
 //   beta = gamma/gamma_old, alpha = gamma / (delta - beta gamma / alpha_old), p = z + beta p, s = w + beta s,
 //   x += alpha p, r -= alpha s.   delta is assembled WITHOUT w:
 //   delta = sum_i z_i.(Hpp_ii z_i) + sum_i z_i.(sum_nbr Hpp_ij z_j) - sum_l t_l.u_l
-//   phase L: (a) pose-parallel off-diagonal pose-pose products yoff_i = sum_nbr Hpp_ij z_j; (b) landmark rows:
+//   phase L: (a) owned poses: off-diagonal pose-pose products yoff_i = sum_nbr Hpp_ij z_j; (b) landmark rows:
 //            t_l over the row's lanes, u_l = Hll^-1 t_l stored per landmark.
-//   phase P: one lane per pose: w_i = Hpp_ii z_i + yoff_i - sum_k Jp_k^T (jh_k.u_l(k)) is complete locally, so the
-//            vector updates, z' = M^-1 r and the next gamma / delta parts follow in the same thread.
+//   phase P: owned poses: w_i = Hpp_ii z_i + yoff_i - sum_k Jp_k^T (jh_k.u_l(k)) is complete locally, so the vector
+//            updates, z' = M^-1 r and the next gamma / delta parts follow in the same thread.
 enum { FS_GAMMA0 = 16, FS_DELTA0 = 19 };
+constexpr int kPcgVecs = 15;                 // p 0-2, s 3-5, x 6-8, r 9-11, yoff 12-14
+constexpr int kPcgSmemBudget = 220 * 1024;   // dynamic shared memory for the resident pose vectors
 
 // -DBOS_PCG_TIMING: thread 0 of a few CTAs prints clock64 deltas per phase (diagnostic builds only)
 #ifdef BOS_PCG_TIMING
@@ -283,7 +289,7 @@ __device__ __forceinline__ double block_sum_pcg(double v, double* red) {   // re
     return s;
 }
 
-// 4-padded vectors: one 32-byte (FP64) / 16-byte (FP32) record per pose or landmark, read and written through L2 (.cg)
+// 4-padded records: one 32-byte (FP64) / 16-byte (FP32) sector per pose or landmark, read and written through L2 (.cg)
 __device__ __forceinline__ void ld4cg(const double* p, double& a, double& b, double& c, double& d) {
     const double2 u = __ldcg(reinterpret_cast<const double2*>(p)), v = __ldcg(reinterpret_cast<const double2*>(p) + 1);
     a = u.x; b = u.y; c = v.x; d = v.y;
@@ -300,7 +306,8 @@ __device__ __forceinline__ void st4cg(float* p, float a, float b, float c) { __s
 __device__ __forceinline__ void st2cg(double* p, double a, double b) { __stcg(reinterpret_cast<double2*>(p), make_double2(a, b)); }
 __device__ __forceinline__ void st2cg(float* p, float a, float b) { __stcg(reinterpret_cast<float2*>(p), make_float2(a, b)); }
 
-// ---- once per GN iteration: per-edge factors in sorted-edge order, then gathered into the two ELL layouts ------------
+// ---- once per GN iteration --------------------------------------------------------------------------------------------
+// per-edge factors in sorted-edge order (scratch for the landmark-major layout)
 template <typename S>
 __global__ void __launch_bounds__(256) k_pcg_edge_factors(Dev<S> d, S* __restrict__ jP, int ld) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,88 +318,86 @@ __global__ void __launch_bounds__(256) k_pcg_edge_factors(Dev<S> d, S* __restric
         const PoseV<S> X = load_pose<S>(d.pose, p);
         S lx, ly;
         load_lm<S>(d.lm, __ldg(d.b_lm + k), lx, ly);
-        S err, J[5];
-        bearing_terms<S>(X, lx, ly, S(0), err, J);
+        bearing_jl<S>(X, lx, ly, j0, j1);
         const S so = sqrt(__ldg(d.b_om + k));
-        j0 = so * J[3]; j1 = so * J[4];
+        j0 *= so; j1 *= so;
     }
     jP[k] = j0; jP[(size_t)ld + k] = j1;
 }
+// landmark-major ELL copy of the factors; per compact landmark row: Hll^-1 and the record {Hll^-1 b_l, lx, ly}
 template <typename S>
 __global__ void __launch_bounds__(256) k_ell_fill(Dev<S> d, PcgWork<S> w) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < d.n_clm) {   // Hll^-1, u = 0 and the landmark position in compact row order
+    if (k < d.n_clm) {
         const int L = __ldg(d.pl_lm_id + k);
         w.hllinv_c[3LL * k] = w.hllinv[3LL * L]; w.hllinv_c[3LL * k + 1] = w.hllinv[3LL * L + 1]; w.hllinv_c[3LL * k + 2] = w.hllinv[3LL * L + 2];
-        w.ul4[4LL * k] = S(0); w.ul4[4LL * k + 1] = S(0); w.ul4[4LL * k + 2] = d.lm[2LL * L]; w.ul4[4LL * k + 3] = d.lm[2LL * L + 1];
+        w.ul4[4LL * k] = w.ul[2LL * L]; w.ul4[4LL * k + 1] = w.ul[2LL * L + 1]; w.ul4[4LL * k + 2] = d.lm[2LL * L]; w.ul4[4LL * k + 3] = d.lm[2LL * L + 1];
     }
     if (k < d.nLs) {
         const int e = __ldg(d.ell_Lmap + k);
         w.Lj[k] = (e >= 0) ? w.jP[e] : S(0);
         w.Lj[d.nLs + k] = (e >= 0) ? w.jP[(size_t)w.Eb_pad + e] : S(0);
     }
-    if (k < d.nPs) {
-        const int e = __ldg(d.ell_Pmap + k);
-        w.Pj[k] = (e >= 0) ? w.jP[e] : S(0);
-        w.Pj[d.nPs + k] = (e >= 0) ? w.jP[(size_t)w.Eb_pad + e] : S(0);
-    }
 }
 
-// one thread per pose: reduced rhs g, diagonal block of S and its inverse, and the start vectors of the fused loop
+// one lane per pose (pose-major ELL groups): reduced rhs g = -(b_p - Hpl Hll^-1 b_l), the block-Jacobi preconditioner
+// M_i = Hpp_ii - sum_k Hpl_k Hll^-1 Hpl_k^T (per EDGE: exact unless a (pose, landmark) pair is observed twice), the start
+// vectors and the first gamma / delta parts
 template <typename S>
 __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) {
     __shared__ double red[8];
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, g = i >> 5;
     double gz = 0.0, zw = 0.0;
-    if (p < d.NP) {
-        S g[3] = {-d.b[3LL * p], -d.b[3LL * p + 1], -d.b[3LL * p + 2]};
+    if (g < d.nPg) {
+        const bool valid = i < d.NP;
+        const int ic = valid ? i : d.NP - 1;
+        const PoseV<S> X = load_pose<S>(d.pose, ic);
+        S gg[3] = {-d.b[3LL * ic], -d.b[3LL * ic + 1], -d.b[3LL * ic + 2]};
         S hp[6], sd[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) { hp[k] = d.Hpp[6LL * p + k]; sd[k] = hp[k]; }
-        for (int s = d.pose_ptr[p]; s < d.pose_ptr[p + 1]; s++) {
-            const S* B = d.Hpl + s;
-            const int l = d.slot_lm[s];
-            const S i00 = w.hllinv[3LL * l], i01 = w.hllinv[3LL * l + 1], i11 = w.hllinv[3LL * l + 2];
-            const S u0 = w.ul[2LL * l], u1 = w.ul[2LL * l + 1];
-            S b[6];
+        for (int k = 0; k < 6; k++) { hp[k] = d.Hpp[6LL * ic + k]; sd[k] = hp[k]; }
+        const int off = __ldg(d.ell_Poff + g), W = __ldg(d.ell_Poff + g + 1) - off;
+        const bool active = valid && ic != d.fixed;
+        for (int t = 0; t < W; t++) {
+            const long long slot = ((long long)off + t) * 32 + lane;
+            const int row = __ldg(d.ell_Prow + slot);
+            if (row < 0 || !active) continue;
+            const S u0 = w.ul4[4LL * row], u1 = w.ul4[4LL * row + 1], lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
+            const S i00 = w.hllinv_c[3LL * row], i01 = w.hllinv_c[3LL * row + 1], i11 = w.hllinv_c[3LL * row + 2];
+            S j0, j1;
+            bearing_jl<S>(X, lx, ly, j0, j1);
+            const S so = w.omega_uniform ? (S)w.sqrt_omega : __ldg(w.Pw + slot);
+            j0 *= so; j1 *= so;
+            const S jp[3] = {-j0, -j1, j0 * ly - j1 * lx};
+            const S m = j0 * u0 + j1 * u1;
+            const S q = i00 * j0 * j0 + S(2) * i01 * j0 * j1 + i11 * j1 * j1;
+            gg[0] += jp[0] * m; gg[1] += jp[1] * m; gg[2] += jp[2] * m;
+            sd[0] -= q * jp[0] * jp[0]; sd[1] -= q * jp[0] * jp[1]; sd[2] -= q * jp[0] * jp[2];
+            sd[3] -= q * jp[1] * jp[1]; sd[4] -= q * jp[1] * jp[2]; sd[5] -= q * jp[2] * jp[2];
+        }
+        if (valid) {
+            S mi[6];
+            sym3_inverse<S>(sd, mi);
 #pragma unroll
-            for (int k = 0; k < 6; k++) b[k] = B[(long long)k * d.hpl_ld];
-            S y[6];
+            for (int k = 0; k < 6; k++) w.minv[6LL * i + k] = mi[k];
+            const S z[3] = {mi[0] * gg[0] + mi[1] * gg[1] + mi[2] * gg[2], mi[1] * gg[0] + mi[3] * gg[1] + mi[4] * gg[2],
+                            mi[2] * gg[0] + mi[4] * gg[1] + mi[5] * gg[2]};
+            const S hz[3] = {hp[0] * z[0] + hp[1] * z[1] + hp[2] * z[2], hp[1] * z[0] + hp[3] * z[1] + hp[4] * z[2],
+                             hp[2] * z[0] + hp[4] * z[1] + hp[5] * z[2]};
+            const size_t np = (size_t)d.NP, np4 = 4 * np;
+#pragma unroll
+            for (int k = 0; k < kPcgVecs; k++) w.vS[(size_t)k * np + i] = (k >= 9 && k < 12) ? gg[k - 9] : S(0);
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                w.z4[4LL * i + a] = (a < 3) ? z[a] : S(0);
+                w.z4[np4 + 4LL * i + a] = S(0);
+            }
 #pragma unroll
             for (int a = 0; a < 3; a++) {
-                g[a] += b[2 * a] * u0 + b[2 * a + 1] * u1;
-                y[2 * a] = b[2 * a] * i00 + b[2 * a + 1] * i01;
-                y[2 * a + 1] = b[2 * a] * i01 + b[2 * a + 1] * i11;
+                gz += (double)gg[a] * (double)z[a];
+                zw += (double)z[a] * (double)hz[a];
             }
-            sd[0] -= y[0] * b[0] + y[1] * b[1];
-            sd[1] -= y[0] * b[2] + y[1] * b[3];
-            sd[2] -= y[0] * b[4] + y[1] * b[5];
-            sd[3] -= y[2] * b[2] + y[3] * b[3];
-            sd[4] -= y[2] * b[4] + y[3] * b[5];
-            sd[5] -= y[4] * b[4] + y[5] * b[5];
-        }
-        S mi[6];
-        sym3_inverse<S>(sd, mi);
-#pragma unroll
-        for (int k = 0; k < 6; k++) w.minv[6LL * p + k] = mi[k];
-        const S z[3] = {mi[0] * g[0] + mi[1] * g[1] + mi[2] * g[2], mi[1] * g[0] + mi[3] * g[1] + mi[4] * g[2],
-                        mi[2] * g[0] + mi[4] * g[1] + mi[5] * g[2]};
-        const S hz[3] = {hp[0] * z[0] + hp[1] * z[1] + hp[2] * z[2], hp[1] * z[0] + hp[3] * z[1] + hp[4] * z[2],
-                         hp[2] * z[0] + hp[4] * z[1] + hp[5] * z[2]};
-        const size_t np4 = 4 * (size_t)d.NP;
-        S* v = w.v4 + 4LL * p;
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            v[a] = S(0); v[np4 + a] = S(0); v[2 * np4 + a] = S(0);          // p, s, x
-            v[3 * np4 + a] = (a < 3) ? g[a] : S(0);                           // r
-            w.z4[4LL * p + a] = (a < 3) ? z[a] : S(0);
-            w.z4[np4 + 4LL * p + a] = S(0);
-            w.yoff[4LL * p + a] = S(0);
-        }
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            gz += (double)g[a] * (double)z[a];
-            zw += (double)z[a] * (double)hz[a];
         }
     }
     double s1 = block_sum_256(gz, red);
@@ -452,20 +457,30 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
 }
 
 template <typename S>
-__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2) {
+__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2, int capG) {
+    extern __shared__ __align__(16) unsigned char pcg_smem[];
+    S* vsm = reinterpret_cast<S*>(pcg_smem);                 // [kPcgVecs][capG * 32]
     __shared__ double red[kPcgThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int nwarps = gridDim.x * (kPcgThreads / 32);
-    const int wg = (tid >> 5) * gridDim.x + blockIdx.x;      // consecutive groups go to different SMs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grid = gridDim.x;
+    const int nwarps = grid * (kPcgThreads / 32);
+    const int wg = warp * grid + blockIdx.x;                 // landmark groups: consecutive groups go to different SMs
+    // pose groups owned by this CTA: g = lg * grid + blockIdx.x, handled by warp lg % 32 in every phase of every iteration
+    const int ngl = ((int)blockIdx.x < d.nPg) ? (d.nPg - (int)blockIdx.x + grid - 1) / grid : 0;
+    const size_t np = (size_t)d.NP, np4 = 4 * np, smstride = (size_t)capG * 32;
     unsigned epoch = 0;
     double* sc = w.scal;
-    const size_t np4 = 4 * (size_t)d.NP;
-    const S* Pj0 = w.Pj;
-    const S* Pj1 = w.Pj + d.nPs;
 #ifdef BOS_PCG_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
+    // resident pose vectors: r from the prep kernel, p = s = x = 0
+    for (int lg = warp; lg < ngl && lg < capG; lg += kPcgThreads / 32) {
+        const int i = (lg * grid + blockIdx.x) * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < kPcgVecs; k++) vsm[(size_t)k * smstride + lg * 32 + lane] = (i < d.NP && k >= 9 && k < 12) ? w.vS[(size_t)k * np + i] : S(0);
+    }
+    __syncthreads();
     const double gamma_init = __ldcg(sc + FS_GAMMA0);
     double gamma_prev = 1.0, alpha_prev = 1.0;
     int it = 0;
@@ -477,11 +492,12 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             S* zn = w.z4 + (size_t)((it + 1) & 1) * np4;
             // ---- phase L: off-diagonal pose-pose products, t_l / u_l per landmark, delta parts ---------------------------------
             double dacc = 0.0;
-            for (int g = wg; g < d.nPg; g += nwarps) {
-                const int i = g * 32 + lane;
+            for (int lg = warp; lg < ngl; lg += kPcgThreads / 32) {
+                const int i = (lg * grid + blockIdx.x) * 32 + lane;
                 if (i >= d.NP) continue;
+                S* v = (lg < capG) ? vsm + lg * 32 + lane : w.vS + i;
+                const size_t vs = (lg < capG) ? smstride : np;
                 const int q0 = __ldg(d.pp_ptr + i), q1 = __ldg(d.pp_ptr + i + 1);
-                if (q0 == q1) continue;
                 S y0 = S(0), y1 = S(0), y2 = S(0);
                 for (int q = q0; q < q1; q++) {
                     const int nb = __ldg(d.pp_nbr + q);
@@ -499,10 +515,12 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                         y2 += Bo[2] * n0 + Bo[5] * n1 + Bo[8] * n2;
                     }
                 }
-                st4cg(w.yoff + 4LL * i, y0, y1, y2);
-                S z0, z1, z2, zp;
-                ld4cg(zc + 4LL * i, z0, z1, z2, zp);
-                dacc += (double)z0 * (double)y0 + (double)z1 * (double)y1 + (double)z2 * (double)y2;
+                v[12 * vs] = y0; v[13 * vs] = y1; v[14 * vs] = y2;
+                if (q0 != q1) {
+                    S z0, z1, z2, zp;
+                    ld4cg(zc + 4LL * i, z0, z1, z2, zp);
+                    dacc += (double)z0 * (double)y0 + (double)z1 * (double)y1 + (double)z2 * (double)y2;
+                }
             }
             PCG_T(0);
             pcg_landmark_rows<S, 0>(d, w, zc, wg, nwarps, dacc);
@@ -520,49 +538,66 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             if (!(denom > 0.0)) { bad = true; break; }
             const double alpha = gamma / denom;
             if (blockIdx.x == 0 && tid == 0) { __stcg(sc + FS_GAMMA0 + nn, 0.0); __stcg(sc + FS_DELTA0 + nn, 0.0); }
-            // ---- phase P: one lane per pose: w_i, vector updates, preconditioner, next gamma / delta parts -------------------
+            // ---- phase P: owned poses: w_i, vector updates, preconditioner, next gamma / delta parts -------------------------
             const S al = (S)alpha, be = (S)beta;
             double gacc = 0.0, dacc2 = 0.0;
-            for (int g = wg; g < d.nPg; g += nwarps) {
+            for (int lg = warp; lg < ngl; lg += kPcgThreads / 32) {
+                const int g = lg * grid + blockIdx.x;
                 const int i = g * 32 + lane;
                 const bool valid = i < d.NP;
                 const int ic = valid ? i : d.NP - 1;
+                S* v = (lg < capG) ? vsm + lg * 32 + lane : w.vS + ic;
+                const size_t vs = (lg < capG) ? smstride : np;
                 const int off = __ldg(d.ell_Poff + g), W = __ldg(d.ell_Poff + g + 1) - off;
-                S z0, z1, z2, zp, y0, y1, y2, yp;
+                const PoseV<S> X = load_pose<S>(d.pose, ic);
+                S z0, z1, z2, zp;
                 ld4cg(zc + 4LL * ic, z0, z1, z2, zp);
-                ld4cg(w.yoff + 4LL * ic, y0, y1, y2, yp);
                 const S* hp = d.Hpp + 6LL * ic;
-                const S h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3), h4 = __ldg(hp + 4), h5 = __ldg(hp + 5);
-                S w0 = h0 * z0 + h1 * z1 + h2 * z2 + y0;
-                S w1 = h1 * z0 + h3 * z1 + h4 * z2 + y1;
-                S w2 = h2 * z0 + h4 * z1 + h5 * z2 + y2;
+                S w0, w1, w2;
+                {
+                    const S h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3), h4 = __ldg(hp + 4), h5 = __ldg(hp + 5);
+                    w0 = h0 * z0 + h1 * z1 + h2 * z2 + v[12 * vs];
+                    w1 = h1 * z0 + h3 * z1 + h4 * z2 + v[13 * vs];
+                    w2 = h2 * z0 + h4 * z1 + h5 * z2 + v[14 * vs];
+                }
+                const bool active = valid && ic != d.fixed;
                 const long long s0 = (long long)off * 32 + lane;
+                const S so_u = (S)w.sqrt_omega;
 #pragma unroll 4
                 for (int t = 0; t < W; t++) {
                     const long long slot = s0 + (long long)t * 32;
-                    const S j0 = __ldg(Pj0 + slot), j1 = __ldg(Pj1 + slot);
                     const int c = __ldg(d.ell_Prow + slot);
+                    if (c < 0 || !active) continue;
                     S u0, u1, lx, ly;
                     ld4cg(w.ul4 + 4LL * c, u0, u1, lx, ly);
+                    S j0, j1;
+                    bearing_jl<S>(X, lx, ly, j0, j1);
+                    const S so = w.omega_uniform ? so_u : __ldg(w.Pw + slot);
+                    j0 *= so; j1 *= so;
                     const S m = j0 * u0 + j1 * u1;
                     w0 += j0 * m; w1 += j1 * m; w2 -= (j0 * ly - j1 * lx) * m;
                 }
                 if (!valid) continue;
-                S* v = w.v4 + 4LL * i;
-                S p0, p1, p2, s0_, s1, s2, x0, x1, x2, r0, r1, r2, pad;
-                ld4cg(v, p0, p1, p2, pad); ld4cg(v + np4, s0_, s1, s2, pad); ld4cg(v + 2 * np4, x0, x1, x2, pad); ld4cg(v + 3 * np4, r0, r1, r2, pad);
-                p0 = z0 + be * p0; p1 = z1 + be * p1; p2 = z2 + be * p2;
-                s0_ = w0 + be * s0_; s1 = w1 + be * s1; s2 = w2 + be * s2;
-                x0 += al * p0; x1 += al * p1; x2 += al * p2;
-                r0 -= al * s0_; r1 -= al * s1; r2 -= al * s2;
-                st4cg(v, p0, p1, p2); st4cg(v + np4, s0_, s1, s2); st4cg(v + 2 * np4, x0, x1, x2); st4cg(v + 3 * np4, r0, r1, r2);
+                S r0, r1, r2;
+                {
+                    const S p0 = z0 + be * v[0], p1 = z1 + be * v[vs], p2 = z2 + be * v[2 * vs];
+                    const S s0_ = w0 + be * v[3 * vs], s1 = w1 + be * v[4 * vs], s2 = w2 + be * v[5 * vs];
+                    v[0] = p0; v[vs] = p1; v[2 * vs] = p2;
+                    v[3 * vs] = s0_; v[4 * vs] = s1; v[5 * vs] = s2;
+                    v[6 * vs] += al * p0; v[7 * vs] += al * p1; v[8 * vs] += al * p2;
+                    r0 = v[9 * vs] - al * s0_; r1 = v[10 * vs] - al * s1; r2 = v[11 * vs] - al * s2;
+                    v[9 * vs] = r0; v[10 * vs] = r1; v[11 * vs] = r2;
+                }
                 const S* mi = w.minv + 6LL * i;
                 const S m0 = __ldg(mi), m1 = __ldg(mi + 1), m2 = __ldg(mi + 2), m3 = __ldg(mi + 3), m4 = __ldg(mi + 4), m5 = __ldg(mi + 5);
                 const S zn0 = m0 * r0 + m1 * r1 + m2 * r2, zn1 = m1 * r0 + m3 * r1 + m4 * r2, zn2 = m2 * r0 + m4 * r1 + m5 * r2;
                 st4cg(zn + 4LL * i, zn0, zn1, zn2);
                 gacc += (double)r0 * (double)zn0 + (double)r1 * (double)zn1 + (double)r2 * (double)zn2;
-                dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
-                         (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
+                {
+                    const S h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3), h4 = __ldg(hp + 4), h5 = __ldg(hp + 5);
+                    dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
+                             (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
+                }
             }
             PCG_T(4);
             {
@@ -582,19 +617,24 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             if (!(gnew > tol2 * gamma_init)) break;
         }
     }
-    // ---- epilogue: dx_p = x, dx_l by back-substitution -------------------------------------------------------------------
-    const S* x4 = w.v4 + 2 * np4;
-    const int gtid = blockIdx.x * kPcgThreads + tid, gsz = gridDim.x * kPcgThreads;
-    for (int i = gtid; i < d.NP; i += gsz) {
-        S x0, x1, x2, xp;
-        ld4cg(x4 + 4LL * i, x0, x1, x2, xp);
+    // ---- epilogue: dx_p = x; x as padded records for the back-substitution gather; dx_l ----------------------------------
+    S* x4 = w.z4 + (size_t)((it + 1) & 1) * np4;    // the z buffer that is not current
+    for (int lg = warp; lg < ngl; lg += kPcgThreads / 32) {
+        const int i = (lg * grid + blockIdx.x) * 32 + lane;
+        if (i >= d.NP) continue;
+        const S* v = (lg < capG) ? vsm + lg * 32 + lane : w.vS + i;
+        const size_t vs = (lg < capG) ? smstride : np;
+        const S x0 = v[6 * vs], x1 = v[7 * vs], x2 = v[8 * vs];
         d.delta[3LL * i] = x0; d.delta[3LL * i + 1] = x1; d.delta[3LL * i + 2] = x2;
+        st4cg(x4 + 4LL * i, x0, x1, x2);
     }
+    const int gtid = blockIdx.x * kPcgThreads + tid, gsz = gridDim.x * kPcgThreads;
     for (int l = gtid; l < d.NL; l += gsz)
         if (__ldg(d.tri_ptr + l) == __ldg(d.tri_ptr + l + 1)) {   // unobserved landmark: dx_l = -Hll^-1 b_l
             d.delta[3LL * d.NP + 2LL * l] = -w.ul[2LL * l];
             d.delta[3LL * d.NP + 2LL * l + 1] = -w.ul[2LL * l + 1];
         }
+    grid_barrier(w.bar, gridDim.x, epoch);
     double unused = 0.0;
     pcg_landmark_rows<S, 1>(d, w, x4, wg, nwarps, unused);
     if (gtid == 0) { sc[SC_ITER] = (double)it; sc[SC_BAD] = bad ? 1.0 : 0.0; }
@@ -609,26 +649,36 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
 template <typename S>
 int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st, int* iterations_out, int* launches) {
     int nl = 0;
-    const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256;
+    const int gl = (d.NL + 255) / 256;
     cudaMemsetAsync(w.scal, 0, 32 * sizeof(double), st);
     cudaMemsetAsync(w.bar, 0, 4 * sizeof(unsigned), st);
     if (d.NL > 0) { k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++; }
     if (d.Eb > 0) {
         k_pcg_edge_factors<S><<<(d.Eb + 255) / 256, 256, 0, st>>>(d, w.jP, w.Eb_pad); nl++;
-        long long n = d.nLs > d.nPs ? d.nLs : d.nPs;
-        if (n < d.n_clm) n = d.n_clm;
+        const long long n = d.nLs > d.n_clm ? d.nLs : d.n_clm;
         k_ell_fill<S><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, w); nl++;
     }
-    k_pcg_fused_prep<S><<<gp, 256, 0, st>>>(d, w); nl++;
+    k_pcg_fused_prep<S><<<(d.nPg * 32 + 255) / 256, 256, 0, st>>>(d, w); nl++;
     int grid = (d.nPg > d.nLg ? d.nPg : d.nLg);                 // groups of 32 rows: one warp each
     grid = (grid + kPcgThreads / 32 - 1) / (kPcgThreads / 32);
     if (grid > w.sm_count) grid = w.sm_count;
     if (grid < 1) grid = 1;
+    const int ngl_max = (d.nPg + grid - 1) / grid;
+    int capG = kPcgSmemBudget / (kPcgVecs * 32 * (int)sizeof(S));
+    if (capG > ngl_max) capG = ngl_max;
+    if (capG < 1) capG = 1;
+    const size_t smem = (size_t)kPcgVecs * capG * 32 * sizeof(S);
+    static size_t configured[2] = {0, 0};
+    size_t& conf = configured[sizeof(S) == 8 ? 0 : 1];
+    if (smem > conf) {
+        if (cudaFuncSetAttribute(k_pcg_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        conf = smem;
+    }
     Dev<S> dd = d;
     PcgWork<S> ww = w;
     double tol2 = rtol * rtol;
-    void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2};
-    if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(grid), dim3(kPcgThreads), args, 0, st) != cudaSuccess) return -1;
+    void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2, (void*)&capG};
+    if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(grid), dim3(kPcgThreads), args, smem, st) != cudaSuccess) return -1;
     nl++;
     double host_scal[32];
     if (cudaMemcpyAsync(host_scal, w.scal, 32 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
