@@ -15,7 +15,10 @@ namespace bos {
 constexpr int kLinTile = 512;
 // the fused PCG kernel reads the per-edge factors from two sliced-ELL layouts (see pattern.cpp)
 constexpr int kPcgThreads = 1024;                  // one persistent CTA per SM
-constexpr int kEllLanesL = 4;                      // lanes per landmark row in the landmark-major layout
+#ifndef BOS_ELL_LANES
+#define BOS_ELL_LANES 8
+#endif
+constexpr int kEllLanesL = BOS_ELL_LANES;          // lanes per landmark row in the landmark-major layout
 
 // Typed view of everything a kernel needs.  One instance per context, built after upload.
 template <typename S>
@@ -61,15 +64,22 @@ struct Dev {
     const int* tg_eptr = nullptr;    // [n_groups+1] into tg_edge
     const unsigned short* tg_edge = nullptr;  // [Eb] tile-local edge index
     // sliced-ELL layouts of the bearing edges for the fused PCG kernel
-    int n_clm = 0, nLg = 0, nPg = 0;
+    int n_clm = 0, nLg = 0;
     long long nLs = 0, nPs = 0;      // slots of the two layouts
     const int* pl_lm_id = nullptr;   // [n_clm] landmark stix of compact row r (rows sorted by descending observation count)
     const int* ell_Loff = nullptr;   // [nLg+1] column offset of each landmark group
-    const int* ell_Lmap = nullptr;   // [nLs] sorted bearing-edge index of the slot, -1 for padding
-    const int* ell_Lpose = nullptr;  // [nLs] pose of the slot (0 for padding; the factor is 0 there)
-    const int* ell_Poff = nullptr;   // [nPg+1]
-    const int* ell_Pmap = nullptr;   // [nPs]
-    const int* ell_Prow = nullptr;   // [nPs] compact landmark row of the slot, -1 for padding
+    const int* ell_Lpose = nullptr;  // [nLs] pose of the slot; -1 for padding and for edges of the fixed pose (zero Jacobian block)
+    // pose-major side: chunks of pc_cp poses (one persistent CTA each), rows sorted by edge count inside a chunk
+    int pc_chunks = 0, pc_cp = 0, pc_ok = 0, pc_cl_max = 0, pc_slots_max = 0;
+    const int* pc_row_pose = nullptr;      // [pc_chunks * pc_cp] pose of chunk row, -1 for padding
+    const int* pc_goff = nullptr;          // [pc_chunks * pc_cp / 32 + 1] column offset of each group of 32 rows
+    const int* pc_cl_ptr = nullptr;        // [pc_chunks + 1] the chunk's distinct landmark rows ...
+    const int* pc_cl_row = nullptr;        // ... ascending compact landmark row ids
+    const unsigned short* pc_loc = nullptr;  // [nPs] index into the chunk's landmark table, 0xffff for padding
+    const int* pc_emap = nullptr;          // [nPs] sorted bearing-edge index of the slot, -1 for padding
+    const int* pc_nbr = nullptr;           // [2][pc_chunks * pc_cp] first two pose-pose neighbours of the row (-1: none)
+    const int* pc_nslot = nullptr;         // [2][..] their Hoff slot (bit 31: this pose is the column side)
+    const int* pc_ncnt = nullptr;          // [..] number of pose-pose neighbours (more than 2: the rest through pp_ptr)
     const int* tri_ptr = nullptr;    // [NL+1] bearing edges grouped by landmark (caller order inside a landmark)
     const int* tri_edge = nullptr;   // [Eb] sorted-edge index
     // state
@@ -134,16 +144,18 @@ struct PcgWork {
     // fused kernel: the operator is applied from per-EDGE factors.  A bearing edge's 3x2 block is rank one,
     // Hpl_k = Jp_k^T omega Jl_k, and Jp_k = (-j0, -j1, j0 ly - j1 lx) is determined by Jl_k = (j0, j1) and the landmark position,
     // so two scalars per edge (sqrt(omega) Jl) replace the six of the block.
-    S* jP = nullptr;               // [2][Eb_pad] factors in sorted-edge order (scratch of the fill)
-    S* Lj = nullptr;               // [2][nLs] factors in the landmark-major ELL layout
+    S* Lw = nullptr;               // [nLs] sqrt(omega) per landmark-major slot; only when the bearing omegas are not all equal
     S* Pw = nullptr;               // [nPs] sqrt(omega) per pose-major slot; only when the bearing omegas are not all equal
     int omega_uniform = 1;         // all bearing omegas equal: the pose-major pass recomputes its factors from the state
     double sqrt_omega = 1.0;       // ... with this scale
     S* hllinv_c = nullptr;         // [n_clm][3] Hll^-1 in compact row order
     S* ul4 = nullptr;              // [n_clm][4] u_l = Hll^-1 t_l (rewritten every CG iteration) and the landmark position lx, ly
     S* z4 = nullptr;               // [2][NP][4] double-buffered z (padded to one 32-byte sector per pose)
-    S* vS = nullptr;               // [15][NP] p, s, x, r, yoff by component: home of the pose vectors that do not fit in the
-                                   // persistent kernel's shared memory, and hand-over buffer (r in, x out) for those that do
+    S* rowS = nullptr;             // [24][pc_chunks * pc_cp] per-row copies, component-major so that a warp's loads are contiguous:
+                                   // 0-5 Hpp_ii, 6-11 M_i^-1, 12-17 / 18-23 the first two pose-pose blocks (symmetric by construction:
+                                   // -J_s^T Omega J_s, so six values each)
+    S* rS = nullptr;               // [3][pc_chunks * pc_cp] initial residual by chunk row (handed to the persistent kernel)
+    S* xS = nullptr;               // [3][pc_chunks * pc_cp] solution by chunk row (updated in place every iteration)
     int Eb_pad = 0;
     double* scal = nullptr;  // [32] classic: rz, pAp, rz_new, rz0, done flag, iterations ...; fused: see solve_pcg.cu
     unsigned* bar = nullptr; // [4] grid barrier counter of the fused kernel
@@ -190,7 +202,11 @@ struct HostPattern {
     std::vector<int> off_lo, off_hi;        // unique pose-pose blocks, sorted
     std::vector<int> pp_ptr, pp_nbr, pp_slot;
     std::vector<int> tri_ptr, tri_edge;
-    std::vector<int> pl_lm_id, b_row, ell_Loff, ell_Lmap, ell_Lpose, ell_Poff, ell_Pmap, ell_Prow;
+    std::vector<int> pl_lm_id, b_row, ell_Loff, ell_Lmap, ell_Lpose;
+    int pc_chunks = 0, pc_cp = 0;
+    bool pc_ok = false;
+    std::vector<int> pc_row_pose, pc_goff, pc_cl_ptr, pc_cl_row, pc_emap, pc_nbr, pc_nslot, pc_ncnt;
+    std::vector<unsigned short> pc_loc;
     std::vector<int> tile_ptr, tg_lm, tg_eptr, epose_ptr;
     std::vector<unsigned short> tg_edge;
     std::vector<char> touched;              // [NP + NL]
@@ -202,6 +218,6 @@ struct HostPattern {
     std::string error;
 };
 int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm,
-                  int64_t Eo, const int32_t* o_src, const int32_t* o_dst);
+                  int64_t Eo, const int32_t* o_src, const int32_t* o_dst, int pcg_chunks = 148);
 
 }  // namespace bos

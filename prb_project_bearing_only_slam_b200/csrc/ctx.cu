@@ -192,10 +192,18 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)
     UP(tri_ptr, P.tri_ptr) UP(tri_edge, P.tri_edge)
     UP(epose_ptr, P.epose_ptr) UP(tile_ptr, P.tile_ptr) UP(tg_lm, P.tg_lm) UP(tg_eptr, P.tg_eptr) UP(tg_edge, P.tg_edge)
-    UP(pl_lm_id, P.pl_lm_id) UP(ell_Loff, P.ell_Loff) UP(ell_Lmap, P.ell_Lmap) UP(ell_Lpose, P.ell_Lpose)
-    UP(ell_Poff, P.ell_Poff) UP(ell_Pmap, P.ell_Pmap) UP(ell_Prow, P.ell_Prow)
-    d.n_clm = (int)P.pl_lm_id.size(); d.nLg = (int)P.ell_Loff.size() - 1; d.nPg = (int)P.ell_Poff.size() - 1;
-    d.nLs = (long long)P.ell_Lmap.size(); d.nPs = (long long)P.ell_Pmap.size();
+    UP(pl_lm_id, P.pl_lm_id) UP(ell_Loff, P.ell_Loff) UP(ell_Lpose, P.ell_Lpose)
+    UP(pc_row_pose, P.pc_row_pose) UP(pc_goff, P.pc_goff) UP(pc_cl_ptr, P.pc_cl_ptr) UP(pc_cl_row, P.pc_cl_row) UP(pc_loc, P.pc_loc)
+    UP(pc_emap, P.pc_emap) UP(pc_nbr, P.pc_nbr) UP(pc_nslot, P.pc_nslot) UP(pc_ncnt, P.pc_ncnt)
+    d.n_clm = (int)P.pl_lm_id.size(); d.nLg = (int)P.ell_Loff.size() - 1;
+    d.nLs = (long long)P.ell_Lmap.size(); d.nPs = (long long)P.pc_loc.size();
+    d.pc_chunks = P.pc_chunks; d.pc_cp = P.pc_cp; d.pc_ok = P.pc_ok ? 1 : 0;
+    d.pc_cl_max = 0; d.pc_slots_max = 0;
+    for (int q = 0; q < P.pc_chunks; q++) {
+        d.pc_cl_max = std::max(d.pc_cl_max, P.pc_cl_ptr[q + 1] - P.pc_cl_ptr[q]);
+        const int gpc = P.pc_cp / 32;
+        d.pc_slots_max = std::max(d.pc_slots_max, (P.pc_goff[(size_t)(q + 1) * gpc] - P.pc_goff[(size_t)q * gpc]) * 32);
+    }
 #undef UP
     d.pose = m.get<S>(4 * (size_t)P.NP);
     d.lm = m.get<S>(2 * (size_t)std::max(P.NL, 1));
@@ -252,8 +260,6 @@ int ensure_pcg(bos_ctx* c) {
     w.scal = c->mem.get<double>(32);
     w.bar = c->mem.get<unsigned>(4);
     w.Eb_pad = d.Eb_pad;
-    w.jP = c->mem.get<S>(2 * (size_t)std::max(d.Eb_pad, 4));
-    w.Lj = c->mem.get<S>(2 * (size_t)std::max(d.nLs, 32LL));
     {   // bearing omegas: one value for all edges is the common case (the reference never sets another, observation.hpp:17)
         const HostPattern& P = c->P;
         w.omega_uniform = 1; w.sqrt_omega = 1.0;
@@ -263,17 +269,22 @@ int ensure_pcg(bos_ctx* c) {
             w.sqrt_omega = std::sqrt(om[0]);
         }
         if (!w.omega_uniform) {
-            std::vector<S> pw(P.ell_Pmap.size(), S(0));
-            for (size_t k = 0; k < pw.size(); k++) if (P.ell_Pmap[k] >= 0) pw[k] = (S)std::sqrt(om[P.ell_Pmap[k]]);
+            std::vector<S> pw(P.pc_emap.size(), S(0));
+            for (size_t k = 0; k < pw.size(); k++) if (P.pc_emap[k] >= 0) pw[k] = (S)std::sqrt(om[P.pc_emap[k]]);
             w.Pw = c->mem.upload(pw);
-            if (!w.Pw) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+            std::vector<S> lw(P.ell_Lmap.size(), S(0));
+            for (size_t k = 0; k < lw.size(); k++) if (P.ell_Lmap[k] >= 0) lw[k] = (S)std::sqrt(om[P.ell_Lmap[k]]);
+            w.Lw = c->mem.upload(lw);
+            if (!w.Pw || !w.Lw) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
         }
     }
     w.hllinv_c = c->mem.get<S>(3 * (size_t)std::max(d.n_clm, 1));
     w.ul4 = c->mem.get<S>(4 * (size_t)std::max(d.n_clm, 1));
     w.z4 = c->mem.get<S>(8 * (size_t)d.NP);
-    w.vS = c->mem.get<S>(15 * (size_t)d.NP);
-    if (!w.jP || !w.Lj || !w.hllinv_c || !w.ul4 || !w.z4 || !w.vS) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+    w.rowS = c->mem.get<S>(24 * (size_t)d.pc_chunks * d.pc_cp);
+    w.rS = c->mem.get<S>(3 * (size_t)d.pc_chunks * d.pc_cp);
+    w.xS = c->mem.get<S>(3 * (size_t)d.pc_chunks * d.pc_cp);
+    if (!w.hllinv_c || !w.ul4 || !w.z4 || !w.rS || !w.xS || !w.rowS) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
     c->pcg_ready = true;
     return BOS_OK;
 }
@@ -569,7 +580,7 @@ int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t 
     CUDA_OK(c, cudaSetDevice(c->opt.device));
     c->have_problem = false; c->dense_ready = false; c->pcg_ready = false;
     c->mem.release();
-    if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst) != 0)
+    if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count) != 0)
         return fail(c, BOS_ERR_INVALID, c->P.error);
     int rc = c->f64() ? upload_impl<double>(c, b_z, b_omega, o_z, o_omega) : upload_impl<float>(c, b_z, b_omega, o_z, o_omega);
     if (rc) return rc;

@@ -11,7 +11,7 @@
 namespace bos {
 
 int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const int32_t* b_pose, const int32_t* b_lm,
-                  int64_t Eo64, const int32_t* o_src, const int32_t* o_dst) {
+                  int64_t Eo64, const int32_t* o_src, const int32_t* o_dst, int pcg_chunks) {
     P = HostPattern();
     if (NP <= 0 || NL < 0 || Eb64 < 0 || Eo64 < 0 || Eb64 > 0x3fffffff || Eo64 > 0x3fffffff) { P.error = "bad sizes"; return 1; }
     if (fixed < 0 || fixed >= NP) { P.error = "fixed pose stix out of range"; return 1; }
@@ -104,30 +104,69 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
             P.ell_Loff[g + 1] = P.ell_Loff[g] + (eptr[l0 + 1] - eptr[l0] + kEllLanesL - 1) / kEllLanesL;
         }
         P.ell_Lmap.assign((size_t)P.ell_Loff[nLg] * 32, -1);
-        P.ell_Lpose.assign((size_t)P.ell_Loff[nLg] * 32, 0);
+        P.ell_Lpose.assign((size_t)P.ell_Loff[nLg] * 32, -1);
         for (int r = 0; r < n_clm; r++) {
             const int l = P.pl_lm_id[r], g = r / RPG, lane0 = (r % RPG) * kEllLanesL;
             for (int q = eptr[l]; q < eptr[l + 1]; q++) {
                 const int k = eord[q], idx = q - eptr[l];
                 const size_t slot = ((size_t)P.ell_Loff[g] + idx / kEllLanesL) * 32 + lane0 + idx % kEllLanesL;
-                P.ell_Lmap[slot] = k; P.ell_Lpose[slot] = P.b_pose[k];
+                P.ell_Lmap[slot] = k; P.ell_Lpose[slot] = (P.b_pose[k] == fixed) ? -1 : P.b_pose[k];
                 P.b_row[k] = r;
             }
         }
-        const int nPg = (NP + 31) / 32;
-        P.ell_Poff.assign(nPg + 1, 0);
-        for (int g = 0; g < nPg; g++) {
-            int wmax = 0;
-            for (int i = g * 32; i < std::min(NP, g * 32 + 32); i++) wmax = std::max(wmax, P.epose_ptr[i + 1] - P.epose_ptr[i]);
-            P.ell_Poff[g + 1] = P.ell_Poff[g] + wmax;
-        }
-        P.ell_Pmap.assign((size_t)P.ell_Poff[nPg] * 32, -1);
-        P.ell_Prow.assign((size_t)P.ell_Poff[nPg] * 32, -1);
-        for (int i = 0; i < NP; i++)
-            for (int k = P.epose_ptr[i]; k < P.epose_ptr[i + 1]; k++) {
-                const size_t slot = ((size_t)P.ell_Poff[i / 32] + (k - P.epose_ptr[i])) * 32 + i % 32;
-                P.ell_Pmap[slot] = k; P.ell_Prow[slot] = P.b_row[k];
+        // P: pose rows in CHUNKS: chunk c (one persistent CTA) owns poses [c * cp, (c + 1) * cp), rows in pose order; every
+        // slot names its landmark by a 16-bit index into the chunk's table of distinct landmark rows (a contiguous pose
+        // range sees few landmarks).
+        int nch = pcg_chunks < 1 ? 1 : pcg_chunks;
+        if (nch > (NP + 31) / 32) nch = (NP + 31) / 32;
+        const int cp = ((NP + nch - 1) / nch + 31) / 32 * 32;
+        nch = (NP + cp - 1) / cp;
+        P.pc_chunks = nch; P.pc_cp = cp;
+        const int gpc = cp / 32;
+        P.pc_row_pose.assign((size_t)nch * cp, -1);
+        P.pc_goff.assign((size_t)nch * gpc + 1, 0);
+        P.pc_cl_ptr.assign(nch + 1, 0);
+        P.pc_cl_row.clear();
+        P.pc_ok = true;
+        std::vector<int> rows, lid(n_clm > 0 ? n_clm : 1, -1);
+        for (int c = 0; c < nch; c++) {
+            const int p0 = c * cp, p1 = std::min(NP, p0 + cp);
+            rows.resize(p1 - p0);
+            std::iota(rows.begin(), rows.end(), p0);
+            for (size_t r = 0; r < rows.size(); r++) P.pc_row_pose[(size_t)c * cp + r] = rows[r];
+            for (int g = 0; g < gpc; g++) {
+                int wdt = 0;   // rows stay in pose order (coalesced per-pose data): the group is as wide as its longest row
+                for (size_t r0 = (size_t)g * 32; r0 < rows.size() && r0 < (size_t)g * 32 + 32; r0++)
+                    wdt = std::max(wdt, P.epose_ptr[rows[r0] + 1] - P.epose_ptr[rows[r0]]);
+                P.pc_goff[(size_t)c * gpc + g + 1] = P.pc_goff[(size_t)c * gpc + g] + wdt;
             }
+            // distinct landmark rows of the chunk, ascending
+            const size_t cl0 = P.pc_cl_row.size();
+            for (int k = P.epose_ptr[p0]; k < P.epose_ptr[p1]; k++) P.pc_cl_row.push_back(P.b_row[k]);
+            std::sort(P.pc_cl_row.begin() + cl0, P.pc_cl_row.end());
+            P.pc_cl_row.erase(std::unique(P.pc_cl_row.begin() + cl0, P.pc_cl_row.end()), P.pc_cl_row.end());
+            P.pc_cl_ptr[c + 1] = (int)P.pc_cl_row.size();
+            if (P.pc_cl_row.size() - cl0 >= 0xffff) P.pc_ok = false;
+        }
+        P.pc_loc.assign((size_t)P.pc_goff.back() * 32, (unsigned short)0xffff);
+        P.pc_emap.assign((size_t)P.pc_goff.back() * 32, -1);
+        for (int c = 0; c < nch && P.pc_ok; c++) {
+            const int cl0 = P.pc_cl_ptr[c], cl1 = P.pc_cl_ptr[c + 1];
+            for (int q = cl0; q < cl1; q++) lid[P.pc_cl_row[q]] = q - cl0;
+            for (int r = 0; r < cp; r++) {
+                const int i = P.pc_row_pose[(size_t)c * cp + r];
+                if (i < 0) continue;
+                const size_t g = (size_t)c * gpc + r / 32;
+                for (int k = P.epose_ptr[i]; k < P.epose_ptr[i + 1]; k++) {
+                    const size_t slot = ((size_t)P.pc_goff[g] + (k - P.epose_ptr[i])) * 32 + r % 32;
+                    P.pc_loc[slot] = (unsigned short)lid[P.b_row[k]];
+                    P.pc_emap[slot] = k;
+                }
+            }
+        }
+        // up to two pose-pose neighbours per row inline (filled once the adjacency exists, below)
+        P.pc_nbr.assign((size_t)nch * cp * 2, -1);
+        P.pc_nslot.assign((size_t)nch * cp * 2, 0);
     }
     // tile-local grouping of the sorted bearing edges by landmark (static: depends only on the edge lists)
     {
@@ -194,6 +233,17 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         // first the neighbours below a pose (it is the 'hi' side), in ascending lo; uniq is sorted by (lo, hi)
         for (int k = 0; k < n_off; k++) { int i = P.off_hi[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_lo[k]; P.pp_slot[c] = k | (int)0x80000000; }
         for (int k = 0; k < n_off; k++) { int i = P.off_lo[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_hi[k]; P.pp_slot[c] = k; }
+    }
+
+    // inline pose-pose neighbours of the PCG chunk rows (needs the adjacency above)
+    P.pc_ncnt.assign((size_t)P.pc_chunks * P.pc_cp, 0);
+    for (size_t R = 0; R < P.pc_row_pose.size(); R++) {
+        const int i = P.pc_row_pose[R];
+        if (i < 0) continue;
+        const int q0 = P.pp_ptr[i], q1 = P.pp_ptr[i + 1];
+        P.pc_ncnt[R] = q1 - q0;
+        const size_t nrows = P.pc_row_pose.size();
+        for (int k = 0; k < 2 && q0 + k < q1; k++) { P.pc_nbr[k * nrows + R] = P.pp_nbr[q0 + k]; P.pc_nslot[k * nrows + R] = P.pp_slot[q0 + k]; }
     }
 
     // ---- scalar CSC pattern of H_nofixed with the source of every entry ------------------------------------

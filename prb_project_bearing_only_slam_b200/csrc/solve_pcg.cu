@@ -249,8 +249,7 @@ __global__ void k_pcg_promote(double* scal) {
 //   phase P: owned poses: w_i = Hpp_ii z_i + yoff_i - sum_k Jp_k^T (jh_k.u_l(k)) is complete locally, so the vector
 //            updates, z' = M^-1 r and the next gamma / delta parts follow in the same thread.
 enum { FS_GAMMA0 = 16, FS_DELTA0 = 19 };
-constexpr int kPcgVecs = 15;                 // p 0-2, s 3-5, x 6-8, r 9-11, yoff 12-14
-constexpr int kPcgSmemBudget = 220 * 1024;   // dynamic shared memory for the resident pose vectors
+constexpr int kPcgSmemBudget = 226 * 1024;   // dynamic shared memory available to the persistent kernel
 
 // -DBOS_PCG_TIMING: thread 0 of a few CTAs prints clock64 deltas per phase (diagnostic builds only)
 #ifdef BOS_PCG_TIMING
@@ -307,24 +306,7 @@ __device__ __forceinline__ void st2cg(double* p, double a, double b) { __stcg(re
 __device__ __forceinline__ void st2cg(float* p, float a, float b) { __stcg(reinterpret_cast<float2*>(p), make_float2(a, b)); }
 
 // ---- once per GN iteration --------------------------------------------------------------------------------------------
-// per-edge factors in sorted-edge order (scratch for the landmark-major layout)
-template <typename S>
-__global__ void __launch_bounds__(256) k_pcg_edge_factors(Dev<S> d, S* __restrict__ jP, int ld) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d.Eb) return;
-    const int p = __ldg(d.b_pose + k);
-    S j0 = S(0), j1 = S(0);
-    if (p != d.fixed) {   // the fixed pose's Jacobian block is zero (gauge): its edges drop out of Hpl
-        const PoseV<S> X = load_pose<S>(d.pose, p);
-        S lx, ly;
-        load_lm<S>(d.lm, __ldg(d.b_lm + k), lx, ly);
-        bearing_jl<S>(X, lx, ly, j0, j1);
-        const S so = sqrt(__ldg(d.b_om + k));
-        j0 *= so; j1 *= so;
-    }
-    jP[k] = j0; jP[(size_t)ld + k] = j1;
-}
-// landmark-major ELL copy of the factors; per compact landmark row: Hll^-1 and the record {Hll^-1 b_l, lx, ly}
+// per compact landmark row: Hll^-1 and the record {Hll^-1 b_l, lx, ly}
 template <typename S>
 __global__ void __launch_bounds__(256) k_ell_fill(Dev<S> d, PcgWork<S> w) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,71 +315,81 @@ __global__ void __launch_bounds__(256) k_ell_fill(Dev<S> d, PcgWork<S> w) {
         w.hllinv_c[3LL * k] = w.hllinv[3LL * L]; w.hllinv_c[3LL * k + 1] = w.hllinv[3LL * L + 1]; w.hllinv_c[3LL * k + 2] = w.hllinv[3LL * L + 2];
         w.ul4[4LL * k] = w.ul[2LL * L]; w.ul4[4LL * k + 1] = w.ul[2LL * L + 1]; w.ul4[4LL * k + 2] = d.lm[2LL * L]; w.ul4[4LL * k + 3] = d.lm[2LL * L + 1];
     }
-    if (k < d.nLs) {
-        const int e = __ldg(d.ell_Lmap + k);
-        w.Lj[k] = (e >= 0) ? w.jP[e] : S(0);
-        w.Lj[d.nLs + k] = (e >= 0) ? w.jP[(size_t)w.Eb_pad + e] : S(0);
-    }
 }
 
-// one lane per pose (pose-major ELL groups): reduced rhs g = -(b_p - Hpl Hll^-1 b_l), the block-Jacobi preconditioner
+// one thread per chunk row (= pose): reduced rhs g = -(b_p - Hpl Hll^-1 b_l), the block-Jacobi preconditioner
 // M_i = Hpp_ii - sum_k Hpl_k Hll^-1 Hpl_k^T (per EDGE: exact unless a (pose, landmark) pair is observed twice), the start
 // vectors and the first gamma / delta parts
 template <typename S>
 __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) {
     __shared__ double red[8];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, g = i >> 5;
+    const long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long nrows = (long long)d.pc_chunks * d.pc_cp;
     double gz = 0.0, zw = 0.0;
-    if (g < d.nPg) {
-        const bool valid = i < d.NP;
-        const int ic = valid ? i : d.NP - 1;
-        const PoseV<S> X = load_pose<S>(d.pose, ic);
-        S gg[3] = {-d.b[3LL * ic], -d.b[3LL * ic + 1], -d.b[3LL * ic + 2]};
+    const int i = (R < nrows) ? __ldg(d.pc_row_pose + R) : -1;
+    if (i >= 0) {
+        const int c = (int)(R / d.pc_cp), r = (int)(R % d.pc_cp);
+        const int gidx = c * (d.pc_cp / 32) + r / 32;
+        const PoseV<S> X = load_pose<S>(d.pose, i);
+        S gg[3] = {-d.b[3LL * i], -d.b[3LL * i + 1], -d.b[3LL * i + 2]};
         S hp[6], sd[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) { hp[k] = d.Hpp[6LL * ic + k]; sd[k] = hp[k]; }
-        const int off = __ldg(d.ell_Poff + g), W = __ldg(d.ell_Poff + g + 1) - off;
-        const bool active = valid && ic != d.fixed;
-        for (int t = 0; t < W; t++) {
-            const long long slot = ((long long)off + t) * 32 + lane;
-            const int row = __ldg(d.ell_Prow + slot);
-            if (row < 0 || !active) continue;
-            const S u0 = w.ul4[4LL * row], u1 = w.ul4[4LL * row + 1], lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
-            const S i00 = w.hllinv_c[3LL * row], i01 = w.hllinv_c[3LL * row + 1], i11 = w.hllinv_c[3LL * row + 2];
-            S j0, j1;
-            bearing_jl<S>(X, lx, ly, j0, j1);
-            const S so = w.omega_uniform ? (S)w.sqrt_omega : __ldg(w.Pw + slot);
-            j0 *= so; j1 *= so;
-            const S jp[3] = {-j0, -j1, j0 * ly - j1 * lx};
-            const S m = j0 * u0 + j1 * u1;
-            const S q = i00 * j0 * j0 + S(2) * i01 * j0 * j1 + i11 * j1 * j1;
-            gg[0] += jp[0] * m; gg[1] += jp[1] * m; gg[2] += jp[2] * m;
-            sd[0] -= q * jp[0] * jp[0]; sd[1] -= q * jp[0] * jp[1]; sd[2] -= q * jp[0] * jp[2];
-            sd[3] -= q * jp[1] * jp[1]; sd[4] -= q * jp[1] * jp[2]; sd[5] -= q * jp[2] * jp[2];
+        for (int k = 0; k < 6; k++) { hp[k] = d.Hpp[6LL * i + k]; sd[k] = hp[k]; }
+        const int off = __ldg(d.pc_goff + gidx), W = __ldg(d.pc_goff + gidx + 1) - off;
+        const int cl0 = __ldg(d.pc_cl_ptr + c);
+        if (i != d.fixed)
+            for (int t = 0; t < W; t++) {
+                const long long slot = ((long long)off + t) * 32 + lane;
+                const unsigned loc = d.pc_loc[slot];
+                if (loc == 0xffffu) continue;
+                const int row = __ldg(d.pc_cl_row + cl0 + (int)loc);
+                const S u0 = w.ul4[4LL * row], u1 = w.ul4[4LL * row + 1], lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
+                const S i00 = w.hllinv_c[3LL * row], i01 = w.hllinv_c[3LL * row + 1], i11 = w.hllinv_c[3LL * row + 2];
+                S j0, j1;
+                bearing_jl<S>(X, lx, ly, j0, j1);
+                const S so = w.omega_uniform ? (S)w.sqrt_omega : __ldg(w.Pw + slot);
+                j0 *= so; j1 *= so;
+                const S jp[3] = {-j0, -j1, j0 * ly - j1 * lx};
+                const S m = j0 * u0 + j1 * u1;
+                const S q = i00 * j0 * j0 + S(2) * i01 * j0 * j1 + i11 * j1 * j1;
+                gg[0] += jp[0] * m; gg[1] += jp[1] * m; gg[2] += jp[2] * m;
+                sd[0] -= q * jp[0] * jp[0]; sd[1] -= q * jp[0] * jp[1]; sd[2] -= q * jp[0] * jp[2];
+                sd[3] -= q * jp[1] * jp[1]; sd[4] -= q * jp[1] * jp[2]; sd[5] -= q * jp[2] * jp[2];
+            }
+        S mi[6];
+        sym3_inverse<S>(sd, mi);
+#pragma unroll
+        for (int k = 0; k < 6; k++) w.minv[6LL * i + k] = mi[k];
+        const S z[3] = {mi[0] * gg[0] + mi[1] * gg[1] + mi[2] * gg[2], mi[1] * gg[0] + mi[3] * gg[1] + mi[4] * gg[2],
+                        mi[2] * gg[0] + mi[4] * gg[1] + mi[5] * gg[2]};
+        const S hz[3] = {hp[0] * z[0] + hp[1] * z[1] + hp[2] * z[2], hp[1] * z[0] + hp[3] * z[1] + hp[4] * z[2],
+                         hp[2] * z[0] + hp[4] * z[1] + hp[5] * z[2]};
+        const size_t np4 = 4 * (size_t)d.NP;
+#pragma unroll
+        for (int a = 0; a < 3; a++) w.rS[(size_t)a * nrows + R] = gg[a];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { w.rowS[(size_t)k * nrows + R] = hp[k]; w.rowS[(size_t)(6 + k) * nrows + R] = mi[k]; }
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+            const int nb = __ldg(d.pc_nbr + (size_t)n * nrows + R);
+            S o[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+            if (nb >= 0) {   // blocks are symmetric by construction (-J_s^T Omega J_s), the orientation flag does not matter
+                const S* Bo = d.Hoff + 9LL * (__ldg(d.pc_nslot + (size_t)n * nrows + R) & 0x7fffffff);
+                o[0] = Bo[0]; o[1] = Bo[1]; o[2] = Bo[2]; o[3] = Bo[4]; o[4] = Bo[5]; o[5] = Bo[8];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) w.rowS[(size_t)(12 + 6 * n + k) * nrows + R] = o[k];
         }
-        if (valid) {
-            S mi[6];
-            sym3_inverse<S>(sd, mi);
 #pragma unroll
-            for (int k = 0; k < 6; k++) w.minv[6LL * i + k] = mi[k];
-            const S z[3] = {mi[0] * gg[0] + mi[1] * gg[1] + mi[2] * gg[2], mi[1] * gg[0] + mi[3] * gg[1] + mi[4] * gg[2],
-                            mi[2] * gg[0] + mi[4] * gg[1] + mi[5] * gg[2]};
-            const S hz[3] = {hp[0] * z[0] + hp[1] * z[1] + hp[2] * z[2], hp[1] * z[0] + hp[3] * z[1] + hp[4] * z[2],
-                             hp[2] * z[0] + hp[4] * z[1] + hp[5] * z[2]};
-            const size_t np = (size_t)d.NP, np4 = 4 * np;
+        for (int a = 0; a < 4; a++) {
+            w.z4[4LL * i + a] = (a < 3) ? z[a] : S(0);
+            w.z4[np4 + 4LL * i + a] = S(0);
+        }
 #pragma unroll
-            for (int k = 0; k < kPcgVecs; k++) w.vS[(size_t)k * np + i] = (k >= 9 && k < 12) ? gg[k - 9] : S(0);
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                w.z4[4LL * i + a] = (a < 3) ? z[a] : S(0);
-                w.z4[np4 + 4LL * i + a] = S(0);
-            }
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                gz += (double)gg[a] * (double)z[a];
-                zw += (double)z[a] * (double)hz[a];
-            }
+        for (int a = 0; a < 3; a++) {
+            gz += (double)gg[a] * (double)z[a];
+            zw += (double)z[a] * (double)hz[a];
         }
     }
     double s1 = block_sum_256(gz, red);
@@ -409,14 +401,13 @@ __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) 
     }
 }
 
-// Landmark rows of the L layout, kEllLanesL lanes per row.  MODE 0: t_l from vec4 (= z), u_l = Hll^-1 t_l stored,
-// dacc -= t.u.   MODE 1: landmark back-substitution dx_l = Hll^-1 (-b_l - t_l) with vec4 = x.
+// Landmark rows of the L layout, kEllLanesL lanes per row; the per-edge factors are re-derived from the state.
+// MODE 0: t_l from vec4 (= z), u_l = Hll^-1 t_l stored, dacc -= t.u.   MODE 1: dx_l = Hll^-1 (-b_l - t_l) with vec4 = x.
 template <typename S, int MODE>
 __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork<S>& w, const S* vec4, int wg, int nwarps, double& dacc) {
     constexpr int RPG = 32 / kEllLanesL;
     const int lane = threadIdx.x & 31;
-    const S* Lj0 = w.Lj;
-    const S* Lj1 = w.Lj + d.nLs;
+    const S so_u = (S)w.sqrt_omega;
     for (int g = wg; g < d.nLg; g += nwarps) {
         const int off = __ldg(d.ell_Loff + g), W = __ldg(d.ell_Loff + g + 1) - off;
         const int row = g * RPG + lane / kEllLanesL;
@@ -425,15 +416,24 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
         if (valid) { lx = __ldg(w.ul4 + 4LL * row + 2); ly = __ldg(w.ul4 + 4LL * row + 3); }   // static half of the record
         S t0 = S(0), t1 = S(0);
         const long long s0 = (long long)off * 32 + lane;
-#pragma unroll 4
-        for (int t = 0; t < W; t++) {
-            const long long slot = s0 + (long long)t * 32;
-            const S j0 = __ldg(Lj0 + slot), j1 = __ldg(Lj1 + slot);
-            const int ps = __ldg(d.ell_Lpose + slot);
-            S z0, z1, z2, zp;
-            ld4cg(vec4 + 4LL * ps, z0, z1, z2, zp);
-            const S sc = (j0 * ly - j1 * lx) * z2 - j0 * z0 - j1 * z1;   // Jp_k . z
-            t0 += j0 * sc; t1 += j1 * sc;
+        for (int tb = 0; tb < W; tb += 8) {
+            int psv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) psv[k] = (tb + k < W) ? __ldg(d.ell_Lpose + s0 + (long long)(tb + k) * 32) : -1;   // all index loads first
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int ps = psv[k];
+                if (ps < 0) continue;                              // padding, or an edge of the fixed pose (zero Jacobian block)
+                const PoseV<S> X = load_pose<S>(d.pose, ps);
+                S z0, z1, z2, zp;
+                ld4cg(vec4 + 4LL * ps, z0, z1, z2, zp);
+                S j0, j1;
+                bearing_jl<S>(X, lx, ly, j0, j1);
+                const S so = w.omega_uniform ? so_u : __ldg(w.Lw + s0 + (long long)(tb + k) * 32);
+                j0 *= so; j1 *= so;
+                const S sc = (j0 * ly - j1 * lx) * z2 - j0 * z0 - j1 * z1;   // Jp_k . z
+                t0 += j0 * sc; t1 += j1 * sc;
+            }
         }
 #pragma unroll
         for (int o = 1; o < kEllLanesL; o <<= 1) {
@@ -456,29 +456,65 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
     }
 }
 
+// shared-memory plan of the persistent kernel (per CTA = per chunk)
 template <typename S>
-__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2, int capG) {
+struct PcgSmemPlan {
+    size_t vec_off, rec_off, loc_off, bytes;
+    __host__ __device__ PcgSmemPlan(int cp, int cl_max, int slots_max) {
+        vec_off = 0;                                                   // [12][cp]  p 0-2, s 3-5, r 6-8, yoff 9-11
+        rec_off = vec_off + (size_t)12 * cp * sizeof(S);               // [cl_max][4]  u0, u1, lx, ly of the chunk's landmarks
+        loc_off = rec_off + (size_t)4 * (cl_max > 0 ? cl_max : 1) * sizeof(S);   // [slots_max] 16-bit landmark table indices
+        bytes = (loc_off + (size_t)2 * (slots_max > 0 ? slots_max : 1) + 15) / 16 * 16;
+    }
+};
+
+template <typename S>
+__global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2) {
     extern __shared__ __align__(16) unsigned char pcg_smem[];
-    S* vsm = reinterpret_cast<S*>(pcg_smem);                 // [kPcgVecs][capG * 32]
     __shared__ double red[kPcgThreads / 32];
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max);
+    S* vsm = reinterpret_cast<S*>(pcg_smem + plan.vec_off);
+    S* rec = reinterpret_cast<S*>(pcg_smem + plan.rec_off);
+    unsigned short* loc_s = reinterpret_cast<unsigned short*>(pcg_smem + plan.loc_off);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grid = gridDim.x;
+    const int grid = gridDim.x, c = blockIdx.x, cp = d.pc_cp, gpc = cp / 32;
     const int nwarps = grid * (kPcgThreads / 32);
     const int wg = warp * grid + blockIdx.x;                 // landmark groups: consecutive groups go to different SMs
-    // pose groups owned by this CTA: g = lg * grid + blockIdx.x, handled by warp lg % 32 in every phase of every iteration
-    const int ngl = ((int)blockIdx.x < d.nPg) ? (d.nPg - (int)blockIdx.x + grid - 1) / grid : 0;
-    const size_t np = (size_t)d.NP, np4 = 4 * np, smstride = (size_t)capG * 32;
+    const size_t np4 = 4 * (size_t)d.NP, nrows = (size_t)d.pc_chunks * cp;
     unsigned epoch = 0;
     double* sc = w.scal;
 #ifdef BOS_PCG_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
-    // resident pose vectors: r from the prep kernel, p = s = x = 0
-    for (int lg = warp; lg < ngl && lg < capG; lg += kPcgThreads / 32) {
-        const int i = (lg * grid + blockIdx.x) * 32 + lane;
+    // ---- static per-thread data: this thread owns chunk rows tid and tid + 1024 for the whole solve ---------------------
+    const int goff0 = __ldg(d.pc_goff + (size_t)c * gpc);
+    const int cl0 = __ldg(d.pc_cl_ptr + c), ncl = __ldg(d.pc_cl_ptr + c + 1) - cl0;
+    int pose_i[2], soff[2], swid[2];
 #pragma unroll
-        for (int k = 0; k < kPcgVecs; k++) vsm[(size_t)k * smstride + lg * 32 + lane] = (i < d.NP && k >= 9 && k < 12) ? w.vS[(size_t)k * np + i] : S(0);
+    for (int h = 0; h < 2; h++) {
+        const int r = tid + h * kPcgThreads;
+        pose_i[h] = (r < cp) ? __ldg(d.pc_row_pose + (size_t)c * cp + r) : -1;
+        soff[h] = 0; swid[h] = 0;
+        if (r < cp) {
+            const int o = __ldg(d.pc_goff + (size_t)c * gpc + r / 32);
+            soff[h] = (o - goff0) * 32 + lane;
+            swid[h] = __ldg(d.pc_goff + (size_t)c * gpc + r / 32 + 1) - o;
+        }
+    }
+    const int myrow0 = (tid < ncl) ? __ldg(d.pc_cl_row + cl0 + tid) : -1;
+    const int myrow1 = (tid + kPcgThreads < ncl) ? __ldg(d.pc_cl_row + cl0 + tid + kPcgThreads) : -1;
+    {
+        const int nslots = (__ldg(d.pc_goff + (size_t)(c + 1) * gpc) - goff0) * 32;
+        for (int k = tid; k < nslots; k += kPcgThreads) loc_s[k] = d.pc_loc[(size_t)goff0 * 32 + k];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = tid + h * kPcgThreads;
+            if (r < cp) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) vsm[(size_t)k * cp + r] = (pose_i[h] >= 0 && k >= 6 && k < 9) ? w.rS[(size_t)(k - 6) * nrows + (size_t)c * cp + r] : S(0);
+            }
+        }
     }
     __syncthreads();
     const double gamma_init = __ldcg(sc + FS_GAMMA0);
@@ -492,35 +528,53 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             S* zn = w.z4 + (size_t)((it + 1) & 1) * np4;
             // ---- phase L: off-diagonal pose-pose products, t_l / u_l per landmark, delta parts ---------------------------------
             double dacc = 0.0;
-            for (int lg = warp; lg < ngl; lg += kPcgThreads / 32) {
-                const int i = (lg * grid + blockIdx.x) * 32 + lane;
-                if (i >= d.NP) continue;
-                S* v = (lg < capG) ? vsm + lg * 32 + lane : w.vS + i;
-                const size_t vs = (lg < capG) ? smstride : np;
-                const int q0 = __ldg(d.pp_ptr + i), q1 = __ldg(d.pp_ptr + i + 1);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = pose_i[h];
+                if (i < 0) continue;
+                const int r = tid + h * kPcgThreads;
+                const size_t R = (size_t)c * cp + r;
+                const int cnt = __ldg(d.pc_ncnt + R);
+                const int nbv[2] = {__ldg(d.pc_nbr + R), __ldg(d.pc_nbr + nrows + R)};   // independent of cnt: one round trip for all three
                 S y0 = S(0), y1 = S(0), y2 = S(0);
-                for (int q = q0; q < q1; q++) {
-                    const int nb = __ldg(d.pp_nbr + q);
-                    const int sl = __ldg(d.pp_slot + q);
-                    const S* Bo = d.Hoff + 9LL * (sl & 0x7fffffff);
-                    S n0, n1, n2, np_;
-                    ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
-                    if (sl >= 0) {
-                        y0 += Bo[0] * n0 + Bo[1] * n1 + Bo[2] * n2;
-                        y1 += Bo[3] * n0 + Bo[4] * n1 + Bo[5] * n2;
-                        y2 += Bo[6] * n0 + Bo[7] * n1 + Bo[8] * n2;
-                    } else {
-                        y0 += Bo[0] * n0 + Bo[3] * n1 + Bo[6] * n2;
-                        y1 += Bo[1] * n0 + Bo[4] * n1 + Bo[7] * n2;
-                        y2 += Bo[2] * n0 + Bo[5] * n1 + Bo[8] * n2;
+                if (cnt > 0) {
+#pragma unroll
+                    for (int n = 0; n < 2; n++) {
+                        const int nb = nbv[n];
+                        if (nb < 0) continue;
+                        const S* o = w.rowS + (size_t)(12 + 6 * n) * nrows + R;
+                        const S b0 = __ldg(o), b1 = __ldg(o + nrows), b2 = __ldg(o + 2 * nrows), b3 = __ldg(o + 3 * nrows), b4 = __ldg(o + 4 * nrows),
+                                b5 = __ldg(o + 5 * nrows);
+                        S n0, n1, n2, np_;
+                        ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+                        y0 += b0 * n0 + b1 * n1 + b2 * n2;
+                        y1 += b1 * n0 + b3 * n1 + b4 * n2;
+                        y2 += b2 * n0 + b4 * n1 + b5 * n2;
                     }
-                }
-                v[12 * vs] = y0; v[13 * vs] = y1; v[14 * vs] = y2;
-                if (q0 != q1) {
+                    if (cnt > 2) {   // loop closures beyond the two inline neighbours: generic adjacency
+                        const int q0 = __ldg(d.pp_ptr + i);
+                        for (int q = q0 + 2; q < q0 + cnt; q++) {
+                            const int nb = __ldg(d.pp_nbr + q);
+                            const int sl = __ldg(d.pp_slot + q);
+                            const S* Bo = d.Hoff + 9LL * (sl & 0x7fffffff);
+                            S n0, n1, n2, np_;
+                            ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+                            if (sl >= 0) {
+                                y0 += Bo[0] * n0 + Bo[1] * n1 + Bo[2] * n2;
+                                y1 += Bo[3] * n0 + Bo[4] * n1 + Bo[5] * n2;
+                                y2 += Bo[6] * n0 + Bo[7] * n1 + Bo[8] * n2;
+                            } else {
+                                y0 += Bo[0] * n0 + Bo[3] * n1 + Bo[6] * n2;
+                                y1 += Bo[1] * n0 + Bo[4] * n1 + Bo[7] * n2;
+                                y2 += Bo[2] * n0 + Bo[5] * n1 + Bo[8] * n2;
+                            }
+                        }
+                    }
                     S z0, z1, z2, zp;
                     ld4cg(zc + 4LL * i, z0, z1, z2, zp);
                     dacc += (double)z0 * (double)y0 + (double)z1 * (double)y1 + (double)z2 * (double)y2;
                 }
+                vsm[(size_t)9 * cp + r] = y0; vsm[(size_t)10 * cp + r] = y1; vsm[(size_t)11 * cp + r] = y2;
             }
             PCG_T(0);
             pcg_landmark_rows<S, 0>(d, w, zc, wg, nwarps, dacc);
@@ -538,66 +592,81 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             if (!(denom > 0.0)) { bad = true; break; }
             const double alpha = gamma / denom;
             if (blockIdx.x == 0 && tid == 0) { __stcg(sc + FS_GAMMA0 + nn, 0.0); __stcg(sc + FS_DELTA0 + nn, 0.0); }
-            // ---- phase P: owned poses: w_i, vector updates, preconditioner, next gamma / delta parts -------------------------
-            const S al = (S)alpha, be = (S)beta;
-            double gacc = 0.0, dacc2 = 0.0;
-            for (int lg = warp; lg < ngl; lg += kPcgThreads / 32) {
-                const int g = lg * grid + blockIdx.x;
-                const int i = g * 32 + lane;
-                const bool valid = i < d.NP;
-                const int ic = valid ? i : d.NP - 1;
-                S* v = (lg < capG) ? vsm + lg * 32 + lane : w.vS + ic;
-                const size_t vs = (lg < capG) ? smstride : np;
-                const int off = __ldg(d.ell_Poff + g), W = __ldg(d.ell_Poff + g + 1) - off;
-                const PoseV<S> X = load_pose<S>(d.pose, ic);
-                S z0, z1, z2, zp;
-                ld4cg(zc + 4LL * ic, z0, z1, z2, zp);
-                const S* hp = d.Hpp + 6LL * ic;
-                S w0, w1, w2;
-                {
-                    const S h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3), h4 = __ldg(hp + 4), h5 = __ldg(hp + 5);
-                    w0 = h0 * z0 + h1 * z1 + h2 * z2 + v[12 * vs];
-                    w1 = h1 * z0 + h3 * z1 + h4 * z2 + v[13 * vs];
-                    w2 = h2 * z0 + h4 * z1 + h5 * z2 + v[14 * vs];
+            // ---- phase P: stage the chunk's landmark records, then every row is shared memory + arithmetic --------------------
+            {
+                if (myrow0 >= 0) { S a, b, e, f; ld4cg(w.ul4 + 4LL * myrow0, a, b, e, f); rec[4 * tid] = a; rec[4 * tid + 1] = b; rec[4 * tid + 2] = e; rec[4 * tid + 3] = f; }
+                if (myrow1 >= 0) {
+                    S a, b, e, f; ld4cg(w.ul4 + 4LL * myrow1, a, b, e, f);
+                    const int k = tid + kPcgThreads;
+                    rec[4 * k] = a; rec[4 * k + 1] = b; rec[4 * k + 2] = e; rec[4 * k + 3] = f;
                 }
-                const bool active = valid && ic != d.fixed;
-                const long long s0 = (long long)off * 32 + lane;
-                const S so_u = (S)w.sqrt_omega;
-#pragma unroll 4
+                for (int k = tid + 2 * kPcgThreads; k < ncl; k += kPcgThreads) {
+                    S a, b, e, f; ld4cg(w.ul4 + 4LL * __ldg(d.pc_cl_row + cl0 + k), a, b, e, f);
+                    rec[4 * k] = a; rec[4 * k + 1] = b; rec[4 * k + 2] = e; rec[4 * k + 3] = f;
+                }
+            }
+            const S al = (S)alpha, be = (S)beta;
+            const S so_u = (S)w.sqrt_omega;
+            double gacc = 0.0, dacc2 = 0.0;
+            // loads by pose index first (independent of the staging), then the barrier, then the rows
+            PoseV<S> X[2];
+            S zz[2][3];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                X[h] = PoseV<S>{S(0), S(0), S(1), S(0)};
+                zz[h][0] = zz[h][1] = zz[h][2] = S(0);
+                if (pose_i[h] >= 0) {
+                    X[h] = load_pose<S>(d.pose, pose_i[h]);
+                    S zp;
+                    ld4cg(zc + 4LL * pose_i[h], zz[h][0], zz[h][1], zz[h][2], zp);
+                }
+            }
+            __syncthreads();
+            PCG_T(7);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = pose_i[h];
+                const int r = tid + h * kPcgThreads;
+                if (r >= cp) continue;                       // warp-uniform: cp is a multiple of 32
+                const int W = swid[h];
+                const S z0 = zz[h][0], z1 = zz[h][1], z2 = zz[h][2];
+                S w0 = S(0), w1 = S(0), w2 = S(0);
+                const bool active = i >= 0 && i != d.fixed;
                 for (int t = 0; t < W; t++) {
-                    const long long slot = s0 + (long long)t * 32;
-                    const int c = __ldg(d.ell_Prow + slot);
-                    if (c < 0 || !active) continue;
-                    S u0, u1, lx, ly;
-                    ld4cg(w.ul4 + 4LL * c, u0, u1, lx, ly);
+                    const unsigned lc = loc_s[soff[h] + t * 32];
+                    if (lc == 0xffffu || !active) continue;
+                    const S u0 = rec[4 * lc], u1 = rec[4 * lc + 1], lx = rec[4 * lc + 2], ly = rec[4 * lc + 3];
                     S j0, j1;
-                    bearing_jl<S>(X, lx, ly, j0, j1);
-                    const S so = w.omega_uniform ? so_u : __ldg(w.Pw + slot);
+                    bearing_jl<S>(X[h], lx, ly, j0, j1);
+                    const S so = w.omega_uniform ? so_u : __ldg(w.Pw + (size_t)goff0 * 32 + soff[h] + t * 32);
                     j0 *= so; j1 *= so;
                     const S m = j0 * u0 + j1 * u1;
                     w0 += j0 * m; w1 += j1 * m; w2 -= (j0 * ly - j1 * lx) * m;
                 }
-                if (!valid) continue;
-                S r0, r1, r2;
-                {
-                    const S p0 = z0 + be * v[0], p1 = z1 + be * v[vs], p2 = z2 + be * v[2 * vs];
-                    const S s0_ = w0 + be * v[3 * vs], s1 = w1 + be * v[4 * vs], s2 = w2 + be * v[5 * vs];
-                    v[0] = p0; v[vs] = p1; v[2 * vs] = p2;
-                    v[3 * vs] = s0_; v[4 * vs] = s1; v[5 * vs] = s2;
-                    v[6 * vs] += al * p0; v[7 * vs] += al * p1; v[8 * vs] += al * p2;
-                    r0 = v[9 * vs] - al * s0_; r1 = v[10 * vs] - al * s1; r2 = v[11 * vs] - al * s2;
-                    v[9 * vs] = r0; v[10 * vs] = r1; v[11 * vs] = r2;
-                }
-                const S* mi = w.minv + 6LL * i;
-                const S m0 = __ldg(mi), m1 = __ldg(mi + 1), m2 = __ldg(mi + 2), m3 = __ldg(mi + 3), m4 = __ldg(mi + 4), m5 = __ldg(mi + 5);
+                if (i < 0) continue;
+                const S* hp = w.rowS + (size_t)c * cp + r;
+                const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
+                        h5 = __ldg(hp + 5 * nrows);
+                w0 += h0 * z0 + h1 * z1 + h2 * z2 + vsm[(size_t)9 * cp + r];
+                w1 += h1 * z0 + h3 * z1 + h4 * z2 + vsm[(size_t)10 * cp + r];
+                w2 += h2 * z0 + h4 * z1 + h5 * z2 + vsm[(size_t)11 * cp + r];
+                S* v = vsm + r;
+                const S p0 = z0 + be * v[0], p1 = z1 + be * v[cp], p2 = z2 + be * v[2 * cp];
+                const S s0_ = w0 + be * v[3 * cp], s1 = w1 + be * v[4 * cp], s2 = w2 + be * v[5 * cp];
+                v[0] = p0; v[cp] = p1; v[2 * cp] = p2;
+                v[3 * cp] = s0_; v[4 * cp] = s1; v[5 * cp] = s2;
+                const S r0 = v[6 * cp] - al * s0_, r1 = v[7 * cp] - al * s1, r2 = v[8 * cp] - al * s2;
+                v[6 * cp] = r0; v[7 * cp] = r1; v[8 * cp] = r2;
+                S* xg = w.xS + (size_t)c * cp + r;
+                xg[0] += al * p0; xg[nrows] += al * p1; xg[2 * nrows] += al * p2;
+                const S* mi = hp + 6 * nrows;
+                const S m0 = __ldg(mi), m1 = __ldg(mi + nrows), m2 = __ldg(mi + 2 * nrows), m3 = __ldg(mi + 3 * nrows), m4 = __ldg(mi + 4 * nrows),
+                        m5 = __ldg(mi + 5 * nrows);
                 const S zn0 = m0 * r0 + m1 * r1 + m2 * r2, zn1 = m1 * r0 + m3 * r1 + m4 * r2, zn2 = m2 * r0 + m4 * r1 + m5 * r2;
                 st4cg(zn + 4LL * i, zn0, zn1, zn2);
                 gacc += (double)r0 * (double)zn0 + (double)r1 * (double)zn1 + (double)r2 * (double)zn2;
-                {
-                    const S h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3), h4 = __ldg(hp + 4), h5 = __ldg(hp + 5);
-                    dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
-                             (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
-                }
+                dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
+                         (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
             }
             PCG_T(4);
             {
@@ -619,12 +688,12 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     }
     // ---- epilogue: dx_p = x; x as padded records for the back-substitution gather; dx_l ----------------------------------
     S* x4 = w.z4 + (size_t)((it + 1) & 1) * np4;    // the z buffer that is not current
-    for (int lg = warp; lg < ngl; lg += kPcgThreads / 32) {
-        const int i = (lg * grid + blockIdx.x) * 32 + lane;
-        if (i >= d.NP) continue;
-        const S* v = (lg < capG) ? vsm + lg * 32 + lane : w.vS + i;
-        const size_t vs = (lg < capG) ? smstride : np;
-        const S x0 = v[6 * vs], x1 = v[7 * vs], x2 = v[8 * vs];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int i = pose_i[h];
+        if (i < 0) continue;
+        const S* xg = w.xS + (size_t)c * cp + tid + h * kPcgThreads;
+        const S x0 = xg[0], x1 = xg[nrows], x2 = xg[2 * nrows];
         d.delta[3LL * i] = x0; d.delta[3LL * i + 1] = x1; d.delta[3LL * i + 2] = x2;
         st4cg(x4 + 4LL * i, x0, x1, x2);
     }
@@ -640,45 +709,43 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     if (gtid == 0) { sc[SC_ITER] = (double)it; sc[SC_BAD] = bad ? 1.0 : 0.0; }
 #ifdef BOS_PCG_TIMING
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2))
-        printf("cta %d iters %d cycles/iter: offdiag %lld Lrows %lld bsum %lld bar1 %lld phaseP %lld bsum2 %lld bar2 %lld\n", (int)blockIdx.x, it,
-               tacc[0] / (it ? it : 1), tacc[1] / (it ? it : 1), tacc[2] / (it ? it : 1), tacc[3] / (it ? it : 1), tacc[4] / (it ? it : 1),
-               tacc[5] / (it ? it : 1), tacc[6] / (it ? it : 1));
+        printf("cta %d iters %d cycles/iter: offdiag %lld Lrows %lld bsum %lld bar1 %lld stage %lld rows %lld bsum2 %lld bar2 %lld\n", (int)blockIdx.x, it,
+               tacc[0] / (it ? it : 1), tacc[1] / (it ? it : 1), tacc[2] / (it ? it : 1), tacc[3] / (it ? it : 1), tacc[7] / (it ? it : 1),
+               tacc[4] / (it ? it : 1), tacc[5] / (it ? it : 1), tacc[6] / (it ? it : 1));
 #endif
+}
+
+// the persistent kernel needs the chunk's vectors, landmark records and slot indices in shared memory, at most two rows per thread
+template <typename S>
+bool pcg_fused_supported(const Dev<S>& d) {
+    if (!d.pc_ok || d.pc_cp > 2 * kPcgThreads || d.pc_chunks < 1) return false;
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max);
+    return plan.bytes <= (size_t)kPcgSmemBudget;
 }
 
 template <typename S>
 int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st, int* iterations_out, int* launches) {
     int nl = 0;
     const int gl = (d.NL + 255) / 256;
+    const long long nrows = (long long)d.pc_chunks * d.pc_cp;
     cudaMemsetAsync(w.scal, 0, 32 * sizeof(double), st);
     cudaMemsetAsync(w.bar, 0, 4 * sizeof(unsigned), st);
+    cudaMemsetAsync(w.xS, 0, 3 * (size_t)nrows * sizeof(S), st);
     if (d.NL > 0) { k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++; }
-    if (d.Eb > 0) {
-        k_pcg_edge_factors<S><<<(d.Eb + 255) / 256, 256, 0, st>>>(d, w.jP, w.Eb_pad); nl++;
-        const long long n = d.nLs > d.n_clm ? d.nLs : d.n_clm;
-        k_ell_fill<S><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, w); nl++;
-    }
-    k_pcg_fused_prep<S><<<(d.nPg * 32 + 255) / 256, 256, 0, st>>>(d, w); nl++;
-    int grid = (d.nPg > d.nLg ? d.nPg : d.nLg);                 // groups of 32 rows: one warp each
-    grid = (grid + kPcgThreads / 32 - 1) / (kPcgThreads / 32);
-    if (grid > w.sm_count) grid = w.sm_count;
-    if (grid < 1) grid = 1;
-    const int ngl_max = (d.nPg + grid - 1) / grid;
-    int capG = kPcgSmemBudget / (kPcgVecs * 32 * (int)sizeof(S));
-    if (capG > ngl_max) capG = ngl_max;
-    if (capG < 1) capG = 1;
-    const size_t smem = (size_t)kPcgVecs * capG * 32 * sizeof(S);
+    if (d.n_clm > 0) { k_ell_fill<S><<<(d.n_clm + 255) / 256, 256, 0, st>>>(d, w); nl++; }
+    k_pcg_fused_prep<S><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(d, w); nl++;
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max);
     static size_t configured[2] = {0, 0};
     size_t& conf = configured[sizeof(S) == 8 ? 0 : 1];
-    if (smem > conf) {
-        if (cudaFuncSetAttribute(k_pcg_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        conf = smem;
+    if (plan.bytes > conf) {
+        if (cudaFuncSetAttribute(k_pcg_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes) != cudaSuccess) return -1;
+        conf = plan.bytes;
     }
     Dev<S> dd = d;
     PcgWork<S> ww = w;
     double tol2 = rtol * rtol;
-    void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2, (void*)&capG};
-    if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(grid), dim3(kPcgThreads), args, smem, st) != cudaSuccess) return -1;
+    void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2};
+    if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(d.pc_chunks), dim3(kPcgThreads), args, plan.bytes, st) != cudaSuccess) return -1;
     nl++;
     double host_scal[32];
     if (cudaMemcpyAsync(host_scal, w.scal, 32 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
@@ -691,7 +758,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
 template <typename S>
 int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st,
                      int* iterations_out, int* launches) {
-    if (w.variant == 0) return launch_pcg_fused<S>(d, w, max_iters, rtol, st, iterations_out, launches);
+    if (w.variant == 0 && pcg_fused_supported<S>(d)) return launch_pcg_fused<S>(d, w, max_iters, rtol, st, iterations_out, launches);
     int nl = 0;
     const int n = 3 * d.NP;
     const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256, gh = (d.n_hpl + 255) / 256, gn = (n + 255) / 256;

@@ -355,7 +355,8 @@ def test_large_world_size_independent_properties(built_lib):
     assert chi[-1] < 0.5 * chi[0] and s.pcg_iterations > 0
 
 
-def test_pcg_fused_kernel_equals_classic_loop(built_lib):
+@pytest.mark.parametrize("uniform_omega", [True, False])
+def test_pcg_fused_kernel_equals_classic_loop(built_lib, uniform_omega):
     """The persistent cooperative PCG kernel (Chronopoulos-Gear recurrences, RED scatter) and the classic multi-kernel loop
     solve the same system: same dx to solver tolerance, on a world with duplicate blocks, unobserved and single-observation
     landmarks (exercises the padded tile layout)."""
@@ -364,8 +365,9 @@ def test_pcg_fused_kernel_equals_classic_loop(built_lib):
     lm_ids = np.concatenate([pr0.lm_ids, [10 ** 6, 10 ** 6 + 1]]).astype(np.int32)      # two landmarks nobody observes
     bp = np.concatenate([w["b_pose_id"], w["b_pose_id"][:50]]); bl = np.concatenate([w["b_lm_id"], w["b_lm_id"][:50]])
     bz = np.concatenate([w["b_z"], w["b_z"][:50] + 0.002])
+    bom = None if uniform_omega else np.random.default_rng(3).uniform(0.5, 2.0, size=len(bz))   # per-edge information values
     pr = Problem(w["pose_ids"], bp, bl, bz, w["o_src_id"], w["o_dst_id"], w["o_z"], w["o_omega"], fixed_pose_id=int(w["pose_ids"][5]),
-                 lm_ids=lm_ids)
+                 lm_ids=lm_ids, b_omega=bom)
     o = oracle_for(w["pose_ids"], w["poses_init"], pr0)
     P, L0 = o.state()
     L = np.vstack([L0, [[1.0, 2.0], [3.0, 4.0]]])
