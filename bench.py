@@ -43,13 +43,28 @@ def load_peaks():
 
 
 def hb_build_bytes(NP, NL, Eb, Eo, n_off, S):
-    """Algorithmic bytes of one H, b build in OUR layout (DESIGN.md): SoA edge reads + state once + every block written once.
+    """Algorithmic bytes of one H, b build in OUR layout (DESIGN.md section 4): SoA edge reads + state once + every block written once.
     reads : bearing 2xint32 + z + omega ; odometry 2xint32 + slot int32 + z[3] + Omega upper[6] ; state 4S/pose + 2S/lm
     writes: pose-lm 3x2 ; pose-pose 3x3 ; diagonal blocks stored symmetric (6 / 3 scalars) ; b."""
     N = 3 * NP + 2 * NL
     reads = Eb * (8 + 2 * S) + Eo * (12 + 9 * S) + NP * 4 * S + NL * 2 * S
     writes = Eb * 6 * S + n_off * 9 * S + NP * 6 * S + NL * 3 * S + N * S
     return reads + writes
+
+
+def pcg_iteration_bytes(NP, NL, Eb, S):
+    """Algorithmic bytes of ONE CG iteration of the persistent PCG kernel: every array the iteration
+    must touch, each element once (gathered records counted once per pass, not once per edge):
+    landmark pass: 4 B pose word per edge, pose state 4S + z 4S per pose, per landmark Hll^-1 3S + position 2S read, u 2S written;
+    pose pass:     2 B landmark-table index per edge, per pose state 4S + z 4S read + z' 4S written + Hpp 6S + M^-1 6S +
+                   two pose-pose blocks 12S + two neighbour indices 8 B + x 3S read and written; u, position 4S per landmark."""
+    return Eb * 6 + NP * (8 * S + 12 * S + 24 * S + 8 + 6 * S) + NL * (7 * S + 4 * S)
+
+
+def load_traffic():
+    """DRAM bytes per unit from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 class ClockSampler:
@@ -259,6 +274,23 @@ def run_ours(args):
     achieved = bytes_build / (ms_lin_kernel * 1e-3) / 1e9
     value = args.steps / elapsed
     clocks = clk.summary()
+    traffic = load_traffic()
+    pcg_iters = statistics.mean(s["pcg_iterations"] for s in stats)
+    if solver == capi.SOLVER_PCG and pcg_iters > 0:
+        # the dominant kernel of a step is the persistent PCG kernel (> 99 % of the step at synth-2M): one launch = one solve
+        b_it = pcg_iteration_bytes(pr.NP, pr.NL, pr.Eb, S)
+        ach = b_it * pcg_iters / (ms_solve * 1e-3) / 1e9
+        t_it = traffic.get("pcg_dram_bytes_per_cg_iteration")
+        roofline = {"kernel": "k_pcg_fused (persistent cooperative kernel: the whole block-Jacobi PCG solve of one GN iteration)",
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": (t_it * pcg_iters) if t_it else None, "peak_source": peak_src,
+                    "bytes_per_launch": b_it * pcg_iters, "bytes_per_cg_iteration": b_it, "cg_iterations_per_launch": pcg_iters,
+                    "ms_per_launch": ms_solve, "us_per_cg_iteration": 1e3 * ms_solve / pcg_iters,
+                    "note": "ms_per_launch is the solve phase (4 setup kernels + the persistent kernel), CUDA events on the context's stream"}
+    else:
+        roofline = {"kernel": "H,b build: k_pose_odometry_init + k_linearize_bearing", "bound": "hbm", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
+                    "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel}
     line = {
         "metric": "gn_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -270,11 +302,12 @@ def run_ours(args):
                    "l2": "no flush: value + edge buffers (%.0f MB) exceed the 126 MB L2" % ((int(pi.vals_len) * S + pr.Eb * 24) / 1e6)},
         "edges_linearized_per_s": E / (ms_lin * 1e-3),
         "phases_ms": {"linearize": ms_lin_kernel, "allreduce": ms_allreduce, "solve": ms_solve, "update": ms_update},
-        "pcg_iterations": statistics.mean(s["pcg_iterations"] for s in stats),
+        "pcg_iterations": pcg_iters,
         "chi2_last": stats[-1]["chi2_bearing"] + stats[-1]["chi2_odometry"],
-        "roofline": {"kernel": "H,b build: k_init_values + k_linearize_bearing + k_linearize_odometry", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel},
+        "roofline": roofline,
+        "roofline_linearize": {"kernel": "H,b build: k_pose_odometry_init + k_linearize_bearing", "bound": "hbm", "achieved": achieved, "peak": peak,
+                               "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
+                               "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel},
         "e2e": {"value": args.steps / e2e_elapsed, "unit": "iterations/s",
                 "h2d_bytes_per_step": int((4 * pr.NP + 2 * pr.NL) * 8), "d2h_bytes_per_step": int((4 * pr.NP + 2 * pr.NL) * 8 + 64)},
         "gpu_launches": int(sum(s["gpu_launches"] for s in stats)),

@@ -62,6 +62,9 @@ struct Dev {
     const int* tile_ptr = nullptr;   // [ntiles+1] groups (distinct landmarks) of each tile
     const int* tg_lm = nullptr;      // [n_groups] landmark of the group
     const int* tg_eptr = nullptr;    // [n_groups+1] into tg_edge
+    const int* tile_meta = nullptr;  // [ntiles][4] padded group offset, groups, first pose, last pose of every tile
+    const int* tgp_lm = nullptr;     // tg_lm with every tile's list starting at a multiple of 8 entries (TMA alignment)
+    const unsigned short* tgp_eptr = nullptr;  // tile-local tg_eptr, same offsets, groups + 1 entries per tile
     const unsigned short* tg_edge = nullptr;  // [Eb] tile-local edge index
     // sliced-ELL layouts of the bearing edges for the fused PCG kernel
     int n_clm = 0, nLg = 0;
@@ -85,6 +88,7 @@ struct Dev {
     // state
     S* pose = nullptr;  // [NP][4] x,y,c,s
     S* lm = nullptr;    // [NL][2]
+    S* theta = nullptr; // [NP] t2v angle of every pose, refreshed whenever the poses change (set_state, update)
     // value buffer  [ b (N) | Hpp (6 NP) | Hll (3 NL) | Hoff (9 n_off) | pad | Hpl (6 planes x hpl_ld) ]
     S* vals = nullptr;
     S* b = nullptr;
@@ -92,6 +96,7 @@ struct Dev {
     S* Hll = nullptr;   // xx xy yy
     S* Hoff = nullptr;  // 3x3 row-major, block H[lo][hi]
     S* Hpl = nullptr;   // SoA: entry k (3x2 row-major index) of block s at Hpl[k * hpl_ld + s]
+    S* bnd = nullptr;         // [tiles][2][9] bearing sums of pose runs cut by a tile boundary (K1 -> K2)
     double* stats = nullptr;  // [8] chi2_b, chi2_o, over_b, over_o, delta_inf(bits), status, -, -
     S* delta = nullptr;       // [N]
 };
@@ -108,6 +113,8 @@ template <typename S>
 int launch_edge_terms(const Dev<S>& d, S* err_b, S* jac_b, S* err_o, S* jac_o, cudaStream_t st);
 template <typename S>
 int launch_update(const Dev<S>& d, cudaStream_t st);
+template <typename S>
+int launch_pose_theta(const Dev<S>& d, cudaStream_t st);
 template <typename S>
 int launch_triangulate(const Dev<S>& d, int* single_obs_count_dev, cudaStream_t st);
 

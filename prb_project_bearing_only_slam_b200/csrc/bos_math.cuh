@@ -114,11 +114,14 @@ __device__ __forceinline__ void bearing_terms(const PoseV<S>& X, S lx, S ly, S z
 // J_src = [[-R_s^T, u], [0 0 -1]] with u = (DR' R_s)^T t_d;  J_dst = -J_src entry for entry
 // (R_s^T DR' t_d = -u), so only A = -R_s^T and u are returned:
 //   J_src rows: (-c, -s, u0), (s, -c, u1), (0, 0, -1).
+// t2v's angle of a pose (framework/definitions.hpp:39-43): Rotation2D(R).smallestAngle() = smallestAngle(atan2(R10, R00))
 template <typename S>
-__device__ __forceinline__ void odometry_terms(const PoseV<S>& Xs, const PoseV<S>& Xd, S z0, S z1, S z2,
+__device__ __forceinline__ S pose_theta(const PoseV<S>& X) { return smallest_angle<S>(atan2(X.s, X.c)); }
+
+// ths / thd = pose_theta of the two poses (the assembly path caches them per pose, K7 refreshes them with the state)
+template <typename S>
+__device__ __forceinline__ void odometry_terms(const PoseV<S>& Xs, const PoseV<S>& Xd, S ths, S thd, S z0, S z1, S z2,
                                                S err[3], S& u0, S& u1) {
-    S ths = smallest_angle<S>(atan2(Xs.s, Xs.c));   // t2v (framework/definitions.hpp:39-43)
-    S thd = smallest_angle<S>(atan2(Xd.s, Xd.c));
     S tx = Xd.x - Xs.x, ty = Xd.y - Xs.y;
     S p0 = Xs.c * tx + Xs.s * ty;
     S p1 = (-Xs.s) * tx + Xs.c * ty;
@@ -128,6 +131,10 @@ __device__ __forceinline__ void odometry_terms(const PoseV<S>& Xs, const PoseV<S
     err[2] = normalized_angle<S>(p2 - z2);
     u0 = (-Xs.s) * Xd.x + Xs.c * Xd.y;
     u1 = (-Xs.c) * Xd.x + (-Xs.s) * Xd.y;
+}
+template <typename S>
+__device__ __forceinline__ void odometry_terms(const PoseV<S>& Xs, const PoseV<S>& Xd, S z0, S z1, S z2, S err[3], S& u0, S& u1) {
+    odometry_terms<S>(Xs, Xd, pose_theta<S>(Xs), pose_theta<S>(Xd), z0, z1, z2, err, u0, u1);
 }
 
 // M = J_s^T Omega J_s (symmetric, 6 unique: 00 01 02 11 12 22), v = J_s^T Omega e, chi = e^T Omega e.

@@ -162,7 +162,7 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     d.NP = P.NP; d.NL = P.NL; d.fixed = P.fixed; d.Eb = P.Eb; d.Eo = P.Eo; d.N = P.N;
     d.n_hpl = (int)P.slot_pose.size(); d.n_off = (int)P.off_lo.size();
     // bearing SoA in sorted order, padded to a multiple of 4 edges (the kernel reads 4 per thread); padding has omega = 0
-    d.Eb_pad = (P.Eb + 3) / 4 * 4 + 4;
+    d.Eb_pad = (P.Eb + kLinTile - 1) / kLinTile * kLinTile + kLinTile;   // whole tiles: the bearing kernel fetches tiles by TMA bulk copies
     d.hpl_ld = (d.n_hpl + 3) / 4 * 4 + 8 * kLinTile;   // room for up to 8 tile-padded rank shards   // room for the padded in-place allgather of rank shards
     std::vector<S> bz(d.Eb_pad, S(0)), bom(d.Eb_pad, S(0));
     std::vector<int> bpose(d.Eb_pad, P.Eb ? P.b_pose[P.Eb - 1] : 0), blm(d.Eb_pad, 0), bslot(d.Eb_pad, 0);
@@ -191,7 +191,32 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(lm_order, P.lm_order) UP(lm_order_pose, P.lm_order_pose) UP(lm_order_lm, P.lm_order_lm)
     UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)
     UP(tri_ptr, P.tri_ptr) UP(tri_edge, P.tri_edge)
-    UP(epose_ptr, P.epose_ptr) UP(tile_ptr, P.tile_ptr) UP(tg_lm, P.tg_lm) UP(tg_eptr, P.tg_eptr) UP(tg_edge, P.tg_edge)
+    {
+        std::vector<int> ep(P.epose_ptr);
+        ep.resize(ep.size() + 16, P.Eb);   // bulk copies read whole 16-byte groups
+        UP(epose_ptr, ep)
+    }
+    UP(tile_ptr, P.tile_ptr) UP(tg_lm, P.tg_lm) UP(tg_eptr, P.tg_eptr)
+    {
+        std::vector<unsigned short> tge(d.Eb_pad, 0);
+        std::copy(P.tg_edge.begin(), P.tg_edge.end(), tge.begin());
+        UP(tg_edge, tge)
+        // per-tile metadata in TMA-friendly form: group lists padded to multiples of 8 entries, one int4 header per tile
+        const int ntiles = (int)P.tile_ptr.size() - 1;
+        std::vector<int> meta(4 * (size_t)std::max(ntiles, 1), 0), glm;
+        std::vector<unsigned short> gep;
+        for (int t = 0; t < ntiles; t++) {
+            const int g0 = P.tile_ptr[t], g1 = P.tile_ptr[t + 1], ng = g1 - g0, ta = t * kLinTile, tb = std::min(P.Eb, ta + kLinTile);
+            meta[4 * t] = (int)glm.size(); meta[4 * t + 1] = ng; meta[4 * t + 2] = P.b_pose[ta]; meta[4 * t + 3] = P.b_pose[tb - 1];
+            const int cnt = (ng + 1 + 7) & ~7;
+            for (int j = 0; j < cnt; j++) {
+                glm.push_back(j < ng ? P.tg_lm[g0 + j] : 0);
+                gep.push_back((unsigned short)(j <= ng ? P.tg_eptr[g0 + j] - ta : 0));
+            }
+        }
+        glm.resize(glm.size() + 8, 0); gep.resize(gep.size() + 8, 0);
+        UP(tile_meta, meta) UP(tgp_lm, glm) UP(tgp_eptr, gep)
+    }
     UP(pl_lm_id, P.pl_lm_id) UP(ell_Loff, P.ell_Loff) UP(ell_Lpose, P.ell_Lpose)
     UP(pc_row_pose, P.pc_row_pose) UP(pc_goff, P.pc_goff) UP(pc_cl_ptr, P.pc_cl_ptr) UP(pc_cl_row, P.pc_cl_row) UP(pc_loc, P.pc_loc)
     UP(pc_emap, P.pc_emap) UP(pc_nbr, P.pc_nbr) UP(pc_nslot, P.pc_nslot) UP(pc_ncnt, P.pc_ncnt)
@@ -207,14 +232,16 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
 #undef UP
     d.pose = m.get<S>(4 * (size_t)P.NP);
     d.lm = m.get<S>(2 * (size_t)std::max(P.NL, 1));
+    d.theta = m.get<S>((size_t)P.NP);
     c->vals_prefix = ((size_t)P.N + 6 * (size_t)P.NP + 3 * (size_t)P.NL + 9 * (size_t)d.n_off + 7) / 8 * 8;  // Hpl planes 32-byte aligned
     c->hpl_padded = 6 * (size_t)d.hpl_ld;
     c->vals_len = c->vals_prefix + c->hpl_padded;
     d.vals = m.get<S>(c->vals_prefix + c->hpl_padded);
+    d.bnd = m.get<S>(18 * (size_t)(d.Eb_pad / kLinTile + 1));
     d.stats = m.get<double>(8);
     d.delta = m.get<S>((size_t)P.N);
     c->d_single_obs = m.get<int>(1);
-    if (!d.pose || !d.lm || !d.vals || !d.stats || !d.delta || !c->d_single_obs) return fail(c, BOS_ERR_NOMEM, "device allocation failed");
+    if (!d.pose || !d.lm || !d.theta || !d.vals || !d.bnd || !d.stats || !d.delta || !c->d_single_obs) return fail(c, BOS_ERR_NOMEM, "device allocation failed");
     d.b = d.vals;
     d.Hpp = d.b + P.N;
     d.Hll = d.Hpp + 6 * (size_t)P.NP;
@@ -225,6 +252,7 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     CUDA_OK(c, cudaMemsetAsync(d.delta, 0, (size_t)P.N * sizeof(S), c->stream));
     CUDA_OK(c, cudaMemsetAsync(d.stats, 0, 8 * sizeof(double), c->stream));
     CUDA_OK(c, cudaMemsetAsync(d.pose, 0, 4 * (size_t)P.NP * sizeof(S), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(d.theta, 0, (size_t)P.NP * sizeof(S), c->stream));
     CUDA_OK(c, cudaMemsetAsync(d.lm, 0, 2 * (size_t)std::max(P.NL, 1) * sizeof(S), c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return BOS_OK;
@@ -412,6 +440,7 @@ int set_state_impl(bos_ctx* c, const double* poses, const double* lms) {
             CUDA_OK(c, cudaStreamSynchronize(c->stream));
         }
     }
+    if (poses) { launch_pose_theta<S>(d, c->stream); CUDA_OK(c, cudaGetLastError()); }
     if (lms && d.NL > 0) {
         if (sizeof(S) == 8) CUDA_OK(c, cudaMemcpyAsync(d.lm, lms, 2 * (size_t)d.NL * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         else {

@@ -4,27 +4,32 @@
 // error_and_jacobian x2 (slam/solver_jacobians.cpp:9-168).  The reference merges an N x N sparse
 // temporary into H for every edge; here every edge adds straight into precomputed block slots.
 //
-//   K2+K3  k_pose_odometry_init   one thread per pose: damping * I (H += damping * I, solver.cpp:64-69) plus the
-//          contributions of the odometry edges incident to that pose, gathered through a CSR list and written
-//          with PLAIN stores (no atomics, no separate zero-init pass).  J_dst = -J_src entry for entry, so one
-//          M = J_s^T Omega J_s and one 3-vector serve the source block, the destination block and the
-//          off-diagonal block.  The same kernel resets the landmark blocks and b_lm.
-//   K1     k_linearize_bearing    edge-parallel over the (pose, landmark)-sorted SoA edge buffer, FOUR consecutive
-//          edges per thread (256-bit vector loads of the index / measurement / omega arrays):
-//          - pose-landmark 3x2 blocks: owned by the edge -> stored SoA (6 planes), each thread writes its four
-//            consecutive entries of a plane with one 256-bit store (no atomics, no zero-init);
-//          - pose 3x3 diagonal block + b_pose: accumulated in registers over the thread's run of equal poses,
-//            then a warp-segmented reduction over the lanes' runs, one RED per value per run head;
-//          - landmark 2x2 diagonal block + b_lm: RED per edge (a landmark's edges are scattered over the buffer);
-//          - chi2 / over-threshold counts: warp + block reduction, one RED per CTA.
+//   K3     k_landmark_init        landmark blocks start at damping * I, b_lm at 0 (H += damping * I, solver.cpp:64-69).
+//   K1     k_linearize_bearing_persistent   persistent CTAs walk tiles of 512 (pose, landmark)-sorted edges fetched by TMA bulk
+//          copies into a 2-stage shared-memory ring:
+//          - pose-landmark 3x2 blocks: owned by the edge -> stored SoA (6 planes), 128-bit coalesced stores, no atomics;
+//          - per edge FOUR numbers are staged in shared memory (a bearing residual is scalar, so every block the edge touches
+//            is an outer product of sqrt(omega) * J with itself or with sqrt(omega) * e; the products are formed while summing);
+//          - landmark 2x2 blocks + b_lm: one thread per distinct landmark of the tile (host-precomputed tile-local grouping)
+//            sums its edges from shared memory and issues ONE set of REDs;
+//          - pose 3x3 blocks + b_pose: one thread per pose run of the tile sums its edges; a run inside the tile (all but the
+//            first / last pose of a tile) is stored PLAINLY into the pose's block, a run cut by a tile boundary goes to a
+//            per-tile side slot: no atomics and no read-modify-write on the pose side;
+//          - chi2 / over-threshold counts: warp + block reduction, one atomic per CTA.
+//   K2     k_pose_finish          one thread per pose, after K1: damping * I + the odometry edges incident to the pose (gathered
+//          through a CSR list; J_dst = -J_src entry for entry, so one M = J_s^T Omega J_s and one 3-vector serve the source
+//          block, the destination block and the off-diagonal block) + the bearing part K1 left in the pose's block or in the
+//          side slots of the tiles that cut it; plain stores.
 //
 // The fixed pose (gauge, solver.cpp:72-73) is handled by zeroing its Jacobian blocks at the source:
 // its rows/cols then hold only the damping and a zero rhs, which is the same linear system as
 // deleting them (dx_fixed = 0) without any special case downstream.
 #include "bos_internal.h"
 #include "bos_math.cuh"
+#include "bos_tma.cuh"
 
-#include <cstdlib>
+#include <cstdio>
+
 
 namespace bos {
 
@@ -60,23 +65,55 @@ template <int N, typename T> __device__ __forceinline__ void storeN(T* p, const 
     if constexpr (N == 4) store4(p, v); else if constexpr (N == 2) store2(p, v); else p[0] = v[0];
 }
 
-// ---- K2 + K3 ---------------------------------------------------------------------------------------------------
+// ---- K3 -------------------------------------------------------------------------------------------------------------
 template <typename S>
-__global__ void __launch_bounds__(128, 8) k_pose_odometry_init(Dev<S> d, int o_begin, int o_end, S kernel_threshold, S damping) {
+__global__ void __launch_bounds__(256) k_landmark_init(Dev<S> d, S damping) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.NL) return;
+    S* hl = d.Hll + 3LL * i;
+    hl[0] = damping; hl[1] = S(0); hl[2] = damping;
+    d.b[3LL * d.NP + 2LL * i] = S(0);
+    d.b[3LL * d.NP + 2LL * i + 1] = S(0);
+}
+
+// ---- K2 -------------------------------------------------------------------------------------------------------------
+// side slots of the bearing kernel: [tile][slot][9], slot 0 = the run that enters the tile from the previous one, 1 = the run
+// that leaves it; 9 = Hpp (xx xy xt yy yt tt) + b (x y t)
+template <typename S>
+__global__ void __launch_bounds__(128, 4) k_pose_finish(Dev<S> d, int e_begin, int e_end, int o_begin, int o_end, S kernel_threshold, S damping,
+                                                        const S* __restrict__ bnd) {
     __shared__ double red[2][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double chi_acc = 0.0;
     int over_acc = 0;
-    if (i < d.NL) {
-        S* hl = d.Hll + 3LL * i;
-        hl[0] = damping; hl[1] = S(0); hl[2] = damping;
-        d.b[3LL * d.NP + 2LL * i] = S(0);
-        d.b[3LL * d.NP + 2LL * i + 1] = S(0);
-    }
     if (i < d.NP) {
         S h[6] = {damping, S(0), S(0), damping, S(0), damping};
         S b[3] = {S(0), S(0), S(0)};
+        // the bearing part left by K1: in the pose's own block when its run lies inside one tile, else in the side slots
+        {
+            const int ra = __ldg(d.epose_ptr + i), rb = __ldg(d.epose_ptr + i + 1);
+            const int lo = ra > e_begin ? ra : e_begin, hi = rb < e_end ? rb : e_end;
+            if (hi > lo && i != d.fixed) {
+                const int t0 = (lo - e_begin) / kLinTile, t1 = (hi - 1 - e_begin) / kLinTile;
+                for (int t = t0; t <= t1; t++) {
+                    const int ta = e_begin + t * kLinTile, tb = (ta + kLinTile < e_end) ? ta + kLinTile : e_end;
+                    const S* src;
+                    if (ra >= ta && rb <= tb) {
+                        const S* hp = d.Hpp + 6LL * i;
+                        const S* bp = d.b + 3LL * i;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) h[k] += hp[k];
+                        b[0] += bp[0]; b[1] += bp[1]; b[2] += bp[2];
+                        continue;
+                    }
+                    src = bnd + (size_t)(2 * t + (ra < ta ? 0 : 1)) * 9;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) h[k] += src[k];
+                    b[0] += src[6]; b[1] += src[7]; b[2] += src[8];
+                }
+            }
+        }
         const size_t Eo = (size_t)d.Eo;
         const PoseV<S> Xi = load_pose<S>(d.pose, i);
         const int q0 = __ldg(d.oe_ptr + i), q1 = __ldg(d.oe_ptr + i + 1);
@@ -92,7 +129,8 @@ __global__ void __launch_bounds__(128, 8) k_pose_odometry_init(Dev<S> d, int o_b
 #pragma unroll
             for (int k = 0; k < 6; k++) om[k] = __ldg(d.o_om + k * Eo + e);
             S err[3], u0, u1;
-            odometry_terms<S>(Xs, Xd, __ldg(d.o_z + e), __ldg(d.o_z + Eo + e), __ldg(d.o_z + 2 * Eo + e), err, u0, u1);
+            const S thi = __ldg(d.theta + i), tho = __ldg(d.theta + other);
+            odometry_terms<S>(Xs, Xd, role ? tho : thi, role ? thi : tho, __ldg(d.o_z + e), __ldg(d.o_z + Eo + e), __ldg(d.o_z + 2 * Eo + e), err, u0, u1);
             const S chi = odometry_chi<S>(om, err);
             S scale = S(1);
             const bool over = chi > kernel_threshold;
@@ -147,135 +185,209 @@ constexpr int kLinThreads = 256;
 constexpr int kEPT = kLinTile / kLinThreads;  // consecutive edges per thread (2)
 static_assert(kLinThreads * kEPT == kLinTile && kEPT == 2, "one CTA covers exactly one tile, two edges per thread");
 #ifndef BOS_LIN_MINBLOCKS
-#define BOS_LIN_MINBLOCKS 3
+#define BOS_LIN_MINBLOCKS 4
 #endif
-constexpr int kNT = 14;  // per-edge terms staged in shared memory: 5 landmark-side + 9 pose-side
+constexpr int kNT = 4;  // per-edge terms staged in shared memory: sqrt(omega) * (J_lm[0], J_lm[1], J_theta) and sqrt(omega) * e
 
-// One CTA per tile of kLinTile sorted edges.
-//   phase 1: every thread linearizes two consecutive edges, stores their pose-landmark blocks (128-bit stores into
-//            the SoA planes) and stages the 14 landmark-/pose-side products in shared memory;
-//   phase 2: one thread per distinct landmark of the tile (host-precomputed grouping) and one thread per pose run of the
-//            tile sum their edges from shared memory and issue ONE set of REDs each.
-// The grouping metadata of phase 2 is fetched before phase 1 so its latency hides behind the arithmetic.
+// A CTA walks tiles blockIdx.x, +gridDim.x, ... and the tile's edge
+// data (pose / landmark indices, measurement, omega, the tile-local landmark grouping) arrives by TMA bulk copies into a
+// 2-stage shared-memory ring, fetched one tile ahead: the HBM latency of the edge stream is off the critical path, the
+// grid is exactly the number of resident CTAs (kLinPersistCtas per SM).
+constexpr int kLinStages = 2;
+constexpr int kLinPersistCtas = 4;
+#ifndef BOS_LIN_SUB
+#define BOS_LIN_SUB 1
+#endif
+constexpr int kLinSub = BOS_LIN_SUB;   // lanes that share one landmark group / pose run in phase 2
+template <typename S>
+struct LinStage {
+    int pose[kLinTile];
+    int lm[kLinTile];
+    S z[kLinTile];
+    S om[kLinTile];
+    unsigned short tge[kLinTile];          // tile-local edge index, grouped by landmark
+    int glm[kLinTile + 8];                 // landmark of every group of the tile
+    int pe[kLinTile + 8];                  // epose_ptr[p_lo ..]: bearing-edge ranges of the tile's poses
+    unsigned short geptr[kLinTile + 8];    // tile-local range of every group in tge
+    int hdr[4];                            // groups, first pose, last pose, p_lo
+};
+template <typename S>
+struct LinSmem {
+    LinStage<S> stage[kLinStages];
+    S st[kNT][kLinTile];
+    double red[2][kLinThreads / 32];
+    unsigned long long bar[kLinStages];
+};
+
 template <typename S, bool kIdentSlots>
-__global__ void __launch_bounds__(kLinThreads, BOS_LIN_MINBLOCKS) k_linearize_bearing(Dev<S> d, int e_begin, int e_end, S kernel_threshold, int dbg) {
-    __shared__ double red[2][kLinThreads / 32];
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    S (*st)[kLinTile] = reinterpret_cast<S (*)[kLinTile]>(smem_raw);   // [kNT][kLinTile]
+__global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bearing_persistent(Dev<S> d, int e_begin, int e_end, S kernel_threshold, S* __restrict__ bnd) {
+    extern __shared__ __align__(128) unsigned char lin_smem_raw[];
+    LinSmem<S>& sm = *reinterpret_cast<LinSmem<S>*>(lin_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
-    const int ta = e_begin + tile * kLinTile;                 // e_begin is a multiple of the tile size
-    const int tb = (ta + kLinTile < e_end) ? ta + kLinTile : e_end;
-    const int e0 = ta + tid * kEPT;
-    const bool any = e0 < tb;
-    // ---- loads: this thread's two edges, then the phase-2 metadata --------------------------------------------------
-    int p2[kEPT] = {-1, -1}, l2[kEPT] = {0, 0};
-    S z2[kEPT] = {S(0), S(0)}, om2[kEPT] = {S(0), S(0)};
-    if (any) {  // the SoA arrays are padded to a multiple of 4 edges
-        loadN<kEPT>(d.b_pose + e0, p2); loadN<kEPT>(d.b_lm + e0, l2);
-        loadN<kEPT>(d.b_z + e0, z2); loadN<kEPT>(d.b_om + e0, om2);
-    }
-    const int gt = ta / kLinTile;
-    const int g0 = __ldg(d.tile_ptr + gt), g1 = __ldg(d.tile_ptr + gt + 1);
-    const int pfirst = __ldg(d.b_pose + ta), plast = __ldg(d.b_pose + tb - 1);
-    int gl = 0, ga = 0, gb = 0, ra = 0, rb = 0;
-    if (g0 + tid < g1) { gl = __ldg(d.tg_lm + g0 + tid); ga = __ldg(d.tg_eptr + g0 + tid); gb = __ldg(d.tg_eptr + g0 + tid + 1); }
-    const int rt = kLinThreads - 1 - tid;   // pose runs are taken from the top of the CTA, landmark groups from the bottom
-    if (pfirst + rt <= plast) { ra = __ldg(d.epose_ptr + pfirst + rt); rb = __ldg(d.epose_ptr + pfirst + rt + 1); }
-    // ---- phase 1 -------------------------------------------------------------------------------------------------------
-    double chi_acc = 0.0;
-    int over_acc = 0;
-    S hpl[6][kEPT];
-    S tv[kNT][kEPT];
-    PoseV<S> X = {S(0), S(0), S(1), S(0)};
-    int xpose = -1;
-#pragma unroll
-    for (int j = 0; j < kEPT; j++) {
-        const bool valid = any && (e0 + j < tb);
-        S J[5] = {S(0), S(0), S(0), S(0), S(0)};
-        S err = S(0), om = S(0);
-        const int p = p2[j], l = l2[j];
-        if (valid) {
-            if (p != xpose) { X = load_pose<S>(d.pose, p); xpose = p; }
-            S lx, ly;
-            load_lm<S>(d.lm, l, lx, ly);
-            om = om2[j];
-            bearing_terms<S>(X, lx, ly, z2[j], err, J);
-            // threshold robust kernel: scales the ERROR only (slam/solver.cpp:37-41)
-            const S chi = err * om * err;
-            chi_acc += (double)chi;
-            if (chi > kernel_threshold) { err *= sqrt(kernel_threshold / chi); over_acc++; }
-            if (p == d.fixed) { J[0] = J[1] = J[2] = S(0); }
-        }
-        const S w0 = J[0] * om, w1 = J[1] * om, w2 = J[2] * om;  // (J^T omega), pose part
-        const S w3 = J[3] * om, w4 = J[4] * om;                  // landmark part
-        hpl[0][j] = w0 * J[3]; hpl[1][j] = w0 * J[4];
-        hpl[2][j] = w1 * J[3]; hpl[3][j] = w1 * J[4];
-        hpl[4][j] = w2 * J[3]; hpl[5][j] = w2 * J[4];
-        tv[0][j] = w3 * J[3]; tv[1][j] = w3 * J[4]; tv[2][j] = w4 * J[4];
-        tv[3][j] = w3 * err; tv[4][j] = w4 * err;
-        tv[5][j] = w0 * J[0]; tv[6][j] = w0 * J[1]; tv[7][j] = w0 * J[2];
-        tv[8][j] = w1 * J[1]; tv[9][j] = w1 * J[2]; tv[10][j] = w2 * J[2];
-        tv[11][j] = w0 * err; tv[12][j] = w1 * err; tv[13][j] = w2 * err;
-        if (!kIdentSlots && valid) {
-            const long long s = __ldg(d.b_slot + e0 + j);
-#pragma unroll
-            for (int k = 0; k < 6; k++) red_add(d.Hpl + (long long)k * d.hpl_ld + s, hpl[k][j]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kNT; k++) {   // two adjacent edges -> one 128-bit (64-bit for float) shared store, conflict-free
-        typedef typename Vec2T<S>::type V2;
-        V2 v; v.x = tv[k][0]; v.y = tv[k][1];
-        *reinterpret_cast<V2*>(&st[k][tid * kEPT]) = v;
-    }
-    if (kIdentSlots && any && !(dbg & 4)) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) storeN<kEPT>(d.Hpl + (long long)k * d.hpl_ld + e0, hpl[k]);
+    const int ntiles = (e_end - e_begin + kLinTile - 1) / kLinTile;
+    constexpr unsigned kEdgeBytes = 2 * kLinTile * 4 + 2 * kLinTile * sizeof(S) + kLinTile * 2;
+    auto issue = [&](int tile, int stg) {   // thread 0: everything the tile needs arrives by bulk copies on one mbarrier
+        const size_t e = (size_t)e_begin + (size_t)tile * kLinTile;
+        LinStage<S>& g = sm.stage[stg];
+        const int4 m = __ldg(reinterpret_cast<const int4*>(d.tile_meta) + e / kLinTile);   // padded group offset, groups, first pose, last pose
+        const int cnt = (m.y + 1 + 7) & ~7;
+        int p_lo = m.z & ~3, pcnt = (m.w + 2 - p_lo + 3) & ~3;
+        if (pcnt > kLinTile + 8) { p_lo = -1; pcnt = 0; }   // a long stretch of edge-free poses inside the tile: read epose_ptr directly
+        g.hdr[0] = m.y; g.hdr[1] = m.z; g.hdr[2] = m.w; g.hdr[3] = p_lo;
+        mbar_expect_tx(&sm.bar[stg], kEdgeBytes + (unsigned)cnt * 6u + (unsigned)pcnt * 4u);
+        tma_bulk_load(g.pose, d.b_pose + e, kLinTile * 4, &sm.bar[stg]);
+        tma_bulk_load(g.lm, d.b_lm + e, kLinTile * 4, &sm.bar[stg]);
+        tma_bulk_load(g.z, d.b_z + e, kLinTile * sizeof(S), &sm.bar[stg]);
+        tma_bulk_load(g.om, d.b_om + e, kLinTile * sizeof(S), &sm.bar[stg]);
+        tma_bulk_load(g.tge, d.tg_edge + e, kLinTile * 2, &sm.bar[stg]);
+        tma_bulk_load(g.glm, d.tgp_lm + m.x, (unsigned)cnt * 4u, &sm.bar[stg]);
+        tma_bulk_load(g.geptr, d.tgp_eptr + m.x, (unsigned)cnt * 2u, &sm.bar[stg]);
+        if (pcnt > 0) tma_bulk_load(g.pe, d.epose_ptr + p_lo, (unsigned)pcnt * 4u, &sm.bar[stg]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kLinStages; s++) mbar_init(&sm.bar[s], 1);
+        mbar_fence_init();
     }
     __syncthreads();
-    // ---- phase 2: landmark groups -------------------------------------------------------------------------------------------
-    if (!(dbg & 1)) {
-        for (int g = g0 + tid; g < g1; g += kLinThreads) {
-            if (g != g0 + tid) { gl = __ldg(d.tg_lm + g); ga = __ldg(d.tg_eptr + g); gb = __ldg(d.tg_eptr + g + 1); }
-            S v0 = S(0), v1 = S(0), v2 = S(0), v3 = S(0), v4 = S(0);
-            for (int q = ga; q < gb; q++) {
-                const int le = __ldg(d.tg_edge + q);
-                v0 += st[0][le]; v1 += st[1][le]; v2 += st[2][le]; v3 += st[3][le]; v4 += st[4][le];
-            }
-            S* hl = d.Hll + 3LL * gl;
-            red_add(hl + 0, v0); red_add(hl + 1, v1); red_add(hl + 2, v2);
-            S* bl = d.b + 3LL * d.NP + 2LL * gl;
-            red_add(bl + 0, v3); red_add(bl + 1, v4);
-        }
+    if (tid == 0) {
+        if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+        if ((int)blockIdx.x + (int)gridDim.x < ntiles) issue(blockIdx.x + gridDim.x, 1);
     }
-    // ---- phase 2: pose runs (taken from the top of the CTA so they overlap the landmark groups of the low threads) --------
-    if (!(dbg & 2)) {
-        for (int p = pfirst + rt; p <= plast; p += kLinThreads) {
-            if (p != pfirst + rt) { ra = __ldg(d.epose_ptr + p); rb = __ldg(d.epose_ptr + p + 1); }
-            const int a = (ra > ta ? ra : ta) - ta, b = (rb < tb ? rb : tb) - ta;
-            if (p == d.fixed || a >= b) continue;
+    double chi_acc = 0.0;
+    int over_acc = 0;
+    int k = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+        const int stg = k % kLinStages;
+        const LinStage<S>& g = sm.stage[stg];
+        const int ta = e_begin + tile * kLinTile;
+        const int tb = (ta + kLinTile < e_end) ? ta + kLinTile : e_end;
+        const int e0 = ta + tid * kEPT;
+        const bool any = e0 < tb;
+        mbar_wait(&sm.bar[stg], (unsigned)((k / kLinStages) & 1));
+        // ---- phase 1 ---------------------------------------------------------------------------------------------------
+        S hpl[6][kEPT];
+        S tv[kNT][kEPT];
+        PoseV<S> X = {S(0), S(0), S(1), S(0)};
+        int xpose = -1;
+#pragma unroll
+        for (int j = 0; j < kEPT; j++) {
+            const bool valid = any && (e0 + j < tb);
+            S J[5] = {S(0), S(0), S(0), S(0), S(0)};
+            S err = S(0), so = S(0);
+            const int p = valid ? g.pose[tid * kEPT + j] : -1;
+            if (valid) {
+                const int l = g.lm[tid * kEPT + j];
+                if (p != xpose) { X = load_pose<S>(d.pose, p); xpose = p; }
+                S lx, ly;
+                load_lm<S>(d.lm, l, lx, ly);
+                const S om = g.om[tid * kEPT + j];
+                bearing_terms<S>(X, lx, ly, g.z[tid * kEPT + j], err, J);
+                // threshold robust kernel: scales the ERROR only (slam/solver.cpp:37-41)
+                const S chi = err * om * err;
+                chi_acc += (double)chi;
+                if (chi > kernel_threshold) { err *= sqrt(kernel_threshold / chi); over_acc++; }
+                so = (om == S(1)) ? S(1) : sqrt(om);
+            }
+            const S j0 = so * J[3], j1 = so * J[4], jt = so * J[2];
+            tv[0][j] = j0; tv[1][j] = j1; tv[2][j] = jt; tv[3][j] = so * err;
+            const S fz = (valid && p == d.fixed) ? S(0) : S(1);   // gauge: the fixed pose's Jacobian block is zero
+            hpl[0][j] = -(j0 * j0) * fz; hpl[1][j] = -(j0 * j1) * fz;
+            hpl[2][j] = -(j1 * j0) * fz; hpl[3][j] = -(j1 * j1) * fz;
+            hpl[4][j] = (jt * j0) * fz;  hpl[5][j] = (jt * j1) * fz;
+            if (!kIdentSlots && valid) {
+                const long long s = __ldg(d.b_slot + e0 + j);
+#pragma unroll
+                for (int q = 0; q < 6; q++) red_add(d.Hpl + (long long)q * d.hpl_ld + s, hpl[q][j]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kNT; q++) {
+            typedef typename Vec2T<S>::type V2;
+            V2 v; v.x = tv[q][0]; v.y = tv[q][1];
+            *reinterpret_cast<V2*>(&sm.st[q][tid * kEPT]) = v;
+        }
+        if (kIdentSlots && any) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) storeN<kEPT>(d.Hpl + (long long)q * d.hpl_ld + e0, hpl[q]);
+        }
+        __syncthreads();
+        // ---- phase 2: kLinSub lanes per landmark group, then per pose run; sums over the lanes by shuffles ----------------------
+        const int ng = g.hdr[0], pfirst = g.hdr[1], plast = g.hdr[2], p_lo = g.hdr[3];
+        const int sub = tid % kLinSub, item = tid / kLinSub;
+        constexpr int kItems = kLinThreads / kLinSub;
+        for (int base = 0; base < ng; base += kItems) {            // uniform trip count: every lane takes part in the shuffles
+            const int gi = base + item;
+            S v0 = S(0), v1 = S(0), v2 = S(0), v3 = S(0), v4 = S(0);
+            if (gi < ng) {
+                const int ga = g.geptr[gi], gb = g.geptr[gi + 1];
+                for (int q = ga + sub; q < gb; q += kLinSub) {
+                    const int le = g.tge[q];
+                    const S j0 = sm.st[0][le], j1 = sm.st[1][le], ee = sm.st[3][le];
+                    v0 += j0 * j0; v1 += j0 * j1; v2 += j1 * j1; v3 += j0 * ee; v4 += j1 * ee;
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < kLinSub; o <<= 1) {
+                v0 += __shfl_xor_sync(BOS_FULL_MASK, v0, o); v1 += __shfl_xor_sync(BOS_FULL_MASK, v1, o); v2 += __shfl_xor_sync(BOS_FULL_MASK, v2, o);
+                v3 += __shfl_xor_sync(BOS_FULL_MASK, v3, o); v4 += __shfl_xor_sync(BOS_FULL_MASK, v4, o);
+            }
+            if (gi < ng && sub == 0) {
+                const int gl = g.glm[gi];
+                S* hl = d.Hll + 3LL * gl;
+                red_add(hl + 0, v0); red_add(hl + 1, v1); red_add(hl + 2, v2);
+                S* bl = d.b + 3LL * d.NP + 2LL * gl;
+                red_add(bl + 0, v3); red_add(bl + 1, v4);
+            }
+        }
+        const int nruns = plast - pfirst + 1;
+        for (int base = 0; base < nruns; base += kItems) {
+            const int p = pfirst + base + item;
             S v[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) v[k] = S(0);
-            for (int q = a; q < b; q++) {
-#pragma unroll
-                for (int k = 0; k < 9; k++) v[k] += st[5 + k][q];
+            for (int q = 0; q < 9; q++) v[q] = S(0);
+            int ra = 0, rb = 0;
+            bool live = false;
+            if (p <= plast) {
+                if (p_lo >= 0) { ra = g.pe[p - p_lo]; rb = g.pe[p + 1 - p_lo]; }
+                else { ra = __ldg(d.epose_ptr + p); rb = __ldg(d.epose_ptr + p + 1); }
+                const int a = (ra > ta ? ra : ta) - ta, b = (rb < tb ? rb : tb) - ta;
+                live = (p != d.fixed) && a < b;
+                if (live)
+                    for (int q = a + sub; q < b; q += kLinSub) {   // J_pose = (-j0, -j1, jt)
+                        const S j0 = sm.st[0][q], j1 = sm.st[1][q], jt = sm.st[2][q], ee = sm.st[3][q];
+                        v[0] += j0 * j0; v[1] += j0 * j1; v[2] -= j0 * jt; v[3] += j1 * j1; v[4] -= j1 * jt; v[5] += jt * jt;
+                        v[6] -= j0 * ee; v[7] -= j1 * ee; v[8] += jt * ee;
+                    }
             }
-            S* hp = d.Hpp + 6LL * p;
 #pragma unroll
-            for (int k = 0; k < 6; k++) red_add(hp + k, v[k]);
-            S* bp = d.b + 3LL * p;
-            red_add(bp + 0, v[6]); red_add(bp + 1, v[7]); red_add(bp + 2, v[8]);
+            for (int o = 1; o < kLinSub; o <<= 1) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) v[q] += __shfl_xor_sync(BOS_FULL_MASK, v[q], o);
+            }
+            if (live && sub == 0) {
+                if (ra >= ta && rb <= tb) {   // the whole run is in this tile: plain store into the pose's own block
+                    S* hp = d.Hpp + 6LL * p;
+                    S* bp = d.b + 3LL * p;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) hp[q] = v[q];
+                    bp[0] = v[6]; bp[1] = v[7]; bp[2] = v[8];
+                } else {                      // cut by a tile boundary: side slot, summed by k_pose_finish
+                    S* dst = bnd + (size_t)(2 * tile + (ra < ta ? 0 : 1)) * 9;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) dst[q] = v[q];
+                }
+            }
         }
+        __syncthreads();                       // everyone is done with this stage and with st
+        if (tid == 0 && tile + kLinStages * (int)gridDim.x < ntiles) issue(tile + kLinStages * gridDim.x, stg);
     }
-    // ---- chi2 / over-threshold ------------------------------------------------------------------------------------------
+    // ---- chi2 / over-threshold: once per CTA ---------------------------------------------------------------------------------
     double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
-    if (lane == 0) { red[0][warp] = c; red[1][warp] = o; }
+    if (lane == 0) { sm.red[0][warp] = c; sm.red[1][warp] = o; }
     __syncthreads();
     if (tid == 0) {
         double cs = 0, os = 0;
-        for (int w = 0; w < kLinThreads / 32; w++) { cs += red[0][w]; os += red[1][w]; }
+        for (int w = 0; w < kLinThreads / 32; w++) { cs += sm.red[0][w]; os += sm.red[1][w]; }
         if (cs != 0.0) atomicAdd(d.stats + 0, cs);
         if (os != 0.0) atomicAdd(d.stats + 2, os);
     }
@@ -288,31 +400,28 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
     cudaMemsetAsync(d.stats, 0, 8 * sizeof(double), st);
     if (zero_hoff && d.n_off > 0) cudaMemsetAsync(d.Hoff, 0, sizeof(S) * 9 * (size_t)d.n_off, st);
     if (zero_hpl && d.n_hpl > 0) cudaMemsetAsync(d.Hpl, 0, sizeof(S) * 6 * (size_t)d.hpl_ld, st);
-    {
-        const int n = d.NP > d.NL ? d.NP : d.NL;
-        k_pose_odometry_init<S><<<(n + 127) / 128, 128, 0, st>>>(d, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here);
-        launches++;
-    }
+    if (d.NL > 0) { k_landmark_init<S><<<(d.NL + 255) / 256, 256, 0, st>>>(d, (S)damping_here); launches++; }
     const int nb = r.b_end - r.b_begin;
     if (nb > 0) {
         const int tiles = (nb + kLinTile - 1) / kLinTile;
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("BOS_LIN_DEBUG"); dbg = e ? atoi(e) : 0; }
-        const size_t smem = sizeof(S) * kNT * kLinTile;
+        const size_t smem = sizeof(LinSmem<S>);
         static bool attr_done[2] = {false, false};
         bool& done = attr_done[sizeof(S) == 8 ? 0 : 1];
         if (!done) {
-            cudaFuncSetAttribute(k_linearize_bearing<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_linearize_bearing<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_linearize_bearing_persistent<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_linearize_bearing_persistent<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             done = true;
         }
+        int grid = sm_count * kLinPersistCtas;
+        if (grid > tiles) grid = tiles;
         if (d.b_slot == nullptr)
-            k_linearize_bearing<S, true><<<tiles, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
+            k_linearize_bearing_persistent<S, true><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, d.bnd);
         else
-            k_linearize_bearing<S, false><<<tiles, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, dbg);
+            k_linearize_bearing_persistent<S, false><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, d.bnd);
         launches++;
     }
-    (void)sm_count;
+    k_pose_finish<S><<<(d.NP + 127) / 128, 128, 0, st>>>(d, r.b_begin, r.b_end, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here, d.bnd);
+    launches++;
     return launches;
 }
 
@@ -372,6 +481,7 @@ __global__ void __launch_bounds__(256) k_update(Dev<S> d) {
         o[1] = (sd * X.x + cd * X.y) + dy;
         o[2] = cd * X.c + (-sd) * X.s;
         o[3] = sd * X.c + cd * X.s;
+        d.theta[i] = pose_theta<S>(PoseV<S>{o[0], o[1], o[2], o[3]});
         m = fmax(fabs((double)dx), fmax(fabs((double)dy), fabs((double)dt)));
     } else if (i < d.NP + d.NL) {
         const int j = i - d.NP;
@@ -390,6 +500,17 @@ __global__ void __launch_bounds__(256) k_update(Dev<S> d) {
         atomicMax(reinterpret_cast<unsigned long long*>(d.stats + 4), (unsigned long long)__double_as_longlong(m));
     }
 }
+// theta cache after the poses were replaced from the host (bos_set_state)
+template <typename S>
+__global__ void __launch_bounds__(256) k_pose_theta(Dev<S> d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.NP) d.theta[i] = pose_theta<S>(load_pose<S>(d.pose, i));
+}
+template <typename S>
+int launch_pose_theta(const Dev<S>& d, cudaStream_t st) {
+    if (d.NP > 0) k_pose_theta<S><<<(d.NP + 255) / 256, 256, 0, st>>>(d);
+    return 1;
+}
 template <typename S>
 int launch_update(const Dev<S>& d, cudaStream_t st) {
     int n = d.NP + d.NL;
@@ -401,6 +522,8 @@ template int launch_linearize<double>(const Dev<double>&, const ShardRange&, dou
 template int launch_linearize<float>(const Dev<float>&, const ShardRange&, double, double, bool, bool, int, cudaStream_t);
 template int launch_edge_terms<double>(const Dev<double>&, double*, double*, double*, double*, cudaStream_t);
 template int launch_edge_terms<float>(const Dev<float>&, float*, float*, float*, float*, cudaStream_t);
+template int launch_pose_theta<double>(const Dev<double>&, cudaStream_t);
+template int launch_pose_theta<float>(const Dev<float>&, cudaStream_t);
 template int launch_update<double>(const Dev<double>&, cudaStream_t);
 template int launch_update<float>(const Dev<float>&, cudaStream_t);
 

@@ -386,3 +386,36 @@ def test_pcg_fused_kernel_equals_classic_loop(built_lib, uniform_omega):
     assert np.abs(ds[0] - ds[1]).max() <= 1e-8 * np.abs(ds[1]).max()
     assert np.all(ds[0][-4:] == 0.0)                                                     # unobserved landmarks: b_l = 0 -> dx_l = 0
     assert its[0] > 0 and abs(its[0] - its[1]) <= 0.2 * its[1] + 5
+
+
+def test_linearize_with_long_edge_free_pose_stretches_and_heavy_poses(built_lib):
+    """Tile bookkeeping of the bearing kernel: a stretch of > 512 poses without bearing edges inside one tile (the pose-range
+    table of the tile does not fit its shared-memory slot), and a pose with more than 512 edges (its run spans three tiles)."""
+    from prb_project_bearing_only_slam_b200.problem import Problem
+    rng = np.random.default_rng(9)
+    NP, NL = 1500, 700
+    pose_ids = np.arange(100, 100 + NP); lm_ids = np.arange(NL)
+    xyt = np.column_stack([np.arange(NP) * 0.5, rng.normal(size=NP) * 0.1, rng.normal(size=NP) * 0.05])
+    lms = np.column_stack([rng.uniform(0, NP * 0.5, NL), rng.uniform(2, 6, NL)])
+    bp, bl = [], []
+    for p in list(range(0, 40)) + list(range(700, 760)):            # poses 40..699 and 760.. have no bearing edges
+        for l in rng.choice(NL, 6, replace=False):
+            bp.append(p); bl.append(l)
+    for l in range(NL):                                             # pose 720 sees every landmark: a run of 700+ edges
+        bp.append(720); bl.append(l)
+    bp = np.array(bp); bl = np.array(bl)
+    th = xyt[bp, 2]
+    bz = np.arctan2(lms[bl, 1] - xyt[bp, 1], lms[bl, 0] - xyt[bp, 0]) - th + rng.normal(size=len(bp)) * 0.01
+    src = pose_ids[:-1]; dst = pose_ids[1:]
+    oz = np.column_stack([np.full(NP - 1, 0.5), np.zeros(NP - 1), np.zeros(NP - 1)]) + rng.normal(size=(NP - 1, 3)) * 0.01
+    oom = np.tile(np.diag([500.0, 500.0, 5000.0]).ravel(), (NP - 1, 1))
+    pr = Problem(pose_ids, pose_ids[bp], lm_ids[bl], bz, src, dst, oz, oom, fixed_pose_id=100, lm_ids=lm_ids)
+    o = oracle_for(pose_ids, xyt, pr, triangulate=False, lms=lms)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L)
+    o.linearize(); ctx.linearize()
+    colptr, rowidx, val, b = ctx.csc(); ocol, orow, oval, ob = o.csc()
+    assert np.array_equal(colptr, ocol) and np.array_equal(rowidx, orow)
+    assert csc_rel_err(colptr, val, oval) <= TOL64 and np.abs(b - ob).max() <= TOL64 * np.abs(ob).max()
+    st, os_ = ctx.stats(), o.stats()
+    assert st.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=TOL64)
