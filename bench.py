@@ -335,7 +335,7 @@ def main():
     ap.add_argument("--workload", default="synth-2M", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
-    ap.add_argument("--pcg-max-iters", type=int, default=5000)
+    ap.add_argument("--pcg-max-iters", type=int, default=20000)
     ap.add_argument("--reduce-mode", type=int, default=1)
     ap.add_argument("--ref-pcg-iters", type=int, default=0, help="CG iterations per GN step the reference arm extrapolates to "
                     "(0 = the count recorded by our arm in profiles/pcg_iterations.json, else 300)")

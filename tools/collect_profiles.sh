@@ -1,0 +1,16 @@
+#!/bin/bash
+# GPU box: the measurement pass of a round -- tests, bench (both arms), ncu launch list and full captures of the top kernels.
+# Everything lands in gpurun_out/; tools/summarize_profiles.py turns it into the committed files under profiles/.
+set -u
+R=${1:-r01}
+O=gpurun_out
+mkdir -p $O
+python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$R.log 2>&1; tail -3 $O/pytest_gpu_$R.log
+python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$R.json 2> $O/bench_ref_$R.err; tail -c 600 $O/bench_ref_$R.json
+python bench.py --steps 5 --warmup 3 > $O/bench_$R.json 2> $O/bench_$R.err; tail -c 400 $O/bench_$R.json; tail -3 $O/bench_$R.err
+# per-launch durations of the same command (cold-cache, serialised: only the kernels' SHARE of a step is comparable)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$R.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches_$R.log 2>&1
+# full captures of the two kernels the bench reports a roofline for, and of the pose kernel of the H, b build
+ncu --set full --import-source on --clock-control none -k k_pcg_fused -s 3 -c 1 -f -o $O/prof_pcg_$R python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_pcg_$R.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"k_linearize_bearing_persistent|k_pose_finish" -s 6 -c 2 -f -o $O/prof_lin_$R python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_lin_$R.log 2>&1
+ls -la $O | tail -12
