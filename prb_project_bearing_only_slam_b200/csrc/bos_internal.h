@@ -14,7 +14,10 @@ namespace bos {
 // are aggregated in shared memory through a host-precomputed tile-local grouping before they touch global memory
 constexpr int kLinTile = 512;
 // the fused PCG kernel reads the per-edge factors from two sliced-ELL layouts (see pattern.cpp)
-constexpr int kPcgThreads = 1024;                  // one persistent CTA per SM
+#ifndef BOS_PCG_THREADS
+#define BOS_PCG_THREADS 1024
+#endif
+constexpr int kPcgThreads = BOS_PCG_THREADS;       // one persistent CTA per SM
 #ifndef BOS_ELL_LANES
 #define BOS_ELL_LANES 8
 #endif

@@ -149,92 +149,106 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// trailing update: C[ti,tj] -= P[ti] P[tj]^T over the lower tiles of the trailing matrix, 64x64 per CTA.
-// P = panel columns k0..k0+kb.  128 threads = 4 warps in a 2x2 arrangement of 32x32 warp tiles.
+// trailing update: C[ti,tj] -= P[ti] P[tj]^T, 64x64 per CTA, P = the kt columns k0..k0+kt of the factor (kt a multiple of 64
+// except for the last panel), accumulated over 64-wide chunks of k.  Updated region: rows r0.., columns r0..r0+64*TC (TC =
+// number of column tiles; TC >= T means the whole lower triangle beyond r0), lower tiles only (ti >= tj).
+// 128 threads = 4 warps in a 2x2 arrangement of 32x32 warp tiles; FP64 on the tensor pipe (DMMA m8n8k4).
+// Two-level blocking: inside an outer panel of kOuter columns only the panel's own remaining columns are updated after each
+// 64-wide step (narrow region), the rest of the matrix once per outer panel with kt = kOuter: the trailing matrix is read
+// and written kOuter/64 times less often, which turns the update from HBM bound into tensor-pipe bound.
 template <typename S>
-__global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, int k0, int kb, int r0, int T) {
+__global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, int k0, int kt, int r0, int T, int TC) {
     extern __shared__ unsigned char smem_raw[];
     S* sA = reinterpret_cast<S*>(smem_raw);   // [NB k][LDT rows]
     S* sB = sA + NB * LDT;
-    // decode the lower-triangular tile index
-    const long long idx = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-    while ((long long)ti * (ti + 1) / 2 > idx) ti--;
-    while ((long long)(ti + 1) * (ti + 2) / 2 <= idx) ti++;
-    const int tj = (int)(idx - (long long)ti * (ti + 1) / 2);
-    (void)T;
-    const int ra = r0 + ti * NB, rb = r0 + tj * NB;
-    for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
-        const int k = t / NB, r = t % NB;
-        S va = S(0), vb = S(0);
-        if (k < kb) {
-            if (ra + r < n) va = Sm[(size_t)(ra + r) + (size_t)(k0 + k) * n];
-            if (rb + r < n) vb = Sm[(size_t)(rb + r) + (size_t)(k0 + k) * n];
-        }
-        sA[k * LDT + r] = va;
-        sB[k * LDT + r] = vb;
+    int ti, tj;
+    if (TC >= T) {   // triangular decode of a 1-D grid
+        const long long idx = blockIdx.x;
+        ti = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+        while ((long long)ti * (ti + 1) / 2 > idx) ti--;
+        while ((long long)(ti + 1) * (ti + 2) / 2 <= idx) ti++;
+        tj = (int)(idx - (long long)ti * (ti + 1) / 2);
+    } else {         // narrow region: grid (T, TC)
+        ti = blockIdx.x; tj = blockIdx.y;
+        if (ti < tj) return;
     }
-    __syncthreads();
+    const int ra = r0 + ti * NB, rb = r0 + tj * NB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
-    if constexpr (sizeof(S) == 8) {
-        double acc[4][4][2];
+    const int fr = lane >> 2, fk = lane & 3;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    double accd[4][4][2];
+    float accf[8][4];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-        const int fr = lane >> 2, fk = lane & 3;
-#pragma unroll 4
-        for (int kk = 0; kk < NB; kk += 4) {
-            double af[4], bf[4];
+        for (int c = 0; c < 4; c++) accd[a][c][0] = accd[a][c][1] = 0.0;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                af[t] = sA[(kk + fk) * LDT + wm + t * 8 + fr];
-                bf[t] = sB[(kk + fk) * LDT + wn + t * 8 + fr];
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) accf[a][c] = 0.f;
+    for (int kc = 0; kc < kt; kc += NB) {
+        const int kb = (kt - kc < NB) ? kt - kc : NB;
+        if (kc) __syncthreads();
+        for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
+            const int k = t / NB, r = t % NB;
+            S va = S(0), vb = S(0);
+            if (k < kb) {
+                if (ra + r < n) va = Sm[(size_t)(ra + r) + (size_t)(k0 + kc + k) * n];
+                if (rb + r < n) vb = Sm[(size_t)(rb + r) + (size_t)(k0 + kc + k) * n];
             }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            sA[k * LDT + r] = va;
+            sB[k * LDT + r] = vb;
         }
+        __syncthreads();
+        if constexpr (sizeof(S) == 8) {
+#pragma unroll 4
+            for (int kk = 0; kk < NB; kk += 4) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    af[t] = sA[(kk + fk) * LDT + wm + t * 8 + fr];
+                    bf[t] = sB[(kk + fk) * LDT + wn + t * 8 + fr];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) dmma_m8n8k4(accd[a][c][0], accd[a][c][1], af[a], bf[c]);
+            }
+        } else {
+            for (int k = 0; k < NB; k++) {
+                float av[8], bv[4];
+#pragma unroll
+                for (int a = 0; a < 8; a++) av[a] = sA[k * LDT + tx * 8 + a];
+#pragma unroll
+                for (int c = 0; c < 4; c++) bv[c] = sB[k * LDT + ty * 4 + c];
+#pragma unroll
+                for (int a = 0; a < 8; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) accf[a][c] += av[a] * bv[c];
+            }
+        }
+    }
+    if constexpr (sizeof(S) == 8) {
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
+            for (int c = 0; c < 4; c++) {
                 const int row = ra + wm + a * 8 + fr;
-                const int col = rb + wn + b * 8 + 2 * fk;
+                const int col = rb + wn + c * 8 + 2 * fk;
                 if (row < n) {
-                    if (col < n) Sm[(size_t)row + (size_t)col * n] -= acc[a][b][0];
-                    if (col + 1 < n) Sm[(size_t)row + (size_t)(col + 1) * n] -= acc[a][b][1];
+                    if (col < n) Sm[(size_t)row + (size_t)col * n] -= accd[a][c][0];
+                    if (col + 1 < n) Sm[(size_t)row + (size_t)(col + 1) * n] -= accd[a][c][1];
                 }
             }
     } else {
-        // FP32 path: scalar FMAs, 8x4 register tile per thread
-        const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-        float acc[8][4];
 #pragma unroll
         for (int a = 0; a < 8; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
-        for (int k = 0; k < NB; k++) {
-            float av[8], bv[4];
-#pragma unroll
-            for (int a = 0; a < 8; a++) av[a] = sA[k * LDT + tx * 8 + a];
-#pragma unroll
-            for (int b = 0; b < 4; b++) bv[b] = sB[k * LDT + ty * 4 + b];
-#pragma unroll
-            for (int a = 0; a < 8; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
-        }
-#pragma unroll
-        for (int a = 0; a < 8; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int row = ra + tx * 8 + a, col = rb + ty * 4 + b;
-                if (row < n && col < n) Sm[(size_t)row + (size_t)col * n] -= acc[a][b];
+            for (int c = 0; c < 4; c++) {
+                const int row = ra + tx * 8 + a, col = rb + ty * 4 + c;
+                if (row < n && col < n) Sm[(size_t)row + (size_t)col * n] -= accf[a][c];
             }
-        (void)lane; (void)wm; (void)wn;
     }
 }
 
@@ -325,15 +339,26 @@ int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStr
         cudaFuncSetAttribute(k_syrk_tiles<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(float)));
         attr_set = true;
     }
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        const int kb = (n - k0 < NB) ? n - k0 : NB;
-        k_potrf_diag<S><<<1, 256, 0, st>>>(w.Smat, n, k0, kb, d.stats); nl++;
-        const int r0 = k0 + kb;
-        if (r0 < n) {
-            k_trsm_panel<S><<<(n - r0 + 127) / 128, 128, 0, st>>>(w.Smat, n, k0, kb); nl++;
-            const int T = (n - r0 + NB - 1) / NB;
-            const long long tiles = (long long)T * (T + 1) / 2;
-            k_syrk_tiles<S><<<(unsigned)tiles, 128, smem, st>>>(w.Smat, n, k0, kb, r0, T); nl++;
+    constexpr int kOuter = 256;   // outer panel: the bulk of the matrix is updated once per kOuter columns
+    for (int c0 = 0; c0 < n; c0 += kOuter) {
+        const int cend = (c0 + kOuter < n) ? c0 + kOuter : n;
+        for (int k0 = c0; k0 < cend; k0 += NB) {
+            const int kb = (cend - k0 < NB) ? cend - k0 : NB;
+            k_potrf_diag<S><<<1, 256, 0, st>>>(w.Smat, n, k0, kb, d.stats); nl++;
+            const int r0 = k0 + kb;
+            if (r0 < n) {
+                k_trsm_panel<S><<<(n - r0 + 127) / 128, 128, 0, st>>>(w.Smat, n, k0, kb); nl++;
+                if (r0 < cend) {   // the outer panel's own remaining columns
+                    const int T = (n - r0 + NB - 1) / NB, TC = (cend - r0 + NB - 1) / NB;
+                    if (TC >= T) k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(w.Smat, n, k0, kb, r0, T, T);
+                    else k_syrk_tiles<S><<<dim3(T, TC), 128, smem, st>>>(w.Smat, n, k0, kb, r0, T, TC);
+                    nl++;
+                }
+            }
+        }
+        if (cend < n) {            // everything beyond the outer panel, once, with all of its columns
+            const int T = (n - cend + NB - 1) / NB;
+            k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(w.Smat, n, c0, cend - c0, cend, T, T); nl++;
         }
     }
     // forward substitution L y = g

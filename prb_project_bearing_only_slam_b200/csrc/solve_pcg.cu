@@ -249,6 +249,7 @@ __global__ void k_pcg_promote(double* scal) {
 //   phase P: owned poses: w_i = Hpp_ii z_i + yoff_i - sum_k Jp_k^T (jh_k.u_l(k)) is complete locally, so the vector
 //            updates, z' = M^-1 r and the next gamma / delta parts follow in the same thread.
 enum { FS_GAMMA0 = 16, FS_DELTA0 = 19 };
+constexpr int kPcgRows = (2048 + kPcgThreads - 1) / kPcgThreads;   // chunk rows per thread (a chunk has at most 2048 poses)
 constexpr int kPcgSmemBudget = 226 * 1024;   // dynamic shared memory available to the persistent kernel
 
 // -DBOS_PCG_TIMING: thread 0 of a few CTAs prints clock64 deltas per phase (diagnostic builds only)
@@ -268,11 +269,17 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks
     __syncthreads();
     epoch++;
     if (threadIdx.x == 0) {
+        const unsigned target = epoch * nblocks;
+#ifdef BOS_PCG_BARRIER_FENCE
         __threadfence();
         atomicAdd(counter, 1u);
-        const unsigned target = epoch * nblocks;
         while (ld_acquire_u32(counter) < target) { }
         __threadfence();
+#else
+        // release (cumulative over the CTA's writes ordered by the bar.sync above) / acquire pair, no separate fences
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        while (ld_acquire_u32(counter) < target) { }
+#endif
     }
     __syncthreads();
 }
@@ -490,9 +497,9 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     // ---- static per-thread data: this thread owns chunk rows tid and tid + 1024 for the whole solve ---------------------
     const int goff0 = __ldg(d.pc_goff + (size_t)c * gpc);
     const int cl0 = __ldg(d.pc_cl_ptr + c), ncl = __ldg(d.pc_cl_ptr + c + 1) - cl0;
-    int pose_i[2], soff[2], swid[2];
+    int pose_i[kPcgRows], soff[kPcgRows], swid[kPcgRows];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < kPcgRows; h++) {
         const int r = tid + h * kPcgThreads;
         pose_i[h] = (r < cp) ? __ldg(d.pc_row_pose + (size_t)c * cp + r) : -1;
         soff[h] = 0; swid[h] = 0;
@@ -508,7 +515,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
         const int nslots = (__ldg(d.pc_goff + (size_t)(c + 1) * gpc) - goff0) * 32;
         for (int k = tid; k < nslots; k += kPcgThreads) loc_s[k] = d.pc_loc[(size_t)goff0 * 32 + k];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < kPcgRows; h++) {
             const int r = tid + h * kPcgThreads;
             if (r < cp) {
 #pragma unroll
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             // ---- phase L: off-diagonal pose-pose products, t_l / u_l per landmark, delta parts ---------------------------------
             double dacc = 0.0;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < kPcgRows; h++) {
                 const int i = pose_i[h];
                 if (i < 0) continue;
                 const int r = tid + h * kPcgThreads;
@@ -609,10 +616,10 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             const S so_u = (S)w.sqrt_omega;
             double gacc = 0.0, dacc2 = 0.0;
             // loads by pose index first (independent of the staging), then the barrier, then the rows
-            PoseV<S> X[2];
-            S zz[2][3];
+            PoseV<S> X[kPcgRows];
+            S zz[kPcgRows][3];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < kPcgRows; h++) {
                 X[h] = PoseV<S>{S(0), S(0), S(1), S(0)};
                 zz[h][0] = zz[h][1] = zz[h][2] = S(0);
                 if (pose_i[h] >= 0) {
@@ -624,7 +631,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             __syncthreads();
             PCG_T(7);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < kPcgRows; h++) {
                 const int i = pose_i[h];
                 const int r = tid + h * kPcgThreads;
                 if (r >= cp) continue;                       // warp-uniform: cp is a multiple of 32
@@ -689,7 +696,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     // ---- epilogue: dx_p = x; x as padded records for the back-substitution gather; dx_l ----------------------------------
     S* x4 = w.z4 + (size_t)((it + 1) & 1) * np4;    // the z buffer that is not current
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < kPcgRows; h++) {
         const int i = pose_i[h];
         if (i < 0) continue;
         const S* xg = w.xS + (size_t)c * cp + tid + h * kPcgThreads;
@@ -718,7 +725,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
 // the persistent kernel needs the chunk's vectors, landmark records and slot indices in shared memory, at most two rows per thread
 template <typename S>
 bool pcg_fused_supported(const Dev<S>& d) {
-    if (!d.pc_ok || d.pc_cp > 2 * kPcgThreads || d.pc_chunks < 1) return false;
+    if (!d.pc_ok || d.pc_cp > kPcgRows * kPcgThreads || d.pc_chunks < 1) return false;
     const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max);
     return plan.bytes <= (size_t)kPcgSmemBudget;
 }
