@@ -178,7 +178,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
 
 
 def run_ours(args):
@@ -208,6 +208,8 @@ def run_ours(args):
     S = 8 if args.precision == "f64" else 4
     ctx = capi.Context(device=local, solver=solver, precision=prec, pcg_rtol=args.pcg_rtol, pcg_max_iters=args.pcg_max_iters)
     pr.upload(ctx)
+    if args.reduce_mode < 0:
+        args.reduce_mode = 2 if solver == capi.SOLVER_PCG else 1
     if world > 1:
         uid = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -253,11 +255,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- H, b build (+ NCCL combine) on its own, ranks aligned by a barrier before every build: inside a full step the
+    # combine's event time also contains the skew the replicated 0.3 s solves accumulate between ranks
+    lin_ms, red_ms = [], []
+    ctx.set_state(P0, L0)
+    for i in range((args.warmup + max(args.steps, 5)) if world > 1 else 0):
+        barrier()
+        ctx.linearize()
+        st_ = ctx.stats()
+        if i >= args.warmup:
+            lin_ms.append(st_.ms_linearize); red_ms.append(st_.ms_allreduce)
     elapsed = reduce_max(elapsed)
     e2e_elapsed = reduce_max(e2e_elapsed)
-    ms_lin = reduce_max(statistics.mean(s["ms_linearize"] + s["ms_allreduce"] for s in stats))
-    ms_lin_kernel = reduce_max(statistics.mean(s["ms_linearize"] for s in stats))
-    ms_allreduce = reduce_max(statistics.mean(s["ms_allreduce"] for s in stats))
+    if world == 1:   # single GPU: the build as timed inside the K timed steps
+        lin_ms = [s["ms_linearize"] for s in stats]; red_ms = [s["ms_allreduce"] for s in stats]
+    ms_lin_kernel = reduce_max(statistics.mean(lin_ms))
+    ms_allreduce = reduce_max(statistics.mean(red_ms))
+    ms_lin = reduce_max(statistics.mean(a + b for a, b in zip(lin_ms, red_ms)))
     ms_solve = reduce_max(statistics.mean(s["ms_solve"] for s in stats))
     ms_update = reduce_max(statistics.mean(s["ms_update"] for s in stats))
     if rank != 0:
@@ -288,7 +302,7 @@ def run_ours(args):
                     "ms_per_launch": ms_solve, "us_per_cg_iteration": 1e3 * ms_solve / pcg_iters,
                     "note": "ms_per_launch is the solve phase (4 setup kernels + the persistent kernel), CUDA events on the context's stream"}
     else:
-        roofline = {"kernel": "H,b build: k_pose_odometry_init + k_linearize_bearing", "bound": "hbm", "achieved": achieved, "peak": peak,
+        roofline = {"kernel": "H,b build: k_landmark_init + k_linearize_bearing_persistent + k_pose_finish", "bound": "hbm", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
                     "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel}
     line = {
@@ -298,14 +312,14 @@ def run_ours(args):
         "config": {"workload": args.workload, "poses": pr.NP, "landmarks": pr.NL, "bearing_edges": pr.Eb, "odometry_edges": pr.Eo,
                    "N": int(pi.N), "solver": "schur+block-jacobi-pcg" if solver == capi.SOLVER_PCG else "schur+dense-cholesky",
                    "pcg_rtol": args.pcg_rtol, "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
-                   (world, "allreduce(overlap)+allgather" if args.reduce_mode == 1 else "allreduce(full)") if world > 1 else "single gpu",
+                   (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)"}[args.reduce_mode]) if world > 1 else "single gpu",
                    "l2": "no flush: value + edge buffers (%.0f MB) exceed the 126 MB L2" % ((int(pi.vals_len) * S + pr.Eb * 24) / 1e6)},
         "edges_linearized_per_s": E / (ms_lin * 1e-3),
         "phases_ms": {"linearize": ms_lin_kernel, "allreduce": ms_allreduce, "solve": ms_solve, "update": ms_update},
         "pcg_iterations": pcg_iters,
         "chi2_last": stats[-1]["chi2_bearing"] + stats[-1]["chi2_odometry"],
         "roofline": roofline,
-        "roofline_linearize": {"kernel": "H,b build: k_pose_odometry_init + k_linearize_bearing", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline_linearize": {"kernel": "H,b build: k_landmark_init + k_linearize_bearing_persistent + k_pose_finish", "bound": "hbm", "achieved": achieved, "peak": peak,
                                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
                                "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel},
         "e2e": {"value": args.steps / e2e_elapsed, "unit": "iterations/s",
@@ -321,9 +335,18 @@ def run_ours(args):
             "sample": "CPU oracle (restatement; the reference needs Eigen3/OpenCV, absent here), 1 thread, full %s world: H,b build timed "
                       "in full (%.3f s), Schur-PCG timed for 2 and 12 CG iterations (%.4f s/iteration) and extrapolated to the %d "
                       "iterations this run needed" % (args.workload, cb["t_lin"], cb["t_cg_iter"], int(round(line["pcg_iterations"])))}
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, for one) write to file descriptor 1; the contract is ONE JSON line on stdout.  Route fd 1 to
+    stderr for the whole run and return a file object on the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -336,13 +359,14 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--pcg-max-iters", type=int, default=20000)
-    ap.add_argument("--reduce-mode", type=int, default=1)
+    ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 2 for the PCG workloads, 1 for the dense ones")
     ap.add_argument("--ref-pcg-iters", type=int, default=0, help="CG iterations per GN step the reference arm extrapolates to "
                     "(0 = the count recorded by our arm in profiles/pcg_iterations.json, else 300)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3)
+    args.out = _quiet_stdout()
     if args.impl == "reference":
         if args.ref_pcg_iters <= 0:
             p = os.path.join(ROOT, "profiles", "pcg_iterations.json")

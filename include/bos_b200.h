@@ -180,8 +180,10 @@ BOS_API int bos_host_edge_shard(int64_t Eb, int64_t Eo, int rank, int nranks, in
 #define BOS_NCCL_UID_BYTES 128
 BOS_API int bos_nccl_unique_id(char* uid128);
 BOS_API int bos_comm_init(bos_ctx* ctx, int rank, int nranks, const char* uid128);
-/* reduce_mode 0: allreduce the whole value buffer (H, b); 1: allreduce only the blocks that can overlap
- * between ranks (b, diagonal blocks, pose-pose blocks) and allgather the rank-owned pose-landmark blocks. */
+/* reduce_mode 0: allreduce the whole value buffer (H, b); 1: allreduce only the blocks that can overlap between ranks
+ * (b, diagonal blocks, pose-pose blocks) and allgather the rank-owned pose-landmark blocks; 2: allreduce those blocks only and
+ * leave the pose-landmark blocks rank-local -- enough for the fused PCG solve, which applies that part of the operator from
+ * per-edge factors (bos_download_blocks / bos_download_csc then see this rank's pose-landmark blocks only). */
 BOS_API int bos_set_reduce_mode(bos_ctx* ctx, int reduce_mode);
 /* Without NCCL: shard bookkeeping only (used by the host-side tests): this rank linearizes its
  * contiguous range of the pose-sorted edges. */

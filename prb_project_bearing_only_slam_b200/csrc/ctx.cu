@@ -329,7 +329,11 @@ int allreduce_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const int dt = sizeof(S) == 8 ? kNcclFloat64 : kNcclFloat32;
     int rc;
-    if (c->reduce_mode == 1 && c->P.slots_identity && c->nranks <= 8) {
+    if (c->reduce_mode == 2 && c->P.slots_identity) {
+        // b, diagonal blocks and pose-pose blocks only: all the fused PCG solve reads (it applies the pose-landmark part of the
+        // operator from per-edge factors); the pose-landmark planes stay rank-local
+        rc = n.AllReduce(d.vals, d.vals, c->vals_prefix, dt, kNcclSum, c->comm, c->stream);
+    } else if (c->reduce_mode == 1 && c->P.slots_identity && c->nranks <= 8) {
         rc = n.AllReduce(d.vals, d.vals, c->vals_prefix, dt, kNcclSum, c->comm, c->stream);
         const size_t cnt = (size_t)c->shard_chunk_b;   // rank shards of every plane are equally sized (padded)
         for (int k = 0; k < 6 && rc == 0; k++) {
@@ -348,7 +352,7 @@ template <typename S>
 int linearize_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const bool multi = c->nranks > 1;
-    const bool zero_hpl = !c->P.slots_identity || (multi && !(c->reduce_mode == 1 && c->P.slots_identity && c->nranks <= 8));
+    const bool zero_hpl = !c->P.slots_identity || (multi && !((c->reduce_mode == 2 || (c->reduce_mode == 1 && c->nranks <= 8)) && c->P.slots_identity));
     const bool zero_hoff = multi || c->P.has_shared_off;
     const double damp_here = (c->rank == 0) ? c->opt.damping : 0.0;
     c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream);
@@ -362,6 +366,8 @@ int solve_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const int which = pick_solver(c);
     c->solver_used = which;
+    if (c->nranks > 1 && c->reduce_mode == 2 && c->P.slots_identity && !(which == BOS_SOLVER_PCG && c->opt.pcg_variant == 0))
+        return fail(c, BOS_ERR_STATE, "reduce_mode 2 leaves the pose-landmark blocks rank-local: only the fused PCG solve (pcg_variant 0) can follow");
     int nl = 0, rc = 0;
     if (which == BOS_SOLVER_DENSE_CHOLESKY) {
         int e = ensure_dense<S>(c);
@@ -645,10 +651,17 @@ int bos_linearize(bos_ctx* c) {
     if (!c) return BOS_ERR_INVALID;
     NEED(c, c->have_problem, "linearize before upload_problem");
     CUDA_OK(c, cudaSetDevice(c->opt.device));
+    c->launches = 0;
+    cudaEventRecord(c->ev[0], c->stream);
     int rc = DISPATCH(c, linearize_impl, c);
     if (rc) return rc;
+    cudaEventRecord(c->ev[1], c->stream);
     if ((rc = DISPATCH(c, allreduce_impl, c))) return rc;
+    cudaEventRecord(c->ev[2], c->stream);
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->stats.ms_linearize, c->ev[0], c->ev[1]);   // readable through bos_get_stats
+    cudaEventElapsedTime(&c->stats.ms_allreduce, c->ev[1], c->ev[2]);
+    c->stats.gpu_launches = c->launches;
     return BOS_OK;
 }
 
@@ -870,7 +883,7 @@ int bos_comm_init(bos_ctx* c, int rank, int nranks, const char* uid128) {
 }
 
 int bos_set_reduce_mode(bos_ctx* c, int mode) {
-    if (!c || (mode != 0 && mode != 1)) return BOS_ERR_INVALID;
+    if (!c || mode < 0 || mode > 2) return BOS_ERR_INVALID;
     c->reduce_mode = mode;
     return BOS_OK;
 }
