@@ -56,7 +56,7 @@ typedef struct bos_options {
     int dense_max_dim;        /* default 36000 */
     double kernel_threshold;  /* slam/solver.cpp:16  default 1.0  */
     double damping;           /* slam/solver.cpp:17  default 0.01 */
-    int pcg_max_iters;        /* default 5000 */
+    int pcg_max_iters;        /* default 20000 (block-Jacobi needs ~5300 CG iterations on a 200k-pose odometry chain) */
     double pcg_rtol;          /* stop when sqrt(r^T M^-1 r) <= rtol * its initial value; default 1e-10 */
     int pcg_variant;          /* 0 = one persistent cooperative kernel for the whole PCG solve (default; falls back to 1 when a
                                  landmark has more than 1024 observations), 1 = classic loop of small kernels */
@@ -121,6 +121,13 @@ BOS_API int bos_step(bos_ctx* ctx, bos_stats* stats);
  * callers read solver.state after every step, executables/bearing_only_slam.cpp:31-36). */
 BOS_API int bos_step_host(bos_ctx* ctx, double* poses_xycs_inout, double* lms_xy_inout, bos_stats* stats);
 BOS_API int bos_get_stats(bos_ctx* ctx, bos_stats* stats);
+
+/* Extension beyond the reference (the reference has a FIXED damping and never rejects a step, slam/solver.cpp:64-69):
+ * one Levenberg-Marquardt iteration.  Takes a GN step with the current damping, relinearizes, and compares the total chi2
+ * (chi2_bearing + chi2_odometry, the pre-kernel error_omeganorm sums) before and after: if it did not decrease the state is
+ * restored and the damping multiplied by 10, otherwise the step is kept and the damping divided by 3 (clamped to [1e-9, 1e9]).
+ * stats describes the GN step taken; chi2_after / accepted / damping_next may be NULL.  Opt-in: bos_step never does this. */
+BOS_API int bos_step_lm(bos_ctx* ctx, bos_stats* stats, double* chi2_after, int* accepted, double* damping_next);
 
 /* triangulate_landmarks (slam/triangulation.cpp:5-74) on the uploaded bearing edges and the current
  * poses; writes all NL landmarks of the device state.  single_obs_count (may be NULL) receives the

@@ -55,7 +55,7 @@ SYMBOLS = [
     "bos_set_edge_shard", "bos_get_edge_shard", "bos_batch_create", "bos_batch_destroy", "bos_batch_set_states",
     "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error", "bos_synth_default_spec",
     "bos_synth_create", "bos_synth_destroy", "bos_synth_counts", "bos_synth_get",
-    "bos_triangulate_landmarks", "bos_eval_bearing_edges", "bos_eval_odometry_edges",
+    "bos_triangulate_landmarks", "bos_eval_bearing_edges", "bos_eval_odometry_edges", "bos_step_lm",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def lib():
         L.bos_step.argtypes = [vp, C.POINTER(Stats)]
         L.bos_step_host.argtypes = [vp, vp, vp, C.POINTER(Stats)]
         L.bos_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.bos_step_lm.argtypes = [vp, C.POINTER(Stats), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.bos_triangulate.argtypes = [vp, C.POINTER(C.c_int)]
         L.bos_pattern_info_get.argtypes = [vp, C.POINTER(PatternInfo)]
         L.bos_download_pattern.argtypes = [vp] + [vp] * 6
@@ -208,6 +209,12 @@ class Context:
         s = Stats()
         self._ck(self.L.bos_step(self.h, C.byref(s)))
         return s
+
+    def step_lm(self):
+        """Opt-in Levenberg-Marquardt iteration (extension): returns (stats of the GN step taken, chi2 after, accepted, next damping)."""
+        s = Stats(); after = C.c_double(0); ok = C.c_int(0); damp = C.c_double(0)
+        self._ck(self.L.bos_step_lm(self.h, C.byref(s), C.byref(after), C.byref(ok), C.byref(damp)))
+        return s, after.value, bool(ok.value), damp.value
 
     def step_host(self, poses_xycs, lms_xy):
         """poses/lms must be C-contiguous float64 arrays; updated in place."""

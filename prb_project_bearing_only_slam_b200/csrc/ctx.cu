@@ -106,6 +106,8 @@ struct bos_ctx {
     int launches = 0;
     bool pcg_bad = false;
     std::vector<double> b_omega_sorted;   // bearing omegas in sorted-edge order (host copy for the PCG setup)
+    void* lm_pose_bak = nullptr;          // state backup of bos_step_lm
+    void* lm_lm_bak = nullptr;
 
     bool f64() const { return opt.precision == BOS_PRECISION_F64; }
 };
@@ -436,6 +438,43 @@ int step_impl(bos_ctx* c) {
 }
 
 template <typename S>
+int step_lm_impl(bos_ctx* c, double* chi2_after, int* accepted, double* damping_next) {
+    Dev<S>& d = dev<S>(c);
+    const size_t pb = 4 * (size_t)d.NP * sizeof(S), lb = 2 * (size_t)std::max(d.NL, 1) * sizeof(S);
+    if (!c->lm_pose_bak) {
+        c->lm_pose_bak = c->mem.get<unsigned char>(pb);
+        c->lm_lm_bak = c->mem.get<unsigned char>(lb);
+        if (!c->lm_pose_bak || !c->lm_lm_bak) return fail(c, BOS_ERR_NOMEM, "LM backup allocation failed");
+    }
+    CUDA_OK(c, cudaMemcpyAsync(c->lm_pose_bak, d.pose, pb, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->lm_lm_bak, d.lm, lb, cudaMemcpyDeviceToDevice, c->stream));
+    int rc = step_impl<S>(c);                       // chi2 of the state BEFORE the update is in c->stats
+    if (rc) return rc;
+    const bos_stats taken = c->stats;
+    const double before = taken.chi2_bearing + taken.chi2_odometry;
+    if ((rc = linearize_impl<S>(c))) return rc;     // chi2 at the new state
+    if ((rc = allreduce_impl<S>(c))) return rc;
+    if ((rc = fetch_stats<S>(c))) return rc;
+    const double after = c->stats.chi2_bearing + c->stats.chi2_odometry;
+    const bool ok = after < before;
+    if (!ok) {
+        CUDA_OK(c, cudaMemcpyAsync(d.pose, c->lm_pose_bak, pb, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_OK(c, cudaMemcpyAsync(d.lm, c->lm_lm_bak, lb, cudaMemcpyDeviceToDevice, c->stream));
+        launch_pose_theta<S>(d, c->stream);
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        c->linearized = false;
+        c->opt.damping = std::min(c->opt.damping * 10.0, 1e9);
+    } else {
+        c->opt.damping = std::max(c->opt.damping / 3.0, 1e-9);
+    }
+    c->stats = taken;
+    if (chi2_after) *chi2_after = after;
+    if (accepted) *accepted = ok ? 1 : 0;
+    if (damping_next) *damping_next = c->opt.damping;
+    return BOS_OK;
+}
+
+template <typename S>
 int set_state_impl(bos_ctx* c, const double* poses, const double* lms) {
     Dev<S>& d = dev<S>(c);
     if (poses) {
@@ -554,7 +593,7 @@ void bos_default_options(bos_options* o) {
     o->dense_max_dim = 36000;
     o->kernel_threshold = 1.0;
     o->damping = 0.01f;  // the reference's float literal, widened (slam/solver.cpp:17)
-    o->pcg_max_iters = 5000;
+    o->pcg_max_iters = 20000;
     o->pcg_rtol = 1e-10;
 }
 
@@ -614,6 +653,7 @@ int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t 
         return fail(c, BOS_ERR_INVALID, "null edge array");
     CUDA_OK(c, cudaSetDevice(c->opt.device));
     c->have_problem = false; c->dense_ready = false; c->pcg_ready = false;
+    c->lm_pose_bak = nullptr; c->lm_lm_bak = nullptr;
     c->mem.release();
     if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count) != 0)
         return fail(c, BOS_ERR_INVALID, c->P.error);
@@ -703,6 +743,16 @@ int bos_step_host(bos_ctx* c, double* poses, double* lms, bos_stats* stats) {
     if (rc) return rc;
     if ((rc = DISPATCH(c, step_impl, c))) return rc;
     if ((rc = bos_get_state(c, poses, lms))) return rc;
+    if (stats) *stats = c->stats;
+    return BOS_OK;
+}
+
+int bos_step_lm(bos_ctx* c, bos_stats* stats, double* chi2_after, int* accepted, double* damping_next) {
+    if (!c) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "step before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    int rc = DISPATCH(c, step_lm_impl, c, chi2_after, accepted, damping_next);
+    if (rc) return rc;
     if (stats) *stats = c->stats;
     return BOS_OK;
 }

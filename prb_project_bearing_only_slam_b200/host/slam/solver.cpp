@@ -121,6 +121,14 @@ void Solver::step(int iterations, bool mirror_every_step) {
     }
 }
 
+bool Solver::step_lm() {
+    if (!device_state_valid_ || state.version() != synced_version_) upload_state();
+    int accepted = 0;
+    check(bos_step_lm(ctx_, &stats_, nullptr, &accepted, nullptr), "bos_step_lm");
+    download_state();
+    return accepted != 0;
+}
+
 // ---- per-edge API ---------------------------------------------------------------------------------------------------------
 void Solver::error_and_jacobian(const State& st, const BearingObservation& obs, float& error, SparseMatrixXf& jacobian) {
     const int N = 3 * st.number_of_poses() + 2 * st.number_of_landmarks();

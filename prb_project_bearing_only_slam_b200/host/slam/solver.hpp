@@ -16,7 +16,7 @@ struct SolverOptions {
     bool fp32 = false;                 // false: FP64 arithmetic (parity path); true: the reference's own precision
     int solver = BOS_SOLVER_AUTO;      // Schur + dense Cholesky for small problems, Schur + block-Jacobi PCG for large ones
     int dense_max_dim = 36000;
-    int pcg_max_iters = 5000;
+    int pcg_max_iters = 20000;
     double pcg_rtol = 1e-10;
 };
 
@@ -56,6 +56,9 @@ class Solver {
 
     // ---- extensions -------------------------------------------------------------------------------------------------
     void step(int iterations, bool mirror_every_step = false);   // several iterations with the state resident on the device
+    // opt-in Levenberg-Marquardt iteration (not in the reference: fixed damping, no step rejection): a GN step that is undone,
+    // with the damping raised, when the total chi2 does not decrease; returns whether the step was kept
+    bool step_lm();
     const bos_stats& last_stats() const { return stats_; }       // chi2 (pre-kernel error_omeganorm sums), |dx|_inf, timings
     bool last_step_not_spd() const { return stats_.solver_status != 0; }
     bos_ctx* context() { return ctx_; }

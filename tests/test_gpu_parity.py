@@ -419,3 +419,42 @@ def test_linearize_with_long_edge_free_pose_stretches_and_heavy_poses(built_lib)
     assert csc_rel_err(colptr, val, oval) <= TOL64 and np.abs(b - ob).max() <= TOL64 * np.abs(ob).max()
     st, os_ = ctx.stats(), o.stats()
     assert st.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=TOL64)
+
+
+def test_levenberg_marquardt_extension_never_increases_chi2(built_lib):
+    """Opt-in LM iteration (the reference has a fixed damping): accepted steps lower the total chi2, rejected steps
+    restore the state and raise the damping; from the triangulated start of the full dataset it ends at or below plain GN."""
+    g = load_golden("full")
+    pr = golden_problem(g)
+    ctx = capi.Context()
+    pr.upload(ctx)
+    ctx.set_state(g["poses_xycs"], None)
+    ctx.triangulate()
+    P0, L0 = ctx.get_state()
+    cur = None
+    rejected = 0
+    for it in range(25):
+        before_state = ctx.get_state()
+        s, after, ok, damp = ctx.step_lm()
+        before = s.chi2_bearing + s.chi2_odometry
+        if cur is not None:
+            assert before == pytest.approx(cur, rel=1e-9)
+        if ok:
+            assert after < before
+            cur = after
+        else:
+            rejected += 1
+            P, L = ctx.get_state()
+            assert np.array_equal(P, before_state[0]) and np.array_equal(L, before_state[1])
+            cur = before
+        assert 1e-9 <= damp <= 1e9
+    ctx.set_state(P0, L0)
+    ctx.set_damping_factor(float(np.float32(0.01)))
+    for it in range(25):
+        s = ctx.step()
+    assert cur <= (s.chi2_bearing + s.chi2_odometry) * 1.05
+    # a step that must be rejected: an absurdly small damping on a state far from the optimum is still handled (no crash, state kept or improved)
+    ctx.set_state(P0, L0)
+    ctx.set_damping_factor(1e-9)
+    s, after, ok, damp = ctx.step_lm()
+    assert (ok and after < s.chi2_bearing + s.chi2_odometry) or (not ok and damp == pytest.approx(1e-8))
