@@ -252,6 +252,90 @@ __global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, i
     }
 }
 
+// The bulk trailing update (once per outer panel, kt = kOuter): 128 x 64 tiles, 256 threads = 8 warps (4 x 2) of 32 x 32
+// DMMA warp tiles, k in chunks of 32 through a 2-stage cp.async pipeline (the next chunk streams into shared memory while the
+// tensor pipe works on the current one).  Rows [r0, n) x columns [r0, n), lower part only: tile (ti, tj) is needed when
+// 128 ti + 127 >= 64 tj; entries above the diagonal of a straddling tile are computed but not stored.
+constexpr int KC = 32;           // k chunk
+constexpr int LDA2 = 128 + 4;    // == 4 (mod 16) doubles: conflict-free fragment loads
+constexpr int LDB2 = 64 + 4;
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 8 : 0;   // src-size 0: zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__global__ void __launch_bounds__(256, 2) k_syrk_big(double* __restrict__ Sm, int n, int k0, int kt, int r0) {
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    if (tj > 2 * ti + 1) return;
+    extern __shared__ unsigned char smem_raw[];
+    double* sbuf = reinterpret_cast<double*>(smem_raw);
+    constexpr int kStage = KC * LDA2 + KC * LDB2;
+    const int ra = r0 + ti * 128, rb = r0 + tj * 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    auto load_stage = [&](int stg, int kc) {
+        double* sA = sbuf + stg * kStage;
+        double* sB = sA + KC * LDA2;
+#pragma unroll
+        for (int j = 0; j < KC * 128 / 256; j++) {
+            const int idx = tid + 256 * j, r = idx & 127, k = idx >> 7;
+            const bool ok = (ra + r < n) && (kc + k < kt);
+            cp_async8(sA + k * LDA2 + r, Sm + (ok ? (size_t)(ra + r) + (size_t)(k0 + kc + k) * n : 0), ok);
+        }
+#pragma unroll
+        for (int j = 0; j < KC * 64 / 256; j++) {
+            const int idx = tid + 256 * j, r = idx & 63, k = idx >> 6;
+            const bool ok = (rb + r < n) && (kc + k < kt);
+            cp_async8(sB + k * LDB2 + r, Sm + (ok ? (size_t)(rb + r) + (size_t)(k0 + kc + k) * n : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[a][c][0] = acc[a][c][1] = 0.0;
+    const int nch = (kt + KC - 1) / KC;
+    load_stage(0, 0);
+    for (int ch = 0; ch < nch; ch++) {
+        if (ch + 1 < nch) {
+            load_stage((ch + 1) & 1, (ch + 1) * KC);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* sA = sbuf + (ch & 1) * kStage;
+        const double* sB = sA + KC * LDA2;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                af[t] = sA[(kk + fk) * LDA2 + wm + t * 8 + fr];
+                bf[t] = sB[(kk + fk) * LDB2 + wn + t * 8 + fr];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) dmma_m8n8k4(acc[a][c][0], acc[a][c][1], af[a], bf[c]);
+        }
+        __syncthreads();   // the stage is refilled two iterations later
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int row = ra + wm + a * 8 + fr;
+            const int col = rb + wn + c * 8 + 2 * fk;
+            if (row < n) {
+                if (col < n && row >= col) Sm[(size_t)row + (size_t)col * n] -= acc[a][c][0];
+                if (col + 1 < n && row >= col + 1) Sm[(size_t)row + (size_t)(col + 1) * n] -= acc[a][c][1];
+            }
+        }
+}
+
 // ---- triangular solves with the factor ------------------------------------------------------------------
 // forward, diagonal block: y_k = L_kk^-1 g_k   (one CTA of NB threads)
 template <typename S>
@@ -358,7 +442,15 @@ int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStr
         }
         if (cend < n) {            // everything beyond the outer panel, once, with all of its columns
             const int T = (n - cend + NB - 1) / NB;
-            k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(w.Smat, n, c0, cend - c0, cend, T, T); nl++;
+            if constexpr (sizeof(S) == 8) {
+                constexpr size_t smem_big = 2 * (size_t)(KC * LDA2 + KC * LDB2) * sizeof(double);
+                static bool big_attr = false;
+                if (!big_attr) { cudaFuncSetAttribute(k_syrk_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big); big_attr = true; }
+                k_syrk_big<<<dim3((n - cend + 127) / 128, T), 256, smem_big, st>>>(w.Smat, n, c0, cend - c0, cend);
+            } else {
+                k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(w.Smat, n, c0, cend - c0, cend, T, T);
+            }
+            nl++;
         }
     }
     // forward substitution L y = g
