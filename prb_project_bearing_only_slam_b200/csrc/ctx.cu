@@ -189,6 +189,15 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     if (!P.slots_identity) { UP(b_slot, bslot) }
     UP(o_src, P.o_src) UP(o_dst, P.o_dst) UP(o_z, oz) UP(o_om, oom) UP(o_slot, P.o_slot)
     UP(oe_ptr, P.oe_ptr) UP(oe_edge, P.oe_edge) UP(oe_other, P.oe_other) UP(o_shared, P.o_shared)
+    {
+        std::vector<int> oe2(4 * (size_t)P.NP, -1);
+        for (int i = 0; i < P.NP; i++)
+            for (int k = 0; k < 2 && P.oe_ptr[i] + k < P.oe_ptr[i + 1]; k++) {
+                oe2[4 * (size_t)i + 2 * k] = P.oe_edge[P.oe_ptr[i] + k];
+                oe2[4 * (size_t)i + 2 * k + 1] = P.oe_other[P.oe_ptr[i] + k];
+            }
+        UP(oe2, oe2)
+    }
     UP(slot_pose, P.slot_pose) UP(slot_lm, P.slot_lm) UP(pose_ptr, P.pose_ptr) UP(lm_ptr, P.lm_ptr)
     UP(lm_order, P.lm_order) UP(lm_order_pose, P.lm_order_pose) UP(lm_order_lm, P.lm_order_lm)
     UP(pp_ptr, P.pp_ptr) UP(pp_nbr, P.pp_nbr) UP(pp_slot, P.pp_slot) UP(off_lo, P.off_lo) UP(off_hi, P.off_hi)

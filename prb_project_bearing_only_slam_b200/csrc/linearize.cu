@@ -116,27 +116,38 @@ __global__ void __launch_bounds__(128, 4) k_pose_finish(Dev<S> d, int e_begin, i
         }
         const size_t Eo = (size_t)d.Eo;
         const PoseV<S> Xi = load_pose<S>(d.pose, i);
-        const int q0 = __ldg(d.oe_ptr + i), q1 = __ldg(d.oe_ptr + i + 1);
-        for (int q = q0; q < q1; q++) {
-            const int code = __ldg(d.oe_edge + q);
-            const int other = __ldg(d.oe_other + q);
-            const int e = code >> 1, role = code & 1;
-            if (e < o_begin || e >= o_end) continue;
-            const PoseV<S> Xo = load_pose<S>(d.pose, other);
-            const int s = role ? other : i, t = role ? i : other;
-            const PoseV<S> Xs = role ? Xo : Xi, Xd = role ? Xi : Xo;
-            S om[6];
+        const S thi = __ldg(d.theta + i);
+        // everything an incident odometry edge needs, loaded up front so that the loads of several edges are in flight together
+        struct EdgeIn { int e, role, other, slot; bool live, shared; PoseV<S> Xo; S tho, om[6], z[3]; };
+        auto load_edge = [&](int code, int other) {
+            EdgeIn in;
+            in.e = code >> 1; in.role = code & 1; in.other = other;
+            in.live = code >= 0 && in.e >= o_begin && in.e < o_end;
+            if (in.live) {
+                in.Xo = load_pose<S>(d.pose, other);
+                in.tho = __ldg(d.theta + other);
 #pragma unroll
-            for (int k = 0; k < 6; k++) om[k] = __ldg(d.o_om + k * Eo + e);
+                for (int k = 0; k < 6; k++) in.om[k] = __ldg(d.o_om + k * Eo + in.e);
+#pragma unroll
+                for (int k = 0; k < 3; k++) in.z[k] = __ldg(d.o_z + k * Eo + in.e);
+                in.slot = __ldg(d.o_slot + in.e);
+                in.shared = d.o_shared[in.e] != 0;
+            }
+            return in;
+        };
+        auto apply_edge = [&](const EdgeIn& in) {
+            if (!in.live) return;
+            const int other = in.other, role = in.role;
+            const int s = role ? other : i, t = role ? i : other;
+            const PoseV<S> Xs = role ? in.Xo : Xi, Xd = role ? Xi : in.Xo;
             S err[3], u0, u1;
-            const S thi = __ldg(d.theta + i), tho = __ldg(d.theta + other);
-            odometry_terms<S>(Xs, Xd, role ? tho : thi, role ? thi : tho, __ldg(d.o_z + e), __ldg(d.o_z + Eo + e), __ldg(d.o_z + 2 * Eo + e), err, u0, u1);
-            const S chi = odometry_chi<S>(om, err);
+            odometry_terms<S>(Xs, Xd, role ? in.tho : thi, role ? thi : in.tho, in.z[0], in.z[1], in.z[2], err, u0, u1);
+            const S chi = odometry_chi<S>(in.om, err);
             S scale = S(1);
             const bool over = chi > kernel_threshold;
             if (over) scale = sqrt(kernel_threshold / chi);   // scales the ERROR only (slam/solver.cpp:54-58)
             S M[6], v[3];
-            odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, om, err, M, v, scale);
+            odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, in.om, err, M, v, scale);
             const bool fs = (s == d.fixed), ft = (t == d.fixed);
             if (role == 0) {
                 chi_acc += (double)chi;
@@ -147,10 +158,10 @@ __global__ void __launch_bounds__(128, 4) k_pose_finish(Dev<S> d, int e_begin, i
                     b[0] += v[0]; b[1] += v[1]; b[2] += v[2];
                 }
                 // H[lo][hi] += J_lo^T Omega J_hi = -M (M symmetric, so the orientation does not matter)
-                S* ho = d.Hoff + 9LL * __ldg(d.o_slot + e);
+                S* ho = d.Hoff + 9LL * in.slot;
                 const S z = (fs || ft) ? S(0) : S(1);
                 const S m9[9] = {-M[0] * z, -M[1] * z, -M[2] * z, -M[1] * z, -M[3] * z, -M[4] * z, -M[2] * z, -M[4] * z, -M[5] * z};
-                if (d.o_shared[e]) {
+                if (in.shared) {
 #pragma unroll
                     for (int k = 0; k < 9; k++) red_add(ho + k, m9[k]);
                 } else {
@@ -161,6 +172,16 @@ __global__ void __launch_bounds__(128, 4) k_pose_finish(Dev<S> d, int e_begin, i
 #pragma unroll
                 for (int k = 0; k < 6; k++) h[k] += M[k];
                 b[0] -= v[0]; b[1] -= v[1]; b[2] -= v[2];
+            }
+        };
+        {
+            const int4 m2 = __ldg(reinterpret_cast<const int4*>(d.oe2) + i);   // the first two incident edges inline (odometry chains)
+            const EdgeIn e0 = load_edge(m2.x, m2.y), e1 = load_edge(m2.z, m2.w);
+            apply_edge(e0);
+            apply_edge(e1);
+            if (m2.z >= 0) {   // more than two incident edges (loop closures): the rest through the CSR list
+                const int q0 = __ldg(d.oe_ptr + i), q1 = __ldg(d.oe_ptr + i + 1);
+                for (int q = q0 + 2; q < q1; q++) apply_edge(load_edge(__ldg(d.oe_edge + q), __ldg(d.oe_other + q)));
             }
         }
         S* hp = d.Hpp + 6LL * i;
