@@ -222,12 +222,14 @@ struct HostPattern {
     std::vector<unsigned short> tg_edge;
     std::vector<char> touched;              // [NP + NL]
     // scalar CSC pattern of H_nofixed (slam/solver.cpp:72-75)
+    bool csc_built = false;
     std::vector<int> csc_colptr, csc_rowidx;
     // where each CSC entry comes from: source kind (0 Hpp,1 Hll,2 Hoff,3 Hpl), flat index into the EXPANDED block arrays
     std::vector<int> csc_src_kind;
     std::vector<int64_t> csc_src_index;
     std::string error;
 };
+void build_csc(HostPattern& P);
 int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm,
                   int64_t Eo, const int32_t* o_src, const int32_t* o_dst, int pcg_chunks = 148);
 

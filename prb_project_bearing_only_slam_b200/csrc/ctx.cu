@@ -788,6 +788,7 @@ int bos_pattern_info_get(bos_ctx* c, bos_pattern_info* out) {
     NEED(c, c->have_problem, "pattern before upload_problem");
     out->n_hpl = (int64_t)c->P.slot_pose.size();
     out->n_hpp_off = (int64_t)c->P.off_lo.size();
+    build_csc(c->P);
     out->csc_n = c->P.N - 3;
     out->csc_nnz = (int64_t)c->P.csc_rowidx.size();
     out->N = c->P.N;
@@ -820,6 +821,7 @@ int bos_download_blocks(bos_ctx* c, double* Hpp, double* Hll, double* Hpl, doubl
 int bos_download_csc(bos_ctx* c, int32_t* colptr, int32_t* rowidx, double* val, double* b_nofixed) {
     if (!c) return BOS_ERR_INVALID;
     NEED(c, c->have_problem, "download_csc before upload_problem");
+    build_csc(c->P);
     const HostPattern& P = c->P;
     if (colptr) std::copy(P.csc_colptr.begin(), P.csc_colptr.end(), colptr);
     if (rowidx) std::copy(P.csc_rowidx.begin(), P.csc_rowidx.end(), rowidx);
@@ -988,6 +990,7 @@ int bos_host_pattern_destroy(bos_host_pattern* p) {
 }
 int bos_host_pattern_info(const bos_host_pattern* p, bos_pattern_info* out) {
     if (!p || !out) return BOS_ERR_INVALID;
+    build_csc(const_cast<HostPattern&>(p->P));
     const HostPattern& P = p->P;
     out->n_hpl = (int64_t)P.slot_pose.size();
     out->n_hpp_off = (int64_t)P.off_lo.size();
@@ -1000,6 +1003,7 @@ int bos_host_pattern_info(const bos_host_pattern* p, bos_pattern_info* out) {
 int bos_host_pattern_get(const bos_host_pattern* p, int32_t* hpl_pose, int32_t* hpl_lm, int32_t* off_lo, int32_t* off_hi,
                          int64_t* b_slot, int64_t* o_slot, int32_t* csc_colptr, int32_t* csc_rowidx) {
     if (!p) return BOS_ERR_INVALID;
+    build_csc(const_cast<HostPattern&>(p->P));
     const HostPattern& P = p->P;
     if (hpl_pose) std::copy(P.slot_pose.begin(), P.slot_pose.end(), hpl_pose);
     if (hpl_lm) std::copy(P.slot_lm.begin(), P.slot_lm.end(), hpl_lm);

@@ -246,7 +246,15 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         for (int k = 0; k < 2 && q0 + k < q1; k++) { P.pc_nbr[k * nrows + R] = P.pp_nbr[q0 + k]; P.pc_nslot[k * nrows + R] = P.pp_slot[q0 + k]; }
     }
 
-    // ---- scalar CSC pattern of H_nofixed with the source of every entry ------------------------------------
+    P.csc_built = false;   // the scalar CSC view is only needed for inspection / parity downloads: built on demand (build_csc)
+    return 0;
+}
+
+// Scalar CSC pattern of H_nofixed (slam/solver.cpp:72-75) with the source of every entry.  Only the inspection entry points
+// (bos_download_csc, bos_pattern_info_get, bos_host_pattern_*) need it, so it is built lazily: at 2 M edges it is 27 M entries.
+void build_csc(HostPattern& P) {
+    if (P.csc_built) return;
+    const int NP = P.NP, NL = P.NL, fixed = P.fixed;
     auto nofixed = [&](int i) { const int f3 = 3 * fixed; return i < f3 ? i : (i < f3 + 3 ? -1 : i - 3); };
     const int n = P.N - 3;
     P.csc_colptr.assign(n + 1, 0);
@@ -288,7 +296,7 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
             P.csc_colptr[nofixed(3 * NP + 2 * l + c) + 1] = (int)P.csc_rowidx.size();
         }
     }
-    return 0;
+    P.csc_built = true;
 }
 
 }  // namespace bos
