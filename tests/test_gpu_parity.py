@@ -458,3 +458,45 @@ def test_levenberg_marquardt_extension_never_increases_chi2(built_lib):
     ctx.set_damping_factor(1e-9)
     s, after, ok, damp = ctx.step_lm()
     assert (ok and after < s.chi2_bearing + s.chi2_odometry) or (not ok and damp == pytest.approx(1e-8))
+
+
+@pytest.mark.parametrize("solver", [capi.SOLVER_DENSE_CHOLESKY, capi.SOLVER_PCG])
+def test_odometry_only_problem(built_lib, solver):
+    """No bearing edges at all (empty landmark side): the pose graph alone, both solvers, against the oracle."""
+    from prb_project_bearing_only_slam_b200.problem import Problem
+    rng = np.random.default_rng(2)
+    NP = 200
+    pose_ids = np.arange(10, 10 + NP)
+    xyt = np.column_stack([np.cumsum(np.full(NP, 0.5)), rng.normal(size=NP) * 0.05, rng.normal(size=NP) * 0.02])
+    src = np.concatenate([pose_ids[:-1], [pose_ids[150]]]); dst = np.concatenate([pose_ids[1:], [pose_ids[20]]])   # chain + one loop closure
+    oz = np.column_stack([np.full(NP, 0.5), np.zeros(NP), np.zeros(NP)]) + rng.normal(size=(NP, 3)) * 0.01
+    oz[-1] = [-65.0, 0.0, 0.0]
+    oom = np.tile(np.diag([500.0, 500.0, 5000.0]).ravel(), (NP, 1))
+    pr = Problem(pose_ids, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0), src, dst, oz, oom, fixed_pose_id=10, lm_ids=np.zeros(0, np.int32))
+    o = oracle_for(pose_ids, xyt, pr, triangulate=False, lms=np.zeros((0, 2)))
+    P, L = o.state()
+    ctx = make_ctx(pr, P, None, solver=solver, pcg_rtol=1e-13)
+    o.linearize(); o.solve(0)
+    ctx.linearize(); ctx.solve()
+    d, od = ctx.delta(), o.delta()
+    assert np.abs(d - od).max() <= 1e-8 * np.abs(od).max()
+    for _ in range(3):
+        o.step(0); s = ctx.step()
+    assert s.chi2_odometry == pytest.approx(o.stats()["chi2_odometry"], rel=1e-6)
+    assert np.abs(ctx.get_state()[0] - o.state()[0]).max() <= 1e-7
+
+
+def test_fp32_fused_pcg_matches_fp32_dense(built_lib):
+    """The persistent PCG kernel in the reference's own precision (documented tolerance, not a parity claim)."""
+    w, pr = synth_problem(600, 130, 6000, seed=21)
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr)
+    P, L = o.state()
+    ds = []
+    for solver in (capi.SOLVER_DENSE_CHOLESKY, capi.SOLVER_PCG):
+        ctx = make_ctx(pr, P, L, solver=solver, precision=capi.PRECISION_F32, pcg_rtol=1e-6, pcg_max_iters=5000)
+        ctx.linearize(); ctx.solve()
+        ds.append(ctx.delta())
+        assert ctx.stats().solver_status == 0
+    o.linearize(); o.solve(0)
+    assert np.abs(ds[0] - ds[1]).max() <= 2e-2 * np.abs(ds[0]).max()
+    assert np.abs(ds[1] - o.delta()).max() <= 5e-2 * np.abs(o.delta()).max()
