@@ -86,6 +86,17 @@ __device__ __forceinline__ void bearing_jl(const PoseV<S>& X, S lx, S ly, S& j0,
     j1 = a0 * s + a1 * c;
 }
 
+// The same landmark Jacobian without the rotation: R g = l - t =: d and rotations commute with the 90-degree turn, so
+// J_lm = [-gy, gx] R^T / |g|^2 = (-dy, dx) / |d|^2.  Algebraically identical to bearing_jl (rounding differs at the 1e-16 level);
+// used by the PCG operator, which only needs the pose translation this way.
+template <typename S>
+__device__ __forceinline__ void bearing_jl_world(S px, S py, S lx, S ly, S& j0, S& j1) {
+    const S dx = lx - px, dy = ly - py;
+    const S f = S(1) / (dx * dx + dy * dy);
+    j0 = -(dy * f);
+    j1 = dx * f;
+}
+
 // Bearing error and 1x5 Jacobian [J_pose(3) | J_lm(2)]  (slam/solver_jacobians.cpp:9-95, 301-305).
 // g = X^-1 * l with Eigen's isometry inverse: R^T l + (-(R^T) t); J = a * [-R^T | R^T (ly,-lx)^T | R^T],
 // a = [-gy, gx] / |g|^2.  The world-frame landmark appears in the theta column because boxplus is a

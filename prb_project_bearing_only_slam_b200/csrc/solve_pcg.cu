@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) 
                 const S u0 = w.ul4[4LL * row], u1 = w.ul4[4LL * row + 1], lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
                 const S i00 = w.hllinv_c[3LL * row], i01 = w.hllinv_c[3LL * row + 1], i11 = w.hllinv_c[3LL * row + 2];
                 S j0, j1;
-                bearing_jl<S>(X, lx, ly, j0, j1);
+                bearing_jl_world<S>(X.x, X.y, lx, ly, j0, j1);
                 const S so = w.omega_uniform ? (S)w.sqrt_omega : __ldg(w.Pw + slot);
                 j0 *= so; j1 *= so;
                 const S jp[3] = {-j0, -j1, j0 * ly - j1 * lx};
@@ -431,11 +431,12 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
             for (int k = 0; k < 8; k++) {
                 const int ps = psv[k];
                 if (ps < 0) continue;                              // padding, or an edge of the fixed pose (zero Jacobian block)
-                const PoseV<S> X = load_pose<S>(d.pose, ps);
+                S px, py;
+                load_lm<S>(d.pose, 2 * ps, px, py);                 // the pose translation: first half of the (x, y, c, s) record
                 S z0, z1, z2, zp;
                 ld4cg(vec4 + 4LL * ps, z0, z1, z2, zp);
                 S j0, j1;
-                bearing_jl<S>(X, lx, ly, j0, j1);
+                bearing_jl_world<S>(px, py, lx, ly, j0, j1);
                 const S so = w.omega_uniform ? so_u : __ldg(w.Lw + s0 + (long long)(tb + k) * 32);
                 j0 *= so; j1 *= so;
                 const S sc = (j0 * ly - j1 * lx) * z2 - j0 * z0 - j1 * z1;   // Jp_k . z
@@ -508,6 +509,12 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             soff[h] = (o - goff0) * 32 + lane;
             swid[h] = __ldg(d.pc_goff + (size_t)c * gpc + r / 32 + 1) - o;
         }
+    }
+    S posx[kPcgRows], posy[kPcgRows];   // the owned poses' translations: all the pose pass needs of the state, constant during the solve
+#pragma unroll
+    for (int h = 0; h < kPcgRows; h++) {
+        posx[h] = posy[h] = S(0);
+        if (pose_i[h] >= 0) load_lm<S>(d.pose, 2 * pose_i[h], posx[h], posy[h]);
     }
     const int myrow0 = (tid < ncl) ? __ldg(d.pc_cl_row + cl0 + tid) : -1;
     const int myrow1 = (tid + kPcgThreads < ncl) ? __ldg(d.pc_cl_row + cl0 + tid + kPcgThreads) : -1;
@@ -616,14 +623,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             const S so_u = (S)w.sqrt_omega;
             double gacc = 0.0, dacc2 = 0.0;
             // loads by pose index first (independent of the staging), then the barrier, then the rows
-            PoseV<S> X[kPcgRows];
             S zz[kPcgRows][3];
 #pragma unroll
             for (int h = 0; h < kPcgRows; h++) {
-                X[h] = PoseV<S>{S(0), S(0), S(1), S(0)};
                 zz[h][0] = zz[h][1] = zz[h][2] = S(0);
                 if (pose_i[h] >= 0) {
-                    X[h] = load_pose<S>(d.pose, pose_i[h]);
                     S zp;
                     ld4cg(zc + 4LL * pose_i[h], zz[h][0], zz[h][1], zz[h][2], zp);
                 }
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                     if (lc == 0xffffu || !active) continue;
                     const S u0 = rec[4 * lc], u1 = rec[4 * lc + 1], lx = rec[4 * lc + 2], ly = rec[4 * lc + 3];
                     S j0, j1;
-                    bearing_jl<S>(X[h], lx, ly, j0, j1);
+                    bearing_jl_world<S>(posx[h], posy[h], lx, ly, j0, j1);
                     const S so = w.omega_uniform ? so_u : __ldg(w.Pw + (size_t)goff0 * 32 + soff[h] + t * 32);
                     j0 *= so; j1 *= so;
                     const S m = j0 * u0 + j1 * u1;
