@@ -13,4 +13,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # full captures of the two kernels the bench reports a roofline for, and of the pose kernel of the H, b build
 ncu --set full --import-source on --clock-control none -k k_pcg_fused -s 3 -c 1 -f -o $O/prof_pcg_$R python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_pcg_$R.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:"k_linearize_bearing_persistent|k_pose_finish" -s 6 -c 2 -f -o $O/prof_lin_$R python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_lin_$R.log 2>&1
+# dense Cholesky (config 3): the DMMA trailing-update kernel of the first outer panels, and the solve time
+python tools/prof_dense.py > $O/dense_$R.log 2>&1; tail -1 $O/dense_$R.log
+ncu --set full --clock-control none -k k_syrk_big -s 2 -c 1 -f -o $O/prof_syrk_$R python tools/prof_dense.py > $O/ncu_syrk_$R.log 2>&1
+# secondary lines: FP32 flavour of the same bench, dense workload, batched config 5
+python bench.py --precision f32 --steps 3 --warmup 3 --no-cpu-baseline > $O/bench_f32_$R.json 2> $O/bench_f32_$R.err; tail -c 300 $O/bench_f32_$R.json
+python bench.py --workload synth-100k --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_100k_$R.json 2> $O/bench_100k_$R.err
+python tools/prof_batch.py 4096 > $O/batch_$R.log 2>&1; cat $O/batch_$R.log
 ls -la $O | tail -12
