@@ -71,7 +71,8 @@ typedef struct bos_stats {
     int64_t over_bearing;     /* edges whose error_omeganorm exceeded kernel_threshold */
     int64_t over_odometry;
     double delta_inf;         /* max |dx| */
-    int solver_status;        /* 0 ok, 1 = non-positive pivot (the reference's "not SPD" console message, solver.cpp:82-84) */
+    int solver_status;        /* 0 ok, 1 = non-positive pivot / CG breakdown (the reference's "not SPD" console message,
+                                 solver.cpp:82-84), 2 = the PCG stopped at pcg_max_iters before reaching pcg_rtol */
     int solver_used;          /* BOS_SOLVER_DENSE_CHOLESKY or BOS_SOLVER_PCG */
     int pcg_iterations;
     int gpu_launches;         /* kernels launched by the last step() */

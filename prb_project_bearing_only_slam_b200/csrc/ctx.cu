@@ -104,7 +104,7 @@ struct bos_ctx {
     ShardRange shard;
     int shard_chunk_b = 0;
     int launches = 0;
-    bool pcg_bad = false;
+    bool pcg_bad = false, pcg_capped = false;
     std::vector<double> b_omega_sorted;   // bearing omegas in sorted-edge order (host copy for the PCG setup)
     void* lm_pose_bak = nullptr;          // state backup of bos_step_lm
     void* lm_lm_bak = nullptr;
@@ -385,7 +385,7 @@ int solve_impl(bos_ctx* c) {
         if (e) return e;
         rc = launch_dense_solve<S>(d, dwork<S>(c), c->opt.damping, c->stream, &nl);
         c->stats.pcg_iterations = 0;
-        c->pcg_bad = false;
+        c->pcg_bad = false; c->pcg_capped = false;
     } else {
         int e = ensure_pcg<S>(c);
         if (e) return e;
@@ -396,6 +396,7 @@ int solve_impl(bos_ctx* c) {
         if (rc < 0) return fail(c, BOS_ERR_CUDA, std::string("pcg: ") + cudaGetErrorString(cudaGetLastError()));
         c->stats.pcg_iterations = iters;
         c->pcg_bad = (rc == 1);
+        c->pcg_capped = (rc == 0 && iters >= c->opt.pcg_max_iters);
     }
     c->launches += nl;
     CUDA_OK(c, cudaGetLastError());
@@ -419,7 +420,7 @@ int fetch_stats(bos_ctx* c) {
     c->stats.chi2_bearing = h[0]; c->stats.chi2_odometry = h[1];
     c->stats.over_bearing = (int64_t)llround(h[2]); c->stats.over_odometry = (int64_t)llround(h[3]);
     c->stats.delta_inf = h[4];
-    c->stats.solver_status = (h[5] != 0.0 || c->pcg_bad) ? 1 : 0;
+    c->stats.solver_status = (h[5] != 0.0 || c->pcg_bad) ? 1 : (c->pcg_capped ? 2 : 0);
     c->stats.solver_used = c->solver_used;
     return BOS_OK;
 }

@@ -3,12 +3,14 @@
 // -> Solver -> step() x K; instead of drawing it prints per-iteration chi2 / |dx| and can dump the final state as g2o.
 //
 //   bearing_only_slam <dataset.g2o> [--iters K=50] [--out final.g2o] [--fp32] [--solver auto|dense|pcg] [--device D] [--quiet]
+//   bearing_only_slam --synth NP NL EDGES [same options]      a synthetic world of that size instead of a file (BASELINE configs 3, 4)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "../slam/solver.hpp"
 #include "../slam/triangulation.hpp"
@@ -25,7 +27,15 @@ int main(int argc, char** argv) {
     std::string out;
     bool quiet = false;
     SolverOptions opt;
-    for (int a = 2; a < argc; a++) {
+    int synth_np = 0, synth_nl = 0;
+    long long synth_e = 0;
+    int first_opt = 2;
+    if (std::string(argv[1]) == "--synth") {
+        if (argc < 5) { std::cout << "--synth needs NP NL EDGES" << std::endl; return 1; }
+        synth_np = std::atoi(argv[2]); synth_nl = std::atoi(argv[3]); synth_e = std::atoll(argv[4]);
+        first_opt = 5;
+    }
+    for (int a = first_opt; a < argc; a++) {
         const std::string s = argv[a];
         if (s == "--iters" && a + 1 < argc) iters = std::atoi(argv[++a]);
         else if (s == "--out" && a + 1 < argc) out = argv[++a];
@@ -44,7 +54,33 @@ int main(int argc, char** argv) {
     odometry_observations.reserve(300);
     int fixed_pose_id;
     float bound = 0;
-    parse_g2o(argv[1], state, bearing_observations, odometry_observations, fixed_pose_id, bound);
+    if (synth_np > 0) {
+        // the library's synthetic world generator, fed through the same State / observation API a file would go through
+        bos_synth_spec spec;
+        bos_synth_default_spec(&spec);
+        spec.n_poses = synth_np; spec.n_landmarks = synth_nl; spec.target_bearing_edges = synth_e;
+        bos_synth* w = nullptr;
+        if (bos_synth_create(&spec, &w) != BOS_OK) { std::cout << "cannot generate the synthetic world" << std::endl; return 2; }
+        int64_t cnt[4];
+        bos_synth_counts(w, cnt);
+        std::vector<int32_t> pid(cnt[0]), bp(cnt[2]), bl(cnt[2]), os(cnt[3]), od(cnt[3]);
+        std::vector<double> xyt(3 * cnt[0]), bz(cnt[2]), oz(3 * cnt[3]), oom(9 * cnt[3]);
+        bos_synth_get(w, pid.data(), xyt.data(), nullptr, nullptr, nullptr, bp.data(), bl.data(), bz.data(), os.data(), od.data(), oz.data(), oom.data());
+        bos_synth_destroy(w);
+        for (int64_t i = 0; i < cnt[0]; i++) state.add_pose((float)xyt[3 * i], (float)xyt[3 * i + 1], (float)xyt[3 * i + 2], pid[i]);
+        bearing_observations.reserve(cnt[2]);
+        for (int64_t e = 0; e < cnt[2]; e++) bearing_observations.emplace_back(bp[e], bl[e], (float)bz[e]);
+        odometry_observations.reserve(cnt[3]);
+        for (int64_t e = 0; e < cnt[3]; e++) {
+            la::Mat3f om;
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) om(a, b) = (float)oom[9 * e + 3 * a + b];
+            odometry_observations.emplace_back(os[e], od[e], (float)oz[3 * e], (float)oz[3 * e + 1], (float)oz[3 * e + 2], om);
+        }
+        fixed_pose_id = -1;
+    } else {
+        parse_g2o(argv[1], state, bearing_observations, odometry_observations, fixed_pose_id, bound);
+    }
     if (state.number_of_poses() == 0) return 2;
     if (fixed_pose_id < 0) fixed_pose_id = state.default_pose_id();
     try {

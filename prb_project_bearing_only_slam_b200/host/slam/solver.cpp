@@ -115,8 +115,10 @@ void Solver::step(int iterations, bool mirror_every_step) {
     if (!device_state_valid_ || state.version() != synced_version_) upload_state();
     for (int it = 0; it < iterations; it++) {
         check(bos_step(ctx_, &stats_), "bos_step");
-        if (stats_.solver_status != 0)   // slam/solver.cpp:82-84: log and carry on
+        if (stats_.solver_status == 1)   // slam/solver.cpp:82-84: log and carry on
             std::cout << "Factorization failed: the reduced system is not positive definite" << std::endl;
+        else if (stats_.solver_status == 2)
+            std::cout << "PCG stopped at its iteration cap before reaching the tolerance (SolverOptions::pcg_max_iters)" << std::endl;
         if (mirror_every_step || it + 1 == iterations) download_state();
     }
 }

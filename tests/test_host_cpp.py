@@ -102,3 +102,14 @@ def test_headless_harness_on_the_full_dataset(host_test_exe, tmp_path):
     # the written poses are where the oracle converges
     P = np.array([[float(x) for x in l.split()[2:5]] for l in lines if l.startswith("VERTEX_SE2")])
     assert np.abs(P[:, :2] - g["poses_final_f64"][:, :2]).max() < 5e-3
+
+
+@pytest.mark.gpu
+def test_headless_harness_on_a_synthetic_world(host_test_exe):
+    """BASELINE configs 3/4 through the C++ host API (State / observation vectors / triangulate_landmarks / Solver), small size."""
+    from prb_project_bearing_only_slam_b200 import build_host
+    r = subprocess.run([build_host.EXE, "--synth", "3000", "700", "30000", "--iters", "6", "--solver", "pcg"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr
+    chi = [float(a) + float(b) for a, b in re.findall(r"chi2_bearing (\S+) chi2_odometry (\S+)", r.stdout)]
+    assert len(chi) == 6 and chi[-1] < 0.2 * chi[0]
+    assert "solver pcg" in r.stdout and "poses 3000" in r.stdout
