@@ -84,111 +84,151 @@ __global__ void __launch_bounds__(128, 4) k_pose_finish(Dev<S> d, int e_begin, i
                                                         const S* __restrict__ bnd) {
     __shared__ double red[2][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ig = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = ig < d.NP;            // every lane runs the whole body (the chain hand-over below shuffles), only valid lanes store
+    const int i = valid ? ig : d.NP - 1;
     double chi_acc = 0.0;
     int over_acc = 0;
-    if (i < d.NP) {
-        S h[6] = {damping, S(0), S(0), damping, S(0), damping};
-        S b[3] = {S(0), S(0), S(0)};
-        // the bearing part left by K1: in the pose's own block when its run lies inside one tile, else in the side slots
-        {
-            const int ra = __ldg(d.epose_ptr + i), rb = __ldg(d.epose_ptr + i + 1);
-            const int lo = ra > e_begin ? ra : e_begin, hi = rb < e_end ? rb : e_end;
-            if (hi > lo && i != d.fixed) {
-                const int t0 = (lo - e_begin) / kLinTile, t1 = (hi - 1 - e_begin) / kLinTile;
-                for (int t = t0; t <= t1; t++) {
-                    const int ta = e_begin + t * kLinTile, tb = (ta + kLinTile < e_end) ? ta + kLinTile : e_end;
-                    const S* src;
-                    if (ra >= ta && rb <= tb) {
-                        const S* hp = d.Hpp + 6LL * i;
-                        const S* bp = d.b + 3LL * i;
+    S h[6] = {damping, S(0), S(0), damping, S(0), damping};
+    S b[3] = {S(0), S(0), S(0)};
+    // the bearing part left by K1: in the pose's own block when its run lies inside one tile, else in the side slots
+    {
+        const int ra = __ldg(d.epose_ptr + i), rb = __ldg(d.epose_ptr + i + 1);
+        const int lo = ra > e_begin ? ra : e_begin, hi = rb < e_end ? rb : e_end;
+        if (hi > lo && i != d.fixed) {
+            const int t0 = (lo - e_begin) / kLinTile, t1 = (hi - 1 - e_begin) / kLinTile;
+            for (int t = t0; t <= t1; t++) {
+                const int ta = e_begin + t * kLinTile, tb = (ta + kLinTile < e_end) ? ta + kLinTile : e_end;
+                if (ra >= ta && rb <= tb) {
+                    const S* hp = d.Hpp + 6LL * i;
+                    const S* bp = d.b + 3LL * i;
 #pragma unroll
-                        for (int k = 0; k < 6; k++) h[k] += hp[k];
-                        b[0] += bp[0]; b[1] += bp[1]; b[2] += bp[2];
-                        continue;
-                    }
-                    src = bnd + (size_t)(2 * t + (ra < ta ? 0 : 1)) * 9;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) h[k] += src[k];
-                    b[0] += src[6]; b[1] += src[7]; b[2] += src[8];
+                    for (int k = 0; k < 6; k++) h[k] += hp[k];
+                    b[0] += bp[0]; b[1] += bp[1]; b[2] += bp[2];
+                    continue;
                 }
+                const S* src = bnd + (size_t)(2 * t + (ra < ta ? 0 : 1)) * 9;
+#pragma unroll
+                for (int k = 0; k < 6; k++) h[k] += src[k];
+                b[0] += src[6]; b[1] += src[7]; b[2] += src[8];
             }
         }
-        const size_t Eo = (size_t)d.Eo;
-        const PoseV<S> Xi = load_pose<S>(d.pose, i);
-        const S thi = __ldg(d.theta + i);
-        // everything an incident odometry edge needs, loaded up front so that the loads of several edges are in flight together
-        struct EdgeIn { int e, role, other, slot; bool live, shared; PoseV<S> Xo; S tho, om[6], z[3]; };
-        auto load_edge = [&](int code, int other) {
-            EdgeIn in;
-            in.e = code >> 1; in.role = code & 1; in.other = other;
-            in.live = code >= 0 && in.e >= o_begin && in.e < o_end;
-            if (in.live) {
-                in.Xo = load_pose<S>(d.pose, other);
-                in.tho = __ldg(d.theta + other);
+    }
+    const size_t Eo = (size_t)d.Eo;
+    const PoseV<S> Xi = load_pose<S>(d.pose, i);
+    const S thi = __ldg(d.theta + i);
+    // everything an incident odometry edge needs, loaded up front so that the loads of several edges are in flight together
+    struct EdgeIn { int e, role, other, slot; bool live, shared; PoseV<S> Xo; S tho, om[6], z[3]; };
+    auto load_edge = [&](int code, int other) {
+        EdgeIn in;
+        in.e = code >> 1; in.role = code & 1; in.other = other; in.slot = 0; in.shared = false;
+        in.live = code >= 0 && in.e >= o_begin && in.e < o_end;
+        if (in.live) {
+            in.Xo = load_pose<S>(d.pose, other);
+            in.tho = __ldg(d.theta + other);
 #pragma unroll
-                for (int k = 0; k < 6; k++) in.om[k] = __ldg(d.o_om + k * Eo + in.e);
+            for (int k = 0; k < 6; k++) in.om[k] = __ldg(d.o_om + k * Eo + in.e);
 #pragma unroll
-                for (int k = 0; k < 3; k++) in.z[k] = __ldg(d.o_z + k * Eo + in.e);
-                in.slot = __ldg(d.o_slot + in.e);
-                in.shared = d.o_shared[in.e] != 0;
-            }
-            return in;
-        };
-        auto apply_edge = [&](const EdgeIn& in) {
-            if (!in.live) return;
-            const int other = in.other, role = in.role;
-            const int s = role ? other : i, t = role ? i : other;
-            const PoseV<S> Xs = role ? in.Xo : Xi, Xd = role ? Xi : in.Xo;
-            S err[3], u0, u1;
-            odometry_terms<S>(Xs, Xd, role ? in.tho : thi, role ? thi : in.tho, in.z[0], in.z[1], in.z[2], err, u0, u1);
-            const S chi = odometry_chi<S>(in.om, err);
-            S scale = S(1);
-            const bool over = chi > kernel_threshold;
-            if (over) scale = sqrt(kernel_threshold / chi);   // scales the ERROR only (slam/solver.cpp:54-58)
-            S M[6], v[3];
-            odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, in.om, err, M, v, scale);
-            const bool fs = (s == d.fixed), ft = (t == d.fixed);
-            if (role == 0) {
-                chi_acc += (double)chi;
-                over_acc += over ? 1 : 0;
-                if (!fs) {
+            for (int k = 0; k < 3; k++) in.z[k] = __ldg(d.o_z + k * Eo + in.e);
+            in.slot = __ldg(d.o_slot + in.e);
+            in.shared = d.o_shared[in.e] != 0;
+        }
+        return in;
+    };
+    // M = J_s^T Omega J_s and v = J_s^T Omega e of an edge (J_dst = -J_src entry for entry); also chi2 / over-threshold
+    auto edge_normal = [&](const EdgeIn& in, S M[6], S v[3], S& chi, bool& over) {
+        const PoseV<S> Xs = in.role ? in.Xo : Xi, Xd = in.role ? Xi : in.Xo;
+        S err[3], u0, u1;
+        odometry_terms<S>(Xs, Xd, in.role ? in.tho : thi, in.role ? thi : in.tho, in.z[0], in.z[1], in.z[2], err, u0, u1);
+        chi = odometry_chi<S>(in.om, err);
+        S scale = S(1);
+        over = chi > kernel_threshold;
+        if (over) scale = sqrt(kernel_threshold / chi);   // scales the ERROR only (slam/solver.cpp:54-58)
+        odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, in.om, err, M, v, scale);
+    };
+    auto add_as_source = [&](const EdgeIn& in, const S M[6], const S v[3], S chi, bool over) {
+        const bool fs = (i == d.fixed), ft = (in.other == d.fixed);
+        chi_acc += (double)chi;
+        over_acc += over ? 1 : 0;
+        if (!fs) {
 #pragma unroll
-                    for (int k = 0; k < 6; k++) h[k] += M[k];
-                    b[0] += v[0]; b[1] += v[1]; b[2] += v[2];
-                }
-                // H[lo][hi] += J_lo^T Omega J_hi = -M (M symmetric, so the orientation does not matter)
-                S* ho = d.Hoff + 9LL * in.slot;
-                const S z = (fs || ft) ? S(0) : S(1);
-                const S m9[9] = {-M[0] * z, -M[1] * z, -M[2] * z, -M[1] * z, -M[3] * z, -M[4] * z, -M[2] * z, -M[4] * z, -M[5] * z};
-                if (in.shared) {
+            for (int k = 0; k < 6; k++) h[k] += M[k];
+            b[0] += v[0]; b[1] += v[1]; b[2] += v[2];
+        }
+        if (!valid) return;
+        // H[lo][hi] += J_lo^T Omega J_hi = -M (M symmetric, so the orientation does not matter)
+        S* ho = d.Hoff + 9LL * in.slot;
+        const S z = (fs || ft) ? S(0) : S(1);
+        const S m9[9] = {-M[0] * z, -M[1] * z, -M[2] * z, -M[1] * z, -M[3] * z, -M[4] * z, -M[2] * z, -M[4] * z, -M[5] * z};
+        if (in.shared) {
 #pragma unroll
-                    for (int k = 0; k < 9; k++) red_add(ho + k, m9[k]);
-                } else {
+            for (int k = 0; k < 9; k++) red_add(ho + k, m9[k]);
+        } else {
 #pragma unroll
-                    for (int k = 0; k < 9; k++) ho[k] = m9[k];
-                }
-            } else if (!ft) {
+            for (int k = 0; k < 9; k++) ho[k] = m9[k];
+        }
+    };
+    auto add_as_destination = [&](const S M[6], const S v[3]) {
+        if (i == d.fixed) return;
 #pragma unroll
-                for (int k = 0; k < 6; k++) h[k] += M[k];
-                b[0] -= v[0]; b[1] -= v[1]; b[2] -= v[2];
-            }
-        };
-        {
-            const int4 m2 = __ldg(reinterpret_cast<const int4*>(d.oe2) + i);   // the first two incident edges inline (odometry chains)
-            const EdgeIn e0 = load_edge(m2.x, m2.y), e1 = load_edge(m2.z, m2.w);
-            apply_edge(e0);
-            apply_edge(e1);
-            if (m2.z >= 0) {   // more than two incident edges (loop closures): the rest through the CSR list
-                const int q0 = __ldg(d.oe_ptr + i), q1 = __ldg(d.oe_ptr + i + 1);
-                for (int q = q0 + 2; q < q1; q++) apply_edge(load_edge(__ldg(d.oe_edge + q), __ldg(d.oe_other + q)));
+        for (int k = 0; k < 6; k++) h[k] += M[k];
+        b[0] -= v[0]; b[1] -= v[1]; b[2] -= v[2];
+    };
+    const int4 m2 = __ldg(reinterpret_cast<const int4*>(d.oe2) + i);   // the first two incident edges inline (odometry chains)
+    const EdgeIn e0 = load_edge(m2.x, m2.y), e1 = load_edge(m2.z, m2.w);
+    // 1. edges this pose is the SOURCE of: computed here; the last one is offered to the next lane, which along an odometry chain
+    //    is that edge's destination and then does not have to recompute it
+    int pub_e = -1;
+    S pubM[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, pubv[3] = {S(0), S(0), S(0)};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const EdgeIn& in = k ? e1 : e0;
+        if (in.live && in.role == 0) {
+            S chi; bool over;
+            edge_normal(in, pubM, pubv, chi, over);
+            add_as_source(in, pubM, pubv, chi, over);
+            pub_e = valid ? in.e : -1;
+        }
+    }
+    const int prev_e = __shfl_up_sync(BOS_FULL_MASK, pub_e, 1);
+    S prevM[6], prevv[3];
+#pragma unroll
+    for (int k = 0; k < 6; k++) prevM[k] = __shfl_up_sync(BOS_FULL_MASK, pubM[k], 1);
+#pragma unroll
+    for (int k = 0; k < 3; k++) prevv[k] = __shfl_up_sync(BOS_FULL_MASK, pubv[k], 1);
+    // 2. edges this pose is the DESTINATION of: taken from the previous lane when it just computed exactly that edge
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const EdgeIn& in = k ? e1 : e0;
+        if (in.live && in.role == 1) {
+            if (lane > 0 && prev_e == in.e) {
+                add_as_destination(prevM, prevv);
+            } else {
+                S M[6], v[3], chi; bool over;
+                edge_normal(in, M, v, chi, over);
+                add_as_destination(M, v);
             }
         }
+    }
+    if (m2.z >= 0) {   // more than two incident edges (loop closures): the rest through the CSR list
+        const int q0 = __ldg(d.oe_ptr + i), q1 = __ldg(d.oe_ptr + i + 1);
+        for (int q = q0 + 2; q < q1; q++) {
+            const EdgeIn in = load_edge(__ldg(d.oe_edge + q), __ldg(d.oe_other + q));
+            if (!in.live) continue;
+            S M[6], v[3], chi; bool over;
+            edge_normal(in, M, v, chi, over);
+            if (in.role == 0) add_as_source(in, M, v, chi, over);
+            else add_as_destination(M, v);
+        }
+    }
+    if (valid) {
         S* hp = d.Hpp + 6LL * i;
 #pragma unroll
         for (int k = 0; k < 6; k++) hp[k] = h[k];
         S* bp = d.b + 3LL * i;
         bp[0] = b[0]; bp[1] = b[1]; bp[2] = b[2];
+    } else {
+        chi_acc = 0.0; over_acc = 0;
     }
     double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
     if (lane == 0) { red[0][warp] = c; red[1][warp] = o; }
