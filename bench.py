@@ -116,6 +116,16 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def recorded_block_jacobi_iterations(workload, default):
+    """CG iterations per GN step of the 3x3 block-Jacobi PCG on this workload (measured on the GPU with --pcg-precond 1; the
+    CPU restatement runs the same algorithm at ~0.05 s per iteration, so it is extrapolated, not run to convergence)."""
+    p = os.path.join(ROOT, "profiles", "pcg_iterations.json")
+    try:
+        return int(json.load(open(p)).get(workload, default))
+    except Exception:
+        return default
+
+
 def make_world(name):
     from prb_project_bearing_only_slam_b200 import capi
     from prb_project_bearing_only_slam_b200.problem import Problem
@@ -206,7 +216,8 @@ def run_ours(args):
     solver = capi.SOLVER_PCG if solver_name == "pcg" else capi.SOLVER_DENSE_CHOLESKY
     prec = capi.PRECISION_F64 if args.precision == "f64" else capi.PRECISION_F32
     S = 8 if args.precision == "f64" else 4
-    ctx = capi.Context(device=local, solver=solver, precision=prec, pcg_rtol=args.pcg_rtol, pcg_max_iters=args.pcg_max_iters)
+    ctx = capi.Context(device=local, solver=solver, precision=prec, pcg_rtol=args.pcg_rtol, pcg_max_iters=args.pcg_max_iters,
+                       pcg_precond=args.pcg_precond)
     pr.upload(ctx)
     if args.reduce_mode < 0:
         args.reduce_mode = 2 if solver == capi.SOLVER_PCG else 1
@@ -293,9 +304,12 @@ def run_ours(args):
     if solver == capi.SOLVER_PCG and pcg_iters > 0:
         # the dominant kernel of a step is the persistent PCG kernel (> 99 % of the step at synth-2M): one launch = one solve
         b_it = pcg_iteration_bytes(pr.NP, pr.NL, pr.Eb, S)
+        if args.pcg_precond == 0:   # chain preconditioner: 15 FP32 factor values per pose row are read every CG iteration
+            b_it += 15 * 4 * pr.NP
         ach = b_it * pcg_iters / (ms_solve * 1e-3) / 1e9
         t_it = traffic.get("pcg_dram_bytes_per_cg_iteration")
-        roofline = {"kernel": "k_pcg_fused (persistent cooperative kernel: the whole block-Jacobi PCG solve of one GN iteration)",
+        roofline = {"kernel": "k_pcg_fused (persistent cooperative kernel: the whole %s PCG solve of one GN iteration)" %
+                              ("chain-preconditioned" if args.pcg_precond == 0 else "block-Jacobi"),
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": (t_it * pcg_iters) if t_it else None, "peak_source": peak_src,
                     "bytes_per_launch": b_it * pcg_iters, "bytes_per_cg_iteration": b_it, "cg_iterations_per_launch": pcg_iters,
@@ -310,7 +324,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": args.workload, "poses": pr.NP, "landmarks": pr.NL, "bearing_edges": pr.Eb, "odometry_edges": pr.Eo,
-                   "N": int(pi.N), "solver": "schur+block-jacobi-pcg" if solver == capi.SOLVER_PCG else "schur+dense-cholesky",
+                   "N": int(pi.N), "solver": ("schur+pcg(block-tridiagonal chain preconditioner)" if args.pcg_precond == 0 else "schur+block-jacobi-pcg")
+                   if solver == capi.SOLVER_PCG else "schur+dense-cholesky",
                    "pcg_rtol": args.pcg_rtol, "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
                    (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)"}[args.reduce_mode]) if world > 1 else "single gpu",
                    "l2": "no flush: value + edge buffers (%.0f MB) exceed the 126 MB L2" % ((int(pi.vals_len) * S + pr.Eb * 24) / 1e6)},
@@ -328,13 +343,18 @@ def run_ours(args):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        cb = oracle_sample(w, pr, int(round(line["pcg_iterations"])), args.pcg_rtol)
+        # the CPU port runs the reference-arm algorithm (3x3 block-Jacobi PCG): its own iteration count at this tolerance
+        cpu_iters = int(round(line["pcg_iterations"]))
+        if solver == capi.SOLVER_PCG and args.pcg_precond == 0:
+            cpu_iters = recorded_block_jacobi_iterations(args.workload, cpu_iters)
+        cb = oracle_sample(w, pr, cpu_iters, args.pcg_rtol)
         line["cpu_baseline"] = {
             "value": 1.0 / cb["t_step"], "unit": "iterations/s", "cores": 1, "kind": "port",
             "edges_linearized_per_s": E / cb["t_lin"],
             "sample": "CPU oracle (restatement; the reference needs Eigen3/OpenCV, absent here), 1 thread, full %s world: H,b build timed "
                       "in full (%.3f s), Schur-PCG timed for 2 and 12 CG iterations (%.4f s/iteration) and extrapolated to the %d "
-                      "iterations this run needed" % (args.workload, cb["t_lin"], cb["t_cg_iter"], int(round(line["pcg_iterations"])))}
+                      "iterations its 3x3 block-Jacobi preconditioner needs at this tolerance (profiles/pcg_iterations.json)" %
+                      (args.workload, cb["t_lin"], cb["t_cg_iter"], cpu_iters)}
     print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -359,6 +379,7 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--pcg-max-iters", type=int, default=20000)
+    ap.add_argument("--pcg-precond", type=int, default=0, choices=[0, 1], help="0 chain (block-tridiagonal) preconditioner, 1 3x3 block-Jacobi")
     ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 2 for the PCG workloads, 1 for the dense ones")
     ap.add_argument("--ref-pcg-iters", type=int, default=0, help="CG iterations per GN step the reference arm extrapolates to "
                     "(0 = the count recorded by our arm in profiles/pcg_iterations.json, else 300)")

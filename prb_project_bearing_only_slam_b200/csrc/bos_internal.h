@@ -171,6 +171,13 @@ struct PcgWork {
     double* scal = nullptr;  // [32] classic: rz, pAp, rz_new, rz0, done flag, iterations ...; fused: see solve_pcg.cu
     unsigned* bar = nullptr; // [4] grid barrier counter of the fused kernel
     int variant = 0;         // bos_options.pcg_variant: 0 = fused persistent kernel, 1 = classic multi-kernel loop
+    // chain preconditioner of the fused kernel (bos_options.pcg_precond 0): per chunk, the block-tridiagonal matrix of the Schur
+    // diagonal blocks and the pose-pose blocks between consecutive chunk rows (the odometry chain), solved exactly per CG iteration
+    int precond = 0;         // 0 = chain (falls back to 1 when its factors do not fit in shared memory), 1 = 3x3 block-Jacobi
+    S* chD = nullptr;        // [6][rows] Schur diagonal blocks (identity on padding rows)
+    S* chO = nullptr;        // [6][rows] block between chunk row R and R + 1 (symmetric by construction), zero if none / across chunks
+    float* chF = nullptr;    // [chunks][ch_fac_floats] factors in the shared-memory layout of the solve (see k_pcg_chain_factor)
+    int ch_Kp = 0, ch_cps = 0, ch_fac_floats = 0;
     int sm_count = 148;
 };
 template <typename S>

@@ -322,6 +322,19 @@ int ensure_pcg(bos_ctx* c) {
     w.z4 = c->mem.get<S>(8 * (size_t)d.NP);
     w.rowS = c->mem.get<S>(24 * (size_t)d.pc_chunks * d.pc_cp);
     w.rS = c->mem.get<S>(3 * (size_t)d.pc_chunks * d.pc_cp);
+    w.variant = c->opt.pcg_variant;
+    w.precond = c->opt.pcg_precond;
+    w.sm_count = c->sm_count;
+    {   // chain preconditioner: factor storage in the solve's shared-memory layout (odd group stride: conflict-free columns)
+        const size_t rows = (size_t)d.pc_chunks * d.pc_cp;
+        w.ch_Kp = (d.pc_cp / 32) | 1;
+        w.ch_cps = w.ch_Kp * 32;
+        w.ch_fac_floats = 16 * w.ch_cps + 28 * w.ch_Kp;
+        w.chD = c->mem.get<S>(6 * std::max<size_t>(rows, 1));
+        w.chO = c->mem.get<S>(6 * std::max<size_t>(rows, 1));
+        w.chF = c->mem.get<float>((size_t)std::max(d.pc_chunks, 1) * w.ch_fac_floats);
+        if (!w.chD || !w.chO || !w.chF) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+    }
     w.xS = c->mem.get<S>(3 * (size_t)d.pc_chunks * d.pc_cp);
     if (!w.hllinv_c || !w.ul4 || !w.z4 || !w.rS || !w.xS || !w.rowS) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
     c->pcg_ready = true;

@@ -364,6 +364,18 @@ __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) 
                 sd[0] -= q * jp[0] * jp[0]; sd[1] -= q * jp[0] * jp[1]; sd[2] -= q * jp[0] * jp[2];
                 sd[3] -= q * jp[1] * jp[1]; sd[4] -= q * jp[1] * jp[2]; sd[5] -= q * jp[2] * jp[2];
             }
+        if (w.precond == 0) {   // chain preconditioner: its diagonal block and the block that couples this row to the next chunk row
+            const int inext = (r + 1 < d.pc_cp) ? __ldg(d.pc_row_pose + R + 1) : -1;
+            S o[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+            if (inext >= 0)
+                for (int q = __ldg(d.pp_ptr + i); q < __ldg(d.pp_ptr + i + 1); q++)
+                    if (__ldg(d.pp_nbr + q) == inext) {
+                        const S* Bo = d.Hoff + 9LL * (__ldg(d.pp_slot + q) & 0x7fffffff);
+                        o[0] = Bo[0]; o[1] = Bo[1]; o[2] = Bo[2]; o[3] = Bo[4]; o[4] = Bo[5]; o[5] = Bo[8];
+                    }
+#pragma unroll
+            for (int k = 0; k < 6; k++) { w.chD[(size_t)k * nrows + R] = sd[k]; w.chO[(size_t)k * nrows + R] = o[k]; }
+        }
         S mi[6];
         sym3_inverse<S>(sd, mi);
 #pragma unroll
@@ -390,14 +402,19 @@ __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) 
         }
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-            w.z4[4LL * i + a] = (a < 3) ? z[a] : S(0);
+            w.z4[4LL * i + a] = (a < 3 && w.precond != 0) ? z[a] : S(0);   // chain: the persistent kernel applies M^-1 to g itself
             w.z4[np4 + 4LL * i + a] = S(0);
         }
+        if (w.precond != 0) {
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            gz += (double)gg[a] * (double)z[a];
-            zw += (double)z[a] * (double)hz[a];
+            for (int a = 0; a < 3; a++) {
+                gz += (double)gg[a] * (double)z[a];
+                zw += (double)z[a] * (double)hz[a];
+            }
         }
+    } else if (R < nrows && w.precond == 0) {   // padding row: identity block, no coupling
+#pragma unroll
+        for (int k = 0; k < 6; k++) { w.chD[(size_t)k * nrows + R] = (k == 0 || k == 3 || k == 5) ? S(1) : S(0); w.chO[(size_t)k * nrows + R] = S(0); }
     }
     double s1 = block_sum_256(gz, red);
     __syncthreads();
@@ -464,15 +481,324 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
     }
 }
 
+// ---- chain preconditioner ----------------------------------------------------------------------------------------------
+// Per chunk (= CTA of the persistent kernel) M is the block-tridiagonal matrix of the Schur diagonal blocks D_r and the
+// pose-pose blocks O_r between consecutive chunk rows (the odometry chain; every such block is -J_s^T Omega J_s, symmetric).
+// M = H_chain + blockdiag(bearing Schur diagonal + damping) is SPD.  It is solved exactly with two levels: the chunk's rows
+// form groups of 32 = 31 interior rows + 1 separator row; the interiors are independent block-tridiagonal systems (one thread
+// each, block LDL^T), the separators a block-tridiagonal Schur system over the groups.  Factors are stored as FP32 (the applied
+// operator stays symmetric positive definite whatever the rounding: it is a congruence of blockdiag(T~^-1, S~^-1)), in the
+// layout the solve reads from shared memory: row (group g, position k) at k * Kp + g with Kp odd.
+// Layout of a chunk's factor block (floats), read from shared memory by the solve as 16-byte vectors without bank conflicts:
+//   interior row (group g, position k): four float4 at F + ((k * 4 + c) * Kp + g) * 4, c = 0..3 holding
+//     {L0..L3} {L4..L7} {L8, d0, d1, d2} {d3, d4, d5, 0}   (L row-major 3x3 with L_0 = 0, d = Delta^-1 symmetric)
+//   separator j: the same 16 floats contiguous at Fs + 16 * j, Fs = F + 16 * cps
+//   coupling blocks of group g: three float4 at Fc + (c * Kp + g) * 4, Fc = Fs + 16 * Kp:
+//     {ct0..ct3} {ct4, ct5, cb0, cb1} {cb2..cb5};  C_top(g) couples separator g - 1 with the first interior row of group g,
+//     C_bot(g) the last interior row with separator g
+__device__ __forceinline__ void chain_store_row(float* base, int sc, const float L[9], const float dv[6]) {
+    base[0] = L[0]; base[1] = L[1]; base[2] = L[2]; base[3] = L[3];
+    base[sc] = L[4]; base[sc + 1] = L[5]; base[sc + 2] = L[6]; base[sc + 3] = L[7];
+    base[2 * sc] = L[8]; base[2 * sc + 1] = dv[0]; base[2 * sc + 2] = dv[1]; base[2 * sc + 3] = dv[2];
+    base[3 * sc] = dv[3]; base[3 * sc + 1] = dv[4]; base[3 * sc + 2] = dv[5]; base[3 * sc + 3] = 0.f;
+}
+template <typename S>
+__device__ __forceinline__ void sym6_to_full(const S a[6], S m[9]) {
+    m[0] = a[0]; m[1] = a[1]; m[2] = a[2]; m[3] = a[1]; m[4] = a[3]; m[5] = a[4]; m[6] = a[2]; m[7] = a[4]; m[8] = a[5];
+}
+template <typename S>
+__device__ __forceinline__ void mat3_mul(const S a[9], const S b[9], S o[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+template <typename S>
+__device__ __forceinline__ void mat3_tmul(const S a[9], const S b[9], S o[9]) {   // a^T b
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
+}
+
+template <typename S>
+__global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w) {
+    __shared__ S Eff[64][6], Ell[64][6], Efl[64][9], Dsep[64][6], Osep[64][9];
+    const int c = blockIdx.x, g = threadIdx.x, cp = d.pc_cp, K = cp / 32, Kp = w.ch_Kp, cps = w.ch_cps;
+    const size_t nrows = (size_t)d.pc_chunks * cp;
+    float* F = w.chF + (size_t)c * w.ch_fac_floats;
+    float* Fs = F + 16 * cps;
+    float* Fc = Fs + 16 * Kp;
+    const size_t R0 = (size_t)c * cp + (size_t)g * 32;
+    auto ldD = [&](int k, S o[6]) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) o[q] = w.chD[(size_t)q * nrows + R0 + k];
+    };
+    auto ldO = [&](long long k, S o[6]) {   // block between rows R0 + k and R0 + k + 1
+#pragma unroll
+        for (int q = 0; q < 6; q++) o[q] = w.chO[(size_t)q * nrows + R0 + k];
+    };
+    if (g < K) {
+        // downward elimination of the interior: L_k = O_{k-1} Delta_{k-1}^-1, Delta_k = D_k - L_k O_{k-1}
+        S dinv[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, op[9];
+        for (int k = 0; k < 31; k++) {
+            S D[6], L[9] = {S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0)};
+            ldD(k, D);
+            if (k > 0) {
+                S di[9], lo[9];
+                sym6_to_full<S>(dinv, di);
+                mat3_mul<S>(op, di, L);
+                mat3_mul<S>(L, op, lo);
+                D[0] -= lo[0]; D[1] -= S(0.5) * (lo[1] + lo[3]); D[2] -= S(0.5) * (lo[2] + lo[6]);
+                D[3] -= lo[4]; D[4] -= S(0.5) * (lo[5] + lo[7]); D[5] -= lo[8];
+            }
+            sym3_inverse<S>(D, dinv);
+            {
+                float Lf[9], df[6];
+#pragma unroll
+                for (int q = 0; q < 9; q++) Lf[q] = (float)L[q];
+#pragma unroll
+                for (int q = 0; q < 6; q++) df[q] = (float)dinv[q];
+                chain_store_row(F + ((size_t)(k * 4) * Kp + g) * 4, Kp * 4, Lf, df);
+            }
+            S o6[6];
+            ldO(k, o6);
+            sym6_to_full<S>(o6, op);
+        }
+        {   // the separator's slot of the interior arrays is never read by the solve
+            const float z9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            chain_store_row(F + ((size_t)(31 * 4) * Kp + g) * 4, Kp * 4, z9, z9);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) Ell[g][q] = dinv[q];            // [T^-1]_(30,30)
+        // [T^-1]_(0,30): X_30 = Delta_30^-1, X_k = -L_{k+1}^T X_{k+1} (with the stored factors)
+        S X[9];
+        sym6_to_full<S>(dinv, X);
+        for (int k = 29; k >= 0; k--) {
+            S L[9], t[9];
+            const float* b = F + ((size_t)((k + 1) * 4) * Kp + g) * 4;
+#pragma unroll
+            for (int q = 0; q < 9; q++) L[q] = (S)b[(q >> 2) * Kp * 4 + (q & 3)];
+            mat3_tmul<S>(L, X, t);
+#pragma unroll
+            for (int q = 0; q < 9; q++) X[q] = -t[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; q++) Efl[g][q] = X[q];
+        // upward elimination: Delta'_30 = D_30, Delta'_k = D_k - O_k Delta'_{k+1}^-1 O_k; [T^-1]_(0,0) = Delta'_0^-1
+        S up[6];
+        ldD(30, up);
+        sym3_inverse<S>(up, dinv);
+        for (int k = 29; k >= 0; k--) {
+            S D[6], o6[6], o[9], di[9], t[9], lo[9];
+            ldD(k, D); ldO(k, o6);
+            sym6_to_full<S>(o6, o); sym6_to_full<S>(dinv, di);
+            mat3_mul<S>(o, di, t);
+            mat3_mul<S>(t, o, lo);
+            D[0] -= lo[0]; D[1] -= S(0.5) * (lo[1] + lo[3]); D[2] -= S(0.5) * (lo[2] + lo[6]);
+            D[3] -= lo[4]; D[4] -= S(0.5) * (lo[5] + lo[7]); D[5] -= lo[8];
+            sym3_inverse<S>(D, dinv);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) Eff[g][q] = dinv[q];
+    }
+    __syncthreads();
+    if (g < K) {
+        // separator Schur system: eliminate the interiors on both sides of separator g
+        S ct6[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, cb6[6], cn6[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, D[6];
+        if (g > 0) ldO(-1, ct6);          // separator g-1 (row R0 - 1) <-> first interior row
+        ldO(30, cb6);                      // last interior row <-> separator g
+        if (g + 1 < K) ldO(31, cn6);       // separator g <-> first interior row of group g + 1  (= C_top(g + 1))
+        ldD(31, D);
+        S cb[9], ct[9], cn[9], e[9], t[9], u[9];
+        sym6_to_full<S>(cb6, cb); sym6_to_full<S>(ct6, ct); sym6_to_full<S>(cn6, cn);
+        sym6_to_full<S>(Ell[g], e);
+        mat3_mul<S>(cb, e, t); mat3_mul<S>(t, cb, u);
+        D[0] -= u[0]; D[1] -= S(0.5) * (u[1] + u[3]); D[2] -= S(0.5) * (u[2] + u[6]); D[3] -= u[4]; D[4] -= S(0.5) * (u[5] + u[7]); D[5] -= u[8];
+        if (g + 1 < K) {
+            sym6_to_full<S>(Eff[g + 1], e);
+            mat3_mul<S>(cn, e, t); mat3_mul<S>(t, cn, u);
+            D[0] -= u[0]; D[1] -= S(0.5) * (u[1] + u[3]); D[2] -= S(0.5) * (u[2] + u[6]); D[3] -= u[4]; D[4] -= S(0.5) * (u[5] + u[7]); D[5] -= u[8];
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) Dsep[g][q] = D[q];
+        // block (separator g-1, separator g) = -C_top(g) [T_g^-1]_(0,30) C_bot(g)
+        mat3_mul<S>(ct, Efl[g], t); mat3_mul<S>(t, cb, u);
+#pragma unroll
+        for (int q = 0; q < 9; q++) Osep[g][q] = -u[q];
+#pragma unroll
+        for (int q = 0; q < 12; q++) Fc[((q >> 2) * Kp + g) * 4 + (q & 3)] = (float)(q < 6 ? ct6[q] : cb6[q - 6]);
+    }
+    __syncthreads();
+    if (g == 0) {   // block LDL^T of the separator chain: L_j = Osep_j^T Delta_{j-1}^-1, Delta_j = Dsep_j - L_j Osep_j
+        S dinv[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+        for (int j = 0; j < K; j++) {
+            S D[6], L[9] = {S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0)};
+#pragma unroll
+            for (int q = 0; q < 6; q++) D[q] = Dsep[j][q];
+            if (j > 0) {
+                S di[9], lo[9];
+                sym6_to_full<S>(dinv, di);
+                mat3_tmul<S>(Osep[j], di, L);
+                mat3_mul<S>(L, Osep[j], lo);
+                D[0] -= lo[0]; D[1] -= S(0.5) * (lo[1] + lo[3]); D[2] -= S(0.5) * (lo[2] + lo[6]);
+                D[3] -= lo[4]; D[4] -= S(0.5) * (lo[5] + lo[7]); D[5] -= lo[8];
+            }
+            sym3_inverse<S>(D, dinv);
+            {
+                float Lf[9], df[6];
+#pragma unroll
+                for (int q = 0; q < 9; q++) Lf[q] = (float)L[q];
+#pragma unroll
+                for (int q = 0; q < 6; q++) df[q] = (float)dinv[q];
+                chain_store_row(Fs + 16 * j, 4, Lf, df);
+            }
+        }
+    }
+}
+
+// One block-tridiagonal solve with stored factors: y_k = rhs_k - L_k y_{k-1}, w_k = Delta_k^-1 y_k, z_k = w_k - L_{k+1}^T z_{k+1}.
+// rhs may alias out.  a0 / aN are added to the first / last right-hand side.  The recurrences run in FP32 like the stored factors
+// (a preconditioner only has to approximate M^-1; the CG recurrences themselves stay in S).  One thread walks a chain, so the
+// cost is the instruction count of a step: operands are float vectors in shared memory, the next step's are fetched while the
+// current one computes (two register sets, no copies).
+//   F: the first row's float4 group; fc4 = distance between a row's four float4 (in float4), fk4 = distance between rows
+#define BOS_CH_FETCH(P, FP, RP)                                                                       \
+    P##a = (FP)[0]; P##b = (FP)[fc4]; P##c = (FP)[2 * fc4]; P##d = (FP)[3 * fc4];                        \
+    P##r0 = (RP)[0]; P##r1 = (RP)[vcs]; P##r2 = (RP)[2 * vcs];
+#define BOS_CH_FWD(P)                                                                                  \
+    {                                                                                                  \
+        const float n0 = fmaf(-P##a.z, y2, fmaf(-P##a.y, y1, fmaf(-P##a.x, y0, P##r0)));                  \
+        const float n1 = fmaf(-P##b.y, y2, fmaf(-P##b.x, y1, fmaf(-P##a.w, y0, P##r1)));                  \
+        const float n2 = fmaf(-P##c.x, y2, fmaf(-P##b.w, y1, fmaf(-P##b.z, y0, P##r2)));                  \
+        y0 = n0; y1 = n1; y2 = n2;                                                                     \
+        op[0] = P##c.y * y0 + P##c.z * y1 + P##c.w * y2;                                                  \
+        op[vcs] = P##c.z * y0 + P##d.x * y1 + P##d.y * y2;                                                \
+        op[2 * vcs] = P##c.w * y0 + P##d.y * y1 + P##d.z * y2;                                            \
+        op += vstep;                                                                                   \
+    }
+#define BOS_CH_BFETCH(P, FP, OP)                                                                      \
+    P##a = (FP)[0]; P##b = (FP)[fc4]; P##e = (FP)[2 * fc4].x; P##w0 = (OP)[0]; P##w1 = (OP)[vcs]; P##w2 = (OP)[2 * vcs];
+#define BOS_CH_BWD(P)                                                                                  \
+    {                                                                                                  \
+        const float n0 = fmaf(-P##b.z, z2, fmaf(-P##a.w, z1, fmaf(-P##a.x, z0, P##w0)));                  \
+        const float n1 = fmaf(-P##b.w, z2, fmaf(-P##b.x, z1, fmaf(-P##a.y, z0, P##w1)));                  \
+        const float n2 = fmaf(-P##e, z2, fmaf(-P##b.y, z1, fmaf(-P##a.z, z0, P##w2)));                    \
+        z0 = n0; z1 = n1; z2 = n2;                                                                     \
+        op[0] = z0; op[vcs] = z1; op[2 * vcs] = z2;                                                    \
+    }
+__device__ __forceinline__ void chain_thomas(const float4* F, int fc4, int fk4, const float* rhs, float* out, int vcs, int vstep, int n, const float a0[3],
+                                             const float aN[3]) {
+    float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+    float4 Aa, Ab, Ac, Ad, Ba, Bb, Bc, Bd;
+    float Ar0, Ar1, Ar2, Br0, Br1, Br2;
+    const float4* Fp = F;
+    const float* rp = rhs;
+    float* op = out;
+    BOS_CH_FETCH(A, Fp, rp)
+    Ar0 += a0[0]; Ar1 += a0[1]; Ar2 += a0[2];
+    if (n == 1) { Ar0 += aN[0]; Ar1 += aN[1]; Ar2 += aN[2]; }
+    for (int k = 0;;) {   // the fetch past the last row re-reads the last row (unused)
+        if (k + 1 < n) { Fp += fk4; rp += vstep; }
+        BOS_CH_FETCH(B, Fp, rp)
+        if (k + 2 == n) { Br0 += aN[0]; Br1 += aN[1]; Br2 += aN[2]; }
+        BOS_CH_FWD(A)
+        if (++k >= n) break;
+        if (k + 1 < n) { Fp += fk4; rp += vstep; }
+        BOS_CH_FETCH(A, Fp, rp)
+        if (k + 2 == n) { Ar0 += aN[0]; Ar1 += aN[1]; Ar2 += aN[2]; }
+        BOS_CH_FWD(B)
+        if (++k >= n) break;
+    }
+    // backward: op is one past the last row, Fp at the last row; row k needs L_{k+1} (zero above the last row) and w_k
+    op -= vstep;
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+    float4 Pa = make_float4(0.f, 0.f, 0.f, 0.f), Pb = Pa, Qa, Qb;
+    float Pe = 0.f, Pw0 = op[0], Pw1 = op[vcs], Pw2 = op[2 * vcs], Qe, Qw0, Qw1, Qw2;
+    for (int k = n - 1;;) {   // row k - 1 needs L_k (at Fp) and its own w; at k = 0 the fetch is unused
+        { const float* wp = (k > 0) ? op - vstep : op; BOS_CH_BFETCH(Q, Fp, wp) }
+        BOS_CH_BWD(P)
+        if (--k < 0) break;
+        op -= vstep; Fp -= fk4;
+        { const float* wp = (k > 0) ? op - vstep : op; BOS_CH_BFETCH(P, Fp, wp) }
+        BOS_CH_BWD(Q)
+        if (--k < 0) break;
+        op -= vstep; Fp -= fk4;
+    }
+}
+
+// z = M^-1 r for the CTA's chunk; called by threads 0..63 (two warps, named barrier 1).  All vectors are FP32 [3][cps] in the
+// transposed row layout (row (g, k) at k * Kp + g) at byte offsets of the dynamic shared memory: r1 / w1 right-hand side and work
+// space of the first interior pass and of the separator system (may coincide), r2 / w2 of the second pass (w2 holds the result;
+// r2 == w2 allowed).  Not inlined: inside the persistent kernel the 64-register budget is taken by the per-thread row state, here
+// the recurrences get their own allocation.
+__device__ __noinline__ void chain_apply(unsigned fac_off, unsigned r1_off, unsigned w1_off, unsigned r2_off, unsigned w2_off, int cps, int Kp, int K) {
+    extern __shared__ __align__(16) unsigned char pcg_smem[];
+    const float* r1 = reinterpret_cast<const float*>(pcg_smem + r1_off);
+    float* w1 = reinterpret_cast<float*>(pcg_smem + w1_off);
+    const float* r2 = reinterpret_cast<const float*>(pcg_smem + r2_off);
+    float* w2 = reinterpret_cast<float*>(pcg_smem + w2_off);
+    const int g = threadIdx.x;
+    const bool act = g < K;
+    const float4* F4 = reinterpret_cast<const float4*>(pcg_smem + fac_off);
+    const float4* Fs4 = F4 + 4 * cps;          // 16 * cps floats
+    const float4* Fc4 = Fs4 + 4 * Kp;          // 16 * Kp floats further
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    float ct[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int sp = 31 * Kp + g;
+    if (act) {
+        const float4 c0 = Fc4[g], c1 = Fc4[Kp + g], c2 = Fc4[2 * Kp + g];
+        ct[0] = c0.x; ct[1] = c0.y; ct[2] = c0.z; ct[3] = c0.w; ct[4] = c1.x; ct[5] = c1.y;
+        cb[0] = c1.z; cb[1] = c1.w; cb[2] = c2.x; cb[3] = c2.y; cb[4] = c2.z; cb[5] = c2.w;
+        chain_thomas(F4 + g, Kp, 4 * Kp, r1 + g, w1 + g, cps, Kp, 31, zero3, zero3);
+    }
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (act) {   // separator right-hand side: r_sep - C_bot(g) y_(g,30) - C_top(g+1) y_(g+1,0)
+        const int lp = 30 * Kp + g;
+        float q0 = r1[sp], q1 = r1[sp + cps], q2 = r1[sp + 2 * cps];
+        {
+            const float v0 = w1[lp], v1 = w1[lp + cps], v2 = w1[lp + 2 * cps];
+            q0 -= cb[0] * v0 + cb[1] * v1 + cb[2] * v2; q1 -= cb[1] * v0 + cb[3] * v1 + cb[4] * v2; q2 -= cb[2] * v0 + cb[4] * v1 + cb[5] * v2;
+        }
+        if (g + 1 < K) {
+            const int q = g + 1;
+            const float4 c0 = Fc4[q], c1 = Fc4[Kp + q];
+            const float v0 = w1[q], v1 = w1[q + cps], v2 = w1[q + 2 * cps];
+            q0 -= c0.x * v0 + c0.y * v1 + c0.z * v2; q1 -= c0.y * v0 + c0.w * v1 + c1.x * v2; q2 -= c0.z * v0 + c1.x * v1 + c1.y * v2;
+        }
+        w1[sp] = q0; w1[sp + cps] = q1; w1[sp + 2 * cps] = q2;
+    }
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (g == 0) chain_thomas(Fs4, 1, 4, w1 + 31 * Kp, w1 + 31 * Kp, cps, 1, K, zero3, zero3);
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (act) {   // interiors again, with the separator solutions moved to the right-hand side
+        float a0[3] = {0.f, 0.f, 0.f}, aN[3];
+        if (g > 0) {
+            const float v0 = w1[sp - 1], v1 = w1[sp - 1 + cps], v2 = w1[sp - 1 + 2 * cps];
+            a0[0] = -(ct[0] * v0 + ct[1] * v1 + ct[2] * v2); a0[1] = -(ct[1] * v0 + ct[3] * v1 + ct[4] * v2); a0[2] = -(ct[2] * v0 + ct[4] * v1 + ct[5] * v2);
+        }
+        const float v0 = w1[sp], v1 = w1[sp + cps], v2 = w1[sp + 2 * cps];
+        aN[0] = -(cb[0] * v0 + cb[1] * v1 + cb[2] * v2); aN[1] = -(cb[1] * v0 + cb[3] * v1 + cb[4] * v2); aN[2] = -(cb[2] * v0 + cb[4] * v1 + cb[5] * v2);
+        chain_thomas(F4 + g, Kp, 4 * Kp, r2 + g, w2 + g, cps, Kp, 31, a0, aN);
+        w2[sp] = v0; w2[sp + cps] = v1; w2[sp + 2 * cps] = v2;   // the separator's own solution joins the result
+    }
+}
+
 // shared-memory plan of the persistent kernel (per CTA = per chunk)
 template <typename S>
 struct PcgSmemPlan {
     size_t vec_off, rec_off, loc_off, bytes;
-    __host__ __device__ PcgSmemPlan(int cp, int cl_max, int slots_max) {
-        vec_off = 0;                                                   // [12][cp]  p 0-2, s 3-5, r 6-8, yoff 9-11
-        rec_off = vec_off + (size_t)12 * cp * sizeof(S);               // [cl_max][4]  u0, u1, lx, ly of the chunk's landmarks
+    int cps, Kp, fac_floats;
+    __host__ __device__ PcgSmemPlan(int cp, int cl_max, int slots_max, bool chain) {
+        Kp = (cp / 32) | 1;
+        cps = chain ? Kp * 32 : cp;                                    // chain: rows transposed to (position in group, group), odd group stride
+        fac_floats = 16 * Kp * 32 + 28 * Kp;
+        vec_off = 0;                                                   // [12][cps]  p 0-2, s 3-5, r 6-8, yoff 9-11 (chain: then z = M^-1 r)
+        rec_off = vec_off + (size_t)12 * cps * sizeof(S);              // [cl_max][4]  u0, u1, lx, ly of the chunk's landmarks
         loc_off = rec_off + (size_t)4 * (cl_max > 0 ? cl_max : 1) * sizeof(S);   // [slots_max] 16-bit landmark table indices
         bytes = (loc_off + (size_t)2 * (slots_max > 0 ? slots_max : 1) + 15) / 16 * 16;
+        // chain: the FP32 factors are staged over the record / index region while the preconditioner runs (the indices are re-staged after)
+        if (chain && rec_off + (size_t)fac_floats * 4 > bytes) bytes = rec_off + (size_t)fac_floats * 4;
     }
 };
 
@@ -480,7 +806,9 @@ template <typename S>
 __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2) {
     extern __shared__ __align__(16) unsigned char pcg_smem[];
     __shared__ double red[kPcgThreads / 32];
-    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max);
+    const bool chain = w.precond == 0;
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, chain);
+    const int cps = plan.cps, Kp = plan.Kp;
     S* vsm = reinterpret_cast<S*>(pcg_smem + plan.vec_off);
     S* rec = reinterpret_cast<S*>(pcg_smem + plan.rec_off);
     unsigned short* loc_s = reinterpret_cast<unsigned short*>(pcg_smem + plan.loc_off);
@@ -492,16 +820,18 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     unsigned epoch = 0;
     double* sc = w.scal;
 #ifdef BOS_PCG_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
     // ---- static per-thread data: this thread owns chunk rows tid and tid + 1024 for the whole solve ---------------------
     const int goff0 = __ldg(d.pc_goff + (size_t)c * gpc);
     const int cl0 = __ldg(d.pc_cl_ptr + c), ncl = __ldg(d.pc_cl_ptr + c + 1) - cl0;
-    int pose_i[kPcgRows], soff[kPcgRows], swid[kPcgRows];
+    const int nslots = (__ldg(d.pc_goff + (size_t)(c + 1) * gpc) - goff0) * 32;
+    int pose_i[kPcgRows], soff[kPcgRows], swid[kPcgRows], vx[kPcgRows];
 #pragma unroll
     for (int h = 0; h < kPcgRows; h++) {
         const int r = tid + h * kPcgThreads;
+        vx[h] = chain ? (r & 31) * Kp + (r >> 5) : r;              // position of the row in the shared-memory vectors
         pose_i[h] = (r < cp) ? __ldg(d.pc_row_pose + (size_t)c * cp + r) : -1;
         soff[h] = 0; swid[h] = 0;
         if (r < cp) {
@@ -518,17 +848,82 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     }
     const int myrow0 = (tid < ncl) ? __ldg(d.pc_cl_row + cl0 + tid) : -1;
     const int myrow1 = (tid + kPcgThreads < ncl) ? __ldg(d.pc_cl_row + cl0 + tid + kPcgThreads) : -1;
+    auto stage_loc = [&]() {   // 16-bit landmark table indices of the chunk's edge slots (64-byte aligned runs of 32)
+        const uint4* src = reinterpret_cast<const uint4*>(d.pc_loc + (size_t)goff0 * 32);
+        uint4* dst = reinterpret_cast<uint4*>(loc_s);
+        for (int k = tid; k < nslots / 8; k += kPcgThreads) dst[k] = __ldg(src + k);
+    };
+    // chain preconditioner: z = M^-1 r from the residual in shared memory into rows 9-11, then the per-row consumers: z to the
+    // global buffer the next operator application gathers from, gamma = r.z and the diagonal-block part of delta = z.S z
+    // FP32 views for the chain solve.  S = float: the residual rows (6-8) are the right-hand side, rows 9-11 work space and
+    // result.  S = double: rows 9-11 hold two float triples, each a copy of the residual that its pass overwrites in place.
+    constexpr bool kWide = sizeof(S) == 8;
+    const unsigned zoff = (unsigned)(plan.vec_off + (size_t)9 * cps * sizeof(S)), roff = (unsigned)(plan.vec_off + (size_t)6 * cps * sizeof(S));
+    const unsigned ch_r1 = kWide ? zoff : roff, ch_w1 = zoff, ch_r2 = kWide ? zoff + 12u * cps : roff, ch_w2 = kWide ? zoff + 12u * cps : zoff;
+    const float* zres = reinterpret_cast<const float*>(pcg_smem + ch_w2);
+    auto precond_chain = [&](S* zdst, double& gacc, double& dacc2) {
+        __syncthreads();
+        if (kWide) {
+            float* c1 = reinterpret_cast<float*>(pcg_smem + ch_r1);
+            float* c2 = reinterpret_cast<float*>(pcg_smem + ch_r2);
+#pragma unroll
+            for (int h = 0; h < kPcgRows; h++) {
+                if (tid + h * kPcgThreads >= cp) continue;
+                const S* v = vsm + vx[h];
+#pragma unroll
+                for (int a = 0; a < 3; a++) { const float f = (float)v[(6 + a) * cps]; c1[a * cps + vx[h]] = f; c2[a * cps + vx[h]] = f; }
+            }
+        }
+        {
+            const float4* src = reinterpret_cast<const float4*>(w.chF + (size_t)c * plan.fac_floats);
+            float4* dst = reinterpret_cast<float4*>(pcg_smem + plan.rec_off);
+            for (int k = tid; k < plan.fac_floats / 4; k += kPcgThreads) dst[k] = __ldg(src + k);
+        }
+        __syncthreads();
+        PCG_T(8);
+        if (tid < 64) chain_apply((unsigned)plan.rec_off, ch_r1, ch_w1, ch_r2, ch_w2, cps, Kp, cp / 32);
+        __syncthreads();
+        PCG_T(9);
+#pragma unroll
+        for (int h = 0; h < kPcgRows; h++) {
+            const int i = pose_i[h];
+            if (i < 0) continue;
+            const int r = tid + h * kPcgThreads;
+            const S* v = vsm + vx[h];
+            const S r0 = v[6 * cps], r1 = v[7 * cps], r2 = v[8 * cps];
+            const S zn0 = (S)zres[vx[h]], zn1 = (S)zres[cps + vx[h]], zn2 = (S)zres[2 * cps + vx[h]];
+            const S* hp = w.rowS + (size_t)c * cp + r;
+            const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
+                    h5 = __ldg(hp + 5 * nrows);
+            st4cg(zdst + 4LL * i, zn0, zn1, zn2);
+            gacc += (double)r0 * (double)zn0 + (double)r1 * (double)zn1 + (double)r2 * (double)zn2;
+            dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
+                     (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
+        }
+        stage_loc();   // the factors overwrote the index table
+        PCG_T(10);
+    };
     {
-        const int nslots = (__ldg(d.pc_goff + (size_t)(c + 1) * gpc) - goff0) * 32;
-        for (int k = tid; k < nslots; k += kPcgThreads) loc_s[k] = d.pc_loc[(size_t)goff0 * 32 + k];
+        stage_loc();
 #pragma unroll
         for (int h = 0; h < kPcgRows; h++) {
             const int r = tid + h * kPcgThreads;
             if (r < cp) {
 #pragma unroll
-                for (int k = 0; k < 12; k++) vsm[(size_t)k * cp + r] = (pose_i[h] >= 0 && k >= 6 && k < 9) ? w.rS[(size_t)(k - 6) * nrows + (size_t)c * cp + r] : S(0);
+                for (int k = 0; k < 12; k++) vsm[(size_t)k * cps + vx[h]] = (pose_i[h] >= 0 && k >= 6 && k < 9) ? w.rS[(size_t)(k - 6) * nrows + (size_t)c * cp + r] : S(0);
             }
         }
+    }
+    if (chain) {   // z_0 = M^-1 g, gamma_0 and the first part of delta_0 (the 3x3 flavour gets them from k_pcg_fused_prep)
+        double g0 = 0.0, d0 = 0.0;
+        precond_chain(w.z4, g0, d0);
+        const double sg = block_sum_pcg(g0, red);
+        const double sd = block_sum_pcg(d0, red);
+        if (tid == 0) {
+            if (sg != 0.0) atomicAdd(sc + FS_GAMMA0, sg);
+            if (sd != 0.0) atomicAdd(sc + FS_DELTA0, sd);
+        }
+        grid_barrier(w.bar, gridDim.x, epoch);
     }
     __syncthreads();
     const double gamma_init = __ldcg(sc + FS_GAMMA0);
@@ -588,7 +983,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                     ld4cg(zc + 4LL * i, z0, z1, z2, zp);
                     dacc += (double)z0 * (double)y0 + (double)z1 * (double)y1 + (double)z2 * (double)y2;
                 }
-                vsm[(size_t)9 * cp + r] = y0; vsm[(size_t)10 * cp + r] = y1; vsm[(size_t)11 * cp + r] = y2;
+                vsm[(size_t)9 * cps + vx[h]] = y0; vsm[(size_t)10 * cps + vx[h]] = y1; vsm[(size_t)11 * cps + vx[h]] = y2;
             }
             PCG_T(0);
             pcg_landmark_rows<S, 0>(d, w, zc, wg, nwarps, dacc);
@@ -658,18 +1053,19 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 const S* hp = w.rowS + (size_t)c * cp + r;
                 const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
                         h5 = __ldg(hp + 5 * nrows);
-                w0 += h0 * z0 + h1 * z1 + h2 * z2 + vsm[(size_t)9 * cp + r];
-                w1 += h1 * z0 + h3 * z1 + h4 * z2 + vsm[(size_t)10 * cp + r];
-                w2 += h2 * z0 + h4 * z1 + h5 * z2 + vsm[(size_t)11 * cp + r];
-                S* v = vsm + r;
-                const S p0 = z0 + be * v[0], p1 = z1 + be * v[cp], p2 = z2 + be * v[2 * cp];
-                const S s0_ = w0 + be * v[3 * cp], s1 = w1 + be * v[4 * cp], s2 = w2 + be * v[5 * cp];
-                v[0] = p0; v[cp] = p1; v[2 * cp] = p2;
-                v[3 * cp] = s0_; v[4 * cp] = s1; v[5 * cp] = s2;
-                const S r0 = v[6 * cp] - al * s0_, r1 = v[7 * cp] - al * s1, r2 = v[8 * cp] - al * s2;
-                v[6 * cp] = r0; v[7 * cp] = r1; v[8 * cp] = r2;
+                S* v = vsm + vx[h];
+                w0 += h0 * z0 + h1 * z1 + h2 * z2 + v[9 * cps];
+                w1 += h1 * z0 + h3 * z1 + h4 * z2 + v[10 * cps];
+                w2 += h2 * z0 + h4 * z1 + h5 * z2 + v[11 * cps];
+                const S p0 = z0 + be * v[0], p1 = z1 + be * v[cps], p2 = z2 + be * v[2 * cps];
+                const S s0_ = w0 + be * v[3 * cps], s1 = w1 + be * v[4 * cps], s2 = w2 + be * v[5 * cps];
+                v[0] = p0; v[cps] = p1; v[2 * cps] = p2;
+                v[3 * cps] = s0_; v[4 * cps] = s1; v[5 * cps] = s2;
+                const S r0 = v[6 * cps] - al * s0_, r1 = v[7 * cps] - al * s1, r2 = v[8 * cps] - al * s2;
+                v[6 * cps] = r0; v[7 * cps] = r1; v[8 * cps] = r2;
                 S* xg = w.xS + (size_t)c * cp + r;
                 xg[0] += al * p0; xg[nrows] += al * p1; xg[2 * nrows] += al * p2;
+                if (chain) continue;                         // z = M^-1 r needs the whole chunk's residual: below
                 const S* mi = hp + 6 * nrows;
                 const S m0 = __ldg(mi), m1 = __ldg(mi + nrows), m2 = __ldg(mi + 2 * nrows), m3 = __ldg(mi + 3 * nrows), m4 = __ldg(mi + 4 * nrows),
                         m5 = __ldg(mi + 5 * nrows);
@@ -680,6 +1076,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                          (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
             }
             PCG_T(4);
+            if (chain) precond_chain(zn, gacc, dacc2);
             {
                 const double sg = block_sum_pcg(gacc, red);
                 const double sd2 = block_sum_pcg(dacc2, red);
@@ -720,9 +1117,9 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     if (gtid == 0) { sc[SC_ITER] = (double)it; sc[SC_BAD] = bad ? 1.0 : 0.0; }
 #ifdef BOS_PCG_TIMING
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2))
-        printf("cta %d iters %d cycles/iter: offdiag %lld Lrows %lld bsum %lld bar1 %lld stage %lld rows %lld bsum2 %lld bar2 %lld\n", (int)blockIdx.x, it,
-               tacc[0] / (it ? it : 1), tacc[1] / (it ? it : 1), tacc[2] / (it ? it : 1), tacc[3] / (it ? it : 1), tacc[7] / (it ? it : 1),
-               tacc[4] / (it ? it : 1), tacc[5] / (it ? it : 1), tacc[6] / (it ? it : 1));
+        printf("cta %d iters %d cycles/iter: offdiag %lld Lrows %lld bsum %lld bar1 %lld stage %lld rows %lld bsum2 %lld bar2 %lld | chain: fac-stage %lld solve %lld finish %lld\n",
+               (int)blockIdx.x, it, tacc[0] / (it ? it : 1), tacc[1] / (it ? it : 1), tacc[2] / (it ? it : 1), tacc[3] / (it ? it : 1), tacc[7] / (it ? it : 1),
+               tacc[4] / (it ? it : 1), tacc[5] / (it ? it : 1), tacc[6] / (it ? it : 1), tacc[8] / (it ? it : 1), tacc[9] / (it ? it : 1), tacc[10] / (it ? it : 1));
 #endif
 }
 
@@ -730,8 +1127,13 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
 template <typename S>
 bool pcg_fused_supported(const Dev<S>& d) {
     if (!d.pc_ok || d.pc_cp > kPcgRows * kPcgThreads || d.pc_chunks < 1) return false;
-    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max);
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, false);
     return plan.bytes <= (size_t)kPcgSmemBudget;
+}
+template <typename S>
+bool pcg_chain_supported(const Dev<S>& d) {
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, true);
+    return plan.bytes <= (size_t)kPcgSmemBudget && d.pc_cp / 32 <= 64;
 }
 
 template <typename S>
@@ -744,8 +1146,12 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     cudaMemsetAsync(w.xS, 0, 3 * (size_t)nrows * sizeof(S), st);
     if (d.NL > 0) { k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++; }
     if (d.n_clm > 0) { k_ell_fill<S><<<(d.n_clm + 255) / 256, 256, 0, st>>>(d, w); nl++; }
+    const int precond = (w.precond == 0 && pcg_chain_supported<S>(d)) ? 0 : 1;
+    const int precond_asked = w.precond;
+    w.precond = precond;
     k_pcg_fused_prep<S><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(d, w); nl++;
-    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max);
+    if (precond == 0) { k_pcg_chain_factor<S><<<d.pc_chunks, 64, 0, st>>>(d, w); nl++; }
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, precond == 0);
     static size_t configured[2] = {0, 0};
     size_t& conf = configured[sizeof(S) == 8 ? 0 : 1];
     if (plan.bytes > conf) {
@@ -754,6 +1160,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     }
     Dev<S> dd = d;
     PcgWork<S> ww = w;
+    w.precond = precond_asked;
     double tol2 = rtol * rtol;
     void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2};
     if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(d.pc_chunks), dim3(kPcgThreads), args, plan.bytes, st) != cudaSuccess) return -1;

@@ -372,8 +372,8 @@ def test_pcg_fused_kernel_equals_classic_loop(built_lib, uniform_omega):
     P, L0 = o.state()
     L = np.vstack([L0, [[1.0, 2.0], [3.0, 4.0]]])
     ds, its = [], []
-    for variant in (0, 1):
-        ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-12, pcg_max_iters=20000, pcg_variant=variant)
+    for variant, precond in ((0, 0), (0, 1), (1, 1)):   # fused + chain preconditioner, fused + 3x3 block-Jacobi, classic loop
+        ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-12, pcg_max_iters=20000, pcg_variant=variant, pcg_precond=precond)
         ctx.linearize(); ctx.solve()
         ds.append(ctx.delta()); its.append(ctx.stats().pcg_iterations)
         if variant == 0:
@@ -381,11 +381,55 @@ def test_pcg_fused_kernel_equals_classic_loop(built_lib, uniform_omega):
             colptr, rowidx, val, b = ctx.csc()
             n = len(colptr) - 1
             H = sp.csc_matrix((val, rowidx, colptr), shape=(n, n))
-            r = H @ nofixed(pr, ds[0]) + b
+            r = H @ nofixed(pr, ds[-1]) + b
             assert np.abs(r).max() <= 1e-9 * np.abs(b).max()
-    assert np.abs(ds[0] - ds[1]).max() <= 1e-8 * np.abs(ds[1]).max()
-    assert np.all(ds[0][-4:] == 0.0)                                                     # unobserved landmarks: b_l = 0 -> dx_l = 0
-    assert its[0] > 0 and abs(its[0] - its[1]) <= 0.2 * its[1] + 5
+    assert np.abs(ds[0] - ds[2]).max() <= 1e-8 * np.abs(ds[2]).max()
+    assert np.abs(ds[1] - ds[2]).max() <= 1e-8 * np.abs(ds[2]).max()
+    for d_ in ds:
+        assert np.all(d_[-4:] == 0.0)                                                    # unobserved landmarks: b_l = 0 -> dx_l = 0
+    assert its[1] > 0 and abs(its[1] - its[2]) <= 0.2 * its[2] + 5
+    assert 0 < its[0] < 0.5 * its[1]                                                     # the chain preconditioner pays
+
+
+def test_pcg_chain_preconditioner_many_groups_and_loop_closures(built_lib):
+    """Chain preconditioner with several 32-row groups per chunk (separator system), loop-closure odometry edges (pose rows with
+    more than two pose-pose blocks; only chain-consecutive blocks enter the preconditioner) and a fixed pose mid-chain: the
+    solution satisfies the full normal equations and equals the 3x3 block-Jacobi solve."""
+    import scipy.sparse as sp
+    from prb_project_bearing_only_slam_b200.problem import Problem
+    w, pr0 = synth_problem(20000, 5000, 200000, seed=11)
+    rng = np.random.default_rng(4)
+    NPn = len(w["pose_ids"])
+    a = rng.integers(0, NPn - 200, size=25); bq = a + rng.integers(2, 150, size=25)          # 25 loop closures
+    osrc = np.concatenate([w["o_src_id"], w["pose_ids"][a]]); odst = np.concatenate([w["o_dst_id"], w["pose_ids"][bq]])
+    xyt = w["poses_init"]
+    dz = []
+    for i, j in zip(a, bq):
+        c, s_ = np.cos(xyt[i, 2]), np.sin(xyt[i, 2])
+        dx, dy = xyt[j, 0] - xyt[i, 0], xyt[j, 1] - xyt[i, 1]
+        dz.append([c * dx + s_ * dy, -s_ * dx + c * dy, np.arctan2(np.sin(xyt[j, 2] - xyt[i, 2]), np.cos(xyt[j, 2] - xyt[i, 2]))])
+    oz = np.vstack([w["o_z"], np.array(dz) + rng.normal(size=(25, 3)) * 0.01])
+    oom = np.vstack([w["o_omega"], np.tile(np.diag([500.0, 500.0, 5000.0]).ravel(), (25, 1))])
+    pr = Problem(w["pose_ids"], w["b_pose_id"], w["b_lm_id"], w["b_z"], osrc, odst, oz, oom, fixed_pose_id=int(w["pose_ids"][777]))
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr0)
+    P, L = o.state()
+    ds, its = [], []
+    for precond in (0, 1):
+        ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-11, pcg_max_iters=20000, pcg_precond=precond)
+        ctx.linearize(); ctx.solve()
+        ds.append(ctx.delta()); its.append(ctx.stats().pcg_iterations)
+        colptr, rowidx, val, b = ctx.csc()
+        n = len(colptr) - 1
+        H = sp.csc_matrix((val, rowidx, colptr), shape=(n, n))
+        r = H @ nofixed(pr, ds[-1]) + b
+        assert np.abs(r).max() <= 1e-8 * np.abs(b).max()
+    assert np.abs(ds[0] - ds[1]).max() <= 1e-7 * np.abs(ds[1]).max()
+    assert 0 < its[0] < 0.25 * its[1]
+    chi = []
+    ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-8)
+    for _ in range(3):
+        st = ctx.step(); chi.append(st.chi2_bearing + st.chi2_odometry)
+    assert chi[-1] < chi[0]
 
 
 def test_linearize_with_long_edge_free_pose_stretches_and_heavy_poses(built_lib):
