@@ -38,6 +38,8 @@ Solver::Solver(const State& st, const BearingObservationVector& bear_obs, const 
     opt_.dense_max_dim = o.dense_max_dim;
     opt_.pcg_max_iters = o.pcg_max_iters;
     opt_.pcg_rtol = o.pcg_rtol;
+    opt_.pcg_variant = o.pcg_variant;
+    opt_.pcg_precond = o.pcg_precond;
     const int rc = bos_create(&opt_, &ctx_);
     if (rc != BOS_OK) throw std::runtime_error("proj02::Solver: bos_create failed with status " + std::to_string(rc) +
                                                " (no CUDA device? there is no CPU fallback)");

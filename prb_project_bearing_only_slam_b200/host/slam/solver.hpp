@@ -14,10 +14,12 @@ namespace proj02 {
 struct SolverOptions {
     int device = 0;
     bool fp32 = false;                 // false: FP64 arithmetic (parity path); true: the reference's own precision
-    int solver = BOS_SOLVER_AUTO;      // Schur + dense Cholesky for small problems, Schur + block-Jacobi PCG for large ones
+    int solver = BOS_SOLVER_AUTO;      // Schur + dense Cholesky for small problems, Schur + preconditioned CG for large ones
     int dense_max_dim = 36000;
     int pcg_max_iters = 20000;
     double pcg_rtol = 1e-10;
+    int pcg_variant = 0;               // 0 persistent cooperative kernel, 1 classic multi-kernel loop
+    int pcg_precond = 0;               // 0 block-tridiagonal chain preconditioner, 1 3x3 block-Jacobi (see bos_b200.h)
 };
 
 class Solver {
