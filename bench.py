@@ -304,12 +304,12 @@ def run_ours(args):
     if solver == capi.SOLVER_PCG and pcg_iters > 0:
         # the dominant kernel of a step is the persistent PCG kernel (> 99 % of the step at synth-2M): one launch = one solve
         b_it = pcg_iteration_bytes(pr.NP, pr.NL, pr.Eb, S)
-        if args.pcg_precond == 0:   # chain preconditioner: 15 FP32 factor values per pose row are read every CG iteration
-            b_it += 15 * 4 * pr.NP
+        if args.pcg_precond != 1:   # chain preconditioner: 16 FP32 factor values per pose row are read every CG iteration
+            b_it += 16 * 4 * pr.NP
         ach = b_it * pcg_iters / (ms_solve * 1e-3) / 1e9
         t_it = traffic.get("pcg_dram_bytes_per_cg_iteration")
         roofline = {"kernel": "k_pcg_fused (persistent cooperative kernel: the whole %s PCG solve of one GN iteration)" %
-                              ("chain-preconditioned" if args.pcg_precond == 0 else "block-Jacobi"),
+                              ({0: "chain + coarse-space preconditioned", 1: "block-Jacobi", 2: "chain-preconditioned"}[args.pcg_precond]),
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": (t_it * pcg_iters) if t_it else None, "peak_source": peak_src,
                     "bytes_per_launch": b_it * pcg_iters, "bytes_per_cg_iteration": b_it, "cg_iterations_per_launch": pcg_iters,
@@ -324,7 +324,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": args.workload, "poses": pr.NP, "landmarks": pr.NL, "bearing_edges": pr.Eb, "odometry_edges": pr.Eo,
-                   "N": int(pi.N), "solver": ("schur+pcg(block-tridiagonal chain preconditioner)" if args.pcg_precond == 0 else "schur+block-jacobi-pcg")
+                   "N": int(pi.N), "solver": {0: "schur+pcg(block-tridiagonal chain + coarse-space preconditioner)", 1: "schur+block-jacobi-pcg",
+                              2: "schur+pcg(block-tridiagonal chain preconditioner)"}[args.pcg_precond]
                    if solver == capi.SOLVER_PCG else "schur+dense-cholesky",
                    "pcg_rtol": args.pcg_rtol, "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
                    (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)"}[args.reduce_mode]) if world > 1 else "single gpu",
@@ -345,7 +346,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         # the CPU port runs the reference-arm algorithm (3x3 block-Jacobi PCG): its own iteration count at this tolerance
         cpu_iters = int(round(line["pcg_iterations"]))
-        if solver == capi.SOLVER_PCG and args.pcg_precond == 0:
+        if solver == capi.SOLVER_PCG and args.pcg_precond != 1:
             cpu_iters = recorded_block_jacobi_iterations(args.workload, cpu_iters)
         cb = oracle_sample(w, pr, cpu_iters, args.pcg_rtol)
         line["cpu_baseline"] = {
@@ -379,7 +380,8 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--pcg-max-iters", type=int, default=20000)
-    ap.add_argument("--pcg-precond", type=int, default=0, choices=[0, 1], help="0 chain (block-tridiagonal) preconditioner, 1 3x3 block-Jacobi")
+    ap.add_argument("--pcg-precond", type=int, default=0, choices=[0, 1, 2],
+                    help="0 chain (block-tridiagonal) + coarse-space preconditioner, 1 3x3 block-Jacobi, 2 chain only")
     ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 2 for the PCG workloads, 1 for the dense ones")
     ap.add_argument("--ref-pcg-iters", type=int, default=0, help="CG iterations per GN step the reference arm extrapolates to "
                     "(0 = the count recorded by our arm in profiles/pcg_iterations.json, else 300)")

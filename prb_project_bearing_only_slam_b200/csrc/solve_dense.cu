@@ -403,6 +403,53 @@ __global__ void __launch_bounds__(256) k_copy_delta_p(const S* __restrict__ g, S
     if (i < n) delta[i] = g[i];
 }
 
+// Blocked Cholesky of the lower triangle of a column-major n x n matrix, in place (the strict upper triangle is not touched).
+// stats[5] is set when a pivot is not positive.  Returns the number of launches.
+template <typename S>
+int dense_cholesky_lower(S* Smat, int n, double* stats, cudaStream_t st) {
+    int nl = 0;
+    const size_t smem = 2 * (size_t)NB * LDT * sizeof(S);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_syrk_tiles<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(double)));
+        cudaFuncSetAttribute(k_syrk_tiles<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(float)));
+        attr_set = true;
+    }
+    constexpr int kOuter = 256;   // outer panel: the bulk of the matrix is updated once per kOuter columns
+    for (int c0 = 0; c0 < n; c0 += kOuter) {
+        const int cend = (c0 + kOuter < n) ? c0 + kOuter : n;
+        for (int k0 = c0; k0 < cend; k0 += NB) {
+            const int kb = (cend - k0 < NB) ? cend - k0 : NB;
+            k_potrf_diag<S><<<1, 256, 0, st>>>(Smat, n, k0, kb, stats); nl++;
+            const int r0 = k0 + kb;
+            if (r0 < n) {
+                k_trsm_panel<S><<<(n - r0 + 127) / 128, 128, 0, st>>>(Smat, n, k0, kb); nl++;
+                if (r0 < cend) {   // the outer panel's own remaining columns
+                    const int T = (n - r0 + NB - 1) / NB, TC = (cend - r0 + NB - 1) / NB;
+                    if (TC >= T) k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(Smat, n, k0, kb, r0, T, T);
+                    else k_syrk_tiles<S><<<dim3(T, TC), 128, smem, st>>>(Smat, n, k0, kb, r0, T, TC);
+                    nl++;
+                }
+            }
+        }
+        if (cend < n) {            // everything beyond the outer panel, once, with all of its columns
+            const int T = (n - cend + NB - 1) / NB;
+            if constexpr (sizeof(S) == 8) {
+                constexpr size_t smem_big = 2 * (size_t)(KC * LDA2 + KC * LDB2) * sizeof(double);
+                static bool big_attr = false;
+                if (!big_attr) { cudaFuncSetAttribute(k_syrk_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big); big_attr = true; }
+                k_syrk_big<<<dim3((n - cend + 127) / 128, T), 256, smem_big, st>>>(Smat, n, c0, cend - c0, cend);
+            } else {
+                k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(Smat, n, c0, cend - c0, cend, T, T);
+            }
+            nl++;
+        }
+    }
+    return nl;
+}
+template int dense_cholesky_lower<double>(double*, int, double*, cudaStream_t);
+template int dense_cholesky_lower<float>(float*, int, double*, cudaStream_t);
+
 template <typename S>
 int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStream_t st, int* launches) {
     (void)damping;
@@ -416,43 +463,7 @@ int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStr
         k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++;
         k_dense_schur<S><<<(d.NL * 32 + 255) / 256, 256, 0, st>>>(d, w.hllinv, w.ul, w.Smat, w.g, n); nl++;
     }
-    const size_t smem = 2 * (size_t)NB * LDT * sizeof(S);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_syrk_tiles<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(double)));
-        cudaFuncSetAttribute(k_syrk_tiles<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(float)));
-        attr_set = true;
-    }
-    constexpr int kOuter = 256;   // outer panel: the bulk of the matrix is updated once per kOuter columns
-    for (int c0 = 0; c0 < n; c0 += kOuter) {
-        const int cend = (c0 + kOuter < n) ? c0 + kOuter : n;
-        for (int k0 = c0; k0 < cend; k0 += NB) {
-            const int kb = (cend - k0 < NB) ? cend - k0 : NB;
-            k_potrf_diag<S><<<1, 256, 0, st>>>(w.Smat, n, k0, kb, d.stats); nl++;
-            const int r0 = k0 + kb;
-            if (r0 < n) {
-                k_trsm_panel<S><<<(n - r0 + 127) / 128, 128, 0, st>>>(w.Smat, n, k0, kb); nl++;
-                if (r0 < cend) {   // the outer panel's own remaining columns
-                    const int T = (n - r0 + NB - 1) / NB, TC = (cend - r0 + NB - 1) / NB;
-                    if (TC >= T) k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(w.Smat, n, k0, kb, r0, T, T);
-                    else k_syrk_tiles<S><<<dim3(T, TC), 128, smem, st>>>(w.Smat, n, k0, kb, r0, T, TC);
-                    nl++;
-                }
-            }
-        }
-        if (cend < n) {            // everything beyond the outer panel, once, with all of its columns
-            const int T = (n - cend + NB - 1) / NB;
-            if constexpr (sizeof(S) == 8) {
-                constexpr size_t smem_big = 2 * (size_t)(KC * LDA2 + KC * LDB2) * sizeof(double);
-                static bool big_attr = false;
-                if (!big_attr) { cudaFuncSetAttribute(k_syrk_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big); big_attr = true; }
-                k_syrk_big<<<dim3((n - cend + 127) / 128, T), 256, smem_big, st>>>(w.Smat, n, c0, cend - c0, cend);
-            } else {
-                k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(w.Smat, n, c0, cend - c0, cend, T, T);
-            }
-            nl++;
-        }
-    }
+    nl += dense_cholesky_lower<S>(w.Smat, n, d.stats, st);
     // forward substitution L y = g
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int kb = (n - k0 < NB) ? n - k0 : NB;

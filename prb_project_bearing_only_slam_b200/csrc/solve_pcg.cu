@@ -250,7 +250,7 @@ __global__ void k_pcg_promote(double* scal) {
 //            updates, z' = M^-1 r and the next gamma / delta parts follow in the same thread.
 enum { FS_GAMMA0 = 16, FS_DELTA0 = 19 };
 constexpr int kPcgRows = (2048 + kPcgThreads - 1) / kPcgThreads;   // chunk rows per thread (a chunk has at most 2048 poses)
-constexpr int kPcgSmemBudget = 226 * 1024;   // dynamic shared memory available to the persistent kernel
+constexpr int kPcgSmemBudget = 227 * 1024 - 6144;   // dynamic shared memory available to the persistent kernel (5.7 KB are static)
 
 // -DBOS_PCG_TIMING: thread 0 of a few CTAs prints clock64 deltas per phase (diagnostic builds only)
 #ifdef BOS_PCG_TIMING
@@ -280,6 +280,19 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         while (ld_acquire_u32(counter) < target) { }
 #endif
+    }
+    __syncthreads();
+}
+
+// split form: arrive early (after the CTA's contribution is written by thread 0), wait later; same counter protocol
+__device__ __forceinline__ void grid_arrive(unsigned* counter, unsigned& epoch) {
+    epoch++;
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned nblocks, unsigned epoch) {
+    if (threadIdx.x == 0) {
+        const unsigned target = epoch * nblocks;
+        while (ld_acquire_u32(counter) < target) { }
     }
     __syncthreads();
 }
@@ -364,7 +377,7 @@ __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) 
                 sd[0] -= q * jp[0] * jp[0]; sd[1] -= q * jp[0] * jp[1]; sd[2] -= q * jp[0] * jp[2];
                 sd[3] -= q * jp[1] * jp[1]; sd[4] -= q * jp[1] * jp[2]; sd[5] -= q * jp[2] * jp[2];
             }
-        if (w.precond == 0) {   // chain preconditioner: its diagonal block and the block that couples this row to the next chunk row
+        if (w.precond != 1) {   // chain preconditioner: its diagonal block and the block that couples this row to the next chunk row
             const int inext = (r + 1 < d.pc_cp) ? __ldg(d.pc_row_pose + R + 1) : -1;
             S o[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
             if (inext >= 0)
@@ -402,17 +415,17 @@ __global__ void __launch_bounds__(256) k_pcg_fused_prep(Dev<S> d, PcgWork<S> w) 
         }
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-            w.z4[4LL * i + a] = (a < 3 && w.precond != 0) ? z[a] : S(0);   // chain: the persistent kernel applies M^-1 to g itself
+            w.z4[4LL * i + a] = (a < 3 && w.precond == 1) ? z[a] : S(0);   // chain: the persistent kernel applies M^-1 to g itself
             w.z4[np4 + 4LL * i + a] = S(0);
         }
-        if (w.precond != 0) {
+        if (w.precond == 1) {
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 gz += (double)gg[a] * (double)z[a];
                 zw += (double)z[a] * (double)hz[a];
             }
         }
-    } else if (R < nrows && w.precond == 0) {   // padding row: identity block, no coupling
+    } else if (R < nrows && w.precond != 1) {   // padding row: identity block, no coupling
 #pragma unroll
         for (int k = 0; k < 6; k++) { w.chD[(size_t)k * nrows + R] = (k == 0 || k == 3 || k == 5) ? S(1) : S(0); w.chO[(size_t)k * nrows + R] = S(0); }
     }
@@ -784,6 +797,216 @@ __device__ __noinline__ void chain_apply(unsigned fac_off, unsigned r1_off, unsi
     }
 }
 
+// ---- coarse space of the chain preconditioner ---------------------------------------------------------------------------
+// The chunk-exact chain solve leaves the smooth, chunk-spanning error modes to CG.  They are taken by a coarse space of
+// piecewise-linear hats along the pose order: node c sits at the start of chunk c (pc_chunks + 1 nodes, 3 dof each); row r of
+// chunk c carries the weights 1 - t and t, t = (r + 1/2) / cp, for nodes c and c + 1 (zero for the fixed pose).  The coarse
+// operator is the Galerkin product A_c = P^T S P with the TRUE Schur complement, so it also sees the pose-pose coupling through
+// the landmarks; z = M_chunk^-1 r + P A_c^-1 P^T r (two-level additive Schwarz, SPD).  A_c is assembled once per solve:
+//   P^T Hpp P                      k_coarse_pose  (per chunk in registers, one set of atomics per chunk)
+//   - sum_l G_l^T Hll_l^-1 G_l     k_coarse_gtab (G per (chunk, landmark), shared-memory atomics) + k_coarse_lm (per landmark)
+// then factorised (dense_cholesky_lower) and inverted explicitly (k_coarse_inverse): applying it is a 6-row mat-vec per CTA.
+__device__ __forceinline__ float coarse_t(int r, int cp) { return ((float)r + 0.5f) / (float)cp; }
+
+template <typename S>
+__global__ void __launch_bounds__(256) k_coarse_gtab(Dev<S> d, PcgWork<S> w) {
+    extern __shared__ float gsm[];   // [ncl][12]
+    const int c = blockIdx.x, cp = d.pc_cp, gpc = cp / 32, lane = threadIdx.x & 31;
+    const int cl0 = __ldg(d.pc_cl_ptr + c), ncl = __ldg(d.pc_cl_ptr + c + 1) - cl0;
+    for (int k = threadIdx.x; k < ncl * 12; k += blockDim.x) gsm[k] = 0.f;
+    __syncthreads();
+    const S so_u = (S)w.sqrt_omega;
+    for (int g = threadIdx.x >> 5; g < gpc; g += blockDim.x >> 5) {
+        const int r = g * 32 + lane;
+        const int i = __ldg(d.pc_row_pose + (size_t)c * cp + r);
+        const int off = __ldg(d.pc_goff + (size_t)c * gpc + g), W = __ldg(d.pc_goff + (size_t)c * gpc + g + 1) - off;
+        if (i < 0 || i == d.fixed) continue;
+        S px, py;
+        load_lm<S>(d.pose, 2 * i, px, py);
+        const float t = coarse_t(r, cp), wl = 1.f - t, wr = t;
+        for (int q = 0; q < W; q++) {
+            const long long slot = ((long long)off + q) * 32 + lane;
+            const unsigned loc = d.pc_loc[slot];
+            if (loc == 0xffffu) continue;
+            const int row = __ldg(d.pc_cl_row + cl0 + (int)loc);
+            const S lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
+            S j0, j1;
+            bearing_jl_world<S>(px, py, lx, ly, j0, j1);
+            const S so = w.omega_uniform ? so_u : __ldg(w.Pw + slot);
+            j0 *= so; j1 *= so;
+            const float jp[3] = {(float)-j0, (float)-j1, (float)(j0 * ly - j1 * lx)};
+            float* gq = gsm + 12 * loc;
+#pragma unroll
+            for (int dd = 0; dd < 3; dd++) {
+                const float a0 = (float)j0 * jp[dd], a1 = (float)j1 * jp[dd];
+                atomicAdd(gq + dd, wl * a0); atomicAdd(gq + 3 + dd, wl * a1);
+                atomicAdd(gq + 6 + dd, wr * a0); atomicAdd(gq + 9 + dd, wr * a1);
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < ncl * 12; k += blockDim.x) w.cG[12LL * cl0 + k] = gsm[k];
+}
+
+// one thread per compact landmark row: node blocks of G_l (its chunks ascending; neighbouring chunks share a node), then the
+// lower triangle of -G^T Hll^-1 G into A_c.  A landmark seen from more than kCoarseMaxChunks chunks is left out altogether
+// (A_c only grows: still SPD).
+constexpr int kCoarseMaxChunks = 8;
+template <typename S>
+__global__ void __launch_bounds__(128) k_coarse_lm(Dev<S> d, PcgWork<S> w) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d.n_clm) return;
+    const int q0 = __ldg(d.lmc_ptr + k), m = __ldg(d.lmc_ptr + k + 1) - q0;
+    if (m <= 0 || m > kCoarseMaxChunks) return;
+    int nid[2 * kCoarseMaxChunks];
+    double G[2 * kCoarseMaxChunks][6];
+    int nn = 0;
+    for (int s = 0; s < m; s++) {
+        const int c = __ldg(d.lmc_chunk + q0 + s);
+        const float* g = w.cG + 12LL * __ldg(d.lmc_slot + q0 + s);
+        int a;
+        if (nn > 0 && nid[nn - 1] == c) a = nn - 1;
+        else { a = nn++; nid[a] = c; for (int e = 0; e < 6; e++) G[a][e] = 0.0; }
+        for (int e = 0; e < 6; e++) G[a][e] += (double)g[e];
+        const int b = nn++;
+        nid[b] = c + 1;
+        for (int e = 0; e < 6; e++) G[b][e] = (double)g[6 + e];
+    }
+    const double i00 = (double)w.hllinv_c[3LL * k], i01 = (double)w.hllinv_c[3LL * k + 1], i11 = (double)w.hllinv_c[3LL * k + 2];
+    const int nc = w.c_nc;
+    for (int a = 0; a < nn; a++) {
+        // T = Hll^-1 G[a] (2x3, rows x = 0, 1)
+        double T0[3], T1[3];
+        for (int e = 0; e < 3; e++) { T0[e] = i00 * G[a][e] + i01 * G[a][3 + e]; T1[e] = i01 * G[a][e] + i11 * G[a][3 + e]; }
+        for (int b = 0; b <= a; b++)
+            for (int dd = 0; dd < 3; dd++)
+                for (int e = 0; e < 3; e++) {
+                    if (a == b && e > dd) continue;
+                    // row (node a, dd), column (node b, e): G[a](:, dd)^T Hll^-1 G[b](:, e) by symmetry of Hll^-1
+                    const double v = T0[dd] * G[b][e] + T1[dd] * G[b][3 + e];
+                    atomicAdd(w.cA + (size_t)(3 * nid[a] + dd) + (size_t)(3 * nid[b] + e) * nc, -v);
+                }
+    }
+}
+
+// P^T Hpp P: one CTA per chunk.  Terms whose two poses lie in this chunk are summed in registers (lower triangle of the 6x6
+// block of nodes c, c + 1), the few that reach into another chunk (chunk-boundary odometry edges, loop closures) go straight
+// to A_c.  Every ordered pose pair (i, j) is visited once from i; a term is kept iff it lands on or below the diagonal.
+template <typename S>
+__global__ void __launch_bounds__(256) k_coarse_pose(Dev<S> d, PcgWork<S> w) {
+    __shared__ double red[8][21];
+    const int c = blockIdx.x, cp = d.pc_cp, nc = w.c_nc;
+    double acc[21];
+#pragma unroll
+    for (int q = 0; q < 21; q++) acc[q] = 0.0;
+    for (int r = threadIdx.x; r < cp; r += blockDim.x) {
+        const int i = __ldg(d.pc_row_pose + (size_t)c * cp + r);
+        if (i < 0 || i == d.fixed) continue;
+        const float t = coarse_t(r, cp);
+        const double wi[2] = {1.0 - (double)t, (double)t};
+        double H[9];
+        {
+            const S* hp = d.Hpp + 6LL * i;
+            H[0] = hp[0]; H[1] = hp[1]; H[2] = hp[2]; H[3] = hp[1]; H[4] = hp[3]; H[5] = hp[4]; H[6] = hp[2]; H[7] = hp[4]; H[8] = hp[5];
+        }
+#pragma unroll
+        for (int sa = 0; sa < 2; sa++)
+#pragma unroll
+            for (int sb = 0; sb < 2; sb++)
+#pragma unroll
+                for (int dd = 0; dd < 3; dd++)
+#pragma unroll
+                    for (int e = 0; e < 3; e++) {
+                        const int row = 3 * sa + dd, col = 3 * sb + e;
+                        if (row >= col) acc[row * (row + 1) / 2 + col] += wi[sa] * wi[sb] * H[3 * dd + e];
+                    }
+        for (int q = __ldg(d.pp_ptr + i); q < __ldg(d.pp_ptr + i + 1); q++) {
+            const int j = __ldg(d.pp_nbr + q);
+            if (j == d.fixed) continue;
+            const int sl = __ldg(d.pp_slot + q);
+            const S* Bo = d.Hoff + 9LL * (sl & 0x7fffffff);
+            // H_ij: the stored block is H[lo][hi]; sl >= 0 means i is the lo side
+#pragma unroll
+            for (int dd = 0; dd < 3; dd++)
+#pragma unroll
+                for (int e = 0; e < 3; e++) H[3 * dd + e] = (sl >= 0) ? (double)Bo[3 * dd + e] : (double)Bo[3 * e + dd];
+            const int cj = j / cp;
+            const float tj = coarse_t(j - cj * cp, cp);
+            const double wj[2] = {1.0 - (double)tj, (double)tj};
+            if (cj == c) {
+#pragma unroll
+                for (int sa = 0; sa < 2; sa++)
+#pragma unroll
+                    for (int sb = 0; sb < 2; sb++)
+#pragma unroll
+                        for (int dd = 0; dd < 3; dd++)
+#pragma unroll
+                            for (int e = 0; e < 3; e++) {
+                                const int row = 3 * sa + dd, col = 3 * sb + e;
+                                if (row >= col) acc[row * (row + 1) / 2 + col] += wi[sa] * wj[sb] * H[3 * dd + e];
+                            }
+            } else {
+                for (int sa = 0; sa < 2; sa++)
+                    for (int sb = 0; sb < 2; sb++)
+                        for (int dd = 0; dd < 3; dd++)
+                            for (int e = 0; e < 3; e++) {
+                                const int row = 3 * (c + sa) + dd, col = 3 * (cj + sb) + e;
+                                if (row >= col) atomicAdd(w.cA + (size_t)row + (size_t)col * nc, wi[sa] * wj[sb] * H[3 * dd + e]);
+                            }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 21; q++) {
+        const double v = warp_sum(acc[q]);
+        if (lane == 0) red[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 21) {
+        double v = 0.0;
+        for (int k = 0; k < 8; k++) v += red[k][threadIdx.x];
+        int row = 0;
+        while ((row + 1) * (row + 2) / 2 <= (int)threadIdx.x) row++;
+        const int col = threadIdx.x - row * (row + 1) / 2;
+        if (v != 0.0) atomicAdd(w.cA + (size_t)(3 * c + row) + (size_t)(3 * c + col) * nc, v);
+    }
+}
+
+// unsupported coarse dofs (empty chunks) get a unit diagonal: their residual is always zero
+__global__ void k_coarse_fix(double* A, int nc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nc && !(A[(size_t)j * nc + j] > 0.0)) A[(size_t)j * nc + j] = 1.0;
+}
+
+// explicit inverse from the Cholesky factor (column-major lower): one warp per column j, L y = e_j by column sweeps, L^T x = y
+// by dot products; the y / x vector lives in shared memory
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_coarse_inverse(const double* __restrict__ L, double* __restrict__ Ainv, int nc) {
+    extern __shared__ double vsh[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * WARPS + warp;
+    if (j >= nc) return;
+    double* v = vsh + (size_t)warp * nc;
+    for (int i = lane; i < nc; i += 32) v[i] = (i == j) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int k = j; k < nc; k++) {
+        const double yk = v[k] / L[(size_t)k + (size_t)k * nc];
+        __syncwarp();
+        if (lane == 0) v[k] = yk;
+        for (int i = k + 1 + lane; i < nc; i += 32) v[i] -= L[(size_t)i + (size_t)k * nc] * yk;
+        __syncwarp();
+    }
+    for (int i = nc - 1; i >= 0; i--) {
+        double sacc = 0.0;
+        for (int k = i + 1 + lane; k < nc; k += 32) sacc += L[(size_t)k + (size_t)i * nc] * v[k];
+        sacc = warp_sum(sacc);
+        if (lane == 0) v[i] = (v[i] - sacc) / L[(size_t)i + (size_t)i * nc];
+        __syncwarp();
+    }
+    for (int i = lane; i < nc; i += 32) Ainv[(size_t)j * nc + i] = v[i];
+}
+
 // shared-memory plan of the persistent kernel (per CTA = per chunk)
 template <typename S>
 struct PcgSmemPlan {
@@ -806,7 +1029,10 @@ template <typename S>
 __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2) {
     extern __shared__ __align__(16) unsigned char pcg_smem[];
     __shared__ double red[kPcgThreads / 32];
-    const bool chain = w.precond == 0;
+    __shared__ double red6[kPcgThreads / 32][6];
+    __shared__ double rc_s[3 * 160];    // coarse residual (3 * (chunks + 1) <= 480)
+    __shared__ double xc_s[6];          // coarse solution at this chunk's two nodes
+    const bool chain = w.precond != 1, coarse = w.precond == 0;
     const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, chain);
     const int cps = plan.cps, Kp = plan.Kp;
     S* vsm = reinterpret_cast<S*>(pcg_smem + plan.vec_off);
@@ -863,6 +1089,29 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     const float* zres = reinterpret_cast<const float*>(pcg_smem + ch_w2);
     auto precond_chain = [&](S* zdst, double& gacc, double& dacc2) {
         __syncthreads();
+        if (coarse) {   // this chunk's part of P^T r; the exchange over the grid overlaps the chain solve below
+            double c6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int h = 0; h < kPcgRows; h++) {
+                const int i = pose_i[h];
+                if (i < 0 || i == d.fixed) continue;
+                const float t = coarse_t(tid + h * kPcgThreads, cp);
+                const S* v = vsm + vx[h];
+#pragma unroll
+                for (int a = 0; a < 3; a++) { const double rv = (double)v[(6 + a) * cps]; c6[a] += (1.0 - (double)t) * rv; c6[3 + a] += (double)t * rv; }
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) { const double sv = warp_sum(c6[a]); if (lane == 0) red6[warp][a] = sv; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int a = 0; a < 6; a++) {
+                    double sv = 0.0;
+                    for (int k = 0; k < kPcgThreads / 32; k++) sv += red6[k][a];
+                    __stcg(w.cRc + 6LL * c + a, sv);
+                }
+            }
+            grid_arrive(w.bar, epoch);
+        }
         if (kWide) {
             float* c1 = reinterpret_cast<float*>(pcg_smem + ch_r1);
             float* c2 = reinterpret_cast<float*>(pcg_smem + ch_r2);
@@ -884,6 +1133,26 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
         if (tid < 64) chain_apply((unsigned)plan.rec_off, ch_r1, ch_w1, ch_r2, ch_w2, cps, Kp, cp / 32);
         __syncthreads();
         PCG_T(9);
+        if (coarse) {
+            grid_wait(w.bar, gridDim.x, epoch);
+            const int nc = w.c_nc;
+            for (int m = tid; m < nc; m += kPcgThreads) {
+                const int nd = m / 3, a = m - 3 * nd;
+                double rv = 0.0;
+                if (nd < grid) rv += __ldcg(w.cRc + 6LL * nd + a);
+                if (nd > 0) rv += __ldcg(w.cRc + 6LL * (nd - 1) + 3 + a);
+                rc_s[m] = rv;
+            }
+            __syncthreads();
+            if (warp < 6) {   // rows of A_c^-1 for nodes c (warps 0-2) and c + 1 (warps 3-5)
+                const double* arow = w.cAinv + (size_t)(3 * c + warp) * nc;
+                double sv = 0.0;
+                for (int m = lane; m < nc; m += 32) sv += __ldg(arow + m) * rc_s[m];
+                sv = warp_sum(sv);
+                if (lane == 0) xc_s[warp] = sv;
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int h = 0; h < kPcgRows; h++) {
             const int i = pose_i[h];
@@ -891,7 +1160,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             const int r = tid + h * kPcgThreads;
             const S* v = vsm + vx[h];
             const S r0 = v[6 * cps], r1 = v[7 * cps], r2 = v[8 * cps];
-            const S zn0 = (S)zres[vx[h]], zn1 = (S)zres[cps + vx[h]], zn2 = (S)zres[2 * cps + vx[h]];
+            S zn0 = (S)zres[vx[h]], zn1 = (S)zres[cps + vx[h]], zn2 = (S)zres[2 * cps + vx[h]];
+            if (coarse && i != d.fixed) {
+                const double t = (double)coarse_t(r, cp);
+                zn0 += (S)((1.0 - t) * xc_s[0] + t * xc_s[3]); zn1 += (S)((1.0 - t) * xc_s[1] + t * xc_s[4]); zn2 += (S)((1.0 - t) * xc_s[2] + t * xc_s[5]);
+            }
             const S* hp = w.rowS + (size_t)c * cp + r;
             const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
                     h5 = __ldg(hp + 5 * nrows);
@@ -1146,12 +1419,35 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     cudaMemsetAsync(w.xS, 0, 3 * (size_t)nrows * sizeof(S), st);
     if (d.NL > 0) { k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++; }
     if (d.n_clm > 0) { k_ell_fill<S><<<(d.n_clm + 255) / 256, 256, 0, st>>>(d, w); nl++; }
-    const int precond = (w.precond == 0 && pcg_chain_supported<S>(d)) ? 0 : 1;
+    int precond = (w.precond != 1 && pcg_chain_supported<S>(d)) ? w.precond : 1;
+    if (precond == 0 && w.c_nc > 3 * 160) precond = 2;
     const int precond_asked = w.precond;
     w.precond = precond;
     k_pcg_fused_prep<S><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(d, w); nl++;
-    if (precond == 0) { k_pcg_chain_factor<S><<<d.pc_chunks, 64, 0, st>>>(d, w); nl++; }
-    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, precond == 0);
+    if (precond != 1) { k_pcg_chain_factor<S><<<d.pc_chunks, 64, 0, st>>>(d, w); nl++; }
+    if (precond == 0) {   // coarse operator A_c = P^T S P, its Cholesky factor and explicit inverse
+        const int nc = w.c_nc;
+        cudaMemsetAsync(w.cA, 0, sizeof(double) * (size_t)nc * nc, st);
+        cudaMemsetAsync(w.cStats, 0, sizeof(double) * 8, st);
+        if (d.n_clm > 0) {
+            const size_t gsm = sizeof(float) * 12 * (size_t)(d.pc_cl_max > 0 ? d.pc_cl_max : 1);
+            static size_t gconf[2] = {0, 0};
+            size_t& gc = gconf[sizeof(S) == 8 ? 0 : 1];
+            if (gsm > gc) {
+                if (cudaFuncSetAttribute(k_coarse_gtab<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess) return -1;
+                gc = gsm;
+            }
+            k_coarse_gtab<S><<<d.pc_chunks, 256, gsm, st>>>(d, w); nl++;
+            k_coarse_lm<S><<<(d.n_clm + 127) / 128, 128, 0, st>>>(d, w); nl++;
+        }
+        k_coarse_pose<S><<<d.pc_chunks, 256, 0, st>>>(d, w); nl++;
+        k_coarse_fix<<<(nc + 127) / 128, 128, 0, st>>>(w.cA, nc); nl++;
+        nl += dense_cholesky_lower<double>(w.cA, nc, w.cStats, st);
+        constexpr int IW = 4;
+        const size_t ism = sizeof(double) * IW * (size_t)nc;
+        k_coarse_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cA, w.cAinv, nc); nl++;
+    }
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, precond != 1);
     static size_t configured[2] = {0, 0};
     size_t& conf = configured[sizeof(S) == 8 ? 0 : 1];
     if (plan.bytes > conf) {

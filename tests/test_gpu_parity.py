@@ -372,7 +372,8 @@ def test_pcg_fused_kernel_equals_classic_loop(built_lib, uniform_omega):
     P, L0 = o.state()
     L = np.vstack([L0, [[1.0, 2.0], [3.0, 4.0]]])
     ds, its = [], []
-    for variant, precond in ((0, 0), (0, 1), (1, 1)):   # fused + chain preconditioner, fused + 3x3 block-Jacobi, classic loop
+    # fused + chain + coarse space, fused + 3x3 block-Jacobi, classic loop, fused + chain only
+    for variant, precond in ((0, 0), (0, 1), (1, 1), (0, 2)):
         ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-12, pcg_max_iters=20000, pcg_variant=variant, pcg_precond=precond)
         ctx.linearize(); ctx.solve()
         ds.append(ctx.delta()); its.append(ctx.stats().pcg_iterations)
@@ -385,10 +386,11 @@ def test_pcg_fused_kernel_equals_classic_loop(built_lib, uniform_omega):
             assert np.abs(r).max() <= 1e-9 * np.abs(b).max()
     assert np.abs(ds[0] - ds[2]).max() <= 1e-8 * np.abs(ds[2]).max()
     assert np.abs(ds[1] - ds[2]).max() <= 1e-8 * np.abs(ds[2]).max()
+    assert np.abs(ds[3] - ds[2]).max() <= 1e-8 * np.abs(ds[2]).max()
     for d_ in ds:
         assert np.all(d_[-4:] == 0.0)                                                    # unobserved landmarks: b_l = 0 -> dx_l = 0
     assert its[1] > 0 and abs(its[1] - its[2]) <= 0.2 * its[2] + 5
-    assert 0 < its[0] < 0.5 * its[1]                                                     # the chain preconditioner pays
+    assert 0 < its[3] < 0.5 * its[1] and 0 < its[0] <= its[3]                            # the chain preconditioner pays, the coarse space too
 
 
 def test_pcg_chain_preconditioner_many_groups_and_loop_closures(built_lib):
@@ -414,7 +416,7 @@ def test_pcg_chain_preconditioner_many_groups_and_loop_closures(built_lib):
     o = oracle_for(w["pose_ids"], w["poses_init"], pr0)
     P, L = o.state()
     ds, its = [], []
-    for precond in (0, 1):
+    for precond in (0, 1, 2):
         ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-11, pcg_max_iters=20000, pcg_precond=precond)
         ctx.linearize(); ctx.solve()
         ds.append(ctx.delta()); its.append(ctx.stats().pcg_iterations)
@@ -423,8 +425,9 @@ def test_pcg_chain_preconditioner_many_groups_and_loop_closures(built_lib):
         H = sp.csc_matrix((val, rowidx, colptr), shape=(n, n))
         r = H @ nofixed(pr, ds[-1]) + b
         assert np.abs(r).max() <= 1e-8 * np.abs(b).max()
-    assert np.abs(ds[0] - ds[1]).max() <= 1e-7 * np.abs(ds[1]).max()
-    assert 0 < its[0] < 0.25 * its[1]
+    assert np.abs(ds[0] - ds[1]).max() <= 1e-7 * np.abs(ds[1]).max() and np.abs(ds[2] - ds[1]).max() <= 1e-7 * np.abs(ds[1]).max()
+    assert 0 < its[2] < 0.25 * its[1] and 0 < its[0] < its[2]
+    print("cg iterations: chain+coarse %d, block-jacobi %d, chain %d" % tuple(its))
     chi = []
     ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-8)
     for _ in range(3):
