@@ -82,9 +82,6 @@ struct Dev {
     const int* pc_goff = nullptr;          // [pc_chunks * pc_cp / 32 + 1] column offset of each group of 32 rows
     const int* pc_cl_ptr = nullptr;        // [pc_chunks + 1] the chunk's distinct landmark rows ...
     const int* pc_cl_row = nullptr;        // ... ascending compact landmark row ids
-    const int* lmc_ptr = nullptr;          // [n_clm + 1] per compact landmark row: its entries in the chunks' landmark tables ...
-    const int* lmc_slot = nullptr;         // ... index into pc_cl_row (ascending chunk)
-    const int* lmc_chunk = nullptr;        // ... and the chunk of that entry
     const unsigned short* pc_loc = nullptr;  // [nPs] index into the chunk's landmark table, 0xffff for padding
     const int* pc_emap = nullptr;          // [nPs] sorted bearing-edge index of the slot, -1 for padding
     const int* pc_nbr = nullptr;           // [2][pc_chunks * pc_cp] first two pose-pose neighbours of the row (-1: none)
@@ -185,7 +182,6 @@ struct PcgWork {
     // coarse space of the chain preconditioner: piecewise-linear hats over the chunks (node c = start of chunk c, 3 dof per
     // node), Galerkin operator A_c = P^T S P assembled and inverted once per solve; z = M_chunk^-1 r + P A_c^-1 P^T r
     int c_nc = 0;            // 3 * (pc_chunks + 1)
-    float* cG = nullptr;     // [pc_cl_row entries][12] per (chunk, landmark): sum_k w_k Jl_k^T omega Jp_k for the chunk's two nodes
     double* cA = nullptr;    // [c_nc][c_nc] column-major lower: A_c, then its Cholesky factor
     double* cAinv = nullptr; // [c_nc][c_nc] A_c^-1 (full, symmetric)
     double* cRc = nullptr;   // [pc_chunks][6] per chunk: P^T r restricted to its rows (left node, right node)
@@ -238,7 +234,7 @@ struct HostPattern {
     std::vector<int> pl_lm_id, b_row, ell_Loff, ell_Lmap, ell_Lpose;
     int pc_chunks = 0, pc_cp = 0;
     bool pc_ok = false;
-    std::vector<int> pc_row_pose, pc_goff, pc_cl_ptr, pc_cl_row, pc_emap, pc_nbr, pc_nslot, pc_ncnt, lmc_ptr, lmc_slot, lmc_chunk;
+    std::vector<int> pc_row_pose, pc_goff, pc_cl_ptr, pc_cl_row, pc_emap, pc_nbr, pc_nslot, pc_ncnt;
     std::vector<unsigned short> pc_loc;
     std::vector<int> tile_ptr, tg_lm, tg_eptr, epose_ptr;
     std::vector<unsigned short> tg_edge;

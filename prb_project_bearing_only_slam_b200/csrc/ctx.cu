@@ -231,7 +231,6 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(pl_lm_id, P.pl_lm_id) UP(ell_Loff, P.ell_Loff) UP(ell_Lpose, P.ell_Lpose)
     UP(pc_row_pose, P.pc_row_pose) UP(pc_goff, P.pc_goff) UP(pc_cl_ptr, P.pc_cl_ptr) UP(pc_cl_row, P.pc_cl_row) UP(pc_loc, P.pc_loc)
     UP(pc_emap, P.pc_emap) UP(pc_nbr, P.pc_nbr) UP(pc_nslot, P.pc_nslot) UP(pc_ncnt, P.pc_ncnt)
-    UP(lmc_ptr, P.lmc_ptr) UP(lmc_slot, P.lmc_slot) UP(lmc_chunk, P.lmc_chunk)
     d.n_clm = (int)P.pl_lm_id.size(); d.nLg = (int)P.ell_Loff.size() - 1;
     d.nLs = (long long)P.ell_Lmap.size(); d.nPs = (long long)P.pc_loc.size();
     d.pc_chunks = P.pc_chunks; d.pc_cp = P.pc_cp; d.pc_ok = P.pc_ok ? 1 : 0;
@@ -336,12 +335,11 @@ int ensure_pcg(bos_ctx* c) {
         w.chF = c->mem.get<float>((size_t)std::max(d.pc_chunks, 1) * w.ch_fac_floats);
         if (!w.chD || !w.chO || !w.chF) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
         w.c_nc = 3 * (d.pc_chunks + 1);
-        w.cG = c->mem.get<float>(12 * std::max<size_t>(c->P.pc_cl_row.size(), 1));
         w.cA = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
         w.cAinv = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
         w.cRc = c->mem.get<double>(6 * (size_t)std::max(d.pc_chunks, 1));
         w.cStats = c->mem.get<double>(8);
-        if (!w.cG || !w.cA || !w.cAinv || !w.cRc || !w.cStats) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+        if (!w.cA || !w.cAinv || !w.cRc || !w.cStats) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
     }
     w.xS = c->mem.get<S>(3 * (size_t)d.pc_chunks * d.pc_cp);
     if (!w.hllinv_c || !w.ul4 || !w.z4 || !w.rS || !w.xS || !w.rowS) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");

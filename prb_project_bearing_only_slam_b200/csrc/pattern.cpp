@@ -164,16 +164,6 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
                 }
             }
         }
-        // per landmark row: where it appears in the chunks' tables (coarse-space assembly walks a landmark's chunks)
-        P.lmc_ptr.assign((size_t)n_clm + 1, 0);
-        for (int row : P.pc_cl_row) P.lmc_ptr[row + 1]++;
-        for (int r = 0; r < n_clm; r++) P.lmc_ptr[r + 1] += P.lmc_ptr[r];
-        P.lmc_slot.assign(P.pc_cl_row.size(), 0); P.lmc_chunk.assign(P.pc_cl_row.size(), 0);
-        {
-            std::vector<int> cur(P.lmc_ptr.begin(), P.lmc_ptr.end() - 1);
-            for (int c = 0; c < nch; c++)
-                for (int q = P.pc_cl_ptr[c]; q < P.pc_cl_ptr[c + 1]; q++) { const int at = cur[P.pc_cl_row[q]]++; P.lmc_slot[at] = q; P.lmc_chunk[at] = c; }
-        }
         // up to two pose-pose neighbours per row inline (filled once the adjacency exists, below)
         P.pc_nbr.assign((size_t)nch * cp * 2, -1);
         P.pc_nslot.assign((size_t)nch * cp * 2, 0);

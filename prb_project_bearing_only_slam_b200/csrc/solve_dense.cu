@@ -84,47 +84,59 @@ __global__ void __launch_bounds__(256) k_dense_schur(Dev<S> d, const S* __restri
 }
 
 // ---- blocked Cholesky ---------------------------------------------------------------------------------
-// diagonal block: unblocked Cholesky in shared memory, one CTA
+// diagonal block: unblocked right-looking Cholesky in shared memory, one CTA, ONE barrier per column.  Thread (r, q) = (tid / 4,
+// tid % 4) updates the entries c = j + 1 + q, j + 5 + q, ... of row r with the UNSCALED column j:
+// A[r][c] -= A[r][j] A[c][j] / A[j][j]; column j itself is scaled by 1 / sqrt(A[j][j]) after the barrier (nobody reads it again).
 template <typename S>
 __global__ void __launch_bounds__(256) k_potrf_diag(S* __restrict__ Sm, int n, int k0, int kb, double* __restrict__ stats) {
-    __shared__ S A[NB][NB + 1];  // A[col][row]
+    __shared__ S A[NB][NB + 1];  // A[row][col]
     for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
         int c = t / kb, r = t % kb;
-        A[c][r] = Sm[(size_t)(k0 + r) + (size_t)(k0 + c) * n];
+        A[r][c] = (r >= c) ? Sm[(size_t)(k0 + r) + (size_t)(k0 + c) * n] : S(0);
     }
     __syncthreads();
+    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+    S sprev = S(1);
     for (int j = 0; j < kb; j++) {
-        if (threadIdx.x == 0) {
-            S dj = A[j][j];
-            if (!(dj > S(0))) { stats[5] = 1.0; dj = (dj < S(0)) ? -dj : S(1e-30); }
-            A[j][j] = sqrt(dj);
+        S p = A[j][j];
+        if (!(p > S(0))) { if (threadIdx.x == 0) stats[5] = 1.0; p = (p < S(0)) ? -p : S(1e-30); }
+        const S s = (S)rsqrt((double)p);
+        if (j > 0 && q == 0 && r >= j - 1 && r < kb) A[r][j - 1] *= sprev;     // finish column j - 1 (diagonal: p_prev * s_prev = sqrt)
+        if (r > j && r < kb) {
+            const S f = A[r][j] * (s * s);
+            int c = j + 1 + q;
+            for (; c + 12 <= r; c += 16) {   // four independent updates in flight
+                const S a0 = A[c][j], a1 = A[c + 4][j], a2 = A[c + 8][j], a3 = A[c + 12][j];
+                const S b0 = A[r][c], b1 = A[r][c + 4], b2 = A[r][c + 8], b3 = A[r][c + 12];
+                A[r][c] = b0 - f * a0; A[r][c + 4] = b1 - f * a1; A[r][c + 8] = b2 - f * a2; A[r][c + 12] = b3 - f * a3;
+            }
+            for (; c <= r; c += 4) A[r][c] -= f * A[c][j];
         }
-        __syncthreads();
-        const S inv = S(1) / A[j][j];
-        for (int i = j + 1 + threadIdx.x; i < kb; i += blockDim.x) A[j][i] *= inv;
-        __syncthreads();
-        // trailing update of columns j+1..kb-1
-        const int i = threadIdx.x & (NB - 1);
-        for (int k = j + 1 + (threadIdx.x >> 6); k < kb; k += (blockDim.x >> 6))
-            if (i >= k && i < kb) A[k][i] -= A[j][i] * A[j][k];
+        sprev = s;
         __syncthreads();
     }
+    if (q == 0 && r == kb - 1) A[r][kb - 1] *= sprev;
+    __syncthreads();
     for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
-        int c = t / kb, r = t % kb;
-        if (r >= c) Sm[(size_t)(k0 + r) + (size_t)(k0 + c) * n] = A[c][r];
+        int c = t / kb, rr = t % kb;
+        if (rr >= c) Sm[(size_t)(k0 + rr) + (size_t)(k0 + c) * n] = A[rr][c];
     }
 }
 
-// panel: A[i, k0:k0+kb] <- A[i, k0:k0+kb] * L_kk^-T, one thread per row below the diagonal block
+// panel: A[i, k0:k0+kb] <- A[i, k0:k0+kb] * L_kk^-T, one thread per row below the diagonal block.  Column-oriented: once x[m] is
+// final, the updates of x[m+1..] are independent FMAs (the dependent chain is one multiply per column, not the whole dot product).
 template <typename S>
 __global__ void __launch_bounds__(128) k_trsm_panel(S* __restrict__ Sm, int n, int k0, int kb) {
     __shared__ S L[NB][NB + 1];  // L[row j][col m]
+    __shared__ S rd[NB];
     for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
-        int j = t / NB, m = t % NB;
+        int j = t % NB, m = t / NB;   // consecutive threads walk down a column: coalesced
         S v = (j == m) ? S(1) : S(0);
         if (j < kb && m <= j) v = Sm[(size_t)(k0 + j) + (size_t)(k0 + m) * n];
         L[j][m] = v;
     }
+    __syncthreads();
+    if (threadIdx.x < NB) rd[threadIdx.x] = S(1) / L[threadIdx.x][threadIdx.x];
     __syncthreads();
     const int i = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -132,11 +144,10 @@ __global__ void __launch_bounds__(128) k_trsm_panel(S* __restrict__ Sm, int n, i
 #pragma unroll
     for (int j = 0; j < NB; j++) x[j] = (j < kb) ? Sm[(size_t)i + (size_t)(k0 + j) * n] : S(0);
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        S s = x[j];
+    for (int m = 0; m < NB; m++) {
+        x[m] *= rd[m];
 #pragma unroll
-        for (int m = 0; m < j; m++) s -= x[m] * L[j][m];
-        x[j] = s / L[j][j];
+        for (int j = m + 1; j < NB; j++) x[j] -= x[m] * L[j][m];
     }
 #pragma unroll
     for (int j = 0; j < NB; j++)

@@ -804,85 +804,76 @@ __device__ __noinline__ void chain_apply(unsigned fac_off, unsigned r1_off, unsi
 // operator is the Galerkin product A_c = P^T S P with the TRUE Schur complement, so it also sees the pose-pose coupling through
 // the landmarks; z = M_chunk^-1 r + P A_c^-1 P^T r (two-level additive Schwarz, SPD).  A_c is assembled once per solve:
 //   P^T Hpp P                      k_coarse_pose  (per chunk in registers, one set of atomics per chunk)
-//   - sum_l G_l^T Hll_l^-1 G_l     k_coarse_gtab (G per (chunk, landmark), shared-memory atomics) + k_coarse_lm (per landmark)
+//   - sum_l G_l^T Hll_l^-1 G_l     k_coarse_lm    (one thread per landmark walks its edges)
 // then factorised (dense_cholesky_lower) and inverted explicitly (k_coarse_inverse): applying it is a 6-row mat-vec per CTA.
 __device__ __forceinline__ float coarse_t(int r, int cp) { return ((float)r + 0.5f) / (float)cp; }
 
-template <typename S>
-__global__ void __launch_bounds__(256) k_coarse_gtab(Dev<S> d, PcgWork<S> w) {
-    extern __shared__ float gsm[];   // [ncl][12]
-    const int c = blockIdx.x, cp = d.pc_cp, gpc = cp / 32, lane = threadIdx.x & 31;
-    const int cl0 = __ldg(d.pc_cl_ptr + c), ncl = __ldg(d.pc_cl_ptr + c + 1) - cl0;
-    for (int k = threadIdx.x; k < ncl * 12; k += blockDim.x) gsm[k] = 0.f;
-    __syncthreads();
-    const S so_u = (S)w.sqrt_omega;
-    for (int g = threadIdx.x >> 5; g < gpc; g += blockDim.x >> 5) {
-        const int r = g * 32 + lane;
-        const int i = __ldg(d.pc_row_pose + (size_t)c * cp + r);
-        const int off = __ldg(d.pc_goff + (size_t)c * gpc + g), W = __ldg(d.pc_goff + (size_t)c * gpc + g + 1) - off;
-        if (i < 0 || i == d.fixed) continue;
-        S px, py;
-        load_lm<S>(d.pose, 2 * i, px, py);
-        const float t = coarse_t(r, cp), wl = 1.f - t, wr = t;
-        for (int q = 0; q < W; q++) {
-            const long long slot = ((long long)off + q) * 32 + lane;
-            const unsigned loc = d.pc_loc[slot];
-            if (loc == 0xffffu) continue;
-            const int row = __ldg(d.pc_cl_row + cl0 + (int)loc);
-            const S lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
-            S j0, j1;
-            bearing_jl_world<S>(px, py, lx, ly, j0, j1);
-            const S so = w.omega_uniform ? so_u : __ldg(w.Pw + slot);
-            j0 *= so; j1 *= so;
-            const float jp[3] = {(float)-j0, (float)-j1, (float)(j0 * ly - j1 * lx)};
-            float* gq = gsm + 12 * loc;
-#pragma unroll
-            for (int dd = 0; dd < 3; dd++) {
-                const float a0 = (float)j0 * jp[dd], a1 = (float)j1 * jp[dd];
-                atomicAdd(gq + dd, wl * a0); atomicAdd(gq + 3 + dd, wl * a1);
-                atomicAdd(gq + 6 + dd, wr * a0); atomicAdd(gq + 9 + dd, wr * a1);
-            }
-        }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < ncl * 12; k += blockDim.x) w.cG[12LL * cl0 + k] = gsm[k];
-}
-
-// one thread per compact landmark row: node blocks of G_l (its chunks ascending; neighbouring chunks share a node), then the
-// lower triangle of -G^T Hll^-1 G into A_c.  A landmark seen from more than kCoarseMaxChunks chunks is left out altogether
-// (A_c only grows: still SPD).
+// one thread per compact landmark row.  Its edges come in ascending pose order (sliced-ELL row), so the chunk index never
+// decreases: the edges of one chunk are summed into G (2 x 3 per node: rows = the two components of Jl, weighted by the hat
+// weights of the pose), neighbouring chunks share a node; then the lower triangle of -G^T Hll^-1 G goes into A_c.  A landmark
+// seen from more than kCoarseMaxChunks chunks is left out altogether (A_c only grows: still SPD).
 constexpr int kCoarseMaxChunks = 8;
 template <typename S>
 __global__ void __launch_bounds__(128) k_coarse_lm(Dev<S> d, PcgWork<S> w) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d.n_clm) return;
-    const int q0 = __ldg(d.lmc_ptr + k), m = __ldg(d.lmc_ptr + k + 1) - q0;
-    if (m <= 0 || m > kCoarseMaxChunks) return;
-    int nid[2 * kCoarseMaxChunks];
+    constexpr int RPG = 32 / kEllLanesL;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= d.n_clm) return;
+    const int g = row / RPG, lane0 = (row % RPG) * kEllLanesL, cp = d.pc_cp;
+    const int off = __ldg(d.ell_Loff + g), W = __ldg(d.ell_Loff + g + 1) - off;
+    const S lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
+    const S so_u = (S)w.sqrt_omega;
+    int nid[2 * kCoarseMaxChunks] = {0};
     double G[2 * kCoarseMaxChunks][6];
-    int nn = 0;
-    for (int s = 0; s < m; s++) {
-        const int c = __ldg(d.lmc_chunk + q0 + s);
-        const float* g = w.cG + 12LL * __ldg(d.lmc_slot + q0 + s);
+    int nn = 0, cur = -1;
+    bool over = false;
+    double acc[12];
+    auto flush = [&]() {
+        if (cur < 0) return;
+        if (nn + 2 > 2 * kCoarseMaxChunks) { over = true; return; }
         int a;
-        if (nn > 0 && nid[nn - 1] == c) a = nn - 1;
-        else { a = nn++; nid[a] = c; for (int e = 0; e < 6; e++) G[a][e] = 0.0; }
-        for (int e = 0; e < 6; e++) G[a][e] += (double)g[e];
+        if (nn > 0 && nid[nn - 1] == cur) a = nn - 1;
+        else { a = nn++; nid[a] = cur; for (int e = 0; e < 6; e++) G[a][e] = 0.0; }
+        for (int e = 0; e < 6; e++) G[a][e] += acc[e];
         const int b = nn++;
-        nid[b] = c + 1;
-        for (int e = 0; e < 6; e++) G[b][e] = (double)g[6 + e];
-    }
-    const double i00 = (double)w.hllinv_c[3LL * k], i01 = (double)w.hllinv_c[3LL * k + 1], i11 = (double)w.hllinv_c[3LL * k + 2];
+        nid[b] = cur + 1;
+        for (int e = 0; e < 6; e++) G[b][e] = acc[6 + e];
+    };
+    for (int tb = 0; tb < W; tb++)
+        for (int q = 0; q < kEllLanesL; q++) {
+            const long long slot = ((long long)off + tb) * 32 + lane0 + q;
+            const int ps = __ldg(d.ell_Lpose + slot);
+            if (ps < 0) continue;                                   // padding, or an edge of the fixed pose
+            const int c = ps / cp;
+            if (c != cur) {
+                flush();
+                cur = c;
+                for (int e = 0; e < 12; e++) acc[e] = 0.0;
+            }
+            S px, py;
+            load_lm<S>(d.pose, 2 * ps, px, py);
+            S j0, j1;
+            bearing_jl_world<S>(px, py, lx, ly, j0, j1);
+            const S so = w.omega_uniform ? so_u : __ldg(w.Lw + slot);
+            j0 *= so; j1 *= so;
+            const double jp[3] = {(double)-j0, (double)-j1, (double)(j0 * ly - j1 * lx)};
+            const double t = (double)coarse_t(ps - c * cp, cp), wl = 1.0 - t;
+            for (int dd = 0; dd < 3; dd++) {
+                const double a0 = (double)j0 * jp[dd], a1 = (double)j1 * jp[dd];
+                acc[dd] += wl * a0; acc[3 + dd] += wl * a1; acc[6 + dd] += t * a0; acc[9 + dd] += t * a1;
+            }
+        }
+    flush();
+    if (over || nn == 0) return;
+    const double i00 = (double)w.hllinv_c[3LL * row], i01 = (double)w.hllinv_c[3LL * row + 1], i11 = (double)w.hllinv_c[3LL * row + 2];
     const int nc = w.c_nc;
     for (int a = 0; a < nn; a++) {
-        // T = Hll^-1 G[a] (2x3, rows x = 0, 1)
-        double T0[3], T1[3];
+        double T0[3], T1[3];   // Hll^-1 G[a]
         for (int e = 0; e < 3; e++) { T0[e] = i00 * G[a][e] + i01 * G[a][3 + e]; T1[e] = i01 * G[a][e] + i11 * G[a][3 + e]; }
         for (int b = 0; b <= a; b++)
             for (int dd = 0; dd < 3; dd++)
                 for (int e = 0; e < 3; e++) {
                     if (a == b && e > dd) continue;
-                    // row (node a, dd), column (node b, e): G[a](:, dd)^T Hll^-1 G[b](:, e) by symmetry of Hll^-1
+                    // row (node a, dd), column (node b, e): G[a](:, dd)^T Hll^-1 G[b](:, e)
                     const double v = T0[dd] * G[b][e] + T1[dd] * G[b][3 + e];
                     atomicAdd(w.cA + (size_t)(3 * nid[a] + dd) + (size_t)(3 * nid[b] + e) * nc, -v);
                 }
@@ -980,7 +971,8 @@ __global__ void k_coarse_fix(double* A, int nc) {
 }
 
 // explicit inverse from the Cholesky factor (column-major lower): one warp per column j, L y = e_j by column sweeps, L^T x = y
-// by dot products; the y / x vector lives in shared memory
+// by dot products; the y / x vector lives in shared memory, the next column of L is in registers before the current step ends
+constexpr int kCoarseMaxPerLane = 15;   // ceil(3 * 160 / 32)
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_coarse_inverse(const double* __restrict__ L, double* __restrict__ Ainv, int nc) {
     extern __shared__ double vsh[];
@@ -990,19 +982,50 @@ __global__ void __launch_bounds__(WARPS * 32) k_coarse_inverse(const double* __r
     double* v = vsh + (size_t)warp * nc;
     for (int i = lane; i < nc; i += 32) v[i] = (i == j) ? 1.0 : 0.0;
     __syncwarp();
+    double col[kCoarseMaxPerLane], nxt[kCoarseMaxPerLane];
+    auto fetch = [&](int k, double* dst) {   // column k from its diagonal down: entry k + lane + 32 q
+#pragma unroll
+        for (int q = 0; q < kCoarseMaxPerLane; q++) {
+            const int i = k + lane + 32 * q;
+            dst[q] = (k < nc && i < nc) ? __ldg(L + (size_t)i + (size_t)k * nc) : 0.0;   // predicated off beyond the column's end
+        }
+    };
+    fetch(j, col);
     for (int k = j; k < nc; k++) {
-        const double yk = v[k] / L[(size_t)k + (size_t)k * nc];
+        fetch(k + 1, nxt);
+        const double dkk = __shfl_sync(0xffffffffu, col[0], 0);
+        const double yk = v[k] / dkk;
+        const int cnt = (nc - k + 31) / 32;                       // live entries per lane (warp-uniform)
         __syncwarp();
-        if (lane == 0) v[k] = yk;
-        for (int i = k + 1 + lane; i < nc; i += 32) v[i] -= L[(size_t)i + (size_t)k * nc] * yk;
+#pragma unroll
+        for (int q = 0; q < kCoarseMaxPerLane; q++) {
+            if (q < cnt) {
+                const int i = k + lane + 32 * q;
+                if (i < nc) v[i] = (i == k) ? yk : v[i] - col[q] * yk;
+            }
+        }
         __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kCoarseMaxPerLane; q++) col[q] = nxt[q];
     }
+    fetch(nc - 1, col);
     for (int i = nc - 1; i >= 0; i--) {
+        fetch(i - 1 >= 0 ? i - 1 : nc, nxt);
+        const int cnt = (nc - i + 31) / 32;
         double sacc = 0.0;
-        for (int k = i + 1 + lane; k < nc; k += 32) sacc += L[(size_t)k + (size_t)i * nc] * v[k];
+#pragma unroll
+        for (int q = 0; q < kCoarseMaxPerLane; q++) {
+            if (q < cnt) {
+                const int k = i + lane + 32 * q;
+                if (k > i && k < nc) sacc += col[q] * v[k];
+            }
+        }
         sacc = warp_sum(sacc);
-        if (lane == 0) v[i] = (v[i] - sacc) / L[(size_t)i + (size_t)i * nc];
+        const double dii = __shfl_sync(0xffffffffu, col[0], 0);
+        if (lane == 0) v[i] = (v[i] - sacc) / dii;
         __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kCoarseMaxPerLane; q++) col[q] = nxt[q];
     }
     for (int i = lane; i < nc; i += 32) Ainv[(size_t)j * nc + i] = v[i];
 }
@@ -1429,17 +1452,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
         const int nc = w.c_nc;
         cudaMemsetAsync(w.cA, 0, sizeof(double) * (size_t)nc * nc, st);
         cudaMemsetAsync(w.cStats, 0, sizeof(double) * 8, st);
-        if (d.n_clm > 0) {
-            const size_t gsm = sizeof(float) * 12 * (size_t)(d.pc_cl_max > 0 ? d.pc_cl_max : 1);
-            static size_t gconf[2] = {0, 0};
-            size_t& gc = gconf[sizeof(S) == 8 ? 0 : 1];
-            if (gsm > gc) {
-                if (cudaFuncSetAttribute(k_coarse_gtab<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess) return -1;
-                gc = gsm;
-            }
-            k_coarse_gtab<S><<<d.pc_chunks, 256, gsm, st>>>(d, w); nl++;
-            k_coarse_lm<S><<<(d.n_clm + 127) / 128, 128, 0, st>>>(d, w); nl++;
-        }
+        if (d.n_clm > 0) { k_coarse_lm<S><<<(d.n_clm + 127) / 128, 128, 0, st>>>(d, w); nl++; }
         k_coarse_pose<S><<<d.pc_chunks, 256, 0, st>>>(d, w); nl++;
         k_coarse_fix<<<(nc + 127) / 128, 128, 0, st>>>(w.cA, nc); nl++;
         nl += dense_cholesky_lower<double>(w.cA, nc, w.cStats, st);
