@@ -333,6 +333,8 @@ def run_ours(args):
         "edges_linearized_per_s": E / (ms_lin * 1e-3),
         "phases_ms": {"linearize": ms_lin_kernel, "allreduce": ms_allreduce, "solve": ms_solve, "update": ms_update},
         "pcg_iterations": pcg_iters,
+        "pcg_iterations_per_step": [int(x["pcg_iterations"]) for x in stats],
+        "solver_status_per_step": [int(x.get("solver_status", 0)) for x in stats],
         "chi2_last": stats[-1]["chi2_bearing"] + stats[-1]["chi2_odometry"],
         "roofline": roofline,
         "roofline_linearize": {"kernel": "H,b build: k_landmark_init + k_linearize_bearing_persistent + k_pose_finish", "bound": "hbm", "achieved": achieved, "peak": peak,

@@ -50,6 +50,7 @@ struct NcclApi {
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
@@ -69,8 +70,9 @@ NcclApi& nccl() {
             api.CommDestroy = (int (*)(nccl_comm_t))dlsym(api.handle, "ncclCommDestroy");
             api.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
             api.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+            api.Broadcast = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclBroadcast");
             api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
-            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather;
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Broadcast;
         }
     }
     return api;
@@ -419,6 +421,16 @@ int solve_impl(bos_ctx* c) {
     }
     c->launches += nl;
     CUDA_OK(c, cudaGetLastError());
+    if (c->nranks > 1 && c->comm) {
+        // Replicated solves are not bitwise identical (atomic summation orders differ), and every rank linearizes its edge shard at
+        // ITS state: rank 0's increment is the one everybody applies, so the replicas never drift apart.  (The implicit Schur
+        // complement cancels terms ~1e8 times larger than its small eigenvalues: a 1e-8 inconsistency between the shards' states
+        // is enough to cost it positive definiteness.)
+        NcclApi& n = nccl();
+        const int dt = (sizeof(S) == 8) ? kNcclFloat64 : kNcclFloat32;
+        if (n.Broadcast(d.delta, d.delta, (size_t)(3 * (size_t)d.NP + 2 * (size_t)d.NL), dt, 0, c->comm, c->stream) != 0)
+            return fail(c, BOS_ERR_NCCL, "ncclBroadcast of the increment failed");
+    }
     c->solved = true;
     return BOS_OK;
 }

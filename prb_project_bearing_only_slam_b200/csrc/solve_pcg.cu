@@ -504,11 +504,24 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
 // layout the solve reads from shared memory: row (group g, position k) at k * Kp + g with Kp odd.
 // Layout of a chunk's factor block (floats), read from shared memory by the solve as 16-byte vectors without bank conflicts:
 //   interior row (group g, position k): four float4 at F + ((k * 4 + c) * Kp + g) * 4, c = 0..3 holding
-//     {L0..L3} {L4..L7} {L8, d0, d1, d2} {d3, d4, d5, 0}   (L row-major 3x3 with L_0 = 0, d = Delta^-1 symmetric)
+//     {L0..L3} {L4..L7} {L8, w00, w10, w11} {w20, w21, w22, 0}   (L row-major 3x3 with L_0 = 0, W W^T = Delta^-1)
 //   separator j: the same 16 floats contiguous at Fs + 16 * j, Fs = F + 16 * cps
 //   coupling blocks of group g: three float4 at Fc + (c * Kp + g) * 4, Fc = Fs + 16 * Kp:
 //     {ct0..ct3} {ct4, ct5, cb0, cb1} {cb2..cb5};  C_top(g) couples separator g - 1 with the first interior row of group g,
 //     C_bot(g) the last interior row with separator g
+// Delta^-1 is stored as its Cholesky factor W (Delta^-1 = W W^T, W lower triangular: w00 w10 w11 w20 w21 w22): the pose blocks are
+// badly conditioned in world coordinates (the rotation couples to the translation with the lever arm |l| ~ the size of the
+// world), so rounding the SIX entries of Delta^-1 to FP32 can cost positive definiteness, whereas W W^T is PSD whatever the rounding
+template <typename S>
+__device__ __forceinline__ void sym3_chol_to_float(const S a[6], float w[6]) {
+    const double a00 = (double)a[0], a10 = (double)a[1], a20 = (double)a[2], a11 = (double)a[3], a21 = (double)a[4], a22 = (double)a[5];
+    const double w00 = sqrt(fmax(a00, 1e-300));
+    const double w10 = a10 / w00, w20 = a20 / w00;
+    const double w11 = sqrt(fmax(a11 - w10 * w10, 1e-30 * fmax(a11, 1e-300)));
+    const double w21 = (a21 - w20 * w10) / w11;
+    const double w22 = sqrt(fmax(a22 - w20 * w20 - w21 * w21, 1e-30 * fmax(a22, 1e-300)));
+    w[0] = (float)w00; w[1] = (float)w10; w[2] = (float)w11; w[3] = (float)w20; w[4] = (float)w21; w[5] = (float)w22;
+}
 __device__ __forceinline__ void chain_store_row(float* base, int sc, const float L[9], const float dv[6]) {
     base[0] = L[0]; base[1] = L[1]; base[2] = L[2]; base[3] = L[3];
     base[sc] = L[4]; base[sc + 1] = L[5]; base[sc + 2] = L[6]; base[sc + 3] = L[7];
@@ -570,8 +583,7 @@ __global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w)
                 float Lf[9], df[6];
 #pragma unroll
                 for (int q = 0; q < 9; q++) Lf[q] = (float)L[q];
-#pragma unroll
-                for (int q = 0; q < 6; q++) df[q] = (float)dinv[q];
+                sym3_chol_to_float<S>(dinv, df);
                 chain_store_row(F + ((size_t)(k * 4) * Kp + g) * 4, Kp * 4, Lf, df);
             }
             S o6[6];
@@ -662,8 +674,7 @@ __global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w)
                 float Lf[9], df[6];
 #pragma unroll
                 for (int q = 0; q < 9; q++) Lf[q] = (float)L[q];
-#pragma unroll
-                for (int q = 0; q < 6; q++) df[q] = (float)dinv[q];
+                sym3_chol_to_float<S>(dinv, df);
                 chain_store_row(Fs + 16 * j, 4, Lf, df);
             }
         }
@@ -685,9 +696,12 @@ __global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w)
         const float n1 = fmaf(-P##b.y, y2, fmaf(-P##b.x, y1, fmaf(-P##a.w, y0, P##r1)));                  \
         const float n2 = fmaf(-P##c.x, y2, fmaf(-P##b.w, y1, fmaf(-P##b.z, y0, P##r2)));                  \
         y0 = n0; y1 = n1; y2 = n2;                                                                     \
-        op[0] = P##c.y * y0 + P##c.z * y1 + P##c.w * y2;                                                  \
-        op[vcs] = P##c.z * y0 + P##d.x * y1 + P##d.y * y2;                                                \
-        op[2 * vcs] = P##c.w * y0 + P##d.y * y1 + P##d.z * y2;                                            \
+        const float t0 = P##c.y * y0 + P##c.z * y1 + P##d.x * y2;         /* W^T y, W = (c.y; c.z c.w; d.x d.y d.z) */ \
+        const float t1 = P##c.w * y1 + P##d.y * y2;                                                        \
+        const float t2 = P##d.z * y2;                                                                      \
+        op[0] = P##c.y * t0;                                                                               \
+        op[vcs] = P##c.z * t0 + P##c.w * t1;                                                                \
+        op[2 * vcs] = P##d.x * t0 + P##d.y * t1 + P##d.z * t2;                                              \
         op += vstep;                                                                                   \
     }
 #define BOS_CH_BFETCH(P, FP, OP)                                                                      \

@@ -18,6 +18,7 @@ python tools/prof_dense.py > $O/dense_$R.log 2>&1; tail -1 $O/dense_$R.log
 ncu --set full --clock-control none -k k_syrk_big -s 2 -c 1 -f -o $O/prof_syrk_$R python tools/prof_dense.py > $O/ncu_syrk_$R.log 2>&1
 # secondary lines: FP32 flavour of the same bench, dense workload, batched config 5
 python bench.py --precision f32 --steps 3 --warmup 3 --no-cpu-baseline > $O/bench_f32_$R.json 2> $O/bench_f32_$R.err; tail -c 300 $O/bench_f32_$R.json
+python bench.py --pcg-precond 1 --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_bj_$R.json 2> $O/bench_bj_$R.err; tail -c 200 $O/bench_bj_$R.json
 python bench.py --workload synth-100k --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_100k_$R.json 2> $O/bench_100k_$R.err
 python tools/prof_batch.py 4096 > $O/batch_$R.log 2>&1; cat $O/batch_$R.log
 ls -la $O | tail -12
