@@ -60,10 +60,12 @@ typedef struct bos_options {
     double pcg_rtol;          /* stop when sqrt(r^T M^-1 r) <= rtol * its initial value; default 1e-10 */
     int pcg_variant;          /* 0 = one persistent cooperative kernel for the whole PCG solve (default; falls back to 1 when a
                                  landmark has more than 1024 observations), 1 = classic loop of small kernels */
-    int pcg_precond;          /* fused kernel only: 0 = block-tridiagonal chain preconditioner (default): Schur diagonal blocks plus the
-                                 pose-pose blocks of consecutive poses, factorised once per solve and applied exactly per chunk of
-                                 ~NP/148 poses (block-Jacobi with chain-sized blocks: ~20x fewer CG iterations on odometry chains);
-                                 1 = the 3x3 block-Jacobi preconditioner.  Both converge to the same solution at pcg_rtol. */
+    int pcg_precond;          /* fused kernel, FP64 only: 0 = chain blocks + coarse space (default): per chunk of ~NP/148 poses the
+                                 block-tridiagonal matrix of the Schur diagonal blocks and the pose-pose blocks of consecutive poses,
+                                 factorised once per solve and applied exactly (block-Jacobi with chunk-sized blocks), plus a
+                                 Galerkin coarse space of piecewise-linear hats over the chunks (~70x fewer CG iterations than 3x3
+                                 blocks on odometry chains); 2 = the chain blocks alone; 1 = the 3x3 block-Jacobi preconditioner
+                                 (also what FP32 and pcg_variant 1 run).  All converge to the same solution at pcg_rtol. */
     int reserved[6];
 } bos_options;
 

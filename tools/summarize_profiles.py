@@ -72,7 +72,7 @@ if os.path.exists(b):
     hb = [v for k, v in ks.items() if "k_linearize_bearing" in k or "k_pose_finish" in k]
     if hb:
         traffic["hb_build_dram_bytes"] = sum(v["dram_read"] + v["dram_write"] for v in hb)
-for extra in ("bench_f32_%s.json", "bench_100k_%s.json", "batch_%s.log", "dense_%s.log", "bench_n2_%s.json", "bench_n4_%s.json", "bench_n8_%s.json"):
+for extra in ("bench_f32_%s.json", "bench_bj_%s.json", "bench_100k_%s.json", "batch_%s.log", "dense_%s.log", "bench_n2_%s.json", "bench_n4_%s.json", "bench_n8_%s.json"):
     e = os.path.join(G, extra % R)
     if os.path.exists(e) and os.path.getsize(e) > 0:
         shutil.copy(e, os.path.join(P, extra % R))
