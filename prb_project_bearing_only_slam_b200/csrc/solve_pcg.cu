@@ -1069,7 +1069,8 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     __shared__ double red6[kPcgThreads / 32][6];
     __shared__ double rc_s[3 * 160];    // coarse residual (3 * (chunks + 1) <= 480)
     __shared__ double xc_s[6];          // coarse solution at this chunk's two nodes
-    const bool chain = w.precond != 1, coarse = w.precond == 0;
+    // the coarse operator is dropped for this solve if its Cholesky factorisation met a non-positive pivot (flag set by k_potrf_diag)
+    const bool chain = w.precond != 1, coarse = w.precond == 0 && __ldcg(w.cStats + 5) == 0.0;
     const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, chain);
     const int cps = plan.cps, Kp = plan.Kp;
     S* vsm = reinterpret_cast<S*>(pcg_smem + plan.vec_off);
@@ -1502,7 +1503,21 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
 template <typename S>
 int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st,
                      int* iterations_out, int* launches) {
-    if (w.variant == 0 && pcg_fused_supported<S>(d)) return launch_pcg_fused<S>(d, w, max_iters, rtol, st, iterations_out, launches);
+    if (w.variant == 0 && pcg_fused_supported<S>(d)) {
+        int rc = launch_pcg_fused<S>(d, w, max_iters, rtol, st, iterations_out, launches);
+        if (rc == 1 && w.precond != 1) {
+            // breakdown (a CG denominator was not positive) under the chain / coarse preconditioner: solve again with the 3x3 blocks,
+            // whose only numerical ingredient is the inverse of each Schur diagonal block
+            const int asked = w.precond;
+            int nl2 = 0, it2 = 0;
+            w.precond = 1;
+            rc = launch_pcg_fused<S>(d, w, max_iters, rtol, st, &it2, &nl2);
+            w.precond = asked;
+            if (iterations_out) *iterations_out += it2;
+            if (launches) *launches += nl2;
+        }
+        return rc;
+    }
     int nl = 0;
     const int n = 3 * d.NP;
     const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256, gh = (d.n_hpl + 255) / 256, gn = (n + 255) / 256;
