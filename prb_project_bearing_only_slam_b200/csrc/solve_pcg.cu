@@ -1,11 +1,13 @@
 // solve_pcg.cu -- K4/K5b/K6 for large problems: the 2x2 landmark blocks are Schur-complemented out
 // IMPLICITLY and the reduced pose system  S dx_p = -(b_p - Hpl Hll^-1 b_l),
-// S = Hpp - Hpl Hll^-1 Hlp, is solved by block-Jacobi preconditioned conjugate gradients.
+// S = Hpp - Hpl Hll^-1 Hlp, is solved by preconditioned conjugate gradients (3x3 block-Jacobi, or chunk-sized
+// block-tridiagonal chain blocks + a Galerkin coarse space: see the fused variant below).
 //
 // Replaces SimplicialLDLT::factorize/solve on H_nofixed (slam/solver.hpp:72, slam/solver.cpp:77-94):
 // eliminating the landmark blocks is exact, so the solution is the same dx up to the PCG tolerance.
-// S is never formed (at 40 observations per landmark it would be ~1600 3x3 blocks per landmark);
-// one application of S is two edge-parallel passes over the pose-landmark blocks:
+// S is never formed (at 40 observations per landmark it would be ~1600 3x3 blocks per landmark).
+// Classic variant (pcg_variant 1; a loop of small kernels): one application of S is two edge-parallel passes over the
+// pose-landmark blocks:
 //   t_l  = sum_k Hpl_k^T p_pose(k)      over the (landmark, pose)-ordered copy, run-reduced per landmark
 //   y_p -= sum_k Hpl_k Hll^-1 t_lm(k)   over the (pose, landmark)-ordered blocks, run-reduced per pose
 // both HBM-bound streams of 6 scalars per block; vectors and landmark blocks stay L2-resident.
@@ -225,15 +227,15 @@ __global__ void k_pcg_promote(double* scal) {
 
 
 // =================================================================================================================
-// Fused variant: the whole PCG solve is ONE persistent cooperative kernel (one 1024-thread CTA per SM, 2 grid barriers
-// per CG iteration, no host round trips, no value atomics).
+// Fused variant (pcg_variant 0, default): the whole PCG solve is ONE persistent cooperative kernel (one 1024-thread CTA per
+// SM, 2 grid barriers per CG iteration -- 3 with the coarse space --, no host round trips, no value atomics).
 //
 // Operator.  A bearing edge's 3x2 block is rank one, Hpl_k = Jp_k^T omega Jl_k, and its pose Jacobian is determined by
 // the landmark Jacobian and the landmark position: Jp_k = (-j0, -j1, j0 ly - j1 lx) for Jl_k = (j0, j1)
 // (slam/solver_jacobians.cpp:51-89: the pose translation columns are minus the landmark columns, the theta column is
 // Jl . (ly, -lx)).  So S z = Hpp z - sum_k Jp_k^T (jh_k . u_l(k)),  u_l = Hll^-1 sum_k jh_k (Jp_k . z_pose(k)),
 // jh = sqrt(omega) Jl, needs TWO scalars per edge instead of the six of the block.
-//   landmark-major pass: the factors are stored (20 B per edge with the pose word) in a sliced-ELL layout, 4 lanes per row;
+//   landmark-major pass: sliced-ELL layout of pose indices (4 B per edge), 8 lanes per row, jh re-derived from the state;
 //   pose-major pass:     one lane per pose; the lane holds its pose, each slot gathers one 32-byte landmark record
 //                        (u_l and the landmark position) and RE-DERIVES jh from the state: 4 B per edge.
 // The pose vectors p, s, x, r and the off-diagonal product live in SHARED MEMORY for the whole solve (a pose is owned by
