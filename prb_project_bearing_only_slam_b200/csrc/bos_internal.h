@@ -7,6 +7,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace bos {
 
@@ -194,6 +197,21 @@ int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
 
 template <typename S>
 int dense_cholesky_lower(S* Smat, int n, double* stats, cudaStream_t st);
+
+// Opt-in dynamic shared memory is a per-device attribute of a kernel: remember the largest size configured per
+// (kernel, current device), so that contexts on several devices of one process all get it.
+inline bool ensure_dyn_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = done[std::make_pair(func, dev)];
+    if (bytes <= cur) return true;
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+    cur = bytes;
+    return true;
+}
 
 // batched
 template <typename S>

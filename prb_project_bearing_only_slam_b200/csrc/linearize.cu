@@ -466,13 +466,8 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
     if (nb > 0) {
         const int tiles = (nb + kLinTile - 1) / kLinTile;
         const size_t smem = sizeof(LinSmem<S>);
-        static bool attr_done[2] = {false, false};
-        bool& done = attr_done[sizeof(S) == 8 ? 0 : 1];
-        if (!done) {
-            cudaFuncSetAttribute(k_linearize_bearing_persistent<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_linearize_bearing_persistent<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            done = true;
-        }
+        ensure_dyn_smem((const void*)k_linearize_bearing_persistent<S, true>, smem);
+        ensure_dyn_smem((const void*)k_linearize_bearing_persistent<S, false>, smem);
         int grid = sm_count * kLinPersistCtas;
         if (grid > tiles) grid = tiles;
         if (d.b_slot == nullptr)

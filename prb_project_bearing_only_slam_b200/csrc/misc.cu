@@ -318,12 +318,7 @@ size_t batch_smem_bytes(int NP, int NL, size_t scalar_bytes) {
 template <typename S>
 int launch_batch_step(const BatchDev<S>& d, double kernel_threshold, double damping, cudaStream_t st) {
     const size_t smem = batch_smem_bytes(d.NP, d.NL, sizeof(S));
-    static size_t configured[2] = {0, 0};
-    size_t& conf = configured[sizeof(S) == 8 ? 0 : 1];
-    if (smem > 48 * 1024 && smem > conf) {
-        if (cudaFuncSetAttribute(k_batch_step<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        conf = smem;
-    }
+    if (smem > 48 * 1024 && !ensure_dyn_smem((const void*)k_batch_step<S>, smem)) return -1;
     k_batch_step<S><<<d.nprob, 32, smem, st>>>(d, (S)kernel_threshold, (S)damping);
     return 1;
 }

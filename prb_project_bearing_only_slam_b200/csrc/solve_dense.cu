@@ -420,12 +420,7 @@ template <typename S>
 int dense_cholesky_lower(S* Smat, int n, double* stats, cudaStream_t st) {
     int nl = 0;
     const size_t smem = 2 * (size_t)NB * LDT * sizeof(S);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_syrk_tiles<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(double)));
-        cudaFuncSetAttribute(k_syrk_tiles<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NB * LDT * sizeof(float)));
-        attr_set = true;
-    }
+    ensure_dyn_smem((const void*)k_syrk_tiles<S>, smem);
     constexpr int kOuter = 256;   // outer panel: the bulk of the matrix is updated once per kOuter columns
     for (int c0 = 0; c0 < n; c0 += kOuter) {
         const int cend = (c0 + kOuter < n) ? c0 + kOuter : n;
@@ -447,8 +442,7 @@ int dense_cholesky_lower(S* Smat, int n, double* stats, cudaStream_t st) {
             const int T = (n - cend + NB - 1) / NB;
             if constexpr (sizeof(S) == 8) {
                 constexpr size_t smem_big = 2 * (size_t)(KC * LDA2 + KC * LDB2) * sizeof(double);
-                static bool big_attr = false;
-                if (!big_attr) { cudaFuncSetAttribute(k_syrk_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big); big_attr = true; }
+                ensure_dyn_smem((const void*)k_syrk_big, smem_big);
                 k_syrk_big<<<dim3((n - cend + 127) / 128, T), 256, smem_big, st>>>(Smat, n, c0, cend - c0, cend);
             } else {
                 k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(Smat, n, c0, cend - c0, cend, T, T);

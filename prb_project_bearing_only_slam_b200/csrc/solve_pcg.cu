@@ -1481,12 +1481,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
         k_coarse_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cA, w.cAinv, nc); nl++;
     }
     const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, precond != 1);
-    static size_t configured[2] = {0, 0};
-    size_t& conf = configured[sizeof(S) == 8 ? 0 : 1];
-    if (plan.bytes > conf) {
-        if (cudaFuncSetAttribute(k_pcg_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes) != cudaSuccess) return -1;
-        conf = plan.bytes;
-    }
+    if (!ensure_dyn_smem((const void*)k_pcg_fused<S>, plan.bytes)) return -1;
     Dev<S> dd = d;
     PcgWork<S> ww = w;
     w.precond = precond_asked;
