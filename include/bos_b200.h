@@ -187,6 +187,9 @@ BOS_API int bos_host_pattern_destroy(bos_host_pattern* p);
 BOS_API int bos_host_pattern_info(const bos_host_pattern* p, bos_pattern_info* out);
 BOS_API int bos_host_pattern_get(const bos_host_pattern* p, int32_t* hpl_pose, int32_t* hpl_lm, int32_t* off_lo, int32_t* off_hi,
                          int64_t* b_slot, int64_t* o_slot, int32_t* csc_colptr, int32_t* csc_rowidx);
+/* 64-bit FNV-1a digest of EVERY integer table of the pattern (block slots, ELL / chunk / tile layouts, adjacency ...): lets a test
+ * assert that two builds (e.g. serial and threaded, BOS_PATTERN_THREADS=1) produced identical device layouts. */
+BOS_API int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out);
 /* The contiguous edge ranges rank `rank` of `nranks` linearizes: out4 = b_begin, b_end, o_begin, o_end. */
 BOS_API int bos_host_edge_shard(int64_t Eb, int64_t Eo, int rank, int nranks, int64_t* out4);
 

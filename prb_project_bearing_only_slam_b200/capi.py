@@ -51,7 +51,7 @@ SYMBOLS = [
     "bos_update", "bos_step", "bos_step_host", "bos_get_stats", "bos_triangulate", "bos_pattern_info_get",
     "bos_download_pattern", "bos_download_blocks", "bos_download_csc", "bos_download_delta", "bos_upload_delta",
     "bos_edge_terms", "bos_host_pattern_create", "bos_host_pattern_destroy", "bos_host_pattern_info",
-    "bos_host_pattern_get", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
+    "bos_host_pattern_get", "bos_host_pattern_checksum", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
     "bos_set_edge_shard", "bos_get_edge_shard", "bos_batch_create", "bos_batch_destroy", "bos_batch_set_states",
     "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error", "bos_synth_default_spec",
     "bos_synth_create", "bos_synth_destroy", "bos_synth_counts", "bos_synth_get",
@@ -98,6 +98,7 @@ def lib():
         L.bos_host_pattern_destroy.argtypes = [vp]
         L.bos_host_pattern_info.argtypes = [vp, C.POINTER(PatternInfo)]
         L.bos_host_pattern_get.argtypes = [vp] + [vp] * 8
+        L.bos_host_pattern_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.bos_host_edge_shard.argtypes = [i64, i64, i32, i32, vp]
         L.bos_nccl_unique_id.argtypes = [C.c_char_p]
         L.bos_comm_init.argtypes = [vp, i32, i32, C.c_char_p]
@@ -321,6 +322,13 @@ class HostPattern:
         pi = PatternInfo()
         self.L.bos_host_pattern_info(self.h, C.byref(pi))
         return pi
+
+    def checksum(self):
+        out = C.c_uint64()
+        rc = self.L.bos_host_pattern_checksum(self.h, C.byref(out))
+        if rc != OK:
+            raise BosError(rc, "bos_host_pattern_checksum")
+        return int(out.value)
 
     def get(self):
         pi = self.info()

@@ -1020,6 +1020,31 @@ int bos_host_pattern_destroy(bos_host_pattern* p) {
     delete p;
     return BOS_OK;
 }
+int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out) {
+    if (!p || !out) return BOS_ERR_INVALID;
+    const HostPattern& P = p->P;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* data, size_t bytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(data);
+        for (size_t i = 0; i < bytes; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    auto vec = [&](const auto& v) {
+        const uint64_t n = v.size();
+        mix(&n, sizeof(n));
+        if (n) mix(v.data(), n * sizeof(v[0]));
+    };
+    const int scal[] = {P.NP, P.NL, P.fixed, P.Eb, P.Eo, P.N, P.pc_chunks, P.pc_cp, (int)P.pc_ok, (int)P.slots_identity, (int)P.has_shared_off};
+    mix(scal, sizeof(scal));
+    vec(P.b_pose); vec(P.b_lm); vec(P.b_perm); vec(P.b_slot); vec(P.slot_pose); vec(P.slot_lm);
+    vec(P.pose_ptr); vec(P.lm_ptr); vec(P.lm_order); vec(P.lm_order_pose); vec(P.lm_order_lm);
+    vec(P.o_src); vec(P.o_dst); vec(P.o_slot); vec(P.oe_ptr); vec(P.oe_edge); vec(P.oe_other); vec(P.o_shared);
+    vec(P.off_lo); vec(P.off_hi); vec(P.pp_ptr); vec(P.pp_nbr); vec(P.pp_slot); vec(P.tri_ptr); vec(P.tri_edge);
+    vec(P.pl_lm_id); vec(P.b_row); vec(P.ell_Loff); vec(P.ell_Lmap); vec(P.ell_Lpose);
+    vec(P.pc_row_pose); vec(P.pc_goff); vec(P.pc_cl_ptr); vec(P.pc_cl_row); vec(P.pc_emap); vec(P.pc_nbr); vec(P.pc_nslot); vec(P.pc_ncnt);
+    vec(P.pc_loc); vec(P.tile_ptr); vec(P.tg_lm); vec(P.tg_eptr); vec(P.epose_ptr); vec(P.tg_edge); vec(P.touched);
+    *out = h;
+    return BOS_OK;
+}
 int bos_host_pattern_info(const bos_host_pattern* p, bos_pattern_info* out) {
     if (!p || !out) return BOS_ERR_INVALID;
     build_csc(const_cast<HostPattern&>(p->P));

@@ -7,8 +7,25 @@
 
 #include <algorithm>
 #include <numeric>
+#include <thread>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace bos {
+
+namespace {
+struct PhaseTimer {   // BOS_PATTERN_TIMING=1: per-phase wall times of the pattern build on stderr
+    bool on; std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(std::getenv("BOS_PATTERN_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[pattern] %-28s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
 
 int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const int32_t* b_pose, const int32_t* b_lm,
                   int64_t Eo64, const int32_t* o_src, const int32_t* o_dst, int pcg_chunks) {
@@ -23,7 +40,9 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         if (o_src[e] < 0 || o_src[e] >= NP || o_dst[e] < 0 || o_dst[e] >= NP) { P.error = "odometry edge index out of range"; return 1; }
         if (o_src[e] == o_dst[e]) { P.error = "odometry self-loop"; return 1; }
     }
+    PhaseTimer tm;
     P.touched.assign((size_t)NP + NL, 0);
+    tm.lap("checks");
 
     // ---- bearing edges sorted by (pose, lm), ties in caller order ------------------------------------------
     std::vector<uint64_t> key(Eb);
@@ -45,6 +64,7 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         P.b_slot[k] = (int)P.slot_pose.size() - 1;
         if (P.b_slot[k] != k) P.slots_identity = false;
     }
+    tm.lap("sort + slots");
     const int n_hpl = (int)P.slot_pose.size();
     P.pose_ptr.assign(NP + 1, 0);
     for (int s = 0; s < n_hpl; s++) P.pose_ptr[P.slot_pose[s] + 1]++;
@@ -61,6 +81,7 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
             P.lm_order[k] = s; P.lm_order_pose[k] = P.slot_pose[s]; P.lm_order_lm[k] = P.slot_lm[s];
         }
     }
+    tm.lap("pose/lm slot orders");
     // bearing edges grouped by landmark in caller order (triangulation rows, slam/triangulation.cpp:5-19)
     P.tri_ptr.assign(NL + 1, 0);
     for (int e = 0; e < Eb; e++) P.tri_ptr[b_lm[e] + 1]++;
@@ -76,6 +97,84 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
     P.epose_ptr.assign(NP + 1, 0);
     for (int k = 0; k < Eb; k++) P.epose_ptr[P.b_pose[k] + 1]++;
     for (int i = 0; i < NP; i++) P.epose_ptr[i + 1] += P.epose_ptr[i];
+    tm.lap("triangulation rows");
+    // tile-local grouping of the sorted bearing edges by landmark (static: depends only on the edge lists); independent of the
+    // layouts below: runs on its own thread
+    auto tile_grouping = [&]() {
+        const int ntiles = (Eb + kLinTile - 1) / kLinTile;
+        P.tile_ptr.assign(ntiles + 1, 0);
+        P.tg_lm.clear(); P.tg_eptr.assign(1, 0); P.tg_edge.resize(Eb);
+        std::vector<std::pair<int, int>> tmp;
+        for (int t = 0; t < ntiles; t++) {
+            const int a = t * kLinTile, b = std::min(Eb, a + kLinTile);
+            tmp.clear();
+            for (int k = a; k < b; k++) tmp.emplace_back(P.b_lm[k], k - a);
+            std::sort(tmp.begin(), tmp.end());
+            for (size_t i = 0; i < tmp.size(); i++) {
+                if (i == 0 || tmp[i].first != tmp[i - 1].first) {
+                    if (i) P.tg_eptr.push_back(a + (int)i);
+                    P.tg_lm.push_back(tmp[i].first);
+                }
+                P.tg_edge[a + i] = (unsigned short)tmp[i].second;
+            }
+            if (!tmp.empty()) P.tg_eptr.push_back(b);
+            P.tile_ptr[t + 1] = (int)P.tg_lm.size();
+        }
+    };
+    // odometry edges and the pose-pose adjacency: independent of the bearing layouts, on its own thread
+    auto odometry_tables = [&]() {
+        // ---- odometry edges: unique unordered pose pairs ---------------------------------------------------------
+        P.o_src.assign(o_src, o_src + Eo); P.o_dst.assign(o_dst, o_dst + Eo);
+        std::vector<uint64_t> okey(Eo);
+        for (int e = 0; e < Eo; e++) {
+            int lo = std::min(o_src[e], o_dst[e]), hi = std::max(o_src[e], o_dst[e]);
+            okey[e] = ((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi;
+            P.touched[o_src[e]] = 1; P.touched[o_dst[e]] = 1;
+        }
+        std::vector<uint64_t> uniq(okey);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        const int n_off = (int)uniq.size();
+        P.off_lo.resize(n_off); P.off_hi.resize(n_off);
+        for (int k = 0; k < n_off; k++) { P.off_lo[k] = (int)(uniq[k] >> 32); P.off_hi[k] = (int)(uniq[k] & 0xffffffffu); }
+        P.o_slot.resize(Eo);
+        for (int e = 0; e < Eo; e++) P.o_slot[e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), okey[e]) - uniq.begin());
+        {
+            std::vector<int> cnt(n_off, 0);
+            for (int e = 0; e < Eo; e++) cnt[P.o_slot[e]]++;
+            P.o_shared.resize(Eo);
+            for (int e = 0; e < Eo; e++) { P.o_shared[e] = cnt[P.o_slot[e]] > 1; P.has_shared_off |= cnt[P.o_slot[e]] > 1; }
+            // odometry edges incident to each pose (edge order inside a pose)
+            P.oe_ptr.assign(NP + 1, 0);
+            for (int e = 0; e < Eo; e++) { P.oe_ptr[o_src[e] + 1]++; P.oe_ptr[o_dst[e] + 1]++; }
+            for (int i = 0; i < NP; i++) P.oe_ptr[i + 1] += P.oe_ptr[i];
+            P.oe_edge.resize(2 * (size_t)Eo); P.oe_other.resize(2 * (size_t)Eo);
+            std::vector<int> cur(P.oe_ptr.begin(), P.oe_ptr.end() - 1);
+            for (int e = 0; e < Eo; e++) {
+                int a = cur[o_src[e]]++; P.oe_edge[a] = (e << 1); P.oe_other[a] = o_dst[e];
+                int b = cur[o_dst[e]]++; P.oe_edge[b] = (e << 1) | 1; P.oe_other[b] = o_src[e];
+            }
+        }
+        // pose-pose adjacency, neighbours ascending
+        P.pp_ptr.assign(NP + 1, 0);
+        for (int k = 0; k < n_off; k++) { P.pp_ptr[P.off_lo[k] + 1]++; P.pp_ptr[P.off_hi[k] + 1]++; }
+        for (int i = 0; i < NP; i++) P.pp_ptr[i + 1] += P.pp_ptr[i];
+        P.pp_nbr.resize(2 * (size_t)n_off); P.pp_slot.resize(2 * (size_t)n_off);
+        {
+            std::vector<int> cur(P.pp_ptr.begin(), P.pp_ptr.end() - 1);
+            // first the neighbours below a pose (it is the 'hi' side), in ascending lo; uniq is sorted by (lo, hi)
+            for (int k = 0; k < n_off; k++) { int i = P.off_hi[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_lo[k]; P.pp_slot[c] = k | (int)0x80000000; }
+            for (int k = 0; k < n_off; k++) { int i = P.off_lo[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_hi[k]; P.pp_slot[c] = k; }
+        }
+
+    };
+    // BOS_PATTERN_THREADS=1 keeps everything on the calling thread (the results are identical: the three parts write disjoint
+    // members of P)
+    const char* thr_env = std::getenv("BOS_PATTERN_THREADS");
+    const bool par = !(thr_env && std::atoi(thr_env) <= 1);
+    std::thread thB, thC;
+    if (par) { thB = std::thread(tile_grouping); thC = std::thread(odometry_tables); }
+    else { tile_grouping(); odometry_tables(); }
     // sliced-ELL layouts of the bearing EDGES for the fused PCG kernel (both coalesced for one-row-per-lane loops):
     //   L: rows = observed landmarks, renumbered compactly by descending observation count (uniform row length inside a
     //      group), kEllLanesL lanes per row (a row's edges go round-robin over its lanes), 32 / kEllLanesL rows per group;
@@ -168,73 +267,10 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         P.pc_nbr.assign((size_t)nch * cp * 2, -1);
         P.pc_nslot.assign((size_t)nch * cp * 2, 0);
     }
-    // tile-local grouping of the sorted bearing edges by landmark (static: depends only on the edge lists)
-    {
-        const int ntiles = (Eb + kLinTile - 1) / kLinTile;
-        P.tile_ptr.assign(ntiles + 1, 0);
-        P.tg_lm.clear(); P.tg_eptr.assign(1, 0); P.tg_edge.resize(Eb);
-        std::vector<std::pair<int, int>> tmp;
-        for (int t = 0; t < ntiles; t++) {
-            const int a = t * kLinTile, b = std::min(Eb, a + kLinTile);
-            tmp.clear();
-            for (int k = a; k < b; k++) tmp.emplace_back(P.b_lm[k], k - a);
-            std::sort(tmp.begin(), tmp.end());
-            for (size_t i = 0; i < tmp.size(); i++) {
-                if (i == 0 || tmp[i].first != tmp[i - 1].first) {
-                    if (i) P.tg_eptr.push_back(a + (int)i);
-                    P.tg_lm.push_back(tmp[i].first);
-                }
-                P.tg_edge[a + i] = (unsigned short)tmp[i].second;
-            }
-            if (!tmp.empty()) P.tg_eptr.push_back(b);
-            P.tile_ptr[t + 1] = (int)P.tg_lm.size();
-        }
-    }
-
-    // ---- odometry edges: unique unordered pose pairs ---------------------------------------------------------
-    P.o_src.assign(o_src, o_src + Eo); P.o_dst.assign(o_dst, o_dst + Eo);
-    std::vector<uint64_t> okey(Eo);
-    for (int e = 0; e < Eo; e++) {
-        int lo = std::min(o_src[e], o_dst[e]), hi = std::max(o_src[e], o_dst[e]);
-        okey[e] = ((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi;
-        P.touched[o_src[e]] = 1; P.touched[o_dst[e]] = 1;
-    }
-    std::vector<uint64_t> uniq(okey);
-    std::sort(uniq.begin(), uniq.end());
-    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-    const int n_off = (int)uniq.size();
-    P.off_lo.resize(n_off); P.off_hi.resize(n_off);
-    for (int k = 0; k < n_off; k++) { P.off_lo[k] = (int)(uniq[k] >> 32); P.off_hi[k] = (int)(uniq[k] & 0xffffffffu); }
-    P.o_slot.resize(Eo);
-    for (int e = 0; e < Eo; e++) P.o_slot[e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), okey[e]) - uniq.begin());
-    {
-        std::vector<int> cnt(n_off, 0);
-        for (int e = 0; e < Eo; e++) cnt[P.o_slot[e]]++;
-        P.o_shared.resize(Eo);
-        for (int e = 0; e < Eo; e++) { P.o_shared[e] = cnt[P.o_slot[e]] > 1; P.has_shared_off |= cnt[P.o_slot[e]] > 1; }
-        // odometry edges incident to each pose (edge order inside a pose)
-        P.oe_ptr.assign(NP + 1, 0);
-        for (int e = 0; e < Eo; e++) { P.oe_ptr[o_src[e] + 1]++; P.oe_ptr[o_dst[e] + 1]++; }
-        for (int i = 0; i < NP; i++) P.oe_ptr[i + 1] += P.oe_ptr[i];
-        P.oe_edge.resize(2 * (size_t)Eo); P.oe_other.resize(2 * (size_t)Eo);
-        std::vector<int> cur(P.oe_ptr.begin(), P.oe_ptr.end() - 1);
-        for (int e = 0; e < Eo; e++) {
-            int a = cur[o_src[e]]++; P.oe_edge[a] = (e << 1); P.oe_other[a] = o_dst[e];
-            int b = cur[o_dst[e]]++; P.oe_edge[b] = (e << 1) | 1; P.oe_other[b] = o_src[e];
-        }
-    }
-    // pose-pose adjacency, neighbours ascending
-    P.pp_ptr.assign(NP + 1, 0);
-    for (int k = 0; k < n_off; k++) { P.pp_ptr[P.off_lo[k] + 1]++; P.pp_ptr[P.off_hi[k] + 1]++; }
-    for (int i = 0; i < NP; i++) P.pp_ptr[i + 1] += P.pp_ptr[i];
-    P.pp_nbr.resize(2 * (size_t)n_off); P.pp_slot.resize(2 * (size_t)n_off);
-    {
-        std::vector<int> cur(P.pp_ptr.begin(), P.pp_ptr.end() - 1);
-        // first the neighbours below a pose (it is the 'hi' side), in ascending lo; uniq is sorted by (lo, hi)
-        for (int k = 0; k < n_off; k++) { int i = P.off_hi[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_lo[k]; P.pp_slot[c] = k | (int)0x80000000; }
-        for (int k = 0; k < n_off; k++) { int i = P.off_lo[k]; int c = cur[i]++; P.pp_nbr[c] = P.off_hi[k]; P.pp_slot[c] = k; }
-    }
-
+    tm.lap("ELL + chunk layouts");
+    if (par) thB.join();
+    tm.lap("tile grouping");
+    if (par) thC.join();
     // inline pose-pose neighbours of the PCG chunk rows (needs the adjacency above)
     P.pc_ncnt.assign((size_t)P.pc_chunks * P.pc_cp, 0);
     for (size_t R = 0; R < P.pc_row_pose.size(); R++) {
@@ -246,6 +282,7 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         for (int k = 0; k < 2 && q0 + k < q1; k++) { P.pc_nbr[k * nrows + R] = P.pp_nbr[q0 + k]; P.pc_nslot[k * nrows + R] = P.pp_slot[q0 + k]; }
     }
 
+    tm.lap("odometry + adjacency");
     P.csc_built = false;   // the scalar CSC view is only needed for inspection / parity downloads: built on demand (build_csc)
     return 0;
 }

@@ -92,3 +92,20 @@ def test_edge_shards_partition_the_edges(built_lib):
         sizes = [p[1] - p[0] for p in pieces]
         assert max(sizes) - min(s for s in sizes if s or True) <= max(sizes)  # contiguous, equal chunks except the tail
         assert len({s for s in sizes[:-1] if s}) <= 2
+
+
+def test_threaded_pattern_build_equals_the_serial_one(built_lib, monkeypatch):
+    """The tile grouping and the odometry tables are built on their own threads beside the ELL / chunk layouts; every integer
+    table the device receives must be identical to a build that stays on one thread (BOS_PATTERN_THREADS=1)."""
+    rng = np.random.default_rng(21)
+    worlds = [synth_problem(4000, 900, 40000, seed=8)[1], synth_problem(333, 71, 2500, seed=9)[1]]
+    for pr in worlds:
+        # shuffled caller order and a few duplicate edges exercise the sort path as well
+        perm = rng.permutation(len(pr.b_pose))
+        bp = np.concatenate([pr.b_pose[perm], pr.b_pose[:17]]); bl = np.concatenate([pr.b_lm[perm], pr.b_lm[:17]])
+        sums = []
+        for threads in ("1", "8"):
+            monkeypatch.setenv("BOS_PATTERN_THREADS", threads)
+            hp = capi.HostPattern(pr.NP, pr.NL, pr.fixed_stix, bp, bl, pr.o_src, pr.o_dst)
+            sums.append(hp.checksum())
+        assert sums[0] == sums[1] and sums[0] != 0
