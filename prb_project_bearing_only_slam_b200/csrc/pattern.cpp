@@ -15,6 +15,26 @@
 namespace bos {
 
 namespace {
+// Static ranges of [0, n) on up to `threads` threads; fn(begin, end, thread index).  Every use below writes disjoint outputs per
+// range, so the result does not depend on the thread count (tests/test_host_pattern.py compares checksums).
+template <typename F>
+void parallel_ranges(int n, int threads, F fn) {
+    if (threads <= 1 || n < 2 * threads) { fn(0, n, 0); return; }
+    std::vector<std::thread> pool;
+    const int per = (n + threads - 1) / threads;
+    for (int t = 1; t < threads; t++) {
+        const int a = std::min(n, t * per), b = std::min(n, a + per);
+        if (a < b) pool.emplace_back([=]() { fn(a, b, t); });
+    }
+    fn(0, std::min(n, per), 0);
+    for (auto& th : pool) th.join();
+}
+int pattern_threads() {
+    const char* env = std::getenv("BOS_PATTERN_THREADS");
+    int t = env ? std::atoi(env) : (int)std::thread::hardware_concurrency();
+    return t < 1 ? 1 : (t > 16 ? 16 : t);
+}
+
 struct PhaseTimer {   // BOS_PATTERN_TIMING=1: per-phase wall times of the pattern build on stderr
     bool on; std::chrono::steady_clock::time_point t0;
     PhaseTimer() : on(std::getenv("BOS_PATTERN_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
@@ -98,27 +118,43 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
     for (int k = 0; k < Eb; k++) P.epose_ptr[P.b_pose[k] + 1]++;
     for (int i = 0; i < NP; i++) P.epose_ptr[i + 1] += P.epose_ptr[i];
     tm.lap("triangulation rows");
+    const int nthreads = pattern_threads();
+    const bool par = nthreads > 1;
+    const int wthreads = par ? std::max(1, (nthreads - 1) / 2) : 1;   // workers of each of the two big parts
     // tile-local grouping of the sorted bearing edges by landmark (static: depends only on the edge lists); independent of the
     // layouts below: runs on its own thread
     auto tile_grouping = [&]() {
         const int ntiles = (Eb + kLinTile - 1) / kLinTile;
         P.tile_ptr.assign(ntiles + 1, 0);
         P.tg_lm.clear(); P.tg_eptr.assign(1, 0); P.tg_edge.resize(Eb);
-        std::vector<std::pair<int, int>> tmp;
-        for (int t = 0; t < ntiles; t++) {
-            const int a = t * kLinTile, b = std::min(Eb, a + kLinTile);
-            tmp.clear();
-            for (int k = a; k < b; k++) tmp.emplace_back(P.b_lm[k], k - a);
-            std::sort(tmp.begin(), tmp.end());
-            for (size_t i = 0; i < tmp.size(); i++) {
-                if (i == 0 || tmp[i].first != tmp[i - 1].first) {
-                    if (i) P.tg_eptr.push_back(a + (int)i);
-                    P.tg_lm.push_back(tmp[i].first);
+        struct Part { std::vector<int> lm, eptr, ngroups; };
+        std::vector<Part> parts(wthreads > 0 ? wthreads : 1);
+        parallel_ranges(ntiles, wthreads, [&](int t0, int t1, int w) {
+            Part& Q = parts[w];
+            std::vector<std::pair<int, int>> tmp;
+            for (int t = t0; t < t1; t++) {
+                const int a = t * kLinTile, b = std::min(Eb, a + kLinTile);
+                tmp.clear();
+                for (int k = a; k < b; k++) tmp.emplace_back(P.b_lm[k], k - a);
+                std::sort(tmp.begin(), tmp.end());
+                int ng = 0;
+                for (size_t i = 0; i < tmp.size(); i++) {
+                    if (i == 0 || tmp[i].first != tmp[i - 1].first) {
+                        if (i) Q.eptr.push_back(a + (int)i);
+                        Q.lm.push_back(tmp[i].first);
+                        ng++;
+                    }
+                    P.tg_edge[a + i] = (unsigned short)tmp[i].second;
                 }
-                P.tg_edge[a + i] = (unsigned short)tmp[i].second;
+                if (!tmp.empty()) Q.eptr.push_back(b);
+                Q.ngroups.push_back(ng);
             }
-            if (!tmp.empty()) P.tg_eptr.push_back(b);
-            P.tile_ptr[t + 1] = (int)P.tg_lm.size();
+        });
+        int t = 0;
+        for (const Part& Q : parts) {   // ranges are in tile order
+            P.tg_lm.insert(P.tg_lm.end(), Q.lm.begin(), Q.lm.end());
+            P.tg_eptr.insert(P.tg_eptr.end(), Q.eptr.begin(), Q.eptr.end());
+            for (int ng : Q.ngroups) { P.tile_ptr[t + 1] = P.tile_ptr[t] + ng; t++; }
         }
     };
     // odometry edges and the pose-pose adjacency: independent of the bearing layouts, on its own thread
@@ -170,8 +206,6 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
     };
     // BOS_PATTERN_THREADS=1 keeps everything on the calling thread (the results are identical: the three parts write disjoint
     // members of P)
-    const char* thr_env = std::getenv("BOS_PATTERN_THREADS");
-    const bool par = !(thr_env && std::atoi(thr_env) <= 1);
     std::thread thB, thC;
     if (par) { thB = std::thread(tile_grouping); thC = std::thread(odometry_tables); }
     else { tile_grouping(); odometry_tables(); }
@@ -204,15 +238,17 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         }
         P.ell_Lmap.assign((size_t)P.ell_Loff[nLg] * 32, -1);
         P.ell_Lpose.assign((size_t)P.ell_Loff[nLg] * 32, -1);
-        for (int r = 0; r < n_clm; r++) {
-            const int l = P.pl_lm_id[r], g = r / RPG, lane0 = (r % RPG) * kEllLanesL;
-            for (int q = eptr[l]; q < eptr[l + 1]; q++) {
-                const int k = eord[q], idx = q - eptr[l];
-                const size_t slot = ((size_t)P.ell_Loff[g] + idx / kEllLanesL) * 32 + lane0 + idx % kEllLanesL;
-                P.ell_Lmap[slot] = k; P.ell_Lpose[slot] = (P.b_pose[k] == fixed) ? -1 : P.b_pose[k];
-                P.b_row[k] = r;
+        parallel_ranges(n_clm, wthreads, [&](int r0, int r1, int) {
+            for (int r = r0; r < r1; r++) {
+                const int l = P.pl_lm_id[r], g = r / RPG, lane0 = (r % RPG) * kEllLanesL;
+                for (int q = eptr[l]; q < eptr[l + 1]; q++) {
+                    const int k = eord[q], idx = q - eptr[l];
+                    const size_t slot = ((size_t)P.ell_Loff[g] + idx / kEllLanesL) * 32 + lane0 + idx % kEllLanesL;
+                    P.ell_Lmap[slot] = k; P.ell_Lpose[slot] = (P.b_pose[k] == fixed) ? -1 : P.b_pose[k];
+                    P.b_row[k] = r;
+                }
             }
-        }
+        });
         // P: pose rows in CHUNKS: chunk c (one persistent CTA) owns poses [c * cp, (c + 1) * cp), rows in pose order; every
         // slot names its landmark by a 16-bit index into the chunk's table of distinct landmark rows (a contiguous pose
         // range sees few landmarks).
@@ -227,42 +263,50 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         P.pc_cl_ptr.assign(nch + 1, 0);
         P.pc_cl_row.clear();
         P.pc_ok = true;
-        std::vector<int> rows, lid(n_clm > 0 ? n_clm : 1, -1);
-        for (int c = 0; c < nch; c++) {
-            const int p0 = c * cp, p1 = std::min(NP, p0 + cp);
-            rows.resize(p1 - p0);
-            std::iota(rows.begin(), rows.end(), p0);
-            for (size_t r = 0; r < rows.size(); r++) P.pc_row_pose[(size_t)c * cp + r] = rows[r];
-            for (int g = 0; g < gpc; g++) {
-                int wdt = 0;   // rows stay in pose order (coalesced per-pose data): the group is as wide as its longest row
-                for (size_t r0 = (size_t)g * 32; r0 < rows.size() && r0 < (size_t)g * 32 + 32; r0++)
-                    wdt = std::max(wdt, P.epose_ptr[rows[r0] + 1] - P.epose_ptr[rows[r0]]);
-                P.pc_goff[(size_t)c * gpc + g + 1] = P.pc_goff[(size_t)c * gpc + g] + wdt;
+        std::vector<int> wdt((size_t)nch * gpc, 0);
+        std::vector<std::vector<int>> cl(nch);
+        parallel_ranges(nch, wthreads, [&](int c0, int c1, int) {
+            for (int c = c0; c < c1; c++) {
+                const int p0 = c * cp, p1 = std::min(NP, p0 + cp);
+                for (int i = p0; i < p1; i++) {
+                    const int r = i - p0;
+                    P.pc_row_pose[(size_t)c * cp + r] = i;
+                    int& wd = wdt[(size_t)c * gpc + r / 32];   // rows stay in pose order: the group is as wide as its longest row
+                    wd = std::max(wd, P.epose_ptr[i + 1] - P.epose_ptr[i]);
+                }
+                // distinct landmark rows of the chunk, ascending
+                std::vector<int>& v = cl[c];
+                v.assign(P.b_row.begin() + P.epose_ptr[p0], P.b_row.begin() + P.epose_ptr[p1]);
+                std::sort(v.begin(), v.end());
+                v.erase(std::unique(v.begin(), v.end()), v.end());
             }
-            // distinct landmark rows of the chunk, ascending
-            const size_t cl0 = P.pc_cl_row.size();
-            for (int k = P.epose_ptr[p0]; k < P.epose_ptr[p1]; k++) P.pc_cl_row.push_back(P.b_row[k]);
-            std::sort(P.pc_cl_row.begin() + cl0, P.pc_cl_row.end());
-            P.pc_cl_row.erase(std::unique(P.pc_cl_row.begin() + cl0, P.pc_cl_row.end()), P.pc_cl_row.end());
+        });
+        for (size_t q = 0; q < wdt.size(); q++) P.pc_goff[q + 1] = P.pc_goff[q] + wdt[q];
+        for (int c = 0; c < nch; c++) {
+            P.pc_cl_row.insert(P.pc_cl_row.end(), cl[c].begin(), cl[c].end());
             P.pc_cl_ptr[c + 1] = (int)P.pc_cl_row.size();
-            if (P.pc_cl_row.size() - cl0 >= 0xffff) P.pc_ok = false;
+            if (cl[c].size() >= 0xffff) P.pc_ok = false;
         }
         P.pc_loc.assign((size_t)P.pc_goff.back() * 32, (unsigned short)0xffff);
         P.pc_emap.assign((size_t)P.pc_goff.back() * 32, -1);
-        for (int c = 0; c < nch && P.pc_ok; c++) {
-            const int cl0 = P.pc_cl_ptr[c], cl1 = P.pc_cl_ptr[c + 1];
-            for (int q = cl0; q < cl1; q++) lid[P.pc_cl_row[q]] = q - cl0;
-            for (int r = 0; r < cp; r++) {
-                const int i = P.pc_row_pose[(size_t)c * cp + r];
-                if (i < 0) continue;
-                const size_t g = (size_t)c * gpc + r / 32;
-                for (int k = P.epose_ptr[i]; k < P.epose_ptr[i + 1]; k++) {
-                    const size_t slot = ((size_t)P.pc_goff[g] + (k - P.epose_ptr[i])) * 32 + r % 32;
-                    P.pc_loc[slot] = (unsigned short)lid[P.b_row[k]];
-                    P.pc_emap[slot] = k;
+        if (P.pc_ok)
+            parallel_ranges(nch, wthreads, [&](int c0, int c1, int) {
+                std::vector<int> lid(n_clm > 0 ? n_clm : 1, -1);   // landmark row -> index in the chunk's table
+                for (int c = c0; c < c1; c++) {
+                    const int cl0 = P.pc_cl_ptr[c], cl1 = P.pc_cl_ptr[c + 1];
+                    for (int q = cl0; q < cl1; q++) lid[P.pc_cl_row[q]] = q - cl0;
+                    for (int r = 0; r < cp; r++) {
+                        const int i = P.pc_row_pose[(size_t)c * cp + r];
+                        if (i < 0) continue;
+                        const size_t g = (size_t)c * gpc + r / 32;
+                        for (int k = P.epose_ptr[i]; k < P.epose_ptr[i + 1]; k++) {
+                            const size_t slot = ((size_t)P.pc_goff[g] + (k - P.epose_ptr[i])) * 32 + r % 32;
+                            P.pc_loc[slot] = (unsigned short)lid[P.b_row[k]];
+                            P.pc_emap[slot] = k;
+                        }
+                    }
                 }
-            }
-        }
+            });
         // up to two pose-pose neighbours per row inline (filled once the adjacency exists, below)
         P.pc_nbr.assign((size_t)nch * cp * 2, -1);
         P.pc_nslot.assign((size_t)nch * cp * 2, 0);
