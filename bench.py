@@ -314,7 +314,8 @@ def run_ours(args):
                     "traffic": (t_it * pcg_iters) if t_it else None, "peak_source": peak_src,
                     "bytes_per_launch": b_it * pcg_iters, "bytes_per_cg_iteration": b_it, "cg_iterations_per_launch": pcg_iters,
                     "ms_per_launch": ms_solve, "us_per_cg_iteration": 1e3 * ms_solve / pcg_iters,
-                    "note": "ms_per_launch is the solve phase (4 setup kernels + the persistent kernel), CUDA events on the context's stream"}
+                    "note": "ms_per_launch is the solve phase: the persistent kernel plus its per-solve setup kernels (Schur preparation, "
+                            "chain factorisation, coarse operator assembly / Cholesky / inverse), CUDA events on the context's stream"}
     else:
         roofline = {"kernel": "H,b build: k_landmark_init + k_linearize_bearing_persistent + k_pose_finish", "bound": "hbm", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
