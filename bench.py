@@ -174,7 +174,7 @@ def run_reference(args):
     t_lin = statistics.mean(x["t_lin"] for x in times)
     value = 1.0 / t_step
     sample = ("full %s world; H,b build timed in full (%.3f s); Schur-PCG timed for 2 and 8 CG iterations (%.4f s/iteration) and "
-              "extrapolated to %d iterations (the count our arm needs at rtol %.0e); single thread" %
+              "extrapolated to %d iterations (what this 3x3 block-Jacobi PCG needs at rtol %.0e: measured on the GPU with --pcg-precond 1); single thread" %
               (args.workload, t_lin, statistics.mean(x["t_cg_iter"] for x in times), iters_full, args.pcg_rtol))
     line = {
         "impl": "reference", "metric": "gn_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
