@@ -127,10 +127,10 @@ def recorded_block_jacobi_iterations(workload, default):
 
 
 def make_world(name):
-    from prb_project_bearing_only_slam_b200 import capi
-    from prb_project_bearing_only_slam_b200.problem import Problem
+    from synth import synth_world                                           # own library: the CPU arm never maps libbos_b200.so
+    from prb_project_bearing_only_slam_b200.problem import Problem          # pure Python (id -> stix bookkeeping)
     NP, NL, E, solver = WORKLOADS[name]
-    w = capi.synth_world(NP, NL, E, seed=SEED)
+    w = synth_world(NP, NL, E, seed=SEED)
     pr = Problem(w["pose_ids"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"], w["o_omega"],
                  fixed_pose_id=int(w["pose_ids"][0]))
     return w, pr, solver

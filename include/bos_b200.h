@@ -58,8 +58,9 @@ typedef struct bos_options {
     double damping;           /* slam/solver.cpp:17  default 0.01 */
     int pcg_max_iters;        /* default 20000 (block-Jacobi needs ~5300 CG iterations on a 200k-pose odometry chain) */
     double pcg_rtol;          /* stop when sqrt(r^T M^-1 r) <= rtol * its initial value; default 1e-10 */
-    int pcg_variant;          /* 0 = one persistent cooperative kernel for the whole PCG solve (default; falls back to 1 when a
-                                 landmark has more than 1024 observations), 1 = classic loop of small kernels */
+    int pcg_variant;          /* 0 = one persistent cooperative kernel for the whole PCG solve (default; falls back to 1 when a CTA's
+                                 chunk of poses does not fit: more than 2048 poses per chunk or more dynamic shared memory than an SM
+                                 has), 1 = classic loop of small kernels */
     int pcg_precond;          /* fused kernel, FP64 only: 0 = chain blocks + coarse space (default): per chunk of ~NP/148 poses the
                                  block-tridiagonal matrix of the Schur diagonal blocks and the pose-pose blocks of consecutive poses,
                                  factorised once per solve and applied exactly (block-Jacobi with chunk-sized blocks), plus a
@@ -86,6 +87,12 @@ typedef struct bos_stats {
     float ms_solve;
     float ms_update;
     float ms_allreduce;
+    int precond_used;         /* PCG: the preconditioner that actually ran, in bos_options.pcg_precond numbering (a request for the
+                                 chain / coarse-space preconditioner is downgraded when its factors do not fit in shared memory, in
+                                 FP32, and after a CG breakdown); -1 when the dense solver ran */
+    int pcg_resolves;         /* 1: the PCG broke down under the chain / coarse preconditioner and was run again with 3x3 blocks */
+    double state_digest;      /* sum of every scalar of the state AFTER the update (x + y + c + s per pose, x + y per landmark):
+                                 lets two runs (1 GPU vs N GPUs, device vs host stepping) be compared without downloading the state */
 } bos_stats;
 
 BOS_API void bos_default_options(bos_options* o);
@@ -104,7 +111,9 @@ BOS_API int bos_set_damping_factor(bos_ctx* ctx, double df);
  * ids already resolved to stix (the reference resolves them per edge per iteration through
  * std::map::at, framework/state.cpp:43-63).  Host buffers are borrowed for the call and copied.
  * b_omega may be NULL (= 1, framework/observation.hpp:17).  o_z is [Eo][3]; o_omega is [Eo][9]
- * row-major, assumed symmetric as utils/g2o_utils.cpp:91-106 builds it.
+ * row-major and must be symmetric, as utils/g2o_utils.cpp:91-106 builds it (the kernels keep the upper
+ * triangle; a non-symmetric matrix is refused with BOS_ERR_INVALID instead of silently differing from
+ * the reference's full 3x3 product).
  * Builds the CSR-of-blocks sparsity pattern and the per-edge block slots. */
 BOS_API int bos_upload_problem(bos_ctx* ctx, int NP, int NL, int fixed_pose_stix,
                        int64_t Eb, const int32_t* b_pose, const int32_t* b_lm, const double* b_z, const double* b_omega,
@@ -120,7 +129,7 @@ BOS_API int bos_get_state(bos_ctx* ctx, double* poses_xycs, double* lms_xy);
  *   update    : line  96     (State::apply_boxplus, framework/state.cpp:69-80) */
 BOS_API int bos_linearize(bos_ctx* ctx);
 BOS_API int bos_solve(bos_ctx* ctx);
-BOS_API int bos_update(bos_ctx* ctx);
+BOS_API int bos_update(bos_ctx* ctx);   /* needs an increment from bos_solve / bos_upload_delta; applies it once (BOS_ERR_STATE otherwise) */
 
 /* Solver::step(): exactly one GN iteration including the state update, state resident on the device. */
 BOS_API int bos_step(bos_ctx* ctx, bos_stats* stats);
@@ -223,32 +232,6 @@ BOS_API int bos_batch_step(bos_batch* b, double* chi2, double* delta_inf, int32_
  * CUDA-event time of the n_steps launches. */
 BOS_API int bos_batch_step_device(bos_batch* b, int n_steps, float* elapsed_ms);
 BOS_API const char* bos_batch_last_error(const bos_batch* b);
-
-/* ---- synthetic bearing-only worlds (bench / tests input generator; host code) ----------------- */
-typedef struct bos_synth_spec {
-    int n_poses;
-    int n_landmarks;
-    int64_t target_bearing_edges;   /* sensor range is tuned to approach this count */
-    uint64_t seed;
-    double bearing_sigma;           /* default 3e-3 rad */
-    double odom_sigma_xy;           /* default 1/sqrt(500) */
-    double odom_sigma_theta;        /* default 1/sqrt(5000) */
-    double init_drift;              /* amplitude (m) of the smooth drift applied to the ground truth for the initial guess */
-    double init_noise;              /* white noise (m, rad/10) on the initial guess */
-    int reserved[8];
-} bos_synth_spec;
-typedef struct bos_synth bos_synth;
-BOS_API void bos_synth_default_spec(bos_synth_spec* s);
-BOS_API int bos_synth_create(const bos_synth_spec* spec, bos_synth** out);
-BOS_API int bos_synth_destroy(bos_synth* w);
-/* counts[0..3] = NP, NL, Eb, Eo */
-BOS_API int bos_synth_counts(const bos_synth* w, int64_t* counts4);
-/* ids and values of the generated world; every pointer may be NULL.  Values are rounded to float and
- * widened, as the g2o loader does (utils/g2o_utils.cpp: std::stof). */
-BOS_API int bos_synth_get(const bos_synth* w, int32_t* pose_ids, double* poses_xyt_init, double* poses_xyt_true,
-                  int32_t* lm_ids, double* lms_xy_true,
-                  int32_t* b_pose_id, int32_t* b_lm_id, double* b_z,
-                  int32_t* o_src_id, int32_t* o_dst_id, double* o_z, double* o_omega);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,10 @@ struct IOracle {
     virtual void bearing_jacobians(int e, double* ana5, double* num5) = 0;
     virtual void odometry_jacobians(int e, double* ana18, double* num18) = 0;
     virtual double time_linearize(int reps) = 0;
+    virtual int solve_sparse(double deadline_s, double* info8) = 0;
+    virtual double time_linearize_literal(int reps) = 0;
+    virtual double literal_max_diff() = 0;
+    virtual void set_wrap_branch(int n, const int* edges, const int* signs) = 0;
 };
 
 template <class T>
@@ -166,7 +170,51 @@ struct Impl : IOracle {
         if (b) for (size_t i = 0; i < bn.size(); i++) b[i] = bn[i];
     }
     void solve(int kind, int max_iters, double rtol) override {
-        if (kind == 0) o.solve_dense_ldlt(); else o.solve_schur_pcg(max_iters, rtol);
+        if (kind == 0) o.solve_dense_ldlt(); else if (kind == 2) o.solve_sparse_ldlt(); else o.solve_schur_pcg(max_iters, rtol);
+    }
+    int solve_sparse(double deadline_s, double* info8) override {
+        const bool ok = o.solve_sparse_ldlt(deadline_s);
+        if (info8) {
+            info8[0] = o.t_order; info8[1] = o.t_analyze; info8[2] = o.t_factor; info8[3] = o.t_trisolve; info8[4] = (double)o.ldlt.nnzL;
+            info8[5] = o.ldlt.flops; info8[6] = o.t_export; info8[7] = o.ldlt.status;
+        }
+        return ok ? 0 : 1;
+    }
+    double time_linearize_literal(int reps) override {
+        auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; r++) o.linearize_literal();
+        auto t1 = std::chrono::steady_clock::now();
+        return std::chrono::duration<double>(t1 - t0).count() / reps;
+    }
+    // max |H_literal - H_blocks| over the entries of the exported CSC (with the fixed pose's rows / columns kept in the literal matrix)
+    double literal_max_diff() override {
+        std::vector<T> bsave = o.bvec;
+        o.linearize_literal();
+        std::vector<T> blit = o.bvec;
+        o.linearize();
+        double worst = 0;
+        for (size_t i = 0; i < blit.size(); i++) worst = std::max(worst, std::abs((double)blit[i] - (double)o.bvec[i]));
+        Csc<T> A; std::vector<T> bnv;
+        o.export_csc(A, bnv);
+        // index map nofixed -> full
+        std::vector<int> full(A.n);
+        for (int i = 0, k = 0; i < o.N; i++) if (o.nofixed_index(i) >= 0) full[k++] = i;
+        for (int j = 0; j < A.n; j++)
+            for (int q = A.colptr[j]; q < A.colptr[j + 1]; q++) {
+                const int gi = full[A.rowidx[q]], gj = full[j];
+                double v = 0; bool found = false;
+                for (int t = o.Hlit.colptr[gj]; t < o.Hlit.colptr[gj + 1]; t++)
+                    if (o.Hlit.rowidx[t] == gi) { v = (double)o.Hlit.val[t]; found = true; break; }
+                if (!found) return 1e300;
+                worst = std::max(worst, std::abs(v - (double)A.val[q]));
+            }
+        csc_valid = false;
+        (void)bsave;
+        return worst;
+    }
+    void set_wrap_branch(int n, const int* edges, const int* signs) override {
+        o.wrap_branch.clear();
+        for (int i = 0; i < n; i++) o.wrap_branch[edges[i]] = signs[i] >= 0 ? 1 : -1;
     }
     void get_delta(double* d) override { for (size_t i = 0; i < o.delta.size(); i++) d[i] = o.delta[i]; }
     void set_delta(const double* d) override { o.delta.resize(o.N); for (int i = 0; i < o.N; i++) o.delta[i] = (T)d[i]; }
@@ -261,6 +309,10 @@ void orc_predict_odometry(void* h, const double* s, const double* d, double* out
 void orc_bearing_jacobians(void* h, int e, double* ana5, double* num5) { H(h)->bearing_jacobians(e, ana5, num5); }
 void orc_odometry_jacobians(void* h, int e, double* ana18, double* num18) { H(h)->odometry_jacobians(e, ana18, num18); }
 double orc_time_linearize(void* h, int reps) { return H(h)->time_linearize(reps); }
+int orc_solve_sparse(void* h, double deadline_s, double* info8) { return H(h)->solve_sparse(deadline_s, info8); }
+double orc_time_linearize_literal(void* h, int reps) { return H(h)->time_linearize_literal(reps); }
+double orc_literal_max_diff(void* h) { return H(h)->literal_max_diff(); }
+void orc_set_wrap_branch(void* h, int n, const int* edges, const int* signs) { H(h)->set_wrap_branch(n, edges, signs); }
 double orc_smallest_angle(int use_double, double a) { return use_double ? smallest_angle<double>(a) : (double)smallest_angle<float>((float)a); }
 double orc_normalized_angle(int use_double, double a) { return use_double ? normalized_angle<double>(a) : (double)normalized_angle<float>((float)a); }
 void orc_colpiv_solve(int use_double, int M, const double* A, const double* b, double* out2) {

@@ -18,7 +18,7 @@ _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 def build(force=False):
     so = os.path.join(_HERE, "libbos_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("bos_oracle_capi.cpp", "bos_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("bos_oracle_capi.cpp", "bos_oracle.hpp", "bos_sparse_ldlt.hpp")]
     stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libbos_oracle.so"], stdout=subprocess.DEVNULL)
@@ -47,6 +47,11 @@ def lib():
         L.orc_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orc_solve_sparse.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.orc_time_linearize_literal.restype = C.c_double
+        L.orc_time_linearize_literal.argtypes = [C.c_void_p, C.c_int]
+        L.orc_literal_max_diff.restype = C.c_double
+        L.orc_literal_max_diff.argtypes = [C.c_void_p]
     return _LIB
 
 
@@ -181,6 +186,26 @@ class Oracle:
 
     def solve(self, kind=0, max_iters=2000, rtol=1e-12):
         self.L.orc_solve(self.h, kind, max_iters, rtol)
+
+    def solve_sparse(self, deadline_s=0.0):
+        """The reference's own solver restated (SimplicialLDLT: minimum-degree ordering + symbolic phase once, up-looking LDL^T per
+        call).  Returns a dict of timings / fill; 'finished' is False when deadline_s (seconds, 0 = none) cut the factorisation."""
+        info = np.zeros(8)
+        rc = self.L.orc_solve_sparse(self.h, float(deadline_s), _p(info))
+        return dict(finished=(rc == 0), t_order=info[0], t_analyze=info[1], t_factor=info[2], t_trisolve=info[3], nnzL=int(info[4]),
+                    flops=info[5], t_export=info[6], status=int(info[7]))
+
+    def time_linearize_literal(self, reps=1):
+        """Seconds per H, b build with the reference's literal per-edge sparse merge (slam/solver.cpp:44,60): O(N + nnz H) per edge."""
+        return float(self.L.orc_time_linearize_literal(self.h, reps))
+
+    def literal_max_diff(self):
+        return float(self.L.orc_literal_max_diff(self.h))
+
+    def set_wrap_branch(self, edges, signs):
+        """Test hook: put the bearing edges `edges` (residual within 1e-9 of +-pi) on the branch `signs` (+1 / -1)."""
+        e = np.ascontiguousarray(edges, np.int32); s = np.ascontiguousarray(signs, np.int32)
+        self.L.orc_set_wrap_branch(self.h, len(e), _p(e), _p(s))
 
     def delta(self):
         d = np.zeros(self.counts()["N"])

@@ -14,8 +14,8 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbos_b200.so")
 
 CU_SOURCES = ["linearize.cu", "solve_pcg.cu", "solve_dense.cu", "misc.cu", "ctx.cu"]
-CPP_SOURCES = ["pattern.cpp", "synth.cpp"]
-HEADERS = ["bos_internal.h", "bos_math.cuh", "bos_schur.cuh", os.path.join("..", "..", "include", "bos_b200.h")]
+CPP_SOURCES = ["pattern.cpp"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".hpp"))) + [os.path.join("..", "..", "include", "bos_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libproj02_b200.so")
 EXE = os.path.join(HERE, "bearing_only_slam")
+SYNTH = os.path.join(os.path.dirname(HERE), "synth")   # input generator of the harness' --synth mode: its own library
 SOURCES = ["framework/state.cpp", "utils/g2o_utils.cpp", "slam/triangulation.cpp", "slam/solver.cpp"]
 HEADERS = ["framework/linalg.hpp", "framework/definitions.hpp", "framework/state.hpp", "framework/observation.hpp", "utils/g2o_utils.hpp",
            "slam/triangulation.hpp", "slam/solver.hpp", "../../include/bos_b200.h"]
@@ -35,8 +36,14 @@ def build(force=False):
     if force or _stale(LIB, deps):
         _run(["g++"] + CXXFLAGS + ["-shared", "-o", LIB] + srcs + link)
     exe_src = os.path.join(HOST, "executables", "bearing_only_slam.cpp")
-    if force or _stale(EXE, deps + [exe_src, LIB]):
-        _run(["g++"] + CXXFLAGS + ["-o", EXE, exe_src, "-L" + HERE, "-lproj02_b200", "-lbos_b200", "-Wl,-rpath,$ORIGIN"])
+    import sys as _sys
+    if os.path.dirname(HERE) not in _sys.path:
+        _sys.path.insert(0, os.path.dirname(HERE))
+    from synth import build as build_synth
+    synth_lib = build_synth()
+    if force or _stale(EXE, deps + [exe_src, LIB, synth_lib]):
+        _run(["g++"] + CXXFLAGS + ["-I" + SYNTH, "-o", EXE, exe_src, "-L" + HERE, "-lproj02_b200", "-lbos_b200", "-L" + SYNTH, "-lbos_synth",
+                                   "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../synth"])
     return LIB, EXE
 
 

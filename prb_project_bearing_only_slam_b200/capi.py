@@ -27,7 +27,8 @@ class Stats(C.Structure):
     _fields_ = [("chi2_bearing", C.c_double), ("chi2_odometry", C.c_double), ("over_bearing", C.c_int64),
                 ("over_odometry", C.c_int64), ("delta_inf", C.c_double), ("solver_status", C.c_int),
                 ("solver_used", C.c_int), ("pcg_iterations", C.c_int), ("gpu_launches", C.c_int),
-                ("ms_linearize", C.c_float), ("ms_solve", C.c_float), ("ms_update", C.c_float), ("ms_allreduce", C.c_float)]
+                ("ms_linearize", C.c_float), ("ms_solve", C.c_float), ("ms_update", C.c_float), ("ms_allreduce", C.c_float),
+                ("precond_used", C.c_int), ("pcg_resolves", C.c_int), ("state_digest", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -36,12 +37,6 @@ class Stats(C.Structure):
 class PatternInfo(C.Structure):
     _fields_ = [("n_hpl", C.c_int64), ("n_hpp_off", C.c_int64), ("csc_n", C.c_int64), ("csc_nnz", C.c_int64),
                 ("N", C.c_int64), ("vals_len", C.c_int64)]
-
-
-class SynthSpec(C.Structure):
-    _fields_ = [("n_poses", C.c_int), ("n_landmarks", C.c_int), ("target_bearing_edges", C.c_int64), ("seed", C.c_uint64),
-                ("bearing_sigma", C.c_double), ("odom_sigma_xy", C.c_double), ("odom_sigma_theta", C.c_double),
-                ("init_drift", C.c_double), ("init_noise", C.c_double), ("reserved", C.c_int * 8)]
 
 
 # every symbol include/bos_b200.h declares (tests check the library exports all of them)
@@ -53,8 +48,7 @@ SYMBOLS = [
     "bos_edge_terms", "bos_host_pattern_create", "bos_host_pattern_destroy", "bos_host_pattern_info",
     "bos_host_pattern_get", "bos_host_pattern_checksum", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
     "bos_set_edge_shard", "bos_get_edge_shard", "bos_batch_create", "bos_batch_destroy", "bos_batch_set_states",
-    "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error", "bos_synth_default_spec",
-    "bos_synth_create", "bos_synth_destroy", "bos_synth_counts", "bos_synth_get",
+    "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error",
     "bos_triangulate_landmarks", "bos_eval_bearing_edges", "bos_eval_odometry_edges", "bos_step_lm",
 ]
 
@@ -113,12 +107,6 @@ def lib():
         L.bos_batch_step_device.argtypes = [vp, i32, C.POINTER(C.c_float)]
         L.bos_batch_last_error.argtypes = [vp]
         L.bos_batch_last_error.restype = C.c_char_p
-        L.bos_synth_default_spec.argtypes = [C.POINTER(SynthSpec)]
-        L.bos_synth_default_spec.restype = None
-        L.bos_synth_create.argtypes = [C.POINTER(SynthSpec), C.POINTER(vp)]
-        L.bos_synth_destroy.argtypes = [vp]
-        L.bos_synth_counts.argtypes = [vp, vp]
-        L.bos_synth_get.argtypes = [vp] + [vp] * 12
         L.bos_triangulate_landmarks.argtypes = [C.POINTER(Options), i32, vp, i64, vp, vp, vp, i32, vp, C.POINTER(C.c_int)]
         L.bos_eval_bearing_edges.argtypes = [C.POINTER(Options), i64, vp, vp, vp, vp, vp]
         L.bos_eval_odometry_edges.argtypes = [C.POINTER(Options), i64, vp, vp, vp, vp, vp]
@@ -400,28 +388,10 @@ class Batch:
 
 
 def synth_world(n_poses, n_landmarks, target_bearing_edges, seed=0xB0500000, **kw):
-    """Generates a synthetic world (host code in the library) and returns its arrays."""
-    L = lib()
-    spec = SynthSpec()
-    L.bos_synth_default_spec(C.byref(spec))
-    spec.n_poses, spec.n_landmarks, spec.target_bearing_edges, spec.seed = int(n_poses), int(n_landmarks), int(target_bearing_edges), int(seed)
-    for k, v in kw.items():
-        setattr(spec, k, v)
-    h = C.c_void_p()
-    rc = L.bos_synth_create(C.byref(spec), C.byref(h))
-    if rc != OK:
-        raise BosError(rc, "bos_synth_create")
-    try:
-        cnt = np.zeros(4, np.int64)
-        L.bos_synth_counts(h, _ptr(cnt))
-        NP, NL, Eb, Eo = [int(x) for x in cnt]
-        w = dict(pose_ids=np.zeros(NP, np.int32), poses_init=np.zeros((NP, 3)), poses_true=np.zeros((NP, 3)),
-                 lm_ids=np.zeros(NL, np.int32), lms_true=np.zeros((NL, 2)),
-                 b_pose_id=np.zeros(Eb, np.int32), b_lm_id=np.zeros(Eb, np.int32), b_z=np.zeros(Eb),
-                 o_src_id=np.zeros(Eo, np.int32), o_dst_id=np.zeros(Eo, np.int32), o_z=np.zeros((Eo, 3)), o_omega=np.zeros((Eo, 9)))
-        L.bos_synth_get(h, _ptr(w["pose_ids"]), _ptr(w["poses_init"]), _ptr(w["poses_true"]), _ptr(w["lm_ids"]), _ptr(w["lms_true"]),
-                        _ptr(w["b_pose_id"]), _ptr(w["b_lm_id"]), _ptr(w["b_z"]), _ptr(w["o_src_id"]), _ptr(w["o_dst_id"]),
-                        _ptr(w["o_z"]), _ptr(w["o_omega"]))
-    finally:
-        L.bos_synth_destroy(h)
-    return w
+    """The synthetic-world generator lives in its own library (synth/, not part of libbos_b200.so); kept here as a forwarder."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from synth import synth_world as gen
+    return gen(n_poses, n_landmarks, target_bearing_edges, seed=seed, **kw)

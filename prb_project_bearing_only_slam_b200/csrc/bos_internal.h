@@ -104,7 +104,7 @@ struct Dev {
     S* Hoff = nullptr;  // 3x3 row-major, block H[lo][hi]
     S* Hpl = nullptr;   // SoA: entry k (3x2 row-major index) of block s at Hpl[k * hpl_ld + s]
     S* bnd = nullptr;         // [tiles][2][9] bearing sums of pose runs cut by a tile boundary (K1 -> K2)
-    double* stats = nullptr;  // [8] chi2_b, chi2_o, over_b, over_o, delta_inf(bits), status, -, -
+    double* stats = nullptr;  // [8] chi2_b, chi2_o, over_b, over_o, delta_inf(bits), status, state digest (k_update), -
     S* delta = nullptr;       // [N]
 };
 
@@ -190,6 +190,8 @@ struct PcgWork {
     double* cRc = nullptr;   // [pc_chunks][6] per chunk: P^T r restricted to its rows (left node, right node)
     double* cStats = nullptr;  // [8] scratch status of the coarse factorisation
     int sm_count = 148;
+    int precond_used = 1;    // what the last solve actually ran (reported through bos_stats)
+    int resolves = 0;        // 1: the last solve broke down under the chain / coarse preconditioner and was repeated with 3x3 blocks
 };
 template <typename S>
 int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st,

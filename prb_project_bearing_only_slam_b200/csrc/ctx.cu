@@ -88,6 +88,7 @@ struct bos_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     bool have_problem = false, linearized = false, solved = false;
+    bool delta_valid = false;            // set by bos_solve / bos_upload_delta, consumed by bos_update
     HostPattern P;
     DevAlloc mem;
     Dev<double> dd;
@@ -406,6 +407,7 @@ int solve_impl(bos_ctx* c) {
         if (e) return e;
         rc = launch_dense_solve<S>(d, dwork<S>(c), c->opt.damping, c->stream, &nl);
         c->stats.pcg_iterations = 0;
+        c->stats.precond_used = -1; c->stats.pcg_resolves = 0;
         c->pcg_bad = false; c->pcg_capped = false;
     } else {
         int e = ensure_pcg<S>(c);
@@ -416,6 +418,7 @@ int solve_impl(bos_ctx* c) {
         rc = launch_pcg_solve<S>(d, pwork<S>(c), c->opt.pcg_max_iters, rtol, c->stream, &iters, &nl);
         if (rc < 0) return fail(c, BOS_ERR_CUDA, std::string("pcg: ") + cudaGetErrorString(cudaGetLastError()));
         c->stats.pcg_iterations = iters;
+        c->stats.precond_used = pwork<S>(c).precond_used; c->stats.pcg_resolves = pwork<S>(c).resolves;
         c->pcg_bad = (rc == 1);
         c->pcg_capped = (rc == 0 && iters >= c->opt.pcg_max_iters);
     }
@@ -431,7 +434,7 @@ int solve_impl(bos_ctx* c) {
         if (n.Broadcast(d.delta, d.delta, (size_t)(3 * (size_t)d.NP + 2 * (size_t)d.NL), dt, 0, c->comm, c->stream) != 0)
             return fail(c, BOS_ERR_NCCL, "ncclBroadcast of the increment failed");
     }
-    c->solved = true;
+    c->solved = true; c->delta_valid = true;
     return BOS_OK;
 }
 
@@ -439,7 +442,7 @@ template <typename S>
 int update_impl(bos_ctx* c) {
     c->launches += launch_update<S>(dev<S>(c), c->stream);
     CUDA_OK(c, cudaGetLastError());
-    c->linearized = false; c->solved = false;
+    c->linearized = false; c->solved = false; c->delta_valid = false;
     return BOS_OK;
 }
 
@@ -451,6 +454,7 @@ int fetch_stats(bos_ctx* c) {
     c->stats.chi2_bearing = h[0]; c->stats.chi2_odometry = h[1];
     c->stats.over_bearing = (int64_t)llround(h[2]); c->stats.over_odometry = (int64_t)llround(h[3]);
     c->stats.delta_inf = h[4];
+    c->stats.state_digest = h[6];
     c->stats.solver_status = (h[5] != 0.0 || c->pcg_bad) ? 1 : (c->pcg_capped ? 2 : 0);
     c->stats.solver_used = c->solver_used;
     return BOS_OK;
@@ -692,8 +696,17 @@ int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t 
     if (!c) return BOS_ERR_INVALID;
     if ((Eb > 0 && (!b_pose || !b_lm || !b_z)) || (Eo > 0 && (!o_src || !o_dst || !o_z || !o_omega)))
         return fail(c, BOS_ERR_INVALID, "null edge array");
+    // the kernels keep the upper triangle of every odometry Omega: refuse a matrix the reference would treat differently
+    // (it multiplies with the full 3x3, slam/solver.cpp:60-61; utils/g2o_utils.cpp:91-106 always builds a symmetric one)
+    for (int64_t e = 0; e < Eo; e++) {
+        const double* om = o_omega + 9 * e;
+        double mx = 0.0;
+        for (int k = 0; k < 9; k++) mx = std::max(mx, std::fabs(om[k]));
+        if (std::fabs(om[1] - om[3]) > 1e-12 * mx || std::fabs(om[2] - om[6]) > 1e-12 * mx || std::fabs(om[5] - om[7]) > 1e-12 * mx)
+            return fail(c, BOS_ERR_INVALID, "odometry omega of edge " + std::to_string(e) + " is not symmetric");
+    }
     CUDA_OK(c, cudaSetDevice(c->opt.device));
-    c->have_problem = false; c->dense_ready = false; c->pcg_ready = false;
+    c->have_problem = false; c->delta_valid = false; c->dense_ready = false; c->pcg_ready = false;
     c->lm_pose_bak = nullptr; c->lm_lm_bak = nullptr;
     c->mem.release();
     if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count) != 0)
@@ -759,6 +772,7 @@ int bos_solve(bos_ctx* c) {
 int bos_update(bos_ctx* c) {
     if (!c) return BOS_ERR_INVALID;
     NEED(c, c->have_problem, "update before upload_problem");
+    NEED(c, c->delta_valid, "update without an increment: call bos_solve or bos_upload_delta first (an increment is applied once)");
     CUDA_OK(c, cudaSetDevice(c->opt.device));
     int rc = DISPATCH(c, update_impl, c);
     if (rc) return rc;
@@ -892,6 +906,7 @@ int bos_upload_delta(bos_ctx* c, const double* delta) {
         std::vector<float> v = narrow<float>(delta, (size_t)c->P.N);
         CUDA_OK(c, cudaMemcpy(c->df.delta, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+    c->delta_valid = true;
     return BOS_OK;
 }
 

@@ -524,34 +524,39 @@ int launch_edge_terms(const Dev<S>& d, S* err_b, S* jac_b, S* err_o, S* jac_o, c
 // X <- v2t(dx) * X:  R' = R(dth) R, t' = R(dth) t + dt ; landmarks += dx.  Also max |dx| for the stats.
 template <typename S>
 __global__ void __launch_bounds__(256) k_update(Dev<S> d) {
-    __shared__ double red[8];
+    __shared__ double red[8], red2[8];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double m = 0.0;
+    double m = 0.0, dig = 0.0;
     if (i < d.NP) {
         S dx = d.delta[3LL * i], dy = d.delta[3LL * i + 1], dt = d.delta[3LL * i + 2];
-        PoseV<S> X = load_pose<S>(d.pose, i);
+        S* o = d.pose + 4LL * i;
+        const PoseV<S> X = {o[0], o[1], o[2], o[3]};   // plain (coherent) loads: this kernel rewrites the pose
         S sd, cd;
         sincos(dt, &sd, &cd);
-        S* o = d.pose + 4LL * i;
         o[0] = (cd * X.x + (-sd) * X.y) + dx;
         o[1] = (sd * X.x + cd * X.y) + dy;
         o[2] = cd * X.c + (-sd) * X.s;
         o[3] = sd * X.c + cd * X.s;
         d.theta[i] = pose_theta<S>(PoseV<S>{o[0], o[1], o[2], o[3]});
+        dig = (double)o[0] + (double)o[1] + (double)o[2] + (double)o[3];
         m = fmax(fabs((double)dx), fmax(fabs((double)dy), fabs((double)dt)));
     } else if (i < d.NP + d.NL) {
         const int j = i - d.NP;
         S dx = d.delta[3LL * d.NP + 2LL * j], dy = d.delta[3LL * d.NP + 2LL * j + 1];
-        d.lm[2LL * j] += dx;
-        d.lm[2LL * j + 1] += dy;
+        const S nx = d.lm[2LL * j] + dx, ny = d.lm[2LL * j + 1] + dy;
+        d.lm[2LL * j] = nx;
+        d.lm[2LL * j + 1] = ny;
+        dig = (double)nx + (double)ny;
         m = fmax(fabs((double)dx), fabs((double)dy));
     }
+    dig = warp_sum(dig);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(BOS_FULL_MASK, m, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; red2[threadIdx.x >> 5] = dig; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; w++) m = fmax(m, red[w]);
+        for (int w = 1; w < 8; w++) { m = fmax(m, red[w]); dig += red2[w]; }
+        atomicAdd(d.stats + 6, dig);
         // non-negative doubles order like their bit patterns
         atomicMax(reinterpret_cast<unsigned long long*>(d.stats + 4), (unsigned long long)__double_as_longlong(m));
     }

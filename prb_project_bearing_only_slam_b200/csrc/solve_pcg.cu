@@ -1466,6 +1466,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     if (precond == 0 && w.c_nc > 3 * 160) precond = 2;
     const int precond_asked = w.precond;
     w.precond = precond;
+    w.precond_used = precond;
     k_pcg_fused_prep<S><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(d, w); nl++;
     if (precond != 1) { k_pcg_chain_factor<S><<<d.pc_chunks, 64, 0, st>>>(d, w); nl++; }
     if (precond == 0) {   // coarse operator A_c = P^T S P, its Cholesky factor and explicit inverse
@@ -1500,6 +1501,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
 template <typename S>
 int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol, cudaStream_t st,
                      int* iterations_out, int* launches) {
+    w.resolves = 0;
     if (w.variant == 0 && pcg_fused_supported<S>(d)) {
         int rc = launch_pcg_fused<S>(d, w, max_iters, rtol, st, iterations_out, launches);
         if (rc == 1 && w.precond != 1) {
@@ -1508,6 +1510,7 @@ int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
             const int asked = w.precond;
             int nl2 = 0, it2 = 0;
             w.precond = 1;
+            w.resolves = 1;
             rc = launch_pcg_fused<S>(d, w, max_iters, rtol, st, &it2, &nl2);
             w.precond = asked;
             if (iterations_out) *iterations_out += it2;
@@ -1516,6 +1519,7 @@ int launch_pcg_solve(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
         return rc;
     }
     int nl = 0;
+    w.precond_used = 1;
     const int n = 3 * d.NP;
     const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256, gh = (d.n_hpl + 255) / 256, gn = (n + 255) / 256;
     cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), st);

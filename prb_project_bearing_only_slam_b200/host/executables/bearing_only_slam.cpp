@@ -15,6 +15,7 @@
 #include "../slam/solver.hpp"
 #include "../slam/triangulation.hpp"
 #include "../utils/g2o_utils.hpp"
+#include "bos_synth.h"   // synth/: the input generator is its own library, not part of libbos_b200.so
 
 using namespace proj02;
 
@@ -55,12 +56,12 @@ int main(int argc, char** argv) {
     int fixed_pose_id;
     float bound = 0;
     if (synth_np > 0) {
-        // the library's synthetic world generator, fed through the same State / observation API a file would go through
+        // the synthetic world generator (synth/libbos_synth.so), fed through the same State / observation API a file would go through
         bos_synth_spec spec;
         bos_synth_default_spec(&spec);
         spec.n_poses = synth_np; spec.n_landmarks = synth_nl; spec.target_bearing_edges = synth_e;
         bos_synth* w = nullptr;
-        if (bos_synth_create(&spec, &w) != BOS_OK) { std::cout << "cannot generate the synthetic world" << std::endl; return 2; }
+        if (bos_synth_create(&spec, &w) != 0) { std::cout << "cannot generate the synthetic world" << std::endl; return 2; }
         int64_t cnt[4];
         bos_synth_counts(w, cnt);
         std::vector<int32_t> pid(cnt[0]), bp(cnt[2]), bl(cnt[2]), os(cnt[3]), od(cnt[3]);

@@ -1,4 +1,5 @@
-// synth.cpp -- synthetic bearing-only worlds for the benchmark configurations (host code, not timed).
+// bos_synth.cpp -- synthetic bearing-only worlds for the benchmark configurations (host code, not timed; own library
+// libbos_synth.so, see bos_synth.h).
 //
 // Mirrors the statistics of the reference's bundled dataset (data/slam2D_bearing_only_*.g2o): unit-step
 // trajectory with half-turns at the row ends, landmarks uniform in the world, a range-limited sensor with
@@ -10,7 +11,7 @@
 // Deviation from a literal "dead-reckoned initial guess": integrating noisy odometry over 10^4..10^5 poses
 // drifts by kilometres, which no Gauss-Newton run recovers from; the initial guess here is the ground
 // truth plus a smooth low-frequency drift and white noise, and landmarks are triangulated from it.
-#include "../../include/bos_b200.h"
+#include "bos_synth.h"
 
 #include <algorithm>
 #include <cmath>
@@ -66,7 +67,7 @@ void bos_synth_default_spec(bos_synth_spec* s) {
 }
 
 int bos_synth_create(const bos_synth_spec* spec, bos_synth** out) {
-    if (!spec || !out || spec->n_poses < 2 || spec->n_landmarks < 1 || spec->target_bearing_edges < 1) return BOS_ERR_INVALID;
+    if (!spec || !out || spec->n_poses < 2 || spec->n_landmarks < 1 || spec->target_bearing_edges < 1) return 1;
     bos_synth* W = new bos_synth();
     W->spec = *spec;
     const int NP = spec->n_poses, NL = spec->n_landmarks;
@@ -201,31 +202,31 @@ int bos_synth_create(const bos_synth_spec* spec, bos_synth** out) {
     W->lms_true.resize(2 * (size_t)NL);
     for (int j = 0; j < NL; j++) { W->lms_true[2 * (size_t)j] = f32(lx[j]); W->lms_true[2 * (size_t)j + 1] = f32(ly[j]); }
     *out = W;
-    return BOS_OK;
+    return 0;
 }
 
 int bos_synth_destroy(bos_synth* w) {
     delete w;
-    return BOS_OK;
+    return 0;
 }
 
 int bos_synth_counts(const bos_synth* w, int64_t* c) {
-    if (!w || !c) return BOS_ERR_INVALID;
+    if (!w || !c) return 1;
     c[0] = (int64_t)w->pose_ids.size(); c[1] = (int64_t)w->lm_ids.size();
     c[2] = (int64_t)w->b_z.size(); c[3] = (int64_t)w->o_src_id.size();
-    return BOS_OK;
+    return 0;
 }
 
 int bos_synth_get(const bos_synth* w, int32_t* pose_ids, double* poses_xyt_init, double* poses_xyt_true, int32_t* lm_ids,
                   double* lms_xy_true, int32_t* b_pose_id, int32_t* b_lm_id, double* b_z, int32_t* o_src_id, int32_t* o_dst_id,
                   double* o_z, double* o_omega) {
-    if (!w) return BOS_ERR_INVALID;
+    if (!w) return 1;
     auto cp = [](auto& v, auto* dst) { if (dst) std::copy(v.begin(), v.end(), dst); };
     cp(w->pose_ids, pose_ids); cp(w->poses_init, poses_xyt_init); cp(w->poses_true, poses_xyt_true);
     cp(w->lm_ids, lm_ids); cp(w->lms_true, lms_xy_true);
     cp(w->b_pose_id, b_pose_id); cp(w->b_lm_id, b_lm_id); cp(w->b_z, b_z);
     cp(w->o_src_id, o_src_id); cp(w->o_dst_id, o_dst_id); cp(w->o_z, o_z); cp(w->o_omega, o_omega);
-    return BOS_OK;
+    return 0;
 }
 
 }  // extern "C"

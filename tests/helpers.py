@@ -50,14 +50,37 @@ def rel_block_err(a, b):
 
 
 def csc_rel_err(colptr, val_a, val_b):
-    """column-norm-relative error of two CSC value arrays on the same pattern"""
-    worst = 0.0
-    for j in range(len(colptr) - 1):
-        s, e = colptr[j], colptr[j + 1]
-        if e > s:
-            den = max(np.abs(val_b[s:e]).max(), 1e-300)
-            worst = max(worst, float(np.abs(val_a[s:e] - val_b[s:e]).max() / den))
-    return worst
+    """column-norm-relative error of two CSC value arrays on the same pattern (vectorised: 30 M entries at synth-2M)"""
+    colptr = np.asarray(colptr, np.int64)
+    if len(val_b) == 0:
+        return 0.0
+    starts = colptr[:-1]
+    nonempty = colptr[1:] > starts
+    idx = starts[nonempty]
+    den = np.maximum(np.maximum.reduceat(np.abs(val_b), idx), 1e-300)
+    num = np.maximum.reduceat(np.abs(np.asarray(val_a) - np.asarray(val_b)), idx)
+    return float((num / den).max())
+
+
+def chi2_odometry_tolerance(pr, o, rel=1e-9, dtheta=4e-15):
+    """Absolute tolerance for chi2_odometry = sum e^T Omega e.  On a dead-reckoned initial guess the odometry residuals are
+    float-rounding residues (|e_theta| ~ 1e-6), so the few-ulp disagreement between CUDA's and glibc's atan2 on the pose angles
+    (up to 4e-15 rad per residual: two angles of magnitude <= pi, 2 ulp each) is visible at ~1e-9 RELATIVE in the sum although
+    every term is as accurate as FP64 allows.  Tolerance = rel * chi2 + sum_e 2 |(Omega e)_theta| * dtheta, from the oracle's terms."""
+    eo = o.edge_terms()[2]
+    we = np.einsum("eij,ej->ei", pr.o_omega.reshape(-1, 3, 3), eo)
+    return rel * float(np.einsum("ei,ei->", we, eo)) + float((2 * np.abs(we[:, 2])).sum()) * dtheta
+
+
+def align_oracle_wrap_branch(o, eb_gpu):
+    """The +-pi policy: a bearing residual within 1e-9 of +-pi may wrap either way depending on the last bit
+    of atan2 -- in the reference's FP32 arithmetic as much as in FP64.  Puts the oracle on the branch the device took for exactly
+    those edges (test hook Oracle.set_wrap_branch) and returns their indices; everything else is compared unmodified."""
+    eb_orc = o.edge_terms()[0]
+    amb = np.where(np.abs(np.abs(eb_orc) - np.pi) < 1e-9)[0]
+    assert np.all(np.abs(np.abs(eb_gpu[amb]) - np.pi) < 1e-9)
+    o.set_wrap_branch(amb, np.where(eb_gpu[amb] >= 0, 1, -1))
+    return amb
 
 
 def angle_diff(a, b):

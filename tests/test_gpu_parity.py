@@ -4,7 +4,11 @@ Tolerances (stated by the north star):
   * sparsity pattern / edge-to-block indexing / landmark association: bit-exact
   * FP64: H, b, chi2 within 1e-9 (block / column-norm relative); dx and states within 1e-8 relative
     after one iteration and 1e-6 after 20 (rounding of two different factorisation orders amplified by
-    the conditioning of H, ~1e6 on the bundled data)
+    the conditioning of H, ~1e6 on the bundled data); chi2_odometry: 1e-9 relative plus the conditioning term of
+    helpers.chi2_odometry_tolerance (dead-reckoned residuals are rounding residues)
+  * +-pi policy: residuals within 1e-9 of +-pi (bundled data: exactly the three edges of the single-observation landmarks
+    69 / 112 / 114) are compared modulo 2 pi and the oracle is put on the device's branch for them (helpers.align_oracle_wrap_branch);
+    everything else, from iteration 0 on, is compared unmodified
   * FP32 path: H within 2e-4, b within 2e-3 (cancellation in J^T e), states within 5e-3 after 10 iterations (documented, not a parity claim)
 """
 import math
@@ -12,7 +16,8 @@ import math
 import numpy as np
 import pytest
 
-from helpers import (angle_diff, csc_rel_err, golden_problem, load_golden, oracle_for, rel_block_err, synth_problem)
+from helpers import (align_oracle_wrap_branch, angle_diff, chi2_odometry_tolerance, csc_rel_err, golden_problem, load_golden, oracle_for,
+                     rel_block_err, synth_problem)
 from prb_project_bearing_only_slam_b200 import capi
 
 pytestmark = pytest.mark.gpu
@@ -34,22 +39,10 @@ def golden_setup(name, dtype="f64"):
     return g, pr, o
 
 
-def align_wrap_branch(pr, o, eb_gpu, jb_orc):
-    """A bearing residual within rounding of +-pi may wrap either way (two-observation landmarks triangulated behind a
-    pose give exactly pi).  Returns the correction to the oracle's b that moves such edges onto the GPU's branch."""
-    eb_orc = o.edge_terms()[0]
-    amb = np.where((np.abs(np.abs(eb_orc) - np.pi) < 1e-9) & (np.sign(eb_orc) != np.sign(eb_gpu)))[0]
-    db = np.zeros(3 * pr.NP + 2 * pr.NL)
-    for e in amb:
-        om = 1.0 if pr.b_omega is None else pr.b_omega[e]
-        scale = lambda v: v * math.sqrt(1.0 / (v * om * v)) if v * om * v > 1.0 else v
-        de = scale(eb_gpu[e]) - scale(eb_orc[e])
-        p, l = pr.b_pose[e], pr.b_lm[e]
-        J = jb_orc[e].copy()
-        if p != pr.fixed_stix:
-            db[3 * p:3 * p + 3] += J[:3] * om * de
-        db[3 * pr.NP + 2 * l:3 * pr.NP + 2 * l + 2] += J[3:] * om * de
-    return db, amb
+# bearing edges (caller order) whose residual sits on the +-pi branch cut at the triangulated start of the bundled datasets: the single
+# edge of each single-observation landmark (the rank-1 basic solution of slam/triangulation.cpp:59 puts it exactly behind its pose)
+WRAP_EDGES = {"mini": [], "full": [29, 1324, 1515]}
+WRAP_LANDMARK_IDS = {"mini": [], "full": [112, 114, 69]}
 
 
 def nofixed(pr, v):
@@ -83,32 +76,41 @@ def test_pattern_and_H_b_chi2_match_oracle(built_lib, name):
     o.linearize()
     ctx.linearize()
     colptr, rowidx, val, b = ctx.csc()
-    ocol, orow, oval, ob = o.csc()
+    ocol, orow, oval, ob_raw = o.csc()
     assert np.array_equal(colptr, ocol) and np.array_equal(rowidx, orow)                 # bit-exact pattern
     assert np.array_equal(colptr, g["csc_colptr"]) and np.array_equal(rowidx, g["csc_rowidx"])
-    eb = ctx.edge_terms()[0]
-    db, amb = align_wrap_branch(pr, o, eb, o.edge_terms()[1])
-    ob = ob + nofixed(pr, db)
+    # the +-pi policy: exactly the edges of the single-observation landmarks sit on the cut, nothing else is touched
+    amb = align_oracle_wrap_branch(o, ctx.edge_terms()[0])
+    assert amb.tolist() == WRAP_EDGES[name] and pr.lm_ids[pr.b_lm[amb]].tolist() == WRAP_LANDMARK_IDS[name]
+    assert sorted(WRAP_LANDMARK_IDS[name]) == sorted(g["single_obs_f64"].tolist()) or name == "mini"
+    o.linearize()
+    _, _, oval, ob = o.csc()
+    # rows of b no branch-cut edge contributes to are identical with and without the alignment
+    touched = np.zeros(3 * pr.NP + 2 * pr.NL, bool)
+    for e in amb:
+        touched[3 * pr.b_pose[e]:3 * pr.b_pose[e] + 3] = True
+        touched[3 * pr.NP + 2 * pr.b_lm[e]:3 * pr.NP + 2 * pr.b_lm[e] + 2] = True
+    assert np.array_equal(ob[~nofixed(pr, touched)], ob_raw[~nofixed(pr, touched)])
     assert csc_rel_err(colptr, val, oval) <= TOL64
     assert np.abs(b - ob).max() <= TOL64 * np.abs(ob).max()
     st, os_ = ctx.stats(), o.stats()
     assert st.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=TOL64)
-    assert st.chi2_odometry == pytest.approx(os_["chi2_odometry"], rel=1e-7, abs=1e-15)
+    assert abs(st.chi2_odometry - os_["chi2_odometry"]) <= chi2_odometry_tolerance(pr, o)
     assert (st.over_bearing, st.over_odometry) == (os_["over_bearing"], os_["over_odometry"])
-    if len(amb) == 0:
-        assert csc_rel_err(colptr, val, g["csc_val_f64"]) <= TOL64
+    assert csc_rel_err(colptr, val, g["csc_val_f64"]) <= TOL64
 
 
 @pytest.mark.parametrize("name,solver", [("mini", capi.SOLVER_DENSE_CHOLESKY), ("full", capi.SOLVER_DENSE_CHOLESKY),
                                          ("mini", capi.SOLVER_PCG), ("full", capi.SOLVER_PCG)])
 def test_solve_and_update_match_oracle(built_lib, name, solver):
     g, pr, o = golden_setup(name)
-    # start two iterations in, where no residual sits on the +-pi branch cut
-    o.step(0); o.step(0)
-    P, L = o.state()
+    P, L = o.state()                          # iteration 0: the reference's own triangulated start
     ctx = make_ctx(pr, P, L, solver=solver, pcg_rtol=1e-13, pcg_max_iters=20000)
+    ctx.linearize()
+    o.linearize()
+    assert align_oracle_wrap_branch(o, ctx.edge_terms()[0]).tolist() == WRAP_EDGES[name]
     o.linearize(); o.solve(0)
-    ctx.linearize(); ctx.solve()
+    ctx.solve()
     d, od = ctx.delta(), o.delta()
     assert np.all(d[3 * pr.fixed_stix:3 * pr.fixed_stix + 3] == 0.0)                      # gauge: the fixed pose does not move
     assert np.abs(d - od).max() <= 1e-8 * np.abs(od).max()
@@ -128,14 +130,16 @@ def test_solve_and_update_match_oracle(built_lib, name, solver):
 @pytest.mark.parametrize("name,iters", [("mini", 50), ("full", 20)])
 def test_gn_trajectory_matches_oracle(built_lib, name, iters):
     g, pr, o = golden_setup(name)
-    o.step(0); o.step(0)                      # leave the +-pi branch cut of the triangulated start (see align_wrap_branch)
-    P, L = o.state()
+    P, L = o.state()                          # iteration 0: the reference's own triangulated start
     ctx = make_ctx(pr, P, L)
+    ctx.linearize(); o.linearize()
+    assert align_oracle_wrap_branch(o, ctx.edge_terms()[0]).tolist() == WRAP_EDGES[name]
     for it in range(iters):
         o.step(0)
         s = ctx.step()
         os_ = o.stats()
-        assert s.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=1e-7), it
+        # from iteration 1 on the two states differ by the solver rounding amplified by cond(H): 1e-7 / 1e-6 are state-drift tolerances
+        assert s.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=TOL64 if it == 0 else 1e-7), it
         assert s.chi2_odometry == pytest.approx(os_["chi2_odometry"], rel=1e-6, abs=1e-12), it
         assert s.over_bearing == os_["over_bearing"] and s.solver_status == 0
     P2, L2 = ctx.get_state(); oP, oL = o.state()
@@ -203,10 +207,10 @@ def test_setters_and_robust_kernel(built_lib):
     for kt, df in ((0.05, 0.5), (1e9, 1e-3)):
         o.set_params(kt, df); ctx.set_kernel_threshold(kt); ctx.set_damping_factor(df)
         o.linearize(); ctx.linearize()
+        align_oracle_wrap_branch(o, ctx.edge_terms()[0]); o.linearize()
         colptr, _, val, b = ctx.csc(); _, _, oval, ob = o.csc()
-        db, _ = align_wrap_branch(pr, o, ctx.edge_terms()[0], o.edge_terms()[1])
         assert csc_rel_err(colptr, val, oval) <= TOL64
-        assert np.abs(b - (ob + nofixed(pr, db))).max() <= TOL64 * np.abs(ob).max()
+        assert np.abs(b - ob).max() <= TOL64 * np.abs(ob).max()
         assert ctx.stats().over_bearing == o.stats()["over_bearing"]
 
 
