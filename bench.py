@@ -2,8 +2,10 @@
 """Benchmark of the hot path: full Gauss-Newton iterations (Solver::step) on a synthetic bearing-only world.
 
     python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA through the C ABI)
-    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host cores (CPU oracle)
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host cores: complete GN steps with a
+                                                             # sparse direct solve, run to completion (no extrapolation)
     torchrun ... bench.py --gpus N ...                       # N ranks: edge-sharded linearization + NCCL combine
+    python bench.py --workload full|mini|synth-100k|synth-20k|batch-4096   # the other BASELINE.json configs
 
 One "step" is one GN iteration: linearize + assemble (+ allreduce) + Schur/PCG solve + boxplus update.
 Prints ONE JSON line (rank 0).  `value` = GN iterations/s with the state resident in HBM; `e2e` = the same through
@@ -26,12 +28,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (poses, landmarks, target bearing edges, solver)   -- BASELINE.json configs[2], configs[3]
+    # name: (poses, landmarks, target bearing edges, solver)   -- BASELINE.json configs[3] (the metric's config), configs[2]
     "synth-2M": (200000, 50000, 2000000, "pcg"),
-    "synth-100k": (10000, 2000, 100000, "dense"),
-    "synth-20k": (2000, 400, 20000, "dense"),
+    "synth-100k": (10000, 2000, 100000, "auto"),
+    "synth-20k": (2000, 400, 20000, "auto"),
+    # BASELINE.json configs[1], configs[0]: the reference's bundled datasets (tests/golden/*.npz = data/*.g2o parsed into arrays)
+    "full": (301, 141, 2132, "auto"),
+    "mini": (3, 6, 15, "auto"),
+    # BASELINE.json configs[4]: 4096 independent mini-sized problems, one GN iteration per problem per launch
+    "batch-4096": (3, 6, 15, "batch"),
 }
 SEED = 0xB0500003
+CPU_STEP_BUDGET_S = 420.0      # the reference arm stops adding steps once it has run this long (a synth-2M step is ~4 minutes of CPU)
 
 
 def load_peaks():
@@ -116,78 +124,230 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def recorded_block_jacobi_iterations(workload, default):
-    """CG iterations per GN step of the 3x3 block-Jacobi PCG on this workload (measured on the GPU with --pcg-precond 1; the
-    CPU restatement runs the same algorithm at ~0.05 s per iteration, so it is extrapolated, not run to convergence)."""
-    p = os.path.join(ROOT, "profiles", "pcg_iterations.json")
-    try:
-        return int(json.load(open(p)).get(workload, default))
-    except Exception:
-        return default
-
-
 def make_world(name):
-    from synth import synth_world                                           # own library: the CPU arm never maps libbos_b200.so
     from prb_project_bearing_only_slam_b200.problem import Problem          # pure Python (id -> stix bookkeeping)
     NP, NL, E, solver = WORKLOADS[name]
+    if name in ("full", "mini", "batch-4096"):
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", ("mini" if name == "batch-4096" else name) + ".npz")))
+        w = dict(pose_ids=g["pose_ids"], poses_init=g["poses_xyt"], b_pose_id=g["b_pose_id"], b_lm_id=g["b_lm_id"], b_z=g["b_z"],
+                 o_src_id=g["o_src_id"], o_dst_id=g["o_dst_id"], o_z=g["o_z"], o_omega=g["o_omega"], lms_tri=g["lms_tri_f64"])
+        pr = Problem(w["pose_ids"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"], w["o_omega"],
+                     fixed_pose_id=int(g["fixed_pose_id"]))
+        return w, pr, solver
+    from synth import synth_world                                           # own library: the CPU arm never maps libbos_b200.so
     w = synth_world(NP, NL, E, seed=SEED)
     pr = Problem(w["pose_ids"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"], w["o_omega"],
                  fixed_pose_id=int(w["pose_ids"][0]))
     return w, pr, solver
 
 
-def oracle_sample(w, pr, pcg_iters_full, pcg_rtol, sample_iters=10):
-    """Times the CPU oracle (single thread, like the reference: CMakeLists.txt:5 has no OpenMP) on this workload.
-    The H, b build is timed in full; the Schur-PCG solve is timed for 2 and 2+sample_iters CG iterations and
-    extrapolated to the iteration count the same algorithm needs at the same tolerance (`pcg_iters_full`)."""
+def data_label(name):
+    return "synthetic" if name.startswith("synth") else ("bundled dataset of the reference (data/*.g2o as arrays in tests/golden/)" if name in ("full", "mini")
+                                                          else "synthetic (4096 perturbed copies of the bundled mini problem)")
+
+
+# ---- CPU arm: the reference's algorithm on the host cores ---------------------------------------------------------------
+def cpu_oracle(w, pr):
     from oracle.oracle import Oracle
     o = Oracle("f64")
     o.set_problem(w["pose_ids"], w["poses_init"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"],
                   w["o_omega"], fixed_id=pr.fixed_pose_id)
     o.triangulate()
     o.solver_init(pr.fixed_pose_id)
-    o.linearize()
+    return o
+
+
+def cpu_step_superlu(o, pr):
+    """One COMPLETE GN step on the CPU with the sparse direct solve done by SuperLU (scipy.sparse.linalg.splu, symmetric mode,
+    MMD ordering of A^T + A, no pivoting): linearize + assemble (oracle, O(E)), export H_nofixed, factorise, solve, boxplus."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    t = {}
+    t0 = time.perf_counter(); o.linearize(); t["linearize"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); colptr, rowidx, val, b = o.csc(); n = len(b)
+    A = sp.csc_matrix((val, rowidx, colptr), shape=(n, n)); t["export"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lu = spl.splu(A, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    t["factor"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); x = lu.solve(-b); t["trisolve"] = time.perf_counter() - t0
+    t["residual"] = float(np.abs(A @ x + b).max() / max(np.abs(b).max(), 1e-300))
+    t["nnzL"] = int(lu.L.nnz)
+    d = np.zeros(3 * pr.NP + 2 * pr.NL)
+    keep = np.ones(len(d), bool); keep[3 * pr.fixed_stix:3 * pr.fixed_stix + 3] = False
+    d[keep] = x
+    t0 = time.perf_counter(); o.set_delta(d); o.apply_boxplus(); t["update"] = time.perf_counter() - t0
+    t["step"] = t["linearize"] + t["export"] + t["factor"] + t["trisolve"] + t["update"]
+    return t
+
+
+def cpu_step_ldlt(o, deadline_s=0.0):
+    """One GN step with the oracle's own sparse LDL^T = the reference's Eigen::SimplicialLDLT restated (slam/solver.hpp:72,
+    solver.cpp:75-94): minimum-degree ordering + symbolic phase on the first call only (analyzePattern once), scalar up-looking
+    numeric factorisation + solve per step.  With a deadline the factorisation may stop early: `finished` False, `flops_done` says
+    how far it got (exact counts from the symbolic phase)."""
+    t = {}
+    t0 = time.perf_counter(); o.linearize(); t["linearize"] = time.perf_counter() - t0
+    info = o.solve_sparse(deadline_s)
+    t.update(export=info["t_export"], order=info["t_order"], analyze=info["t_analyze"], factor=info["t_factor"], trisolve=info["t_trisolve"],
+             nnzL=info["nnzL"], flops=info["flops"], flops_done=info["flops_done"], finished=info["finished"])
+    if info["finished"]:
+        t0 = time.perf_counter(); o.apply_boxplus(); t["update"] = time.perf_counter() - t0
+        t["step"] = t["linearize"] + t["export"] + t["factor"] + t["trisolve"] + t["update"]
+    return t
+
+
+def cpu_baseline_sample(w, pr, budget_s=20.0):
+    """`cpu_baseline` of our arm: a BOUNDED sample of one reference-algorithm GN step on the same workload, single thread (the
+    reference has no threads: CMakeLists.txt:5).  The H, b build and the symbolic phase run in full; the numeric LDL^T runs for at
+    most `budget_s` seconds and, if it did not finish, its time is scaled by flops_total / flops_done (exact counts from the
+    symbolic phase -- the complete, unscaled measurement is what `--impl reference` prints)."""
+    o = cpu_oracle(w, pr)
     t_lin = o.time_linearize(3)
-    t0 = time.perf_counter(); o.solve(1, 2, 0.0); t2 = time.perf_counter() - t0
-    t0 = time.perf_counter(); o.solve(1, 2 + sample_iters, 0.0); tk = time.perf_counter() - t0
-    t_iter = max((tk - t2) / sample_iters, 1e-9)
-    t0 = time.perf_counter(); o.apply_boxplus(); t_upd = time.perf_counter() - t0
-    t_step = t_lin + (t2 - 2 * t_iter) + pcg_iters_full * t_iter + t_upd
-    return dict(t_lin=t_lin, t_cg_iter=t_iter, t_step=t_step, t_fixed=t2 - 2 * t_iter, t_update=t_upd)
+    r = cpu_step_ldlt(o, deadline_s=budget_s)
+    scale = 1.0 if r["finished"] else r["flops"] / max(r["flops_done"], 1.0)
+    t_factor = r["factor"] * scale
+    t_tri = r["trisolve"] if r["finished"] else 2.5 * 8 * r["nnzL"] / 2.0e9     # two sweeps over L (12 B per entry) at ~2 GB/s/sweep-equivalent
+    t_step = t_lin + r["export"] + t_factor + t_tri
+    E = pr.Eb + pr.Eo
+    what = ("complete" if r["finished"] else "numeric factorisation stopped after %.0f s at %.1f %% of its %.3g flops and scaled" % (r["factor"], 100.0 / scale, r["flops"]))
+    return {"value": 1.0 / t_step, "unit": "iterations/s", "cores": 1, "kind": "port", "edges_linearized_per_s": E / t_lin,
+            "phases_s": {"linearize": t_lin, "export_csc": r["export"], "factor": t_factor, "trisolve": t_tri,
+                         "order_once": r["order"], "analyze_once": r["analyze"]},
+            "nnzL": r["nnzL"], "factor_flops": r["flops"],
+            "sample": "CPU oracle = the reference's algorithm restated (it needs Eigen3 / OpenCV, absent here), 1 thread, %s workload: H, b build timed in "
+                      "full (%.3f s), sparse LDL^T (SimplicialLDLT restated: minimum-degree ordering + symbolic phase once, up-looking numeric "
+                      "phase per step): %s" % (pr_name(pr), t_lin, what)}
+
+
+def pr_name(pr):
+    return "%d-pose / %d-landmark / %d-edge" % (pr.NP, pr.NL, pr.Eb + pr.Eo)
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm for the path (CPU oracle restatement: the reference itself
-    needs Eigen3 + OpenCV and cannot be built in this image), single host thread, same workload / metric / unit."""
+    """--impl reference: COMPLETE Gauss-Newton steps of the reference's algorithm on the host cores, nothing extrapolated.
+    linearize + assemble = the CPU oracle (O(E) restatement of slam/solver.cpp:31-69); linear solve = a sparse direct factorisation of
+    H_nofixed, as the reference does with Eigen::SimplicialLDLT (slam/solver.hpp:72): `ldlt` = the oracle's own restatement of that
+    solver (scalar up-looking LDL^T, the same algorithm class and speed), `superlu` = SuperLU through scipy (supernodal: a STRONGER
+    CPU solver than the reference's, used where the restatement would not finish inside the driver's time limit: 661 s per
+    factorisation at synth-2M, profiles/ref_ldlt_2M_r02.json).  Never maps libbos_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w, pr, solver = make_world(args.workload)
+    t_start = time.perf_counter()
+    if args.workload == "batch-4096":
+        return run_reference_batch(args)
+    w, pr, _ = make_world(args.workload)
     E = pr.Eb + pr.Eo
-    iters_full = args.ref_pcg_iters
-    times = []
+    o = cpu_oracle(w, pr)
+    solver = args.ref_solver
+    first = None
+    if solver in ("auto", "ldlt"):
+        # the symbolic phase (once per problem, like analyzePattern) tells the factorisation's flop count exactly
+        o.linearize()
+        first = cpu_step_ldlt(o, deadline_s=(1e-9 if solver == "auto" else 0.0))
+        if solver == "auto":
+            solver = "ldlt" if first["flops"] / 0.8e9 < 60.0 else "superlu"      # ~0.8 GFLOP/s: what the scalar up-looking kernel sustains
+            first = None
+            o = cpu_oracle(w, pr)
+            if solver == "ldlt":
+                o.linearize(); o.solve_sparse(1e-9)                               # symbolic phase again on the fresh oracle (untimed, once)
+    steps, warm = [], 0
     for i in range(args.warmup + args.steps):
-        s = oracle_sample(w, pr, iters_full, args.pcg_rtol, sample_iters=6)
-        if i >= args.warmup:
-            times.append(s)
-    t_step = statistics.mean(x["t_step"] for x in times)
-    t_lin = statistics.mean(x["t_lin"] for x in times)
+        r = cpu_step_superlu(o, pr) if solver == "superlu" else cpu_step_ldlt(o)
+        long_step = r["step"] > 20.0
+        if i < args.warmup and not long_step:
+            warm += 1
+            continue
+        steps.append(r)
+        if time.perf_counter() - t_start + r["step"] > CPU_STEP_BUDGET_S:
+            break
+    t_step = statistics.mean(x["step"] for x in steps)
+    t_lin = statistics.mean(x["linearize"] for x in steps)
+    literal = None
+    if args.workload in ("full", "mini"):
+        # the reference's LITERAL accumulation (slam/solver.cpp:44,60: an N x N sparse temporary merged into H per edge), FP32 like it
+        from oracle.oracle import Oracle
+        o32 = Oracle("f32")
+        o32.set_problem(w["pose_ids"], w["poses_init"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"],
+                        w["o_omega"], fixed_id=pr.fixed_pose_id)
+        o32.triangulate(); o32.solver_init(pr.fixed_pose_id)
+        t_lit = o32.time_linearize_literal(3 if args.workload == "full" else 200)
+        literal = {"linearize_literal_s": t_lit, "edges_linearized_per_s": E / t_lit, "gn_iterations_per_s": 1.0 / (t_lit + t_step - t_lin),
+                   "what": "H += J^T Omega J with the reference's per-edge O(N + nnz H) sparse merge, FP32, then the same sparse LDL^T"}
     value = 1.0 / t_step
-    sample = ("full %s world; H,b build timed in full (%.3f s); Schur-PCG timed for 2 and 8 CG iterations (%.4f s/iteration) and "
-              "extrapolated to %d iterations (what this 3x3 block-Jacobi PCG needs at rtol %.0e: measured on the GPU with --pcg-precond 1); single thread" %
-              (args.workload, t_lin, statistics.mean(x["t_cg_iter"] for x in times), iters_full, args.pcg_rtol))
+    restated = None
+    if literal:   # bundled datasets: the headline is the reference's LITERAL per-edge accumulation; the O(E) restatement is the secondary
+        restated = {"gn_iterations_per_s": value, "edges_linearized_per_s": E / t_lin, "what": "O(E) block-slot assembly (same arithmetic), FP64"}
+        t_step = literal["linearize_literal_s"] + t_step - t_lin
+        t_lin = literal["linearize_literal_s"]
+        value = 1.0 / t_step
+    phases = {k: statistics.mean(x[k] for x in steps) for k in ("linearize", "export", "factor", "trisolve", "update")}
+    if literal:
+        phases["linearize"] = t_lin
+    sample = ("%d complete GN step(s) of the %s workload on 1 thread, nothing extrapolated: linearize + assemble %.3f s (CPU oracle, O(E)), sparse direct solve "
+              "%.3f s (%s, nnz(L) = %d)%s" %
+              (len(steps), args.workload, t_lin, phases["factor"] + phases["trisolve"] + phases["export"],
+               "SuperLU via scipy.sparse.linalg.splu, symmetric mode, MMD ordering: supernodal, stronger than the reference's SimplicialLDLT"
+               if solver == "superlu" else "the oracle's restatement of Eigen::SimplicialLDLT, symbolic phase cached",
+               steps[-1]["nnzL"], "; %d warm-up step(s)" % warm if warm else "; no warm-up (a CPU step of this size is minutes long)"))
     line = {
         "impl": "reference", "metric": "gn_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "steps": len(steps), "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": data_label(args.workload),
         "config": {"workload": args.workload, "poses": pr.NP, "landmarks": pr.NL, "bearing_edges": pr.Eb, "odometry_edges": pr.Eo,
-                   "solver": "schur+block-jacobi-pcg", "pcg_rtol": args.pcg_rtol},
+                   "solver": "sparse direct (%s)" % solver},
         "edges_linearized_per_s": E / t_lin,
+        "phases_s": phases,
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port", "sample": sample,
                          "edges_linearized_per_s": E / t_lin},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t_start,
     }
+    if solver == "superlu":
+        line["solve_residual"] = steps[-1]["residual"]
+    if literal:
+        line["literal_reference_accumulation"] = literal
+        line["restated_assembly"] = restated
+        line["cpu_baseline"]["sample"] += "; linearize + assemble here = the reference's LITERAL per-edge sparse merge (slam/solver.cpp:44,60), FP32, %.3f s" % t_lin
+    print(json.dumps(line), file=args.out, flush=True)
+
+
+def batch_inputs(nprob, seed=0):
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "mini.npz")))
+    w, pr, _ = make_world("mini")
+    rng = np.random.default_rng(seed)
+    from prb_project_bearing_only_slam_b200.problem import xyt_to_xycs
+    P0 = xyt_to_xycs(g["poses_xyt"]); L0 = g["lms_tri_f64"]
+    poses = np.repeat(P0[None], nprob, 0); lms = np.repeat(L0[None], nprob, 0) + rng.normal(size=(nprob,) + L0.shape) * 0.02
+    bz = np.repeat(pr.b_z[None], nprob, 0) + rng.normal(size=(nprob, pr.Eb)) * 0.003
+    oz = np.repeat(pr.o_z[None], nprob, 0) + rng.normal(size=(nprob,) + pr.o_z.shape) * 0.01
+    return g, pr, poses, lms, bz, oz
+
+
+def run_reference_batch(args):
+    """config 5 on the CPU: the oracle steps the same 4096 mini-sized problems one after the other (sparse LDL^T each)."""
+    from oracle.oracle import Oracle
+    nprob = 4096
+    g, pr, poses, lms, bz, oz = batch_inputs(nprob)
+    sample_n = 512
+    t0 = time.perf_counter()
+    for k in range(sample_n):
+        ok = Oracle("f64")
+        ok.set_problem(g["pose_ids"], g["poses_xyt"], g["b_pose_id"], g["b_lm_id"], bz[k], g["o_src_id"], g["o_dst_id"], oz[k],
+                       pr.o_omega, fixed_id=pr.fixed_pose_id, lm_ids=pr.lm_ids, lms_xy=lms[k])
+        ok.solver_init(pr.fixed_pose_id)
+        ok.set_state(poses[k], lms[k])
+        ok.step(2)
+    dt = (time.perf_counter() - t0) / sample_n
+    value = 1.0 / dt
+    line = {"impl": "reference", "metric": "gn_iterations_per_s", "value": value, "unit": "problem-iterations/s", "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "ms_per_step": 1e3 * dt * nprob, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": data_label("batch-4096"), "config": {"workload": "batch-4096", "problems": nprob, "poses": pr.NP, "landmarks": pr.NL},
+            "cpu_baseline": {"value": value, "unit": "problem-iterations/s", "cores": 1, "kind": "port",
+                             "sample": "%d of the 4096 problems stepped one after the other by the CPU oracle (problem set-up included), 1 thread" % sample_n},
+            "e2e": {"value": value, "unit": "problem-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), file=args.out, flush=True)
 
 
@@ -212,8 +372,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.workload == "batch-4096":
+        return run_ours_batch(args, torch, dist, rank, world, local)
     w, pr, solver_name = make_world(args.workload)
-    solver = capi.SOLVER_PCG if solver_name == "pcg" else capi.SOLVER_DENSE_CHOLESKY
+    if args.solver != "workload":
+        solver_name = args.solver
+    solver = {"pcg": capi.SOLVER_PCG, "dense": capi.SOLVER_DENSE_CHOLESKY, "auto": capi.SOLVER_AUTO}[solver_name]
     prec = capi.PRECISION_F64 if args.precision == "f64" else capi.PRECISION_F32
     S = 8 if args.precision == "f64" else 4
     ctx = capi.Context(device=local, solver=solver, precision=prec, pcg_rtol=args.pcg_rtol, pcg_max_iters=args.pcg_max_iters,
@@ -221,6 +385,8 @@ def run_ours(args):
     pr.upload(ctx)
     if args.reduce_mode < 0:
         args.reduce_mode = 2 if solver == capi.SOLVER_PCG else 1
+    if solver == capi.SOLVER_AUTO:   # what AUTO resolves to is only known after the first solve; the roofline block follows solver_used
+        solver = None
     if world > 1:
         uid = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -301,6 +467,8 @@ def run_ours(args):
     clocks = clk.summary()
     traffic = load_traffic()
     pcg_iters = statistics.mean(s["pcg_iterations"] for s in stats)
+    if solver is None:
+        solver = int(stats[-1]["solver_used"])
     if solver == capi.SOLVER_PCG and pcg_iters > 0:
         # the dominant kernel of a step is the persistent PCG kernel (> 99 % of the step at synth-2M): one launch = one solve
         b_it = pcg_iteration_bytes(pr.NP, pr.NL, pr.Eb, S)
@@ -323,7 +491,8 @@ def run_ours(args):
     line = {
         "metric": "gn_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "vs_baseline": None, "dtype": args.precision, "data": data_label(args.workload),
+        "ms_per_step_device_events": statistics.mean(s["ms_linearize"] + s["ms_allreduce"] + s["ms_solve"] + s["ms_update"] for s in stats),
         "config": {"workload": args.workload, "poses": pr.NP, "landmarks": pr.NL, "bearing_edges": pr.Eb, "odometry_edges": pr.Eo,
                    "N": int(pi.N), "solver": {0: "schur+pcg(block-tridiagonal chain + coarse-space preconditioner)", 1: "schur+block-jacobi-pcg",
                               2: "schur+pcg(block-tridiagonal chain preconditioner)"}[args.pcg_precond]
@@ -337,6 +506,8 @@ def run_ours(args):
         "pcg_iterations_per_step": [int(x["pcg_iterations"]) for x in stats],
         "solver_status_per_step": [int(x.get("solver_status", 0)) for x in stats],
         "chi2_last": stats[-1]["chi2_bearing"] + stats[-1]["chi2_odometry"],
+        "state_digest_last": stats[-1]["state_digest"],
+        "precond_used": sorted(set(int(x["precond_used"]) for x in stats)), "pcg_resolves": int(sum(x["pcg_resolves"] for x in stats)),
         "roofline": roofline,
         "roofline_linearize": {"kernel": "H,b build: k_landmark_init + k_linearize_bearing_persistent + k_pose_finish", "bound": "hbm", "achieved": achieved, "peak": peak,
                                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
@@ -347,18 +518,65 @@ def run_ours(args):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        # the CPU port runs the reference-arm algorithm (3x3 block-Jacobi PCG): its own iteration count at this tolerance
-        cpu_iters = int(round(line["pcg_iterations"]))
-        if solver == capi.SOLVER_PCG and args.pcg_precond != 1:
-            cpu_iters = recorded_block_jacobi_iterations(args.workload, cpu_iters)
-        cb = oracle_sample(w, pr, cpu_iters, args.pcg_rtol)
-        line["cpu_baseline"] = {
-            "value": 1.0 / cb["t_step"], "unit": "iterations/s", "cores": 1, "kind": "port",
-            "edges_linearized_per_s": E / cb["t_lin"],
-            "sample": "CPU oracle (restatement; the reference needs Eigen3/OpenCV, absent here), 1 thread, full %s world: H,b build timed "
-                      "in full (%.3f s), Schur-PCG timed for 2 and 12 CG iterations (%.4f s/iteration) and extrapolated to the %d "
-                      "iterations its 3x3 block-Jacobi preconditioner needs at this tolerance (profiles/pcg_iterations.json)" %
-                      (args.workload, cb["t_lin"], cb["t_cg_iter"], cpu_iters)}
+        line["cpu_baseline"] = cpu_baseline_sample(w, pr, budget_s=args.cpu_budget)
+    print(json.dumps(line), file=args.out, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ours_batch(args, torch, dist, rank, world, local):
+    """BASELINE config 5: 4096 independent mini-sized problems, ONE launch = one GN iteration of every problem (k_batch_step).
+    Replicas only across GPUs (every rank steps its own 4096 problems, no collective): value = problem-iterations/s of all ranks."""
+    from prb_project_bearing_only_slam_b200 import capi
+    nprob = 4096
+    g, pr, poses, lms, bz, oz = batch_inputs(nprob, seed=rank)
+    prec = capi.PRECISION_F64 if args.precision == "f64" else capi.PRECISION_F32
+    S = 8 if args.precision == "f64" else 4
+    B = capi.Batch(nprob, pr.NP, pr.NL, pr.fixed_stix, pr.b_pose, pr.b_lm, bz, None, pr.o_src, pr.o_dst, oz, pr.o_omega, precision=prec, device=local)
+    B.set_states(poses, lms)
+    B.step_device(max(args.warmup, 3))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    with ClockSampler(local) as clk:
+        ms = B.step_device(args.steps)          # CUDA events around the K launches on the batch's stream
+        barrier()
+    # end to end: states from pinned host memory, one launch, chi2 / status back, every step
+    ph = torch.from_numpy(poses.copy()).pin_memory().numpy(); lh = torch.from_numpy(lms.copy()).pin_memory().numpy()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        B.set_states(ph, lh)
+        chi, dinf, st = B.step()
+    barrier()
+    e2e = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    # algorithmic bytes of one launch: per problem the state in and out, the measurements, chi2 / status out (topology is shared)
+    b_launch = nprob * ((4 * pr.NP + 2 * pr.NL) * S * 2 + (pr.Eb + 3 * pr.Eo) * S + 32)
+    ach = b_launch / (ms / args.steps * 1e-3) / 1e9
+    value = world * nprob * args.steps / (ms * 1e-3)
+    line = {"metric": "gn_iterations_per_s", "value": value, "unit": "problem-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+            "data": data_label("batch-4096"),
+            "config": {"workload": "batch-4096", "problems": nprob, "poses": pr.NP, "landmarks": pr.NL, "bearing_edges": pr.Eb, "odometry_edges": pr.Eo,
+                       "parallelism": "replicas only x%d" % world, "l2": "working set %.1f MB stays in L2: launch-latency bound by design" % (b_launch / 1e6)},
+            "edges_linearized_per_s": value * (pr.Eb + pr.Eo),
+            "roofline": {"kernel": "k_batch_step (one warp per problem, whole GN iteration in shared memory)", "bound": "hbm", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": b_launch,
+                         "ms_per_launch": ms / args.steps},
+            "e2e": {"value": world * nprob * args.steps / e2e, "unit": "problem-iterations/s",
+                    "h2d_bytes_per_step": int(nprob * (4 * pr.NP + 2 * pr.NL) * 8), "d2h_bytes_per_step": int(nprob * (2 * 8 + 8 + 4))},
+            "gpu_launches": args.steps, "clocks": clk.summary(), "status_ok": bool(np.all(st == 0))}
     print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -386,17 +604,17 @@ def main():
     ap.add_argument("--pcg-precond", type=int, default=0, choices=[0, 1, 2],
                     help="0 chain (block-tridiagonal) + coarse-space preconditioner, 1 3x3 block-Jacobi, 2 chain only")
     ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 2 for the PCG workloads, 1 for the dense ones")
-    ap.add_argument("--ref-pcg-iters", type=int, default=0, help="CG iterations per GN step the reference arm extrapolates to "
-                    "(0 = the count recorded by our arm in profiles/pcg_iterations.json, else 300)")
+    ap.add_argument("--ref-solver", default="auto", choices=["auto", "ldlt", "superlu"],
+                    help="reference arm: ldlt = the oracle's restatement of Eigen::SimplicialLDLT, superlu = scipy's SuperLU; auto = ldlt when "
+                         "its symbolic phase predicts under a minute per factorisation, else superlu")
+    ap.add_argument("--solver", default="workload", choices=["workload", "auto", "dense", "pcg"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds the cpu_baseline sample may spend in the numeric factorisation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3)
     args.out = _quiet_stdout()
     if args.impl == "reference":
-        if args.ref_pcg_iters <= 0:
-            p = os.path.join(ROOT, "profiles", "pcg_iterations.json")
-            args.ref_pcg_iters = int(json.load(open(p)).get(args.workload, 300)) if os.path.exists(p) else 300
         run_reference(args)
     else:
         run_ours(args)

@@ -49,7 +49,7 @@ struct IOracle {
     virtual void bearing_jacobians(int e, double* ana5, double* num5) = 0;
     virtual void odometry_jacobians(int e, double* ana18, double* num18) = 0;
     virtual double time_linearize(int reps) = 0;
-    virtual int solve_sparse(double deadline_s, double* info8) = 0;
+    virtual int solve_sparse(double deadline_s, double* info10) = 0;
     virtual double time_linearize_literal(int reps) = 0;
     virtual double literal_max_diff() = 0;
     virtual void set_wrap_branch(int n, const int* edges, const int* signs) = 0;
@@ -172,11 +172,11 @@ struct Impl : IOracle {
     void solve(int kind, int max_iters, double rtol) override {
         if (kind == 0) o.solve_dense_ldlt(); else if (kind == 2) o.solve_sparse_ldlt(); else o.solve_schur_pcg(max_iters, rtol);
     }
-    int solve_sparse(double deadline_s, double* info8) override {
+    int solve_sparse(double deadline_s, double* info8) override {   // info8: 10 doubles
         const bool ok = o.solve_sparse_ldlt(deadline_s);
         if (info8) {
             info8[0] = o.t_order; info8[1] = o.t_analyze; info8[2] = o.t_factor; info8[3] = o.t_trisolve; info8[4] = (double)o.ldlt.nnzL;
-            info8[5] = o.ldlt.flops; info8[6] = o.t_export; info8[7] = o.ldlt.status;
+            info8[5] = o.ldlt.flops; info8[6] = o.t_export; info8[7] = o.ldlt.status; info8[8] = o.ldlt.flops_done; info8[9] = o.ldlt.rows_done;
         }
         return ok ? 0 : 1;
     }

@@ -137,7 +137,9 @@ struct SparseLdlt {
     bool analyzed = false;
     int status = 0;                     // 1: a non-positive pivot was met (the reference only prints a message, solver.cpp:82-84)
     long long nnzL = 0;
-    double flops = 0;
+    double flops = 0;                   // of one numeric factorisation: sum over columns of c (c + 2), c = entries of the column of L
+    double flops_done = 0;              // same count for the rows the last factorize() call completed (== flops when it finished)
+    int rows_done = 0;
 
     // analyzePattern (solver.cpp:77-80): elimination tree + column counts for the permuted matrix
     void analyze(int n_, const std::vector<int>& colptr, const std::vector<int>& rowidx, const std::vector<int>& perm_) {
@@ -163,7 +165,7 @@ struct SparseLdlt {
         }
         Lp.assign(n + 1, 0);
         flops = 0;
-        for (int k = 0; k < n; k++) { Lp[k + 1] = Lp[k] + Lnz[k]; flops += (double)Lnz[k] * ((double)Lnz[k] + 3.0); }
+        for (int k = 0; k < n; k++) { Lp[k + 1] = Lp[k] + Lnz[k]; flops += (double)Lnz[k] * ((double)Lnz[k] + 2.0); }
         nnzL = Lp[n];
         Li.assign((size_t)nnzL, 0);
         Lx.assign((size_t)nnzL, T(0));
@@ -177,11 +179,15 @@ struct SparseLdlt {
         std::vector<int> pattern(n), flag(n);
         std::fill(Lnz.begin(), Lnz.end(), 0);
         status = 0;
+        flops_done = 0; rows_done = 0;
+        double fl = 0;
         const auto t0 = std::chrono::steady_clock::now();
         for (int k = 0; k < n; k++) {
             if (deadline_s > 0.0 && (k & 1023) == 0 &&
-                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > deadline_s)
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > deadline_s) {
+                flops_done = fl; rows_done = k;
                 return false;
+            }
             int top = n;
             flag[k] = k;
             const int c = perm[k];
@@ -200,6 +206,7 @@ struct SparseLdlt {
                 const T yi = Y[i];
                 Y[i] = T(0);
                 const int p2 = Lp[i] + Lnz[i];
+                fl += 2.0 * Lnz[i] + 3.0;
                 for (int q = Lp[i]; q < p2; q++) Y[Li[q]] -= Lx[q] * yi;
                 const T lki = yi / D[i];
                 dk -= lki * yi;
@@ -210,6 +217,7 @@ struct SparseLdlt {
             D[k] = dk;
             if (!(dk > T(0))) status = 1;
         }
+        flops_done = fl; rows_done = n;
         return true;
     }
 

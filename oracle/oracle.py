@@ -190,10 +190,11 @@ class Oracle:
     def solve_sparse(self, deadline_s=0.0):
         """The reference's own solver restated (SimplicialLDLT: minimum-degree ordering + symbolic phase once, up-looking LDL^T per
         call).  Returns a dict of timings / fill; 'finished' is False when deadline_s (seconds, 0 = none) cut the factorisation."""
-        info = np.zeros(8)
+        info = np.zeros(10)
         rc = self.L.orc_solve_sparse(self.h, float(deadline_s), _p(info))
-        return dict(finished=(rc == 0), t_order=info[0], t_analyze=info[1], t_factor=info[2], t_trisolve=info[3], nnzL=int(info[4]),
-                    flops=info[5], t_export=info[6], status=int(info[7]))
+        return dict(finished=(rc == 0), t_order=float(info[0]), t_analyze=float(info[1]), t_factor=float(info[2]), t_trisolve=float(info[3]),
+                    nnzL=int(info[4]), flops=float(info[5]), t_export=float(info[6]), status=int(info[7]), flops_done=float(info[8]),
+                    rows_done=int(info[9]))
 
     def time_linearize_literal(self, reps=1):
         """Seconds per H, b build with the reference's literal per-edge sparse merge (slam/solver.cpp:44,60): O(N + nnz H) per edge."""
