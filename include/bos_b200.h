@@ -67,7 +67,13 @@ typedef struct bos_options {
                                  Galerkin coarse space of piecewise-linear hats over the chunks (~70x fewer CG iterations than 3x3
                                  blocks on odometry chains); 2 = the chain blocks alone; 1 = the 3x3 block-Jacobi preconditioner
                                  (also what FP32 and pcg_variant 1 run).  All converge to the same solution at pcg_rtol. */
-    int reserved[6];
+    int pcg_coarse_nodes;     /* coarse-space nodes per chunk of the default preconditioner: 0 = default (4), 1 = the round-1 layout (one
+                                 hat per chunk); rounded so that segments are whole groups of 32 poses, at most 8 */
+    int pcg_coarse_refresh;   /* the coarse operator's inverse is kept across GN steps and rebuilt every this many solves (also whenever
+                                 the state is replaced through the API or the CG iteration count drifts up by 25 %); 0 = default (4),
+                                 1 = rebuild for every solve.  Any SPD coarse operator is a valid preconditioner: only the iteration
+                                 count depends on it, never the solution */
+    int reserved[4];
 } bos_options;
 
 /* Per-iteration outputs.  The reference prints none of these; chi2 is defined as the sum of the

@@ -20,7 +20,8 @@ NCCL_UID_BYTES = 128
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("precision", C.c_int), ("solver", C.c_int), ("dense_max_dim", C.c_int),
                 ("kernel_threshold", C.c_double), ("damping", C.c_double), ("pcg_max_iters", C.c_int),
-                ("pcg_rtol", C.c_double), ("pcg_variant", C.c_int), ("pcg_precond", C.c_int), ("reserved", C.c_int * 6)]
+                ("pcg_rtol", C.c_double), ("pcg_variant", C.c_int), ("pcg_precond", C.c_int), ("pcg_coarse_nodes", C.c_int),
+                ("pcg_coarse_refresh", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class Stats(C.Structure):

@@ -184,10 +184,19 @@ struct PcgWork {
     int ch_Kp = 0, ch_cps = 0, ch_fac_floats = 0;
     // coarse space of the chain preconditioner: piecewise-linear hats over the chunks (node c = start of chunk c, 3 dof per
     // node), Galerkin operator A_c = P^T S P assembled and inverted once per solve; z = M_chunk^-1 r + P A_c^-1 P^T r
-    int c_nc = 0;            // 3 * (pc_chunks + 1)
+    int c_nc = 0;            // 3 * (pc_chunks * c_nseg + 1)
+    int c_h = 32, c_nseg = 1;   // node geometry: every chunk is cut into c_nseg segments of c_h rows (a multiple of 32), nodes at their ends
+    int c_bw = 0;            // half bandwidth of A_c in scalars (from the pattern); 0 = treat A_c as dense (wide loop closures)
+    double* cLc = nullptr;   // [c_nc][c_bw + 1] band of the Cholesky factor by columns, cLr the same by rows, cLdi = 1 / diagonal
+    double* cLr = nullptr;
+    double* cLdi = nullptr;
+    // A_c^-1 is kept across GN steps (any SPD coarse operator is a valid preconditioner): refreshed every coarse_refresh solves, when the
+    // state was replaced from outside (coarse_valid = false) and when the CG iteration count drifts (coarse_stale)
+    bool coarse_valid = false, coarse_stale = false;
+    int coarse_age = 0, coarse_refresh = 1, coarse_its_ref = 0;
     double* cA = nullptr;    // [c_nc][c_nc] column-major lower: A_c, then its Cholesky factor
     double* cAinv = nullptr; // [c_nc][c_nc] A_c^-1 (full, symmetric)
-    double* cRc = nullptr;   // [pc_chunks][6] per chunk: P^T r restricted to its rows (left node, right node)
+    double* cRc = nullptr;   // [pc_chunks * c_nseg][6] per segment: P^T r restricted to its rows (left node, right node)
     double* cStats = nullptr;  // [8] scratch status of the coarse factorisation
     int sm_count = 148;
     int precond_used = 1;    // what the last solve actually ran (reported through bos_stats)

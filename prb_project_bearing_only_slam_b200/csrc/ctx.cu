@@ -88,6 +88,7 @@ struct bos_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     bool have_problem = false, linearized = false, solved = false;
+    bool stepping_host = false;          // bos_step_host: the uploaded state is the one the previous step produced
     bool delta_valid = false;            // set by bos_solve / bos_upload_delta, consumed by bos_update
     HostPattern P;
     DevAlloc mem;
@@ -337,12 +338,52 @@ int ensure_pcg(bos_ctx* c) {
         w.chO = c->mem.get<S>(6 * std::max<size_t>(rows, 1));
         w.chF = c->mem.get<float>((size_t)std::max(d.pc_chunks, 1) * w.ch_fac_floats);
         if (!w.chD || !w.chO || !w.chF) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
-        w.c_nc = 3 * (d.pc_chunks + 1);
+        // coarse nodes: c_nseg segments of c_h = 32 m rows per chunk (pcg_coarse_nodes asked for; whole 32-row groups; at most 8)
+        {
+            const HostPattern& P = c->P;
+            const int groups = std::max(d.pc_cp / 32, 1);
+            int want = c->opt.pcg_coarse_nodes > 0 ? c->opt.pcg_coarse_nodes : 4;
+            want = std::min(std::min(want, 8), groups);
+            auto geometry = [&](int k) { const int m = (groups + k - 1) / k; w.c_h = 32 * m; w.c_nseg = (groups + m - 1) / m; };
+            // half bandwidth of A_c in nodes: the span of the landmarks the assembly keeps (at most 16 nodes, k_coarse_lm) and of the pose-pose blocks
+            auto band_nodes = [&]() {
+                const int cp = d.pc_cp, h = w.c_h, ns = w.c_nseg;
+                auto seg_of = [&](int pose) { const int cc = pose / cp; return cc * ns + (pose - cc * cp) / h; };
+                int bwn = 1;
+                for (int l = 0; l < P.NL; l++) {
+                    int nn = 0, last = -2, first = -1;
+                    bool over = false;
+                    for (int q = P.lm_ptr[l]; q < P.lm_ptr[l + 1]; q++) {
+                        const int gs = seg_of(P.lm_order_pose[q]);
+                        if (gs == last) continue;
+                        if (nn + 2 > 16) { over = true; break; }
+                        nn += (last + 1 == gs) ? 1 : 2;
+                        if (first < 0) first = gs;
+                        last = gs;
+                    }
+                    if (!over && first >= 0) bwn = std::max(bwn, last + 1 - first);
+                }
+                for (size_t k = 0; k < P.off_lo.size(); k++) bwn = std::max(bwn, std::abs(seg_of(P.off_hi[k]) - seg_of(P.off_lo[k])) + 1);
+                return bwn;
+            };
+            geometry(want);
+            int bw = 3 * band_nodes() + 2;
+            if (bw > 158 && w.c_nseg > 1) { geometry(1); bw = 3 * band_nodes() + 2; }   // wide coupling: fall back to one hat per chunk
+            w.c_nc = 3 * (d.pc_chunks * w.c_nseg + 1);
+            w.c_bw = (bw <= 158) ? std::min(bw, w.c_nc - 1) : 0;
+            if (w.c_bw < 1 && w.c_nc > 1) w.c_bw = (bw <= 158) ? 1 : 0;
+            w.coarse_refresh = c->opt.pcg_coarse_refresh > 0 ? c->opt.pcg_coarse_refresh : 4;
+            w.coarse_valid = false; w.coarse_stale = false; w.coarse_age = 0;
+        }
         w.cA = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
         w.cAinv = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
-        w.cRc = c->mem.get<double>(6 * (size_t)std::max(d.pc_chunks, 1));
+        w.cRc = c->mem.get<double>(6 * (size_t)std::max(d.pc_chunks * w.c_nseg, 1));
         w.cStats = c->mem.get<double>(8);
-        if (!w.cA || !w.cAinv || !w.cRc || !w.cStats) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+        w.cLc = c->mem.get<double>((size_t)w.c_nc * (w.c_bw + 1));
+        w.cLr = c->mem.get<double>((size_t)w.c_nc * (w.c_bw + 1));
+        w.cLdi = c->mem.get<double>((size_t)w.c_nc);
+        if (!w.cA || !w.cAinv || !w.cRc || !w.cStats || !w.cLc || !w.cLr || !w.cLdi) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+        CUDA_OK(c, cudaMemsetAsync(w.cLr, 0, sizeof(double) * (size_t)w.c_nc * (w.c_bw + 1), c->stream));
     }
     w.xS = c->mem.get<S>(3 * (size_t)d.pc_chunks * d.pc_cp);
     if (!w.hllinv_c || !w.ul4 || !w.z4 || !w.rS || !w.xS || !w.rowS) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
@@ -540,6 +581,7 @@ int set_state_impl(bos_ctx* c, const double* poses, const double* lms) {
         }
     }
     c->linearized = false; c->solved = false;
+    if (!c->stepping_host) { c->pwd.coarse_valid = false; c->pwf.coarse_valid = false; }   // a state from outside: the cached coarse operator describes another one
     return BOS_OK;
 }
 
@@ -794,7 +836,9 @@ int bos_step_host(bos_ctx* c, double* poses, double* lms, bos_stats* stats) {
     NEED(c, c->have_problem, "step before upload_problem");
     if (!poses) return fail(c, BOS_ERR_INVALID, "null state");
     CUDA_OK(c, cudaSetDevice(c->opt.device));
+    c->stepping_host = true;
     int rc = DISPATCH(c, set_state_impl, c, poses, lms);
+    c->stepping_host = false;
     if (rc) return rc;
     if ((rc = DISPATCH(c, step_impl, c))) return rc;
     if ((rc = bos_get_state(c, poses, lms))) return rc;

@@ -822,19 +822,28 @@ __device__ __noinline__ void chain_apply(unsigned fac_off, unsigned r1_off, unsi
 //   P^T Hpp P                      k_coarse_pose  (per chunk in registers, one set of atomics per chunk)
 //   - sum_l G_l^T Hll_l^-1 G_l     k_coarse_lm    (one thread per landmark walks its edges)
 // then factorised (dense_cholesky_lower) and inverted explicitly (k_coarse_inverse): applying it is a 6-row mat-vec per CTA.
-__device__ __forceinline__ float coarse_t(int r, int cp) { return ((float)r + 0.5f) / (float)cp; }
+// Node geometry: every chunk is cut into c_nseg segments of c_h = 32 m rows (the last one may be shorter); node n sits at the start of
+// GLOBAL segment n = c * c_nseg + j, one more node closes the last segment.  Row r of a chunk carries the weights 1 - t and t for the nodes
+// at the two ends of its segment, t = (r - j h + 1/2) / len_j.  (One segment per chunk = the round-1 layout; four per chunk cut the CG
+// iterations at synth-2M from 73 to 46: the nodes then also resolve the variation ALONG a serpentine row, tests/precond_model.py.)
+__host__ __device__ __forceinline__ void coarse_seg(int r, int cp, int h, int& j, float& t) {
+    j = r / h;
+    const int len = (cp - j * h < h) ? cp - j * h : h;
+    t = ((float)(r - j * h) + 0.5f) / (float)len;
+}
 
 // one thread per compact landmark row.  Its edges come in ascending pose order (sliced-ELL row), so the chunk index never
 // decreases: the edges of one chunk are summed into G (2 x 3 per node: rows = the two components of Jl, weighted by the hat
 // weights of the pose), neighbouring chunks share a node; then the lower triangle of -G^T Hll^-1 G goes into A_c.  A landmark
 // seen from more than kCoarseMaxChunks chunks is left out altogether (A_c only grows: still SPD).
-constexpr int kCoarseMaxChunks = 8;
+constexpr int kCoarseMaxChunks = 8;     // ... segments, since the nodes sit at segment ends
+constexpr int kCoarseMaxSeg = 8;        // segments per chunk, at most
 template <typename S>
 __global__ void __launch_bounds__(128) k_coarse_lm(Dev<S> d, PcgWork<S> w) {
     constexpr int RPG = 32 / kEllLanesL;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= d.n_clm) return;
-    const int g = row / RPG, lane0 = (row % RPG) * kEllLanesL, cp = d.pc_cp;
+    const int g = row / RPG, lane0 = (row % RPG) * kEllLanesL, cp = d.pc_cp, hseg = w.c_h, nseg = w.c_nseg;
     const int off = __ldg(d.ell_Loff + g), W = __ldg(d.ell_Loff + g + 1) - off;
     const S lx = w.ul4[4LL * row + 2], ly = w.ul4[4LL * row + 3];
     const S so_u = (S)w.sqrt_omega;
@@ -860,9 +869,12 @@ __global__ void __launch_bounds__(128) k_coarse_lm(Dev<S> d, PcgWork<S> w) {
             const int ps = __ldg(d.ell_Lpose + slot);
             if (ps < 0) continue;                                   // padding, or an edge of the fixed pose
             const int c = ps / cp;
-            if (c != cur) {
+            int jseg; float tf;
+            coarse_seg(ps - c * cp, cp, hseg, jseg, tf);
+            const int gs = c * nseg + jseg;
+            if (gs != cur) {
                 flush();
-                cur = c;
+                cur = gs;
                 for (int e = 0; e < 12; e++) acc[e] = 0.0;
             }
             S px, py;
@@ -872,7 +884,7 @@ __global__ void __launch_bounds__(128) k_coarse_lm(Dev<S> d, PcgWork<S> w) {
             const S so = w.omega_uniform ? so_u : __ldg(w.Lw + slot);
             j0 *= so; j1 *= so;
             const double jp[3] = {(double)-j0, (double)-j1, (double)(j0 * ly - j1 * lx)};
-            const double t = (double)coarse_t(ps - c * cp, cp), wl = 1.0 - t;
+            const double t = (double)tf, wl = 1.0 - t;
             for (int dd = 0; dd < 3; dd++) {
                 const double a0 = (double)j0 * jp[dd], a1 = (double)j1 * jp[dd];
                 acc[dd] += wl * a0; acc[3 + dd] += wl * a1; acc[6 + dd] += t * a0; acc[9 + dd] += t * a1;
@@ -902,14 +914,17 @@ __global__ void __launch_bounds__(128) k_coarse_lm(Dev<S> d, PcgWork<S> w) {
 template <typename S>
 __global__ void __launch_bounds__(256) k_coarse_pose(Dev<S> d, PcgWork<S> w) {
     __shared__ double red[8][21];
-    const int c = blockIdx.x, cp = d.pc_cp, nc = w.c_nc;
+    const int cp = d.pc_cp, nc = w.c_nc, hseg = w.c_h, nseg = w.c_nseg;
+    const int c = blockIdx.x / nseg, jseg = blockIdx.x % nseg, gs = blockIdx.x;     // one CTA per (chunk, segment)
+    const int r_lo = jseg * hseg, r_hi = (r_lo + hseg < cp) ? r_lo + hseg : cp;
     double acc[21];
 #pragma unroll
     for (int q = 0; q < 21; q++) acc[q] = 0.0;
-    for (int r = threadIdx.x; r < cp; r += blockDim.x) {
+    for (int r = r_lo + (int)threadIdx.x; r < r_hi; r += blockDim.x) {
         const int i = __ldg(d.pc_row_pose + (size_t)c * cp + r);
         if (i < 0 || i == d.fixed) continue;
-        const float t = coarse_t(r, cp);
+        int jj; float t;
+        coarse_seg(r, cp, hseg, jj, t);
         const double wi[2] = {1.0 - (double)t, (double)t};
         double H[9];
         {
@@ -938,9 +953,11 @@ __global__ void __launch_bounds__(256) k_coarse_pose(Dev<S> d, PcgWork<S> w) {
 #pragma unroll
                 for (int e = 0; e < 3; e++) H[3 * dd + e] = (sl >= 0) ? (double)Bo[3 * dd + e] : (double)Bo[3 * e + dd];
             const int cj = j / cp;
-            const float tj = coarse_t(j - cj * cp, cp);
+            int js; float tj;
+            coarse_seg(j - cj * cp, cp, hseg, js, tj);
+            const int gsj = cj * nseg + js;
             const double wj[2] = {1.0 - (double)tj, (double)tj};
-            if (cj == c) {
+            if (gsj == gs) {
 #pragma unroll
                 for (int sa = 0; sa < 2; sa++)
 #pragma unroll
@@ -957,7 +974,7 @@ __global__ void __launch_bounds__(256) k_coarse_pose(Dev<S> d, PcgWork<S> w) {
                     for (int sb = 0; sb < 2; sb++)
                         for (int dd = 0; dd < 3; dd++)
                             for (int e = 0; e < 3; e++) {
-                                const int row = 3 * (c + sa) + dd, col = 3 * (cj + sb) + e;
+                                const int row = 3 * (gs + sa) + dd, col = 3 * (gsj + sb) + e;
                                 if (row >= col) atomicAdd(w.cA + (size_t)row + (size_t)col * nc, wi[sa] * wj[sb] * H[3 * dd + e]);
                             }
             }
@@ -976,7 +993,7 @@ __global__ void __launch_bounds__(256) k_coarse_pose(Dev<S> d, PcgWork<S> w) {
         int row = 0;
         while ((row + 1) * (row + 2) / 2 <= (int)threadIdx.x) row++;
         const int col = threadIdx.x - row * (row + 1) / 2;
-        if (v != 0.0) atomicAdd(w.cA + (size_t)(3 * c + row) + (size_t)(3 * c + col) * nc, v);
+        if (v != 0.0) atomicAdd(w.cA + (size_t)(3 * gs + row) + (size_t)(3 * gs + col) * nc, v);
     }
 }
 
@@ -984,6 +1001,118 @@ __global__ void __launch_bounds__(256) k_coarse_pose(Dev<S> d, PcgWork<S> w) {
 __global__ void k_coarse_fix(double* A, int nc) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < nc && !(A[(size_t)j * nc + j] > 0.0)) A[(size_t)j * nc + j] = 1.0;
+}
+
+// ---- banded factorisation / inverse of the coarse operator ---------------------------------------------------------------------
+// A_c couples node n only with nodes a few segments away (the observers of a landmark are close to each other along the pose order, pose-pose
+// blocks join consecutive poses): it is a band matrix of half bandwidth bw, and its Cholesky factor keeps the band.  ONE CTA factorises it with
+// the active (bw + 1) x (bw + 1) window in shared memory (a ring over the columns); finished columns go to two compact copies of the band with row
+// stride W = bw + 1:  Lc[k][e] = L[k + e][k] (column k, contiguous) and Lr[i][e] = L[i][i - e] (row i, contiguous), e = 0..bw, plus Ldi[k] = 1 / L[k][k].
+// (Round 1 ran 21 dense-Cholesky launches + a dense triangular inverse here: 1.2 ms per solve for a 447 x 447 matrix.)
+constexpr int kBandCholThreads = 256;      // a 16 x 16 grid of threads over the (a, b) pairs of the trailing window
+__global__ void __launch_bounds__(kBandCholThreads) k_coarse_band_chol(const double* __restrict__ A, int nc, int bw, double* __restrict__ Lc,
+                                                                       double* __restrict__ Lr, double* __restrict__ Ldi, double* __restrict__ stats) {
+    extern __shared__ double win[];           // [R][W]: slot (k % R), entry e = row k + e.  R = bw + 2: one slot more than the window, so that the
+                                              // column entering the ring is not yet part of the NEXT step's trailing window (one barrier per step)
+    const int W = bw + 1, R = bw + 2, tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;
+    for (int q = tid; q < R * W; q += kBandCholThreads) {
+        const int k = q / W, e = q - k * W;
+        win[q] = (k < nc && k + e < nc) ? A[(size_t)(k + e) + (size_t)k * nc] : 0.0;
+    }
+    // column j + R enters the ring when column j leaves it; its entries travel through registers, loaded one column step early so that the
+    // global-memory latency is hidden behind a whole step (thread e holds entry e; W <= 160 < 256 threads)
+    double pre = 0.0;
+    auto prefetch = [&](int kn) { pre = (tid < W && kn < nc && kn + tid < nc) ? __ldg(A + (size_t)(kn + tid) + (size_t)kn * nc) : 0.0; };
+    prefetch(R);
+    __syncthreads();
+    bool bad = false;
+    int sj = 0;                                // j % R
+    for (int j = 0; j < nc; j++, sj = (sj + 1 == R) ? 0 : sj + 1) {
+        double* cj = win + (size_t)sj * W;
+        // every thread derives the pivot itself: no barrier between the pivot and the update, which works on the UNSCALED column
+        double p = cj[0];
+        if (!(p > 0.0)) { bad = true; p = 1.0; }
+        const double ip = 1.0 / p, rs = sqrt(ip);
+        const double held = pre;               // column j + R, loaded during step j - 1
+        prefetch(j + 1 + R);
+        // trailing window: column j + a (a = 1..bw), row j + b (b = a..bw):  A[j+b][j+a] -= A[j+b][j] A[j+a][j] / A[j][j]
+        for (int a = 1 + ta; a <= bw; a += 16) {
+            const double la = cj[a] * ip;
+            const int sa = (sj + a >= R) ? sj + a - R : sj + a;
+            double* ca = win + (size_t)sa * W - a;
+            for (int b = 1 + tb + ((a - 1 - tb + 15) >> 4 << 4); b <= bw; b += 16)      // first b >= a with b = 1 + tb (mod 16)
+                if (j + b < nc) ca[b] -= cj[b] * la;
+        }
+        // the finished column: L[j + e][j] = A[j + e][j] / sqrt(A[j][j])
+        if (tid < W) {
+            const int e = tid;
+            const double v = (j + e < nc) ? ((e == 0) ? p * rs : cj[e] * rs) : 0.0;
+            Lc[(size_t)j * W + e] = v;
+            if (j + e < nc) Lr[(size_t)(j + e) * W + e] = v;
+            if (e == 0) Ldi[j] = rs;
+        }
+        __syncthreads();
+        if (tid < W) cj[tid] = held;           // the slot of column j now holds column j + R: first touched two steps later, after the next barrier
+    }
+    if (bad && tid == 0) stats[5] = 1.0;       // the persistent kernel drops the coarse term for this solve
+}
+// rows of Lr above the band's start were never written: they are read only where i - e >= 0
+// A_c^-1 column by column from the banded factor: one warp per column j.  L y = e_j by column sweeps starting at k = j, then L^T x = y by column
+// sweeps of L^T (= rows of L) from the bottom; the vector lives in shared memory, the next band column is in registers before the current step ends.
+constexpr int kBandMaxPerLane = 5;       // bw <= 159
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_coarse_band_inverse(const double* __restrict__ Lc, const double* __restrict__ Lr, const double* __restrict__ Ldi,
+                                                                    double* __restrict__ Ainv, int nc, int bw) {
+    extern __shared__ double vsh[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = bw + 1;
+    const int j = blockIdx.x * WARPS + warp;
+    if (j >= nc) return;
+    double* v = vsh + (size_t)warp * nc;
+    for (int i = lane; i < nc; i += 32) v[i] = (i == j) ? 1.0 : 0.0;
+    __syncwarp();
+    double cur[kBandMaxPerLane], nxt[kBandMaxPerLane], dcur, dnxt;
+    auto fetch = [&](const double* base, int k, double* dst, double& dg) {      // entries e = 1 + lane + 32 q of band line k, and 1 / L[k][k]
+        const bool in = k >= 0 && k < nc;
+#pragma unroll
+        for (int q = 0; q < kBandMaxPerLane; q++) {
+            const int e = 1 + lane + 32 * q;
+            dst[q] = (in && e <= bw) ? __ldg(base + (size_t)k * W + e) : 0.0;
+        }
+        dg = in ? __ldg(Ldi + k) : 0.0;
+    };
+    fetch(Lc, j, cur, dcur);
+    for (int k = j; k < nc; k++) {
+        fetch(Lc, k + 1, nxt, dnxt);
+        const double yk = v[k] * dcur;
+        __syncwarp();
+        if (lane == 0) v[k] = yk;
+#pragma unroll
+        for (int q = 0; q < kBandMaxPerLane; q++) {
+            const int e = 1 + lane + 32 * q;
+            if (e <= bw && k + e < nc) v[k + e] -= cur[q] * yk;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kBandMaxPerLane; q++) cur[q] = nxt[q];
+        dcur = dnxt;
+    }
+    fetch(Lr, nc - 1, cur, dcur);
+    for (int i = nc - 1; i >= 0; i--) {
+        fetch(Lr, i - 1, nxt, dnxt);
+        const double xi = v[i] * dcur;
+        __syncwarp();
+        if (lane == 0) v[i] = xi;
+#pragma unroll
+        for (int q = 0; q < kBandMaxPerLane; q++) {
+            const int e = 1 + lane + 32 * q;
+            if (e <= bw && i - e >= 0) v[i - e] -= cur[q] * xi;      // Lr[i][e] = L[i][i - e] = (L^T)[i - e][i]
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kBandMaxPerLane; q++) cur[q] = nxt[q];
+        dcur = dnxt;
+    }
+    for (int i = lane; i < nc; i += 32) Ainv[(size_t)j * nc + i] = v[i];
 }
 
 // explicit inverse from the Cholesky factor (column-major lower): one warp per column j, L y = e_j by column sweeps, L^T x = y
@@ -1051,7 +1180,7 @@ template <typename S>
 struct PcgSmemPlan {
     size_t vec_off, rec_off, loc_off, bytes;
     int cps, Kp, fac_floats;
-    __host__ __device__ PcgSmemPlan(int cp, int cl_max, int slots_max, bool chain) {
+    __host__ __device__ PcgSmemPlan(int cp, int cl_max, int slots_max, bool chain, int nc_coarse = 0) {
         Kp = (cp / 32) | 1;
         cps = chain ? Kp * 32 : cp;                                    // chain: rows transposed to (position in group, group), odd group stride
         fac_floats = 16 * Kp * 32 + 28 * Kp;
@@ -1061,6 +1190,8 @@ struct PcgSmemPlan {
         bytes = (loc_off + (size_t)2 * (slots_max > 0 ? slots_max : 1) + 15) / 16 * 16;
         // chain: the FP32 factors are staged over the record / index region while the preconditioner runs (the indices are re-staged after)
         if (chain && rec_off + (size_t)fac_floats * 4 > bytes) bytes = rec_off + (size_t)fac_floats * 4;
+        // ... and, once the chunk solve is done, by the coarse residual (nc_coarse doubles)
+        if (chain && rec_off + (size_t)nc_coarse * 8 > bytes) bytes = (rec_off + (size_t)nc_coarse * 8 + 15) / 16 * 16;
     }
 };
 
@@ -1068,13 +1199,19 @@ template <typename S>
 __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<S> w, int max_iters, double tol2) {
     extern __shared__ __align__(16) unsigned char pcg_smem[];
     __shared__ double red[kPcgThreads / 32];
-    __shared__ double red6[kPcgThreads / 32][6];
-    __shared__ double rc_s[3 * 160];    // coarse residual (3 * (chunks + 1) <= 480)
-    __shared__ double xc_s[6];          // coarse solution at this chunk's two nodes
+    __shared__ double red6[kPcgRows][kPcgThreads / 32][6];   // per (row set, warp): P^T r of the warp's 32 rows (one segment: segments are whole groups)
+    __shared__ double xc_s[3 * (kCoarseMaxSeg + 1)];          // coarse solution at this chunk's nodes
+    __shared__ signed char seg_of_s[kPcgRows][kPcgThreads / 32];   // segment of each (row set, warp); -1 beyond the chunk
     // the coarse operator is dropped for this solve if its Cholesky factorisation met a non-positive pivot (flag set by k_potrf_diag)
     const bool chain = w.precond != 1, coarse = w.precond == 0 && __ldcg(w.cStats + 5) == 0.0;
-    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, chain);
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, chain, w.precond == 0 ? w.c_nc : 0);
     const int cps = plan.cps, Kp = plan.Kp;
+    const int hseg = w.c_h, nseg = w.c_nseg;
+    double* rc_s = reinterpret_cast<double*>(pcg_smem + plan.rec_off);   // coarse residual: over the factor staging area, after the chunk solve
+    if (threadIdx.x < kPcgRows * (kPcgThreads / 32)) {
+        const int hh = threadIdx.x / (kPcgThreads / 32), kk = threadIdx.x % (kPcgThreads / 32), r0 = 32 * kk + hh * kPcgThreads;
+        seg_of_s[hh][kk] = (signed char)((r0 < d.pc_cp) ? r0 / hseg : -1);
+    }
     S* vsm = reinterpret_cast<S*>(pcg_smem + plan.vec_off);
     S* rec = reinterpret_cast<S*>(pcg_smem + plan.rec_off);
     unsigned short* loc_s = reinterpret_cast<unsigned short*>(pcg_smem + plan.loc_off);
@@ -1130,26 +1267,30 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     auto precond_chain = [&](S* zdst, double& gacc, double& dacc2) {
         __syncthreads();
         if (coarse) {   // this chunk's part of P^T r; the exchange over the grid overlaps the chain solve below
-            double c6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int h = 0; h < kPcgRows; h++) {
+                double c6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
                 const int i = pose_i[h];
-                if (i < 0 || i == d.fixed) continue;
-                const float t = coarse_t(tid + h * kPcgThreads, cp);
-                const S* v = vsm + vx[h];
+                if (i >= 0 && i != d.fixed) {
+                    int js; float t;
+                    coarse_seg(tid + h * kPcgThreads, cp, hseg, js, t);
+                    const S* v = vsm + vx[h];
 #pragma unroll
-                for (int a = 0; a < 3; a++) { const double rv = (double)v[(6 + a) * cps]; c6[a] += (1.0 - (double)t) * rv; c6[3 + a] += (double)t * rv; }
-            }
-#pragma unroll
-            for (int a = 0; a < 6; a++) { const double sv = warp_sum(c6[a]); if (lane == 0) red6[warp][a] = sv; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int a = 0; a < 6; a++) {
-                    double sv = 0.0;
-                    for (int k = 0; k < kPcgThreads / 32; k++) sv += red6[k][a];
-                    __stcg(w.cRc + 6LL * c + a, sv);
+                    for (int a = 0; a < 3; a++) { const double rv = (double)v[(6 + a) * cps]; c6[a] = (1.0 - (double)t) * rv; c6[3 + a] = (double)t * rv; }
                 }
+#pragma unroll
+                for (int a = 0; a < 6; a++) { const double sv = warp_sum(c6[a]); if (lane == 0) red6[h][warp][a] = sv; }
             }
+            __syncthreads();
+            if (tid < 6 * nseg) {   // segment js = the warps whose 32 rows lie in it
+                const int js = tid / 6, a = tid - 6 * js;
+                double sv = 0.0;
+                for (int h = 0; h < kPcgRows; h++)
+                    for (int k = 0; k < kPcgThreads / 32; k++)
+                        if (seg_of_s[h][k] == js) sv += red6[h][k][a];
+                __stcg(w.cRc + 6LL * ((size_t)c * nseg + js) + a, sv);
+            }
+            __syncthreads();
             grid_arrive(w.bar, epoch);
         }
         if (kWide) {
@@ -1175,21 +1316,38 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
         PCG_T(9);
         if (coarse) {
             grid_wait(w.bar, gridDim.x, epoch);
-            const int nc = w.c_nc;
+            const int nc = w.c_nc, nsegs_all = grid * nseg;      // node n = start of global segment n; the last node only closes a segment
             for (int m = tid; m < nc; m += kPcgThreads) {
                 const int nd = m / 3, a = m - 3 * nd;
                 double rv = 0.0;
-                if (nd < grid) rv += __ldcg(w.cRc + 6LL * nd + a);
+                if (nd < nsegs_all) rv += __ldcg(w.cRc + 6LL * nd + a);
                 if (nd > 0) rv += __ldcg(w.cRc + 6LL * (nd - 1) + 3 + a);
                 rc_s[m] = rv;
             }
             __syncthreads();
-            if (warp < 6) {   // rows of A_c^-1 for nodes c (warps 0-2) and c + 1 (warps 3-5)
-                const double* arow = w.cAinv + (size_t)(3 * c + warp) * nc;
-                double sv = 0.0;
-                for (int m = lane; m < nc; m += 32) sv += __ldg(arow + m) * rc_s[m];
-                sv = warp_sum(sv);
-                if (lane == 0) xc_s[warp] = sv;
+            {   // rows of A_c^-1 for this chunk's nodes c * nseg .. (c + 1) * nseg: every warp takes a slice of one row, four loads in flight per lane
+                const int nr = 3 * (nseg + 1), parts = (kPcgThreads / 32) / nr > 0 ? (kPcgThreads / 32) / nr : 1;
+                const int len = ((nc + parts - 1) / parts + 31) / 32 * 32;
+                if (warp < nr * parts) {
+                    const int row = warp % nr, part = warp / nr;
+                    const double* arow = w.cAinv + (size_t)(3 * c * nseg + row) * nc;
+                    const int m1 = (part + 1) * len < nc ? (part + 1) * len : nc;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int m = part * len + lane;
+                    for (; m + 96 < m1; m += 128) {
+                        const double a0 = __ldg(arow + m), a1 = __ldg(arow + m + 32), a2 = __ldg(arow + m + 64), a3 = __ldg(arow + m + 96);
+                        s0 += a0 * rc_s[m]; s1 += a1 * rc_s[m + 32]; s2 += a2 * rc_s[m + 64]; s3 += a3 * rc_s[m + 96];
+                    }
+                    for (; m < m1; m += 32) s0 += __ldg(arow + m) * rc_s[m];
+                    const double sv = warp_sum((s0 + s1) + (s2 + s3));
+                    if (lane == 0) red6[0][warp][0] = sv;          // red6 is free here: reused as the per-warp partial
+                }
+                __syncthreads();
+                if (tid < nr) {
+                    double sv = 0.0;
+                    for (int q = 0; q < parts; q++) sv += red6[0][q * nr + tid][0];
+                    xc_s[tid] = sv;
+                }
             }
             __syncthreads();
         }
@@ -1202,8 +1360,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             const S r0 = v[6 * cps], r1 = v[7 * cps], r2 = v[8 * cps];
             S zn0 = (S)zres[vx[h]], zn1 = (S)zres[cps + vx[h]], zn2 = (S)zres[2 * cps + vx[h]];
             if (coarse && i != d.fixed) {
-                const double t = (double)coarse_t(r, cp);
-                zn0 += (S)((1.0 - t) * xc_s[0] + t * xc_s[3]); zn1 += (S)((1.0 - t) * xc_s[1] + t * xc_s[4]); zn2 += (S)((1.0 - t) * xc_s[2] + t * xc_s[5]);
+                int js; float tf;
+                coarse_seg(r, cp, hseg, js, tf);
+                const double t = (double)tf;
+                const double* xl = xc_s + 3 * js;
+                zn0 += (S)((1.0 - t) * xl[0] + t * xl[3]); zn1 += (S)((1.0 - t) * xl[1] + t * xl[4]); zn2 += (S)((1.0 - t) * xl[2] + t * xl[5]);
             }
             const S* hp = w.rowS + (size_t)c * cp + r;
             const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
@@ -1444,8 +1605,8 @@ bool pcg_fused_supported(const Dev<S>& d) {
     return plan.bytes <= (size_t)kPcgSmemBudget;
 }
 template <typename S>
-bool pcg_chain_supported(const Dev<S>& d) {
-    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, true);
+bool pcg_chain_supported(const Dev<S>& d, int nc_coarse) {
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, true, nc_coarse);
     return plan.bytes <= (size_t)kPcgSmemBudget && d.pc_cp / 32 <= 64;
 }
 
@@ -1462,26 +1623,45 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     // FP32 flavour: the Schur diagonal blocks are differences of terms ~1e8 times larger than their small eigenvalues (world-frame
     // lever arms); in float they are not reliably positive definite, and a block-tridiagonal factorisation built on them breaks
     // down at synth-2M.  The 3x3 block-Jacobi preconditioner (which only inverts them) is what the FP32 path runs.
-    int precond = (w.precond != 1 && sizeof(S) == 8 && pcg_chain_supported<S>(d)) ? w.precond : 1;
-    if (precond == 0 && w.c_nc > 3 * 160) precond = 2;
+    int precond = (w.precond != 1 && sizeof(S) == 8 && pcg_chain_supported<S>(d, 0)) ? w.precond : 1;
+    if (precond == 0 && !pcg_chain_supported<S>(d, w.c_nc)) precond = 2;
+    if (precond == 0 && (w.c_nseg < 1 || w.c_nseg > kCoarseMaxSeg || (w.c_bw <= 0 && w.c_nc > 3 * 160))) precond = 2;
     const int precond_asked = w.precond;
     w.precond = precond;
     w.precond_used = precond;
     k_pcg_fused_prep<S><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(d, w); nl++;
     if (precond != 1) { k_pcg_chain_factor<S><<<d.pc_chunks, 64, 0, st>>>(d, w); nl++; }
-    if (precond == 0) {   // coarse operator A_c = P^T S P, its Cholesky factor and explicit inverse
+    // coarse operator A_c = P^T S P, its Cholesky factor and explicit inverse.  Any SPD coarse operator makes a valid preconditioner, so A_c^-1 is
+    // kept across GN steps and refreshed every w.coarse_refresh solves, after the state was replaced from outside, or when the CG iteration
+    // count drifts above what it was right after the last refresh (coarse_stale).
+    const bool refresh = precond == 0 && (!w.coarse_valid || w.coarse_age >= w.coarse_refresh || w.coarse_stale);
+    if (refresh) {
         const int nc = w.c_nc;
         cudaMemsetAsync(w.cA, 0, sizeof(double) * (size_t)nc * nc, st);
         cudaMemsetAsync(w.cStats, 0, sizeof(double) * 8, st);
         if (d.n_clm > 0) { k_coarse_lm<S><<<(d.n_clm + 127) / 128, 128, 0, st>>>(d, w); nl++; }
-        k_coarse_pose<S><<<d.pc_chunks, 256, 0, st>>>(d, w); nl++;
+        k_coarse_pose<S><<<d.pc_chunks * w.c_nseg, 256, 0, st>>>(d, w); nl++;
         k_coarse_fix<<<(nc + 127) / 128, 128, 0, st>>>(w.cA, nc); nl++;
-        nl += dense_cholesky_lower<double>(w.cA, nc, w.cStats, st);
-        constexpr int IW = 4;
-        const size_t ism = sizeof(double) * IW * (size_t)nc;
-        k_coarse_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cA, w.cAinv, nc); nl++;
+        if (w.c_bw > 0) {   // band matrix: one CTA factorises it, one warp per column inverts it
+            const int W = w.c_bw + 1;
+            const size_t csm = sizeof(double) * (size_t)(W + 1) * W;
+            if (!ensure_dyn_smem((const void*)k_coarse_band_chol, csm)) return -1;
+            k_coarse_band_chol<<<1, kBandCholThreads, csm, st>>>(w.cA, nc, w.c_bw, w.cLc, w.cLr, w.cLdi, w.cStats); nl++;
+            constexpr int IW = 4;
+            const size_t ism = sizeof(double) * IW * (size_t)nc;
+            if (!ensure_dyn_smem((const void*)k_coarse_band_inverse<IW>, ism)) return -1;
+            k_coarse_band_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cLc, w.cLr, w.cLdi, w.cAinv, nc, w.c_bw); nl++;
+        } else {            // wide coupling (loop closures far along the chain): dense Cholesky + dense triangular inverse, nc <= 480
+            nl += dense_cholesky_lower<double>(w.cA, nc, w.cStats, st);
+            constexpr int IW = 4;
+            const size_t ism = sizeof(double) * IW * (size_t)nc;
+            k_coarse_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cA, w.cAinv, nc); nl++;
+        }
+        w.coarse_valid = true; w.coarse_age = 0; w.coarse_stale = false;
     }
-    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, precond != 1);
+    if (precond == 0) w.coarse_age++;
+    const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, precond != 1, precond == 0 ? w.c_nc : 0);
+    if (plan.bytes > (size_t)kPcgSmemBudget) return -1;
     if (!ensure_dyn_smem((const void*)k_pcg_fused<S>, plan.bytes)) return -1;
     Dev<S> dd = d;
     PcgWork<S> ww = w;
@@ -1495,6 +1675,12 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     if (iterations_out) *iterations_out = (int)host_scal[SC_ITER];
     if (launches) *launches = nl;
+    if (precond == 0) {   // iteration count right after a refresh is the yardstick for the following, lagged solves
+        const int its = (int)host_scal[SC_ITER];
+        if (refresh) w.coarse_its_ref = its;
+        else if (its > w.coarse_its_ref + w.coarse_its_ref / 4 + 4) w.coarse_stale = true;
+        if (host_scal[SC_BAD] != 0.0) w.coarse_valid = false;
+    }
     return host_scal[SC_BAD] != 0.0 ? 1 : 0;
 }
 

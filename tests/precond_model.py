@@ -10,7 +10,15 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spl
 
-COARSE_MAX_CHUNKS = 8       # kCoarseMaxChunks in solve_pcg.cu
+COARSE_MAX_CHUNKS = 8       # kCoarseMaxChunks in solve_pcg.cu (counts segments: the nodes sit at segment ends)
+
+
+def coarse_geometry(cp, nodes_per_chunk=4):
+    """ctx.cu ensure_pcg: every chunk is cut into nseg segments of h = 32 m rows (whole 32-row groups, at most 8 per chunk)"""
+    groups = max(cp // 32, 1)
+    want = min(min(nodes_per_chunk, 8), groups)
+    m = (groups + want - 1) // want
+    return 32 * m, (groups + m - 1) // m
 
 
 def chunking(NP, sm_count=148):
@@ -80,19 +88,25 @@ def chain_blocks(S, Hpp, NP, cp):
     return M, lu.solve
 
 
-def coarse_space(Hpp, Hpl, Hlli, NP, cp, nch, fixed_stix):
-    """hats over the chunks, Galerkin operator with the landmarks the kernel keeps (node list of at most 2 * COARSE_MAX_CHUNKS)"""
+def coarse_space(Hpp, Hpl, Hlli, NP, cp, nch, fixed_stix, h=None, nseg=1):
+    """hats over the segments (node n = start of global segment n = chunk * nseg + j, one more node closes the last segment), Galerkin
+    operator with the landmarks the kernel keeps (node list of at most 2 * COARSE_MAX_CHUNKS)"""
+    if h is None:
+        h = cp
     r = np.arange(NP) % cp
     c = np.arange(NP) // cp
-    t = (r + 0.5) / cp
+    j = r // h
+    seglen = np.minimum(h, cp - j * h)
+    t = (r - j * h + 0.5) / seglen
+    gs = c * nseg + j
     wl, wr = 1.0 - t, t.copy()
     wl[fixed_stix] = 0.0; wr[fixed_stix] = 0.0
     rows, cols, vals = [], [], []
     for a in range(3):
-        rows += list(3 * np.arange(NP) + a); cols += list(3 * c + a); vals += list(wl)
-        rows += list(3 * np.arange(NP) + a); cols += list(3 * (c + 1) + a); vals += list(wr)
-    P = sp.csr_matrix((vals, (rows, cols)), shape=(3 * NP, 3 * (nch + 1)))
-    # landmarks seen from too many chunks are left out of the coarse operator
+        rows += list(3 * np.arange(NP) + a); cols += list(3 * gs + a); vals += list(wl)
+        rows += list(3 * np.arange(NP) + a); cols += list(3 * (gs + 1) + a); vals += list(wr)
+    P = sp.csr_matrix((vals, (rows, cols)), shape=(3 * NP, 3 * (nch * nseg + 1)))
+    # landmarks seen from too many segments are left out of the coarse operator
     Hb = Hpl.tocsc()
     nl = Hpl.shape[1] // 2
     keep = np.ones(2 * nl)
@@ -100,14 +114,14 @@ def coarse_space(Hpp, Hpl, Hlli, NP, cp, nch, fixed_stix):
         col = Hb[:, 2 * l:2 * l + 2]
         poses = np.unique(col.nonzero()[0] // 3)
         poses = poses[poses != fixed_stix]
-        # k_coarse_lm: chunks ascending, neighbouring chunks share a node, at most 2 * COARSE_MAX_CHUNKS nodes
+        # k_coarse_lm: segments ascending, neighbouring segments share a node, at most 2 * COARSE_MAX_CHUNKS nodes
         nn, last = 0, -2
-        for ch in np.unique(poses // cp):
+        for sg in np.unique(gs[poses]):
             if nn + 2 > 2 * COARSE_MAX_CHUNKS:
                 keep[2 * l:2 * l + 2] = 0.0
                 break
-            nn += 1 if last == ch else 2
-            last = ch + 1
+            nn += 1 if last == sg else 2
+            last = sg + 1
     K = sp.diags(keep)
     HP = Hpl.T @ P
     Ac = (P.T @ (Hpp @ P) - HP.T @ (K @ Hlli @ K) @ HP).toarray()

@@ -584,3 +584,37 @@ def test_pcg_iteration_counts_match_the_cpu_model_of_the_preconditioners(built_l
         print("precond %d: %d CG iterations on the GPU, %d in the model" % (precond, st.pcg_iterations, want))
         dp = ctx.delta()[:3 * m["pr"].NP]
         assert np.abs(dp - x_model).max() <= 1e-6 * np.abs(x_model).max()
+
+
+def test_pcg_multi_segment_coarse_space_matches_the_cpu_model(built_lib):
+    """Chunks of several 32-row groups get several coarse nodes each (segments of whole groups, hats over the segments; the band
+    Cholesky / band inverse of the coarse operator): same CG iteration counts as the scipy model of that preconditioner, with the
+    coarse operator rebuilt every solve and with the lagged rebuild (same solution either way)."""
+    import torch
+    from test_precond_model import model_counts
+    rtol = 1e-9
+    m = model_counts(20000, 5000, 200000, 77, rtol, sm_count=torch.cuda.get_device_properties(0).multi_processor_count, with_bj=False)
+    assert m["nseg"] >= 2
+    P, L = m["o"].state()
+    want_cc, _, want_ch = m["its"]
+    x_model = m["x"][0]
+    for precond, want in ((0, want_cc), (2, want_ch)):
+        ctx = make_ctx(m["pr"], P, L, solver=capi.SOLVER_PCG, pcg_rtol=rtol, pcg_max_iters=20000, pcg_precond=precond, pcg_coarse_refresh=1)
+        ctx.linearize(); ctx.solve()
+        st = ctx.stats()
+        assert st.solver_status == 0 and st.precond_used == precond
+        assert 0.9 * want <= st.pcg_iterations <= 1.35 * want + 3, (precond, st.pcg_iterations, want)
+        print("multi-segment precond %d: %d CG iterations on the GPU, %d in the model (h = %d, %d segments per chunk)" %
+              (precond, st.pcg_iterations, want, m["h"], m["nseg"]))
+        dp = ctx.delta()[:3 * m["pr"].NP]
+        assert np.abs(dp - x_model).max() <= 1e-5 * np.abs(x_model).max()
+        ctx.close()
+    # lagged coarse operator: GN steps with the inverse kept for 4 solves end in the same state as with a rebuild per solve
+    outs = []
+    for refresh in (1, 4):
+        ctx = make_ctx(m["pr"], P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-10, pcg_max_iters=20000, pcg_coarse_refresh=refresh)
+        its = [ctx.step().pcg_iterations for _ in range(5)]
+        outs.append(ctx.get_state()); print("refresh %d: CG iterations per GN step %s" % (refresh, its))
+        assert ctx.stats().solver_status == 0 and max(its) <= 2.5 * its[0] + 10
+        ctx.close()
+    assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-6 and np.abs(outs[0][1] - outs[1][1]).max() <= 1e-6

@@ -8,7 +8,7 @@ from helpers import synth_problem, oracle_for
 import precond_model as pm
 
 
-def model_counts(NP, NL, E, seed, rtol, sm_count=148):
+def model_counts(NP, NL, E, seed, rtol, sm_count=148, nodes_per_chunk=4, with_bj=True):
     w, pr = synth_problem(NP, NL, E, seed=seed)
     o = oracle_for(w["pose_ids"], w["poses_init"], pr)
     o.linearize()
@@ -16,11 +16,12 @@ def model_counts(NP, NL, E, seed, rtol, sm_count=148):
     S, g = pm.schur(Hpp, Hpl, Hlli, bp, bl)
     nch, cp = pm.chunking(pr.NP, sm_count)
     M, chain = pm.chain_blocks(S, Hpp, pr.NP, cp)
-    P, Ac, coarse = pm.coarse_space(Hpp, Hpl, Hlli, pr.NP, cp, nch, pr.fixed_stix)
-    x_bj, it_bj = pm.pcg(S, g, pm.block_jacobi(S), rtol)
+    h, nseg = pm.coarse_geometry(cp, nodes_per_chunk)
+    P, Ac, coarse = pm.coarse_space(Hpp, Hpl, Hlli, pr.NP, cp, nch, pr.fixed_stix, h, nseg)
+    x_bj, it_bj = pm.pcg(S, g, pm.block_jacobi(S), rtol) if with_bj else (None, -1)
     x_ch, it_ch = pm.pcg(S, g, chain, rtol)
     x_cc, it_cc = pm.pcg(S, g, lambda r: chain(r) + coarse(r), rtol)
-    return dict(S=S, g=g, M=M, Ac=Ac, x=(x_cc, x_bj, x_ch), its=(it_cc, it_bj, it_ch), w=w, pr=pr, o=o, nch=nch, cp=cp)
+    return dict(S=S, g=g, M=M, Ac=Ac, x=(x_cc, x_bj, x_ch), its=(it_cc, it_bj, it_ch), w=w, pr=pr, o=o, nch=nch, cp=cp, h=h, nseg=nseg)
 
 
 def test_chain_and_coarse_preconditioners_are_spd_and_cut_the_iterations():
