@@ -384,7 +384,7 @@ def run_ours(args):
                        pcg_precond=args.pcg_precond)
     pr.upload(ctx)
     if args.reduce_mode < 0:
-        args.reduce_mode = 2 if solver == capi.SOLVER_PCG else 1
+        args.reduce_mode = 3 if solver == capi.SOLVER_PCG else 1
     if solver == capi.SOLVER_AUTO:   # what AUTO resolves to is only known after the first solve; the roofline block follows solver_used
         solver = None
     if world > 1:
@@ -485,7 +485,7 @@ def run_ours(args):
                     "note": "ms_per_launch is the solve phase: the persistent kernel plus its per-solve setup kernels (Schur preparation, "
                             "chain factorisation, coarse operator assembly / Cholesky / inverse), CUDA events on the context's stream"}
     else:
-        roofline = {"kernel": "H,b build: k_landmark_init + k_linearize_bearing_persistent + k_pose_finish", "bound": "hbm", "achieved": achieved, "peak": peak,
+        roofline = {"kernel": "H,b build: k_linearize_odometry (+ block init) + k_linearize_bearing_persistent", "bound": "hbm", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
                     "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel}
     line = {
@@ -498,7 +498,8 @@ def run_ours(args):
                               2: "schur+pcg(block-tridiagonal chain preconditioner)"}[args.pcg_precond]
                    if solver == capi.SOLVER_PCG else "schur+dense-cholesky",
                    "pcg_rtol": args.pcg_rtol, "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
-                   (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)"}[args.reduce_mode]) if world > 1 else "single gpu",
+                   (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)",
+                           3: "ownership: allreduce(landmark blocks, b_l) + gather of the owned pose ranges"}[args.reduce_mode]) if world > 1 else "single gpu",
                    "l2": "no flush: value + edge buffers (%.0f MB) exceed the 126 MB L2" % ((int(pi.vals_len) * S + pr.Eb * 24) / 1e6)},
         "edges_linearized_per_s": E / (ms_lin * 1e-3),
         "phases_ms": {"linearize": ms_lin_kernel, "allreduce": ms_allreduce, "solve": ms_solve, "update": ms_update},
@@ -509,7 +510,7 @@ def run_ours(args):
         "state_digest_last": stats[-1]["state_digest"],
         "precond_used": sorted(set(int(x["precond_used"]) for x in stats)), "pcg_resolves": int(sum(x["pcg_resolves"] for x in stats)),
         "roofline": roofline,
-        "roofline_linearize": {"kernel": "H,b build: k_landmark_init + k_linearize_bearing_persistent + k_pose_finish", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline_linearize": {"kernel": "H,b build: k_linearize_odometry (+ block init) + k_linearize_bearing_persistent", "bound": "hbm", "achieved": achieved, "peak": peak,
                                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
                                "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel},
         "e2e": {"value": args.steps / e2e_elapsed, "unit": "iterations/s",

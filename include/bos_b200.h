@@ -215,7 +215,10 @@ BOS_API int bos_comm_init(bos_ctx* ctx, int rank, int nranks, const char* uid128
 /* reduce_mode 0: allreduce the whole value buffer (H, b); 1: allreduce only the blocks that can overlap between ranks
  * (b, diagonal blocks, pose-pose blocks) and allgather the rank-owned pose-landmark blocks; 2: allreduce those blocks only and
  * leave the pose-landmark blocks rank-local -- enough for the fused PCG solve, which applies that part of the operator from
- * per-edge factors (bos_download_blocks / bos_download_csc then see this rank's pose-landmark blocks only). */
+ * per-edge factors (bos_download_blocks / bos_download_csc then see this rank's pose-landmark blocks only); 3: ownership-based
+ * combine: a pose's diagonal block and rhs are complete on the rank whose edge tiles own the pose (the tile its bearing run starts in),
+ * every rank computes every pose-pose block itself, so only the landmark blocks and b_l are summed (5 scalars per landmark) and the
+ * owned pose ranges are gathered (grouped broadcasts); pose-landmark blocks stay rank-local as in mode 2. */
 BOS_API int bos_set_reduce_mode(bos_ctx* ctx, int reduce_mode);
 /* Without NCCL: shard bookkeeping only (used by the host-side tests): this rank linearizes its
  * contiguous range of the pose-sorted edges. */

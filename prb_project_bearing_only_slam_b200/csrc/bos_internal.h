@@ -103,7 +103,9 @@ struct Dev {
     S* Hll = nullptr;   // xx xy yy
     S* Hoff = nullptr;  // 3x3 row-major, block H[lo][hi]
     S* Hpl = nullptr;   // SoA: entry k (3x2 row-major index) of block s at Hpl[k * hpl_ld + s]
-    S* bnd = nullptr;         // [tiles][2][9] bearing sums of pose runs cut by a tile boundary (K1 -> K2)
+    S* Mv = nullptr;          // [9][Eo] per odometry edge: M = J_s^T Omega J_s (6) and v = J_s^T Omega e (3), written by k_linearize_odometry
+    const int* cut_pose = nullptr;   // [n_cut] poses whose bearing-edge run is cut by a tile boundary (their block is assembled by REDs)
+    int n_cut = 0;
     double* stats = nullptr;  // [8] chi2_b, chi2_o, over_b, over_o, delta_inf(bits), status, state digest (k_update), -
     S* delta = nullptr;       // [N]
 };
@@ -114,8 +116,8 @@ struct ShardRange {
 
 // ---- launchers (one translation unit each) -------------------------------------------------------
 template <typename S>
-int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping_here,
-                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st);
+int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping, double damping_here,
+                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st, bool multi_rank, int rank, bool all_hoff);
 template <typename S>
 int launch_edge_terms(const Dev<S>& d, S* err_b, S* jac_b, S* err_o, S* jac_o, cudaStream_t st);
 template <typename S>

@@ -51,6 +51,8 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
@@ -71,6 +73,8 @@ NcclApi& nccl() {
             api.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
             api.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclAllGather");
             api.Broadcast = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(api.handle, "ncclBroadcast");
+            api.GroupStart = (int (*)())dlsym(api.handle, "ncclGroupStart");
+            api.GroupEnd = (int (*)())dlsym(api.handle, "ncclGroupEnd");
             api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
             api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Broadcast;
         }
@@ -106,6 +110,7 @@ struct bos_ctx {
     int rank = 0, nranks = 1, reduce_mode = 0;
     nccl_comm_t comm = nullptr;
     ShardRange shard;
+    std::vector<int> own_p0;              // [nranks + 1] first pose owned by each rank's tiles (a pose belongs to the tile its run starts in)
     int shard_chunk_b = 0;
     int launches = 0;
     bool pcg_bad = false, pcg_capped = false;
@@ -157,6 +162,17 @@ void compute_shard(bos_ctx* c) {
     c->shard_chunk_b = (int)cb;
     c->shard.b_begin = (int)o[0]; c->shard.b_end = (int)o[1];
     c->shard.o_begin = (int)o[2]; c->shard.o_end = (int)o[3];
+    c->own_p0.assign(c->nranks + 1, c->P.NP);
+    if ((int)c->P.epose_ptr.size() < c->P.NP + 1) return;      // no problem uploaded yet
+    for (int r = 0; r < c->nranks; r++) {
+        int64_t q[4];
+        shard_ranges(c->P.Eb, c->P.Eo, r, c->nranks, q, nullptr);
+        // first pose whose run starts at or after the rank's first edge; rank 0 starts at pose 0, trailing edge-free poses go to the last
+        // rank that has edges (the tile with tb == Eb), ranks without edges own nothing
+        c->own_p0[r] = (q[0] >= c->P.Eb && r > 0) ? c->P.NP
+                       : (int)(std::lower_bound(c->P.epose_ptr.begin(), c->P.epose_ptr.begin() + c->P.NP + 1, (int)q[0]) - c->P.epose_ptr.begin());
+    }
+    c->own_p0[0] = 0;
 }
 
 template <typename S>
@@ -222,7 +238,11 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
         std::vector<unsigned short> gep;
         for (int t = 0; t < ntiles; t++) {
             const int g0 = P.tile_ptr[t], g1 = P.tile_ptr[t + 1], ng = g1 - g0, ta = t * kLinTile, tb = std::min(P.Eb, ta + kLinTile);
-            meta[4 * t] = (int)glm.size(); meta[4 * t + 1] = ng; meta[4 * t + 2] = P.b_pose[ta]; meta[4 * t + 3] = P.b_pose[tb - 1];
+            // pose range the tile walks: the runs it intersects plus the poses it OWNS (run starts in the tile; edge-free poses included)
+            const int own0 = (int)(std::lower_bound(P.epose_ptr.begin(), P.epose_ptr.begin() + P.NP + 1, ta) - P.epose_ptr.begin());
+            const int own1 = (t + 1 < ntiles) ? (int)(std::lower_bound(P.epose_ptr.begin(), P.epose_ptr.begin() + P.NP + 1, ta + kLinTile) - P.epose_ptr.begin()) : P.NP;
+            meta[4 * t] = (int)glm.size(); meta[4 * t + 1] = ng;
+            meta[4 * t + 2] = std::min(P.b_pose[ta], own0); meta[4 * t + 3] = std::max(P.b_pose[tb - 1], own1 - 1);
             const int cnt = (ng + 1 + 7) & ~7;
             for (int j = 0; j < cnt; j++) {
                 glm.push_back(j < ng ? P.tg_lm[g0 + j] : 0);
@@ -231,6 +251,14 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
         }
         glm.resize(glm.size() + 8, 0); gep.resize(gep.size() + 8, 0);
         UP(tile_meta, meta) UP(tgp_lm, glm) UP(tgp_eptr, gep)
+        std::vector<int> cut;
+        for (int p = 0; p < P.NP; p++) {
+            const int ra = P.epose_ptr[p], rb = P.epose_ptr[p + 1];
+            if (rb > ra && ra / kLinTile != (rb - 1) / kLinTile) cut.push_back(p);
+        }
+        d.n_cut = (int)cut.size();
+        cut.resize(cut.size() + 1, 0);
+        UP(cut_pose, cut)
     }
     UP(pl_lm_id, P.pl_lm_id) UP(ell_Loff, P.ell_Loff) UP(ell_Lpose, P.ell_Lpose)
     UP(pc_row_pose, P.pc_row_pose) UP(pc_goff, P.pc_goff) UP(pc_cl_ptr, P.pc_cl_ptr) UP(pc_cl_row, P.pc_cl_row) UP(pc_loc, P.pc_loc)
@@ -252,11 +280,11 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     c->hpl_padded = 6 * (size_t)d.hpl_ld;
     c->vals_len = c->vals_prefix + c->hpl_padded;
     d.vals = m.get<S>(c->vals_prefix + c->hpl_padded);
-    d.bnd = m.get<S>(18 * (size_t)(d.Eb_pad / kLinTile + 1));
     d.stats = m.get<double>(8);
+    d.Mv = m.get<S>(9 * (size_t)std::max(P.Eo, 1));
     d.delta = m.get<S>((size_t)P.N);
     c->d_single_obs = m.get<int>(1);
-    if (!d.pose || !d.lm || !d.theta || !d.vals || !d.bnd || !d.stats || !d.delta || !c->d_single_obs) return fail(c, BOS_ERR_NOMEM, "device allocation failed");
+    if (!d.pose || !d.lm || !d.theta || !d.vals || !d.stats || !d.Mv || !d.delta || !c->d_single_obs) return fail(c, BOS_ERR_NOMEM, "device allocation failed");
     d.b = d.vals;
     d.Hpp = d.b + P.N;
     d.Hll = d.Hpp + 6 * (size_t)P.NP;
@@ -403,7 +431,36 @@ int allreduce_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const int dt = sizeof(S) == 8 ? kNcclFloat64 : kNcclFloat32;
     int rc;
-    if (c->reduce_mode == 2 && c->P.slots_identity) {
+    if (c->reduce_mode == 3 && c->P.slots_identity && n.GroupStart && n.GroupEnd) {
+        // Ownership-based combine (reduce only what can overlap).  A pose block (b_p, Hpp) is complete on the rank whose tiles
+        // own the pose, every rank computed every pose-pose block itself, the pose-landmark blocks stay rank-local (the fused PCG applies
+        // that part of the operator from per-edge factors): only the landmark blocks and b_l are SUMMED (5 scalars per landmark), the
+        // owned pose ranges are GATHERED (one broadcast per rank and array, grouped).
+        const size_t NP = (size_t)d.NP, NL = (size_t)d.NL;
+        rc = n.GroupStart();
+        if (rc == 0 && NL > 0) rc = n.AllReduce(d.b + 3 * NP, d.b + 3 * NP, 2 * NL, dt, kNcclSum, c->comm, c->stream);
+        if (rc == 0 && NL > 0) rc = n.AllReduce(d.Hll, d.Hll, 3 * NL, dt, kNcclSum, c->comm, c->stream);
+        for (int r = 0; r < c->nranks && rc == 0; r++) {
+            const size_t p0 = (size_t)c->own_p0[r];
+            size_t cnt = (size_t)(c->own_p0[r + 1] - c->own_p0[r]);
+            if (cnt == 0) continue;
+            // the last owned pose's run may continue into the next rank's first tile: that one block is summed (k_hb_init zeroed it on every
+            // rank, the owner holds damping + odometry + its part, the next rank the rest), everything else is gathered from its owner
+            const int pb = c->own_p0[r + 1] - 1;
+            int64_t q[4];
+            shard_ranges(c->P.Eb, c->P.Eo, r, c->nranks, q, nullptr);
+            if (r + 1 < c->nranks && c->P.epose_ptr[pb + 1] > (int)q[1] && c->P.epose_ptr[pb] < (int)q[1]) {
+                rc = n.AllReduce(d.b + 3 * (size_t)pb, d.b + 3 * (size_t)pb, 3, dt, kNcclSum, c->comm, c->stream);
+                if (rc == 0) rc = n.AllReduce(d.Hpp + 6 * (size_t)pb, d.Hpp + 6 * (size_t)pb, 6, dt, kNcclSum, c->comm, c->stream);
+                cnt--;
+                if (cnt == 0 || rc != 0) continue;
+            }
+            rc = n.Broadcast(d.b + 3 * p0, d.b + 3 * p0, 3 * cnt, dt, r, c->comm, c->stream);
+            if (rc == 0) rc = n.Broadcast(d.Hpp + 6 * p0, d.Hpp + 6 * p0, 6 * cnt, dt, r, c->comm, c->stream);
+        }
+        const int rc2 = n.GroupEnd();
+        if (rc == 0) rc = rc2;
+    } else if (c->reduce_mode == 2 && c->P.slots_identity) {
         // b, diagonal blocks and pose-pose blocks only: all the fused PCG solve reads (it applies the pose-landmark part of the
         // operator from per-edge factors); the pose-landmark planes stay rank-local
         rc = n.AllReduce(d.vals, d.vals, c->vals_prefix, dt, kNcclSum, c->comm, c->stream);
@@ -426,10 +483,11 @@ template <typename S>
 int linearize_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const bool multi = c->nranks > 1;
-    const bool zero_hpl = !c->P.slots_identity || (multi && !((c->reduce_mode == 2 || (c->reduce_mode == 1 && c->nranks <= 8)) && c->P.slots_identity));
-    const bool zero_hoff = multi || c->P.has_shared_off;
+    const bool zero_hpl = !c->P.slots_identity || (multi && !((c->reduce_mode >= 2 || (c->reduce_mode == 1 && c->nranks <= 8)) && c->P.slots_identity));
+    const bool owned = multi && c->reduce_mode == 3 && c->P.slots_identity;   // every rank writes every pose-pose block itself
+    const bool zero_hoff = (multi && !owned) || c->P.has_shared_off;
     const double damp_here = (c->rank == 0) ? c->opt.damping : 0.0;
-    c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream);
+    c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, multi && !owned, c->rank, owned);
     CUDA_OK(c, cudaGetLastError());
     c->linearized = true; c->solved = false;
     return BOS_OK;
@@ -440,8 +498,8 @@ int solve_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const int which = pick_solver(c);
     c->solver_used = which;
-    if (c->nranks > 1 && c->reduce_mode == 2 && c->P.slots_identity && !(which == BOS_SOLVER_PCG && c->opt.pcg_variant == 0))
-        return fail(c, BOS_ERR_STATE, "reduce_mode 2 leaves the pose-landmark blocks rank-local: only the fused PCG solve (pcg_variant 0) can follow");
+    if (c->nranks > 1 && c->reduce_mode >= 2 && c->P.slots_identity && !(which == BOS_SOLVER_PCG && c->opt.pcg_variant == 0))
+        return fail(c, BOS_ERR_STATE, "reduce_mode 2 / 3 leave the pose-landmark blocks rank-local: only the fused PCG solve (pcg_variant 0) can follow");
     int nl = 0, rc = 0;
     if (which == BOS_SOLVER_DENSE_CHOLESKY) {
         int e = ensure_dense<S>(c);
@@ -1035,7 +1093,7 @@ int bos_comm_init(bos_ctx* c, int rank, int nranks, const char* uid128) {
 }
 
 int bos_set_reduce_mode(bos_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 2) return BOS_ERR_INVALID;
+    if (!c || mode < 0 || mode > 3) return BOS_ERR_INVALID;
     c->reduce_mode = mode;
     return BOS_OK;
 }

@@ -4,7 +4,11 @@
 // error_and_jacobian x2 (slam/solver_jacobians.cpp:9-168).  The reference merges an N x N sparse
 // temporary into H for every edge; here every edge adds straight into precomputed block slots.
 //
-//   K3     k_landmark_init        landmark blocks start at damping * I, b_lm at 0 (H += damping * I, solver.cpp:64-69).
+//   K3     k_hb_init              every diagonal block starts at damping * I and b at 0 (H += damping * I, solver.cpp:64-69): one coalesced
+//          store pass over 9 scalars per pose and 5 per landmark.
+//   K2     k_linearize_odometry   one thread per odometry edge: error, J_s (J_dst = -J_src entry for entry, so one M = J_s^T Omega J_s and one
+//          3-vector serve the source block, the destination block and the off-diagonal block), robust kernel; the off-diagonal block is
+//          stored plainly (its slot belongs to the edge), the two diagonal blocks and b take REDs.  Independent of K1.
 //   K1     k_linearize_bearing_persistent   persistent CTAs walk tiles of 512 (pose, landmark)-sorted edges fetched by TMA bulk
 //          copies into a 2-stage shared-memory ring:
 //          - pose-landmark 3x2 blocks: owned by the edge -> stored SoA (6 planes), 128-bit coalesced stores, no atomics;
@@ -12,14 +16,9 @@
 //            is an outer product of sqrt(omega) * J with itself or with sqrt(omega) * e; the products are formed while summing);
 //          - landmark 2x2 blocks + b_lm: one thread per distinct landmark of the tile (host-precomputed tile-local grouping)
 //            sums its edges from shared memory and issues ONE set of REDs;
-//          - pose 3x3 blocks + b_pose: one thread per pose run of the tile sums its edges; a run inside the tile (all but the
-//            first / last pose of a tile) is stored PLAINLY into the pose's block, a run cut by a tile boundary goes to a
-//            per-tile side slot: no atomics and no read-modify-write on the pose side;
+//          - pose 3x3 blocks + b_pose: one thread per pose run of the tile sums its edges and issues one set of REDs (round 1 stored
+//            them plainly / into side slots and had a third kernel read them back: 25 us at 25 % occupancy; REDs cost less);
 //          - chi2 / over-threshold counts: warp + block reduction, one atomic per CTA.
-//   K2     k_pose_finish          one thread per pose, after K1: damping * I + the odometry edges incident to the pose (gathered
-//          through a CSR list; J_dst = -J_src entry for entry, so one M = J_s^T Omega J_s and one 3-vector serve the source
-//          block, the destination block and the off-diagonal block) + the bearing part K1 left in the pose's block or in the
-//          side slots of the tiles that cut it; plain stores.
 //
 // The fixed pose (gauge, solver.cpp:72-73) is handled by zeroing its Jacobian blocks at the source:
 // its rows/cols then hold only the damping and a zero rhs, which is the same linear system as
@@ -67,168 +66,74 @@ template <int N, typename T> __device__ __forceinline__ void storeN(T* p, const 
 
 // ---- K3 -------------------------------------------------------------------------------------------------------------
 template <typename S>
-__global__ void __launch_bounds__(256) k_landmark_init(Dev<S> d, S damping) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.NL) return;
-    S* hl = d.Hll + 3LL * i;
-    hl[0] = damping; hl[1] = S(0); hl[2] = damping;
-    d.b[3LL * d.NP + 2LL * i] = S(0);
-    d.b[3LL * d.NP + 2LL * i + 1] = S(0);
+__device__ __forceinline__ void hb_init_item(const Dev<S>& d, S damping, int i) {
+    if (i < d.NL) {
+        S* hl = d.Hll + 3LL * i;
+        hl[0] = damping; hl[1] = S(0); hl[2] = damping;
+        d.b[3LL * d.NP + 2LL * i] = S(0);
+        d.b[3LL * d.NP + 2LL * i + 1] = S(0);
+    } else if (i - d.NL < d.n_cut) {      // poses whose bearing run is cut by a tile boundary: their parts arrive by REDs
+        const int p = __ldg(d.cut_pose + (i - d.NL));
+        S* hp = d.Hpp + 6LL * p;
+#pragma unroll
+        for (int k = 0; k < 6; k++) hp[k] = S(0);
+        d.b[3LL * p] = S(0); d.b[3LL * p + 1] = S(0); d.b[3LL * p + 2] = S(0);
+    }
 }
+template <typename S>
+__global__ void __launch_bounds__(256) k_hb_init(Dev<S> d, S damping) { hb_init_item<S>(d, damping, blockIdx.x * blockDim.x + threadIdx.x); }
 
 // ---- K2 -------------------------------------------------------------------------------------------------------------
-// side slots of the bearing kernel: [tile][slot][9], slot 0 = the run that enters the tile from the previous one, 1 = the run
-// that leaves it; 9 = Hpp (xx xy xt yy yt tt) + b (x y t)
 template <typename S>
-__global__ void __launch_bounds__(128, 4) k_pose_finish(Dev<S> d, int e_begin, int e_end, int o_begin, int o_end, S kernel_threshold, S damping,
-                                                        const S* __restrict__ bnd) {
+__global__ void __launch_bounds__(128) k_linearize_odometry(Dev<S> d, int o_begin, int o_end, int s_begin, int s_end, S kernel_threshold, S damping_init, int all_hoff) {
     __shared__ double red[2][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ig = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = ig < d.NP;            // every lane runs the whole body (the chain hand-over below shuffles), only valid lanes store
-    const int i = valid ? ig : d.NP - 1;
+    const int e = o_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    // K3 rides in the same launch: the threads past the last edge initialise the landmark blocks and the cut poses (nothing here reads them)
+    if (e >= o_end) hb_init_item<S>(d, damping_init, e - o_end);
     double chi_acc = 0.0;
     int over_acc = 0;
-    S h[6] = {damping, S(0), S(0), damping, S(0), damping};
-    S b[3] = {S(0), S(0), S(0)};
-    // the bearing part left by K1: in the pose's own block when its run lies inside one tile, else in the side slots
-    {
-        const int ra = __ldg(d.epose_ptr + i), rb = __ldg(d.epose_ptr + i + 1);
-        const int lo = ra > e_begin ? ra : e_begin, hi = rb < e_end ? rb : e_end;
-        if (hi > lo && i != d.fixed) {
-            const int t0 = (lo - e_begin) / kLinTile, t1 = (hi - 1 - e_begin) / kLinTile;
-            for (int t = t0; t <= t1; t++) {
-                const int ta = e_begin + t * kLinTile, tb = (ta + kLinTile < e_end) ? ta + kLinTile : e_end;
-                if (ra >= ta && rb <= tb) {
-                    const S* hp = d.Hpp + 6LL * i;
-                    const S* bp = d.b + 3LL * i;
+    bool return_skip = false;
+    if (e < o_end) {
+        const size_t Eo = (size_t)d.Eo;
+        const int s = __ldg(d.o_src + e), t = __ldg(d.o_dst + e);
+        const PoseV<S> Xs = load_pose<S>(d.pose, s), Xd = load_pose<S>(d.pose, t);
+        const S ths = __ldg(d.theta + s), thd = __ldg(d.theta + t);
+        S om[6], z[3];
 #pragma unroll
-                    for (int k = 0; k < 6; k++) h[k] += hp[k];
-                    b[0] += bp[0]; b[1] += bp[1]; b[2] += bp[2];
-                    continue;
-                }
-                const S* src = bnd + (size_t)(2 * t + (ra < ta ? 0 : 1)) * 9;
+        for (int k = 0; k < 6; k++) om[k] = __ldg(d.o_om + k * Eo + e);
 #pragma unroll
-                for (int k = 0; k < 6; k++) h[k] += src[k];
-                b[0] += src[6]; b[1] += src[7]; b[2] += src[8];
-            }
-        }
-    }
-    const size_t Eo = (size_t)d.Eo;
-    const PoseV<S> Xi = load_pose<S>(d.pose, i);
-    const S thi = __ldg(d.theta + i);
-    // everything an incident odometry edge needs, loaded up front so that the loads of several edges are in flight together
-    struct EdgeIn { int e, role, other, slot; bool live, shared; PoseV<S> Xo; S tho, om[6], z[3]; };
-    auto load_edge = [&](int code, int other) {
-        EdgeIn in;
-        in.e = code >> 1; in.role = code & 1; in.other = other; in.slot = 0; in.shared = false;
-        in.live = code >= 0 && in.e >= o_begin && in.e < o_end;
-        if (in.live) {
-            in.Xo = load_pose<S>(d.pose, other);
-            in.tho = __ldg(d.theta + other);
-#pragma unroll
-            for (int k = 0; k < 6; k++) in.om[k] = __ldg(d.o_om + k * Eo + in.e);
-#pragma unroll
-            for (int k = 0; k < 3; k++) in.z[k] = __ldg(d.o_z + k * Eo + in.e);
-            in.slot = __ldg(d.o_slot + in.e);
-            in.shared = d.o_shared[in.e] != 0;
-        }
-        return in;
-    };
-    // M = J_s^T Omega J_s and v = J_s^T Omega e of an edge (J_dst = -J_src entry for entry); also chi2 / over-threshold
-    auto edge_normal = [&](const EdgeIn& in, S M[6], S v[3], S& chi, bool& over) {
-        const PoseV<S> Xs = in.role ? in.Xo : Xi, Xd = in.role ? Xi : in.Xo;
+        for (int k = 0; k < 3; k++) z[k] = __ldg(d.o_z + k * Eo + e);
+        const int slot = __ldg(d.o_slot + e);
+        const bool shared = d.o_shared[e] != 0;
         S err[3], u0, u1;
-        odometry_terms<S>(Xs, Xd, in.role ? in.tho : thi, in.role ? thi : in.tho, in.z[0], in.z[1], in.z[2], err, u0, u1);
-        chi = odometry_chi<S>(in.om, err);
+        odometry_terms<S>(Xs, Xd, ths, thd, z[0], z[1], z[2], err, u0, u1);
+        const S chi = odometry_chi<S>(om, err);
         S scale = S(1);
-        over = chi > kernel_threshold;
+        const bool over = chi > kernel_threshold;
         if (over) scale = sqrt(kernel_threshold / chi);   // scales the ERROR only (slam/solver.cpp:54-58)
-        odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, in.om, err, M, v, scale);
-    };
-    auto add_as_source = [&](const EdgeIn& in, const S M[6], const S v[3], S chi, bool over) {
-        const bool fs = (i == d.fixed), ft = (in.other == d.fixed);
-        chi_acc += (double)chi;
-        over_acc += over ? 1 : 0;
-        if (!fs) {
+        S M[6], v[3];
+        odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, om, err, M, v, scale);
+        if (e >= s_begin && e < s_end) { chi_acc = (double)chi; over_acc = over ? 1 : 0; }   // statistics: this rank's share of the edges only
+        const bool fs = (s == d.fixed), ft = (t == d.fixed);      // gauge: the fixed pose's Jacobian block is zero
+        // M and v go to a per-edge scratch (SoA, coalesced); the pose threads of the bearing kernel add them to the two diagonal blocks
 #pragma unroll
-            for (int k = 0; k < 6; k++) h[k] += M[k];
-            b[0] += v[0]; b[1] += v[1]; b[2] += v[2];
-        }
-        if (!valid) return;
+        for (int k = 0; k < 6; k++) d.Mv[k * Eo + e] = M[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) d.Mv[(6 + k) * Eo + e] = v[k];
         // H[lo][hi] += J_lo^T Omega J_hi = -M (M symmetric, so the orientation does not matter)
-        S* ho = d.Hoff + 9LL * in.slot;
-        const S z = (fs || ft) ? S(0) : S(1);
-        const S m9[9] = {-M[0] * z, -M[1] * z, -M[2] * z, -M[1] * z, -M[3] * z, -M[4] * z, -M[2] * z, -M[4] * z, -M[5] * z};
-        if (in.shared) {
+        if (!all_hoff && (e < s_begin || e >= s_end)) return_skip = true;      // several ranks: the off-diagonal block comes from the rank whose share holds the edge
+        S* ho = d.Hoff + 9LL * slot;
+        const S zf = (fs || ft) ? S(0) : S(1);
+        const S m9[9] = {-M[0] * zf, -M[1] * zf, -M[2] * zf, -M[1] * zf, -M[3] * zf, -M[4] * zf, -M[2] * zf, -M[4] * zf, -M[5] * zf};
+        if (return_skip) {
+        } else if (shared) {
 #pragma unroll
             for (int k = 0; k < 9; k++) red_add(ho + k, m9[k]);
         } else {
 #pragma unroll
             for (int k = 0; k < 9; k++) ho[k] = m9[k];
         }
-    };
-    auto add_as_destination = [&](const S M[6], const S v[3]) {
-        if (i == d.fixed) return;
-#pragma unroll
-        for (int k = 0; k < 6; k++) h[k] += M[k];
-        b[0] -= v[0]; b[1] -= v[1]; b[2] -= v[2];
-    };
-    const int4 m2 = __ldg(reinterpret_cast<const int4*>(d.oe2) + i);   // the first two incident edges inline (odometry chains)
-    const EdgeIn e0 = load_edge(m2.x, m2.y), e1 = load_edge(m2.z, m2.w);
-    // 1. edges this pose is the SOURCE of: computed here; the last one is offered to the next lane, which along an odometry chain
-    //    is that edge's destination and then does not have to recompute it
-    int pub_e = -1;
-    S pubM[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, pubv[3] = {S(0), S(0), S(0)};
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const EdgeIn& in = k ? e1 : e0;
-        if (in.live && in.role == 0) {
-            S chi; bool over;
-            edge_normal(in, pubM, pubv, chi, over);
-            add_as_source(in, pubM, pubv, chi, over);
-            pub_e = valid ? in.e : -1;
-        }
-    }
-    const int prev_e = __shfl_up_sync(BOS_FULL_MASK, pub_e, 1);
-    S prevM[6], prevv[3];
-#pragma unroll
-    for (int k = 0; k < 6; k++) prevM[k] = __shfl_up_sync(BOS_FULL_MASK, pubM[k], 1);
-#pragma unroll
-    for (int k = 0; k < 3; k++) prevv[k] = __shfl_up_sync(BOS_FULL_MASK, pubv[k], 1);
-    // 2. edges this pose is the DESTINATION of: taken from the previous lane when it just computed exactly that edge
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const EdgeIn& in = k ? e1 : e0;
-        if (in.live && in.role == 1) {
-            if (lane > 0 && prev_e == in.e) {
-                add_as_destination(prevM, prevv);
-            } else {
-                S M[6], v[3], chi; bool over;
-                edge_normal(in, M, v, chi, over);
-                add_as_destination(M, v);
-            }
-        }
-    }
-    if (m2.z >= 0) {   // more than two incident edges (loop closures): the rest through the CSR list
-        const int q0 = __ldg(d.oe_ptr + i), q1 = __ldg(d.oe_ptr + i + 1);
-        for (int q = q0 + 2; q < q1; q++) {
-            const EdgeIn in = load_edge(__ldg(d.oe_edge + q), __ldg(d.oe_other + q));
-            if (!in.live) continue;
-            S M[6], v[3], chi; bool over;
-            edge_normal(in, M, v, chi, over);
-            if (in.role == 0) add_as_source(in, M, v, chi, over);
-            else add_as_destination(M, v);
-        }
-    }
-    if (valid) {
-        S* hp = d.Hpp + 6LL * i;
-#pragma unroll
-        for (int k = 0; k < 6; k++) hp[k] = h[k];
-        S* bp = d.b + 3LL * i;
-        bp[0] = b[0]; bp[1] = b[1]; bp[2] = b[2];
-    } else {
-        chi_acc = 0.0; over_acc = 0;
     }
     double c = warp_sum(chi_acc), o = warp_sum((double)over_acc);
     if (lane == 0) { red[0][warp] = c; red[1][warp] = o; }
@@ -281,7 +186,7 @@ struct LinSmem {
 };
 
 template <typename S, bool kIdentSlots>
-__global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bearing_persistent(Dev<S> d, int e_begin, int e_end, S kernel_threshold, S* __restrict__ bnd) {
+__global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bearing_persistent(Dev<S> d, int e_begin, int e_end, S kernel_threshold, S damping) {
     extern __shared__ __align__(128) unsigned char lin_smem_raw[];
     LinSmem<S>& sm = *reinterpret_cast<LinSmem<S>*>(lin_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,17 +330,45 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
 #pragma unroll
                 for (int q = 0; q < 9; q++) v[q] += __shfl_xor_sync(BOS_FULL_MASK, v[q], o);
             }
-            if (live && sub == 0) {
-                if (ra >= ta && rb <= tb) {   // the whole run is in this tile: plain store into the pose's own block
+            if (p <= plast && sub == 0) {
+                // The tile in which a pose's run STARTS owns the pose (edge-free poses included: their empty run starts somewhere too):
+                // it adds the damping and the pose's odometry edges, so the block is final after ONE plain store.  Only a run cut by a
+                // tile boundary (one pose per boundary, zeroed by k_hb_init) arrives in parts, by REDs.
+                const bool owner = (ra >= ta && ra < tb) || (tb == d.Eb && ra == d.Eb);
+                const bool cut = rb > ra && (ra / kLinTile != (rb - 1) / kLinTile);
+                if (owner) {
+                    v[0] += damping; v[3] += damping; v[5] += damping;
+                    if (p != d.fixed) {
+                        const size_t Eo = (size_t)d.Eo;
+                        auto add_edge = [&](int code) {      // (edge << 1) | role; J_dst = -J_src: M enters both diagonal blocks, v changes sign
+                            const int e = code >> 1;
+                            const S sg = (code & 1) ? S(-1) : S(1);
+#pragma unroll
+                            for (int q = 0; q < 6; q++) v[q] += __ldg(d.Mv + q * Eo + e);
+#pragma unroll
+                            for (int q = 0; q < 3; q++) v[6 + q] += sg * __ldg(d.Mv + (6 + q) * Eo + e);
+                        };
+                        const int4 m2 = __ldg(reinterpret_cast<const int4*>(d.oe2) + p);
+                        if (m2.x >= 0) add_edge(m2.x);
+                        if (m2.z >= 0) {
+                            add_edge(m2.z);
+                            const int q0 = __ldg(d.oe_ptr + p), q1 = __ldg(d.oe_ptr + p + 1);
+                            for (int q = q0 + 2; q < q1; q++) add_edge(__ldg(d.oe_edge + q));   // loop closures
+                        }
+                    }
+                }
+                if (owner || live) {
                     S* hp = d.Hpp + 6LL * p;
                     S* bp = d.b + 3LL * p;
+                    if (cut) {
 #pragma unroll
-                    for (int q = 0; q < 6; q++) hp[q] = v[q];
-                    bp[0] = v[6]; bp[1] = v[7]; bp[2] = v[8];
-                } else {                      // cut by a tile boundary: side slot, summed by k_pose_finish
-                    S* dst = bnd + (size_t)(2 * tile + (ra < ta ? 0 : 1)) * 9;
+                        for (int q = 0; q < 6; q++) red_add(hp + q, v[q]);
+                        red_add(bp, v[6]); red_add(bp + 1, v[7]); red_add(bp + 2, v[8]);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < 9; q++) dst[q] = v[q];
+                        for (int q = 0; q < 6; q++) hp[q] = v[q];
+                        bp[0] = v[6]; bp[1] = v[7]; bp[2] = v[8];
+                    }
                 }
             }
         }
@@ -454,14 +387,41 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
     }
 }
 
+// no bearing edges at all (a pure pose graph): nobody walks tiles, so the poses are finished here
 template <typename S>
-int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping_here,
-                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st) {
+__global__ void __launch_bounds__(128) k_pose_finish_nobearing(Dev<S> d, S damping) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.NP) return;
+    S v[9] = {damping, S(0), S(0), damping, S(0), damping, S(0), S(0), S(0)};
+    if (p != d.fixed) {
+        const size_t Eo = (size_t)d.Eo;
+        for (int q = __ldg(d.oe_ptr + p); q < __ldg(d.oe_ptr + p + 1); q++) {
+            const int code = __ldg(d.oe_edge + q), e = code >> 1;
+            const S sg = (code & 1) ? S(-1) : S(1);
+            for (int k = 0; k < 6; k++) v[k] += __ldg(d.Mv + k * Eo + e);
+            for (int k = 0; k < 3; k++) v[6 + k] += sg * __ldg(d.Mv + (6 + k) * Eo + e);
+        }
+    }
+    for (int k = 0; k < 6; k++) d.Hpp[6LL * p + k] = v[k];
+    for (int k = 0; k < 3; k++) d.b[3LL * p + k] = v[6 + k];
+}
+
+template <typename S>
+int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping, double damping_here,
+                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st, bool multi_rank, int rank, bool all_hoff) {
+    // damping: what an owned pose block starts from; damping_here: what this rank adds to the landmark blocks (they are summed over ranks)
     int launches = 0;
     cudaMemsetAsync(d.stats, 0, 8 * sizeof(double), st);
     if (zero_hoff && d.n_off > 0) cudaMemsetAsync(d.Hoff, 0, sizeof(S) * 9 * (size_t)d.n_off, st);
     if (zero_hpl && d.n_hpl > 0) cudaMemsetAsync(d.Hpl, 0, sizeof(S) * 6 * (size_t)d.hpl_ld, st);
-    if (d.NL > 0) { k_landmark_init<S><<<(d.NL + 255) / 256, 256, 0, st>>>(d, (S)damping_here); launches++; }
+    // several ranks: a pose block is written by the rank that owns the pose only, the others contribute zeros to the combine
+    if (multi_rank) cudaMemsetAsync(d.vals, 0, sizeof(S) * ((size_t)d.N + 6 * (size_t)d.NP), st);
+    // every rank linearizes ALL odometry edges (0.2 M at synth-2M: the pose owner needs both of a pose's edges); statistics count the rank's share.
+    // The same launch initialises the landmark blocks and the cut poses (K3).
+    if (d.Eo > 0) {
+        k_linearize_odometry<S><<<(d.Eo + d.NL + d.n_cut + 127) / 128, 128, 0, st>>>(d, 0, d.Eo, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here, all_hoff ? 1 : 0);
+        launches++;
+    } else if (d.NL + d.n_cut > 0) { k_hb_init<S><<<(d.NL + d.n_cut + 255) / 256, 256, 0, st>>>(d, (S)damping_here); launches++; }
     const int nb = r.b_end - r.b_begin;
     if (nb > 0) {
         const int tiles = (nb + kLinTile - 1) / kLinTile;
@@ -471,13 +431,14 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
         int grid = sm_count * kLinPersistCtas;
         if (grid > tiles) grid = tiles;
         if (d.b_slot == nullptr)
-            k_linearize_bearing_persistent<S, true><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, d.bnd);
+            k_linearize_bearing_persistent<S, true><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
         else
-            k_linearize_bearing_persistent<S, false><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, d.bnd);
+            k_linearize_bearing_persistent<S, false><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
+        launches++;
+    } else if (d.Eb == 0 && rank == 0 && d.NP > 0) {
+        k_pose_finish_nobearing<S><<<(d.NP + 127) / 128, 128, 0, st>>>(d, (S)damping);
         launches++;
     }
-    k_pose_finish<S><<<(d.NP + 127) / 128, 128, 0, st>>>(d, r.b_begin, r.b_end, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here, d.bnd);
-    launches++;
     return launches;
 }
 
@@ -579,8 +540,8 @@ int launch_update(const Dev<S>& d, cudaStream_t st) {
     return 1;
 }
 
-template int launch_linearize<double>(const Dev<double>&, const ShardRange&, double, double, bool, bool, int, cudaStream_t);
-template int launch_linearize<float>(const Dev<float>&, const ShardRange&, double, double, bool, bool, int, cudaStream_t);
+template int launch_linearize<double>(const Dev<double>&, const ShardRange&, double, double, double, bool, bool, int, cudaStream_t, bool, int, bool);
+template int launch_linearize<float>(const Dev<float>&, const ShardRange&, double, double, double, bool, bool, int, cudaStream_t, bool, int, bool);
 template int launch_edge_terms<double>(const Dev<double>&, double*, double*, double*, double*, cudaStream_t);
 template int launch_edge_terms<float>(const Dev<float>&, float*, float*, float*, float*, cudaStream_t);
 template int launch_pose_theta<double>(const Dev<double>&, cudaStream_t);

@@ -4,8 +4,8 @@ rows = [r for r in csv.reader(open(sys.argv[1], errors="ignore")) if len(r) > 5]
 h = rows[0]
 kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
 seq = [(r[kn].split("(")[0], float(r[mv].replace(",", "")) * (1e-3 if r[mu] in ("ns", "nsecond") else 1.0)) for r in rows[1:] if r[mv]]
-# the last GN step: from the last k_landmark_init on
-start = max((i for i, (k, _) in enumerate(seq) if "k_landmark_init" in k), default=0)
+# the last GN step: from the last k_hb_init on
+start = max((i for i, (k, _) in enumerate(seq) if "k_hb_init" in k), default=0)
 step = seq[start:]
 tot = sum(t for _, t in step)
 agg = collections.OrderedDict()

@@ -1,7 +1,8 @@
 """torchrun --nproc-per-node N tools/mgpu_check.py : edge-sharded linearization + NCCL combine against the single-GPU result.
 Every rank builds the same synthetic world; rank r linearizes its edge shard on GPU r; after the combine every rank must
-hold the same H, b, chi2 as an unsharded context (1e-12 relative: only the summation order differs), for both reduce modes,
-and a full step must give the same state."""
+hold the same H, b, chi2 as an unsharded context (1e-12 relative: only the summation order differs), for every reduce mode
+(0 full allreduce, 1 allreduce of the overlapping blocks + allgather of the pose-landmark planes, 2 allreduce of the overlapping
+blocks only, 3 ownership-based: landmark blocks summed, owned pose ranges gathered), and a full step must give the same state."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,7 +28,7 @@ P0, L0 = ref.get_state()
 ref.linearize()
 rb = ref.blocks(); rs = ref.stats()
 ok = True
-for mode in (0, 1, 2):
+for mode in (0, 1, 2, 3):
     ctx = capi.Context(device=local, solver=capi.SOLVER_PCG, pcg_rtol=1e-12, pcg_max_iters=20000)
     pr.upload(ctx)
     uid = [capi.nccl_unique_id() if rank == 0 else None]
@@ -37,7 +38,7 @@ for mode in (0, 1, 2):
     ctx.set_state(P0, L0)
     ctx.linearize()
     b = ctx.blocks(); s = ctx.stats()
-    for k in ("Hpp", "Hll", "Hoff", "b") + (("Hpl",) if mode < 2 else ()):
+    for k in ("Hpp", "Hll", "Hoff", "b") + (("Hpl",) if mode < 2 else ()):   # modes 2 / 3 leave the pose-landmark blocks rank-local
         den = max(np.abs(rb[k]).max(), 1e-300)
         err = np.abs(b[k] - rb[k]).max() / den
         if err > 1e-12:
