@@ -479,14 +479,27 @@ def run_ours(args):
         roofline = {"kernel": "k_pcg_fused (persistent cooperative kernel: the whole %s PCG solve of one GN iteration)" %
                               ({0: "chain + coarse-space preconditioned", 1: "block-Jacobi", 2: "chain-preconditioned"}[args.pcg_precond]),
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": (t_it * pcg_iters) if t_it else None, "peak_source": peak_src,
+                    "traffic": (t_it * pcg_iters) if (t_it and world == 1) else None,
+                    "traffic_source": "profiles/traffic.json: dram__bytes of one ncu --set full capture of this command at N = 1, scaled to this run's CG iterations (not re-measured here)",
+                    "peak_source": peak_src,
                     "bytes_per_launch": b_it * pcg_iters, "bytes_per_cg_iteration": b_it, "cg_iterations_per_launch": pcg_iters,
                     "ms_per_launch": ms_solve, "us_per_cg_iteration": 1e3 * ms_solve / pcg_iters,
                     "note": "ms_per_launch is the solve phase: the persistent kernel plus its per-solve setup kernels (Schur preparation, "
                             "chain factorisation, coarse operator assembly / Cholesky / inverse), CUDA events on the context's stream"}
+    elif solver == capi.SOLVER_DENSE_CHOLESKY and 3 * pr.NP >= 2048:
+        # the dominant kernels of a dense step are the FP64 tensor-pipe (DMMA) trailing updates of the blocked Cholesky
+        n3 = 3.0 * pr.NP
+        flops = n3 ** 3 / 3.0
+        p64 = os.path.join(ROOT, "profiles", "fp64_peak_r02.json")
+        peak64 = float(json.load(open(p64))["fp64_gemm_tflops_sustained"]) if os.path.exists(p64) else 35.3
+        ach = flops / (ms_solve * 1e-3) / 1e12
+        roofline = {"kernel": "dense Cholesky of the reduced pose system (k_syrk_big: mma.sync.m8n8k4.f64 trailing updates; tcgen05 has no FP64 kind)",
+                    "bound": "tensor", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64, "traffic": None,
+                    "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/fp64_peak_r02.json)", "flops_per_launch": flops,
+                    "ms_per_launch": ms_solve, "note": "ms_per_launch is the whole solve phase (Schur assembly, factorisation, triangular solves)"}
     else:
         roofline = {"kernel": "H,b build: k_linearize_odometry (+ block init) + k_linearize_bearing_persistent", "bound": "hbm", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes") if world == 1 else None, "peak_source": peak_src,
                     "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel}
     line = {
         "metric": "gn_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
@@ -497,7 +510,8 @@ def run_ours(args):
                    "N": int(pi.N), "solver": {0: "schur+pcg(block-tridiagonal chain + coarse-space preconditioner)", 1: "schur+block-jacobi-pcg",
                               2: "schur+pcg(block-tridiagonal chain preconditioner)"}[args.pcg_precond]
                    if solver == capi.SOLVER_PCG else "schur+dense-cholesky",
-                   "pcg_rtol": args.pcg_rtol, "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
+                   "pcg_rtol": args.pcg_rtol, "pcg_coarse": "4 nodes per chunk, inverse kept for 8 solves" if solver == capi.SOLVER_PCG and args.pcg_precond == 0 else None,
+                   "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
                    (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)",
                            3: "ownership: allreduce(landmark blocks, b_l) + gather of the owned pose ranges"}[args.reduce_mode]) if world > 1 else "single gpu",
                    "l2": "no flush: value + edge buffers (%.0f MB) exceed the 126 MB L2" % ((int(pi.vals_len) * S + pr.Eb * 24) / 1e6)},
@@ -511,7 +525,7 @@ def run_ours(args):
         "precond_used": sorted(set(int(x["precond_used"]) for x in stats)), "pcg_resolves": int(sum(x["pcg_resolves"] for x in stats)),
         "roofline": roofline,
         "roofline_linearize": {"kernel": "H,b build: k_linearize_odometry (+ block init) + k_linearize_bearing_persistent", "bound": "hbm", "achieved": achieved, "peak": peak,
-                               "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes"), "peak_source": peak_src,
+                               "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get("hb_build_dram_bytes") if world == 1 else None, "peak_source": peak_src,
                                "bytes_per_launch": bytes_build, "ms_per_launch": ms_lin_kernel},
         "e2e": {"value": args.steps / e2e_elapsed, "unit": "iterations/s",
                 "h2d_bytes_per_step": int((4 * pr.NP + 2 * pr.NL) * 8), "d2h_bytes_per_step": int((4 * pr.NP + 2 * pr.NL) * 8 + 64)},

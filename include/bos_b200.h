@@ -53,7 +53,9 @@ typedef struct bos_options {
     int device;               /* CUDA ordinal */
     int precision;            /* BOS_PRECISION_* ; F64 is the 1e-9 parity path, F32 is the reference's own precision */
     int solver;               /* BOS_SOLVER_* ; AUTO = dense Cholesky when 3*NP <= dense_max_dim, else PCG */
-    int dense_max_dim;        /* default 36000 */
+    int dense_max_dim;        /* default 192: measured on B200 (profiles/solver_sweep_r02.jsonl) the persistent PCG beats the dense
+                                 Cholesky from 3*NP ~ 300 on (0.6 vs 0.8 ms) and by 44x at 3*NP = 18000; the dense path stays available through
+                                 BOS_SOLVER_DENSE_CHOLESKY (BASELINE config 3 names it) */
     double kernel_threshold;  /* slam/solver.cpp:16  default 1.0  */
     double damping;           /* slam/solver.cpp:17  default 0.01 */
     int pcg_max_iters;        /* default 20000 (block-Jacobi needs ~5300 CG iterations on a 200k-pose odometry chain) */
@@ -70,7 +72,7 @@ typedef struct bos_options {
     int pcg_coarse_nodes;     /* coarse-space nodes per chunk of the default preconditioner: 0 = default (4), 1 = the round-1 layout (one
                                  hat per chunk); rounded so that segments are whole groups of 32 poses, at most 8 */
     int pcg_coarse_refresh;   /* the coarse operator's inverse is kept across GN steps and rebuilt every this many solves (also whenever
-                                 the state is replaced through the API or the CG iteration count drifts up by 25 %); 0 = default (4),
+                                 the state is replaced through the API or the CG iteration count drifts up by 25 %); 0 = default (8),
                                  1 = rebuild for every solve.  Any SPD coarse operator is a valid preconditioner: only the iteration
                                  count depends on it, never the solution */
     int reserved[4];

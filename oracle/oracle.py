@@ -223,6 +223,29 @@ class Oracle:
     def step(self, kind=0, max_iters=2000, rtol=1e-12):
         self.L.orc_step(self.h, kind, max_iters, rtol)
 
+    def step_lm(self, damping, kernel_threshold=1.0, kind=0):
+        """Restatement of the opt-in Levenberg-Marquardt iteration of include/bos_b200.h (bos_step_lm; an extension: the reference has
+        a FIXED damping and never rejects a step, slam/solver.cpp:64-69): take a GN step with `damping`, relinearize, keep the step
+        and divide the damping by 3 if the total chi2 (pre-kernel error_omeganorm sums) decreased, else restore the state and
+        multiply the damping by 10 (clamped to [1e-9, 1e9]).  Returns (chi2_before, chi2_after, accepted, next_damping)."""
+        P, L = self.state()
+        self.set_params(kernel_threshold, damping)
+        self.linearize()
+        s = self.stats()
+        before = s["chi2_bearing"] + s["chi2_odometry"]
+        self.solve(kind)
+        self.apply_boxplus()
+        self.linearize()
+        s = self.stats()
+        after = s["chi2_bearing"] + s["chi2_odometry"]
+        ok = after < before
+        if ok:
+            damping = max(damping / 3.0, 1e-9)
+        else:
+            self.set_state(P, L)
+            damping = min(damping * 10.0, 1e9)
+        return before, after, ok, damping
+
     def stats(self):
         s = np.zeros(8)
         self.L.orc_get_stats(self.h, _p(s))

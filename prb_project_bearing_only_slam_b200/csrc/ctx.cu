@@ -400,7 +400,7 @@ int ensure_pcg(bos_ctx* c) {
             w.c_nc = 3 * (d.pc_chunks * w.c_nseg + 1);
             w.c_bw = (bw <= 158) ? std::min(bw, w.c_nc - 1) : 0;
             if (w.c_bw < 1 && w.c_nc > 1) w.c_bw = (bw <= 158) ? 1 : 0;
-            w.coarse_refresh = c->opt.pcg_coarse_refresh > 0 ? c->opt.pcg_coarse_refresh : 4;
+            w.coarse_refresh = c->opt.pcg_coarse_refresh > 0 ? c->opt.pcg_coarse_refresh : 8;
             w.coarse_valid = false; w.coarse_stale = false; w.coarse_age = 0;
         }
         w.cA = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
@@ -735,7 +735,7 @@ void bos_default_options(bos_options* o) {
     o->device = 0;
     o->precision = BOS_PRECISION_F64;
     o->solver = BOS_SOLVER_AUTO;
-    o->dense_max_dim = 36000;
+    o->dense_max_dim = 192;   // measured crossover (profiles/solver_sweep_r02.jsonl): the PCG wins from 3 NP ~ 300 on
     o->kernel_threshold = 1.0;
     o->damping = 0.01f;  // the reference's float literal, widened (slam/solver.cpp:17)
     o->pcg_max_iters = 20000;

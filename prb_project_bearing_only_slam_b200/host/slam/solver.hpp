@@ -15,7 +15,7 @@ struct SolverOptions {
     int device = 0;
     bool fp32 = false;                 // false: FP64 arithmetic (parity path); true: the reference's own precision
     int solver = BOS_SOLVER_AUTO;      // Schur + dense Cholesky for small problems, Schur + preconditioned CG for large ones
-    int dense_max_dim = 36000;
+    int dense_max_dim = 192;     // measured crossover on B200: the PCG wins from 3 NP ~ 300 on
     int pcg_max_iters = 20000;
     double pcg_rtol = 1e-10;
     int pcg_variant = 0;               // 0 persistent cooperative kernel, 1 classic multi-kernel loop
