@@ -25,6 +25,7 @@ constexpr int kPcgThreads = BOS_PCG_THREADS;       // one persistent CTA per SM
 #define BOS_ELL_LANES 8
 #endif
 constexpr int kEllLanesL = BOS_ELL_LANES;          // lanes per landmark row in the landmark-major layout
+constexpr int kShareEll = 8;                       // sharers of a (chunk, landmark) kept in the transposed list (the rest through the CSR list)
 
 // Typed view of everything a kernel needs.  One instance per context, built after upload.
 template <typename S>
@@ -90,6 +91,16 @@ struct Dev {
     const int* pc_nbr = nullptr;           // [2][pc_chunks * pc_cp] first two pose-pose neighbours of the row (-1: none)
     const int* pc_nslot = nullptr;         // [2][..] their Hoff slot (bit 31: this pose is the column side)
     const int* pc_ncnt = nullptr;          // [..] number of pose-pose neighbours (more than 2: the rest through pp_ptr)
+    // chunk-local landmark-major layout of the persistent PCG kernel (see pattern.cpp "LC") and the landmark sharing lists
+    const int* lc_gptr = nullptr;          // [pc_chunks + 1]
+    const int* lc_goff = nullptr;          // [groups + 1]
+    const unsigned short* lc_row = nullptr;   // [slots] chunk-local pose row, 0xffff: none
+    const unsigned short* lc_k = nullptr;     // [groups * 32] local landmark of every ELL row (rows sorted by descending edge count), 0xffff: none
+    const int* sh_ptr = nullptr;           // [n_q + 1], q = pc_cl_ptr[c] + k
+    const int* sh_src = nullptr;           // the q' of every chunk that sees the same landmark
+    const int* sh_ell = nullptr;           // [kShareEll][n_q] the first sharers of q once more, transposed, -1 = none
+    const unsigned char* sh_first = nullptr;  // [n_q] 1 in the lowest chunk that sees the landmark
+    int n_q = 0;
     const int* tri_ptr = nullptr;    // [NL+1] bearing edges grouped by landmark (caller order inside a landmark)
     const int* tri_edge = nullptr;   // [Eb] sorted-edge index
     // state
@@ -162,6 +173,9 @@ struct PcgWork {
     // so two scalars per edge (sqrt(omega) Jl) replace the six of the block.
     S* Lw = nullptr;               // [nLs] sqrt(omega) per landmark-major slot; only when the bearing omegas are not all equal
     S* Pw = nullptr;               // [nPs] sqrt(omega) per pose-major slot; only when the bearing omegas are not all equal
+    S* Cw = nullptr;               // the same per slot of the chunk-local landmark-major layout
+    S* qstat = nullptr;            // [5][n_q] per (chunk, landmark), constant during a solve: Hll^-1 (3) and the landmark position (2)
+    S* tpart = nullptr;            // [2][n_q][2] per (chunk, landmark): the chunk's partial t_l, double-buffered by CG iteration parity
     int omega_uniform = 1;         // all bearing omegas equal: the pose-major pass recomputes its factors from the state
     double sqrt_omega = 1.0;       // ... with this scale
     S* hllinv_c = nullptr;         // [n_clm][3] Hll^-1 in compact row order
@@ -188,6 +202,7 @@ struct PcgWork {
     // node), Galerkin operator A_c = P^T S P assembled and inverted once per solve; z = M_chunk^-1 r + P A_c^-1 P^T r
     int c_nc = 0;            // 3 * (pc_chunks * c_nseg + 1)
     int c_h = 32, c_nseg = 1;   // node geometry: every chunk is cut into c_nseg segments of c_h rows (a multiple of 32), nodes at their ends
+    int c_ld = 0;            // leading dimension of cAinv (c_nc rounded up to a multiple of 4: 32-byte aligned rows)
     int c_bw = 0;            // half bandwidth of A_c in scalars (from the pattern); 0 = treat A_c as dense (wide loop closures)
     double* cLc = nullptr;   // [c_nc][c_bw + 1] band of the Cholesky factor by columns, cLr the same by rows, cLdi = 1 / diagonal
     double* cLr = nullptr;
@@ -197,7 +212,7 @@ struct PcgWork {
     bool coarse_valid = false, coarse_stale = false;
     int coarse_age = 0, coarse_refresh = 1, coarse_its_ref = 0;
     double* cA = nullptr;    // [c_nc][c_nc] column-major lower: A_c, then its Cholesky factor
-    double* cAinv = nullptr; // [c_nc][c_nc] A_c^-1 (full, symmetric)
+    double* cAinv = nullptr; // [c_nc][c_ld] A_c^-1 (full, symmetric)
     double* cRc = nullptr;   // [pc_chunks * c_nseg][6] per segment: P^T r restricted to its rows (left node, right node)
     double* cStats = nullptr;  // [8] scratch status of the coarse factorisation
     int sm_count = 148;
@@ -267,6 +282,9 @@ struct HostPattern {
     bool pc_ok = false;
     std::vector<int> pc_row_pose, pc_goff, pc_cl_ptr, pc_cl_row, pc_emap, pc_nbr, pc_nslot, pc_ncnt;
     std::vector<unsigned short> pc_loc;
+    std::vector<int> lc_gptr, lc_goff, lc_emap, sh_ptr, sh_src, sh_ell;   // chunk-local landmark-major layout + landmark sharing lists (pattern.cpp)
+    std::vector<unsigned short> lc_row, lc_k;
+    std::vector<unsigned char> sh_first;
     std::vector<int> tile_ptr, tg_lm, tg_eptr, epose_ptr;
     std::vector<unsigned short> tg_edge;
     std::vector<char> touched;              // [NP + NL]

@@ -263,6 +263,18 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(pl_lm_id, P.pl_lm_id) UP(ell_Loff, P.ell_Loff) UP(ell_Lpose, P.ell_Lpose)
     UP(pc_row_pose, P.pc_row_pose) UP(pc_goff, P.pc_goff) UP(pc_cl_ptr, P.pc_cl_ptr) UP(pc_cl_row, P.pc_cl_row) UP(pc_loc, P.pc_loc)
     UP(pc_emap, P.pc_emap) UP(pc_nbr, P.pc_nbr) UP(pc_nslot, P.pc_nslot) UP(pc_ncnt, P.pc_ncnt)
+    if (P.pc_ok) {
+        std::vector<int> a = P.lc_gptr, b = P.lc_goff, e = P.sh_ptr, f = P.sh_src, se = P.sh_ell;
+        se.resize(se.size() + 1, -1);
+        UP(sh_ell, se)
+        std::vector<unsigned short> r = P.lc_row, lk = P.lc_k;
+        lk.resize(lk.size() + 32, 0xffff);
+        UP(lc_k, lk)
+        std::vector<unsigned char> g = P.sh_first;
+        a.resize(a.size() + 1, 0); b.resize(b.size() + 1, 0); e.resize(e.size() + 1, 0); f.resize(f.size() + 1, 0); r.resize(r.size() + 32, 0xffff); g.resize(g.size() + 1, 0);
+        UP(lc_gptr, a) UP(lc_goff, b) UP(lc_row, r) UP(sh_ptr, e) UP(sh_src, f) UP(sh_first, g)
+        d.n_q = (int)P.pc_cl_row.size();
+    }
     d.n_clm = (int)P.pl_lm_id.size(); d.nLg = (int)P.ell_Loff.size() - 1;
     d.nLs = (long long)P.ell_Lmap.size(); d.nPs = (long long)P.pc_loc.size();
     d.pc_chunks = P.pc_chunks; d.pc_cp = P.pc_cp; d.pc_ok = P.pc_ok ? 1 : 0;
@@ -346,12 +358,18 @@ int ensure_pcg(bos_ctx* c) {
             std::vector<S> lw(P.ell_Lmap.size(), S(0));
             for (size_t k = 0; k < lw.size(); k++) if (P.ell_Lmap[k] >= 0) lw[k] = (S)std::sqrt(om[P.ell_Lmap[k]]);
             w.Lw = c->mem.upload(lw);
-            if (!w.Pw || !w.Lw) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
+            std::vector<S> cw(P.lc_emap.size() + 32, S(0));
+            for (size_t k = 0; k < P.lc_emap.size(); k++) if (P.lc_emap[k] >= 0) cw[k] = (S)std::sqrt(om[P.lc_emap[k]]);
+            w.Cw = c->mem.upload(cw);
+            if (!w.Pw || !w.Lw || !w.Cw) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
         }
     }
     w.hllinv_c = c->mem.get<S>(3 * (size_t)std::max(d.n_clm, 1));
     w.ul4 = c->mem.get<S>(4 * (size_t)std::max(d.n_clm, 1));
     w.z4 = c->mem.get<S>(8 * (size_t)d.NP);
+    w.tpart = c->mem.get<S>(4 * (size_t)std::max(d.n_q, 1));
+    w.qstat = c->mem.get<S>(5 * (size_t)std::max(d.n_q, 1));
+    if (!w.tpart || !w.qstat) return fail(c, BOS_ERR_NOMEM, "pcg workspace allocation failed");
     w.rowS = c->mem.get<S>(24 * (size_t)d.pc_chunks * d.pc_cp);
     w.rS = c->mem.get<S>(3 * (size_t)d.pc_chunks * d.pc_cp);
     w.variant = c->opt.pcg_variant;
@@ -404,7 +422,8 @@ int ensure_pcg(bos_ctx* c) {
             w.coarse_valid = false; w.coarse_stale = false; w.coarse_age = 0;
         }
         w.cA = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
-        w.cAinv = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
+        w.c_ld = (w.c_nc + 3) / 4 * 4;
+        w.cAinv = c->mem.get<double>((size_t)w.c_nc * w.c_ld);
         w.cRc = c->mem.get<double>(6 * (size_t)std::max(d.pc_chunks * w.c_nseg, 1));
         w.cStats = c->mem.get<double>(8);
         w.cLc = c->mem.get<double>((size_t)w.c_nc * (w.c_bw + 1));
@@ -1158,6 +1177,7 @@ int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out) {
     vec(P.off_lo); vec(P.off_hi); vec(P.pp_ptr); vec(P.pp_nbr); vec(P.pp_slot); vec(P.tri_ptr); vec(P.tri_edge);
     vec(P.pl_lm_id); vec(P.b_row); vec(P.ell_Loff); vec(P.ell_Lmap); vec(P.ell_Lpose);
     vec(P.pc_row_pose); vec(P.pc_goff); vec(P.pc_cl_ptr); vec(P.pc_cl_row); vec(P.pc_emap); vec(P.pc_nbr); vec(P.pc_nslot); vec(P.pc_ncnt);
+    vec(P.lc_gptr); vec(P.lc_goff); vec(P.lc_emap); vec(P.sh_ptr); vec(P.sh_src); vec(P.sh_ell); vec(P.lc_row); vec(P.lc_k); vec(P.sh_first);
     vec(P.pc_loc); vec(P.tile_ptr); vec(P.tg_lm); vec(P.tg_eptr); vec(P.epose_ptr); vec(P.tg_edge); vec(P.touched);
     *out = h;
     return BOS_OK;

@@ -307,6 +307,82 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
                     }
                 }
             });
+        // LC: per chunk, the landmark-major view of the chunk's OWN edges: rows = the chunk's distinct landmarks in table order,
+        // ONE lane per row (a landmark has ~10 edges inside a chunk: eight lanes per row would mostly idle), 32 rows per group, column-major
+        // groups like the L layout.  The persistent PCG kernel
+        // forms, per chunk, the partial t_l = sum_k jh_k (Jp_k . z) of every landmark it sees from SHARED MEMORY (its poses' z and
+        // positions live there) instead of gathering 48 bytes per edge from global memory; a landmark seen from several chunks is
+        // summed from the chunks' partials through the sharing lists below.
+        //   lc_gptr[c]   first group of chunk c (groups numbered globally)       lc_goff[g]  column offset of group g
+        //   lc_row[slot] chunk-local pose row (0xffff: padding, or an edge of the fixed pose)   lc_emap[slot] sorted edge (-1: none)
+        //   q = pc_cl_ptr[c] + k numbers every (chunk, local landmark): sh_ptr / sh_src list the q' of ALL chunks (own included) that
+        //   see the same landmark, sh_first[q] = 1 in the lowest such chunk (it accounts for the landmark's part of z . S z)
+        if (P.pc_ok) {
+            constexpr int kLcLanes = 1, RPGc = 32 / kLcLanes;
+            P.lc_gptr.assign(nch + 1, 0);
+            for (int c = 0; c < nch; c++) P.lc_gptr[c + 1] = P.lc_gptr[c] + (P.pc_cl_ptr[c + 1] - P.pc_cl_ptr[c] + RPGc - 1) / RPGc;
+            const int ngl = P.lc_gptr[nch];
+            std::vector<int> gw(ngl > 0 ? ngl : 1, 0);
+            P.lc_k.assign((size_t)(ngl > 0 ? ngl : 1) * 32, (unsigned short)0xffff);
+            std::vector<std::vector<std::pair<unsigned short, int>>> ledges(P.pc_cl_row.size());   // per q: (local row, sorted edge)
+            parallel_ranges(nch, wthreads, [&](int c0, int c1, int) {
+                std::vector<int> lid(n_clm > 0 ? n_clm : 1, -1);
+                for (int c = c0; c < c1; c++) {
+                    const int cl0 = P.pc_cl_ptr[c], cl1 = P.pc_cl_ptr[c + 1];
+                    for (int q = cl0; q < cl1; q++) lid[P.pc_cl_row[q]] = q - cl0;
+                    for (int r = 0; r < cp; r++) {
+                        const int i = P.pc_row_pose[(size_t)c * cp + r];
+                        if (i < 0 || i == fixed) continue;
+                        for (int k = P.epose_ptr[i]; k < P.epose_ptr[i + 1]; k++) ledges[cl0 + lid[P.b_row[k]]].emplace_back((unsigned short)r, k);
+                    }
+                    // ELL rows in descending edge count (uniform groups); lc_k names the local landmark of every row
+                    std::vector<int> ord(cl1 - cl0);
+                    for (int q = cl0; q < cl1; q++) ord[q - cl0] = q;
+                    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return ledges[a].size() > ledges[b].size(); });
+                    for (int j = 0; j < cl1 - cl0; j++) {
+                        P.lc_k[(size_t)P.lc_gptr[c] * 32 + j] = (unsigned short)(ord[j] - cl0);
+                        int& wd = gw[P.lc_gptr[c] + j / RPGc];
+                        wd = std::max(wd, ((int)ledges[ord[j]].size() + kLcLanes - 1) / kLcLanes);
+                    }
+                }
+            });
+            P.lc_goff.assign(ngl + 1, 0);
+            for (int g = 0; g < ngl; g++) P.lc_goff[g + 1] = P.lc_goff[g] + gw[g];
+            P.lc_row.assign((size_t)P.lc_goff[ngl] * 32, (unsigned short)0xffff);
+            P.lc_emap.assign((size_t)P.lc_goff[ngl] * 32, -1);
+            parallel_ranges(nch, wthreads, [&](int c0, int c1, int) {
+                for (int c = c0; c < c1; c++) {
+                    const int cl0 = P.pc_cl_ptr[c], cl1 = P.pc_cl_ptr[c + 1];
+                    for (int j = 0; j < cl1 - cl0; j++) {
+                        const int q = cl0 + P.lc_k[(size_t)P.lc_gptr[c] * 32 + j];
+                        const int g = P.lc_gptr[c] + j / RPGc, lane0 = (j % RPGc) * kLcLanes;
+                        for (size_t idx = 0; idx < ledges[q].size(); idx++) {
+                            const size_t slot = ((size_t)P.lc_goff[g] + idx / kLcLanes) * 32 + lane0 + idx % kLcLanes;
+                            P.lc_row[slot] = ledges[q][idx].first;
+                            P.lc_emap[slot] = ledges[q][idx].second;
+                        }
+                    }
+                }
+            });
+            // sharing lists
+            std::vector<std::vector<int>> seen(n_clm > 0 ? n_clm : 1);
+            for (size_t q = 0; q < P.pc_cl_row.size(); q++) seen[P.pc_cl_row[q]].push_back((int)q);   // ascending q = ascending chunk
+            P.sh_ptr.assign(P.pc_cl_row.size() + 1, 0);
+            for (size_t q = 0; q < P.pc_cl_row.size(); q++) P.sh_ptr[q + 1] = P.sh_ptr[q] + (int)seen[P.pc_cl_row[q]].size();
+            P.sh_src.resize((size_t)P.sh_ptr.back());
+            P.sh_first.assign(P.pc_cl_row.size(), 0);
+            for (size_t q = 0; q < P.pc_cl_row.size(); q++) {
+                const std::vector<int>& v = seen[P.pc_cl_row[q]];
+                std::copy(v.begin(), v.end(), P.sh_src.begin() + P.sh_ptr[q]);
+                P.sh_first[q] = (v[0] == (int)q) ? 1 : 0;
+            }
+            // the first kShareEll sharers of every q once more, transposed ([j][n_q], -1 = none): consecutive threads read consecutive
+            // words and all of a landmark's sources are known after ONE round trip (the CSR above serves the rare longer lists)
+            const size_t nq = P.pc_cl_row.size();
+            P.sh_ell.assign((size_t)kShareEll * (nq > 0 ? nq : 1), -1);
+            for (size_t q = 0; q < nq; q++)
+                for (int j = 0; j < kShareEll && P.sh_ptr[q] + j < P.sh_ptr[q + 1]; j++) P.sh_ell[(size_t)j * nq + q] = P.sh_src[P.sh_ptr[q] + j];
+        }
         // up to two pose-pose neighbours per row inline (filled once the adjacency exists, below)
         P.pc_nbr.assign((size_t)nch * cp * 2, -1);
         P.pc_nslot.assign((size_t)nch * cp * 2, 0);

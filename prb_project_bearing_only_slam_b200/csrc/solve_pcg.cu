@@ -332,6 +332,12 @@ __device__ __forceinline__ void st2cg(float* p, float a, float b) { __stcg(reint
 template <typename S>
 __global__ void __launch_bounds__(256) k_ell_fill(Dev<S> d, PcgWork<S> w) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < d.n_q) {   // per (chunk, landmark): what the persistent kernel needs of the landmark, in q order (coalesced per chunk)
+        const int L = __ldg(d.pl_lm_id + __ldg(d.pc_cl_row + k));
+        const size_t nq = (size_t)d.n_q;
+        w.qstat[k] = w.hllinv[3LL * L]; w.qstat[nq + k] = w.hllinv[3LL * L + 1]; w.qstat[2 * nq + k] = w.hllinv[3LL * L + 2];
+        w.qstat[3 * nq + k] = d.lm[2LL * L]; w.qstat[4 * nq + k] = d.lm[2LL * L + 1];
+    }
     if (k < d.n_clm) {
         const int L = __ldg(d.pl_lm_id + k);
         w.hllinv_c[3LL * k] = w.hllinv[3LL * L]; w.hllinv_c[3LL * k + 1] = w.hllinv[3LL * L + 1]; w.hllinv_c[3LL * k + 2] = w.hllinv[3LL * L + 2];
@@ -493,6 +499,49 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
                 d.delta[3LL * d.NP + 2LL * L + 1] = i01 * r0 + i11 * r1;
             }
         }
+    }
+}
+
+// Chunk-local landmark pass of the operator: the chunk's partial t_l = sum_k jh_k (Jp_k . z_pose(k)) over ITS OWN edges of every landmark it
+// sees, with the poses' z (rows 9-11 of the shared vectors) and positions (pxy) read from shared memory; one 16-byte record per (chunk,
+// landmark) goes to global memory, the chunks that share a landmark sum each other's records after the grid barrier (pattern.cpp "LC").
+// Round 1 gathered pose position + z (two 32-byte sectors per EDGE) from L2 here: 30 of the 100 us of a CG iteration.
+template <typename S>
+__device__ __forceinline__ void pcg_local_landmark_rows(const Dev<S>& d, const PcgWork<S>& w, int c, const S* zs, int cps, int Kp, bool chain,
+                                                        const S* pxy, S* tp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g0 = __ldg(d.lc_gptr + c), g1 = __ldg(d.lc_gptr + c + 1);
+    const int cl0 = __ldg(d.pc_cl_ptr + c), ncl = __ldg(d.pc_cl_ptr + c + 1) - cl0;
+    const S so_u = (S)w.sqrt_omega;
+    const size_t nq = (size_t)d.n_q;
+    for (int g = g0 + warp; g < g1; g += kPcgThreads / 32) {   // one lane per landmark, 32 landmarks per group
+        const int off = __ldg(d.lc_goff + g), W = __ldg(d.lc_goff + g + 1) - off;
+        const int k = (int)__ldg(d.lc_k + (size_t)g * 32 + lane);          // rows are sorted by edge count: the local landmark of this row
+        const bool valid = k != 0xffff && k < ncl;
+        S lx = S(0), ly = S(0);
+        if (valid) { lx = __ldg(w.qstat + 3 * nq + cl0 + k); ly = __ldg(w.qstat + 4 * nq + cl0 + k); }
+        S t0 = S(0), t1 = S(0);
+        const long long s0 = (long long)off * 32 + lane;
+        for (int tb = 0; tb < W; tb += 8) {
+            unsigned rv[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) rv[q] = (tb + q < W) ? (unsigned)__ldg(d.lc_row + s0 + (long long)(tb + q) * 32) : 0xffffu;   // all index loads first
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const unsigned r = rv[q];
+                if (r == 0xffffu) continue;
+                const int xv = chain ? (int)(r & 31u) * Kp + (int)(r >> 5) : (int)r;
+                const S px = pxy[2 * r], py = pxy[2 * r + 1];
+                const S z0 = zs[xv], z1 = zs[cps + xv], z2 = zs[2 * cps + xv];
+                S j0, j1;
+                bearing_jl_world<S>(px, py, lx, ly, j0, j1);
+                const S so = w.omega_uniform ? so_u : __ldg(w.Cw + s0 + (long long)(tb + q) * 32);
+                j0 *= so; j1 *= so;
+                const S sc = (j0 * ly - j1 * lx) * z2 - j0 * z0 - j1 * z1;   // Jp_k . z
+                t0 += j0 * sc; t1 += j1 * sc;
+            }
+        }
+        if (valid) st2cg(tp + 2LL * (cl0 + k), t0, t1);
     }
 }
 
@@ -1062,7 +1111,7 @@ __global__ void __launch_bounds__(kBandCholThreads) k_coarse_band_chol(const dou
 constexpr int kBandMaxPerLane = 5;       // bw <= 159
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_coarse_band_inverse(const double* __restrict__ Lc, const double* __restrict__ Lr, const double* __restrict__ Ldi,
-                                                                    double* __restrict__ Ainv, int nc, int bw) {
+                                                                    double* __restrict__ Ainv, int nc, int bw, int ld) {
     extern __shared__ double vsh[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = bw + 1;
     const int j = blockIdx.x * WARPS + warp;
@@ -1112,14 +1161,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_coarse_band_inverse(const double
         for (int q = 0; q < kBandMaxPerLane; q++) cur[q] = nxt[q];
         dcur = dnxt;
     }
-    for (int i = lane; i < nc; i += 32) Ainv[(size_t)j * nc + i] = v[i];
+    for (int i = lane; i < nc; i += 32) Ainv[(size_t)j * ld + i] = v[i];
 }
 
 // explicit inverse from the Cholesky factor (column-major lower): one warp per column j, L y = e_j by column sweeps, L^T x = y
 // by dot products; the y / x vector lives in shared memory, the next column of L is in registers before the current step ends
 constexpr int kCoarseMaxPerLane = 15;   // ceil(3 * 160 / 32)
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_coarse_inverse(const double* __restrict__ L, double* __restrict__ Ainv, int nc) {
+__global__ void __launch_bounds__(WARPS * 32) k_coarse_inverse(const double* __restrict__ L, double* __restrict__ Ainv, int nc, int ld) {
     extern __shared__ double vsh[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * WARPS + warp;
@@ -1172,7 +1221,51 @@ __global__ void __launch_bounds__(WARPS * 32) k_coarse_inverse(const double* __r
 #pragma unroll
         for (int q = 0; q < kCoarseMaxPerLane; q++) col[q] = nxt[q];
     }
-    for (int i = lane; i < nc; i += 32) Ainv[(size_t)j * nc + i] = v[i];
+    for (int i = lane; i < nc; i += 32) Ainv[(size_t)j * ld + i] = v[i];
+}
+
+// Coarse solve of one chunk, run by warps 2 .. 2 + kCoarseWarps - 1 of the persistent kernel WHILE warps 0-1 do the chunk's chain solve (the two halves
+// of the preconditioner are independent until they are added): wait for the exchange of P^T r, then x_c = A_c^-1 rc at this chunk's nr <= 15
+// node scalars.  A_c^-1 is symmetric, so lane m reads the nr CONTIGUOUS entries A_c^-1[m][row0 .. row0 + nr) of "its" columns m and the two halves
+// of rc[m] straight from global memory: no shared-memory copy of rc (the factors occupy that space while the chain solve runs).
+constexpr int kCoarseWarps = 24;     // 24 warps x 16 row slots = the 384 doubles of the reduction scratch
+constexpr int kCoarseNr = 15;        // 3 * (4 segments + 1) <= 16 row slots
+__device__ __noinline__ void coarse_apply(const double* __restrict__ Ainv, int ld, const double* __restrict__ cRc, int nc, int nsegs_all, int row0, int nr,
+                                          const unsigned* counter, unsigned target, double* part /* [kCoarseWarps][16] */, double* xc) {
+    const int t = threadIdx.x - 64, lane = t & 31, wq = t >> 5;
+    if (t == 0)
+        while (ld_acquire_u32(counter) < target) { }
+    asm volatile("bar.sync 2, %0;" ::"n"(kCoarseWarps * 32) : "memory");
+    // a HALF-WARP per column m: lane j of it reads A_c^-1[m][row0 + j] (the 16 lanes read 128 contiguous bytes) and the two halves of rc[m]
+    // (one address for the whole half-warp); 48 half-warps stride over the columns, four columns in flight
+    const int j = lane & 15, hw = 2 * wq + (lane >> 4);
+    const bool live = j < nr;
+    auto rc_of = [&](int m) {
+        const int nd = m / 3, a = m - 3 * nd;
+        double rv = 0.0;
+        if (nd < nsegs_all) rv += __ldcg(cRc + 6LL * nd + a);
+        if (nd > 0) rv += __ldcg(cRc + 6LL * (nd - 1) + 3 + a);
+        return rv;
+    };
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    constexpr int kStride = 2 * kCoarseWarps;
+    int m = hw;
+    for (; m + 3 * kStride < nc; m += 4 * kStride) {
+        const double r0 = rc_of(m), r1 = rc_of(m + kStride), r2 = rc_of(m + 2 * kStride), r3 = rc_of(m + 3 * kStride);
+        const double v0 = live ? __ldg(Ainv + (size_t)m * ld + row0 + j) : 0.0, v1 = live ? __ldg(Ainv + (size_t)(m + kStride) * ld + row0 + j) : 0.0;
+        const double v2 = live ? __ldg(Ainv + (size_t)(m + 2 * kStride) * ld + row0 + j) : 0.0, v3 = live ? __ldg(Ainv + (size_t)(m + 3 * kStride) * ld + row0 + j) : 0.0;
+        a0 += v0 * r0; a1 += v1 * r1; a2 += v2 * r2; a3 += v3 * r3;
+    }
+    for (; m < nc; m += kStride) a0 += (live ? __ldg(Ainv + (size_t)m * ld + row0 + j) : 0.0) * rc_of(m);
+    double sv = (a0 + a1) + (a2 + a3);
+    sv += __shfl_xor_sync(BOS_FULL_MASK, sv, 16);            // the warp's two half-warps
+    if (lane < 16) part[wq * 16 + lane] = sv;
+    asm volatile("bar.sync 2, %0;" ::"n"(kCoarseWarps * 32) : "memory");
+    if (t < nr) {
+        double tot = 0.0;
+        for (int q = 0; q < kCoarseWarps; q++) tot += part[q * 16 + t];
+        xc[t] = tot;
+    }
 }
 
 // shared-memory plan of the persistent kernel (per CTA = per chunk)
@@ -1186,7 +1279,9 @@ struct PcgSmemPlan {
         fac_floats = 16 * Kp * 32 + 28 * Kp;
         vec_off = 0;                                                   // [12][cps]  p 0-2, s 3-5, r 6-8, yoff 9-11 (chain: then z = M^-1 r)
         rec_off = vec_off + (size_t)12 * cps * sizeof(S);              // [cl_max][4]  u0, u1, lx, ly of the chunk's landmarks
-        loc_off = rec_off + (size_t)4 * (cl_max > 0 ? cl_max : 1) * sizeof(S);   // [slots_max] 16-bit landmark table indices
+        size_t rec_bytes = (size_t)4 * (cl_max > 0 ? cl_max : 1) * sizeof(S);
+        if (rec_bytes < (size_t)2 * cp * sizeof(S)) rec_bytes = (size_t)2 * cp * sizeof(S);   // ... and, before it is staged, the chunk's pose positions [cp][2]
+        loc_off = rec_off + rec_bytes;                                 // [slots_max] 16-bit landmark table indices
         bytes = (loc_off + (size_t)2 * (slots_max > 0 ? slots_max : 1) + 15) / 16 * 16;
         // chain: the FP32 factors are staged over the record / index region while the preconditioner runs (the indices are re-staged after)
         if (chain && rec_off + (size_t)fac_floats * 4 > bytes) bytes = rec_off + (size_t)fac_floats * 4;
@@ -1249,8 +1344,6 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
         posx[h] = posy[h] = S(0);
         if (pose_i[h] >= 0) load_lm<S>(d.pose, 2 * pose_i[h], posx[h], posy[h]);
     }
-    const int myrow0 = (tid < ncl) ? __ldg(d.pc_cl_row + cl0 + tid) : -1;
-    const int myrow1 = (tid + kPcgThreads < ncl) ? __ldg(d.pc_cl_row + cl0 + tid + kPcgThreads) : -1;
     auto stage_loc = [&]() {   // 16-bit landmark table indices of the chunk's edge slots (64-byte aligned runs of 32)
         const uint4* src = reinterpret_cast<const uint4*>(d.pc_loc + (size_t)goff0 * 32);
         uint4* dst = reinterpret_cast<uint4*>(loc_s);
@@ -1311,10 +1404,17 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
         }
         __syncthreads();
         PCG_T(8);
+        const int nr_c = 3 * (nseg + 1);
+        const bool coarse_side = coarse && nr_c <= kCoarseNr;      // the coarse solve runs beside the chain solve, on other warps
+#ifndef BOS_EXP_NO_CHAIN
         if (tid < 64) chain_apply((unsigned)plan.rec_off, ch_r1, ch_w1, ch_r2, ch_w2, cps, Kp, cp / 32);
+        else
+#endif
+        if (coarse_side && tid < 64 + kCoarseWarps * 32)
+            coarse_apply(w.cAinv, w.c_ld, w.cRc, w.c_nc, grid * nseg, 3 * c * nseg, nr_c, w.bar, epoch * gridDim.x, &red6[0][0][0], xc_s);
         __syncthreads();
         PCG_T(9);
-        if (coarse) {
+        if (coarse && !coarse_side) {
             grid_wait(w.bar, gridDim.x, epoch);
             const int nc = w.c_nc, nsegs_all = grid * nseg;      // node n = start of global segment n; the last node only closes a segment
             for (int m = tid; m < nc; m += kPcgThreads) {
@@ -1330,7 +1430,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 const int len = ((nc + parts - 1) / parts + 31) / 32 * 32;
                 if (warp < nr * parts) {
                     const int row = warp % nr, part = warp / nr;
-                    const double* arow = w.cAinv + (size_t)(3 * c * nseg + row) * nc;
+                    const double* arow = w.cAinv + (size_t)(3 * c * nseg + row) * w.c_ld;
                     const int m1 = (part + 1) * len < nc ? (part + 1) * len : nc;
                     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                     int m = part * len + lane;
@@ -1351,14 +1451,23 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             }
             __syncthreads();
         }
+        // the FP32 result sits in rows 9-11, which now become the chunk's z in S (read by the next operator application): registers first
+        float zf[kPcgRows][3];
+#pragma unroll
+        for (int h = 0; h < kPcgRows; h++) {
+            zf[h][0] = zf[h][1] = zf[h][2] = 0.f;
+            if (tid + h * kPcgThreads < cp) { zf[h][0] = zres[vx[h]]; zf[h][1] = zres[cps + vx[h]]; zf[h][2] = zres[2 * cps + vx[h]]; }
+        }
+        __syncthreads();
 #pragma unroll
         for (int h = 0; h < kPcgRows; h++) {
             const int i = pose_i[h];
-            if (i < 0) continue;
             const int r = tid + h * kPcgThreads;
-            const S* v = vsm + vx[h];
+            if (r >= cp) continue;
+            S* v = vsm + vx[h];
+            if (i < 0) { v[9 * cps] = S(0); v[10 * cps] = S(0); v[11 * cps] = S(0); continue; }
             const S r0 = v[6 * cps], r1 = v[7 * cps], r2 = v[8 * cps];
-            S zn0 = (S)zres[vx[h]], zn1 = (S)zres[cps + vx[h]], zn2 = (S)zres[2 * cps + vx[h]];
+            S zn0 = (S)zf[h][0], zn1 = (S)zf[h][1], zn2 = (S)zf[h][2];
             if (coarse && i != d.fixed) {
                 int js; float tf;
                 coarse_seg(r, cp, hseg, js, tf);
@@ -1370,6 +1479,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
                     h5 = __ldg(hp + 5 * nrows);
             st4cg(zdst + 4LL * i, zn0, zn1, zn2);
+            v[9 * cps] = zn0; v[10 * cps] = zn1; v[11 * cps] = zn2;
             gacc += (double)r0 * (double)zn0 + (double)r1 * (double)zn1 + (double)r2 * (double)zn2;
             dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
                      (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
@@ -1385,6 +1495,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             if (r < cp) {
 #pragma unroll
                 for (int k = 0; k < 12; k++) vsm[(size_t)k * cps + vx[h]] = (pose_i[h] >= 0 && k >= 6 && k < 9) ? w.rS[(size_t)(k - 6) * nrows + (size_t)c * cp + r] : S(0);
+                if (!chain && pose_i[h] >= 0) {   // z_0 = M^-1 g of the 3x3 flavour comes from k_pcg_fused_prep; the chain flavour computes its own below
+                    S a0, a1, a2, ap;
+                    ld4cg(w.z4 + 4LL * pose_i[h], a0, a1, a2, ap);
+                    vsm[(size_t)9 * cps + vx[h]] = a0; vsm[(size_t)10 * cps + vx[h]] = a1; vsm[(size_t)11 * cps + vx[h]] = a2;
+                }
             }
         }
     }
@@ -1404,15 +1519,36 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     double gamma_prev = 1.0, alpha_prev = 1.0;
     int it = 0;
     bool bad = false;
+    S* pxy = rec;                                   // [cp][2] the chunk's pose positions, in the record region while the landmark pass runs
     if (gamma_init > 0.0) {
         for (; it < max_iters;) {
             const int cur = it % 3, nxt = (it + 1) % 3, nn = (it + 2) % 3;
             const S* zc = w.z4 + (size_t)(it & 1) * np4;
             S* zn = w.z4 + (size_t)((it + 1) & 1) * np4;
-            // ---- phase L: off-diagonal pose-pose products, t_l / u_l per landmark, delta parts ---------------------------------
-            double dacc = 0.0;
+            S* tp = w.tpart + (size_t)(it & 1) * 2 * (size_t)d.n_q;
+            // ---- phase L: the chunk's partial t_l of every landmark it sees (shared memory only), off-diagonal pose-pose products -----------
 #pragma unroll
             for (int h = 0; h < kPcgRows; h++) {
+                const int r = tid + h * kPcgThreads;
+                if (r < cp) { pxy[2 * r] = posx[h]; pxy[2 * r + 1] = posy[h]; }
+            }
+            __syncthreads();
+            double dacc = 0.0;
+            S yo[kPcgRows][3];       // off-diagonal pose-pose product of the owned rows, in registers until the pose pass
+            // z of a neighbour: a pose of this chunk is in shared memory (rows 9-11), any other comes from the global records
+            auto nbr_z = [&](int nb, S& n0, S& n1, S& n2) {
+                const int rr = nb - c * cp;
+                if (rr >= 0 && rr < cp) {
+                    const int xv = chain ? (rr & 31) * Kp + (rr >> 5) : rr;
+                    n0 = vsm[(size_t)9 * cps + xv]; n1 = vsm[(size_t)10 * cps + xv]; n2 = vsm[(size_t)11 * cps + xv];
+                } else {
+                    S np_;
+                    ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+                }
+            };
+#pragma unroll
+            for (int h = 0; h < kPcgRows; h++) {
+                yo[h][0] = yo[h][1] = yo[h][2] = S(0);
                 const int i = pose_i[h];
                 if (i < 0) continue;
                 const int r = tid + h * kPcgThreads;
@@ -1420,7 +1556,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 const int cnt = __ldg(d.pc_ncnt + R);
                 const int nbv[2] = {__ldg(d.pc_nbr + R), __ldg(d.pc_nbr + nrows + R)};   // independent of cnt: one round trip for all three
                 S y0 = S(0), y1 = S(0), y2 = S(0);
+#ifdef BOS_EXP_NO_OFFDIAG
+                if (false) {
+#else
                 if (cnt > 0) {
+#endif
 #pragma unroll
                     for (int n = 0; n < 2; n++) {
                         const int nb = nbv[n];
@@ -1428,8 +1568,8 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                         const S* o = w.rowS + (size_t)(12 + 6 * n) * nrows + R;
                         const S b0 = __ldg(o), b1 = __ldg(o + nrows), b2 = __ldg(o + 2 * nrows), b3 = __ldg(o + 3 * nrows), b4 = __ldg(o + 4 * nrows),
                                 b5 = __ldg(o + 5 * nrows);
-                        S n0, n1, n2, np_;
-                        ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+                        S n0, n1, n2;
+                        nbr_z(nb, n0, n1, n2);
                         y0 += b0 * n0 + b1 * n1 + b2 * n2;
                         y1 += b1 * n0 + b3 * n1 + b4 * n2;
                         y2 += b2 * n0 + b4 * n1 + b5 * n2;
@@ -1440,8 +1580,8 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                             const int nb = __ldg(d.pp_nbr + q);
                             const int sl = __ldg(d.pp_slot + q);
                             const S* Bo = d.Hoff + 9LL * (sl & 0x7fffffff);
-                            S n0, n1, n2, np_;
-                            ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+                            S n0, n1, n2;
+                            nbr_z(nb, n0, n1, n2);
                             if (sl >= 0) {
                                 y0 += Bo[0] * n0 + Bo[1] * n1 + Bo[2] * n2;
                                 y1 += Bo[3] * n0 + Bo[4] * n1 + Bo[5] * n2;
@@ -1453,63 +1593,65 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                             }
                         }
                     }
-                    S z0, z1, z2, zp;
-                    ld4cg(zc + 4LL * i, z0, z1, z2, zp);
-                    dacc += (double)z0 * (double)y0 + (double)z1 * (double)y1 + (double)z2 * (double)y2;
+                    const S* v = vsm + vx[h];
+                    dacc += (double)v[9 * cps] * (double)y0 + (double)v[10 * cps] * (double)y1 + (double)v[11 * cps] * (double)y2;
                 }
-                vsm[(size_t)9 * cps + vx[h]] = y0; vsm[(size_t)10 * cps + vx[h]] = y1; vsm[(size_t)11 * cps + vx[h]] = y2;
+                yo[h][0] = y0; yo[h][1] = y1; yo[h][2] = y2;
             }
             PCG_T(0);
-            pcg_landmark_rows<S, 0>(d, w, zc, wg, nwarps, dacc);
+#ifndef BOS_EXP_NO_LROWS
+            pcg_local_landmark_rows<S>(d, w, c, vsm + (size_t)9 * cps, cps, Kp, chain, pxy, tp);
+#endif
             PCG_T(1);
-            {
-                const double sdel = block_sum_pcg(dacc, red);
-                if (tid == 0 && sdel != 0.0) atomicAdd(sc + FS_DELTA0 + cur, sdel);
-            }
-            PCG_T(2);
-            grid_barrier(w.bar, gridDim.x, epoch);
+            grid_barrier(w.bar, gridDim.x, epoch);       // every chunk's partials are visible
             PCG_T(3);
-            const double gamma = __ldcg(sc + FS_GAMMA0 + cur), delta = __ldcg(sc + FS_DELTA0 + cur);
-            const double beta = (it == 0) ? 0.0 : gamma / gamma_prev;
-            const double denom = (it == 0) ? delta : delta - beta * gamma / alpha_prev;
-            if (!(denom > 0.0)) { bad = true; break; }
-            const double alpha = gamma / denom;
-            if (blockIdx.x == 0 && tid == 0) { __stcg(sc + FS_GAMMA0 + nn, 0.0); __stcg(sc + FS_DELTA0 + nn, 0.0); }
-            // ---- phase P: stage the chunk's landmark records, then every row is shared memory + arithmetic --------------------
+            // ---- phase P, part 1: stage the chunk's landmark records {u_l, position}: t_l = the partials of all chunks that see the landmark ----
             {
-                if (myrow0 >= 0) { S a, b, e, f; ld4cg(w.ul4 + 4LL * myrow0, a, b, e, f); rec[4 * tid] = a; rec[4 * tid + 1] = b; rec[4 * tid + 2] = e; rec[4 * tid + 3] = f; }
-                if (myrow1 >= 0) {
-                    S a, b, e, f; ld4cg(w.ul4 + 4LL * myrow1, a, b, e, f);
-                    const int k = tid + kPcgThreads;
-                    rec[4 * k] = a; rec[4 * k + 1] = b; rec[4 * k + 2] = e; rec[4 * k + 3] = f;
-                }
-                for (int k = tid + 2 * kPcgThreads; k < ncl; k += kPcgThreads) {
-                    S a, b, e, f; ld4cg(w.ul4 + 4LL * __ldg(d.pc_cl_row + cl0 + k), a, b, e, f);
-                    rec[4 * k] = a; rec[4 * k + 1] = b; rec[4 * k + 2] = e; rec[4 * k + 3] = f;
-                }
-            }
-            const S al = (S)alpha, be = (S)beta;
-            const S so_u = (S)w.sqrt_omega;
-            double gacc = 0.0, dacc2 = 0.0;
-            // loads by pose index first (independent of the staging), then the barrier, then the rows
-            S zz[kPcgRows][3];
+                double tu = 0.0;
+                const size_t nq = (size_t)d.n_q;
+                for (int k = tid; k < ncl; k += kPcgThreads) {
+                    const int q = cl0 + k;
+                    int src[kShareEll];
 #pragma unroll
-            for (int h = 0; h < kPcgRows; h++) {
-                zz[h][0] = zz[h][1] = zz[h][2] = S(0);
-                if (pose_i[h] >= 0) {
-                    S zp;
-                    ld4cg(zc + 4LL * pose_i[h], zz[h][0], zz[h][1], zz[h][2], zp);
+                    for (int j = 0; j < kShareEll; j++) src[j] = __ldg(d.sh_ell + (size_t)j * nq + q);      // one round trip: all sources
+                    const S i00 = __ldg(w.qstat + q), i01 = __ldg(w.qstat + nq + q), i11 = __ldg(w.qstat + 2 * nq + q);
+                    const S lx = __ldg(w.qstat + 3 * nq + q), ly = __ldg(w.qstat + 4 * nq + q);
+                    S t0 = S(0), t1 = S(0);
+#pragma unroll
+                    for (int j = 0; j < kShareEll; j++)
+                        if (src[j] >= 0) {
+                            const typename Vec2T<S>::type v2 = __ldcg(reinterpret_cast<const typename Vec2T<S>::type*>(tp) + src[j]);
+                            t0 += v2.x; t1 += v2.y;
+                        }
+                    if (src[kShareEll - 1] >= 0)   // a landmark seen from more than kShareEll chunks: the rest of its list
+                        for (int qq = __ldg(d.sh_ptr + q) + kShareEll; qq < __ldg(d.sh_ptr + q + 1); qq++) {
+                            const typename Vec2T<S>::type v2 = __ldcg(reinterpret_cast<const typename Vec2T<S>::type*>(tp) + __ldg(d.sh_src + qq));
+                            t0 += v2.x; t1 += v2.y;
+                        }
+                    const S u0 = i00 * t0 + i01 * t1, u1 = i01 * t0 + i11 * t1;
+                    rec[4 * k] = u0; rec[4 * k + 1] = u1; rec[4 * k + 2] = lx; rec[4 * k + 3] = ly;
+                    if (d.sh_first[q]) tu += (double)t0 * (double)u0 + (double)t1 * (double)u1;     // counted once per landmark
                 }
+                // delta = z . S z is complete once every chunk has added its  z . (off-diagonal part) - t . u  (the diagonal part came with z)
+                const double sdel = block_sum_pcg(dacc - tu, red);
+                if (tid == 0) {
+                    if (sdel != 0.0) atomicAdd(sc + FS_DELTA0 + cur, sdel);
+                    __threadfence();
+                }
+                __syncthreads();                           // rec is staged; thread 0's atomic is ordered before the arrive
+                grid_arrive(w.bar, epoch);
             }
-            __syncthreads();
             PCG_T(7);
+            // ---- part 2: w = S z for the owned rows while the delta exchange is in flight -------------------------------------------
+            const S so_u = (S)w.sqrt_omega;
+            S wv[kPcgRows][3];
 #pragma unroll
             for (int h = 0; h < kPcgRows; h++) {
                 const int i = pose_i[h];
                 const int r = tid + h * kPcgThreads;
+                wv[h][0] = wv[h][1] = wv[h][2] = S(0);
                 if (r >= cp) continue;                       // warp-uniform: cp is a multiple of 32
                 const int W = swid[h];
-                const S z0 = zz[h][0], z1 = zz[h][1], z2 = zz[h][2];
                 S w0 = S(0), w1 = S(0), w2 = S(0);
                 const bool active = i >= 0 && i != d.fixed;
                 for (int t = 0; t < W; t++) {
@@ -1527,12 +1669,32 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 const S* hp = w.rowS + (size_t)c * cp + r;
                 const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
                         h5 = __ldg(hp + 5 * nrows);
+                const S* v = vsm + vx[h];
+                const S z0 = v[9 * cps], z1 = v[10 * cps], z2 = v[11 * cps];
+                wv[h][0] = w0 + h0 * z0 + h1 * z1 + h2 * z2 + yo[h][0];
+                wv[h][1] = w1 + h1 * z0 + h3 * z1 + h4 * z2 + yo[h][1];
+                wv[h][2] = w2 + h2 * z0 + h4 * z1 + h5 * z2 + yo[h][2];
+            }
+            PCG_T(4);
+            grid_wait(w.bar, gridDim.x, epoch);
+            const double gamma = __ldcg(sc + FS_GAMMA0 + cur), delta = __ldcg(sc + FS_DELTA0 + cur);
+            const double beta = (it == 0) ? 0.0 : gamma / gamma_prev;
+            const double denom = (it == 0) ? delta : delta - beta * gamma / alpha_prev;
+            if (!(denom > 0.0)) { bad = true; break; }
+            const double alpha = gamma / denom;
+            if (blockIdx.x == 0 && tid == 0) { __stcg(sc + FS_GAMMA0 + nn, 0.0); __stcg(sc + FS_DELTA0 + nn, 0.0); }
+            const S al = (S)alpha, be = (S)beta;
+            double gacc = 0.0, dacc2 = 0.0;
+            // ---- part 3: the recurrences of the owned rows ---------------------------------------------------------------------------
+#pragma unroll
+            for (int h = 0; h < kPcgRows; h++) {
+                const int i = pose_i[h];
+                const int r = tid + h * kPcgThreads;
+                if (r >= cp || i < 0) continue;
                 S* v = vsm + vx[h];
-                w0 += h0 * z0 + h1 * z1 + h2 * z2 + v[9 * cps];
-                w1 += h1 * z0 + h3 * z1 + h4 * z2 + v[10 * cps];
-                w2 += h2 * z0 + h4 * z1 + h5 * z2 + v[11 * cps];
+                const S z0 = v[9 * cps], z1 = v[10 * cps], z2 = v[11 * cps];
                 const S p0 = z0 + be * v[0], p1 = z1 + be * v[cps], p2 = z2 + be * v[2 * cps];
-                const S s0_ = w0 + be * v[3 * cps], s1 = w1 + be * v[4 * cps], s2 = w2 + be * v[5 * cps];
+                const S s0_ = wv[h][0] + be * v[3 * cps], s1 = wv[h][1] + be * v[4 * cps], s2 = wv[h][2] + be * v[5 * cps];
                 v[0] = p0; v[cps] = p1; v[2 * cps] = p2;
                 v[3 * cps] = s0_; v[4 * cps] = s1; v[5 * cps] = s2;
                 const S r0 = v[6 * cps] - al * s0_, r1 = v[7 * cps] - al * s1, r2 = v[8 * cps] - al * s2;
@@ -1540,16 +1702,19 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 S* xg = w.xS + (size_t)c * cp + r;
                 xg[0] += al * p0; xg[nrows] += al * p1; xg[2 * nrows] += al * p2;
                 if (chain) continue;                         // z = M^-1 r needs the whole chunk's residual: below
+                const S* hp = w.rowS + (size_t)c * cp + r;
+                const S h0 = __ldg(hp), h1 = __ldg(hp + nrows), h2 = __ldg(hp + 2 * nrows), h3 = __ldg(hp + 3 * nrows), h4 = __ldg(hp + 4 * nrows),
+                        h5 = __ldg(hp + 5 * nrows);
                 const S* mi = hp + 6 * nrows;
                 const S m0 = __ldg(mi), m1 = __ldg(mi + nrows), m2 = __ldg(mi + 2 * nrows), m3 = __ldg(mi + 3 * nrows), m4 = __ldg(mi + 4 * nrows),
                         m5 = __ldg(mi + 5 * nrows);
                 const S zn0 = m0 * r0 + m1 * r1 + m2 * r2, zn1 = m1 * r0 + m3 * r1 + m4 * r2, zn2 = m2 * r0 + m4 * r1 + m5 * r2;
                 st4cg(zn + 4LL * i, zn0, zn1, zn2);
+                v[9 * cps] = zn0; v[10 * cps] = zn1; v[11 * cps] = zn2;      // the chunk's copy for the next operator application
                 gacc += (double)r0 * (double)zn0 + (double)r1 * (double)zn1 + (double)r2 * (double)zn2;
                 dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
                          (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
             }
-            PCG_T(4);
             if (chain) precond_chain(zn, gacc, dacc2);
             {
                 const double sg = block_sum_pcg(gacc, red);
@@ -1619,7 +1784,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     cudaMemsetAsync(w.bar, 0, 4 * sizeof(unsigned), st);
     cudaMemsetAsync(w.xS, 0, 3 * (size_t)nrows * sizeof(S), st);
     if (d.NL > 0) { k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++; }
-    if (d.n_clm > 0) { k_ell_fill<S><<<(d.n_clm + 255) / 256, 256, 0, st>>>(d, w); nl++; }
+    if (d.n_clm > 0) { k_ell_fill<S><<<(std::max(d.n_clm, d.n_q) + 255) / 256, 256, 0, st>>>(d, w); nl++; }
     // FP32 flavour: the Schur diagonal blocks are differences of terms ~1e8 times larger than their small eigenvalues (world-frame
     // lever arms); in float they are not reliably positive definite, and a block-tridiagonal factorisation built on them breaks
     // down at synth-2M.  The 3x3 block-Jacobi preconditioner (which only inverts them) is what the FP32 path runs.
@@ -1650,12 +1815,12 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
             constexpr int IW = 4;
             const size_t ism = sizeof(double) * IW * (size_t)nc;
             if (!ensure_dyn_smem((const void*)k_coarse_band_inverse<IW>, ism)) return -1;
-            k_coarse_band_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cLc, w.cLr, w.cLdi, w.cAinv, nc, w.c_bw); nl++;
+            k_coarse_band_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cLc, w.cLr, w.cLdi, w.cAinv, nc, w.c_bw, w.c_ld); nl++;
         } else {            // wide coupling (loop closures far along the chain): dense Cholesky + dense triangular inverse, nc <= 480
             nl += dense_cholesky_lower<double>(w.cA, nc, w.cStats, st);
             constexpr int IW = 4;
             const size_t ism = sizeof(double) * IW * (size_t)nc;
-            k_coarse_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cA, w.cAinv, nc); nl++;
+            k_coarse_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cA, w.cAinv, nc, w.c_ld); nl++;
         }
         w.coarse_valid = true; w.coarse_age = 0; w.coarse_stale = false;
     }
