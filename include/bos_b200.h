@@ -113,6 +113,13 @@ BOS_API const char* bos_last_error(const bos_ctx* ctx);
 
 /* Solver::set_kernel_threshold / set_damping_factor (slam/solver.cpp:20-25). */
 BOS_API int bos_set_kernel_threshold(bos_ctx* ctx, double kt);
+/* Robust kernel flavour (opt-in; the default is the reference's).  BOS_ROBUST_REFERENCE: an edge whose chi2 = e^T Omega e exceeds
+ * kernel_threshold has its ERROR scaled by w = sqrt(kt / chi2), J and Omega untouched (slam/solver.cpp:37-41, 54-58).  BOS_ROBUST_IRLS: the
+ * standard iteratively re-weighted form of the same (Huber-type) weight: Omega <- w Omega, so b is what the reference computes and
+ * H += w J^T Omega J instead of J^T Omega J.  IRLS solves run on the stored blocks (dense Cholesky or the classic PCG loop). */
+#define BOS_ROBUST_REFERENCE 0
+#define BOS_ROBUST_IRLS 1
+BOS_API int bos_set_robust_mode(bos_ctx* ctx, int mode);
 BOS_API int bos_set_damping_factor(bos_ctx* ctx, double df);
 
 /* The edge vectors + construct_the_permutation (slam/solver.cpp:5-18, 99-125).  Edges arrive with

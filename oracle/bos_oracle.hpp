@@ -359,6 +359,9 @@ public:
 
     // ---------------- Solver (slam/solver.cpp:5-18) --------------------------------------
     T kernel_threshold = 1, damping_factor = T(0.01f);
+    // opt-in beyond the reference: IRLS flavour of the same threshold kernel -- the weight w = sqrt(kt / chi2) scales Omega
+    // (H and b) instead of the error alone (b is identical, H += w J^T Omega J)
+    bool irls = false;
     int N = 0, fixed_stix = 0;
     // resolved indices (id -> stix once; the reference does 2-3 map::at per edge per iteration)
     std::vector<int> b_pose, b_lm, o_src, o_dst;
@@ -535,19 +538,25 @@ public:
             const T om = bearings[e].omega;
             T chi = err * om * err;
             stats.chi2_bearing += (double)chi;
-            if (chi > kernel_threshold) { err *= std::sqrt(kernel_threshold / chi); stats.over_bearing++; }
+            T om_h = om;     // the omega the H terms see
+            if (chi > kernel_threshold) {
+                const T wgt = std::sqrt(kernel_threshold / chi);
+                err *= wgt;                       // slam/solver.cpp:37-41 (b sees w e either way)
+                if (irls) om_h = om * wgt;
+                stats.over_bearing++;
+            }
             T* Hp = &Hdiag_p[(size_t)p * 9];
             T* Hl = &Hdiag_l[(size_t)l * 4];
             T* Hpl = &Hoff[(size_t)b_slot[e] * 9];
             for (int a = 0; a < 3; a++) {
-                T ja = J[a] * om;
-                for (int c = 0; c < 3; c++) Hp[a * 3 + c] += ja * J[c];
-                for (int c = 0; c < 2; c++) Hpl[a * 2 + c] += ja * J[3 + c];
+                T ja = J[a] * om, jh = J[a] * om_h;
+                for (int c = 0; c < 3; c++) Hp[a * 3 + c] += jh * J[c];
+                for (int c = 0; c < 2; c++) Hpl[a * 2 + c] += jh * J[3 + c];
                 bvec[3 * p + a] += ja * err;
             }
             for (int a = 0; a < 2; a++) {
-                T ja = J[3 + a] * om;
-                for (int c = 0; c < 2; c++) Hl[a * 2 + c] += ja * J[3 + c];
+                T ja = J[3 + a] * om, jh = J[3 + a] * om_h;
+                for (int c = 0; c < 2; c++) Hl[a * 2 + c] += jh * J[3 + c];
                 bvec[3 * np + 2 * l + a] += ja * err;
             }
         }
@@ -562,9 +571,11 @@ public:
             for (int k = 0; k < 3; k++) eo[k] = err[0] * Om[0 * 3 + k] + err[1] * Om[1 * 3 + k] + err[2] * Om[2 * 3 + k];
             T chi = eo[0] * err[0] + eo[1] * err[1] + eo[2] * err[2];
             stats.chi2_odometry += (double)chi;
+            T wh = 1;        // weight of the H terms
             if (chi > kernel_threshold) {
                 T sc = std::sqrt(kernel_threshold / chi);
                 for (int i = 0; i < 3; i++) err[i] *= sc;
+                if (irls) wh = sc;
                 stats.over_odometry++;
             }
             // JtO = J^T * Omega (6x3)
@@ -572,7 +583,7 @@ public:
             for (int a = 0; a < 6; a++)
                 for (int k = 0; k < 3; k++)
                     JtO[a][k] = J[0 * 6 + a] * Om[0 * 3 + k] + J[1 * 6 + a] * Om[1 * 3 + k] + J[2 * 6 + a] * Om[2 * 3 + k];
-            auto HJ = [&](int a, int c) { return JtO[a][0] * J[0 * 6 + c] + JtO[a][1] * J[1 * 6 + c] + JtO[a][2] * J[2 * 6 + c]; };
+            auto HJ = [&](int a, int c) { return wh * (JtO[a][0] * J[0 * 6 + c] + JtO[a][1] * J[1 * 6 + c] + JtO[a][2] * J[2 * 6 + c]); };
             T* Hs = &Hdiag_p[(size_t)s * 9];
             T* Hd = &Hdiag_p[(size_t)d * 9];
             T* Ho = &Hoff[(size_t)o_slot[e] * 9];

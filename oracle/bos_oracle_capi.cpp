@@ -31,6 +31,7 @@ struct IOracle {
     virtual int get_single_obs(int* ids, int cap) = 0;
     virtual int solver_init(int fixed_id) = 0;
     virtual void set_params(double kt, double damp) = 0;
+    virtual void set_irls(int on) = 0;
     virtual void get_edge_stix(int* bp, int* bl, int* os, int* od) = 0;
     virtual void linearize() = 0;
     virtual int n_off() = 0;
@@ -136,6 +137,7 @@ struct Impl : IOracle {
         return 0;
     }
     void set_params(double kt, double damp) override { o.kernel_threshold = (T)kt; o.damping_factor = (T)damp; }
+    void set_irls(int on) override { o.irls = on != 0; }
     void get_edge_stix(int* bp, int* bl, int* os, int* od) override {
         if (bp) std::copy(o.b_pose.begin(), o.b_pose.end(), bp);
         if (bl) std::copy(o.b_lm.begin(), o.b_lm.end(), bl);
@@ -291,6 +293,7 @@ void orc_get_edges(void* h, int* bp, int* bl, double* bz, double* bom, int* os, 
 int orc_get_single_obs(void* h, int* ids, int cap) { return H(h)->get_single_obs(ids, cap); }
 int orc_solver_init(void* h, int fixed_id) { return H(h)->solver_init(fixed_id); }
 void orc_set_params(void* h, double kt, double damp) { H(h)->set_params(kt, damp); }
+void orc_set_irls(void* h, int on) { H(h)->set_irls(on); }
 void orc_get_edge_stix(void* h, int* bp, int* bl, int* os, int* od) { H(h)->get_edge_stix(bp, bl, os, od); }
 void orc_linearize(void* h) { H(h)->linearize(); }
 int orc_n_off(void* h) { return H(h)->n_off(); }

@@ -47,6 +47,7 @@ def lib():
         L.orc_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orc_set_irls.argtypes = [C.c_void_p, C.c_int]
         L.orc_solve_sparse.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.orc_time_linearize_literal.restype = C.c_double
         L.orc_time_linearize_literal.argtypes = [C.c_void_p, C.c_int]
@@ -151,6 +152,10 @@ class Oracle:
 
     def set_params(self, kernel_threshold=1.0, damping=0.01):
         self.L.orc_set_params(self.h, float(kernel_threshold), float(damping))
+
+    def set_irls(self, on=True):
+        """opt-in IRLS flavour of the threshold kernel (the weight scales Omega; not in the reference)."""
+        self.L.orc_set_irls(self.h, 1 if on else 0)
 
     def edge_stix(self):
         c = self.counts()

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("BOS_LIB_PATH") or os.path.join(_HERE, "libbos_b200.so
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_NOMEM = range(6)
 PRECISION_F64, PRECISION_F32 = 0, 1
 SOLVER_AUTO, SOLVER_DENSE_CHOLESKY, SOLVER_PCG = 0, 1, 2
+ROBUST_REFERENCE, ROBUST_IRLS = 0, 1
 NCCL_UID_BYTES = 128
 
 
@@ -42,7 +43,7 @@ class PatternInfo(C.Structure):
 
 # every symbol include/bos_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "bos_default_options", "bos_version", "bos_create", "bos_destroy", "bos_last_error", "bos_set_kernel_threshold",
+    "bos_default_options", "bos_version", "bos_create", "bos_destroy", "bos_last_error", "bos_set_kernel_threshold", "bos_set_robust_mode",
     "bos_set_damping_factor", "bos_upload_problem", "bos_set_state", "bos_get_state", "bos_linearize", "bos_solve",
     "bos_update", "bos_step", "bos_step_host", "bos_get_stats", "bos_triangulate", "bos_pattern_info_get",
     "bos_download_pattern", "bos_download_blocks", "bos_download_csc", "bos_download_delta", "bos_upload_delta",
@@ -71,6 +72,7 @@ def lib():
         L.bos_last_error.argtypes = [vp]
         L.bos_last_error.restype = C.c_char_p
         L.bos_set_kernel_threshold.argtypes = [vp, dbl]
+        L.bos_set_robust_mode.argtypes = [vp, C.c_int]
         L.bos_set_damping_factor.argtypes = [vp, dbl]
         L.bos_upload_problem.argtypes = [vp, i32, i32, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp]
         L.bos_set_state.argtypes = [vp, vp, vp]
@@ -166,6 +168,10 @@ class Context:
 
     def set_kernel_threshold(self, kt):
         self._ck(self.L.bos_set_kernel_threshold(self.h, float(kt)))
+
+    def set_robust_mode(self, mode):
+        """0 = the reference's robust kernel (error scaled), 1 = IRLS (Omega scaled)."""
+        self._ck(self.L.bos_set_robust_mode(self.h, int(mode)))
 
     def set_damping_factor(self, df):
         self._ck(self.L.bos_set_damping_factor(self.h, float(df)))

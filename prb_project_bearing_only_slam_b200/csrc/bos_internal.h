@@ -32,6 +32,7 @@ template <typename S>
 struct Dev {
     int NP = 0, NL = 0, fixed = 0, Eb = 0, Eo = 0, N = 0;
     int n_hpl = 0, n_off = 0;
+    int irls = 0;                 // robust kernel flavour: 0 = the reference's (scales the error only), 1 = IRLS (the weight scales Omega: H too)
     // bearing edges, sorted by (pose, landmark); SoA
     const int* b_pose = nullptr;
     const int* b_lm = nullptr;

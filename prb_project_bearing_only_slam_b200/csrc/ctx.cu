@@ -108,6 +108,7 @@ struct bos_ctx {
     int solver_used = 0;
     // multi-GPU
     int rank = 0, nranks = 1, reduce_mode = 0;
+    int robust_mode = 0;          // 0 = reference robust kernel, 1 = IRLS (bos_set_robust_mode)
     nccl_comm_t comm = nullptr;
     ShardRange shard;
     std::vector<int> own_p0;              // [nranks + 1] first pose owned by each rank's tiles (a pose belongs to the tile its run starts in)
@@ -506,6 +507,7 @@ int linearize_impl(bos_ctx* c) {
     const bool owned = multi && c->reduce_mode == 3 && c->P.slots_identity;   // every rank writes every pose-pose block itself
     const bool zero_hoff = (multi && !owned) || c->P.has_shared_off;
     const double damp_here = (c->rank == 0) ? c->opt.damping : 0.0;
+    d.irls = c->robust_mode;
     c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, multi && !owned, c->rank, owned);
     CUDA_OK(c, cudaGetLastError());
     c->linearized = true; c->solved = false;
@@ -533,6 +535,9 @@ int solve_impl(bos_ctx* c) {
         int iters = 0;
         double rtol = c->opt.pcg_rtol;
         if (sizeof(S) == 4 && rtol < 1e-6) rtol = 1e-6;
+        // IRLS re-weights every edge every iteration; the fused kernel re-derives its per-edge factors from the state and the STATIC omegas, so
+        // IRLS solves take the classic loop, which applies the stored pose-landmark blocks
+        pwork<S>(c).variant = c->robust_mode ? 1 : c->opt.pcg_variant;
         rc = launch_pcg_solve<S>(d, pwork<S>(c), c->opt.pcg_max_iters, rtol, c->stream, &iters, &nl);
         if (rc < 0) return fail(c, BOS_ERR_CUDA, std::string("pcg: ") + cudaGetErrorString(cudaGetLastError()));
         c->stats.pcg_iterations = iters;
@@ -801,6 +806,13 @@ const char* bos_last_error(const bos_ctx* c) { return c ? c->err.c_str() : "null
 int bos_set_kernel_threshold(bos_ctx* c, double kt) {
     if (!c) return BOS_ERR_INVALID;
     c->opt.kernel_threshold = kt;
+    return BOS_OK;
+}
+int bos_set_robust_mode(bos_ctx* c, int mode) {
+    if (!c || (mode != BOS_ROBUST_REFERENCE && mode != BOS_ROBUST_IRLS)) return BOS_ERR_INVALID;
+    if (mode == BOS_ROBUST_IRLS && c->nranks > 1 && c->reduce_mode >= 2)
+        return fail(c, BOS_ERR_STATE, "IRLS needs the stored pose-landmark blocks: use reduce_mode 0 or 1 with several ranks");
+    c->robust_mode = mode;
     return BOS_OK;
 }
 int bos_set_damping_factor(bos_ctx* c, double df) {

@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(128) k_linearize_odometry(Dev<S> d, int o_begi
         if (over) scale = sqrt(kernel_threshold / chi);   // scales the ERROR only (slam/solver.cpp:54-58)
         S M[6], v[3];
         odometry_normal_terms<S>(Xs.c, Xs.s, u0, u1, om, err, M, v, scale);
+        if (d.irls && over) {                             // opt-in IRLS: the weight belongs to Omega, so it scales J^T Omega J as well
+#pragma unroll
+            for (int k = 0; k < 6; k++) M[k] *= scale;
+        }
         if (e >= s_begin && e < s_end) { chi_acc = (double)chi; over_acc = over ? 1 : 0; }   // statistics: this rank's share of the edges only
         const bool fs = (s == d.fixed), ft = (t == d.fixed);      // gauge: the fixed pose's Jacobian block is zero
         // M and v go to a per-edge scratch (SoA, coalesced); the pose threads of the bearing kernel add them to the two diagonal blocks
@@ -251,8 +255,13 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
                 // threshold robust kernel: scales the ERROR only (slam/solver.cpp:37-41)
                 const S chi = err * om * err;
                 chi_acc += (double)chi;
-                if (chi > kernel_threshold) { err *= sqrt(kernel_threshold / chi); over_acc++; }
                 so = (om == S(1)) ? S(1) : sqrt(om);
+                if (chi > kernel_threshold) {
+                    const S wgt = sqrt(kernel_threshold / chi);
+                    over_acc++;
+                    if (d.irls) so *= sqrt(wgt);   // opt-in IRLS: sqrt(w omega) on J and on e (b is the same, H is scaled by w)
+                    else err *= wgt;
+                }
             }
             const S j0 = so * J[3], j1 = so * J[4], jt = so * J[2];
             tv[0][j] = j0; tv[1][j] = j1; tv[2][j] = jt; tv[3][j] = so * err;

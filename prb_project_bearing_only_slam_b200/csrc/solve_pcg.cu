@@ -1338,6 +1338,20 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             swid[h] = __ldg(d.pc_goff + (size_t)c * gpc + r / 32 + 1) - o;
         }
     }
+    bool out_nb[kPcgRows];              // the row has a pose-pose neighbour in another chunk (pass B of the off-diagonal product)
+#pragma unroll
+    for (int h = 0; h < kPcgRows; h++) {
+        out_nb[h] = false;
+        if (pose_i[h] < 0) continue;
+        const size_t R = (size_t)c * cp + tid + h * kPcgThreads;
+        const int cnt = __ldg(d.pc_ncnt + R);
+#pragma unroll
+        for (int n = 0; n < 2; n++) {
+            const int nb = __ldg(d.pc_nbr + (size_t)n * ((size_t)d.pc_chunks * cp) + R);
+            if (nb >= 0 && (nb < c * cp || nb >= (c + 1) * cp)) out_nb[h] = true;
+        }
+        if (cnt > 2) out_nb[h] = true;
+    }
     S posx[kPcgRows], posy[kPcgRows];   // the owned poses' translations: all the pose pass needs of the state, constant during the solve
 #pragma unroll
     for (int h = 0; h < kPcgRows; h++) {
@@ -1535,67 +1549,75 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             __syncthreads();
             double dacc = 0.0;
             S yo[kPcgRows][3];       // off-diagonal pose-pose product of the owned rows, in registers until the pose pass
-            // z of a neighbour: a pose of this chunk is in shared memory (rows 9-11), any other comes from the global records
-            auto nbr_z = [&](int nb, S& n0, S& n1, S& n2) {
-                const int rr = nb - c * cp;
-                if (rr >= 0 && rr < cp) {
-                    const int xv = chain ? (rr & 31) * Kp + (rr >> 5) : rr;
-                    n0 = vsm[(size_t)9 * cps + xv]; n1 = vsm[(size_t)10 * cps + xv]; n2 = vsm[(size_t)11 * cps + xv];
-                } else {
-                    S np_;
-                    ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+            // Pass A (before the grid barrier): neighbours inside this chunk, whose z is in shared memory (rows 9-11).  Neighbours in other chunks
+            // (the two ends of the chunk, loop closures) follow in pass B, after the barrier that makes every chunk's z visible: the end-of-iteration
+            // barrier of round 1 is gone.  The row's static data (neighbour ids, both inline blocks) is fetched in ONE batch of independent loads:
+            // rows without a neighbour hold zero blocks.
+            auto off_row = [&](int h, bool outside, S& y0, S& y1, S& y2) {
+                const int i = pose_i[h];
+                const int r = tid + h * kPcgThreads;
+                const size_t R = (size_t)c * cp + r;
+                const int cnt = __ldg(d.pc_ncnt + R);
+                const int nbv[2] = {__ldg(d.pc_nbr + R), __ldg(d.pc_nbr + nrows + R)};
+                S bb[2][6];
+#pragma unroll
+                for (int n = 0; n < 2; n++) {
+                    const S* o = w.rowS + (size_t)(12 + 6 * n) * nrows + R;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) bb[n][k] = __ldg(o + (size_t)k * nrows);
                 }
+                auto nbr_z = [&](int nb, S& n0, S& n1, S& n2) -> bool {      // false: the neighbour belongs to the other pass
+                    const int rr = nb - c * cp;
+                    const bool inside = rr >= 0 && rr < cp;
+                    if (inside == outside) return false;
+                    if (inside) {
+                        const int xv = chain ? (rr & 31) * Kp + (rr >> 5) : rr;
+                        n0 = vsm[(size_t)9 * cps + xv]; n1 = vsm[(size_t)10 * cps + xv]; n2 = vsm[(size_t)11 * cps + xv];
+                    } else {
+                        S np_;
+                        ld4cg(zc + 4LL * nb, n0, n1, n2, np_);
+                    }
+                    return true;
+                };
+#ifndef BOS_EXP_NO_OFFDIAG
+#pragma unroll
+                for (int n = 0; n < 2; n++) {
+                    const int nb = nbv[n];
+                    S n0, n1, n2;
+                    if (nb < 0 || !nbr_z(nb, n0, n1, n2)) continue;
+                    y0 += bb[n][0] * n0 + bb[n][1] * n1 + bb[n][2] * n2;
+                    y1 += bb[n][1] * n0 + bb[n][3] * n1 + bb[n][4] * n2;
+                    y2 += bb[n][2] * n0 + bb[n][4] * n1 + bb[n][5] * n2;
+                }
+                if (cnt > 2) {   // loop closures beyond the two inline neighbours: generic adjacency
+                    const int q0 = __ldg(d.pp_ptr + i);
+                    for (int q = q0 + 2; q < q0 + cnt; q++) {
+                        const int nb = __ldg(d.pp_nbr + q);
+                        const int sl = __ldg(d.pp_slot + q);
+                        const S* Bo = d.Hoff + 9LL * (sl & 0x7fffffff);
+                        S n0, n1, n2;
+                        if (!nbr_z(nb, n0, n1, n2)) continue;
+                        if (sl >= 0) {
+                            y0 += Bo[0] * n0 + Bo[1] * n1 + Bo[2] * n2;
+                            y1 += Bo[3] * n0 + Bo[4] * n1 + Bo[5] * n2;
+                            y2 += Bo[6] * n0 + Bo[7] * n1 + Bo[8] * n2;
+                        } else {
+                            y0 += Bo[0] * n0 + Bo[3] * n1 + Bo[6] * n2;
+                            y1 += Bo[1] * n0 + Bo[4] * n1 + Bo[7] * n2;
+                            y2 += Bo[2] * n0 + Bo[5] * n1 + Bo[8] * n2;
+                        }
+                    }
+                }
+#endif
             };
 #pragma unroll
             for (int h = 0; h < kPcgRows; h++) {
                 yo[h][0] = yo[h][1] = yo[h][2] = S(0);
-                const int i = pose_i[h];
-                if (i < 0) continue;
-                const int r = tid + h * kPcgThreads;
-                const size_t R = (size_t)c * cp + r;
-                const int cnt = __ldg(d.pc_ncnt + R);
-                const int nbv[2] = {__ldg(d.pc_nbr + R), __ldg(d.pc_nbr + nrows + R)};   // independent of cnt: one round trip for all three
+                if (pose_i[h] < 0) continue;
                 S y0 = S(0), y1 = S(0), y2 = S(0);
-#ifdef BOS_EXP_NO_OFFDIAG
-                if (false) {
-#else
-                if (cnt > 0) {
-#endif
-#pragma unroll
-                    for (int n = 0; n < 2; n++) {
-                        const int nb = nbv[n];
-                        if (nb < 0) continue;
-                        const S* o = w.rowS + (size_t)(12 + 6 * n) * nrows + R;
-                        const S b0 = __ldg(o), b1 = __ldg(o + nrows), b2 = __ldg(o + 2 * nrows), b3 = __ldg(o + 3 * nrows), b4 = __ldg(o + 4 * nrows),
-                                b5 = __ldg(o + 5 * nrows);
-                        S n0, n1, n2;
-                        nbr_z(nb, n0, n1, n2);
-                        y0 += b0 * n0 + b1 * n1 + b2 * n2;
-                        y1 += b1 * n0 + b3 * n1 + b4 * n2;
-                        y2 += b2 * n0 + b4 * n1 + b5 * n2;
-                    }
-                    if (cnt > 2) {   // loop closures beyond the two inline neighbours: generic adjacency
-                        const int q0 = __ldg(d.pp_ptr + i);
-                        for (int q = q0 + 2; q < q0 + cnt; q++) {
-                            const int nb = __ldg(d.pp_nbr + q);
-                            const int sl = __ldg(d.pp_slot + q);
-                            const S* Bo = d.Hoff + 9LL * (sl & 0x7fffffff);
-                            S n0, n1, n2;
-                            nbr_z(nb, n0, n1, n2);
-                            if (sl >= 0) {
-                                y0 += Bo[0] * n0 + Bo[1] * n1 + Bo[2] * n2;
-                                y1 += Bo[3] * n0 + Bo[4] * n1 + Bo[5] * n2;
-                                y2 += Bo[6] * n0 + Bo[7] * n1 + Bo[8] * n2;
-                            } else {
-                                y0 += Bo[0] * n0 + Bo[3] * n1 + Bo[6] * n2;
-                                y1 += Bo[1] * n0 + Bo[4] * n1 + Bo[7] * n2;
-                                y2 += Bo[2] * n0 + Bo[5] * n1 + Bo[8] * n2;
-                            }
-                        }
-                    }
-                    const S* v = vsm + vx[h];
-                    dacc += (double)v[9 * cps] * (double)y0 + (double)v[10 * cps] * (double)y1 + (double)v[11 * cps] * (double)y2;
-                }
+                off_row(h, false, y0, y1, y2);
+                const S* v = vsm + vx[h];
+                dacc += (double)v[9 * cps] * (double)y0 + (double)v[10 * cps] * (double)y1 + (double)v[11 * cps] * (double)y2;
                 yo[h][0] = y0; yo[h][1] = y1; yo[h][2] = y2;
             }
             PCG_T(0);
@@ -1603,8 +1625,19 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             pcg_local_landmark_rows<S>(d, w, c, vsm + (size_t)9 * cps, cps, Kp, chain, pxy, tp);
 #endif
             PCG_T(1);
-            grid_barrier(w.bar, gridDim.x, epoch);       // every chunk's partials are visible
+            grid_barrier(w.bar, gridDim.x, epoch);       // every chunk's partials, and the z and gamma the previous iteration left, are visible
             PCG_T(3);
+            if (it > 0 && !(__ldcg(sc + FS_GAMMA0 + cur) > tol2 * gamma_init)) break;      // converged: x is final (the L phase above was for nothing)
+            // pass B of the off-diagonal product: neighbours in other chunks
+#pragma unroll
+            for (int h = 0; h < kPcgRows; h++) {
+                if (!out_nb[h]) continue;
+                S y0 = S(0), y1 = S(0), y2 = S(0);
+                off_row(h, true, y0, y1, y2);
+                const S* v = vsm + vx[h];
+                dacc += (double)v[9 * cps] * (double)y0 + (double)v[10 * cps] * (double)y1 + (double)v[11 * cps] * (double)y2;
+                yo[h][0] += y0; yo[h][1] += y1; yo[h][2] += y2;
+            }
             // ---- phase P, part 1: stage the chunk's landmark records {u_l, position}: t_l = the partials of all chunks that see the landmark ----
             {
                 double tu = 0.0;
@@ -1725,12 +1758,9 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 }
             }
             PCG_T(5);
-            grid_barrier(w.bar, gridDim.x, epoch);
-            PCG_T(6);
+            // no barrier here: the next iteration's first grid barrier orders this iteration's z, gamma and delta parts before their readers
             gamma_prev = gamma; alpha_prev = alpha;
             it++;
-            const double gnew = __ldcg(sc + FS_GAMMA0 + nxt);
-            if (!(gnew > tol2 * gamma_init)) break;
         }
     }
     // ---- epilogue: dx_p = x; x as padded records for the back-substitution gather; dx_l ----------------------------------

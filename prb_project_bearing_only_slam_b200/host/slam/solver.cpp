@@ -109,6 +109,7 @@ void Solver::download_state() {
 }
 
 void Solver::set_kernel_threshold(float kt) { check(bos_set_kernel_threshold(ctx_, kt), "bos_set_kernel_threshold"); }
+void Solver::set_irls(bool on) { check(bos_set_robust_mode(ctx_, on ? BOS_ROBUST_IRLS : BOS_ROBUST_REFERENCE), "bos_set_robust_mode"); }
 void Solver::set_damping_factor(float df) { check(bos_set_damping_factor(ctx_, df), "bos_set_damping_factor"); }
 
 void Solver::step() { step(1, true); }

@@ -61,6 +61,9 @@ class Solver {
     // opt-in Levenberg-Marquardt iteration (not in the reference: fixed damping, no step rejection): a GN step that is undone,
     // with the damping raised, when the total chi2 does not decrease; returns whether the step was kept
     bool step_lm();
+    // opt-in IRLS flavour of the threshold robust kernel (not in the reference, which scales the error only, slam/solver.cpp:37-41): the
+    // weight sqrt(kt / chi2) of an over-threshold edge scales its Omega, i.e. H as well as b
+    void set_irls(bool on);
     const bos_stats& last_stats() const { return stats_; }       // chi2 (pre-kernel error_omeganorm sums), |dx|_inf, timings
     bool last_step_not_spd() const { return stats_.solver_status != 0; }
     bos_ctx* context() { return ctx_; }

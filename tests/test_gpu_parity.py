@@ -660,3 +660,45 @@ def test_run_to_run_variation_is_bounded(built_lib):
         outs.append((s.chi2_bearing + s.chi2_odometry, s.state_digest))
         ctx.close()
     assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-6) and outs[0][1] == pytest.approx(outs[1][1], rel=1e-7)
+
+
+@pytest.mark.parametrize("solver", [capi.SOLVER_DENSE_CHOLESKY, capi.SOLVER_PCG])
+def test_irls_extension_matches_its_oracle_restatement(built_lib, solver):
+    """Opt-in IRLS flavour of the threshold kernel (bos_set_robust_mode) against the oracle's restatement from the triangulated
+    state two GN steps after the triangulated start of the full dataset, kernel threshold 1e-3 (edges of both kinds exceed it): b is the
+    reference's, H differs, both within 1e-9 of the oracle; eight IRLS iterations follow the oracle's trajectory and the increment solves
+    the IRLS normal equations."""
+    g, pr, o = golden_setup("full")
+    for _ in range(2):
+        o.step(0)
+    P, L = o.state()
+    ctx = make_ctx(pr, P, L, solver=solver, pcg_rtol=1e-13, pcg_max_iters=20000)
+    o.set_params(1e-3, float(np.float32(0.01))); ctx.set_kernel_threshold(1e-3)
+    ctx.linearize(); o.linearize()
+    assert len(align_oracle_wrap_branch(o, ctx.edge_terms()[0])) == 0
+    o.linearize()
+    _, _, val_ref, b_ref = o.csc()
+    ctx.set_robust_mode(capi.ROBUST_IRLS); o.set_irls(True)
+    ctx.linearize(); o.linearize()
+    colptr, rowidx, val, b = ctx.csc()
+    _, _, oval, ob = o.csc()
+    assert np.abs(b - ob).max() <= TOL64 * np.abs(ob).max(), np.abs(b - ob).max() / np.abs(ob).max()
+    assert csc_rel_err(colptr, val, oval) <= TOL64, (csc_rel_err(colptr, val, oval), csc_rel_err(colptr, val, val_ref))
+    assert np.abs(ob - b_ref).max() <= 1e-12 * np.abs(b_ref).max()      # the weight reaches b either way
+    assert np.abs(oval - val_ref).max() > 1e-3 * np.abs(val_ref).max()  # ... but H is re-weighted
+    assert ctx.stats().over_odometry == o.stats()["over_odometry"] > 0 and ctx.stats().over_bearing == o.stats()["over_bearing"] > 0
+    import scipy.sparse as sp
+    ctx.solve()
+    n = len(colptr) - 1
+    r = sp.csc_matrix((val, rowidx, colptr), shape=(n, n)) @ nofixed(pr, ctx.delta()) + b
+    assert np.abs(r).max() <= 1e-9 * np.abs(b).max()
+    ctx.set_state(P, L)
+    for it in range(8):
+        o.step(0)
+        s = ctx.step()
+        os_ = o.stats()
+        assert s.chi2_bearing == pytest.approx(os_["chi2_bearing"], rel=TOL64 if it == 0 else 1e-6), it
+        assert s.solver_status == 0 and s.over_odometry == os_["over_odometry"]
+    P2, L2 = ctx.get_state(); oP, oL = o.state()
+    assert np.abs(P2 - oP).max() <= 1e-6 and np.abs(L2 - oL).max() <= 1e-6
+    ctx.set_robust_mode(capi.ROBUST_REFERENCE)

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import load_golden, golden_problem
+from helpers import load_golden, golden_problem, oracle_for
 from oracle import oracle as orc
 from oracle.oracle import Oracle
 
@@ -209,3 +209,27 @@ def test_oracle_agrees_with_independent_numpy_restatement(name):
     assert np.abs(g["b_nofixed_f64"] - bn).max() <= 1e-9 * max(np.abs(bn).max(), 1e-12)
     assert g["trajectory_f64"][0, 0] == pytest.approx(chi_b, rel=1e-10) and g["trajectory_f64"][0, 1] == pytest.approx(chi_o, rel=1e-8)
     assert np.abs(g["delta0_f64"] - dx).max() <= 1e-8 * np.abs(dx).max()
+
+
+def test_irls_flavour_keeps_b_and_reweights_H():
+    """The opt-in IRLS robust kernel (not in the reference): the threshold weight w = sqrt(kt / chi2) scales Omega instead of the error,
+    so b is unchanged and H shrinks exactly on the blocks of the over-threshold edges."""
+    g = load_golden("full")
+    pr = golden_problem(g)
+    o = oracle_for(g["pose_ids"], g["poses_xyt"], pr)
+    for _ in range(2):       # the dead-reckoned start has zero odometry residuals
+        o.step(0)
+    o.set_params(1e-3, float(np.float32(0.01)))    # ... and at the reference's threshold of 1 no odometry edge of this trajectory is re-weighted
+    o.linearize()
+    col, row, v0, b0 = o.csc()
+    o.set_irls(True)
+    o.linearize()
+    _, _, v1, b1 = o.csc()
+    assert np.array_equal(b0, b1)
+    assert o.stats()["over_odometry"] > 0 and o.stats()["over_bearing"] > 0
+    diag0 = np.array([v0[col[j]:col[j + 1]][row[col[j]:col[j + 1]] == j][0] for j in range(len(col) - 1)])
+    diag1 = np.array([v1[col[j]:col[j + 1]][row[col[j]:col[j + 1]] == j][0] for j in range(len(col) - 1)])
+    assert np.all(diag1 <= diag0 + 1e-12) and np.any(diag1 < 0.9 * diag0)
+    o.set_irls(False)
+    o.linearize()
+    assert np.array_equal(o.csc()[2], v0)

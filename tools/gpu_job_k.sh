@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+O=gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 400 python bench.py --steps 20 --warmup 5 > $O/k_bench.json 2> $O/k_bench.err; python - <<'P'
+import json
+d=json.load(open('gpurun_out/k_bench.json'))
+print(d['value'], d['ms_per_step'], d['phases_ms'], d['pcg_iterations'], d['e2e']['value'], d['roofline']['frac'], d['roofline_linearize']['frac'])
+P
