@@ -377,7 +377,7 @@ def run_ours(args):
     w, pr, solver_name = make_world(args.workload)
     if args.solver != "workload":
         solver_name = args.solver
-    solver = {"pcg": capi.SOLVER_PCG, "dense": capi.SOLVER_DENSE_CHOLESKY, "auto": capi.SOLVER_AUTO}[solver_name]
+    solver = {"pcg": capi.SOLVER_PCG, "dense": capi.SOLVER_DENSE_CHOLESKY, "auto": capi.SOLVER_AUTO, "sparse": capi.SOLVER_SPARSE_CHOLESKY}[solver_name]
     prec = capi.PRECISION_F64 if args.precision == "f64" else capi.PRECISION_F32
     S = 8 if args.precision == "f64" else 4
     ctx = capi.Context(device=local, solver=solver, precision=prec, pcg_rtol=args.pcg_rtol, pcg_max_iters=args.pcg_max_iters,
@@ -509,7 +509,7 @@ def run_ours(args):
         "config": {"workload": args.workload, "poses": pr.NP, "landmarks": pr.NL, "bearing_edges": pr.Eb, "odometry_edges": pr.Eo,
                    "N": int(pi.N), "solver": {0: "schur+pcg(block-tridiagonal chain + coarse-space preconditioner)", 1: "schur+block-jacobi-pcg",
                               2: "schur+pcg(block-tridiagonal chain preconditioner)"}[args.pcg_precond]
-                   if solver == capi.SOLVER_PCG else "schur+dense-cholesky",
+                   if solver == capi.SOLVER_PCG else ("schur+skyline-cholesky" if solver == capi.SOLVER_SPARSE_CHOLESKY else "schur+dense-cholesky"),
                    "pcg_rtol": args.pcg_rtol, "pcg_coarse": "4 nodes per chunk, inverse kept for 8 solves" if solver == capi.SOLVER_PCG and args.pcg_precond == 0 else None,
                    "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
                    (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)",
@@ -622,7 +622,7 @@ def main():
     ap.add_argument("--ref-solver", default="auto", choices=["auto", "ldlt", "superlu"],
                     help="reference arm: ldlt = the oracle's restatement of Eigen::SimplicialLDLT, superlu = scipy's SuperLU; auto = ldlt when "
                          "its symbolic phase predicts under a minute per factorisation, else superlu")
-    ap.add_argument("--solver", default="workload", choices=["workload", "auto", "dense", "pcg"])
+    ap.add_argument("--solver", default="workload", choices=["workload", "auto", "dense", "pcg", "sparse"])
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds the cpu_baseline sample may spend in the numeric factorisation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -47,7 +47,10 @@ enum {
 };
 
 enum { BOS_PRECISION_F64 = 0, BOS_PRECISION_F32 = 1 };
-enum { BOS_SOLVER_AUTO = 0, BOS_SOLVER_DENSE_CHOLESKY = 1, BOS_SOLVER_PCG = 2 };
+/* BOS_SOLVER_SPARSE_CHOLESKY: Schur complement + Cholesky of the reduced pose system in SKYLINE storage: the symbolic phase (the
+ * envelope of the pose-only Schur complement in pose order: the analogue of SimplicialLDLT::analyzePattern, slam/solver.cpp:77-80) runs once
+ * per uploaded pattern, the numeric phase runs the dense solver's blocked DMMA kernels on the windows the envelope allows. */
+enum { BOS_SOLVER_AUTO = 0, BOS_SOLVER_DENSE_CHOLESKY = 1, BOS_SOLVER_PCG = 2, BOS_SOLVER_SPARSE_CHOLESKY = 3 };
 
 typedef struct bos_options {
     int device;               /* CUDA ordinal */
@@ -88,7 +91,7 @@ typedef struct bos_stats {
     double delta_inf;         /* max |dx| */
     int solver_status;        /* 0 ok, 1 = non-positive pivot / CG breakdown (the reference's "not SPD" console message,
                                  solver.cpp:82-84), 2 = the PCG stopped at pcg_max_iters before reaching pcg_rtol */
-    int solver_used;          /* BOS_SOLVER_DENSE_CHOLESKY or BOS_SOLVER_PCG */
+    int solver_used;          /* BOS_SOLVER_DENSE_CHOLESKY, BOS_SOLVER_PCG or BOS_SOLVER_SPARSE_CHOLESKY */
     int pcg_iterations;
     int gpu_launches;         /* kernels launched by the last step() */
     float ms_linearize;       /* CUDA-event times of the last step(), on the context's stream */
@@ -214,6 +217,10 @@ BOS_API int bos_host_pattern_get(const bos_host_pattern* p, int32_t* hpl_pose, i
 /* 64-bit FNV-1a digest of EVERY integer table of the pattern (block slots, ELL / chunk / tile layouts, adjacency ...): lets a test
  * assert that two builds (e.g. serial and threaded, BOS_PATTERN_THREADS=1) produced identical device layouts. */
 BOS_API int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out);
+/* Symbolic phase of BOS_SOLVER_SPARSE_CHOLESKY (what SimplicialLDLT::analyzePattern is to the reference, slam/solver.cpp:77-80): the row limit
+ * of every 64-column panel of the reduced pose system's skyline (panel_end: n_panels = ceil(3 NP / 64) entries, may be NULL), the rows stored
+ * per column and the stored fraction of the lower triangle.  Host only. */
+BOS_API int bos_host_pattern_skyline(const bos_host_pattern* p, int32_t* panel_end, int32_t* n_panels, int32_t* rows_per_column, double* fill);
 /* The contiguous edge ranges rank `rank` of `nranks` linearizes: out4 = b_begin, b_end, o_begin, o_end. */
 BOS_API int bos_host_edge_shard(int64_t Eb, int64_t Eo, int rank, int nranks, int64_t* out4);
 

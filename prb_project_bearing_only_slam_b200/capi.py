@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("BOS_LIB_PATH") or os.path.join(_HERE, "libbos_b200.so
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NCCL, ERR_NOMEM = range(6)
 PRECISION_F64, PRECISION_F32 = 0, 1
-SOLVER_AUTO, SOLVER_DENSE_CHOLESKY, SOLVER_PCG = 0, 1, 2
+SOLVER_AUTO, SOLVER_DENSE_CHOLESKY, SOLVER_PCG, SOLVER_SPARSE_CHOLESKY = 0, 1, 2, 3
 ROBUST_REFERENCE, ROBUST_IRLS = 0, 1
 NCCL_UID_BYTES = 128
 
@@ -48,7 +48,7 @@ SYMBOLS = [
     "bos_update", "bos_step", "bos_step_host", "bos_get_stats", "bos_triangulate", "bos_pattern_info_get",
     "bos_download_pattern", "bos_download_blocks", "bos_download_csc", "bos_download_delta", "bos_upload_delta",
     "bos_edge_terms", "bos_host_pattern_create", "bos_host_pattern_destroy", "bos_host_pattern_info",
-    "bos_host_pattern_get", "bos_host_pattern_checksum", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
+    "bos_host_pattern_get", "bos_host_pattern_checksum", "bos_host_pattern_skyline", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
     "bos_set_edge_shard", "bos_get_edge_shard", "bos_batch_create", "bos_batch_destroy", "bos_batch_set_states",
     "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error",
     "bos_triangulate_landmarks", "bos_eval_bearing_edges", "bos_eval_odometry_edges", "bos_step_lm",
@@ -96,6 +96,7 @@ def lib():
         L.bos_host_pattern_info.argtypes = [vp, C.POINTER(PatternInfo)]
         L.bos_host_pattern_get.argtypes = [vp] + [vp] * 8
         L.bos_host_pattern_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.bos_host_pattern_skyline.argtypes = [vp, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
         L.bos_host_edge_shard.argtypes = [i64, i64, i32, i32, vp]
         L.bos_nccl_unique_id.argtypes = [C.c_char_p]
         L.bos_comm_init.argtypes = [vp, i32, i32, C.c_char_p]
@@ -317,6 +318,16 @@ class HostPattern:
         pi = PatternInfo()
         self.L.bos_host_pattern_info(self.h, C.byref(pi))
         return pi
+
+    def skyline(self):
+        """Symbolic phase of the skyline Cholesky: (panel_end[int32], rows per column, stored fraction of the lower triangle)."""
+        npan, W, fill = C.c_int32(), C.c_int32(), C.c_double()
+        self.L.bos_host_pattern_skyline(self.h, None, C.byref(npan), C.byref(W), C.byref(fill))
+        pe = np.zeros(npan.value, np.int32)
+        rc = self.L.bos_host_pattern_skyline(self.h, _ptr(pe), C.byref(npan), C.byref(W), C.byref(fill))
+        if rc != OK:
+            raise BosError(rc, "bos_host_pattern_skyline")
+        return pe, int(W.value), float(fill.value)
 
     def checksum(self):
         out = C.c_uint64()

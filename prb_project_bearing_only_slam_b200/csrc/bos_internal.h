@@ -16,6 +16,8 @@ namespace bos {
 // bearing edges are linearized in tiles of this many (pose, landmark)-sorted edges; the landmark-side sums of a tile
 // are aggregated in shared memory through a host-precomputed tile-local grouping before they touch global memory
 constexpr int kLinTile = 512;
+constexpr int kDenseNB = 64;       // panel width of the blocked Cholesky
+constexpr int kDenseOuter = 256;   // outer panel: the bulk of the matrix is updated once per kDenseOuter columns
 // the fused PCG kernel reads the per-edge factors from two sliced-ELL layouts (see pattern.cpp)
 #ifndef BOS_PCG_THREADS
 #define BOS_PCG_THREADS 1024
@@ -150,7 +152,15 @@ struct DenseWork {
     S* tl_blk = nullptr;    // [64] scratch of the backward substitution
     int n = 0;              // 3*NP
     size_t bytes = 0;
+    // skyline flavour (BOS_SOLVER_SPARSE_CHOLESKY): Smat holds W rows per column (column j: rows j .. j + W - 1, addressed as a column-major
+    // matrix with leading dimension W - 1), sky_panel_end[k] = the row limit of the 64-column panel k.  Both come from the symbolic phase
+    // (skyline_symbolic), which runs once per uploaded pattern.
+    bool sky = false;
+    int sky_W = 0;
+    std::vector<int> sky_panel_end;
+    double sky_fill = 0.0;  // stored entries / (n (n + 1) / 2)
 };
+
 template <typename S>
 int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStream_t st, int* launches);
 

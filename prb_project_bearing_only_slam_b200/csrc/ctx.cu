@@ -99,6 +99,8 @@ struct bos_ctx {
     Dev<double> dd;
     Dev<float> df;
     DenseWork<double> dwd; DenseWork<float> dwf;
+    DenseWork<double> swd; DenseWork<float> swf;      // skyline flavour (BOS_SOLVER_SPARSE_CHOLESKY)
+    bool sky_ready = false;
     PcgWork<double> pwd; PcgWork<float> pwf;
     bool dense_ready = false, pcg_ready = false;
     void* edge_scratch = nullptr;
@@ -140,6 +142,9 @@ template <> Dev<float>& dev<float>(bos_ctx* c) { return c->df; }
 template <typename S> DenseWork<S>& dwork(bos_ctx* c);
 template <> DenseWork<double>& dwork<double>(bos_ctx* c) { return c->dwd; }
 template <> DenseWork<float>& dwork<float>(bos_ctx* c) { return c->dwf; }
+template <typename S> DenseWork<S>& swork(bos_ctx* c);
+template <> DenseWork<double>& swork<double>(bos_ctx* c) { return c->swd; }
+template <> DenseWork<float>& swork<float>(bos_ctx* c) { return c->swf; }
 template <typename S> PcgWork<S>& pwork(bos_ctx* c);
 template <> PcgWork<double>& pwork<double>(bos_ctx* c) { return c->pwd; }
 template <> PcgWork<float>& pwork<float>(bos_ctx* c) { return c->pwf; }
@@ -330,6 +335,56 @@ int ensure_dense(bos_ctx* c) {
     c->dense_ready = true;
     return BOS_OK;
 }
+// Symbolic phase of the skyline Cholesky (the analogue of SimplicialLDLT::analyzePattern, slam/solver.cpp:77-80), once per uploaded pattern: pose p is coupled with every pose that shares a landmark or an odometry
+// edge with it; in pose order the factor's fill stays inside the monotone envelope, so column j needs rows up to the largest coupled row of
+// any column <= j.  Row limits are kept per 64-column panel; W = the tallest window any outer panel of the factorisation touches.
+template <typename S>
+void skyline_symbolic(const HostPattern& P, DenseWork<S>& w) {
+    const int NP = P.NP, n = 3 * NP;
+    std::vector<int> lastpose(NP);
+    for (int p = 0; p < NP; p++) lastpose[p] = p;
+    for (int l = 0; l < P.NL; l++) {
+        const int a = P.lm_ptr[l], b = P.lm_ptr[l + 1];
+        if (b <= a) continue;
+        const int pmax = P.lm_order_pose[b - 1];      // ascending pose inside a landmark
+        for (int k = a; k < b; k++) lastpose[P.lm_order_pose[k]] = std::max(lastpose[P.lm_order_pose[k]], pmax);
+    }
+    for (size_t k = 0; k < P.off_lo.size(); k++) lastpose[P.off_lo[k]] = std::max(lastpose[P.off_lo[k]], P.off_hi[k]);
+    const int npanels = (n + kDenseNB - 1) / kDenseNB;
+    w.sky_panel_end.assign(npanels, 0);
+    int run = 0;
+    for (int k = 0; k < npanels; k++) {
+        const int j1 = std::min(n, (k + 1) * kDenseNB);
+        for (int j = k * kDenseNB; j < j1; j++) run = std::max(run, 3 * lastpose[j / 3] + 3);
+        w.sky_panel_end[k] = std::max(run, j1);
+    }
+    int W = 1;
+    double stored = 0.0;
+    for (int c0 = 0; c0 < n; c0 += kDenseOuter) {
+        const int cend = std::min(n, c0 + kDenseOuter);
+        W = std::max(W, w.sky_panel_end[(cend - 1) / kDenseNB] - c0);
+    }
+    for (int j = 0; j < n; j++) stored += (double)(w.sky_panel_end[j / kDenseNB] - j);     // lower-triangle entries inside the row limits
+    w.n = n; w.sky = true; w.sky_W = std::min(W + 1, n + 1);
+    w.sky_fill = stored / (0.5 * (double)n * (n + 1));
+}
+
+template <typename S>
+int ensure_skyline(bos_ctx* c) {
+    if (c->sky_ready) return BOS_OK;
+    Dev<S>& d = dev<S>(c);
+    DenseWork<S>& w = swork<S>(c);
+    skyline_symbolic<S>(c->P, w);
+    w.Smat = c->mem.get<S>((size_t)w.n * w.sky_W);
+    w.g = c->mem.get<S>((size_t)w.n);
+    w.hllinv = c->mem.get<S>(3 * (size_t)std::max(d.NL, 1));
+    w.ul = c->mem.get<S>(2 * (size_t)std::max(d.NL, 1));
+    w.tl = c->mem.get<S>(2 * (size_t)std::max(d.NL, 1));
+    w.tl_blk = c->mem.get<S>(64);
+    if (!w.Smat || !w.g || !w.hllinv || !w.ul || !w.tl || !w.tl_blk) return fail(c, BOS_ERR_NOMEM, "skyline workspace allocation failed");
+    c->sky_ready = true;
+    return BOS_OK;
+}
 template <typename S>
 int ensure_pcg(bos_ctx* c) {
     if (c->pcg_ready) return BOS_OK;
@@ -440,7 +495,7 @@ int ensure_pcg(bos_ctx* c) {
 }
 
 int pick_solver(bos_ctx* c) {
-    if (c->opt.solver == BOS_SOLVER_DENSE_CHOLESKY || c->opt.solver == BOS_SOLVER_PCG) return c->opt.solver;
+    if (c->opt.solver == BOS_SOLVER_DENSE_CHOLESKY || c->opt.solver == BOS_SOLVER_PCG || c->opt.solver == BOS_SOLVER_SPARSE_CHOLESKY) return c->opt.solver;
     return (3 * c->P.NP <= c->opt.dense_max_dim) ? BOS_SOLVER_DENSE_CHOLESKY : BOS_SOLVER_PCG;
 }
 
@@ -522,10 +577,11 @@ int solve_impl(bos_ctx* c) {
     if (c->nranks > 1 && c->reduce_mode >= 2 && c->P.slots_identity && !(which == BOS_SOLVER_PCG && c->opt.pcg_variant == 0))
         return fail(c, BOS_ERR_STATE, "reduce_mode 2 / 3 leave the pose-landmark blocks rank-local: only the fused PCG solve (pcg_variant 0) can follow");
     int nl = 0, rc = 0;
-    if (which == BOS_SOLVER_DENSE_CHOLESKY) {
-        int e = ensure_dense<S>(c);
+    if (which == BOS_SOLVER_DENSE_CHOLESKY || which == BOS_SOLVER_SPARSE_CHOLESKY) {
+        const bool sky = which == BOS_SOLVER_SPARSE_CHOLESKY;
+        int e = sky ? ensure_skyline<S>(c) : ensure_dense<S>(c);
         if (e) return e;
-        rc = launch_dense_solve<S>(d, dwork<S>(c), c->opt.damping, c->stream, &nl);
+        rc = launch_dense_solve<S>(d, sky ? swork<S>(c) : dwork<S>(c), c->opt.damping, c->stream, &nl);
         c->stats.pcg_iterations = 0;
         c->stats.precond_used = -1; c->stats.pcg_resolves = 0;
         c->pcg_bad = false; c->pcg_capped = false;
@@ -837,7 +893,7 @@ int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t 
             return fail(c, BOS_ERR_INVALID, "odometry omega of edge " + std::to_string(e) + " is not symmetric");
     }
     CUDA_OK(c, cudaSetDevice(c->opt.device));
-    c->have_problem = false; c->delta_valid = false; c->dense_ready = false; c->pcg_ready = false;
+    c->have_problem = false; c->delta_valid = false; c->dense_ready = false; c->pcg_ready = false; c->sky_ready = false;
     c->lm_pose_bak = nullptr; c->lm_lm_bak = nullptr;
     c->mem.release();
     if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count) != 0)
@@ -1166,6 +1222,16 @@ int bos_host_pattern_create(int NP, int NL, int fixed, int64_t Eb, const int32_t
 }
 int bos_host_pattern_destroy(bos_host_pattern* p) {
     delete p;
+    return BOS_OK;
+}
+int bos_host_pattern_skyline(const bos_host_pattern* p, int32_t* panel_end, int32_t* n_panels, int32_t* rows_per_column, double* fill) {
+    if (!p) return BOS_ERR_INVALID;
+    DenseWork<double> w;
+    skyline_symbolic<double>(p->P, w);
+    if (n_panels) *n_panels = (int32_t)w.sky_panel_end.size();
+    if (rows_per_column) *rows_per_column = w.sky_W;
+    if (fill) *fill = w.sky_fill;
+    if (panel_end) std::copy(w.sky_panel_end.begin(), w.sky_panel_end.end(), panel_end);
     return BOS_OK;
 }
 int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out) {

@@ -8,41 +8,44 @@
 // contraction on the path, run on the FP64 tensor pipe (mma.sync m8n8k4 f64 = DMMA; tcgen05 has no FP64
 // kind).  S is column-major, lower triangle only.
 #include "bos_internal.h"
+
+#include <cstdio>
+#include <cstdlib>
 #include "bos_math.cuh"
 #include "bos_schur.cuh"
 
 namespace bos {
 
-constexpr int NB = 64;        // panel width / tile edge
+constexpr int NB = kDenseNB;  // panel width / tile edge (64)
 constexpr int LDT = NB + 4;   // smem leading dimension: == 4 (mod 16) doubles -> conflict-free DMMA fragment loads
 
 // ---- assembly of the dense reduced system -----------------------------------------------------------
 template <typename S>
-__global__ void __launch_bounds__(256) k_dense_fill_diag(Dev<S> d, S* __restrict__ Sm, S* __restrict__ g, int n) {
+__global__ void __launch_bounds__(256) k_dense_fill_diag(Dev<S> d, S* __restrict__ Sm, S* __restrict__ g, int ld) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.NP) return;
     const S* h = d.Hpp + 6LL * p;
     const S m[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
     for (int a = 0; a < 3; a++) {
-        for (int c = 0; c < 3; c++) Sm[(size_t)(3 * p + a) + (size_t)(3 * p + c) * n] = m[a * 3 + c];
+        for (int c = 0; c < 3; c++) if (a >= c) Sm[(size_t)(3 * p + a) + (size_t)(3 * p + c) * ld] = m[a * 3 + c];   // lower triangle only
         g[3 * p + a] = -d.b[3LL * p + a];
     }
 }
 template <typename S>
-__global__ void __launch_bounds__(256) k_dense_fill_off(Dev<S> d, S* __restrict__ Sm, int n) {
+__global__ void __launch_bounds__(256) k_dense_fill_off(Dev<S> d, S* __restrict__ Sm, int ld) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= d.n_off) return;
     const int lo = d.off_lo[k], hi = d.off_hi[k];
     const S* B = d.Hoff + 9LL * k;  // H[lo][hi]; the lower triangle holds its transpose at (hi, lo)
     for (int a = 0; a < 3; a++)
-        for (int c = 0; c < 3; c++) Sm[(size_t)(3 * hi + c) + (size_t)(3 * lo + a) * n] = B[a * 3 + c];
+        for (int c = 0; c < 3; c++) Sm[(size_t)(3 * hi + c) + (size_t)(3 * lo + a) * ld] = B[a * 3 + c];
 }
 
 // one warp per landmark: S[pi,pj] -= Hpl_i Hll^-1 Hpl_j^T for every pair of its observing poses (pi >= pj),
 // g[pi] += Hpl_i Hll^-1 b_l
 template <typename S>
 __global__ void __launch_bounds__(256) k_dense_schur(Dev<S> d, const S* __restrict__ hllinv, const S* __restrict__ ul,
-                                                     S* __restrict__ Sm, S* __restrict__ g, int n) {
+                                                     S* __restrict__ Sm, S* __restrict__ g, int ldS) {
     const int lane = threadIdx.x & 31;
     const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (l >= d.NL) return;
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256) k_dense_schur(Dev<S> d, const S* __restri
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 if (i == j && c > a) continue;  // diagonal block: lower part only
-                red_add(Sm + (size_t)(3 * pi + a) + (size_t)(3 * pj + c) * n, -(ya0 * bj[2 * c] + ya1 * bj[2 * c + 1]));
+                red_add(Sm + (size_t)(3 * pi + a) + (size_t)(3 * pj + c) * ldS, -(ya0 * bj[2 * c] + ya1 * bj[2 * c + 1]));
             }
         }
     }
@@ -88,11 +91,11 @@ __global__ void __launch_bounds__(256) k_dense_schur(Dev<S> d, const S* __restri
 // tid % 4) updates the entries c = j + 1 + q, j + 5 + q, ... of row r with the UNSCALED column j:
 // A[r][c] -= A[r][j] A[c][j] / A[j][j]; column j itself is scaled by 1 / sqrt(A[j][j]) after the barrier (nobody reads it again).
 template <typename S>
-__global__ void __launch_bounds__(256) k_potrf_diag(S* __restrict__ Sm, int n, int k0, int kb, double* __restrict__ stats) {
+__global__ void __launch_bounds__(256) k_potrf_diag(S* __restrict__ Sm, int ld, int k0, int kb, double* __restrict__ stats) {
     __shared__ S A[NB][NB + 1];  // A[row][col]
     for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
         int c = t / kb, r = t % kb;
-        A[r][c] = (r >= c) ? Sm[(size_t)(k0 + r) + (size_t)(k0 + c) * n] : S(0);
+        A[r][c] = (r >= c) ? Sm[(size_t)(k0 + r) + (size_t)(k0 + c) * ld] : S(0);
     }
     __syncthreads();
     const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
@@ -119,30 +122,30 @@ __global__ void __launch_bounds__(256) k_potrf_diag(S* __restrict__ Sm, int n, i
     __syncthreads();
     for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
         int c = t / kb, rr = t % kb;
-        if (rr >= c) Sm[(size_t)(k0 + rr) + (size_t)(k0 + c) * n] = A[rr][c];
+        if (rr >= c) Sm[(size_t)(k0 + rr) + (size_t)(k0 + c) * ld] = A[rr][c];
     }
 }
 
 // panel: A[i, k0:k0+kb] <- A[i, k0:k0+kb] * L_kk^-T, one thread per row below the diagonal block.  Column-oriented: once x[m] is
 // final, the updates of x[m+1..] are independent FMAs (the dependent chain is one multiply per column, not the whole dot product).
 template <typename S>
-__global__ void __launch_bounds__(128) k_trsm_panel(S* __restrict__ Sm, int n, int k0, int kb) {
+__global__ void __launch_bounds__(128) k_trsm_panel(S* __restrict__ Sm, int ld, int nend, int k0, int kb) {
     __shared__ S L[NB][NB + 1];  // L[row j][col m]
     __shared__ S rd[NB];
     for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
         int j = t % NB, m = t / NB;   // consecutive threads walk down a column: coalesced
         S v = (j == m) ? S(1) : S(0);
-        if (j < kb && m <= j) v = Sm[(size_t)(k0 + j) + (size_t)(k0 + m) * n];
+        if (j < kb && m <= j) v = Sm[(size_t)(k0 + j) + (size_t)(k0 + m) * ld];
         L[j][m] = v;
     }
     __syncthreads();
     if (threadIdx.x < NB) rd[threadIdx.x] = S(1) / L[threadIdx.x][threadIdx.x];
     __syncthreads();
     const int i = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= nend) return;
     S x[NB];
 #pragma unroll
-    for (int j = 0; j < NB; j++) x[j] = (j < kb) ? Sm[(size_t)i + (size_t)(k0 + j) * n] : S(0);
+    for (int j = 0; j < NB; j++) x[j] = (j < kb) ? Sm[(size_t)i + (size_t)(k0 + j) * ld] : S(0);
 #pragma unroll
     for (int m = 0; m < NB; m++) {
         x[m] *= rd[m];
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128) k_trsm_panel(S* __restrict__ Sm, int n, i
     }
 #pragma unroll
     for (int j = 0; j < NB; j++)
-        if (j < kb) Sm[(size_t)i + (size_t)(k0 + j) * n] = x[j];
+        if (j < kb) Sm[(size_t)i + (size_t)(k0 + j) * ld] = x[j];
 }
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -168,7 +171,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 // 64-wide step (narrow region), the rest of the matrix once per outer panel with kt = kOuter: the trailing matrix is read
 // and written kOuter/64 times less often, which turns the update from HBM bound into tensor-pipe bound.
 template <typename S>
-__global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, int k0, int kt, int r0, int T, int TC) {
+__global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int ld, int nend, int k0, int kt, int r0, int T, int TC) {
     extern __shared__ unsigned char smem_raw[];
     S* sA = reinterpret_cast<S*>(smem_raw);   // [NB k][LDT rows]
     S* sB = sA + NB * LDT;
@@ -205,8 +208,8 @@ __global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, i
             const int k = t / NB, r = t % NB;
             S va = S(0), vb = S(0);
             if (k < kb) {
-                if (ra + r < n) va = Sm[(size_t)(ra + r) + (size_t)(k0 + kc + k) * n];
-                if (rb + r < n) vb = Sm[(size_t)(rb + r) + (size_t)(k0 + kc + k) * n];
+                if (ra + r < nend) va = Sm[(size_t)(ra + r) + (size_t)(k0 + kc + k) * ld];
+                if (rb + r < nend) vb = Sm[(size_t)(rb + r) + (size_t)(k0 + kc + k) * ld];
             }
             sA[k * LDT + r] = va;
             sB[k * LDT + r] = vb;
@@ -247,9 +250,9 @@ __global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, i
             for (int c = 0; c < 4; c++) {
                 const int row = ra + wm + a * 8 + fr;
                 const int col = rb + wn + c * 8 + 2 * fk;
-                if (row < n) {
-                    if (col < n) Sm[(size_t)row + (size_t)col * n] -= accd[a][c][0];
-                    if (col + 1 < n) Sm[(size_t)row + (size_t)(col + 1) * n] -= accd[a][c][1];
+                if (row < nend) {   // lower triangle only: in skyline storage an entry above the diagonal is somebody else's
+                    if (col <= row) Sm[(size_t)row + (size_t)col * ld] -= accd[a][c][0];
+                    if (col + 1 <= row) Sm[(size_t)row + (size_t)(col + 1) * ld] -= accd[a][c][1];
                 }
             }
     } else {
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(128) k_syrk_tiles(S* __restrict__ Sm, int n, i
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const int row = ra + tx * 8 + a, col = rb + ty * 4 + c;
-                if (row < n && col < n) Sm[(size_t)row + (size_t)col * n] -= accf[a][c];
+                if (row < nend && col <= row) Sm[(size_t)row + (size_t)col * ld] -= accf[a][c];
             }
     }
 }
@@ -275,7 +278,7 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid
     const int sz = valid ? 8 : 0;   // src-size 0: zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
-__global__ void __launch_bounds__(256, 2) k_syrk_big(double* __restrict__ Sm, int n, int k0, int kt, int r0) {
+__global__ void __launch_bounds__(256, 2) k_syrk_big(double* __restrict__ Sm, int ld, int nend, int k0, int kt, int r0) {
     const int ti = blockIdx.x, tj = blockIdx.y;
     if (tj > 2 * ti + 1) return;
     extern __shared__ unsigned char smem_raw[];
@@ -291,14 +294,14 @@ __global__ void __launch_bounds__(256, 2) k_syrk_big(double* __restrict__ Sm, in
 #pragma unroll
         for (int j = 0; j < KC * 128 / 256; j++) {
             const int idx = tid + 256 * j, r = idx & 127, k = idx >> 7;
-            const bool ok = (ra + r < n) && (kc + k < kt);
-            cp_async8(sA + k * LDA2 + r, Sm + (ok ? (size_t)(ra + r) + (size_t)(k0 + kc + k) * n : 0), ok);
+            const bool ok = (ra + r < nend) && (kc + k < kt);
+            cp_async8(sA + k * LDA2 + r, Sm + (ok ? (size_t)(ra + r) + (size_t)(k0 + kc + k) * ld : 0), ok);
         }
 #pragma unroll
         for (int j = 0; j < KC * 64 / 256; j++) {
             const int idx = tid + 256 * j, r = idx & 63, k = idx >> 6;
-            const bool ok = (rb + r < n) && (kc + k < kt);
-            cp_async8(sB + k * LDB2 + r, Sm + (ok ? (size_t)(rb + r) + (size_t)(k0 + kc + k) * n : 0), ok);
+            const bool ok = (rb + r < nend) && (kc + k < kt);
+            cp_async8(sB + k * LDB2 + r, Sm + (ok ? (size_t)(rb + r) + (size_t)(k0 + kc + k) * ld : 0), ok);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -340,9 +343,9 @@ __global__ void __launch_bounds__(256, 2) k_syrk_big(double* __restrict__ Sm, in
         for (int c = 0; c < 4; c++) {
             const int row = ra + wm + a * 8 + fr;
             const int col = rb + wn + c * 8 + 2 * fk;
-            if (row < n) {
-                if (col < n && row >= col) Sm[(size_t)row + (size_t)col * n] -= acc[a][c][0];
-                if (col + 1 < n && row >= col + 1) Sm[(size_t)row + (size_t)(col + 1) * n] -= acc[a][c][1];
+            if (row < nend) {
+                if (row >= col) Sm[(size_t)row + (size_t)col * ld] -= acc[a][c][0];
+                if (row >= col + 1) Sm[(size_t)row + (size_t)(col + 1) * ld] -= acc[a][c][1];
             }
         }
 }
@@ -350,39 +353,39 @@ __global__ void __launch_bounds__(256, 2) k_syrk_big(double* __restrict__ Sm, in
 // ---- triangular solves with the factor ------------------------------------------------------------------
 // forward, diagonal block: y_k = L_kk^-1 g_k   (one CTA of NB threads)
 template <typename S>
-__global__ void __launch_bounds__(NB) k_fwd_diag(const S* __restrict__ Sm, S* __restrict__ g, int n, int k0, int kb) {
+__global__ void __launch_bounds__(NB) k_fwd_diag(const S* __restrict__ Sm, S* __restrict__ g, int ld, int k0, int kb) {
     __shared__ S y[NB];
     const int j = threadIdx.x;
     S v = (j < kb) ? g[k0 + j] : S(0);
     for (int m = 0; m < kb; m++) {
-        if (j == m) y[m] = v / Sm[(size_t)(k0 + m) + (size_t)(k0 + m) * n];
+        if (j == m) y[m] = v / Sm[(size_t)(k0 + m) + (size_t)(k0 + m) * ld];
         __syncthreads();
-        if (j > m && j < kb) v -= Sm[(size_t)(k0 + j) + (size_t)(k0 + m) * n] * y[m];
+        if (j > m && j < kb) v -= Sm[(size_t)(k0 + j) + (size_t)(k0 + m) * ld] * y[m];
     }
     if (j < kb) g[k0 + j] = y[j];
 }
 // forward, below the block: g_i -= sum_m L[i, k0+m] y_m
 template <typename S>
-__global__ void __launch_bounds__(256) k_fwd_update(const S* __restrict__ Sm, S* __restrict__ g, int n, int k0, int kb) {
+__global__ void __launch_bounds__(256) k_fwd_update(const S* __restrict__ Sm, S* __restrict__ g, int ld, int nend, int k0, int kb) {
     __shared__ S y[NB];
     if (threadIdx.x < NB) y[threadIdx.x] = (threadIdx.x < kb) ? g[k0 + threadIdx.x] : S(0);
     __syncthreads();
     const int i = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= nend) return;
     S s = S(0);
-    for (int m = 0; m < kb; m++) s += Sm[(size_t)i + (size_t)(k0 + m) * n] * y[m];
+    for (int m = 0; m < kb; m++) s += Sm[(size_t)i + (size_t)(k0 + m) * ld] * y[m];
     g[i] -= s;
 }
 // backward, gather: t_m = sum_{i >= k0+kb} L[i, k0+m] x_i   (t zeroed by the caller)
 template <typename S>
 __global__ void __launch_bounds__(256) k_bwd_gather(const S* __restrict__ Sm, const S* __restrict__ x, S* __restrict__ t,
-                                                    int n, int k0, int kb) {
+                                                    int ld, int nend, int k0, int kb) {
     __shared__ S part[8][NB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
-    const S xi = (i < n) ? x[i] : S(0);
+    const S xi = (i < nend) ? x[i] : S(0);
     for (int m = 0; m < kb; m++) {
-        S v = (i < n) ? Sm[(size_t)i + (size_t)(k0 + m) * n] * xi : S(0);
+        S v = (i < nend) ? Sm[(size_t)i + (size_t)(k0 + m) * ld] * xi : S(0);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BOS_FULL_MASK, v, o);
         if (lane == 0) part[warp][m] = v;
@@ -396,14 +399,14 @@ __global__ void __launch_bounds__(256) k_bwd_gather(const S* __restrict__ Sm, co
 }
 // backward, diagonal block: x_k = L_kk^-T (y_k - t)
 template <typename S>
-__global__ void __launch_bounds__(NB) k_bwd_diag(const S* __restrict__ Sm, S* __restrict__ g, const S* __restrict__ t, int n, int k0, int kb) {
+__global__ void __launch_bounds__(NB) k_bwd_diag(const S* __restrict__ Sm, S* __restrict__ g, const S* __restrict__ t, int ld, int k0, int kb) {
     __shared__ S x[NB];
     const int j = threadIdx.x;
     S v = (j < kb) ? g[k0 + j] - t[j] : S(0);
     for (int m = kb - 1; m >= 0; m--) {
-        if (j == m) x[m] = v / Sm[(size_t)(k0 + m) + (size_t)(k0 + m) * n];
+        if (j == m) x[m] = v / Sm[(size_t)(k0 + m) + (size_t)(k0 + m) * ld];
         __syncthreads();
-        if (j < m) v -= Sm[(size_t)(k0 + m) + (size_t)(k0 + j) * n] * x[m];  // L^T[j][m] = L[m][j]
+        if (j < m) v -= Sm[(size_t)(k0 + m) + (size_t)(k0 + j) * ld] * x[m];  // L^T[j][m] = L[m][j]
     }
     if (j < kb) g[k0 + j] = x[j];
 }
@@ -414,77 +417,101 @@ __global__ void __launch_bounds__(256) k_copy_delta_p(const S* __restrict__ g, S
     if (i < n) delta[i] = g[i];
 }
 
-// Blocked Cholesky of the lower triangle of a column-major n x n matrix, in place (the strict upper triangle is not touched).
+// Blocked Cholesky of the lower triangle of a column-major matrix, in place (the strict upper triangle is never touched).
+// Dense: ld = n, panel_end = nullptr.  Skyline: column j holds rows j .. < panel_end[j / NB] (a non-decreasing row limit per 64-column panel,
+// from the cached symbolic phase) in storage with leading dimension ld = W - 1, W rows per column (element (i, j) at A[i + j * ld], the LAPACK
+// band-storage trick): every kernel below sees an ordinary column-major window, bounded by the panel's row limit.
 // stats[5] is set when a pivot is not positive.  Returns the number of launches.
+static bool dbg_sync_on() { static int v = -1; if (v < 0) v = std::getenv("BOS_DEBUG_SYNC") ? 1 : 0; return v == 1; }
+#define DBG_SYNC(what, a, b) do { if (dbg_sync_on()) { cudaError_t e__ = cudaStreamSynchronize(st); if (e__ != cudaSuccess) { std::fprintf(stderr, "[dense] %s (%d, %d): %s\n", what, (int)(a), (int)(b), cudaGetErrorString(e__)); return -1; } } } while (0)
 template <typename S>
-int dense_cholesky_lower(S* Smat, int n, double* stats, cudaStream_t st) {
+int skyline_cholesky_lower(S* Smat, int n, int ld, const int* panel_end, double* stats, cudaStream_t st) {
     int nl = 0;
     const size_t smem = 2 * (size_t)NB * LDT * sizeof(S);
     ensure_dyn_smem((const void*)k_syrk_tiles<S>, smem);
-    constexpr int kOuter = 256;   // outer panel: the bulk of the matrix is updated once per kOuter columns
-    for (int c0 = 0; c0 < n; c0 += kOuter) {
-        const int cend = (c0 + kOuter < n) ? c0 + kOuter : n;
+    auto rend_of = [&](int k0) { return panel_end ? panel_end[k0 / NB] : n; };
+    for (int c0 = 0; c0 < n; c0 += kDenseOuter) {
+        const int cend = (c0 + kDenseOuter < n) ? c0 + kDenseOuter : n;
         for (int k0 = c0; k0 < cend; k0 += NB) {
             const int kb = (cend - k0 < NB) ? cend - k0 : NB;
-            k_potrf_diag<S><<<1, 256, 0, st>>>(Smat, n, k0, kb, stats); nl++;
-            const int r0 = k0 + kb;
-            if (r0 < n) {
-                k_trsm_panel<S><<<(n - r0 + 127) / 128, 128, 0, st>>>(Smat, n, k0, kb); nl++;
+            k_potrf_diag<S><<<1, 256, 0, st>>>(Smat, ld, k0, kb, stats); nl++;
+            DBG_SYNC("potrf", k0, kb);
+            const int r0 = k0 + kb, rend = rend_of(k0);
+            if (r0 < rend) {
+                k_trsm_panel<S><<<(rend - r0 + 127) / 128, 128, 0, st>>>(Smat, ld, rend, k0, kb); nl++;
+                DBG_SYNC("trsm", k0, rend);
                 if (r0 < cend) {   // the outer panel's own remaining columns
-                    const int T = (n - r0 + NB - 1) / NB, TC = (cend - r0 + NB - 1) / NB;
-                    if (TC >= T) k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(Smat, n, k0, kb, r0, T, T);
-                    else k_syrk_tiles<S><<<dim3(T, TC), 128, smem, st>>>(Smat, n, k0, kb, r0, T, TC);
+                    const int T = (rend - r0 + NB - 1) / NB, TC = (cend - r0 + NB - 1) / NB;
+                    if (TC >= T) k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(Smat, ld, rend, k0, kb, r0, T, T);
+                    else k_syrk_tiles<S><<<dim3(T, TC), 128, smem, st>>>(Smat, ld, rend, k0, kb, r0, T, TC);
                     nl++;
+                    DBG_SYNC("syrk narrow", k0, rend);
                 }
             }
         }
-        if (cend < n) {            // everything beyond the outer panel, once, with all of its columns
-            const int T = (n - cend + NB - 1) / NB;
+        const int wend = rend_of(cend - 1);   // rows the outer panel's columns reach (non-decreasing limits: the last panel's)
+        if (cend < wend) {            // everything beyond the outer panel, once, with all of its columns
+            const int T = (wend - cend + NB - 1) / NB;
             if constexpr (sizeof(S) == 8) {
                 constexpr size_t smem_big = 2 * (size_t)(KC * LDA2 + KC * LDB2) * sizeof(double);
                 ensure_dyn_smem((const void*)k_syrk_big, smem_big);
-                k_syrk_big<<<dim3((n - cend + 127) / 128, T), 256, smem_big, st>>>(Smat, n, c0, cend - c0, cend);
+                k_syrk_big<<<dim3((wend - cend + 127) / 128, T), 256, smem_big, st>>>(Smat, ld, wend, c0, cend - c0, cend);
             } else {
-                k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(Smat, n, c0, cend - c0, cend, T, T);
+                k_syrk_tiles<S><<<(unsigned)((long long)T * (T + 1) / 2), 128, smem, st>>>(Smat, ld, wend, c0, cend - c0, cend, T, T);
             }
             nl++;
+            DBG_SYNC("syrk bulk", c0, wend);
         }
     }
     return nl;
 }
+template <typename S>
+int dense_cholesky_lower(S* Smat, int n, double* stats, cudaStream_t st) { return skyline_cholesky_lower<S>(Smat, n, n, nullptr, stats, st); }
 template int dense_cholesky_lower<double>(double*, int, double*, cudaStream_t);
 template int dense_cholesky_lower<float>(float*, int, double*, cudaStream_t);
 
+// Schur complement of the landmark blocks into a dense (ld = n) or skyline (w.sky: ld = W - 1, W rows per column) lower triangle, Cholesky,
+// the two triangular solves, landmark back-substitution
 template <typename S>
 int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStream_t st, int* launches) {
     (void)damping;
     int nl = 0;
     const int n = w.n;
+    const bool sky = w.sky;
+    const int ld = sky ? w.sky_W - 1 : n;
+    const int* pend = sky ? w.sky_panel_end.data() : nullptr;
+    auto rend_of = [&](int k0) { return pend ? pend[k0 / NB] : n; };
     const int gp = (d.NP + 255) / 256, gl = (d.NL + 255) / 256;
-    cudaMemsetAsync(w.Smat, 0, sizeof(S) * (size_t)n * n, st);
-    k_dense_fill_diag<S><<<gp, 256, 0, st>>>(d, w.Smat, w.g, n); nl++;
-    if (d.n_off > 0) { k_dense_fill_off<S><<<(d.n_off + 255) / 256, 256, 0, st>>>(d, w.Smat, n); nl++; }
+    cudaMemsetAsync(w.Smat, 0, sizeof(S) * (sky ? (size_t)n * w.sky_W : (size_t)n * n), st);
+    k_dense_fill_diag<S><<<gp, 256, 0, st>>>(d, w.Smat, w.g, ld); nl++;
+    if (d.n_off > 0) { k_dense_fill_off<S><<<(d.n_off + 255) / 256, 256, 0, st>>>(d, w.Smat, ld); nl++; }
     if (d.NL > 0) {
         k_lm_prep<S><<<gl, 256, 0, st>>>(d, w.hllinv, w.ul); nl++;
-        k_dense_schur<S><<<(d.NL * 32 + 255) / 256, 256, 0, st>>>(d, w.hllinv, w.ul, w.Smat, w.g, n); nl++;
+        k_dense_schur<S><<<(d.NL * 32 + 255) / 256, 256, 0, st>>>(d, w.hllinv, w.ul, w.Smat, w.g, ld); nl++;
     }
-    nl += dense_cholesky_lower<S>(w.Smat, n, d.stats, st);
+    DBG_SYNC("schur fill", n, ld);
+    {
+        const int nc = skyline_cholesky_lower<S>(w.Smat, n, ld, pend, d.stats, st);
+        if (nc < 0) return -1;
+        nl += nc;
+    }
     // forward substitution L y = g
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int kb = (n - k0 < NB) ? n - k0 : NB;
-        k_fwd_diag<S><<<1, NB, 0, st>>>(w.Smat, w.g, n, k0, kb); nl++;
-        const int r0 = k0 + kb;
-        if (r0 < n) { k_fwd_update<S><<<(n - r0 + 255) / 256, 256, 0, st>>>(w.Smat, w.g, n, k0, kb); nl++; }
+        k_fwd_diag<S><<<1, NB, 0, st>>>(w.Smat, w.g, ld, k0, kb); nl++;
+        const int r0 = k0 + kb, rend = rend_of(k0);
+        if (r0 < rend) { k_fwd_update<S><<<(rend - r0 + 255) / 256, 256, 0, st>>>(w.Smat, w.g, ld, rend, k0, kb); nl++; }
     }
     // backward substitution L^T x = y
     const int last = ((n - 1) / NB) * NB;
     for (int k0 = last; k0 >= 0; k0 -= NB) {
         const int kb = (n - k0 < NB) ? n - k0 : NB;
-        const int r0 = k0 + kb;
+        const int r0 = k0 + kb, rend = rend_of(k0);
         cudaMemsetAsync(w.tl_blk, 0, sizeof(S) * NB, st);
-        if (r0 < n) { k_bwd_gather<S><<<(n - r0 + 255) / 256, 256, 0, st>>>(w.Smat, w.g, w.tl_blk, n, k0, kb); nl++; }
-        k_bwd_diag<S><<<1, NB, 0, st>>>(w.Smat, w.g, w.tl_blk, n, k0, kb); nl++;
+        if (r0 < rend) { k_bwd_gather<S><<<(rend - r0 + 255) / 256, 256, 0, st>>>(w.Smat, w.g, w.tl_blk, ld, rend, k0, kb); nl++; }
+        k_bwd_diag<S><<<1, NB, 0, st>>>(w.Smat, w.g, w.tl_blk, ld, k0, kb); nl++;
     }
+    DBG_SYNC("triangular solves", n, ld);
     k_copy_delta_p<S><<<(n + 255) / 256, 256, 0, st>>>(w.g, d.delta, n); nl++;
     if (d.NL > 0) {
         cudaMemsetAsync(w.tl, 0, sizeof(S) * 2 * (size_t)d.NL, st);

@@ -101,7 +101,8 @@ def test_pattern_and_H_b_chi2_match_oracle(built_lib, name):
 
 
 @pytest.mark.parametrize("name,solver", [("mini", capi.SOLVER_DENSE_CHOLESKY), ("full", capi.SOLVER_DENSE_CHOLESKY),
-                                         ("mini", capi.SOLVER_PCG), ("full", capi.SOLVER_PCG)])
+                                         ("mini", capi.SOLVER_PCG), ("full", capi.SOLVER_PCG),
+                                         ("mini", capi.SOLVER_SPARSE_CHOLESKY), ("full", capi.SOLVER_SPARSE_CHOLESKY)])
 def test_solve_and_update_match_oracle(built_lib, name, solver):
     g, pr, o = golden_setup(name)
     P, L = o.state()                          # iteration 0: the reference's own triangulated start
@@ -702,3 +703,38 @@ def test_irls_extension_matches_its_oracle_restatement(built_lib, solver):
     P2, L2 = ctx.get_state(); oP, oL = o.state()
     assert np.abs(P2 - oP).max() <= 1e-6 and np.abs(L2 - oL).max() <= 1e-6
     ctx.set_robust_mode(capi.ROBUST_REFERENCE)
+
+
+def test_sparse_skyline_cholesky_matches_dense_and_oracle(built_lib):
+    """BOS_SOLVER_SPARSE_CHOLESKY on a 3000-pose trajectory world, where the skyline is a real envelope (38 % of the triangle,
+    several outer panels, windows that end inside the matrix): the increment equals the dense Cholesky's to 1e-10 and the oracle's dense
+    LDL^T to 1e-8, solves the GPU's own normal equations, and four GN steps follow the dense path."""
+    import scipy.sparse as sp
+    w, pr = synth_problem(3000, 600, 30000, seed=3)
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr)
+    P, L = o.state()
+    from prb_project_bearing_only_slam_b200.capi import HostPattern
+    pe, W, fill = HostPattern(pr.NP, pr.NL, pr.fixed_stix, pr.b_pose, pr.b_lm, pr.o_src, pr.o_dst).skyline()
+    assert fill < 0.6 and W < 3 * pr.NP
+    outs = {}
+    for name, solver in (("dense", capi.SOLVER_DENSE_CHOLESKY), ("sparse", capi.SOLVER_SPARSE_CHOLESKY)):
+        ctx = make_ctx(pr, P, L, solver=solver)
+        ctx.linearize(); ctx.solve()
+        d = ctx.delta()
+        assert ctx.stats().solver_status == 0 and ctx.stats().solver_used == solver
+        colptr, rowidx, val, b = ctx.csc()
+        n = len(colptr) - 1
+        r = sp.csc_matrix((val, rowidx, colptr), shape=(n, n)) @ nofixed(pr, d) + b
+        assert np.abs(r).max() <= 1e-9 * np.abs(b).max(), name
+        ctx.update()
+        for _ in range(3):
+            s = ctx.step()
+            assert s.solver_status == 0
+        outs[name] = (d, ctx.get_state(), s.ms_solve)
+        ctx.close()
+    o.linearize(); o.solve(0)
+    od = o.delta()
+    assert np.abs(outs["sparse"][0] - outs["dense"][0]).max() <= 1e-10 * np.abs(od).max()
+    assert np.abs(outs["sparse"][0] - od).max() <= 1e-8 * np.abs(od).max()
+    assert np.abs(outs["sparse"][1][0] - outs["dense"][1][0]).max() <= 1e-8 and np.abs(outs["sparse"][1][1] - outs["dense"][1][1]).max() <= 1e-8
+    print("n = %d: dense %.2f ms, skyline (fill %.2f) %.2f ms per solve" % (3 * pr.NP, outs["dense"][2], fill, outs["sparse"][2]))

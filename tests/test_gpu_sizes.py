@@ -104,7 +104,7 @@ def test_config3_synth_100k_dense_pcg_and_sparse_ldlt_agree(built_lib):
     od = o.delta()
     ds = {}
     for name, opts in (("dense", dict(solver=capi.SOLVER_DENSE_CHOLESKY)), ("pcg", dict(solver=capi.SOLVER_PCG, pcg_rtol=1e-13, pcg_max_iters=40000)),
-                       ("auto", dict(pcg_rtol=1e-13, pcg_max_iters=40000))):
+                       ("auto", dict(pcg_rtol=1e-13, pcg_max_iters=40000)), ("sparse", dict(solver=capi.SOLVER_SPARSE_CHOLESKY))):
         ctx = capi.Context(**opts)
         pr.upload(ctx)
         ctx.set_state(P, L)
@@ -121,9 +121,10 @@ def test_config3_synth_100k_dense_pcg_and_sparse_ldlt_agree(built_lib):
         r = H @ nofixed(pr, ds[name]) + b
         assert np.abs(r).max() <= 1e-9 * np.abs(b).max(), name
         assert np.abs(ds[name] - od).max() <= 1e-8 * np.abs(od).max(), name
-        print("synth-100k %s: solver_used %d, %.3f ms solve" % (name, st.solver_used, 0.0))
+        print("synth-100k %s: solver_used %d" % (name, st.solver_used))
         ctx.close()
     assert np.abs(ds["dense"] - ds["pcg"]).max() <= 1e-8 * np.abs(ds["pcg"]).max()
+    assert np.abs(ds["dense"] - ds["sparse"]).max() <= 1e-9 * np.abs(ds["dense"]).max()
 
 
 def test_config5_batch_4096_spot_checked_against_oracle(built_lib):

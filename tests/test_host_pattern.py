@@ -109,3 +109,45 @@ def test_threaded_pattern_build_equals_the_serial_one(built_lib, monkeypatch):
             hp = capi.HostPattern(pr.NP, pr.NL, pr.fixed_stix, bp, bl, pr.o_src, pr.o_dst)
             sums.append(hp.checksum())
         assert sums[0] == sums[1] and sums[0] != 0
+
+
+def _schur_pose_pattern(pr):
+    """Pose pairs of the reduced (pose-only Schur) system: poses sharing a landmark or an odometry edge (dense boolean, small worlds)."""
+    A = np.zeros((pr.NP, pr.NP), bool)
+    for l in range(pr.NL):
+        ps = np.unique(pr.b_pose[pr.b_lm == l])
+        A[np.ix_(ps, ps)] = True
+    A[pr.o_src, pr.o_dst] = True
+    A[pr.o_dst, pr.o_src] = True
+    A[np.arange(pr.NP), np.arange(pr.NP)] = True
+    return A
+
+
+@pytest.mark.parametrize("case", ["full", "synth"])
+def test_skyline_symbolic_phase_covers_the_factor(built_lib, case):
+    """The symbolic phase of BOS_SOLVER_SPARSE_CHOLESKY (analyzePattern's analogue): its per-panel row limits are non-decreasing, contain every
+    entry of the reduced system AND of its Cholesky factor (checked with a dense symbolic elimination), and every window the blocked
+    factorisation touches fits into the stored rows per column."""
+    if case == "full":
+        g = load_golden("full")
+        pr = golden_problem(g)
+    else:
+        _, pr = synth_problem(500, 120, 5000, seed=11)
+    hp = capi.HostPattern(pr.NP, pr.NL, pr.fixed_stix, pr.b_pose, pr.b_lm, pr.o_src, pr.o_dst)
+    pe, W, fill = hp.skyline()
+    n = 3 * pr.NP
+    assert len(pe) == (n + 63) // 64 and np.all(np.diff(pe) >= 0) and pe[-1] == n and 0 < fill <= 1.0 + 1e-12
+    A = np.kron(_schur_pose_pattern(pr), np.ones((3, 3), bool))
+    # symbolic Cholesky (no cancellation): L's pattern column by column
+    Lp = np.tril(A)
+    for j in range(n):
+        rows = np.nonzero(Lp[j + 1:, j])[0] + j + 1
+        if len(rows):
+            Lp[np.ix_(rows, rows)] |= np.tril(np.ones((len(rows), len(rows)), bool))
+    last = np.array([np.nonzero(Lp[:, j])[0].max() + 1 for j in range(n)])
+    assert np.all(last <= pe[np.arange(n) // 64])
+    for c0 in range(0, n, 256):
+        cend = min(n, c0 + 256)
+        assert pe[(cend - 1) // 64] - c0 <= W - 1 or W == n + 1
+    if case == "synth":
+        assert fill < 0.9          # a trajectory-ordered world has a real envelope

@@ -1,9 +1,5 @@
 #!/bin/bash
 set -u
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-timeout 400 python bench.py --steps 20 --warmup 5 > $O/k_bench.json 2> $O/k_bench.err; python - <<'P'
-import json
-d=json.load(open('gpurun_out/k_bench.json'))
-print(d['value'], d['ms_per_step'], d['phases_ms'], d['pcg_iterations'], d['e2e']['value'], d['roofline']['frac'], d['roofline_linearize']['frac'])
-P
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_sizes.py -m gpu -x -q -k "sparse or solve_and_update or config3 or dense" -s 2>&1 | grep -E "passed|failed|^E  |dense .* ms|synth-100k" | head -20
+timeout 600 python tools/sweep_solvers.py > $O/k_sweep.jsonl 2> $O/k_sweep.err; cat $O/k_sweep.jsonl; tail -3 $O/k_sweep.err

@@ -15,7 +15,7 @@ for name, n in cases:
     else:
         w, pr = synth_problem(n, max(n // 5, 4), 10 * n, seed=0xB0500003); P0 = xyt_to_xycs(w["poses_init"])
     res = {"case": name if n is None else "synth-%d" % n, "n": 3 * pr.NP}
-    for sname, solver in (("dense", capi.SOLVER_DENSE_CHOLESKY), ("pcg", capi.SOLVER_PCG)):
+    for sname, solver in (("dense", capi.SOLVER_DENSE_CHOLESKY), ("sparse", capi.SOLVER_SPARSE_CHOLESKY), ("pcg", capi.SOLVER_PCG)):
         if sname == "dense" and 3 * pr.NP > 20000:
             continue
         ctx = capi.Context(solver=solver, pcg_rtol=1e-8, pcg_max_iters=20000)
