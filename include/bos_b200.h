@@ -217,6 +217,21 @@ BOS_API int bos_host_pattern_get(const bos_host_pattern* p, int32_t* hpl_pose, i
 /* 64-bit FNV-1a digest of EVERY integer table of the pattern (block slots, ELL / chunk / tile layouts, adjacency ...): lets a test
  * assert that two builds (e.g. serial and threaded, BOS_PATTERN_THREADS=1) produced identical device layouts. */
 BOS_API int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out);
+/* On-device problem setup (the reference resolves ids through std::map for every edge of every iteration, framework/state.cpp:43-63,
+ * and this library's default builds its tables on host threads).
+ * bos_set_device_setup(ctx, 1): bos_upload_problem builds the bearing-edge core of the pattern -- the (pose, landmark)-sorted edge order, the
+ *   pose-landmark block slots, the CSR-of-blocks row pointers, the landmark-major slot order and the triangulation rows -- with GPU radix sorts,
+ *   scans and run-length kernels; the remaining layouts (tiles, PCG chunks) are derived from them on the host.  The tables are bit-identical to
+ *   the host builder's: bos_pattern_checksum equals bos_host_pattern_checksum.  bos_last_setup_ms reports the two parts of the last upload.
+ * bos_device_resolve_ids: id -> stix for all edge end points on the device (map::at semantics: an unknown pose id is BOS_ERR_INVALID, a duplicated
+ *   pose id resolves to its last insertion; landmark stix = rank of the id among the observed landmark ids, slam/triangulation.cpp:68-73);
+ *   lm_ids (capacity Eb) receives the ascending landmark id table, *NL_out its length. */
+BOS_API int bos_set_device_setup(bos_ctx* ctx, int on);
+BOS_API int bos_last_setup_ms(const bos_ctx* ctx, double* device_core_ms, double* host_ms);
+BOS_API int bos_pattern_checksum(bos_ctx* ctx, uint64_t* out);
+BOS_API int bos_device_resolve_ids(int device, int NP, const int32_t* pose_ids, int64_t Eb, const int32_t* b_pose_id, const int32_t* b_lm_id, int64_t Eo,
+                                   const int32_t* o_src_id, const int32_t* o_dst_id, int32_t* b_pose, int32_t* b_lm, int32_t* o_src, int32_t* o_dst,
+                                   int32_t* lm_ids, int32_t* NL_out);
 /* Symbolic phase of BOS_SOLVER_SPARSE_CHOLESKY (what SimplicialLDLT::analyzePattern is to the reference, slam/solver.cpp:77-80): the row limit
  * of every 64-column panel of the reduced pose system's skyline (panel_end: n_panels = ceil(3 NP / 64) entries, may be NULL), the rows stored
  * per column and the stored fraction of the lower triangle.  Host only. */

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbos_b200.so")
 
-CU_SOURCES = ["linearize.cu", "solve_pcg.cu", "solve_dense.cu", "misc.cu", "ctx.cu"]
+CU_SOURCES = ["linearize.cu", "solve_pcg.cu", "solve_dense.cu", "misc.cu", "setup.cu", "ctx.cu"]
 CPP_SOURCES = ["pattern.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".hpp"))) + [os.path.join("..", "..", "include", "bos_b200.h")]
 

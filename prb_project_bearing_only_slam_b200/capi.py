@@ -48,7 +48,8 @@ SYMBOLS = [
     "bos_update", "bos_step", "bos_step_host", "bos_get_stats", "bos_triangulate", "bos_pattern_info_get",
     "bos_download_pattern", "bos_download_blocks", "bos_download_csc", "bos_download_delta", "bos_upload_delta",
     "bos_edge_terms", "bos_host_pattern_create", "bos_host_pattern_destroy", "bos_host_pattern_info",
-    "bos_host_pattern_get", "bos_host_pattern_checksum", "bos_host_pattern_skyline", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
+    "bos_host_pattern_get", "bos_host_pattern_checksum", "bos_host_pattern_skyline", "bos_set_device_setup", "bos_last_setup_ms",
+    "bos_pattern_checksum", "bos_device_resolve_ids", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
     "bos_set_edge_shard", "bos_get_edge_shard", "bos_batch_create", "bos_batch_destroy", "bos_batch_set_states",
     "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error",
     "bos_triangulate_landmarks", "bos_eval_bearing_edges", "bos_eval_odometry_edges", "bos_step_lm",
@@ -101,6 +102,10 @@ def lib():
         L.bos_nccl_unique_id.argtypes = [C.c_char_p]
         L.bos_comm_init.argtypes = [vp, i32, i32, C.c_char_p]
         L.bos_set_reduce_mode.argtypes = [vp, i32]
+        L.bos_set_device_setup.argtypes = [vp, i32]
+        L.bos_last_setup_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.bos_pattern_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.bos_device_resolve_ids.argtypes = [i32, i32, vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32)]
         L.bos_set_edge_shard.argtypes = [vp, i32, i32]
         L.bos_get_edge_shard.argtypes = [vp] + [C.POINTER(i64)] * 4
         L.bos_batch_create.argtypes = [C.POINTER(Options), i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(vp)]
@@ -277,6 +282,20 @@ class Context:
     def set_reduce_mode(self, mode):
         self._ck(self.L.bos_set_reduce_mode(self.h, int(mode)))
 
+    def set_device_setup(self, on=True):
+        """Build the bearing-edge core of the pattern on the device at the next upload_problem."""
+        self._ck(self.L.bos_set_device_setup(self.h, 1 if on else 0))
+
+    def last_setup_ms(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.bos_last_setup_ms(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def pattern_checksum(self):
+        out = C.c_uint64()
+        self._ck(self.L.bos_pattern_checksum(self.h, C.byref(out)))
+        return int(out.value)
+
     def set_edge_shard(self, rank, nranks):
         self._ck(self.L.bos_set_edge_shard(self.h, int(rank), int(nranks)))
 
@@ -292,6 +311,22 @@ def nccl_unique_id():
     if rc != OK:
         raise BosError(rc, "bos_nccl_unique_id failed")
     return buf.raw
+
+
+def device_resolve_ids(pose_ids, b_pose_id, b_lm_id, o_src_id, o_dst_id, device=0):
+    """id -> stix of every edge end point on the device; returns (b_pose, b_lm, o_src, o_dst, lm_ids).  Unknown pose id: BosError."""
+    L = lib()
+    pose_ids = _c(pose_ids, np.int32); b_pose_id = _c(b_pose_id, np.int32); b_lm_id = _c(b_lm_id, np.int32)
+    o_src_id = _c(o_src_id, np.int32); o_dst_id = _c(o_dst_id, np.int32)
+    Eb, Eo = len(b_pose_id), len(o_src_id)
+    bp = np.zeros(Eb, np.int32); bl = np.zeros(Eb, np.int32); os_ = np.zeros(Eo, np.int32); od = np.zeros(Eo, np.int32)
+    lm = np.zeros(max(Eb, 1), np.int32)
+    nl = C.c_int32(0)
+    rc = L.bos_device_resolve_ids(int(device), len(pose_ids), _ptr(pose_ids), Eb, _ptr(b_pose_id), _ptr(b_lm_id), Eo, _ptr(o_src_id), _ptr(o_dst_id),
+                                  _ptr(bp), _ptr(bl), _ptr(os_), _ptr(od), _ptr(lm), C.byref(nl))
+    if rc != OK:
+        raise BosError(rc, "bos_device_resolve_ids")
+    return bp, bl, os_, od, lm[:nl.value].copy()
 
 
 class HostPattern:

@@ -308,7 +308,17 @@ struct HostPattern {
     std::string error;
 };
 void build_csc(HostPattern& P);
+// The bearing-edge core of the pattern (sorted edge order, block slots, CSR-of-blocks row pointers, landmark-major order, triangulation rows):
+// built on the host by build_pattern's first phases, or on the device (setup.cu) and handed to build_pattern.
+struct PatternCore {
+    bool valid = false, slots_identity = true;
+    std::vector<int> b_perm, b_pose, b_lm, b_slot, slot_pose, slot_lm, pose_ptr, lm_ptr, lm_order, lm_order_pose, lm_order_lm, tri_ptr, tri_edge, epose_ptr;
+};
 int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm,
-                  int64_t Eo, const int32_t* o_src, const int32_t* o_dst, int pcg_chunks = 148);
+                  int64_t Eo, const int32_t* o_src, const int32_t* o_dst, int pcg_chunks = 148, PatternCore* core = nullptr);
+int device_pattern_core(PatternCore& core, int NP, int NL, int64_t Eb, const int32_t* b_pose, const int32_t* b_lm, cudaStream_t st, std::string& err);
+int device_resolve_ids(int NP, const int32_t* pose_ids, int64_t Eb, const int32_t* b_pose_id, const int32_t* b_lm_id, int64_t Eo, const int32_t* o_src_id,
+                       const int32_t* o_dst_id, int32_t* b_pose, int32_t* b_lm, int32_t* o_src, int32_t* o_dst, int32_t* lm_ids, int32_t* NL_out, cudaStream_t st,
+                       std::string& err);
 
 }  // namespace bos

@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -111,6 +112,8 @@ struct bos_ctx {
     // multi-GPU
     int rank = 0, nranks = 1, reduce_mode = 0;
     int robust_mode = 0;          // 0 = reference robust kernel, 1 = IRLS (bos_set_robust_mode)
+    int device_setup = 0;         // 1: the bearing-edge core of the pattern is built on the device (bos_set_device_setup)
+    double setup_ms[2] = {0.0, 0.0};   // last upload: device core, host remainder
     nccl_comm_t comm = nullptr;
     ShardRange shard;
     std::vector<int> own_p0;              // [nranks + 1] first pose owned by each rank's tiles (a pose belongs to the tile its run starts in)
@@ -896,8 +899,18 @@ int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t 
     c->have_problem = false; c->delta_valid = false; c->dense_ready = false; c->pcg_ready = false; c->sky_ready = false;
     c->lm_pose_bak = nullptr; c->lm_lm_bak = nullptr;
     c->mem.release();
-    if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count) != 0)
+    PatternCore core;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (c->device_setup) {
+        std::string err;
+        const int rcd = device_pattern_core(core, NP, NL, Eb, b_pose, b_lm, c->stream, err);
+        if (rcd != 0) return fail(c, rcd == 1 ? BOS_ERR_INVALID : BOS_ERR_CUDA, err);
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count, c->device_setup ? &core : nullptr) != 0)
         return fail(c, BOS_ERR_INVALID, c->P.error);
+    c->setup_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    c->setup_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     int rc = c->f64() ? upload_impl<double>(c, b_z, b_omega, o_z, o_omega) : upload_impl<float>(c, b_z, b_omega, o_z, o_omega);
     if (rc) return rc;
     compute_shard(c);
@@ -1234,9 +1247,39 @@ int bos_host_pattern_skyline(const bos_host_pattern* p, int32_t* panel_end, int3
     if (panel_end) std::copy(w.sky_panel_end.begin(), w.sky_panel_end.end(), panel_end);
     return BOS_OK;
 }
+static uint64_t pattern_checksum(const HostPattern& P);
 int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out) {
     if (!p || !out) return BOS_ERR_INVALID;
-    const HostPattern& P = p->P;
+    *out = pattern_checksum(p->P);
+    return BOS_OK;
+}
+int bos_pattern_checksum(bos_ctx* c, uint64_t* out) {
+    if (!c || !out) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "pattern_checksum before upload_problem");
+    *out = pattern_checksum(c->P);
+    return BOS_OK;
+}
+int bos_set_device_setup(bos_ctx* c, int on) {
+    if (!c) return BOS_ERR_INVALID;
+    c->device_setup = on ? 1 : 0;
+    return BOS_OK;
+}
+int bos_last_setup_ms(const bos_ctx* c, double* device_core_ms, double* host_ms) {
+    if (!c) return BOS_ERR_INVALID;
+    if (device_core_ms) *device_core_ms = c->setup_ms[0];
+    if (host_ms) *host_ms = c->setup_ms[1];
+    return BOS_OK;
+}
+int bos_device_resolve_ids(int device, int NP, const int32_t* pose_ids, int64_t Eb, const int32_t* b_pose_id, const int32_t* b_lm_id, int64_t Eo,
+                           const int32_t* o_src_id, const int32_t* o_dst_id, int32_t* b_pose, int32_t* b_lm, int32_t* o_src, int32_t* o_dst,
+                           int32_t* lm_ids, int32_t* NL_out) {
+    if (!pose_ids || (Eb > 0 && (!b_pose_id || !b_lm_id || !b_pose || !b_lm)) || (Eo > 0 && (!o_src_id || !o_dst_id || !o_src || !o_dst))) return BOS_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return BOS_ERR_CUDA;
+    std::string err;
+    const int rc = device_resolve_ids(NP, pose_ids, Eb, b_pose_id, b_lm_id, Eo, o_src_id, o_dst_id, b_pose, b_lm, o_src, o_dst, lm_ids, NL_out, 0, err);
+    return rc == 0 ? BOS_OK : (rc == 1 ? BOS_ERR_INVALID : BOS_ERR_CUDA);
+}
+static uint64_t pattern_checksum(const HostPattern& P) {
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](const void* data, size_t bytes) {
         const unsigned char* b = static_cast<const unsigned char*>(data);
@@ -1257,8 +1300,7 @@ int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out) {
     vec(P.pc_row_pose); vec(P.pc_goff); vec(P.pc_cl_ptr); vec(P.pc_cl_row); vec(P.pc_emap); vec(P.pc_nbr); vec(P.pc_nslot); vec(P.pc_ncnt);
     vec(P.lc_gptr); vec(P.lc_goff); vec(P.lc_emap); vec(P.sh_ptr); vec(P.sh_src); vec(P.sh_ell); vec(P.lc_row); vec(P.lc_k); vec(P.sh_first);
     vec(P.pc_loc); vec(P.tile_ptr); vec(P.tg_lm); vec(P.tg_eptr); vec(P.epose_ptr); vec(P.tg_edge); vec(P.touched);
-    *out = h;
-    return BOS_OK;
+    return h;
 }
 int bos_host_pattern_info(const bos_host_pattern* p, bos_pattern_info* out) {
     if (!p || !out) return BOS_ERR_INVALID;
