@@ -707,7 +707,7 @@ def test_irls_extension_matches_its_oracle_restatement(built_lib, solver):
 
 def test_sparse_skyline_cholesky_matches_dense_and_oracle(built_lib):
     """BOS_SOLVER_SPARSE_CHOLESKY on a 3000-pose trajectory world, where the skyline is a real envelope (38 % of the triangle,
-    several outer panels, windows that end inside the matrix): the increment equals the dense Cholesky's to 1e-10 and the oracle's dense
+    several outer panels, windows that end inside the matrix): the increment equals the dense Cholesky's to 1e-10 and the oracle's sparse
     LDL^T to 1e-8, solves the GPU's own normal equations, and four GN steps follow the dense path."""
     import scipy.sparse as sp
     w, pr = synth_problem(3000, 600, 30000, seed=3)
@@ -732,7 +732,8 @@ def test_sparse_skyline_cholesky_matches_dense_and_oracle(built_lib):
             assert s.solver_status == 0
         outs[name] = (d, ctx.get_state(), s.ms_solve)
         ctx.close()
-    o.linearize(); o.solve(0)
+    o.linearize()
+    assert o.solve_sparse()["status"] == 0          # the reference's solver restated (sparse LDL^T, minimum-degree ordering)
     od = o.delta()
     assert np.abs(outs["sparse"][0] - outs["dense"][0]).max() <= 1e-10 * np.abs(od).max()
     assert np.abs(outs["sparse"][0] - od).max() <= 1e-8 * np.abs(od).max()

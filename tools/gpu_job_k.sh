@@ -1,5 +1,5 @@
 #!/bin/bash
 set -u
-O=gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_sizes.py -m gpu -x -q -k "sparse or solve_and_update or config3 or dense" -s 2>&1 | grep -E "passed|failed|^E  |dense .* ms|synth-100k" | head -20
-timeout 600 python tools/sweep_solvers.py > $O/k_sweep.jsonl 2> $O/k_sweep.err; cat $O/k_sweep.jsonl; tail -3 $O/k_sweep.err
+BOS_LIB_PATH=tools/_variants/libbos_b200_timing.so timeout 200 python tools/prof_solve.py 200000 50000 2000000 60 0 0 2>&1 | tail -5
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/k_launches.csv python tools/prof_solve.py 200000 50000 2000000 60 0 0 > /dev/null 2>&1
+python tools/launch_list.py gpurun_out/k_launches.csv 2>&1 | tail -14
