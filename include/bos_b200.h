@@ -76,8 +76,9 @@ typedef struct bos_options {
                                  hat per chunk); rounded so that segments are whole groups of 32 poses, at most 8 */
     int pcg_coarse_refresh;   /* the coarse operator's inverse is kept across GN steps and rebuilt every this many solves (also whenever
                                  the state is replaced through the API or the CG iteration count drifts up by 25 %); 0 = default (8),
-                                 1 = rebuild for every solve.  Any SPD coarse operator is a valid preconditioner: only the iteration
-                                 count depends on it, never the solution */
+                                 1 = rebuild for every solve.  The period doubles (up to 8x) each time a scheduled rebuild saves fewer than
+                                 two CG iterations -- near convergence A_c hardly changes -- and falls back when one pays again.  Any SPD
+                                 coarse operator is a valid preconditioner: only the iteration count depends on it, never the solution */
     int reserved[4];
 } bos_options;
 

@@ -478,7 +478,7 @@ int ensure_pcg(bos_ctx* c) {
             w.c_bw = (bw <= 158) ? std::min(bw, w.c_nc - 1) : 0;
             if (w.c_bw < 1 && w.c_nc > 1) w.c_bw = (bw <= 158) ? 1 : 0;
             w.coarse_refresh = c->opt.pcg_coarse_refresh > 0 ? c->opt.pcg_coarse_refresh : 8;
-            w.coarse_valid = false; w.coarse_stale = false; w.coarse_age = 0;
+            w.coarse_valid = false; w.coarse_stale = false; w.coarse_age = 0; w.coarse_period = 0; w.coarse_its_last = 0;
         }
         w.cA = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
         w.c_ld = (w.c_nc + 3) / 4 * 4;

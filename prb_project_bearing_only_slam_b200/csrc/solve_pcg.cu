@@ -1829,7 +1829,11 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     // coarse operator A_c = P^T S P, its Cholesky factor and explicit inverse.  Any SPD coarse operator makes a valid preconditioner, so A_c^-1 is
     // kept across GN steps and refreshed every w.coarse_refresh solves, after the state was replaced from outside, or when the CG iteration
     // count drifts above what it was right after the last refresh (coarse_stale).
-    const bool refresh = precond == 0 && (!w.coarse_valid || w.coarse_age >= w.coarse_refresh || w.coarse_stale);
+    // The period starts at pcg_coarse_refresh solves and DOUBLES (up to 8x) every time a scheduled refresh did not pay -- near convergence the
+    // state, hence A_c, hardly changes; a refresh that does cut the iteration count, a stale flag or an invalidation resets it.
+    if (w.coarse_period < w.coarse_refresh) w.coarse_period = w.coarse_refresh;
+    const bool refresh = precond == 0 && (!w.coarse_valid || w.coarse_age >= w.coarse_period || w.coarse_stale);
+    const bool scheduled = refresh && w.coarse_valid && !w.coarse_stale;
     if (refresh) {
         const int nc = w.c_nc;
         cudaMemsetAsync(w.cA, 0, sizeof(double) * (size_t)nc * nc, st);
@@ -1872,8 +1876,14 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     if (launches) *launches = nl;
     if (precond == 0) {   // iteration count right after a refresh is the yardstick for the following, lagged solves
         const int its = (int)host_scal[SC_ITER];
-        if (refresh) w.coarse_its_ref = its;
-        else if (its > w.coarse_its_ref + w.coarse_its_ref / 4 + 4) w.coarse_stale = true;
+        if (refresh) {
+            w.coarse_its_ref = its;
+            if (scheduled && w.coarse_refresh > 1) {   // did the rebuilt operator save at least two iterations over the one it replaced?
+                if (its + 2 > w.coarse_its_last) w.coarse_period = std::min(2 * w.coarse_period, 8 * w.coarse_refresh);
+                else w.coarse_period = w.coarse_refresh;
+            } else if (!scheduled) w.coarse_period = w.coarse_refresh;
+        } else if (its > w.coarse_its_ref + w.coarse_its_ref / 4 + 4) w.coarse_stale = true;
+        w.coarse_its_last = its;
         if (host_scal[SC_BAD] != 0.0) w.coarse_valid = false;
     }
     return host_scal[SC_BAD] != 0.0 ? 1 : 0;

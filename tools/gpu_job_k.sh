@@ -1,5 +1,9 @@
 #!/bin/bash
 set -u
-BOS_LIB_PATH=tools/_variants/libbos_b200_timing.so timeout 200 python tools/prof_solve.py 200000 50000 2000000 60 0 0 2>&1 | tail -5
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/k_launches.csv python tools/prof_solve.py 200000 50000 2000000 60 0 0 > /dev/null 2>&1
-python tools/launch_list.py gpurun_out/k_launches.csv 2>&1 | tail -14
+O=gpurun_out
+timeout 400 python bench.py --steps 20 --warmup 5 > $O/k_bench.json 2> $O/k_bench.err; python - <<'P'
+import json
+d=json.load(open('gpurun_out/k_bench.json'))
+print(d['value'], d['ms_per_step'], d['phases_ms'], d['pcg_iterations'], d['e2e']['value'], d['roofline']['frac'], d['roofline_linearize']['frac'], d['pcg_iterations_per_step'])
+P
+timeout 600 python -m pytest tests -m gpu -x -q -k "pcg or lagged or refresh or coarse or run_to_run" 2>&1 | tail -3
