@@ -54,6 +54,7 @@ struct IOracle {
     virtual double time_linearize_literal(int reps) = 0;
     virtual double literal_max_diff() = 0;
     virtual void set_wrap_branch(int n, const int* edges, const int* signs) = 0;
+    virtual void set_wrap_branch_tol(double tol) = 0;
 };
 
 template <class T>
@@ -214,6 +215,7 @@ struct Impl : IOracle {
         (void)bsave;
         return worst;
     }
+    void set_wrap_branch_tol(double tol) override { o.wrap_branch_tol = tol; }
     void set_wrap_branch(int n, const int* edges, const int* signs) override {
         o.wrap_branch.clear();
         for (int i = 0; i < n; i++) o.wrap_branch[edges[i]] = signs[i] >= 0 ? 1 : -1;
@@ -316,6 +318,7 @@ int orc_solve_sparse(void* h, double deadline_s, double* info8) { return H(h)->s
 double orc_time_linearize_literal(void* h, int reps) { return H(h)->time_linearize_literal(reps); }
 double orc_literal_max_diff(void* h) { return H(h)->literal_max_diff(); }
 void orc_set_wrap_branch(void* h, int n, const int* edges, const int* signs) { H(h)->set_wrap_branch(n, edges, signs); }
+void orc_set_wrap_branch_tol(void* h, double tol) { H(h)->set_wrap_branch_tol(tol); }
 double orc_smallest_angle(int use_double, double a) { return use_double ? smallest_angle<double>(a) : (double)smallest_angle<float>((float)a); }
 double orc_normalized_angle(int use_double, double a) { return use_double ? normalized_angle<double>(a) : (double)normalized_angle<float>((float)a); }
 void orc_colpiv_solve(int use_double, int M, const double* A, const double* b, double* out2) {

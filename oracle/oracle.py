@@ -48,6 +48,7 @@ def lib():
         L.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_set_params.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.orc_set_irls.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_wrap_branch_tol.argtypes = [C.c_void_p, C.c_double]
         L.orc_solve_sparse.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.orc_time_linearize_literal.restype = C.c_double
         L.orc_time_linearize_literal.argtypes = [C.c_void_p, C.c_int]
@@ -208,9 +209,10 @@ class Oracle:
     def literal_max_diff(self):
         return float(self.L.orc_literal_max_diff(self.h))
 
-    def set_wrap_branch(self, edges, signs):
-        """Test hook: put the bearing edges `edges` (residual within 1e-9 of +-pi) on the branch `signs` (+1 / -1)."""
+    def set_wrap_branch(self, edges, signs, tol=1e-9):
+        """Test hook: put the bearing edges `edges` (residual within `tol` of +-pi) on the branch `signs` (+1 / -1)."""
         e = np.ascontiguousarray(edges, np.int32); s = np.ascontiguousarray(signs, np.int32)
+        self.L.orc_set_wrap_branch_tol(self.h, float(tol))
         self.L.orc_set_wrap_branch(self.h, len(e), _p(e), _p(s))
 
     def delta(self):
