@@ -9,15 +9,18 @@
 //                   framework/definitions.hpp:17-37) and evaluation order.
 //   Oracle<double>  the FP64 parity target of the CUDA kernels (same formulas).
 //
-// PARITY PIN STATUS: "parity unpinned by the reference".  The reference cannot be
-// compiled here (Eigen3 and OpenCV C++ are absent, no network) and its tests hold
-// no assertions.  The oracle is pinned instead against every soft pin the reference
-// offers (tests/test_oracle_pins.py): the predict_bearing known answers
-// (tests/solver_stuff.cpp:25-38), the analytic-vs-numeric Jacobian statistics
-// (tests/solver_stuff.cpp:82-88,156-162), predict_odometry == measurement on the
-// dead-reckoned initial guess (tests/solver_stuff.cpp:93-114), the single-observation
-// landmarks 69/112/114 (slam/triangulation.cpp:41), fixed pose 1498, the README's
-// "~20 iterations" (README.md:22-24), and an independent numpy restatement.
+// PARITY PIN STATUS: pinned by the reference's own code, run here.  The reference needs Eigen3 and OpenCV C++ (absent from this
+// image, no network), so it cannot be built against them; `make -C oracle ref` compiles its UNMODIFIED hot-path sources where they lie
+// under /root/reference against a stand-in for the Eigen / OpenCV calls they make (oracle/eigen_standin, oracle/ref_driver.cpp ->
+// oracle/_ref/libbos_ref.so; standin.hpp lists what the stand-in supplies -- the arithmetic behind the operators, an LDL^T, a
+// column-pivoting QR -- and what therefore remains unpinned: Eigen's own rounding and its QR rank decisions).  tests/test_ref_build.py:
+// from the same state Oracle<float> and that build agree BIT FOR BIT on every per-edge error, Jacobian and on b, to 1e-6 on H, on the
+// sparsity pattern exactly, and along the 20 / 50-iteration trajectories of the bundled datasets and two random worlds;
+// Oracle<double> agrees with it to float rounding.  Its results are committed as tests/golden/ref_*.npz
+// (tests/golden/make_ref_golden.py).  The soft pins the reference itself offers stay in tests/test_oracle_pins.py: the predict_bearing
+// known answers (tests/solver_stuff.cpp:25-38), the analytic-vs-numeric Jacobian statistics (:82-88, 156-162), predict_odometry ==
+// measurement on the dead-reckoned initial guess (:93-114), the single-observation landmarks 69/112/114 (slam/triangulation.cpp:41),
+// fixed pose 1498, the README's "~20 iterations" (README.md:22-24), and an independent numpy restatement.
 //
 // Third-party arithmetic restated (Eigen3 >= 3.3, unpinned; OpenCV constants):
 //   Rotation2D::smallestAngle, Rotation2D(Matrix2), Rotation2D::matrix,
