@@ -539,6 +539,22 @@ def run_ours(args):
                      "device_setup": bool(args.device_setup)},
         "clocks": clocks,
     }
+    if world > 1:
+        # NCCL combine of the sharded H, b against the NVLink roofline (B200_PROFILING.md: 770 GB/s measured peer copy per direction per GPU,
+        # 900 nominal).  Bytes a rank must RECEIVE per step: a ring / tree all-reduce moves 2 (N-1)/N of the summed payload through every
+        # GPU's link, a gather brings in the (N-1)/N of the gathered arrays that other ranks own.
+        f = (world - 1) / world
+        n_pp, Ntot = int(pi.n_hpp_off), int(pi.N)
+        summed, gathered = {0: (int(pi.vals_len), 0), 1: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 6 * pr.Eb),
+                            2: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 0), 3: (5 * pr.NL, 9 * pr.NP)}[args.reduce_mode]
+        nv_bytes = (2 * f * summed + f * gathered) * S
+        nv_peak = 770.0
+        line["roofline_combine"] = {"kernel": "ncclAllReduce / ncclBroadcast of the partial H, b (reduce_mode %d)" % args.reduce_mode, "bound": "nvlink",
+                                    "achieved": nv_bytes / (ms_allreduce * 1e-3) / 1e9, "peak": nv_peak, "unit": "GB/s",
+                                    "frac": nv_bytes / (ms_allreduce * 1e-3) / 1e9 / nv_peak, "bytes_per_rank_per_step": int(nv_bytes),
+                                    "ms_per_step": ms_allreduce, "summed_scalars": int(summed), "gathered_scalars": int(gathered),
+                                    "peak_source": "B200_PROFILING.md: measured peer copy, GB/s per direction per GPU (900 nominal)",
+                                    "note": "latency bound at this size: %d collectives of a few MB per step" % (2 + 2 * world if args.reduce_mode == 3 else 1)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(w, pr, budget_s=args.cpu_budget)
     print(json.dumps(line), file=args.out, flush=True)
