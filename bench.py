@@ -396,6 +396,8 @@ def run_ours(args):
         uid = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
+        if args.reduce_mode == 4:      # fused build + combine over NVLink peer memory: the ranks map each other's value buffers (CUDA IPC)
+            ctx.peer_connect(dist)
         ctx.set_reduce_mode(args.reduce_mode)
     # initial guess: generated poses + landmarks triangulated ON THE DEVICE (K8)
     P0 = xyt_to_xycs(w["poses_init"])
@@ -518,7 +520,8 @@ def run_ours(args):
                    "pcg_rtol": args.pcg_rtol, "pcg_coarse": "4 nodes per chunk, inverse kept for 8 solves (the period doubles while rebuilds stop paying)" if solver == capi.SOLVER_PCG and args.pcg_precond == 0 else None,
                    "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
                    (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)",
-                           3: "ownership: allreduce(landmark blocks, b_l) + gather of the owned pose ranges"}[args.reduce_mode]) if world > 1 else "single gpu",
+                           3: "ownership: allreduce(landmark blocks, b_l) + gather of the owned pose ranges",
+                           4: "ownership, no collective: the bearing kernel stores / adds into every rank's replica over NVLink peer memory"}[args.reduce_mode]) if world > 1 else "single gpu",
                    "l2": "no flush: value + edge buffers (%.0f MB) exceed the 126 MB L2" % ((int(pi.vals_len) * S + pr.Eb * 24) / 1e6)},
         "edges_linearized_per_s": E / (ms_lin * 1e-3),
         "phases_ms": {"linearize": ms_lin_kernel, "allreduce": ms_allreduce, "solve": ms_solve, "update": ms_update},
@@ -546,15 +549,25 @@ def run_ours(args):
         f = (world - 1) / world
         n_pp, Ntot = int(pi.n_hpp_off), int(pi.N)
         summed, gathered = {0: (int(pi.vals_len), 0), 1: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 6 * pr.Eb),
-                            2: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 0), 3: (5 * pr.NL, 9 * pr.NP)}[args.reduce_mode]
-        nv_bytes = (2 * f * summed + f * gathered) * S
+                            2: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 0), 3: (5 * pr.NL, 9 * pr.NP), 4: (5 * pr.NL, 9 * pr.NP)}[args.reduce_mode]
         nv_peak = 770.0
-        line["roofline_combine"] = {"kernel": "ncclAllReduce / ncclBroadcast of the partial H, b (reduce_mode %d)" % args.reduce_mode, "bound": "nvlink",
-                                    "achieved": nv_bytes / (ms_allreduce * 1e-3) / 1e9, "peak": nv_peak, "unit": "GB/s",
-                                    "frac": nv_bytes / (ms_allreduce * 1e-3) / 1e9 / nv_peak, "bytes_per_rank_per_step": int(nv_bytes),
-                                    "ms_per_step": ms_allreduce, "summed_scalars": int(summed), "gathered_scalars": int(gathered),
-                                    "peak_source": "B200_PROFILING.md: measured peer copy, GB/s per direction per GPU (900 nominal)",
-                                    "note": "latency bound at this size: %d collectives of a few MB per step" % (2 + 2 * world if args.reduce_mode == 3 else 1)}
+        if args.reduce_mode == 4:
+            # fused: a rank's link carries OUT its owned pose blocks to the N-1 other replicas and (at least) its share of the landmark parts to
+            # each of them; there is no separate combine phase, so the time is the whole sharded build (both barriers included)
+            nv_bytes = (world - 1) * (gathered / world + summed / world) * S
+            t_comb = ms_lin
+            what = "k_linearize_bearing_persistent<peer>: stores / REDs into every replica over NVLink + two cross-GPU barriers (reduce_mode 4)"
+            note = "fused with the build: time = the whole sharded build, bytes = the lower bound a rank must send (one landmark part per landmark and peer)"
+        else:
+            nv_bytes = (2 * f * summed + f * gathered) * S
+            t_comb = ms_allreduce
+            what = "ncclAllReduce / ncclBroadcast of the partial H, b (reduce_mode %d)" % args.reduce_mode
+            note = "latency bound at this size: %d collectives of a few MB per step" % (2 + 2 * world if args.reduce_mode == 3 else 1)
+        line["roofline_combine"] = {"kernel": what, "bound": "nvlink",
+                                    "achieved": nv_bytes / (t_comb * 1e-3) / 1e9, "peak": nv_peak, "unit": "GB/s",
+                                    "frac": nv_bytes / (t_comb * 1e-3) / 1e9 / nv_peak, "bytes_per_rank_per_step": int(nv_bytes),
+                                    "ms_per_step": t_comb, "summed_scalars": int(summed), "gathered_scalars": int(gathered),
+                                    "peak_source": "B200_PROFILING.md: measured peer copy, GB/s per direction per GPU (900 nominal)", "note": note}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(w, pr, budget_s=args.cpu_budget)
     print(json.dumps(line), file=args.out, flush=True)
@@ -641,7 +654,7 @@ def main():
     ap.add_argument("--pcg-max-iters", type=int, default=20000)
     ap.add_argument("--pcg-precond", type=int, default=0, choices=[0, 1, 2],
                     help="0 chain (block-tridiagonal) + coarse-space preconditioner, 1 3x3 block-Jacobi, 2 chain only")
-    ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 2 for the PCG workloads, 1 for the dense ones")
+    ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 3 (ownership combine over NCCL) for the PCG workloads, 1 for the dense ones; 4 = fused build + combine over NVLink peer memory (measured slower, DESIGN.md section 6)")
     ap.add_argument("--ref-solver", default="auto", choices=["auto", "ldlt", "superlu"],
                     help="reference arm: ldlt = the oracle's restatement of Eigen::SimplicialLDLT, superlu = scipy's SuperLU; auto = ldlt when "
                          "its symbolic phase predicts under a minute per factorisation, else superlu")

@@ -250,8 +250,18 @@ BOS_API int bos_comm_init(bos_ctx* ctx, int rank, int nranks, const char* uid128
  * per-edge factors (bos_download_blocks / bos_download_csc then see this rank's pose-landmark blocks only); 3: ownership-based
  * combine: a pose's diagonal block and rhs are complete on the rank whose edge tiles own the pose (the tile its bearing run starts in),
  * every rank computes every pose-pose block itself, so only the landmark blocks and b_l are summed (5 scalars per landmark) and the
- * owned pose ranges are gathered (grouped broadcasts); pose-landmark blocks stay rank-local as in mode 2. */
+ * owned pose ranges are gathered (grouped broadcasts); pose-landmark blocks stay rank-local as in mode 2;
+ * 4: mode 3's ownership with NO collective: the bearing kernel itself stores every owned pose block and adds every landmark part straight into
+ * EVERY rank's replica through NVLink peer mappings (bos_peer_open), between two cross-GPU barriers -- the combine rides on the build. */
 BOS_API int bos_set_reduce_mode(bos_ctx* ctx, int reduce_mode);
+/* reduce_mode 4 plumbing (ranks = processes of ONE NVSwitch box, at most 8).  After bos_upload_problem and bos_comm_init / bos_set_edge_shard:
+ * every rank exports the CUDA IPC handle of its value buffer (+ byte offset inside the underlying allocation), the host program exchanges them
+ * (any transport: the Python wrapper uses torch.distributed.all_gather_object) and every rank opens all of them: handles = nranks x
+ * BOS_IPC_HANDLE_BYTES, offsets = nranks entries, both indexed by rank (the own entry is ignored).  Collective: from then on every rank must
+ * call bos_linearize / bos_step the same number of times.  A rank that never arrives makes the barrier time out: BOS_ERR_NCCL from bos_get_stats. */
+#define BOS_IPC_HANDLE_BYTES 64
+BOS_API int bos_peer_export(bos_ctx* ctx, void* handle64, int64_t* offset);
+BOS_API int bos_peer_open(bos_ctx* ctx, const void* handles, const int64_t* offsets);
 /* Without NCCL: shard bookkeeping only (used by the host-side tests): this rank linearizes its
  * contiguous range of the pose-sorted edges. */
 BOS_API int bos_set_edge_shard(bos_ctx* ctx, int rank, int nranks);

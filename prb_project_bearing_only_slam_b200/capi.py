@@ -16,6 +16,7 @@ PRECISION_F64, PRECISION_F32 = 0, 1
 SOLVER_AUTO, SOLVER_DENSE_CHOLESKY, SOLVER_PCG, SOLVER_SPARSE_CHOLESKY = 0, 1, 2, 3
 ROBUST_REFERENCE, ROBUST_IRLS = 0, 1
 NCCL_UID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 class Options(C.Structure):
@@ -49,7 +50,7 @@ SYMBOLS = [
     "bos_download_pattern", "bos_download_blocks", "bos_download_csc", "bos_download_delta", "bos_upload_delta",
     "bos_edge_terms", "bos_host_pattern_create", "bos_host_pattern_destroy", "bos_host_pattern_info",
     "bos_host_pattern_get", "bos_host_pattern_checksum", "bos_host_pattern_skyline", "bos_set_device_setup", "bos_last_setup_ms",
-    "bos_pattern_checksum", "bos_device_resolve_ids", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode",
+    "bos_pattern_checksum", "bos_device_resolve_ids", "bos_host_edge_shard", "bos_nccl_unique_id", "bos_comm_init", "bos_set_reduce_mode", "bos_peer_export", "bos_peer_open",
     "bos_set_edge_shard", "bos_get_edge_shard", "bos_batch_create", "bos_batch_destroy", "bos_batch_set_states",
     "bos_batch_get_states", "bos_batch_step", "bos_batch_step_device", "bos_batch_last_error",
     "bos_triangulate_landmarks", "bos_eval_bearing_edges", "bos_eval_odometry_edges", "bos_step_lm",
@@ -102,6 +103,8 @@ def lib():
         L.bos_nccl_unique_id.argtypes = [C.c_char_p]
         L.bos_comm_init.argtypes = [vp, i32, i32, C.c_char_p]
         L.bos_set_reduce_mode.argtypes = [vp, i32]
+        L.bos_peer_export.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
+        L.bos_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
         L.bos_set_device_setup.argtypes = [vp, i32]
         L.bos_last_setup_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.bos_pattern_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -281,6 +284,26 @@ class Context:
 
     def set_reduce_mode(self, mode):
         self._ck(self.L.bos_set_reduce_mode(self.h, int(mode)))
+
+    def peer_export(self):
+        """(CUDA IPC handle of the value buffer, byte offset inside its allocation) -- reduce_mode 4, see bos_peer_export."""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        off = C.c_int64()
+        self._ck(self.L.bos_peer_export(self.h, buf, C.byref(off)))
+        return buf.raw, int(off.value)
+
+    def peer_open(self, handles, offsets):
+        """handles / offsets of ALL ranks, indexed by rank (what every rank's peer_export returned)."""
+        blob = b"".join(handles)
+        arr = (C.c_int64 * len(offsets))(*[int(o) for o in offsets])
+        self._ck(self.L.bos_peer_open(self.h, blob, arr))
+
+    def peer_connect(self, dist):
+        """Exchange the IPC handles over torch.distributed and open the peers' value buffers (collective)."""
+        mine = self.peer_export()
+        everyone = [None] * dist.get_world_size()
+        dist.all_gather_object(everyone, mine)
+        self.peer_open([h for h, _ in everyone], [o for _, o in everyone])
 
     def set_device_setup(self, on=True):
         """Build the bearing-edge core of the pattern on the device at the next upload_problem."""

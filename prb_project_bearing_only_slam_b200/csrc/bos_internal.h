@@ -27,6 +27,7 @@ constexpr int kPcgThreads = BOS_PCG_THREADS;       // one persistent CTA per SM
 #define BOS_ELL_LANES 8
 #endif
 constexpr int kEllLanesL = BOS_ELL_LANES;          // lanes per landmark row in the landmark-major layout
+constexpr int kMaxPeers = 8;                        // ranks of one NVSwitch box (reduce_mode 4)
 constexpr int kShareEll = 8;                       // sharers of a (chunk, landmark) kept in the transposed list (the rest through the CSR list)
 
 // Typed view of everything a kernel needs.  One instance per context, built after upload.
@@ -122,7 +123,25 @@ struct Dev {
     int n_cut = 0;
     double* stats = nullptr;  // [8] chi2_b, chi2_o, over_b, over_o, delta_inf(bits), status, state digest (k_update), -
     S* delta = nullptr;       // [N]
+    // fused linearize + combine over NVLink peer memory (reduce_mode 4): every rank's value buffer and statistics, own included, mapped
+    // through CUDA IPC; the bearing kernel stores / REDs every block that must be combined straight into all replicas
+    double* stats_k2 = nullptr;      // where the odometry kernel adds its statistics (stats, or the scratch the peer barrier publishes)
+    int npeer = 0;
+    S* pv[kMaxPeers] = {};
+    double* pstats[kMaxPeers] = {};
 };
+
+// tail of the value-buffer allocation (8-byte units): statistics, the odometry kernel's share of them, peer barrier slots, error flag
+constexpr int kTailStats = 0, kTailStatsK2 = 8, kTailSlots = 16, kTailError = 16 + kMaxPeers, kTailWords = 64;
+struct PeerBarrier {
+    unsigned long long* slots[kMaxPeers];   // slots[r]: rank r's slot array (own included); rank q signals slots[r][q]
+    double* pstats[kMaxPeers];
+    const double* publish;                  // non-null: add these 4 statistics (chi2_o, over_o at [1], [3]) to every replica before signalling
+    unsigned long long* error;              // local flag, set when the wait timed out
+    int n, rank;
+    unsigned long long epoch;
+};
+int launch_peer_barrier(const PeerBarrier& pb, cudaStream_t st);
 
 struct ShardRange {
     int b_begin = 0, b_end = 0, o_begin = 0, o_end = 0;
@@ -131,7 +150,7 @@ struct ShardRange {
 // ---- launchers (one translation unit each) -------------------------------------------------------
 template <typename S>
 int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping, double damping_here,
-                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st, bool multi_rank, int rank, bool all_hoff);
+                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st, bool multi_rank, int rank, bool all_hoff, int phases = 3);
 template <typename S>
 int launch_edge_terms(const Dev<S>& d, S* err_b, S* jac_b, S* err_o, S* jac_o, cudaStream_t st);
 template <typename S>

@@ -115,6 +115,12 @@ struct bos_ctx {
     int device_setup = 0;         // 1: the bearing-edge core of the pattern is built on the device (bos_set_device_setup)
     double setup_ms[2] = {0.0, 0.0};   // last upload: device core, host remainder
     nccl_comm_t comm = nullptr;
+    // reduce_mode 4: the ranks' value buffers mapped into this process through CUDA IPC (bos_peer_export / bos_peer_open)
+    size_t tail_off = 0;                          // byte offset of the statistics / barrier tail inside the value-buffer allocation
+    unsigned char* peer_base[kMaxPeers] = {};     // value buffer of every rank (own included) in this process' address space
+    void* peer_opened[kMaxPeers] = {};            // what cudaIpcOpenMemHandle returned (to close)
+    bool peers_open = false;
+    unsigned long long peer_epoch = 0;
     ShardRange shard;
     std::vector<int> own_p0;              // [nranks + 1] first pose owned by each rank's tiles (a pose belongs to the tile its run starts in)
     int shard_chunk_b = 0;
@@ -300,8 +306,14 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     c->vals_prefix = ((size_t)P.N + 6 * (size_t)P.NP + 3 * (size_t)P.NL + 9 * (size_t)d.n_off + 7) / 8 * 8;  // Hpl planes 32-byte aligned
     c->hpl_padded = 6 * (size_t)d.hpl_ld;
     c->vals_len = c->vals_prefix + c->hpl_padded;
-    d.vals = m.get<S>(c->vals_prefix + c->hpl_padded);
-    d.stats = m.get<double>(8);
+    // one allocation: [ values | tail: statistics, odometry-share scratch, peer barrier slots, error flag ] -- the window the other ranks
+    // map through CUDA IPC in reduce_mode 4
+    c->tail_off = ((c->vals_prefix + c->hpl_padded) * sizeof(S) + 15) / 16 * 16;
+    unsigned char* vbase = m.get<unsigned char>(c->tail_off + kTailWords * 8);
+    d.vals = reinterpret_cast<S*>(vbase);
+    d.stats = vbase ? reinterpret_cast<double*>(vbase + c->tail_off) : nullptr;
+    d.stats_k2 = d.stats;
+    d.npeer = 0;
     d.Mv = m.get<S>(9 * (size_t)std::max(P.Eo, 1));
     d.delta = m.get<S>((size_t)P.N);
     c->d_single_obs = m.get<int>(1);
@@ -314,7 +326,7 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     // on the context's own (non-blocking) stream: a legacy-stream memset is not ordered with later copies on that stream
     CUDA_OK(c, cudaMemsetAsync(d.vals, 0, (c->vals_prefix + c->hpl_padded) * sizeof(S), c->stream));
     CUDA_OK(c, cudaMemsetAsync(d.delta, 0, (size_t)P.N * sizeof(S), c->stream));
-    CUDA_OK(c, cudaMemsetAsync(d.stats, 0, 8 * sizeof(double), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(d.stats, 0, kTailWords * 8, c->stream));
     CUDA_OK(c, cudaMemsetAsync(d.pose, 0, 4 * (size_t)P.NP * sizeof(S), c->stream));
     CUDA_OK(c, cudaMemsetAsync(d.theta, 0, (size_t)P.NP * sizeof(S), c->stream));
     CUDA_OK(c, cudaMemsetAsync(d.lm, 0, 2 * (size_t)std::max(P.NL, 1) * sizeof(S), c->stream));
@@ -497,6 +509,45 @@ int ensure_pcg(bos_ctx* c) {
     return BOS_OK;
 }
 
+void close_peers(bos_ctx* c) {
+    for (int r = 0; r < kMaxPeers; r++) {
+        if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
+        c->peer_opened[r] = nullptr; c->peer_base[r] = nullptr;
+    }
+    c->peers_open = false;
+    c->peer_epoch = 0;
+    if (c->reduce_mode == 4) c->reduce_mode = 3;
+    c->dd.npeer = 0; c->df.npeer = 0;
+    c->dd.stats_k2 = c->dd.stats; c->df.stats_k2 = c->df.stats;
+}
+
+// the peer window of rank r: values at peer_base[r], tail (statistics, barrier slots) tail_off bytes further (same problem => same layout)
+template <typename S>
+void apply_peer_mode(bos_ctx* c) {
+    Dev<S>& d = dev<S>(c);
+    const bool on = c->reduce_mode == 4 && c->peers_open && c->nranks > 1;
+    d.npeer = on ? c->nranks : 0;
+    for (int r = 0; r < kMaxPeers; r++) {
+        d.pv[r] = (on && r < c->nranks) ? reinterpret_cast<S*>(c->peer_base[r]) : nullptr;
+        d.pstats[r] = (on && r < c->nranks) ? reinterpret_cast<double*>(c->peer_base[r] + c->tail_off) : nullptr;
+    }
+    d.stats_k2 = on ? d.stats + kTailStatsK2 : d.stats;
+}
+
+int peer_barrier(bos_ctx* c, const double* publish) {
+    PeerBarrier pb;
+    for (int r = 0; r < kMaxPeers; r++) {
+        unsigned char* tail = (r < c->nranks && c->peer_base[r]) ? c->peer_base[r] + c->tail_off : nullptr;
+        pb.slots[r] = tail ? reinterpret_cast<unsigned long long*>(tail) + kTailSlots : nullptr;
+        pb.pstats[r] = reinterpret_cast<double*>(tail);
+    }
+    pb.publish = publish;
+    pb.error = reinterpret_cast<unsigned long long*>(c->peer_base[c->rank] + c->tail_off) + kTailError;
+    pb.n = c->nranks; pb.rank = c->rank;
+    pb.epoch = ++c->peer_epoch;
+    return launch_peer_barrier(pb, c->stream);
+}
+
 int pick_solver(bos_ctx* c) {
     if (c->opt.solver == BOS_SOLVER_DENSE_CHOLESKY || c->opt.solver == BOS_SOLVER_PCG || c->opt.solver == BOS_SOLVER_SPARSE_CHOLESKY) return c->opt.solver;
     return (3 * c->P.NP <= c->opt.dense_max_dim) ? BOS_SOLVER_DENSE_CHOLESKY : BOS_SOLVER_PCG;
@@ -504,6 +555,14 @@ int pick_solver(bos_ctx* c) {
 
 template <typename S>
 int allreduce_impl(bos_ctx* c) {
+    if (c->nranks > 1 && c->reduce_mode == 4) {
+        // nothing left to move: the bearing kernel wrote every combined block into every replica.  The second cross-GPU barrier tells this
+        // rank that ALL ranks' kernels have finished (their remote writes are visible after their kernel boundary) and publishes the
+        // odometry share of the statistics.
+        c->launches += peer_barrier(c, dev<S>(c).stats + kTailStatsK2);
+        CUDA_OK(c, cudaGetLastError());
+        return BOS_OK;
+    }
     if (c->nranks <= 1 || !c->comm) return BOS_OK;
     NcclApi& n = nccl();
     Dev<S>& d = dev<S>(c);
@@ -562,11 +621,25 @@ int linearize_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const bool multi = c->nranks > 1;
     const bool zero_hpl = !c->P.slots_identity || (multi && !((c->reduce_mode >= 2 || (c->reduce_mode == 1 && c->nranks <= 8)) && c->P.slots_identity));
-    const bool owned = multi && c->reduce_mode == 3 && c->P.slots_identity;   // every rank writes every pose-pose block itself
+    const bool peer = multi && c->reduce_mode == 4;
+    if (peer && !(c->peers_open && c->P.slots_identity && c->nranks <= kMaxPeers))
+        return fail(c, BOS_ERR_STATE, "reduce_mode 4 needs bos_peer_open after the problem upload, at most 8 ranks and no duplicate (pose, landmark) edges");
+    const bool owned = multi && (c->reduce_mode == 3 || peer) && c->P.slots_identity;   // every rank writes every pose-pose block itself
     const bool zero_hoff = (multi && !owned) || c->P.has_shared_off;
-    const double damp_here = (c->rank == 0) ? c->opt.damping : 0.0;
+    // NCCL modes SUM the replicas' landmark blocks: only rank 0 contributes the damping.  Peer mode: every replica receives every rank's REDs
+    // on top of its own initialisation, so every replica starts from the full damping.
+    const double damp_here = (c->rank == 0 || peer) ? c->opt.damping : 0.0;
     d.irls = c->robust_mode;
-    c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, multi && !owned, c->rank, owned);
+    if (peer) {
+        apply_peer_mode<S>(c);
+        // initialisation + odometry kernel (local replica only) | barrier: every replica is initialised | bearing kernel writing to all replicas
+        c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, false, c->rank, true, 1);
+        c->launches += peer_barrier(c, nullptr);
+        c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, false, c->rank, true, 2);
+    } else {
+        if (d.npeer) apply_peer_mode<S>(c);
+        c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, multi && !owned, c->rank, owned);
+    }
     CUDA_OK(c, cudaGetLastError());
     c->linearized = true; c->solved = false;
     return BOS_OK;
@@ -630,9 +703,12 @@ int update_impl(bos_ctx* c) {
 
 template <typename S>
 int fetch_stats(bos_ctx* c) {
-    double h[8];
+    double h[kTailError + 1];
     CUDA_OK(c, cudaMemcpyAsync(h, dev<S>(c).stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    unsigned long long peer_err;
+    std::memcpy(&peer_err, &h[kTailError], sizeof(peer_err));
+    if (peer_err != 0) return fail(c, BOS_ERR_NCCL, "reduce_mode 4: a cross-GPU barrier timed out (a rank did not reach bos_linearize)");
     c->stats.chi2_bearing = h[0]; c->stats.chi2_odometry = h[1];
     c->stats.over_bearing = (int64_t)llround(h[2]); c->stats.over_odometry = (int64_t)llround(h[3]);
     c->stats.delta_inf = h[4];
@@ -852,6 +928,7 @@ int bos_destroy(bos_ctx* c) {
     cudaSetDevice(c->opt.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    close_peers(c);
     c->mem.release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -898,6 +975,7 @@ int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t 
     CUDA_OK(c, cudaSetDevice(c->opt.device));
     c->have_problem = false; c->delta_valid = false; c->dense_ready = false; c->pcg_ready = false; c->sky_ready = false;
     c->lm_pose_bak = nullptr; c->lm_lm_bak = nullptr;
+    close_peers(c);
     c->mem.release();
     PatternCore core;
     const auto t0 = std::chrono::steady_clock::now();
@@ -1193,8 +1271,58 @@ int bos_comm_init(bos_ctx* c, int rank, int nranks, const char* uid128) {
 }
 
 int bos_set_reduce_mode(bos_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 3) return BOS_ERR_INVALID;
+    if (!c || mode < 0 || mode > 4) return BOS_ERR_INVALID;
+    if (mode == 4 && !c->peers_open) return fail(c, BOS_ERR_STATE, "reduce_mode 4: call bos_peer_open first (after bos_upload_problem)");
     c->reduce_mode = mode;
+    return BOS_OK;
+}
+
+// ---- reduce_mode 4: the value buffers of the ranks of one box, mapped into each other's address space (CUDA IPC over NVLink) ----
+int bos_peer_export(bos_ctx* c, void* handle64, int64_t* offset) {
+    if (!c || !handle64 || !offset) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "peer export before upload_problem");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    unsigned char* vals = c->f64() ? reinterpret_cast<unsigned char*>(c->dd.vals) : reinterpret_cast<unsigned char*>(c->df.vals);
+    // small cudaMalloc blocks are sub-allocated: the IPC handle names the whole underlying allocation, so the offset inside it travels along
+    typedef int (*get_range_t)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    unsigned long long base = reinterpret_cast<unsigned long long>(vals);
+    size_t size = 0;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn && qr == cudaDriverEntryPointSuccess) {
+        if (reinterpret_cast<get_range_t>(fn)(&base, &size, reinterpret_cast<unsigned long long>(vals)) != 0) base = reinterpret_cast<unsigned long long>(vals);
+    } else {
+        cudaGetLastError();
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_OK(c, cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+    static_assert(sizeof(cudaIpcMemHandle_t) == BOS_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    std::memcpy(handle64, &h, sizeof(h));
+    *offset = (int64_t)(reinterpret_cast<unsigned long long>(vals) - base);
+    return BOS_OK;
+}
+
+int bos_peer_open(bos_ctx* c, const void* handles, const int64_t* offsets) {
+    if (!c || !handles || !offsets) return BOS_ERR_INVALID;
+    NEED(c, c->have_problem, "peer open before upload_problem");
+    if (c->nranks < 2 || c->nranks > kMaxPeers) return fail(c, BOS_ERR_STATE, "bos_peer_open: 2 to 8 ranks (bos_comm_init / bos_set_edge_shard first)");
+    CUDA_OK(c, cudaSetDevice(c->opt.device));
+    close_peers(c);
+    unsigned char* own = c->f64() ? reinterpret_cast<unsigned char*>(c->dd.vals) : reinterpret_cast<unsigned char*>(c->df.vals);
+    for (int r = 0; r < c->nranks; r++) {
+        if (r == c->rank) { c->peer_base[r] = own; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * BOS_IPC_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            const std::string why = cudaGetErrorString(cudaGetLastError());
+            close_peers(c);
+            return fail(c, BOS_ERR_CUDA, "cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + why);
+        }
+        c->peer_opened[r] = p;
+        c->peer_base[r] = static_cast<unsigned char*>(p) + offsets[r];
+    }
+    c->peers_open = true;
     return BOS_OK;
 }
 

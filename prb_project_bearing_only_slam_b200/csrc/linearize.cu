@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(128) k_linearize_odometry(Dev<S> d, int o_begi
     if (threadIdx.x == 0) {
         double cs = 0, os = 0;
         for (int w = 0; w < 4; w++) { cs += red[0][w]; os += red[1][w]; }
-        if (cs != 0.0) atomicAdd(d.stats + 1, cs);
-        if (os != 0.0) atomicAdd(d.stats + 3, os);
+        if (cs != 0.0) atomicAdd(d.stats_k2 + 1, cs);   // d.stats, or the scratch the peer barrier publishes to every replica (reduce_mode 4)
+        if (os != 0.0) atomicAdd(d.stats_k2 + 3, os);
     }
 }
 
@@ -189,7 +189,28 @@ struct LinSmem {
     unsigned long long bar[kLinStages];
 };
 
-template <typename S, bool kIdentSlots>
+// Outputs that must be combined across ranks (landmark blocks, b, pose blocks, statistics).  Single rank / NCCL modes: the local buffer.
+// kPeer (reduce_mode 4): the SAME store or RED goes to every rank's replica through its peer mapping (NVLink; the add is performed by the
+// memory that owns the address, system scope), so when the last rank's kernel has finished every replica holds the combined H, b --
+// the combine rides on the build, tile by tile, instead of following it as a collective.
+template <bool kPeer, typename S>
+__device__ __forceinline__ void out_red(const Dev<S>& d, S* p, S v) {
+    if constexpr (!kPeer) red_add(p, v);
+    else {
+        const long long off = p - d.vals;
+        for (int r = 0; r < d.npeer; r++) atomicAdd_system(d.pv[r] + off, v);
+    }
+}
+template <bool kPeer, typename S>
+__device__ __forceinline__ void out_store(const Dev<S>& d, S* p, S v) {
+    if constexpr (!kPeer) *p = v;
+    else {
+        const long long off = p - d.vals;
+        for (int r = 0; r < d.npeer; r++) d.pv[r][off] = v;
+    }
+}
+
+template <typename S, bool kIdentSlots, bool kPeer = false>
 __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bearing_persistent(Dev<S> d, int e_begin, int e_end, S kernel_threshold, S damping) {
     extern __shared__ __align__(128) unsigned char lin_smem_raw[];
     LinSmem<S>& sm = *reinterpret_cast<LinSmem<S>*>(lin_smem_raw);
@@ -309,9 +330,9 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
             if (gi < ng && sub == 0) {
                 const int gl = g.glm[gi];
                 S* hl = d.Hll + 3LL * gl;
-                red_add(hl + 0, v0); red_add(hl + 1, v1); red_add(hl + 2, v2);
+                out_red<kPeer>(d, hl + 0, v0); out_red<kPeer>(d, hl + 1, v1); out_red<kPeer>(d, hl + 2, v2);
                 S* bl = d.b + 3LL * d.NP + 2LL * gl;
-                red_add(bl + 0, v3); red_add(bl + 1, v4);
+                out_red<kPeer>(d, bl + 0, v3); out_red<kPeer>(d, bl + 1, v4);
             }
         }
         const int nruns = plast - pfirst + 1;
@@ -371,12 +392,12 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
                     S* bp = d.b + 3LL * p;
                     if (cut) {
 #pragma unroll
-                        for (int q = 0; q < 6; q++) red_add(hp + q, v[q]);
-                        red_add(bp, v[6]); red_add(bp + 1, v[7]); red_add(bp + 2, v[8]);
+                        for (int q = 0; q < 6; q++) out_red<kPeer>(d, hp + q, v[q]);
+                        out_red<kPeer>(d, bp, v[6]); out_red<kPeer>(d, bp + 1, v[7]); out_red<kPeer>(d, bp + 2, v[8]);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 6; q++) hp[q] = v[q];
-                        bp[0] = v[6]; bp[1] = v[7]; bp[2] = v[8];
+                        for (int q = 0; q < 6; q++) out_store<kPeer>(d, hp + q, v[q]);
+                        out_store<kPeer>(d, bp, v[6]); out_store<kPeer>(d, bp + 1, v[7]); out_store<kPeer>(d, bp + 2, v[8]);
                     }
                 }
             }
@@ -391,9 +412,47 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
     if (tid == 0) {
         double cs = 0, os = 0;
         for (int w = 0; w < kLinThreads / 32; w++) { cs += sm.red[0][w]; os += sm.red[1][w]; }
-        if (cs != 0.0) atomicAdd(d.stats + 0, cs);
-        if (os != 0.0) atomicAdd(d.stats + 2, os);
+        if constexpr (!kPeer) {
+            if (cs != 0.0) atomicAdd(d.stats + 0, cs);
+            if (os != 0.0) atomicAdd(d.stats + 2, os);
+        } else {
+            for (int r = 0; r < d.npeer; r++) {
+                if (cs != 0.0) atomicAdd_system(d.pstats[r] + 0, cs);
+                if (os != 0.0) atomicAdd_system(d.pstats[r] + 2, os);
+            }
+        }
     }
+}
+
+// Cross-GPU barrier of reduce_mode 4 (one warp, stream-ordered after the kernel whose remote writes it publishes: a kernel boundary makes
+// them visible system-wide).  Lane q signals rank q's slot array, then waits for rank q's signal in its own; `publish` first adds the odometry
+// kernel's share of the statistics to every replica.  A wait that exceeds ~4 s of clock raises the local error flag instead of hanging.
+__global__ void k_peer_barrier(PeerBarrier pb) {
+    const int q = threadIdx.x;
+    if (pb.publish && q < pb.n) {
+        const double c = pb.publish[1], o = pb.publish[3];
+        if (c != 0.0) atomicAdd_system(pb.pstats[q] + 1, c);
+        if (o != 0.0) atomicAdd_system(pb.pstats[q] + 3, o);
+    }
+    __threadfence_system();
+    if (q < pb.n) {
+        unsigned long long* dst = pb.slots[q] + pb.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(pb.epoch) : "memory");
+        const unsigned long long* src = pb.slots[pb.rank] + q;
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if (v >= pb.epoch) break;
+            if (clock64() - t0 > 8000000000LL) { *pb.error = 1ULL; break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+int launch_peer_barrier(const PeerBarrier& pb, cudaStream_t st) {
+    k_peer_barrier<<<1, 32, 0, st>>>(pb);
+    return 1;
 }
 
 // no bearing edges at all (a pure pose graph): nobody walks tiles, so the poses are finished here
@@ -417,10 +476,12 @@ __global__ void __launch_bounds__(128) k_pose_finish_nobearing(Dev<S> d, S dampi
 
 template <typename S>
 int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_threshold, double damping, double damping_here,
-                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st, bool multi_rank, int rank, bool all_hoff) {
+                     bool zero_hpl, bool zero_hoff, int sm_count, cudaStream_t st, bool multi_rank, int rank, bool all_hoff, int phases) {
     // damping: what an owned pose block starts from; damping_here: what this rank adds to the landmark blocks (they are summed over ranks)
+    // phases: bit 0 = initialisation + odometry kernel, bit 1 = bearing kernel (reduce_mode 4 puts a cross-GPU barrier between the two)
     int launches = 0;
-    cudaMemsetAsync(d.stats, 0, 8 * sizeof(double), st);
+    if (phases & 1) {
+    cudaMemsetAsync(d.stats, 0, 16 * sizeof(double), st);   // statistics + the odometry kernel's scratch (tail of the value buffer)
     if (zero_hoff && d.n_off > 0) cudaMemsetAsync(d.Hoff, 0, sizeof(S) * 9 * (size_t)d.n_off, st);
     if (zero_hpl && d.n_hpl > 0) cudaMemsetAsync(d.Hpl, 0, sizeof(S) * 6 * (size_t)d.hpl_ld, st);
     // several ranks: a pose block is written by the rank that owns the pose only, the others contribute zeros to the combine
@@ -431,6 +492,8 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
         k_linearize_odometry<S><<<(d.Eo + d.NL + d.n_cut + 127) / 128, 128, 0, st>>>(d, 0, d.Eo, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here, all_hoff ? 1 : 0);
         launches++;
     } else if (d.NL + d.n_cut > 0) { k_hb_init<S><<<(d.NL + d.n_cut + 255) / 256, 256, 0, st>>>(d, (S)damping_here); launches++; }
+    }
+    if (!(phases & 2)) return launches;
     const int nb = r.b_end - r.b_begin;
     if (nb > 0) {
         const int tiles = (nb + kLinTile - 1) / kLinTile;
@@ -439,7 +502,10 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
         ensure_dyn_smem((const void*)k_linearize_bearing_persistent<S, false>, smem);
         int grid = sm_count * kLinPersistCtas;
         if (grid > tiles) grid = tiles;
-        if (d.b_slot == nullptr)
+        if (d.npeer > 0 && d.b_slot == nullptr) {
+            ensure_dyn_smem((const void*)k_linearize_bearing_persistent<S, true, true>, smem);
+            k_linearize_bearing_persistent<S, true, true><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
+        } else if (d.b_slot == nullptr)
             k_linearize_bearing_persistent<S, true><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
         else
             k_linearize_bearing_persistent<S, false><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
@@ -549,8 +615,8 @@ int launch_update(const Dev<S>& d, cudaStream_t st) {
     return 1;
 }
 
-template int launch_linearize<double>(const Dev<double>&, const ShardRange&, double, double, double, bool, bool, int, cudaStream_t, bool, int, bool);
-template int launch_linearize<float>(const Dev<float>&, const ShardRange&, double, double, double, bool, bool, int, cudaStream_t, bool, int, bool);
+template int launch_linearize<double>(const Dev<double>&, const ShardRange&, double, double, double, bool, bool, int, cudaStream_t, bool, int, bool, int);
+template int launch_linearize<float>(const Dev<float>&, const ShardRange&, double, double, double, bool, bool, int, cudaStream_t, bool, int, bool, int);
 template int launch_edge_terms<double>(const Dev<double>&, double*, double*, double*, double*, cudaStream_t);
 template int launch_edge_terms<float>(const Dev<float>&, float*, float*, float*, float*, cudaStream_t);
 template int launch_pose_theta<double>(const Dev<double>&, cudaStream_t);
