@@ -219,11 +219,11 @@ BOS_API int bos_host_pattern_get(const bos_host_pattern* p, int32_t* hpl_pose, i
  * assert that two builds (e.g. serial and threaded, BOS_PATTERN_THREADS=1) produced identical device layouts. */
 BOS_API int bos_host_pattern_checksum(const bos_host_pattern* p, uint64_t* out);
 /* On-device problem setup (the reference resolves ids through std::map for every edge of every iteration, framework/state.cpp:43-63,
- * and this library's default builds its tables on host threads).
- * bos_set_device_setup(ctx, 1): bos_upload_problem builds the bearing-edge core of the pattern -- the (pose, landmark)-sorted edge order, the
+ * and this library builds its tables on host threads for small problems).
+ * bos_set_device_setup(ctx, on): 1 = always, 0 = never, -1 = from 200 000 bearing edges on (the default): bos_upload_problem builds the bearing-edge core of the pattern -- the (pose, landmark)-sorted edge order, the
  *   pose-landmark block slots, the CSR-of-blocks row pointers, the landmark-major slot order and the triangulation rows -- with GPU radix sorts,
  *   scans and run-length kernels; the remaining layouts (tiles, PCG chunks) are derived from them on the host.  The tables are bit-identical to
- *   the host builder's: bos_pattern_checksum equals bos_host_pattern_checksum.  bos_last_setup_ms reports the two parts of the last upload.
+ *   the host builder's: bos_pattern_checksum equals bos_host_pattern_checksum.  bos_last_setup_ms reports the two parts of the last upload (device part 0 when the host built everything).
  * bos_device_resolve_ids: id -> stix for all edge end points on the device (map::at semantics: an unknown pose id is BOS_ERR_INVALID, a duplicated
  *   pose id resolves to its last insertion; landmark stix = rank of the id among the observed landmark ids, slam/triangulation.cpp:68-73);
  *   lm_ids (capacity Eb) receives the ascending landmark id table, *NL_out its length. */

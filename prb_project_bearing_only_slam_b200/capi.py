@@ -306,8 +306,9 @@ class Context:
         self.peer_open([h for h, _ in everyone], [o for _, o in everyone])
 
     def set_device_setup(self, on=True):
-        """Build the bearing-edge core of the pattern on the device at the next upload_problem."""
-        self._ck(self.L.bos_set_device_setup(self.h, 1 if on else 0))
+        """Build the bearing-edge core of the pattern on the device at the next upload_problem: True / False, None = the
+        library's default (on the device from 200 000 bearing edges on)."""
+        self._ck(self.L.bos_set_device_setup(self.h, -1 if on is None else (1 if on else 0)))
 
     def last_setup_ms(self):
         a, b = C.c_double(), C.c_double()

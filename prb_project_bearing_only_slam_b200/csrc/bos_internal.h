@@ -28,6 +28,10 @@ constexpr int kPcgThreads = BOS_PCG_THREADS;       // one persistent CTA per SM
 #endif
 constexpr int kEllLanesL = BOS_ELL_LANES;          // lanes per landmark row in the landmark-major layout
 constexpr int kMaxPeers = 8;                        // ranks of one NVSwitch box (reduce_mode 4)
+#ifndef BOS_LC_LANES
+#define BOS_LC_LANES 1
+#endif
+constexpr int kLcLanes = BOS_LC_LANES;            // lanes per (chunk, landmark) row of the chunk-local landmark-major layout (pattern.cpp "LC")
 constexpr int kShareEll = 8;                       // sharers of a (chunk, landmark) kept in the transposed list (the rest through the CSR list)
 
 // Typed view of everything a kernel needs.  One instance per context, built after upload.

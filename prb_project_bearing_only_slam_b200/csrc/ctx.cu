@@ -112,7 +112,8 @@ struct bos_ctx {
     // multi-GPU
     int rank = 0, nranks = 1, reduce_mode = 0;
     int robust_mode = 0;          // 0 = reference robust kernel, 1 = IRLS (bos_set_robust_mode)
-    int device_setup = 0;         // 1: the bearing-edge core of the pattern is built on the device (bos_set_device_setup)
+    int device_setup = -1;        // 1: the bearing-edge core of the pattern is built on the device, 0: on host threads, -1: device from 200 k edges on (bos_set_device_setup)
+    bool device_setup_used = false;
     double setup_ms[2] = {0.0, 0.0};   // last upload: device core, host remainder
     nccl_comm_t comm = nullptr;
     // reduce_mode 4: the ranks' value buffers mapped into this process through CUDA IPC (bos_peer_export / bos_peer_open)
@@ -979,13 +980,22 @@ int bos_upload_problem(bos_ctx* c, int NP, int NL, int fixed_pose_stix, int64_t 
     c->mem.release();
     PatternCore core;
     const auto t0 = std::chrono::steady_clock::now();
-    if (c->device_setup) {
+    // auto: the GPU sorts pay from ~200 k edges on (mini / full build in microseconds on the host); the tables are identical either way
+    bool on_device = c->device_setup == 1 || (c->device_setup < 0 && Eb >= 200000);
+    if (on_device) {
         std::string err;
         const int rcd = device_pattern_core(core, NP, NL, Eb, b_pose, b_lm, c->stream, err);
-        if (rcd != 0) return fail(c, rcd == 1 ? BOS_ERR_INVALID : BOS_ERR_CUDA, err);
+        if (rcd == 1) return fail(c, BOS_ERR_INVALID, err);
+        if (rcd != 0) {
+            if (c->device_setup == 1) return fail(c, BOS_ERR_CUDA, err);
+            cudaGetLastError();
+            core = PatternCore();
+            on_device = false;     // auto: no room for the sort buffers -- the host builder produces the same tables
+        }
     }
+    c->device_setup_used = on_device;
     const auto t1 = std::chrono::steady_clock::now();
-    if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count, c->device_setup ? &core : nullptr) != 0)
+    if (build_pattern(c->P, NP, NL, fixed_pose_stix, Eb, b_pose, b_lm, Eo, o_src, o_dst, c->sm_count, on_device ? &core : nullptr) != 0)
         return fail(c, BOS_ERR_INVALID, c->P.error);
     c->setup_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
     c->setup_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
@@ -1389,12 +1399,12 @@ int bos_pattern_checksum(bos_ctx* c, uint64_t* out) {
 }
 int bos_set_device_setup(bos_ctx* c, int on) {
     if (!c) return BOS_ERR_INVALID;
-    c->device_setup = on ? 1 : 0;
+    c->device_setup = on < 0 ? -1 : (on ? 1 : 0);
     return BOS_OK;
 }
 int bos_last_setup_ms(const bos_ctx* c, double* device_core_ms, double* host_ms) {
     if (!c) return BOS_ERR_INVALID;
-    if (device_core_ms) *device_core_ms = c->setup_ms[0];
+    if (device_core_ms) *device_core_ms = c->device_setup_used ? c->setup_ms[0] : 0.0;
     if (host_ms) *host_ms = c->setup_ms[1];
     return BOS_OK;
 }

@@ -320,8 +320,9 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
                 }
             });
         // LC: per chunk, the landmark-major view of the chunk's OWN edges: rows = the chunk's distinct landmarks in table order,
-        // ONE lane per row (a landmark has ~10 edges inside a chunk: eight lanes per row would mostly idle), 32 rows per group, column-major
-        // groups like the L layout.  The persistent PCG kernel
+        // kLcLanes (= 1) lanes per row (a landmark has ~10 edges inside a chunk, the busiest ~20; measured at synth-2M: two lanes per row
+        // change nothing, four cost 5 %), 32 / kLcLanes rows per group in descending edge count (the kernel hands the groups to its warps
+        // longest first), column-major groups like the L layout.  The persistent PCG kernel
         // forms, per chunk, the partial t_l = sum_k jh_k (Jp_k . z) of every landmark it sees from SHARED MEMORY (its poses' z and
         // positions live there) instead of gathering 48 bytes per edge from global memory; a landmark seen from several chunks is
         // summed from the chunks' partials through the sharing lists below.
@@ -330,7 +331,7 @@ int build_pattern(HostPattern& P, int NP, int NL, int fixed, int64_t Eb64, const
         //   q = pc_cl_ptr[c] + k numbers every (chunk, local landmark): sh_ptr / sh_src list the q' of ALL chunks (own included) that
         //   see the same landmark, sh_first[q] = 1 in the lowest such chunk (it accounts for the landmark's part of z . S z)
         if (P.pc_ok) {
-            constexpr int kLcLanes = 1, RPGc = 32 / kLcLanes;
+            constexpr int RPGc = 32 / kLcLanes;
             P.lc_gptr.assign(nch + 1, 0);
             for (int c = 0; c < nch; c++) P.lc_gptr[c + 1] = P.lc_gptr[c] + (P.pc_cl_ptr[c + 1] - P.pc_cl_ptr[c] + RPGc - 1) / RPGc;
             const int ngl = P.lc_gptr[nch];

@@ -508,15 +508,24 @@ __device__ __forceinline__ void pcg_landmark_rows(const Dev<S>& d, const PcgWork
 // Round 1 gathered pose position + z (two 32-byte sectors per EDGE) from L2 here: 30 of the 100 us of a CG iteration.
 template <typename S>
 __device__ __forceinline__ void pcg_local_landmark_rows(const Dev<S>& d, const PcgWork<S>& w, int c, const S* zs, int cps, int Kp, bool chain,
-                                                        const S* pxy, S* tp) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g0 = __ldg(d.lc_gptr + c), g1 = __ldg(d.lc_gptr + c + 1);
+                                                        const S* pxy, S* tp, int* next_group) {
+    constexpr int RPG = 32 / kLcLanes;   // rows (landmarks) per group
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % kLcLanes, rowl = lane / kLcLanes;
+    const int g0 = __ldg(d.lc_gptr + c), ng = __ldg(d.lc_gptr + c + 1) - g0;
     const int cl0 = __ldg(d.pc_cl_ptr + c), ncl = __ldg(d.pc_cl_ptr + c + 1) - cl0;
     const S so_u = (S)w.sqrt_omega;
     const size_t nq = (size_t)d.n_q;
-    for (int g = g0 + warp; g < g1; g += kPcgThreads / 32) {   // one lane per landmark, 32 landmarks per group
+    // The groups are sorted by descending length; the warps take them from a shared counter (*next_group, zero on entry) as they become free:
+    // longest-processing-time-first scheduling.  A static round robin left the warps that drew two long groups working twice as long as the rest.
+    for (;;) {
+        int gi = 0;
+        if (lane == 0) gi = atomicAdd(next_group, 1);
+        gi = __shfl_sync(BOS_FULL_MASK, gi, 0);
+        if (gi >= ng) break;
+        const int g = g0 + gi;
         const int off = __ldg(d.lc_goff + g), W = __ldg(d.lc_goff + g + 1) - off;
-        const int k = (int)__ldg(d.lc_k + (size_t)g * 32 + lane);          // rows are sorted by edge count: the local landmark of this row
+        const int k = (int)__ldg(d.lc_k + (size_t)g0 * 32 + (size_t)gi * RPG + rowl);   // the local landmark of this lane's row
         const bool valid = k != 0xffff && k < ncl;
         S lx = S(0), ly = S(0);
         if (valid) { lx = __ldg(w.qstat + 3 * nq + cl0 + k); ly = __ldg(w.qstat + 4 * nq + cl0 + k); }
@@ -541,7 +550,9 @@ __device__ __forceinline__ void pcg_local_landmark_rows(const Dev<S>& d, const P
                 t0 += j0 * sc; t1 += j1 * sc;
             }
         }
-        if (valid) st2cg(tp + 2LL * (cl0 + k), t0, t1);
+#pragma unroll
+        for (int o = 1; o < kLcLanes; o <<= 1) { t0 += __shfl_xor_sync(BOS_FULL_MASK, t0, o); t1 += __shfl_xor_sync(BOS_FULL_MASK, t1, o); }
+        if (valid && sub == 0) st2cg(tp + 2LL * (cl0 + k), t0, t1);
     }
 }
 
@@ -1296,6 +1307,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     __shared__ double red[kPcgThreads / 32];
     __shared__ double red6[kPcgRows][kPcgThreads / 32][6];   // per (row set, warp): P^T r of the warp's 32 rows (one segment: segments are whole groups)
     __shared__ double xc_s[3 * (kCoarseMaxSeg + 1)];          // coarse solution at this chunk's nodes
+    __shared__ int lc_next;                                   // next group of the chunk-local landmark pass (dynamic scheduling)
     __shared__ signed char seg_of_s[kPcgRows][kPcgThreads / 32];   // segment of each (row set, warp); -1 beyond the chunk
     // the coarse operator is dropped for this solve if its Cholesky factorisation met a non-positive pivot (flag set by k_potrf_diag)
     const bool chain = w.precond != 1, coarse = w.precond == 0 && __ldcg(w.cStats + 5) == 0.0;
@@ -1307,6 +1319,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
         const int hh = threadIdx.x / (kPcgThreads / 32), kk = threadIdx.x % (kPcgThreads / 32), r0 = 32 * kk + hh * kPcgThreads;
         seg_of_s[hh][kk] = (signed char)((r0 < d.pc_cp) ? r0 / hseg : -1);
     }
+    if (threadIdx.x == 0) lc_next = 0;
     S* vsm = reinterpret_cast<S*>(pcg_smem + plan.vec_off);
     S* rec = reinterpret_cast<S*>(pcg_smem + plan.rec_off);
     unsigned short* loc_s = reinterpret_cast<unsigned short*>(pcg_smem + plan.loc_off);
@@ -1622,10 +1635,11 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             }
             PCG_T(0);
 #ifndef BOS_EXP_NO_LROWS
-            pcg_local_landmark_rows<S>(d, w, c, vsm + (size_t)9 * cps, cps, Kp, chain, pxy, tp);
+            pcg_local_landmark_rows<S>(d, w, c, vsm + (size_t)9 * cps, cps, Kp, chain, pxy, tp, &lc_next);
 #endif
             PCG_T(1);
             grid_barrier(w.bar, gridDim.x, epoch);       // every chunk's partials, and the z and gamma the previous iteration left, are visible
+            if (tid == 0) lc_next = 0;                   // every warp is past the landmark pass; the next one is several CTA barriers away
             PCG_T(3);
             if (it > 0 && !(__ldcg(sc + FS_GAMMA0 + cur) > tol2 * gamma_init)) break;      // converged: x is final (the L phase above was for nothing)
             // pass B of the off-diagonal product: neighbours in other chunks

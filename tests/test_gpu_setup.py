@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 def _both(pr, chunks=None):
     host = capi.HostPattern(pr.NP, pr.NL, pr.fixed_stix, pr.b_pose, pr.b_lm, pr.o_src, pr.o_dst)
-    ctx_h = capi.Context(); pr.upload(ctx_h)
+    ctx_h = capi.Context(); ctx_h.set_device_setup(False); pr.upload(ctx_h)
     ctx_d = capi.Context(); ctx_d.set_device_setup(True); pr.upload(ctx_d)
     return host, ctx_h, ctx_d
 
