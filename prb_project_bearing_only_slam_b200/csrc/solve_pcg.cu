@@ -14,6 +14,7 @@
 #include "bos_internal.h"
 #include "bos_math.cuh"
 #include "bos_schur.cuh"
+#include "bos_tma.cuh"
 
 #include <cstdio>
 
@@ -1308,6 +1309,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     __shared__ double red6[kPcgRows][kPcgThreads / 32][6];   // per (row set, warp): P^T r of the warp's 32 rows (one segment: segments are whole groups)
     __shared__ double xc_s[3 * (kCoarseMaxSeg + 1)];          // coarse solution at this chunk's nodes
     __shared__ int lc_next;                                   // next group of the chunk-local landmark pass (dynamic scheduling)
+    __shared__ unsigned long long tma_bar[2];                 // mbarriers of the two per-iteration bulk copies (chain factors, index table)
     __shared__ signed char seg_of_s[kPcgRows][kPcgThreads / 32];   // segment of each (row set, warp); -1 beyond the chunk
     // the coarse operator is dropped for this solve if its Cholesky factorisation met a non-positive pivot (flag set by k_potrf_diag)
     const bool chain = w.precond != 1, coarse = w.precond == 0 && __ldcg(w.cStats + 5) == 0.0;
@@ -1319,7 +1321,12 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
         const int hh = threadIdx.x / (kPcgThreads / 32), kk = threadIdx.x % (kPcgThreads / 32), r0 = 32 * kk + hh * kPcgThreads;
         seg_of_s[hh][kk] = (signed char)((r0 < d.pc_cp) ? r0 / hseg : -1);
     }
-    if (threadIdx.x == 0) lc_next = 0;
+    if (threadIdx.x == 0) {
+        lc_next = 0;
+        mbar_init(&tma_bar[0], 1); mbar_init(&tma_bar[1], 1);
+        mbar_fence_init();
+    }
+    unsigned tma_phase = 0;                                   // preconditioner applications so far: parity of both mbarriers
     S* vsm = reinterpret_cast<S*>(pcg_smem + plan.vec_off);
     S* rec = reinterpret_cast<S*>(pcg_smem + plan.rec_off);
     unsigned short* loc_s = reinterpret_cast<unsigned short*>(pcg_smem + plan.loc_off);
@@ -1386,6 +1393,16 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     const float* zres = reinterpret_cast<const float*>(pcg_smem + ch_w2);
     auto precond_chain = [&](S* zdst, double& gacc, double& dacc2) {
         __syncthreads();
+        // The record / index region is free from here on (the pose pass is over): the chunk's FP32 factors (93 KB at synth-2M) arrive by 1-D TMA
+        // bulk copies WHILE the coarse restriction below runs; everybody waits on the mbarrier right before the chunk solve.  A cooperative
+        // copy loop (six dependent L2 round trips per thread) took 20 k cycles per iteration here.
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the region's earlier generic-proxy accesses before the async-proxy writes
+            const unsigned fb = (unsigned)plan.fac_floats * 4u;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(w.chF + (size_t)c * plan.fac_floats);
+            mbar_expect_tx(&tma_bar[0], fb);
+            for (unsigned o = 0; o < fb; o += 16384u) tma_bulk_load(pcg_smem + plan.rec_off + o, src + o, fb - o < 16384u ? fb - o : 16384u, &tma_bar[0]);
+        }
         if (coarse) {   // this chunk's part of P^T r; the exchange over the grid overlaps the chain solve below
 #pragma unroll
             for (int h = 0; h < kPcgRows; h++) {
@@ -1424,11 +1441,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 for (int a = 0; a < 3; a++) { const float f = (float)v[(6 + a) * cps]; c1[a * cps + vx[h]] = f; c2[a * cps + vx[h]] = f; }
             }
         }
-        {
-            const float4* src = reinterpret_cast<const float4*>(w.chF + (size_t)c * plan.fac_floats);
-            float4* dst = reinterpret_cast<float4*>(pcg_smem + plan.rec_off);
-            for (int k = tid; k < plan.fac_floats / 4; k += kPcgThreads) dst[k] = __ldg(src + k);
-        }
+        mbar_wait(&tma_bar[0], tma_phase & 1u);   // the factors have landed
         __syncthreads();
         PCG_T(8);
         const int nr_c = 3 * (nseg + 1);
@@ -1478,6 +1491,14 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             }
             __syncthreads();
         }
+        // the factors are not needed any more: the index table they overwrote comes back by a bulk copy while the per-row work below runs
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const unsigned lb = (unsigned)nslots * 2u;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(d.pc_loc + (size_t)goff0 * 32);
+            mbar_expect_tx(&tma_bar[1], lb);
+            for (unsigned o = 0; o < lb; o += 16384u) tma_bulk_load(reinterpret_cast<unsigned char*>(loc_s) + o, src + o, lb - o < 16384u ? lb - o : 16384u, &tma_bar[1]);
+        }
         // the FP32 result sits in rows 9-11, which now become the chunk's z in S (read by the next operator application): registers first
         float zf[kPcgRows][3];
 #pragma unroll
@@ -1511,7 +1532,8 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
                      (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
         }
-        stage_loc();   // the factors overwrote the index table
+        mbar_wait(&tma_bar[1], tma_phase & 1u);   // the index table is back
+        tma_phase++;
         PCG_T(10);
     };
     {
