@@ -1338,7 +1338,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     unsigned epoch = 0;
     double* sc = w.scal;
 #ifdef BOS_PCG_TIMING
-    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
     // ---- static per-thread data: this thread owns chunk rows tid and tid + 1024 for the whole solve ---------------------
@@ -1430,6 +1430,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             __syncthreads();
             grid_arrive(w.bar, epoch);
         }
+        PCG_T(11);
         if (kWide) {
             float* c1 = reinterpret_cast<float*>(pcg_smem + ch_r1);
             float* c2 = reinterpret_cast<float*>(pcg_smem + ch_r2);
@@ -1441,6 +1442,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
                 for (int a = 0; a < 3; a++) { const float f = (float)v[(6 + a) * cps]; c1[a * cps + vx[h]] = f; c2[a * cps + vx[h]] = f; }
             }
         }
+        PCG_T(12);
         mbar_wait(&tma_bar[0], tma_phase & 1u);   // the factors have landed
         __syncthreads();
         PCG_T(8);
@@ -1507,6 +1509,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             if (tid + h * kPcgThreads < cp) { zf[h][0] = zres[vx[h]]; zf[h][1] = zres[cps + vx[h]]; zf[h][2] = zres[2 * cps + vx[h]]; }
         }
         __syncthreads();
+        PCG_T(13);
 #pragma unroll
         for (int h = 0; h < kPcgRows; h++) {
             const int i = pose_i[h];
@@ -1532,6 +1535,7 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
             dacc2 += (double)zn0 * (double)(h0 * zn0 + h1 * zn1 + h2 * zn2) + (double)zn1 * (double)(h1 * zn0 + h3 * zn1 + h4 * zn2) +
                      (double)zn2 * (double)(h2 * zn0 + h4 * zn1 + h5 * zn2);
         }
+        PCG_T(14);
         mbar_wait(&tma_bar[1], tma_phase & 1u);   // the index table is back
         tma_phase++;
         PCG_T(10);
@@ -1822,9 +1826,10 @@ __global__ void __launch_bounds__(kPcgThreads, 1) k_pcg_fused(Dev<S> d, PcgWork<
     if (gtid == 0) { sc[SC_ITER] = (double)it; sc[SC_BAD] = bad ? 1.0 : 0.0; }
 #ifdef BOS_PCG_TIMING
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2))
-        printf("cta %d iters %d cycles/iter: offdiag %lld Lrows %lld bsum %lld bar1 %lld stage %lld rows %lld bsum2 %lld bar2 %lld | chain: fac-stage %lld solve %lld finish %lld\n",
+        printf("cta %d iters %d cycles/iter: offdiag %lld Lrows %lld bsum %lld bar1 %lld stage %lld rows %lld bsum2 %lld bar2 %lld | chain: restrict %lld f32copy %lld tma-wait %lld solve %lld | finish: zload %lld rows %lld loc-wait %lld\n",
                (int)blockIdx.x, it, tacc[0] / (it ? it : 1), tacc[1] / (it ? it : 1), tacc[2] / (it ? it : 1), tacc[3] / (it ? it : 1), tacc[7] / (it ? it : 1),
-               tacc[4] / (it ? it : 1), tacc[5] / (it ? it : 1), tacc[6] / (it ? it : 1), tacc[8] / (it ? it : 1), tacc[9] / (it ? it : 1), tacc[10] / (it ? it : 1));
+               tacc[4] / (it ? it : 1), tacc[5] / (it ? it : 1), tacc[6] / (it ? it : 1), tacc[11] / (it ? it : 1), tacc[12] / (it ? it : 1), tacc[8] / (it ? it : 1),
+               tacc[9] / (it ? it : 1), tacc[13] / (it ? it : 1), tacc[14] / (it ? it : 1), tacc[10] / (it ? it : 1));
 #endif
 }
 
