@@ -246,6 +246,7 @@ struct PcgWork {
     bool coarse_valid = false, coarse_stale = false;
     int coarse_age = 0, coarse_refresh = 1, coarse_its_ref = 0;
     int coarse_period = 0, coarse_its_last = 0;   // current refresh period (grows while refreshes stop paying), iterations of the previous solve
+    double* host_scal = nullptr;                  // 32 doubles of PINNED host memory (owned by the context): where the solve's scalars are read back
     double* cA = nullptr;    // [c_nc][c_nc] column-major lower: A_c, then its Cholesky factor
     double* cAinv = nullptr; // [c_nc][c_ld] A_c^-1 (full, symmetric)
     double* cRc = nullptr;   // [pc_chunks * c_nseg][6] per segment: P^T r restricted to its rows (left node, right node)

@@ -114,6 +114,7 @@ struct bos_ctx {
     int robust_mode = 0;          // 0 = reference robust kernel, 1 = IRLS (bos_set_robust_mode)
     int device_setup = -1;        // 1: the bearing-edge core of the pattern is built on the device, 0: on host threads, -1: device from 200 k edges on (bos_set_device_setup)
     bool device_setup_used = false;
+    double* pinned = nullptr;     // 64 doubles of pinned host memory: statistics and solver scalars are read back through it
     double setup_ms[2] = {0.0, 0.0};   // last upload: device core, host remainder
     nccl_comm_t comm = nullptr;
     // reduce_mode 4: the ranks' value buffers mapped into this process through CUDA IPC (bos_peer_export / bos_peer_open)
@@ -671,6 +672,7 @@ int solve_impl(bos_ctx* c) {
         // IRLS re-weights every edge every iteration; the fused kernel re-derives its per-edge factors from the state and the STATIC omegas, so
         // IRLS solves take the classic loop, which applies the stored pose-landmark blocks
         pwork<S>(c).variant = c->robust_mode ? 1 : c->opt.pcg_variant;
+        pwork<S>(c).host_scal = c->pinned;
         rc = launch_pcg_solve<S>(d, pwork<S>(c), c->opt.pcg_max_iters, rtol, c->stream, &iters, &nl);
         if (rc < 0) return fail(c, BOS_ERR_CUDA, std::string("pcg: ") + cudaGetErrorString(cudaGetLastError()));
         c->stats.pcg_iterations = iters;
@@ -704,8 +706,9 @@ int update_impl(bos_ctx* c) {
 
 template <typename S>
 int fetch_stats(bos_ctx* c) {
-    double h[kTailError + 1];
-    CUDA_OK(c, cudaMemcpyAsync(h, dev<S>(c).stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    double h_pageable[kTailError + 1];
+    double* h = c->pinned ? c->pinned + 32 : h_pageable;
+    CUDA_OK(c, cudaMemcpyAsync(h, dev<S>(c).stats, sizeof(h_pageable), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     unsigned long long peer_err;
     std::memcpy(&peer_err, &h[kTailError], sizeof(peer_err));
@@ -918,6 +921,7 @@ int bos_create(const bos_options* opts, bos_ctx** out) {
     if (cudaGetDeviceProperties(&prop, c->opt.device) != cudaSuccess) return BOS_ERR_CUDA;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return BOS_ERR_CUDA;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->pinned), 64 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { c->pinned = nullptr; cudaGetLastError(); }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return BOS_ERR_CUDA;
     *out = c.release();
@@ -931,6 +935,7 @@ int bos_destroy(bos_ctx* c) {
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     close_peers(c);
     c->mem.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);

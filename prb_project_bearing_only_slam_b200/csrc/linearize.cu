@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(256) k_hb_init(Dev<S> d, S damping) { hb_init_
 template <typename S>
 __global__ void __launch_bounds__(128) k_linearize_odometry(Dev<S> d, int o_begin, int o_end, int s_begin, int s_end, S kernel_threshold, S damping_init, int all_hoff) {
     __shared__ double red[2][4];
+    // programmatic dependent launch: the bearing kernel that follows may start its CTAs (edge prefetch, phase 1 of its first tiles: nothing
+    // of that reads what this kernel writes) while this grid is still running; it waits (griddepcontrol.wait) before its first phase 2
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = o_begin + blockIdx.x * blockDim.x + threadIdx.x;
     // K3 rides in the same launch: the threads past the last edge initialise the landmark blocks and the cut poses (nothing here reads them)
@@ -307,6 +310,9 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
             for (int q = 0; q < 6; q++) storeN<kEPT>(d.Hpl + (long long)q * d.hpl_ld + e0, hpl[q]);
         }
         __syncthreads();
+        // everything below reads or accumulates into what the preceding kernel wrote (landmark blocks and cut poses initialised, the odometry
+        // scratch Mv): wait for it -- once per CTA, a no-op when the kernel was not launched with programmatic stream serialization
+        if (k == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
         // ---- phase 2: kLinSub lanes per landmark group, then per pose run; sums over the lanes by shuffles ----------------------
         const int ng = g.hdr[0], pfirst = g.hdr[1], plast = g.hdr[2], p_lo = g.hdr[3];
         const int sub = tid % kLinSub, item = tid / kLinSub;
@@ -502,13 +508,22 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
         ensure_dyn_smem((const void*)k_linearize_bearing_persistent<S, false>, smem);
         int grid = sm_count * kLinPersistCtas;
         if (grid > tiles) grid = tiles;
+        // launched with programmatic stream serialization: its CTAs may become resident while the odometry kernel is still running
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kLinThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const int eb = r.b_begin, ee = r.b_end;
+        const S kt = (S)kernel_threshold, dm = (S)damping;
         if (d.npeer > 0 && d.b_slot == nullptr) {
             ensure_dyn_smem((const void*)k_linearize_bearing_persistent<S, true, true>, smem);
-            k_linearize_bearing_persistent<S, true, true><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
+            cudaLaunchKernelEx(&cfg, k_linearize_bearing_persistent<S, true, true>, d, eb, ee, kt, dm);
         } else if (d.b_slot == nullptr)
-            k_linearize_bearing_persistent<S, true><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
+            cudaLaunchKernelEx(&cfg, k_linearize_bearing_persistent<S, true, false>, d, eb, ee, kt, dm);
         else
-            k_linearize_bearing_persistent<S, false><<<grid, kLinThreads, smem, st>>>(d, r.b_begin, r.b_end, (S)kernel_threshold, (S)damping);
+            cudaLaunchKernelEx(&cfg, k_linearize_bearing_persistent<S, false, false>, d, eb, ee, kt, dm);
         launches++;
     } else if (d.Eb == 0 && rank == 0 && d.NP > 0) {
         k_pose_finish_nobearing<S><<<(d.NP + 127) / 128, 128, 0, st>>>(d, (S)damping);

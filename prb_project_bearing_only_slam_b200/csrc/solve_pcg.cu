@@ -1910,7 +1910,8 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2};
     if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(d.pc_chunks), dim3(kPcgThreads), args, plan.bytes, st) != cudaSuccess) return -1;
     nl++;
-    double host_scal[32];
+    double host_pageable[32];
+    double* host_scal = w.host_scal ? w.host_scal : host_pageable;   // pinned: a true asynchronous copy instead of a staged one
     if (cudaMemcpyAsync(host_scal, w.scal, 32 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     if (iterations_out) *iterations_out = (int)host_scal[SC_ITER];
