@@ -102,6 +102,18 @@ def test_headless_harness_on_the_full_dataset(host_test_exe, tmp_path):
     # the written poses are where the oracle converges
     P = np.array([[float(x) for x in l.split()[2:5]] for l in lines if l.startswith("VERTEX_SE2")])
     assert np.abs(P[:, :2] - g["poses_final_f64"][:, :2]).max() < 5e-3
+    # ... and where THE REFERENCE'S OWN CODE converges on the same file (tests/golden/ref_full.npz = oracle/_ref, 20 of its float iterations):
+    # the drop-in claim end to end -- parse, triangulate, Solver::step loop, written result
+    r_ = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_full.npz"))
+    rP = r_["P_it20"]
+    assert np.abs(P[:, :2] - rP[:, :2]).max() < 5e-3
+    assert np.abs(np.angle(np.exp(1j * (P[:, 2] - np.arctan2(rP[:, 3], rP[:, 2]))))).max() < 5e-3
+    L = {int(l.split()[1]): [float(x) for x in l.split()[2:4]] for l in lines if l.startswith("VERTEX_XY")}
+    ids, cnt = np.unique(g["b_lm_id"], return_counts=True)
+    seen_twice = set(ids[cnt > 1].tolist())
+    dl = [np.abs(np.array(L[int(i)]) - r_["L_it20"][k]).max() for k, i in enumerate(r_["lm_ids"]) if int(i) in seen_twice]
+    # a few landmarks seen under a narrow parallax are known to 0.1 only (float iterations, 20 vs 30 of them): the bulk must agree closely
+    assert len(dl) == 138 and np.percentile(dl, 95) < 5e-3 and max(dl) < 0.5
 
 
 @pytest.mark.gpu

@@ -279,7 +279,7 @@ def _gpu_problem(w, r):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("precision", ["f64", "f32", "f64-pcg", "f64-skyline"])
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_path_matches_the_reference(built_lib, name, precision):
     """The product (C ABI -> CUDA kernels) from the reference's triangulated start: pattern bit-exact, per-edge terms / H / b within
@@ -289,7 +289,8 @@ def test_cuda_path_matches_the_reference(built_lib, name, precision):
     pr = _gpu_problem(w, r)
     assert np.array_equal(pr.lm_ids, r["lm_ids"]) and np.array_equal(pr.pose_ids, r["pose_ids"])      # landmark association
     f32 = precision == "f32"
-    ctx = capi.Context(precision=capi.PRECISION_F32 if f32 else capi.PRECISION_F64, solver=capi.SOLVER_DENSE_CHOLESKY)
+    solver = {"f64-pcg": capi.SOLVER_PCG, "f64-skyline": capi.SOLVER_SPARSE_CHOLESKY}.get(precision, capi.SOLVER_DENSE_CHOLESKY)
+    ctx = capi.Context(precision=capi.PRECISION_F32 if f32 else capi.PRECISION_F64, solver=solver, pcg_rtol=1e-12, pcg_max_iters=20000)
     pr.upload(ctx)
     ctx.set_kernel_threshold(kt)
     ctx.set_damping_factor(damping)
