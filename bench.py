@@ -388,16 +388,28 @@ def run_ours(args):
     pr.upload(ctx)
     t_up = time.perf_counter() - t_up
     setup_dev_ms, setup_host_ms = ctx.last_setup_ms()
-    if args.reduce_mode < 0:
-        args.reduce_mode = 3 if solver == capi.SOLVER_PCG else 1
+    auto_mode = args.reduce_mode < 0
+    if args.reduce_mode < 0:   # PCG workloads on one box: the pull-based combine over NVLink peer memory; NCCL ownership combine if the mappings cannot be opened
+        args.reduce_mode = (5 if world <= 8 else 3) if solver == capi.SOLVER_PCG else 1
     if solver == capi.SOLVER_AUTO:   # what AUTO resolves to is only known after the first solve; the roofline block follows solver_used
         solver = None
     if world > 1:
         uid = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
-        if args.reduce_mode == 4:      # fused build + combine over NVLink peer memory: the ranks map each other's value buffers (CUDA IPC)
-            ctx.peer_connect(dist)
+        if args.reduce_mode >= 4:      # combine over NVLink peer memory: the ranks map each other's value buffers (CUDA IPC)
+            ok = 1.0
+            try:
+                ctx.peer_connect(dist)
+            except capi.BosError as e:
+                ok = 0.0
+                print("rank %d: peer mappings unavailable (%s)" % (rank, e), file=sys.stderr)
+            t = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if t.item() < 1.0:
+                if not auto_mode:
+                    raise SystemExit("--reduce-mode %d needs CUDA IPC peer mappings between the ranks" % args.reduce_mode)
+                args.reduce_mode = 3
         ctx.set_reduce_mode(args.reduce_mode)
     # initial guess: generated poses + landmarks triangulated ON THE DEVICE (K8)
     P0 = xyt_to_xycs(w["poses_init"])
@@ -518,10 +530,11 @@ def run_ours(args):
                               2: "schur+pcg(block-tridiagonal chain preconditioner)"}[args.pcg_precond]
                    if solver == capi.SOLVER_PCG else ("schur+skyline-cholesky" if solver == capi.SOLVER_SPARSE_CHOLESKY else "schur+dense-cholesky"),
                    "pcg_rtol": args.pcg_rtol, "pcg_coarse": "4 nodes per chunk, inverse kept for 8 solves (the period doubles while rebuilds stop paying)" if solver == capi.SOLVER_PCG and args.pcg_precond == 0 else None,
-                   "parallelism": "edge-shard x%d + nccl %s, solve replicated" %
-                   (world, {0: "allreduce(full H,b)", 1: "allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "allreduce(b,diag,pose-pose)",
-                           3: "ownership: allreduce(landmark blocks, b_l) + gather of the owned pose ranges",
-                           4: "ownership, no collective: the bearing kernel stores / adds into every rank's replica over NVLink peer memory"}[args.reduce_mode]) if world > 1 else "single gpu",
+                   "parallelism": "edge-shard x%d + %s, solve replicated (rank 0's increment broadcast over NCCL)" %
+                   (world, {0: "nccl allreduce(full H,b)", 1: "nccl allreduce(b,diag,pose-pose)+allgather(pose-landmark)", 2: "nccl allreduce(b,diag,pose-pose)",
+                           3: "nccl ownership: allreduce(landmark blocks, b_l) + gather of the owned pose ranges",
+                           4: "ownership, no collective: the bearing kernel stores / adds into every rank's replica over NVLink peer memory",
+                           5: "ownership, no collective: local build, then bulk pulls of the owners' pose ranges and rank-ordered sums of the landmark parts over NVLink peer memory"}[args.reduce_mode]) if world > 1 else "single gpu",
                    "l2": "no flush: value + edge buffers (%.0f MB) exceed the 126 MB L2" % ((int(pi.vals_len) * S + pr.Eb * 24) / 1e6)},
         "edges_linearized_per_s": E / (ms_lin * 1e-3),
         "phases_ms": {"linearize": ms_lin_kernel, "allreduce": ms_allreduce, "solve": ms_solve, "update": ms_update},
@@ -549,7 +562,7 @@ def run_ours(args):
         f = (world - 1) / world
         n_pp, Ntot = int(pi.n_hpp_off), int(pi.N)
         summed, gathered = {0: (int(pi.vals_len), 0), 1: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 6 * pr.Eb),
-                            2: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 0), 3: (5 * pr.NL, 9 * pr.NP), 4: (5 * pr.NL, 9 * pr.NP)}[args.reduce_mode]
+                            2: (Ntot + 6 * pr.NP + 3 * pr.NL + 9 * n_pp, 0), 3: (5 * pr.NL, 9 * pr.NP), 4: (5 * pr.NL, 9 * pr.NP), 5: (5 * pr.NL, 9 * pr.NP)}[args.reduce_mode]
         nv_peak = 770.0
         if args.reduce_mode == 4:
             # fused: a rank's link carries OUT its owned pose blocks to the N-1 other replicas and (at least) its share of the landmark parts to
@@ -558,6 +571,12 @@ def run_ours(args):
             t_comb = ms_lin
             what = "k_linearize_bearing_persistent<peer>: stores / REDs into every replica over NVLink + two cross-GPU barriers (reduce_mode 4)"
             note = "fused with the build: time = the whole sharded build, bytes = the lower bound a rank must send (one landmark part per landmark and peer)"
+        elif args.reduce_mode == 5:
+            # pulled: a rank's link carries IN the pose ranges it does not own and every other rank's landmark parts
+            nv_bytes = (f * gathered + (world - 1) * summed) * S
+            t_comb = ms_allreduce
+            what = "k_peer_pull + k_peer_commit between two cross-GPU barriers (reduce_mode 5)"
+            note = "bulk coalesced reads over NVLink peer mappings; the time holds both barriers (launch skew between the ranks included)"
         else:
             nv_bytes = (2 * f * summed + f * gathered) * S
             t_comb = ms_allreduce
@@ -654,7 +673,7 @@ def main():
     ap.add_argument("--pcg-max-iters", type=int, default=20000)
     ap.add_argument("--pcg-precond", type=int, default=0, choices=[0, 1, 2],
                     help="0 chain (block-tridiagonal) + coarse-space preconditioner, 1 3x3 block-Jacobi, 2 chain only")
-    ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 3 (ownership combine over NCCL) for the PCG workloads, 1 for the dense ones; 4 = fused build + combine over NVLink peer memory (measured slower, DESIGN.md section 6)")
+    ap.add_argument("--reduce-mode", type=int, default=-1, help="-1: 5 (local build + bulk pulls over NVLink peer memory; 3 = ownership combine over NCCL when the mappings cannot be opened or beyond 8 ranks) for the PCG workloads, 1 for the dense ones; 4 = the bearing kernel pushes into every replica (measured slower, DESIGN.md section 6)")
     ap.add_argument("--ref-solver", default="auto", choices=["auto", "ldlt", "superlu"],
                     help="reference arm: ldlt = the oracle's restatement of Eigen::SimplicialLDLT, superlu = scipy's SuperLU; auto = ldlt when "
                          "its symbolic phase predicts under a minute per factorisation, else superlu")

@@ -252,7 +252,10 @@ BOS_API int bos_comm_init(bos_ctx* ctx, int rank, int nranks, const char* uid128
  * every rank computes every pose-pose block itself, so only the landmark blocks and b_l are summed (5 scalars per landmark) and the
  * owned pose ranges are gathered (grouped broadcasts); pose-landmark blocks stay rank-local as in mode 2;
  * 4: mode 3's ownership with NO collective: the bearing kernel itself stores every owned pose block and adds every landmark part straight into
- * EVERY rank's replica through NVLink peer mappings (bos_peer_open), between two cross-GPU barriers -- the combine rides on the build. */
+ * EVERY rank's replica through NVLink peer mappings (bos_peer_open), between two cross-GPU barriers -- the combine rides on the build;
+ * 5: mode 3's local build, then the combine as bulk PULLS over the same peer mappings: after a cross-GPU barrier one kernel copies the owners'
+ * pose ranges from their replicas and sums the landmark parts of all ranks in rank order (every rank ends up with bit-identical H, b), a
+ * second barrier, a commit kernel.  No NCCL call in the build. */
 BOS_API int bos_set_reduce_mode(bos_ctx* ctx, int reduce_mode);
 /* reduce_mode 4 plumbing (ranks = processes of ONE NVSwitch box, at most 8).  After bos_upload_problem and bos_comm_init / bos_set_edge_shard:
  * every rank exports the CUDA IPC handle of its value buffer (+ byte offset inside the underlying allocation), the host program exchanges them

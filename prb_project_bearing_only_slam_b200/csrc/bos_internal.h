@@ -130,7 +130,8 @@ struct Dev {
     // fused linearize + combine over NVLink peer memory (reduce_mode 4): every rank's value buffer and statistics, own included, mapped
     // through CUDA IPC; the bearing kernel stores / REDs every block that must be combined straight into all replicas
     double* stats_k2 = nullptr;      // where the odometry kernel adds its statistics (stats, or the scratch the peer barrier publishes)
-    int npeer = 0;
+    int npeer = 0;                   // > 0: pv / pstats are valid (reduce_mode 4 and 5)
+    int peer_push = 0;               // reduce_mode 4: the bearing kernel writes into every replica
     S* pv[kMaxPeers] = {};
     double* pstats[kMaxPeers] = {};
 };
@@ -146,6 +147,21 @@ struct PeerBarrier {
     unsigned long long epoch;
 };
 int launch_peer_barrier(const PeerBarrier& pb, cudaStream_t st);
+// reduce_mode 5: after a LOCAL sharded build (mode 3's kernels) and a cross-GPU barrier, one kernel PULLS what the rank lacks from the peers'
+// replicas -- the owners' pose ranges (copied in place), the landmark parts of all ranks and the few rank-boundary poses (summed in rank order
+// into a scratch: the peers are still reading this rank's parts), the statistics -- and after a second barrier a commit kernel moves the scratch
+// into the replica.  Bulk, coalesced NVLink reads instead of mode 4's per-scalar remote writes.
+// element offset (in S) of the four double statistics inside the pull scratch: behind 5 NL landmark totals and 9 kMaxPeers boundary totals, 8-byte aligned
+__host__ __device__ inline long long peer_scratch_stats_off(int NL) { return (5LL * NL + 9 * kMaxPeers + 1) & ~1LL; }
+struct PeerPull {
+    int n, rank, NP, NL;
+    int own_p0[kMaxPeers + 1];   // pose ranges owned by the ranks' tiles
+    int bnd[kMaxPeers];          // last owned pose of rank q when its bearing run continues into rank q + 1's first tile (summed from both), else -1
+};
+template <typename S>
+int launch_peer_pull(const Dev<S>& d, const PeerPull& pp, S* scratch, int sm_count, cudaStream_t st);
+template <typename S>
+int launch_peer_commit(const Dev<S>& d, const PeerPull& pp, const S* scratch, cudaStream_t st);
 
 struct ShardRange {
     int b_begin = 0, b_end = 0, o_begin = 0, o_end = 0;

@@ -123,6 +123,7 @@ struct bos_ctx {
     void* peer_opened[kMaxPeers] = {};            // what cudaIpcOpenMemHandle returned (to close)
     bool peers_open = false;
     unsigned long long peer_epoch = 0;
+    void* peer_scratch = nullptr;                 // reduce_mode 5: totals pulled from the peers, committed after the second barrier
     ShardRange shard;
     std::vector<int> own_p0;              // [nranks + 1] first pose owned by each rank's tiles (a pose belongs to the tile its run starts in)
     int shard_chunk_b = 0;
@@ -518,8 +519,9 @@ void close_peers(bos_ctx* c) {
     }
     c->peers_open = false;
     c->peer_epoch = 0;
-    if (c->reduce_mode == 4) c->reduce_mode = 3;
-    c->dd.npeer = 0; c->df.npeer = 0;
+    if (c->reduce_mode == 4 || c->reduce_mode == 5) c->reduce_mode = 3;
+    c->dd.npeer = 0; c->df.npeer = 0; c->dd.peer_push = 0; c->df.peer_push = 0;
+    c->peer_scratch = nullptr;   // owned by c->mem
     c->dd.stats_k2 = c->dd.stats; c->df.stats_k2 = c->df.stats;
 }
 
@@ -527,13 +529,14 @@ void close_peers(bos_ctx* c) {
 template <typename S>
 void apply_peer_mode(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
-    const bool on = c->reduce_mode == 4 && c->peers_open && c->nranks > 1;
+    const bool on = (c->reduce_mode == 4 || c->reduce_mode == 5) && c->peers_open && c->nranks > 1;
     d.npeer = on ? c->nranks : 0;
+    d.peer_push = (on && c->reduce_mode == 4) ? 1 : 0;
     for (int r = 0; r < kMaxPeers; r++) {
         d.pv[r] = (on && r < c->nranks) ? reinterpret_cast<S*>(c->peer_base[r]) : nullptr;
         d.pstats[r] = (on && r < c->nranks) ? reinterpret_cast<double*>(c->peer_base[r] + c->tail_off) : nullptr;
     }
-    d.stats_k2 = on ? d.stats + kTailStatsK2 : d.stats;
+    d.stats_k2 = d.peer_push ? d.stats + kTailStatsK2 : d.stats;
 }
 
 int peer_barrier(bos_ctx* c, const double* publish) {
@@ -562,6 +565,28 @@ int allreduce_impl(bos_ctx* c) {
         // rank that ALL ranks' kernels have finished (their remote writes are visible after their kernel boundary) and publishes the
         // odometry share of the statistics.
         c->launches += peer_barrier(c, dev<S>(c).stats + kTailStatsK2);
+        CUDA_OK(c, cudaGetLastError());
+        return BOS_OK;
+    }
+    if (c->nranks > 1 && c->reduce_mode == 5) {
+        // pull-based combine over peer memory: barrier (every rank's local build is complete) | pull the owners' pose ranges in place, sum the
+        // landmark parts / rank-boundary poses / statistics of all ranks into a scratch | barrier (nobody reads this rank's parts any more) | commit
+        Dev<S>& dp = dev<S>(c);
+        PeerPull pp;
+        pp.n = c->nranks; pp.rank = c->rank; pp.NP = c->P.NP; pp.NL = c->P.NL;
+        for (int r = 0; r <= kMaxPeers; r++) pp.own_p0[r] = c->own_p0[std::min(r, c->nranks)];
+        for (int r = 0; r < kMaxPeers; r++) {
+            pp.bnd[r] = -1;
+            if (r + 1 >= c->nranks || c->own_p0[r + 1] <= c->own_p0[r]) continue;
+            const int pb = c->own_p0[r + 1] - 1;
+            int64_t q[4];
+            shard_ranges(c->P.Eb, c->P.Eo, r, c->nranks, q, nullptr);
+            if (c->P.epose_ptr[pb + 1] > (int)q[1] && c->P.epose_ptr[pb] < (int)q[1]) pp.bnd[r] = pb;
+        }
+        c->launches += peer_barrier(c, nullptr);
+        c->launches += launch_peer_pull<S>(dp, pp, static_cast<S*>(c->peer_scratch), c->sm_count, c->stream);
+        c->launches += peer_barrier(c, nullptr);
+        c->launches += launch_peer_commit<S>(dp, pp, static_cast<const S*>(c->peer_scratch), c->stream);
         CUDA_OK(c, cudaGetLastError());
         return BOS_OK;
     }
@@ -623,10 +648,10 @@ int linearize_impl(bos_ctx* c) {
     Dev<S>& d = dev<S>(c);
     const bool multi = c->nranks > 1;
     const bool zero_hpl = !c->P.slots_identity || (multi && !((c->reduce_mode >= 2 || (c->reduce_mode == 1 && c->nranks <= 8)) && c->P.slots_identity));
-    const bool peer = multi && c->reduce_mode == 4;
-    if (peer && !(c->peers_open && c->P.slots_identity && c->nranks <= kMaxPeers))
-        return fail(c, BOS_ERR_STATE, "reduce_mode 4 needs bos_peer_open after the problem upload, at most 8 ranks and no duplicate (pose, landmark) edges");
-    const bool owned = multi && (c->reduce_mode == 3 || peer) && c->P.slots_identity;   // every rank writes every pose-pose block itself
+    const bool peer = multi && c->reduce_mode == 4, pull = multi && c->reduce_mode == 5;
+    if ((peer || pull) && !(c->peers_open && c->P.slots_identity && c->nranks <= kMaxPeers))
+        return fail(c, BOS_ERR_STATE, "reduce_mode 4 / 5 need bos_peer_open after the problem upload, at most 8 ranks and no duplicate (pose, landmark) edges");
+    const bool owned = multi && (c->reduce_mode == 3 || peer || pull) && c->P.slots_identity;   // every rank writes every pose-pose block itself
     const bool zero_hoff = (multi && !owned) || c->P.has_shared_off;
     // NCCL modes SUM the replicas' landmark blocks: only rank 0 contributes the damping.  Peer mode: every replica receives every rank's REDs
     // on top of its own initialisation, so every replica starts from the full damping.
@@ -639,7 +664,7 @@ int linearize_impl(bos_ctx* c) {
         c->launches += peer_barrier(c, nullptr);
         c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, false, c->rank, true, 2);
     } else {
-        if (d.npeer) apply_peer_mode<S>(c);
+        if (d.npeer || pull) apply_peer_mode<S>(c);
         c->launches += launch_linearize<S>(d, c->shard, c->opt.kernel_threshold, c->opt.damping, damp_here, zero_hpl, zero_hoff, c->sm_count, c->stream, multi && !owned, c->rank, owned);
     }
     CUDA_OK(c, cudaGetLastError());
@@ -1286,8 +1311,8 @@ int bos_comm_init(bos_ctx* c, int rank, int nranks, const char* uid128) {
 }
 
 int bos_set_reduce_mode(bos_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 4) return BOS_ERR_INVALID;
-    if (mode == 4 && !c->peers_open) return fail(c, BOS_ERR_STATE, "reduce_mode 4: call bos_peer_open first (after bos_upload_problem)");
+    if (!c || mode < 0 || mode > 5) return BOS_ERR_INVALID;
+    if (mode >= 4 && !c->peers_open) return fail(c, BOS_ERR_STATE, "reduce_mode 4 / 5: call bos_peer_open first (after bos_upload_problem)");
     c->reduce_mode = mode;
     return BOS_OK;
 }
@@ -1337,6 +1362,8 @@ int bos_peer_open(bos_ctx* c, const void* handles, const int64_t* offsets) {
         c->peer_opened[r] = p;
         c->peer_base[r] = static_cast<unsigned char*>(p) + offsets[r];
     }
+    c->peer_scratch = c->mem.get<double>((size_t)peer_scratch_stats_off(c->P.NL) + 8);
+    if (!c->peer_scratch) { close_peers(c); return fail(c, BOS_ERR_NOMEM, "peer scratch allocation failed"); }
     c->peers_open = true;
     return BOS_OK;
 }

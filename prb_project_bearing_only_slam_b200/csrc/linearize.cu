@@ -461,6 +461,76 @@ int launch_peer_barrier(const PeerBarrier& pb, cudaStream_t st) {
     return 1;
 }
 
+// ---- reduce_mode 5: pull-based combine over peer memory -----------------------------------------------------------------------
+// scratch layout (S): [5 NL] landmark totals (Hll 3/landmark, then b_l 2/landmark) | [9 kMaxPeers] boundary-pose totals (Hpp 6, b 3) | [4] statistics (as S)
+template <typename S>
+__global__ void __launch_bounds__(256) k_peer_pull(Dev<S> d, PeerPull pp, S* __restrict__ T) {
+    const long long nA = 6LL * pp.NP, nB = 3LL * pp.NP, nC = 5LL * pp.NL, nD = 9LL * (pp.n - 1), nE = 4;
+    const long long total = nA + nB + nC + nD + nE;
+    const long long oHpp = d.Hpp - d.vals, oHll = d.Hll - d.vals, oBl = 3LL * pp.NP;
+    auto owner = [&](int p) { int q = 0; while (q + 1 < pp.n && p >= pp.own_p0[q + 1]) q++; return q; };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (i < nA + nB) {                    // pose blocks / rhs: copied in place from the owner's replica (nobody reads this rank's copy of them)
+            const bool hp = i < nA;
+            const long long e = hp ? i : i - nA;
+            const int p = (int)(hp ? e / 6 : e / 3);
+            const int q = owner(p);
+            if (q == pp.rank || p == pp.bnd[q]) continue;
+            const long long off = hp ? oHpp + e : e;
+            d.vals[off] = __ldcg(d.pv[q] + off);
+        } else if (i < nA + nB + nC) {        // landmark blocks and b_l: the sum of every rank's part, in rank order (identical on all ranks)
+            const long long e = i - nA - nB;
+            const long long off = e < 3LL * pp.NL ? oHll + e : oBl + (e - 3LL * pp.NL);
+            S s = S(0);
+            for (int q = 0; q < pp.n; q++) s += __ldcg(d.pv[q] + off);
+            T[e] = s;
+        } else if (i < nA + nB + nC + nD) {   // the pose whose run straddles the boundary between rank q and rank q + 1
+            const long long e = i - nA - nB - nC;
+            const int q = (int)(e / 9), k = (int)(e % 9), p = pp.bnd[q];
+            if (p < 0) continue;
+            const long long off = k < 6 ? oHpp + 6LL * p + k : 3LL * p + (k - 6);
+            T[nC + e] = __ldcg(d.pv[q] + off) + __ldcg(d.pv[q + 1] + off);
+        } else {                              // chi2 / over-threshold counts of the ranks' shares
+            const int k = (int)(i - nA - nB - nC - nD);
+            double s = 0.0;
+            for (int q = 0; q < pp.n; q++) s += __ldcg(d.pstats[q] + k);
+            reinterpret_cast<double*>(T + peer_scratch_stats_off(pp.NL))[k] = s;   // 8-byte aligned slot behind the boundary totals
+        }
+    }
+}
+template <typename S>
+__global__ void __launch_bounds__(256) k_peer_commit(Dev<S> d, PeerPull pp, const S* __restrict__ T) {
+    const long long nC = 5LL * pp.NL, nD = 9LL * (pp.n - 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nC + nD + 4; i += (long long)gridDim.x * blockDim.x) {
+        if (i < nC) {
+            if (i < 3LL * pp.NL) d.Hll[i] = T[i]; else d.b[3LL * pp.NP + (i - 3LL * pp.NL)] = T[i];
+        } else if (i < nC + nD) {
+            const long long e = i - nC;
+            const int q = (int)(e / 9), k = (int)(e % 9), p = pp.bnd[q];
+            if (p < 0) continue;
+            if (k < 6) d.Hpp[6LL * p + k] = T[i]; else d.b[3LL * p + (k - 6)] = T[i];
+        } else {
+            const int k = (int)(i - nC - nD);
+            d.stats[k] = reinterpret_cast<const double*>(T + peer_scratch_stats_off(pp.NL))[k];
+        }
+    }
+}
+template <typename S>
+int launch_peer_pull(const Dev<S>& d, const PeerPull& pp, S* scratch, int sm_count, cudaStream_t st) {
+    k_peer_pull<S><<<sm_count * 8, 256, 0, st>>>(d, pp, scratch);
+    return 1;
+}
+template <typename S>
+int launch_peer_commit(const Dev<S>& d, const PeerPull& pp, const S* scratch, cudaStream_t st) {
+    const long long n = 5LL * pp.NL + 9LL * (pp.n - 1) + 4;
+    k_peer_commit<S><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, pp, scratch);
+    return 1;
+}
+template int launch_peer_pull<double>(const Dev<double>&, const PeerPull&, double*, int, cudaStream_t);
+template int launch_peer_pull<float>(const Dev<float>&, const PeerPull&, float*, int, cudaStream_t);
+template int launch_peer_commit<double>(const Dev<double>&, const PeerPull&, const double*, cudaStream_t);
+template int launch_peer_commit<float>(const Dev<float>&, const PeerPull&, const float*, cudaStream_t);
+
 // no bearing edges at all (a pure pose graph): nobody walks tiles, so the poses are finished here
 template <typename S>
 __global__ void __launch_bounds__(128) k_pose_finish_nobearing(Dev<S> d, S damping) {
@@ -517,7 +587,7 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
         cfg.attrs = at; cfg.numAttrs = 1;
         const int eb = r.b_begin, ee = r.b_end;
         const S kt = (S)kernel_threshold, dm = (S)damping;
-        if (d.npeer > 0 && d.b_slot == nullptr) {
+        if (d.peer_push && d.npeer > 0 && d.b_slot == nullptr) {
             ensure_dyn_smem((const void*)k_linearize_bearing_persistent<S, true, true>, smem);
             cudaLaunchKernelEx(&cfg, k_linearize_bearing_persistent<S, true, true>, d, eb, ee, kt, dm);
         } else if (d.b_slot == nullptr)

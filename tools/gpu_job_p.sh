@@ -3,7 +3,7 @@
 set -u
 O=gpurun_out
 mkdir -p $O
-for m in 4 3; do
+for m in 5 3; do
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$m bench.py --gpus 2 --steps 20 --warmup 5 --reduce-mode $m > $O/bench_n2_mode${m}_r02.json 2> $O/bench_n2_mode${m}_r02.err
 python - $m <<'PY'
 import json, sys

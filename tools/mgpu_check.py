@@ -3,7 +3,8 @@ Every rank builds the same synthetic world; rank r linearizes its edge shard on 
 hold the same H, b, chi2 as an unsharded context (1e-12 relative: only the summation order differs), for every reduce mode
 (0 full allreduce, 1 allreduce of the overlapping blocks + allgather of the pose-landmark planes, 2 allreduce of the overlapping
 blocks only, 3 ownership-based: landmark blocks summed, owned pose ranges gathered, 4 the same ownership with the bearing kernel writing
-straight into every rank's replica over NVLink peer memory, no collective), and a full step must give the same state."""
+straight into every rank's replica over NVLink peer memory, no collective, 5 a local build followed by bulk pulls over the same peer
+mappings), and a full step must give the same state."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,13 +30,13 @@ P0, L0 = ref.get_state()
 ref.linearize()
 rb = ref.blocks(); rs = ref.stats()
 ok = True
-for mode in (0, 1, 2, 3, 4):
+for mode in (0, 1, 2, 3, 4, 5):
     ctx = capi.Context(device=local, solver=capi.SOLVER_PCG, pcg_rtol=1e-12, pcg_max_iters=20000)
     pr.upload(ctx)
     uid = [capi.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0])
-    if mode == 4:                      # fused build + combine over NVLink peer memory: exchange the CUDA IPC handles of the value buffers
+    if mode >= 4:                      # combine over NVLink peer memory (4: pushed by the bearing kernel, 5: pulled in bulk): exchange the CUDA IPC handles
         ctx.peer_connect(dist)
     ctx.set_reduce_mode(mode)
     ctx.set_state(P0, L0)
@@ -51,14 +52,14 @@ for mode in (0, 1, 2, 3, 4):
             or s.over_bearing != rs.over_bearing or s.over_odometry != rs.over_odometry:
         ok = False
         print("rank %d mode %d chi2 mismatch" % (rank, mode), s.chi2_bearing, rs.chi2_bearing, s.chi2_odometry, rs.chi2_odometry, flush=True)
-    if mode == 4:                      # several builds in a row: the barrier epochs and the re-initialisation of the replicas hold up
+    if mode >= 4:                      # several builds in a row: the barrier epochs and the re-initialisation of the replicas hold up
         for _ in range(3):
             ctx.linearize()
         b2 = ctx.blocks()
         for k in ("Hpp", "Hll", "Hoff", "b"):
             if np.abs(b2[k] - rb[k]).max() > 1e-12 * max(np.abs(rb[k]).max(), 1e-300):
                 ok = False
-                print("rank %d mode 4 repeated build: %s mismatch" % (rank, k), flush=True)
+                print("rank %d mode %d repeated build: %s mismatch" % (rank, mode, k), flush=True)
     ctx.set_state(P0, L0); ref.set_state(P0, L0)
     st = ctx.step(); ref.step()
     Pa, La = ctx.get_state(); Pb, Lb = ref.get_state()
