@@ -466,36 +466,55 @@ int launch_peer_barrier(const PeerBarrier& pb, cudaStream_t st) {
 template <typename S>
 __global__ void __launch_bounds__(256) k_peer_pull(Dev<S> d, PeerPull pp, S* __restrict__ T) {
     const long long nA = 6LL * pp.NP, nB = 3LL * pp.NP, nC = 5LL * pp.NL, nD = 9LL * (pp.n - 1), nE = 4;
-    const long long total = nA + nB + nC + nD + nE;
     const long long oHpp = d.Hpp - d.vals, oHll = d.Hll - d.vals, oBl = 3LL * pp.NP;
+    const long long gsz = (long long)gridDim.x * blockDim.x, gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     auto owner = [&](int p) { int q = 0; while (q + 1 < pp.n && p >= pp.own_p0[q + 1]) q++; return q; };
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        if (i < nA + nB) {                    // pose blocks / rhs: copied in place from the owner's replica (nobody reads this rank's copy of them)
+    // pose blocks / rhs: copied in place from the owner's replica (nobody reads this rank's copy of them); four independent NVLink loads in
+    // flight per thread -- a remote load takes microseconds, the link is only busy when many of them overlap
+    for (long long i0 = gid; i0 < nA + nB; i0 += 4 * gsz) {
+        S v[4];
+        long long off[4];
+        bool take[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = i0 + u * gsz;
+            take[u] = false; off[u] = 0; v[u] = S(0);
+            if (i >= nA + nB) continue;
             const bool hp = i < nA;
             const long long e = hp ? i : i - nA;
             const int p = (int)(hp ? e / 6 : e / 3);
             const int q = owner(p);
             if (q == pp.rank || p == pp.bnd[q]) continue;
-            const long long off = hp ? oHpp + e : e;
-            d.vals[off] = __ldcg(d.pv[q] + off);
-        } else if (i < nA + nB + nC) {        // landmark blocks and b_l: the sum of every rank's part, in rank order (identical on all ranks)
-            const long long e = i - nA - nB;
-            const long long off = e < 3LL * pp.NL ? oHll + e : oBl + (e - 3LL * pp.NL);
-            S s = S(0);
-            for (int q = 0; q < pp.n; q++) s += __ldcg(d.pv[q] + off);
-            T[e] = s;
-        } else if (i < nA + nB + nC + nD) {   // the pose whose run straddles the boundary between rank q and rank q + 1
-            const long long e = i - nA - nB - nC;
-            const int q = (int)(e / 9), k = (int)(e % 9), p = pp.bnd[q];
-            if (p < 0) continue;
-            const long long off = k < 6 ? oHpp + 6LL * p + k : 3LL * p + (k - 6);
-            T[nC + e] = __ldcg(d.pv[q] + off) + __ldcg(d.pv[q + 1] + off);
-        } else {                              // chi2 / over-threshold counts of the ranks' shares
-            const int k = (int)(i - nA - nB - nC - nD);
-            double s = 0.0;
-            for (int q = 0; q < pp.n; q++) s += __ldcg(d.pstats[q] + k);
-            reinterpret_cast<double*>(T + peer_scratch_stats_off(pp.NL))[k] = s;   // 8-byte aligned slot behind the boundary totals
+            off[u] = hp ? oHpp + e : e;
+            take[u] = true;
+            v[u] = __ldcg(d.pv[q] + off[u]);
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (take[u]) d.vals[off[u]] = v[u];
+    }
+    // landmark blocks and b_l: the sum of every rank's part, in rank order (identical on all ranks); all ranks' loads issued before the adds
+    for (long long e = gid; e < nC; e += gsz) {
+        const long long off = e < 3LL * pp.NL ? oHll + e : oBl + (e - 3LL * pp.NL);
+        S part[kMaxPeers];
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; q++) part[q] = q < pp.n ? __ldcg(d.pv[q] + off) : S(0);
+        S s = S(0);
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; q++) s += part[q];
+        T[e] = s;
+    }
+    if (gid < nD) {                           // the pose whose run straddles the boundary between rank q and rank q + 1
+        const int q = (int)(gid / 9), k = (int)(gid % 9), p = pp.bnd[q];
+        if (p >= 0) {
+            const long long off = k < 6 ? oHpp + 6LL * p + k : 3LL * p + (k - 6);
+            T[nC + gid] = __ldcg(d.pv[q] + off) + __ldcg(d.pv[q + 1] + off);
+        }
+    } else if (gid < nD + nE) {               // chi2 / over-threshold counts of the ranks' shares
+        const int k = (int)(gid - nD);
+        double s = 0.0;
+        for (int q = 0; q < pp.n; q++) s += __ldcg(d.pstats[q] + k);
+        reinterpret_cast<double*>(T + peer_scratch_stats_off(pp.NL))[k] = s;   // 8-byte aligned slot behind the boundary totals
     }
 }
 template <typename S>
