@@ -308,6 +308,26 @@ def run_reference(args):
     if solver == "superlu":
         line["solve_residual"] = steps[-1]["residual"]
     if literal:
+        # the reference's OWN compiled sources (oracle/_ref: built against the stand-in for Eigen, whose std::map-based sparse containers are not
+        # Eigen's -- a figure beside the headline, not the headline)
+        try:
+            from oracle import ref as _ref
+            if _ref.available():
+                rf = _ref.Reference()
+                rf.set_problem(w["pose_ids"], w["poses_init"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"],
+                               w["o_omega"], fixed_id=pr.fixed_pose_id)
+                rf.triangulate(); rf.solver_init(pr.fixed_pose_id)
+                rf.step()
+                n_ref = 3 if args.workload == "full" else 50
+                t0 = time.perf_counter()
+                for _ in range(n_ref):
+                    rf.step()
+                t_ref = (time.perf_counter() - t0) / n_ref
+                line["reference_own_sources"] = {"gn_iterations_per_s": 1.0 / t_ref, "steps": n_ref, "kind": "reference",
+                                                 "what": "proj02::Solver::step() of the reference's unmodified sources (oracle/_ref), float, compiled against "
+                                                         "oracle/eigen_standin instead of Eigen3"}
+        except OSError as e:
+            line["reference_own_sources"] = {"unavailable": str(e)}
         line["literal_reference_accumulation"] = literal
         line["restated_assembly"] = restated
         line["cpu_baseline"]["sample"] += "; linearize + assemble here = the reference's LITERAL per-edge sparse merge (slam/solver.cpp:44,60), FP32, %.3f s" % t_lin
