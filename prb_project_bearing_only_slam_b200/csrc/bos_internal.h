@@ -198,6 +198,13 @@ struct DenseWork {
     int sky_W = 0;
     std::vector<int> sky_panel_end;
     double sky_fill = 0.0;  // stored entries / (n (n + 1) / 2)
+    // The launch sequence of a solve (hundreds to thousands of small kernels: one POTRF / TRSM / update per 64-column panel, one launch per
+    // substitution block) depends only on the pattern: after one eager solve it is captured into a CUDA graph and replayed.  The captured
+    // kernel arguments are the bytes of Dev<S> and of the work pointers: the graph is dropped when they change (new problem, robust mode).
+    cudaGraphExec_t graph = nullptr;
+    int graph_launches = 0, eager_calls = 0;
+    bool graph_failed = false;
+    std::vector<unsigned char> graph_key;
 };
 
 template <typename S>

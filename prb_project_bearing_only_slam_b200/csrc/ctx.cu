@@ -959,6 +959,8 @@ int bos_destroy(bos_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     close_peers(c);
+    for (cudaGraphExec_t* g : {&c->dwd.graph, &c->dwf.graph, &c->swd.graph, &c->swf.graph})
+        if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
     c->mem.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto& e : c->ev)

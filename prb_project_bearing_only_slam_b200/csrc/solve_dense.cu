@@ -10,6 +10,7 @@
 #include "bos_internal.h"
 
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include "bos_math.cuh"
 #include "bos_schur.cuh"
@@ -473,8 +474,54 @@ template int dense_cholesky_lower<float>(float*, int, double*, cudaStream_t);
 // Schur complement of the landmark blocks into a dense (ld = n) or skyline (w.sky: ld = W - 1, W rows per column) lower triangle, Cholesky,
 // the two triangular solves, landmark back-substitution
 template <typename S>
+static int dense_solve_eager(const Dev<S>& d, DenseWork<S>& w, cudaStream_t st, int* launches);
+
+template <typename S>
 int launch_dense_solve(const Dev<S>& d, DenseWork<S>& w, double damping, cudaStream_t st, int* launches) {
     (void)damping;
+    static const bool no_graph = std::getenv("BOS_NO_GRAPH") != nullptr;
+    // what the captured kernels were given: the device view and the work buffers
+    std::vector<unsigned char> key(sizeof(Dev<S>) + 6 * sizeof(void*) + 3 * sizeof(int));
+    {
+        unsigned char* k = key.data();
+        std::memcpy(k, &d, sizeof(Dev<S>)); k += sizeof(Dev<S>);
+        const void* ptrs[6] = {w.Smat, w.g, w.hllinv, w.ul, w.tl, w.tl_blk};
+        std::memcpy(k, ptrs, sizeof(ptrs)); k += sizeof(ptrs);
+        const int ints[3] = {w.n, w.sky ? 1 : 0, w.sky_W};
+        std::memcpy(k, ints, sizeof(ints));
+    }
+    if (w.graph && key != w.graph_key) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; w.eager_calls = 0; w.graph_failed = false; }
+    if (w.graph) {
+        if (cudaGraphLaunch(w.graph, st) != cudaSuccess) return -1;
+        if (launches) *launches = w.graph_launches;
+        return 0;
+    }
+    if (!no_graph && !dbg_sync_on() && !w.graph_failed && w.eager_calls >= 1) {
+        // the first solve ran eagerly (function attributes set, modules loaded); capture this one
+        int nl = 0;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = dense_solve_eager<S>(d, w, st, &nl);
+            cudaGraph_t g = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(st, &g);
+            cudaGraphExec_t ge = nullptr;
+            if (rc == 0 && e == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+                cudaGraphDestroy(g);
+                w.graph = ge; w.graph_launches = nl; w.graph_key = key;
+                if (cudaGraphLaunch(w.graph, st) != cudaSuccess) return -1;
+                if (launches) *launches = nl;
+                return 0;
+            }
+            if (g) cudaGraphDestroy(g);
+        }
+        cudaGetLastError();
+        w.graph_failed = true;      // stay eager
+    }
+    w.eager_calls++;
+    return dense_solve_eager<S>(d, w, st, launches);
+}
+
+template <typename S>
+static int dense_solve_eager(const Dev<S>& d, DenseWork<S>& w, cudaStream_t st, int* launches) {
     int nl = 0;
     const int n = w.n;
     const bool sky = w.sky;
