@@ -31,3 +31,24 @@ def test_two_ranks_sharded_build_and_step_equal_single_gpu(built_lib, size):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "MGPU_CHECK OK world 2" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_peer_modes_need_the_peer_mappings(built_lib):
+    """reduce_mode 4 / 5 (combines over NVLink peer memory) are refused until the ranks' value buffers have been exchanged and opened;
+    the export half works on a single GPU (handle + offset of the one allocation that holds values, statistics and barrier slots)."""
+    from helpers import synth_problem
+    from prb_project_bearing_only_slam_b200 import capi
+    _, pr = synth_problem(300, 80, 3000, seed=5)
+    ctx = capi.Context(solver=capi.SOLVER_PCG)
+    with pytest.raises(capi.BosError):
+        ctx.peer_export()                       # nothing uploaded yet
+    pr.upload(ctx)
+    for mode in (4, 5):
+        with pytest.raises(capi.BosError):
+            ctx.set_reduce_mode(mode)
+    handle, offset = ctx.peer_export()
+    assert len(handle) == capi.IPC_HANDLE_BYTES and offset >= 0 and any(handle)
+    with pytest.raises(capi.BosError):
+        ctx.peer_open([handle], [offset])       # a single rank has no peers
+    ctx.set_reduce_mode(3)
+    ctx.close()
