@@ -74,11 +74,11 @@ typedef struct bos_options {
                                  (also what FP32 and pcg_variant 1 run).  All converge to the same solution at pcg_rtol. */
     int pcg_coarse_nodes;     /* coarse-space nodes per chunk of the default preconditioner: 0 = default (4), 1 = the round-1 layout (one
                                  hat per chunk); rounded so that segments are whole groups of 32 poses, at most 8 */
-    int pcg_coarse_refresh;   /* the coarse operator's inverse is kept across GN steps and rebuilt every this many solves (also whenever
-                                 the state is replaced through the API or the CG iteration count drifts up by 25 %); 0 = default (8),
-                                 1 = rebuild for every solve.  The period doubles (up to 8x) each time a scheduled rebuild saves fewer than
-                                 two CG iterations -- near convergence A_c hardly changes -- and falls back when one pays again.  Any SPD
-                                 coarse operator is a valid preconditioner: only the iteration count depends on it, never the solution */
+    int pcg_coarse_refresh;   /* the coarse operator's inverse is kept across GN steps.  1 = rebuild for every solve; otherwise (0 = default = 8) it is
+                                 rebuilt when that pays -- once the CG iterations spent above the post-rebuild count add up to the measured price
+                                 of a rebuild (about 31 iterations on the 200 k-pose world) --, at the latest after 8 x this many solves, and
+                                 whenever the state is replaced through the API or the CG iteration count drifts up by 25 %.  Any SPD coarse
+                                 operator is a valid preconditioner: only the iteration count depends on it, never the solution */
     int reserved[4];
 } bos_options;
 

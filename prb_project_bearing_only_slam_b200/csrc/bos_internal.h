@@ -268,7 +268,11 @@ struct PcgWork {
     // state was replaced from outside (coarse_valid = false) and when the CG iteration count drifts (coarse_stale)
     bool coarse_valid = false, coarse_stale = false;
     int coarse_age = 0, coarse_refresh = 1, coarse_its_ref = 0;
-    int coarse_period = 0, coarse_its_last = 0;   // current refresh period (grows while refreshes stop paying), iterations of the previous solve
+    int coarse_period = 0, coarse_its_last = 0;   // (unused since the amortised schedule) / iterations of the previous solve
+    // amortised refresh schedule: CG iterations spent above the post-refresh count since the last rebuild, and what a rebuild costs in CG iterations
+    // (measured with CUDA events on every rebuilding solve: refresh kernels / (fused kernel / iterations))
+    double coarse_excess = 0.0, coarse_ratio = 32.0;
+    cudaEvent_t coarse_ev[3] = {nullptr, nullptr, nullptr};
     double* host_scal = nullptr;                  // 32 doubles of PINNED host memory (owned by the context): where the solve's scalars are read back
     double* cA = nullptr;    // [c_nc][c_nc] column-major lower: A_c, then its Cholesky factor
     double* cAinv = nullptr; // [c_nc][c_ld] A_c^-1 (full, symmetric)

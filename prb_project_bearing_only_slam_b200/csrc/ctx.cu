@@ -493,7 +493,7 @@ int ensure_pcg(bos_ctx* c) {
             w.c_bw = (bw <= 158) ? std::min(bw, w.c_nc - 1) : 0;
             if (w.c_bw < 1 && w.c_nc > 1) w.c_bw = (bw <= 158) ? 1 : 0;
             w.coarse_refresh = c->opt.pcg_coarse_refresh > 0 ? c->opt.pcg_coarse_refresh : 8;
-            w.coarse_valid = false; w.coarse_stale = false; w.coarse_age = 0; w.coarse_period = 0; w.coarse_its_last = 0;
+            w.coarse_valid = false; w.coarse_stale = false; w.coarse_age = 0; w.coarse_period = 0; w.coarse_its_last = 0; w.coarse_excess = 0.0;
         }
         w.cA = c->mem.get<double>((size_t)w.c_nc * w.c_nc);
         w.c_ld = (w.c_nc + 3) / 4 * 4;
@@ -961,6 +961,10 @@ int bos_destroy(bos_ctx* c) {
     close_peers(c);
     for (cudaGraphExec_t* g : {&c->dwd.graph, &c->dwf.graph, &c->swd.graph, &c->swf.graph})
         if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
+    for (int k = 0; k < 3; k++) {
+        if (c->pwd.coarse_ev[k]) cudaEventDestroy(c->pwd.coarse_ev[k]);
+        if (c->pwf.coarse_ev[k]) cudaEventDestroy(c->pwf.coarse_ev[k]);
+    }
     c->mem.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto& e : c->ev)

@@ -1868,13 +1868,21 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     k_pcg_fused_prep<S><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(d, w); nl++;
     if (precond != 1) { k_pcg_chain_factor<S><<<d.pc_chunks, 64, 0, st>>>(d, w); nl++; }
     // coarse operator A_c = P^T S P, its Cholesky factor and explicit inverse.  Any SPD coarse operator makes a valid preconditioner, so A_c^-1 is
-    // kept across GN steps and refreshed every w.coarse_refresh solves, after the state was replaced from outside, or when the CG iteration
-    // count drifts above what it was right after the last refresh (coarse_stale).
-    // The period starts at pcg_coarse_refresh solves and DOUBLES (up to 8x) every time a scheduled refresh did not pay -- near convergence the
-    // state, hence A_c, hardly changes; a refresh that does cut the iteration count, a stale flag or an invalidation resets it.
-    if (w.coarse_period < w.coarse_refresh) w.coarse_period = w.coarse_refresh;
-    const bool refresh = precond == 0 && (!w.coarse_valid || w.coarse_age >= w.coarse_period || w.coarse_stale);
-    const bool scheduled = refresh && w.coarse_valid && !w.coarse_stale;
+    // kept across GN steps.  It is rebuilt (a) after the state was replaced from outside or a breakdown (coarse_valid), (b) when the CG iteration
+    // count drifts 25 % above what it was right after the last rebuild (coarse_stale), (c) for every solve with pcg_coarse_refresh = 1, and
+    // otherwise (d) when it PAYS: a rebuild costs coarse_ratio CG iterations (measured below: 2.65 ms against 86 us per iteration at synth-2M = 31),
+    // a stale operator costs its - its_ref extra iterations per solve; rebuild once the extra iterations spent since the last rebuild add up to
+    // the price of one (the break-even rule of rent-or-buy), at the latest after 8 x pcg_coarse_refresh solves.
+    const bool every = w.coarse_refresh <= 1;
+    const bool due = every || w.coarse_age >= 8 * w.coarse_refresh || (w.coarse_age >= 2 && w.coarse_excess >= w.coarse_ratio);
+    const bool refresh = precond == 0 && (!w.coarse_valid || w.coarse_stale || due);
+    bool timed = false;
+    if (refresh) {
+        timed = true;
+        for (int k = 0; k < 3 && timed; k++)
+            if (!w.coarse_ev[k] && cudaEventCreate(&w.coarse_ev[k]) != cudaSuccess) { w.coarse_ev[k] = nullptr; cudaGetLastError(); timed = false; }
+        if (timed) cudaEventRecord(w.coarse_ev[0], st);
+    }
     if (refresh) {
         const int nc = w.c_nc;
         cudaMemsetAsync(w.cA, 0, sizeof(double) * (size_t)nc * nc, st);
@@ -1898,6 +1906,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
             k_coarse_inverse<IW><<<(nc + IW - 1) / IW, IW * 32, ism, st>>>(w.cA, w.cAinv, nc, w.c_ld); nl++;
         }
         w.coarse_valid = true; w.coarse_age = 0; w.coarse_stale = false;
+        if (timed) cudaEventRecord(w.coarse_ev[1], st);
     }
     if (precond == 0) w.coarse_age++;
     const PcgSmemPlan<S> plan(d.pc_cp, d.pc_cl_max, d.pc_slots_max, precond != 1, precond == 0 ? w.c_nc : 0);
@@ -1910,21 +1919,26 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     void* args[] = {(void*)&dd, (void*)&ww, (void*)&max_iters, (void*)&tol2};
     if (cudaLaunchCooperativeKernel((const void*)k_pcg_fused<S>, dim3(d.pc_chunks), dim3(kPcgThreads), args, plan.bytes, st) != cudaSuccess) return -1;
     nl++;
+    if (timed) cudaEventRecord(w.coarse_ev[2], st);
     double host_pageable[32];
     double* host_scal = w.host_scal ? w.host_scal : host_pageable;   // pinned: a true asynchronous copy instead of a staged one
     if (cudaMemcpyAsync(host_scal, w.scal, 32 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     if (iterations_out) *iterations_out = (int)host_scal[SC_ITER];
     if (launches) *launches = nl;
-    if (precond == 0) {   // iteration count right after a refresh is the yardstick for the following, lagged solves
+    if (precond == 0) {   // iteration count right after a rebuild is the yardstick for the following, lagged solves
         const int its = (int)host_scal[SC_ITER];
         if (refresh) {
             w.coarse_its_ref = its;
-            if (scheduled && w.coarse_refresh > 1) {   // did the rebuilt operator save at least two iterations over the one it replaced?
-                if (its + 2 > w.coarse_its_last) w.coarse_period = std::min(2 * w.coarse_period, 8 * w.coarse_refresh);
-                else w.coarse_period = w.coarse_refresh;
-            } else if (!scheduled) w.coarse_period = w.coarse_refresh;
-        } else if (its > w.coarse_its_ref + w.coarse_its_ref / 4 + 4) w.coarse_stale = true;
+            w.coarse_excess = 0.0;
+            float t_refresh = 0.f, t_solve = 0.f;
+            if (timed && its > 0 && cudaEventElapsedTime(&t_refresh, w.coarse_ev[0], w.coarse_ev[1]) == cudaSuccess &&
+                cudaEventElapsedTime(&t_solve, w.coarse_ev[1], w.coarse_ev[2]) == cudaSuccess && t_solve > 0.f)
+                w.coarse_ratio = std::min(256.0, std::max(4.0, (double)t_refresh / ((double)t_solve / its)));
+        } else {
+            if (its > w.coarse_its_ref) w.coarse_excess += its - w.coarse_its_ref;
+            if (its > w.coarse_its_ref + w.coarse_its_ref / 4 + 4) w.coarse_stale = true;
+        }
         w.coarse_its_last = its;
         if (host_scal[SC_BAD] != 0.0) w.coarse_valid = false;
     }
