@@ -611,9 +611,12 @@ __device__ __forceinline__ void mat3_tmul(const S a[9], const S b[9], S o[9]) { 
 }
 
 template <typename S>
-__global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w) {
+__global__ void __launch_bounds__(128) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w) {
     __shared__ S Eff[64][6], Ell[64][6], Efl[64][9], Dsep[64][6], Osep[64][9];
-    const int c = blockIdx.x, g = threadIdx.x, cp = d.pc_cp, K = cp / 32, Kp = w.ch_Kp, cps = w.ch_cps;
+    // threads 0-63: group g's downward elimination (the stored factors) and the corner blocks that follow from it; threads 64-127: the
+    // UPWARD elimination of the same group, which only yields [T^-1]_(0,0) and is independent of the first -- 61 instead of 91 sequential steps
+    const bool upper = threadIdx.x >= 64;
+    const int c = blockIdx.x, g = threadIdx.x & 63, cp = d.pc_cp, K = cp / 32, Kp = w.ch_Kp, cps = w.ch_cps;
     const size_t nrows = (size_t)d.pc_chunks * cp;
     float* F = w.chF + (size_t)c * w.ch_fac_floats;
     float* Fs = F + 16 * cps;
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w)
 #pragma unroll
         for (int q = 0; q < 6; q++) o[q] = w.chO[(size_t)q * nrows + R0 + k];
     };
-    if (g < K) {
+    if (g < K && !upper) {
         // downward elimination of the interior: L_k = O_{k-1} Delta_{k-1}^-1, Delta_k = D_k - L_k O_{k-1}
         S dinv[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, op[9];
         for (int k = 0; k < 31; k++) {
@@ -673,7 +676,10 @@ __global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w)
         }
 #pragma unroll
         for (int q = 0; q < 9; q++) Efl[g][q] = X[q];
+    }
+    if (g < K && upper) {
         // upward elimination: Delta'_30 = D_30, Delta'_k = D_k - O_k Delta'_{k+1}^-1 O_k; [T^-1]_(0,0) = Delta'_0^-1
+        S dinv[6];
         S up[6];
         ldD(30, up);
         sym3_inverse<S>(up, dinv);
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w)
         for (int q = 0; q < 6; q++) Eff[g][q] = dinv[q];
     }
     __syncthreads();
-    if (g < K) {
+    if (g < K && !upper) {
         // separator Schur system: eliminate the interiors on both sides of separator g
         S ct6[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, cb6[6], cn6[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, D[6];
         if (g > 0) ldO(-1, ct6);          // separator g-1 (row R0 - 1) <-> first interior row
@@ -718,7 +724,7 @@ __global__ void __launch_bounds__(64) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w)
         for (int q = 0; q < 12; q++) Fc[((q >> 2) * Kp + g) * 4 + (q & 3)] = (float)(q < 6 ? ct6[q] : cb6[q - 6]);
     }
     __syncthreads();
-    if (g == 0) {   // block LDL^T of the separator chain: L_j = Osep_j^T Delta_{j-1}^-1, Delta_j = Dsep_j - L_j Osep_j
+    if (threadIdx.x == 0) {   // block LDL^T of the separator chain: L_j = Osep_j^T Delta_{j-1}^-1, Delta_j = Dsep_j - L_j Osep_j
         S dinv[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
         for (int j = 0; j < K; j++) {
             S D[6], L[9] = {S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0)};
@@ -1866,7 +1872,7 @@ int launch_pcg_fused(const Dev<S>& d, PcgWork<S>& w, int max_iters, double rtol,
     w.precond = precond;
     w.precond_used = precond;
     k_pcg_fused_prep<S><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(d, w); nl++;
-    if (precond != 1) { k_pcg_chain_factor<S><<<d.pc_chunks, 64, 0, st>>>(d, w); nl++; }
+    if (precond != 1) { k_pcg_chain_factor<S><<<d.pc_chunks, 128, 0, st>>>(d, w); nl++; }
     // coarse operator A_c = P^T S P, its Cholesky factor and explicit inverse.  Any SPD coarse operator makes a valid preconditioner, so A_c^-1 is
     // kept across GN steps.  It is rebuilt (a) after the state was replaced from outside or a breakdown (coarse_valid), (b) when the CG iteration
     // count drifts 25 % above what it was right after the last rebuild (coarse_stale), (c) for every solve with pcg_coarse_refresh = 1, and
