@@ -633,9 +633,13 @@ __global__ void __launch_bounds__(128) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w
     if (g < K && !upper) {
         // downward elimination of the interior: L_k = O_{k-1} Delta_{k-1}^-1, Delta_k = D_k - L_k O_{k-1}
         S dinv[6] = {S(0), S(0), S(0), S(0), S(0), S(0)}, op[9];
+        S Dn[6], On[6];                      // row k's blocks are fetched one step ahead: the loads do not depend on the recurrence
+        ldD(0, Dn); ldO(0, On);
         for (int k = 0; k < 31; k++) {
-            S D[6], L[9] = {S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0)};
-            ldD(k, D);
+            S D[6], o6[6], L[9] = {S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0), S(0)};
+#pragma unroll
+            for (int q = 0; q < 6; q++) { D[q] = Dn[q]; o6[q] = On[q]; }
+            if (k + 1 < 31) { ldD(k + 1, Dn); ldO(k + 1, On); }
             if (k > 0) {
                 S di[9], lo[9];
                 sym6_to_full<S>(dinv, di);
@@ -652,8 +656,6 @@ __global__ void __launch_bounds__(128) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w
                 sym3_chol_to_float<S>(dinv, df);
                 chain_store_row(F + ((size_t)(k * 4) * Kp + g) * 4, Kp * 4, Lf, df);
             }
-            S o6[6];
-            ldO(k, o6);
             sym6_to_full<S>(o6, op);
         }
         {   // the separator's slot of the interior arrays is never read by the solve
@@ -683,9 +685,13 @@ __global__ void __launch_bounds__(128) k_pcg_chain_factor(Dev<S> d, PcgWork<S> w
         S up[6];
         ldD(30, up);
         sym3_inverse<S>(up, dinv);
+        S Dn[6], On[6];
+        ldD(29, Dn); ldO(29, On);
         for (int k = 29; k >= 0; k--) {
             S D[6], o6[6], o[9], di[9], t[9], lo[9];
-            ldD(k, D); ldO(k, o6);
+#pragma unroll
+            for (int q = 0; q < 6; q++) { D[q] = Dn[q]; o6[q] = On[q]; }
+            if (k > 0) { ldD(k - 1, Dn); ldO(k - 1, On); }
             sym6_to_full<S>(o6, o); sym6_to_full<S>(dinv, di);
             mat3_mul<S>(o, di, t);
             mat3_mul<S>(t, o, lo);
