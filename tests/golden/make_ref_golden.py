@@ -3,7 +3,8 @@ sources compiled against oracle/eigen_standin, see oracle/Makefile target `ref`)
 
     python tests/golden/make_ref_golden.py
 
-Cases: the two bundled datasets (parsed by the reference's own parse_g2o from /root/reference/data) and two small random worlds fed
+Cases: the two bundled datasets and their ground-truth flavours (parsed by the reference's own parse_g2o from /root/reference/data; the
+GT files carry VERTEX_XY lines: landmarks in file order, no triangulation) and two small random worlds fed
 through State::add_pose / the observation constructors (shuffled non-contiguous ids, a fixed pose in mid-chain, per-edge bearing
 omegas, full 3x3 odometry omegas, a loop closure with source > destination, outliers that trigger the threshold kernel, a landmark
 seen once).  Stored per case: the problem (random worlds only; mini / full are in mini.npz / full.npz), the id tables and the
@@ -21,7 +22,9 @@ from oracle import ref  # noqa: E402
 
 DATA = os.path.join(ref.REFERENCE_ROOT, "data")
 OUT = os.path.dirname(os.path.abspath(__file__))
-G2O = {"mini": ("mini_initial_guess.g2o", 50), "full": ("slam2D_bearing_only_initial_guess.g2o", 20)}
+G2O = {"mini": ("mini_initial_guess.g2o", 50), "full": ("slam2D_bearing_only_initial_guess.g2o", 20),
+       # the ground-truth files carry VERTEX_XY lines: landmarks enter the state in FILE order (no triangulation), the start is the GT state
+       "mini_gt": ("mini_ground_truth.g2o", 10), "full_gt": ("slam2D_bearing_only_ground_truth.g2o", 10)}
 CHECKPOINTS = [1, 2, 5, 10, 20, 50]
 
 
@@ -91,7 +94,7 @@ def run(name):
     if name in G2O:
         fname, iters = G2O[name]
         r.load_g2o(os.path.join(DATA, fname))
-        w = dict(np.load(os.path.join(OUT, name + ".npz")))
+        w = dict(np.load(os.path.join(OUT, name.replace("_gt", "") + ".npz")))
         b_omega = np.ones(len(w["b_z"])); o_omega = w["o_omega"]
         out["bound"] = np.float32(r.bound())
     else:
@@ -101,7 +104,8 @@ def run(name):
                       w["o_omega"], b_omega=w["b_omega"], fixed_id=int(w["fixed_pose_id"]))
         b_omega, o_omega = w["b_omega"], w["o_omega"]
         out.update({"problem_" + k: v for k, v in w.items()})
-    r.triangulate()
+    if not name.endswith("_gt"):
+        r.triangulate()
     pid, lid = r.ids()
     out["pose_ids"], out["lm_ids"] = pid, lid
     r.solver_init(-1)

@@ -24,18 +24,21 @@ from helpers import GOLDEN, angle_diff, csc_rel_err, golden_problem, load_golden
 from oracle import ref
 from oracle.oracle import Oracle
 
-CASES = ["mini", "full", "rand_a", "rand_b"]
+CASES = ["mini", "full", "rand_a", "rand_b", "mini_gt", "full_gt"]
 # bearing edges that sit on the +-pi branch cut at the triangulated start: the float reference and a double
 # evaluation of the same state may wrap them differently; `full` only, the single edges of landmarks 112 / 114 / 69
-WRAP_EDGES = {"mini": [], "full": [29, 1324, 1515], "rand_a": [], "rand_b": []}
+WRAP_EDGES = {"mini": [], "full": [29, 1324, 1515], "rand_a": [], "rand_b": [], "mini_gt": [], "full_gt": []}
 
 
 def load_case(name):
     r = dict(np.load(os.path.join(GOLDEN, "ref_%s.npz" % name)))
-    if name in ("mini", "full"):
-        w = load_golden(name)
+    if name in ("mini", "full", "mini_gt", "full_gt"):
+        w = load_golden(name.replace("_gt", ""))
         w["b_omega"] = None
         kt, damping = 1.0, 0.01
+        if name.endswith("_gt"):   # the ground-truth files: same edges, GT poses, landmarks given as VERTEX_XY lines (file order = stix order)
+            w["pose_ids"], w["poses_xyt"] = w["gt_pose_ids"], w["gt_poses_xyt"]
+            w["given_lm_ids"], w["given_lms_xy"] = w["gt_lm_ids"], w["gt_lms_xy"]
     else:
         w = {k[len("problem_"):]: v for k, v in r.items() if k.startswith("problem_")}
         kt, damping = float(w["kernel_threshold"]), float(w["damping"])
@@ -45,8 +48,9 @@ def load_case(name):
 def oracle_on(w, dtype, kt, damping, fixed):
     o = Oracle(dtype)
     o.set_problem(w["pose_ids"], w["poses_xyt"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"],
-                  w["o_omega"], b_omega=w.get("b_omega"), fixed_id=fixed)
-    o.triangulate()
+                  w["o_omega"], b_omega=w.get("b_omega"), fixed_id=fixed, lm_ids=w.get("given_lm_ids"), lms_xy=w.get("given_lms_xy"))
+    if "given_lm_ids" not in w:
+        o.triangulate()
     o.solver_init(fixed)
     o.set_params(kt, damping)
     return o
@@ -123,11 +127,11 @@ def test_oracle_float_reproduces_the_reference(name):
     s = o.stats()
     assert s["chi2_bearing"] == pytest.approx(r["chi2"][0, 0], rel=1e-6) and s["chi2_odometry"] == pytest.approx(r["chi2"][0, 1], rel=1e-5)
     # the Gauss-Newton trajectory from the reference's start, against the reference's states
-    tol = 2e-3 if name == "full" else 1e-5
+    tol = 2e-3 if name.startswith("full") else 1e-5
     it = 0
     for cp in r["checkpoints"]:
         while it < cp:
-            o.step(2 if name == "full" else 0)      # sparse LDL^T (the reference's kind of solver) on full, dense LDL^T elsewhere
+            o.step(2 if name.startswith("full") else 0)      # sparse LDL^T (the reference's kind of solver) on full, dense LDL^T elsewhere
             it += 1
         P, L = o.state()
         assert np.abs(P - r["P_it%d" % cp]).max() <= tol * max(1.0, np.abs(r["P_it%d" % cp]).max())
@@ -155,14 +159,16 @@ def test_oracle_double_matches_the_reference_within_float_rounding(name):
     c = o.counts()
     assert np.all(np.abs(b - r["b_nofixed"]) <= b_rounding_bound(r, w, o.edge_stix(), c["NP"], c["fixed_stix"]))
     s = o.stats()
-    assert s["chi2_bearing"] == pytest.approx(r["chi2"][0, 0], rel=1e-5) and s["chi2_odometry"] == pytest.approx(r["chi2"][0, 1], rel=1e-3)
+    # at the ground-truth state the bearing residuals are noise (3e-3 rad): their float rounding (1e-7) shows at 1e-4 relative in the sum of squares
+    chi_tol = 2e-4 if name.endswith("_gt") else 1e-5
+    assert s["chi2_bearing"] == pytest.approx(r["chi2"][0, 0], rel=chi_tol) and s["chi2_odometry"] == pytest.approx(r["chi2"][0, 1], rel=1e-3)
     iters = int(r["checkpoints"][-1])
     for _ in range(iters):
         o.step(0)
     P, L = o.state()
     rP, rL = r["P_it%d" % iters], r["L_it%d" % iters]
     keep = ~single_observation_landmarks(w, r["lm_ids"])
-    assert int((~keep).sum()) == (3 if name == "full" else 1 if name.startswith("rand") else 0)
+    assert int((~keep).sum()) == (3 if name.startswith("full") else 1 if name.startswith("rand") else 0)
     assert np.abs(P - rP).max() <= 1e-4 * max(1.0, np.abs(rP).max())
     assert np.abs(L - rL)[keep].max() <= 5e-3 * max(1.0, np.abs(rL).max())
     assert len(amb) == len(WRAP_EDGES[name])
@@ -275,7 +281,7 @@ def test_reference_error_behaviour():
 def _gpu_problem(w, r):
     from prb_project_bearing_only_slam_b200.problem import Problem
     return Problem(w["pose_ids"], w["b_pose_id"], w["b_lm_id"], w["b_z"], w["o_src_id"], w["o_dst_id"], w["o_z"], w["o_omega"],
-                   fixed_pose_id=int(r["fixed_pose_id"]), b_omega=w.get("b_omega"))
+                   fixed_pose_id=int(r["fixed_pose_id"]), b_omega=w.get("b_omega"), lm_ids=w.get("given_lm_ids"))
 
 
 @pytest.mark.gpu
@@ -294,11 +300,11 @@ def test_cuda_path_matches_the_reference(built_lib, name, precision):
     pr.upload(ctx)
     ctx.set_kernel_threshold(kt)
     ctx.set_damping_factor(damping)
-    # device triangulation against the reference's (same poses): observable landmarks
-    ctx.set_state(r["poses0_xycs"].astype(np.float64), None)
-    ctx.triangulate()
-    Ltri = ctx.get_state()[1]
-    assert np.abs(Ltri - r["lms_tri"]).max() <= (2e-4 if f32 else 1e-5) * np.abs(r["lms_tri"]).max()
+    if "given_lm_ids" not in w:   # device triangulation against the reference's (same poses): observable landmarks
+        ctx.set_state(r["poses0_xycs"].astype(np.float64), None)
+        ctx.triangulate()
+        Ltri = ctx.get_state()[1]
+        assert np.abs(Ltri - r["lms_tri"]).max() <= (2e-4 if f32 else 1e-5) * np.abs(r["lms_tri"]).max()
     ctx.set_state(r["poses0_xycs"].astype(np.float64), r["lms_tri"].astype(np.float64))
     ctx.linearize()
     eb, jb, eo, jo = ctx.edge_terms()
@@ -316,9 +322,9 @@ def test_cuda_path_matches_the_reference(built_lib, name, precision):
         bound = b_rounding_bound(r, w, (pr.b_pose, pr.b_lm, pr.o_src, pr.o_dst), pr.NP, pr.fixed_stix, d_err=4e-5 if f32 else 4e-6)
         assert np.all(np.abs(b - r["b_nofixed"]) <= bound)
     st = ctx.stats()
-    assert st.chi2_bearing == pytest.approx(r["chi2"][0, 0], rel=1e-3 if f32 else 1e-5)
+    assert st.chi2_bearing == pytest.approx(r["chi2"][0, 0], rel=1e-3 if f32 else (2e-4 if name.endswith("_gt") else 1e-5))
     assert st.chi2_odometry == pytest.approx(r["chi2"][0, 1], rel=5e-2 if f32 else 1e-3, abs=1e-9)
-    if f32 and name == "full":
+    if f32 and name.startswith("full"):
         return                 # FP32 trajectories on the ill-conditioned full start are documented, not claimed
     iters = int(r["checkpoints"][-1])
     for _ in range(iters):
