@@ -76,31 +76,82 @@ def load_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the headline workload is
+    ~85 ms long, shorter than one `nvidia-smi -lms` period, so the samples are taken through NVML (nvidia_ml_py: the library nvidia-smi
+    itself queries) from a thread every 5 ms, each stamped with perf_counter; summary(t0, t1) keeps the samples that fall inside the timed
+    region.  Falls back to an `nvidia-smi -lms 100` child process when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+            index = ids[index] if ids else index
+        except (ValueError, IndexError):
+            pass
         self.index = index
-        self.rows = []
+        self.rows = []          # (timestamp, sm_mhz, sm_max_mhz, reasons)
         self.proc = None
+        self.nvml = None
+        self.stop = threading.Event()
+        self.source = None
 
     def __enter__(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
         return self
 
+    def _poll(self):
+        n = self.nvml
+        bits = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)]
+        while not self.stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, self.max_sm, [nm for nm, b in bits if r & b]))
+            except Exception:
+                pass
+            self.stop.wait(0.005)
+
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]),
+                                  [nm for k, nm in enumerate(names) if r[4 + k].lower().startswith("active")]))
+            except Exception:
+                pass
 
     def __exit__(self, *a):
-        if self.proc:
+        if self.nvml:
+            self.stop.set()
+            self.t.join(timeout=1)
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
+        elif self.proc:
             time.sleep(0.15)
             self.proc.terminate()
             try:
@@ -108,20 +159,17 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[4 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+    def summary(self, t0=None, t1=None):
+        rows = self.rows
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        where = "inside the timed region"
+        if not inside:      # the child-process fallback may only deliver its first line after a short region has ended
+            inside, where = rows, "around the timed region"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        reasons = sorted({nm for r in inside for nm in r[3]})
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside), "reasons": reasons,
+                "samples": len(inside), "source": "%s, %s" % (self.source, where)}
 
 
 def make_world(name):
@@ -451,6 +499,7 @@ def run_ours(args):
         barrier()
         t1 = time.perf_counter()
     elapsed = t1 - t0
+    clk_region = (t0, t1)
     # ---- end-to-end arm: host state in, host state out, every step -------------------------------------------------
     Ph = torch.from_numpy(P0.copy()).pin_memory().numpy()
     Lh = torch.from_numpy(L0.copy()).pin_memory().numpy()
@@ -503,7 +552,7 @@ def run_ours(args):
     bytes_build = hb_build_bytes(pr.NP, pr.NL, eb_local, eo_local, int(pi.n_hpp_off), S)
     achieved = bytes_build / (ms_lin_kernel * 1e-3) / 1e9
     value = args.steps / elapsed
-    clocks = clk.summary()
+    clocks = clk.summary(*clk_region)
     traffic = load_traffic()
     pcg_iters = statistics.mean(s["pcg_iterations"] for s in stats)
     if solver is None:
@@ -632,8 +681,10 @@ def run_ours_batch(args, torch, dist, rank, world, local):
         torch.cuda.synchronize()
     barrier()
     with ClockSampler(local) as clk:
+        clk_t0 = time.perf_counter()
         ms = B.step_device(args.steps)          # CUDA events around the K launches on the batch's stream
         barrier()
+        clk_t1 = time.perf_counter()
     # end to end: states from pinned host memory, one launch, chi2 / status back, every step
     ph = torch.from_numpy(poses.copy()).pin_memory().numpy(); lh = torch.from_numpy(lms.copy()).pin_memory().numpy()
     t0 = time.perf_counter()
@@ -666,7 +717,7 @@ def run_ours_batch(args, torch, dist, rank, world, local):
                          "ms_per_launch": ms / args.steps},
             "e2e": {"value": world * nprob * args.steps / e2e, "unit": "problem-iterations/s",
                     "h2d_bytes_per_step": int(nprob * (4 * pr.NP + 2 * pr.NL) * 8), "d2h_bytes_per_step": int(nprob * (2 * 8 + 8 + 4))},
-            "gpu_launches": args.steps, "clocks": clk.summary(), "status_ok": bool(np.all(st == 0))}
+            "gpu_launches": args.steps, "clocks": clk.summary(clk_t0, clk_t1), "status_ok": bool(np.all(st == 0))}
     print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()

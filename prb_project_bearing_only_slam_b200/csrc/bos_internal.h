@@ -56,7 +56,7 @@ struct Dev {
     const int* oe_ptr = nullptr;     // [NP+1] odometry edges incident to a pose
     const int* oe_edge = nullptr;    // [2*Eo] (edge << 1) | role, role 0: the pose is the edge's source, 1: its destination
     const int* oe_other = nullptr;   // [2*Eo] the pose at the other end of that edge
-    const int* oe2 = nullptr;        // [NP][4] the first two entries of a pose's list inline: code0, other0, code1, other1 (-1: none)
+    const int* oe2 = nullptr;        // [NP + 8][2] the first two entries of a pose's list inline: code0, code1 (-1: none)
     const unsigned char* o_shared = nullptr;  // [Eo] 1 when the edge's pose pair is shared with another edge (needs RED + zero init)
     int has_shared_off = 0;
     int Eb_pad = 0;                  // bearing SoA arrays are padded to a multiple of 4 (omega = 0 in the padding)

@@ -228,12 +228,9 @@ int upload_impl(bos_ctx* c, const double* b_z, const double* b_omega, const doub
     UP(o_src, P.o_src) UP(o_dst, P.o_dst) UP(o_z, oz) UP(o_om, oom) UP(o_slot, P.o_slot)
     UP(oe_ptr, P.oe_ptr) UP(oe_edge, P.oe_edge) UP(oe_other, P.oe_other) UP(o_shared, P.o_shared)
     {
-        std::vector<int> oe2(4 * (size_t)P.NP, -1);
+        std::vector<int> oe2(2 * ((size_t)P.NP + 8), -1);   // padded: the bearing kernel fetches it in whole groups of four poses
         for (int i = 0; i < P.NP; i++)
-            for (int k = 0; k < 2 && P.oe_ptr[i] + k < P.oe_ptr[i + 1]; k++) {
-                oe2[4 * (size_t)i + 2 * k] = P.oe_edge[P.oe_ptr[i] + k];
-                oe2[4 * (size_t)i + 2 * k + 1] = P.oe_other[P.oe_ptr[i] + k];
-            }
+            for (int k = 0; k < 2 && P.oe_ptr[i] + k < P.oe_ptr[i + 1]; k++) oe2[2 * (size_t)i + k] = P.oe_edge[P.oe_ptr[i] + k];
         UP(oe2, oe2)
     }
     UP(slot_pose, P.slot_pose) UP(slot_lm, P.slot_lm) UP(pose_ptr, P.pose_ptr) UP(lm_ptr, P.lm_ptr)

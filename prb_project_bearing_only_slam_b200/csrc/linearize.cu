@@ -168,10 +168,7 @@ constexpr int kNT = 4;  // per-edge terms staged in shared memory: sqrt(omega) *
 // grid is exactly the number of resident CTAs (kLinPersistCtas per SM).
 constexpr int kLinStages = 2;
 constexpr int kLinPersistCtas = 4;
-#ifndef BOS_LIN_SUB
-#define BOS_LIN_SUB 1
-#endif
-constexpr int kLinSub = BOS_LIN_SUB;   // lanes that share one landmark group / pose run in phase 2
+constexpr int kOeMax = 96;             // poses per tile whose odometry edge codes are staged with the tile (longer pose ranges read them from global memory)
 template <typename S>
 struct LinStage {
     int pose[kLinTile];
@@ -183,6 +180,7 @@ struct LinStage {
     int pe[kLinTile + 8];                  // epose_ptr[p_lo ..]: bearing-edge ranges of the tile's poses
     unsigned short geptr[kLinTile + 8];    // tile-local range of every group in tge
     int hdr[4];                            // groups, first pose, last pose, p_lo
+    int oec[2 * kOeMax];                   // oe2[p_lo ..]: the first two odometry edge codes of the tile's poses
 };
 template <typename S>
 struct LinSmem {
@@ -228,7 +226,8 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
         int p_lo = m.z & ~3, pcnt = (m.w + 2 - p_lo + 3) & ~3;
         if (pcnt > kLinTile + 8) { p_lo = -1; pcnt = 0; }   // a long stretch of edge-free poses inside the tile: read epose_ptr directly
         g.hdr[0] = m.y; g.hdr[1] = m.z; g.hdr[2] = m.w; g.hdr[3] = p_lo;
-        mbar_expect_tx(&sm.bar[stg], kEdgeBytes + (unsigned)cnt * 6u + (unsigned)pcnt * 4u);
+        const bool oe = pcnt > 0 && pcnt <= kOeMax;
+        mbar_expect_tx(&sm.bar[stg], kEdgeBytes + (unsigned)cnt * 6u + (unsigned)pcnt * (oe ? 12u : 4u));
         tma_bulk_load(g.pose, d.b_pose + e, kLinTile * 4, &sm.bar[stg]);
         tma_bulk_load(g.lm, d.b_lm + e, kLinTile * 4, &sm.bar[stg]);
         tma_bulk_load(g.z, d.b_z + e, kLinTile * sizeof(S), &sm.bar[stg]);
@@ -237,6 +236,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
         tma_bulk_load(g.glm, d.tgp_lm + m.x, (unsigned)cnt * 4u, &sm.bar[stg]);
         tma_bulk_load(g.geptr, d.tgp_eptr + m.x, (unsigned)cnt * 2u, &sm.bar[stg]);
         if (pcnt > 0) tma_bulk_load(g.pe, d.epose_ptr + p_lo, (unsigned)pcnt * 4u, &sm.bar[stg]);
+        if (oe) tma_bulk_load(g.oec, d.oe2 + 2 * (size_t)p_lo, (unsigned)pcnt * 8u, &sm.bar[stg]);
     };
     if (tid == 0) {
         for (int s = 0; s < kLinStages; s++) mbar_init(&sm.bar[s], 1);
@@ -313,87 +313,87 @@ __global__ void __launch_bounds__(kLinThreads, kLinPersistCtas) k_linearize_bear
         // everything below reads or accumulates into what the preceding kernel wrote (landmark blocks and cut poses initialised, the odometry
         // scratch Mv): wait for it -- once per CTA, a no-op when the kernel was not launched with programmatic stream serialization
         if (k == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
-        // ---- phase 2: kLinSub lanes per landmark group, then per pose run; sums over the lanes by shuffles ----------------------
+        // ---- phase 2: ONE item list per tile -- the pose runs first (padded to whole warps, so that no warp mixes the two kinds of item),
+        // then the landmark groups.  The runs are the long items (ten edges, then the owner's odometry parts): they start at once in the
+        // first warps while the other warps sum the landmark groups beside them, instead of after them.
         const int ng = g.hdr[0], pfirst = g.hdr[1], plast = g.hdr[2], p_lo = g.hdr[3];
-        const int sub = tid % kLinSub, item = tid / kLinSub;
-        constexpr int kItems = kLinThreads / kLinSub;
-        for (int base = 0; base < ng; base += kItems) {            // uniform trip count: every lane takes part in the shuffles
-            const int gi = base + item;
-            S v0 = S(0), v1 = S(0), v2 = S(0), v3 = S(0), v4 = S(0);
-            if (gi < ng) {
+        constexpr int kRunSub = 2;   // lanes per pose run (they split the run's edges and the owner's odometry edges)
+        const int nruns = plast - pfirst + 1, rpad = (nruns * kRunSub + 31) & ~31, nitems = rpad + ng;
+        for (int it = tid; it < nitems; it += kLinThreads) {
+            if (it >= rpad) {
+                const int gi = it - rpad;
+                S v0 = S(0), v1 = S(0), v2 = S(0), v3 = S(0), v4 = S(0);
                 const int ga = g.geptr[gi], gb = g.geptr[gi + 1];
-                for (int q = ga + sub; q < gb; q += kLinSub) {
+                for (int q = ga; q < gb; q++) {
                     const int le = g.tge[q];
                     const S j0 = sm.st[0][le], j1 = sm.st[1][le], ee = sm.st[3][le];
                     v0 += j0 * j0; v1 += j0 * j1; v2 += j1 * j1; v3 += j0 * ee; v4 += j1 * ee;
                 }
-            }
-#pragma unroll
-            for (int o = 1; o < kLinSub; o <<= 1) {
-                v0 += __shfl_xor_sync(BOS_FULL_MASK, v0, o); v1 += __shfl_xor_sync(BOS_FULL_MASK, v1, o); v2 += __shfl_xor_sync(BOS_FULL_MASK, v2, o);
-                v3 += __shfl_xor_sync(BOS_FULL_MASK, v3, o); v4 += __shfl_xor_sync(BOS_FULL_MASK, v4, o);
-            }
-            if (gi < ng && sub == 0) {
                 const int gl = g.glm[gi];
                 S* hl = d.Hll + 3LL * gl;
                 out_red<kPeer>(d, hl + 0, v0); out_red<kPeer>(d, hl + 1, v1); out_red<kPeer>(d, hl + 2, v2);
                 S* bl = d.b + 3LL * d.NP + 2LL * gl;
                 out_red<kPeer>(d, bl + 0, v3); out_red<kPeer>(d, bl + 1, v4);
-            }
-        }
-        const int nruns = plast - pfirst + 1;
-        for (int base = 0; base < nruns; base += kItems) {
-            const int p = pfirst + base + item;
-            S v[9];
-#pragma unroll
-            for (int q = 0; q < 9; q++) v[q] = S(0);
-            int ra = 0, rb = 0;
-            bool live = false;
-            if (p <= plast) {
+            } else {
+                const int run = it / kRunSub, sub = it % kRunSub;
+                const bool have = run < nruns;
+                const int p = have ? pfirst + run : plast;
+                int ra, rb;
                 if (p_lo >= 0) { ra = g.pe[p - p_lo]; rb = g.pe[p + 1 - p_lo]; }
                 else { ra = __ldg(d.epose_ptr + p); rb = __ldg(d.epose_ptr + p + 1); }
+                // The tile in which a pose's run STARTS owns the pose (edge-free poses included: their empty run starts somewhere too):
+                // it adds the damping and the pose's odometry edges, so the block is final after ONE plain store.  Only a run cut by a
+                // tile boundary (one pose per boundary, zeroed by k_hb_init) arrives in parts, by REDs.
+                const bool owner = have && ((ra >= ta && ra < tb) || (tb == d.Eb && ra == d.Eb));
+                const bool cut = rb > ra && (ra / kLinTile != (rb - 1) / kLinTile);
+                const bool odo = owner && p != d.fixed;
+                // The owner's odometry parts (K2's scratch) are fetched BEFORE the run is summed, into registers of their own, so the
+                // latency of those loads hides behind the edge loop: lane `sub` takes the pose's sub-th odometry edge (its code comes
+                // with the tile's staged data when the tile's pose range is short enough), lane 1 also the loop closures.
+                S w[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) w[q] = S(0);
+                int code = -1, q0 = 0, q1 = 0;
+                const size_t Eo = (size_t)d.Eo;
+                if (odo) {
+                    const bool staged = p_lo >= 0 && ((plast + 2 - p_lo + 3) & ~3) <= kOeMax;
+                    code = staged ? g.oec[2 * (p - p_lo) + sub] : __ldg(d.oe2 + 2 * (size_t)p + sub);
+                    if (code >= 0) {       // (edge << 1) | role; J_dst = -J_src: M enters both diagonal blocks, v changes sign
+                        const int e = code >> 1;
+                        const S sg = (code & 1) ? S(-1) : S(1);
+#pragma unroll
+                        for (int q = 0; q < 6; q++) w[q] = __ldg(d.Mv + q * Eo + e);
+#pragma unroll
+                        for (int q = 0; q < 3; q++) w[6 + q] = sg * __ldg(d.Mv + (6 + q) * Eo + e);
+                        if (sub == 1) { q0 = __ldg(d.oe_ptr + p) + 2; q1 = __ldg(d.oe_ptr + p + 1); }
+                    }
+                }
+                S v[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) v[q] = S(0);
+                if (owner && sub == 0) { v[0] = damping; v[3] = damping; v[5] = damping; }
                 const int a = (ra > ta ? ra : ta) - ta, b = (rb < tb ? rb : tb) - ta;
-                live = (p != d.fixed) && a < b;
+                const bool live = have && (p != d.fixed) && a < b;
                 if (live)
-                    for (int q = a + sub; q < b; q += kLinSub) {   // J_pose = (-j0, -j1, jt)
+                    for (int q = a + sub; q < b; q += kRunSub) {   // J_pose = (-j0, -j1, jt)
                         const S j0 = sm.st[0][q], j1 = sm.st[1][q], jt = sm.st[2][q], ee = sm.st[3][q];
                         v[0] += j0 * j0; v[1] += j0 * j1; v[2] -= j0 * jt; v[3] += j1 * j1; v[4] -= j1 * jt; v[5] += jt * jt;
                         v[6] -= j0 * ee; v[7] -= j1 * ee; v[8] += jt * ee;
                     }
-            }
 #pragma unroll
-            for (int o = 1; o < kLinSub; o <<= 1) {
+                for (int q = 0; q < 9; q++) v[q] += w[q];
+                for (int q = q0; q < q1; q++) {                    // loop closures (lane 1 of an owner with two or more odometry edges)
+                    const int cc = __ldg(d.oe_edge + q), e = cc >> 1;
+                    const S sg = (cc & 1) ? S(-1) : S(1);
 #pragma unroll
-                for (int q = 0; q < 9; q++) v[q] += __shfl_xor_sync(BOS_FULL_MASK, v[q], o);
-            }
-            if (p <= plast && sub == 0) {
-                // The tile in which a pose's run STARTS owns the pose (edge-free poses included: their empty run starts somewhere too):
-                // it adds the damping and the pose's odometry edges, so the block is final after ONE plain store.  Only a run cut by a
-                // tile boundary (one pose per boundary, zeroed by k_hb_init) arrives in parts, by REDs.
-                const bool owner = (ra >= ta && ra < tb) || (tb == d.Eb && ra == d.Eb);
-                const bool cut = rb > ra && (ra / kLinTile != (rb - 1) / kLinTile);
-                if (owner) {
-                    v[0] += damping; v[3] += damping; v[5] += damping;
-                    if (p != d.fixed) {
-                        const size_t Eo = (size_t)d.Eo;
-                        auto add_edge = [&](int code) {      // (edge << 1) | role; J_dst = -J_src: M enters both diagonal blocks, v changes sign
-                            const int e = code >> 1;
-                            const S sg = (code & 1) ? S(-1) : S(1);
+                    for (int k = 0; k < 6; k++) v[k] += __ldg(d.Mv + k * Eo + e);
 #pragma unroll
-                            for (int q = 0; q < 6; q++) v[q] += __ldg(d.Mv + q * Eo + e);
-#pragma unroll
-                            for (int q = 0; q < 3; q++) v[6 + q] += sg * __ldg(d.Mv + (6 + q) * Eo + e);
-                        };
-                        const int4 m2 = __ldg(reinterpret_cast<const int4*>(d.oe2) + p);
-                        if (m2.x >= 0) add_edge(m2.x);
-                        if (m2.z >= 0) {
-                            add_edge(m2.z);
-                            const int q0 = __ldg(d.oe_ptr + p), q1 = __ldg(d.oe_ptr + p + 1);
-                            for (int q = q0 + 2; q < q1; q++) add_edge(__ldg(d.oe_edge + q));   // loop closures
-                        }
-                    }
+                    for (int k = 0; k < 3; k++) v[6 + k] += sg * __ldg(d.Mv + (6 + k) * Eo + e);
                 }
-                if (owner || live) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) v[q] += __shfl_xor_sync(BOS_FULL_MASK, v[q], 1);   // the branch is warp-uniform (rpad is a multiple of 32): all 32 lanes are here
+                const bool any_live = have && (p != d.fixed) && a < b;   // the run has edges in this tile (whichever lane summed them)
+                if (sub == 0 && (owner || any_live)) {
                     S* hp = d.Hpp + 6LL * p;
                     S* bp = d.b + 3LL * p;
                     if (cut) {
