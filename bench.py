@@ -76,12 +76,14 @@ def load_traffic():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The timed region of the headline workload is
-    ~85 ms long, shorter than one `nvidia-smi -lms` period, so the samples are taken through NVML (nvidia_ml_py: the library nvidia-smi
-    itself queries) from a thread every 5 ms, each stamped with perf_counter; summary(t0, t1) keeps the samples that fall inside the timed
-    region.  Falls back to an `nvidia-smi -lms 100` child process when NVML cannot be loaded."""
+    """SM clock and throttle reasons under the timed load (B200_PROFILING.md recipe): an `nvidia-smi -lms 100` child process, started before
+    the timed region, every line stamped on arrival.  The timed region of the headline workload is ~85 ms long, about one sampling period, so
+    the caller keeps the SAME load running (untimed steps of the same workload, `keep_load`) after its timing is closed until three samples
+    have arrived; summary(t0, t1) says how many of them fell inside the timed region itself.  (Polling NVML from a thread of this process
+    was tried: its queries contend with the kernel launches and slowed the timed steps by 2 %.)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
@@ -91,68 +93,45 @@ class ClockSampler:
         except (ValueError, IndexError):
             pass
         self.index = index
-        self.rows = []          # (timestamp, sm_mhz, sm_max_mhz, reasons)
+        self.rows = []          # (arrival time, sm_mhz, sm_max_mhz, reasons)
         self.proc = None
-        self.nvml = None
-        self.stop = threading.Event()
-        self.source = None
 
     def __enter__(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.nvml = pynvml
-            self.source = "nvml"
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return self
-        except Exception:
-            self.nvml = None
-        try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
         return self
 
-    def _poll(self):
-        n = self.nvml
-        bits = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
-                ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)]
-        while not self.stop.is_set():
-            try:
-                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
-                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.rows.append((time.perf_counter(), sm, self.max_sm, [nm for nm, b in bits if r & b]))
-            except Exception:
-                pass
-            self.stop.wait(0.005)
-
     def _read(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
             r = [x.strip() for x in line.split(",")]
             try:
                 self.rows.append((time.perf_counter(), float(r[1]), float(r[2]),
-                                  [nm for k, nm in enumerate(names) if r[4 + k].lower().startswith("active")]))
+                                  [nm for k, nm in enumerate(self.NAMES) if r[4 + k].lower().startswith("active")]))
             except Exception:
                 pass
 
+    def keep_load(self, one_more_step, want=3, limit_s=2.0, fixed=None):
+        """Untimed steps of the same workload until `want` samples have arrived (or the child process is gone / limit_s has passed).
+        `fixed`: exactly that many steps instead (several ranks: the steps hold collectives, every rank must take the same number)."""
+        t = time.perf_counter()
+        extra = 0
+        if fixed is not None:
+            for _ in range(fixed):
+                one_more_step()
+            extra = fixed
+        else:
+            while self.proc and self.proc.poll() is None and len(self.rows) < want and time.perf_counter() - t < limit_s:
+                one_more_step()
+                extra += 1
+        self.extra_steps = extra
+
     def __exit__(self, *a):
-        if self.nvml:
-            self.stop.set()
-            self.t.join(timeout=1)
-            try:
-                self.nvml.nvmlShutdown()
-            except Exception:
-                pass
-        elif self.proc:
-            time.sleep(0.15)
+        if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -160,16 +139,14 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self, t0=None, t1=None):
-        rows = self.rows
-        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
-        where = "inside the timed region"
-        if not inside:      # the child-process fallback may only deliver its first line after a short region has ended
-            inside, where = rows, "around the timed region"
-        if not inside:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
-        reasons = sorted({nm for r in inside for nm in r[3]})
-        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside), "reasons": reasons,
-                "samples": len(inside), "source": "%s, %s" % (self.source, where)}
+        rows = list(self.rows)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        inside = sum(1 for r in rows if t0 is not None and t0 <= r[0] <= t1)
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
+                "reasons": sorted({nm for r in rows for nm in r[3]}), "samples": len(rows), "samples_inside_timed_region": inside,
+                "sampling": "nvidia-smi -lms 100 from before the timed region; the same load kept running (%d untimed steps) until %d samples"
+                            % (getattr(self, "extra_steps", 0), len(rows))}
 
 
 def make_world(name):
@@ -498,6 +475,12 @@ def run_ours(args):
             stats.append(ctx.step().as_dict())
         barrier()
         t1 = time.perf_counter()
+        if world == 1:
+            clk.keep_load(ctx.step)
+        else:      # ~0.35 s of the same load, the same number of steps on every rank (rank 0 decides)
+            nx = torch.tensor([min(400, int(0.35 / max((t1 - t0) / args.steps, 1e-4)) + 1)], device="cuda")
+            dist.broadcast(nx, 0)
+            clk.keep_load(ctx.step, fixed=int(nx.item()))
     elapsed = t1 - t0
     clk_region = (t0, t1)
     # ---- end-to-end arm: host state in, host state out, every step -------------------------------------------------
@@ -685,6 +668,7 @@ def run_ours_batch(args, torch, dist, rank, world, local):
         ms = B.step_device(args.steps)          # CUDA events around the K launches on the batch's stream
         barrier()
         clk_t1 = time.perf_counter()
+        clk.keep_load(lambda: B.step_device(1))
     # end to end: states from pinned host memory, one launch, chi2 / status back, every step
     ph = torch.from_numpy(poses.copy()).pin_memory().numpy(); lh = torch.from_numpy(lms.copy()).pin_memory().numpy()
     t0 = time.perf_counter()

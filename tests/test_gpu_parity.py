@@ -663,6 +663,32 @@ def test_run_to_run_variation_is_bounded(built_lib):
     assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-6) and outs[0][1] == pytest.approx(outs[1][1], rel=1e-7)
 
 
+def test_step_equals_linearize_solve_update(built_lib):
+    """bos_step against the separate entry points (bos_linearize, bos_solve, bos_update, bos_get_stats) on the fused PCG path: same
+    statistics, same preconditioner bookkeeping and the same state after three iterations."""
+    w, pr = synth_problem(3000, 700, 30000, seed=5)
+    o = oracle_for(w["pose_ids"], w["poses_init"], pr)
+    P, L = o.state()
+    res = []
+    for whole in (True, False):
+        ctx = make_ctx(pr, P, L, solver=capi.SOLVER_PCG, pcg_rtol=1e-12, pcg_max_iters=5000)
+        stats = []
+        for _ in range(3):
+            if whole:
+                stats.append(ctx.step())
+            else:
+                ctx.linearize(); ctx.solve(); ctx.update()
+                stats.append(ctx.stats())
+        res.append((stats, ctx.get_state()))
+        ctx.close()
+    for a, b in zip(res[0][0], res[1][0]):
+        assert a.solver_status == b.solver_status == 0 and a.pcg_resolves == b.pcg_resolves == 0 and a.precond_used == b.precond_used
+        # the lagged coarse operator is rebuilt on a schedule that weighs MEASURED times: the two runs may rebuild at different steps
+        assert abs(a.pcg_iterations - b.pcg_iterations) <= 0.25 * b.pcg_iterations + 4
+        assert a.chi2_bearing == pytest.approx(b.chi2_bearing, rel=1e-6) and a.delta_inf == pytest.approx(b.delta_inf, rel=1e-5)
+    assert np.abs(res[0][1][0] - res[1][1][0]).max() <= 1e-8 and np.abs(res[0][1][1] - res[1][1][1]).max() <= 1e-8
+
+
 @pytest.mark.parametrize("solver", [capi.SOLVER_DENSE_CHOLESKY, capi.SOLVER_PCG])
 def test_irls_extension_matches_its_oracle_restatement(built_lib, solver):
     """Opt-in IRLS flavour of the threshold kernel (bos_set_robust_mode) against the oracle's restatement from the triangulated
