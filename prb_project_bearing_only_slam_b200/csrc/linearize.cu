@@ -84,9 +84,13 @@ template <typename S>
 __global__ void __launch_bounds__(256) k_hb_init(Dev<S> d, S damping) { hb_init_item<S>(d, damping, blockIdx.x * blockDim.x + threadIdx.x); }
 
 // ---- K2 -------------------------------------------------------------------------------------------------------------
+#ifndef BOS_ODO_THREADS
+#define BOS_ODO_THREADS 128
+#endif
+constexpr int kOdoThreads = BOS_ODO_THREADS;
 template <typename S>
-__global__ void __launch_bounds__(128) k_linearize_odometry(Dev<S> d, int o_begin, int o_end, int s_begin, int s_end, S kernel_threshold, S damping_init, int all_hoff) {
-    __shared__ double red[2][4];
+__global__ void __launch_bounds__(kOdoThreads) k_linearize_odometry(Dev<S> d, int o_begin, int o_end, int s_begin, int s_end, S kernel_threshold, S damping_init, int all_hoff) {
+    __shared__ double red[2][kOdoThreads / 32];
     // programmatic dependent launch: the bearing kernel that follows may start its CTAs (edge prefetch, phase 1 of its first tiles: nothing
     // of that reads what this kernel writes) while this grid is still running; it waits (griddepcontrol.wait) before its first phase 2
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(128) k_linearize_odometry(Dev<S> d, int o_begi
     __syncthreads();
     if (threadIdx.x == 0) {
         double cs = 0, os = 0;
-        for (int w = 0; w < 4; w++) { cs += red[0][w]; os += red[1][w]; }
+        for (int w = 0; w < kOdoThreads / 32; w++) { cs += red[0][w]; os += red[1][w]; }
         if (cs != 0.0) atomicAdd(d.stats_k2 + 1, cs);   // d.stats, or the scratch the peer barrier publishes to every replica (reduce_mode 4)
         if (os != 0.0) atomicAdd(d.stats_k2 + 3, os);
     }
@@ -584,7 +588,7 @@ int launch_linearize(const Dev<S>& d, const ShardRange& r, double kernel_thresho
     // every rank linearizes ALL odometry edges (0.2 M at synth-2M: the pose owner needs both of a pose's edges); statistics count the rank's share.
     // The same launch initialises the landmark blocks and the cut poses (K3).
     if (d.Eo > 0) {
-        k_linearize_odometry<S><<<(d.Eo + d.NL + d.n_cut + 127) / 128, 128, 0, st>>>(d, 0, d.Eo, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here, all_hoff ? 1 : 0);
+        k_linearize_odometry<S><<<(d.Eo + d.NL + d.n_cut + kOdoThreads - 1) / kOdoThreads, kOdoThreads, 0, st>>>(d, 0, d.Eo, r.o_begin, r.o_end, (S)kernel_threshold, (S)damping_here, all_hoff ? 1 : 0);
         launches++;
     } else if (d.NL + d.n_cut > 0) { k_hb_init<S><<<(d.NL + d.n_cut + 255) / 256, 256, 0, st>>>(d, (S)damping_here); launches++; }
     }

@@ -69,7 +69,7 @@ if os.path.exists(b):
     if pcg and line.get("pcg_iterations"):
         # the captured launch ran the same solve as the bench step: divide by its CG iterations
         traffic["pcg_dram_bytes_per_cg_iteration"] = (pcg[0]["dram_read"] + pcg[0]["dram_write"]) / line["pcg_iterations"]
-    hb = [v for k, v in ks.items() if "k_linearize_bearing" in k or "k_pose_finish" in k]
+    hb = [v for k, v in ks.items() if "k_linearize_bearing" in k or "k_linearize_odometry" in k]   # both kernels of the H, b build
     if hb:
         traffic["hb_build_dram_bytes"] = sum(v["dram_read"] + v["dram_write"] for v in hb)
 for extra in ("bench_f32_%s.json", "bench_bj_%s.json", "bench_100k_%s.json", "batch_%s.log", "dense_%s.log", "bench_n2_%s.json", "bench_n4_%s.json", "bench_n8_%s.json"):
