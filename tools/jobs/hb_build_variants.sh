@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU box: H, b build variants (tools/_variants/libbos_b200_<V>.so, built with -DBOS_LIN_MERGED=...) timed beside the default library,
+# GPU box: H, b build variants (tools/_variants/libbos_b200_<V>.so, built with -D... by build.build(extra_flags=, out=, objdir=)) timed beside the default library,
 # then the H, b parity tests on every variant
 set -u
 O=gpurun_out
