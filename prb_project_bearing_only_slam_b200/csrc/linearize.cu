@@ -171,7 +171,7 @@ constexpr int kNT = 4;  // per-edge terms staged in shared memory: sqrt(omega) *
 // 2-stage shared-memory ring, fetched one tile ahead: the HBM latency of the edge stream is off the critical path, the
 // grid is exactly the number of resident CTAs (kLinPersistCtas per SM).
 constexpr int kLinStages = 2;
-constexpr int kLinPersistCtas = 4;
+constexpr int kLinPersistCtas = BOS_LIN_MINBLOCKS;   // 4: 64 registers per thread, the whole register file and 220 KB of shared memory per SM
 constexpr int kOeMax = 96;             // poses per tile whose odometry edge codes are staged with the tile (longer pose ranges read them from global memory)
 template <typename S>
 struct LinStage {
